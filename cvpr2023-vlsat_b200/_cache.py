@@ -1,0 +1,37 @@
+"""Derived-weight cache: packed / concatenated / folded copies of parameters that the kernels consume.
+
+A derived tensor is rebuilt whenever one of its source parameters changes storage (``.to(device)``) or
+is written in place (``load_state_dict``, ``optimizer.step`` bump ``Tensor._version``).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Sequence, Tuple
+
+import torch
+
+
+class DerivedCache:
+    def __init__(self) -> None:
+        self._store: Dict[str, Tuple[tuple, object]] = {}
+
+    def get(self, key: str, sources: Sequence[torch.Tensor], build: Callable[[], object]):
+        sig = tuple((t.data_ptr(), t._version, t.device) for t in sources)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        with torch.no_grad():
+            val = build()
+        self._store[key] = (sig, val)
+        return val
+
+    def clear(self) -> None:
+        self._store.clear()
+
+
+def require_inference(module: torch.nn.Module, what: str) -> None:
+    """The CUDA path implements the eval-mode forward. Training-mode dropout (six sites on the path) and
+    the backward kernels are not built yet: refuse loudly instead of silently differing."""
+    if module.training:
+        raise NotImplementedError(
+            f"{what}: training mode (dropout masks, BatchNorm batch statistics, backward) is not implemented in "
+            "vlsat_b200 yet; call .eval(). There is no PyTorch fallback by design.")

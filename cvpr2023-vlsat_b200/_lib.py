@@ -1,0 +1,69 @@
+"""ctypes binding of libvlsat_b200.so (the C ABI declared in include/vlsat_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing, or a call returns a non-zero status,
+a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvlsat_b200.so")
+
+i64, i32, f32, vp, sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t
+
+
+class Epilogue(C.Structure):
+    """Mirror of ``vlsat_epilogue`` (include/vlsat_b200.h)."""
+    _fields_ = [("bias", vp), ("gather_a", vp), ("idx_a", vp), ("gather_b", vp), ("idx_b", vp),
+                ("ld_gather", i64), ("residual", vp), ("ld_res", i64), ("alpha", f32), ("beta", f32),
+                ("scale_ptr", vp), ("act", i32)]
+
+
+# name -> argtypes ; every function returns int status unless listed in _RESTYPES
+SIGNATURES = {
+    "vlsat_version": [],
+    "vlsat_error_string": [i32],
+    "vlsat_gemm_engine": [],
+    "vlsat_launch_count": [],
+    "vlsat_pointnet_fwd": [vp, i64, i32, i64, vp, vp, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp],
+    "vlsat_edge_descriptor_fwd": [vp, i64, vp, i64, vp, vp],
+    "vlsat_linear_fwd": [vp, i64, vp, i64, vp, i64, i64, i64, i64, C.POINTER(Epilogue), vp],
+    "vlsat_add_layernorm_fwd": [vp, i64, vp, i64, vp, vp, vp, i64, i64, i32, f32, i32, vp],
+    "vlsat_relu_fwd": [vp, vp, i64, vp],
+    "vlsat_row_l2norm_fwd": [vp, vp, i64, i32, vp],
+    "vlsat_spatial_tail_fwd": [vp, vp, i64, i32, i64, vp],
+    "vlsat_scene_ranges": [vp, i64, vp, vp, vp, vp],
+    "vlsat_node_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, vp, i64, i64, vp],
+    "vlsat_flash_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp],
+    "vlsat_build_csr": [vp, i64, i64, vp, vp, vp, sz, vp],
+    "vlsat_gat_edge_fwd": [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64,
+                           i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, vp, vp],
+}
+_RESTYPES = {"vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). vlsat_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.argtypes = args
+        fn.restype = _RESTYPES.get(name, i32)
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().vlsat_error_string(status).decode()
+        raise RuntimeError(f"{what}: vlsat status {status} ({msg})")

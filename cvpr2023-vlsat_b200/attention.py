@@ -1,0 +1,128 @@
+"""Host-side mirror of ``src/model/transformer/attention.py`` (MultiHeadAttention /
+ScaledDotProductAttention): same constructor arguments, same parameter names (``attention.fc_q`` ...
+``layer_norm``), same initialisation; the forward runs on the vlsat_b200 CUDA kernels.
+
+The reference evaluates dense [1,H,n,n] score tensors with a block-diagonal mask and an additive bias
+(attention.py:60-75). Here the two uses on the hot path get their own entry points:
+  * ``attend_scenes`` - attention between the nodes of each scene with the distance bias computed
+    inside the kernel (network_MMG.py:217-218);
+  * ``attend_all``    - unmasked attention over all keys with a streaming softmax (network_MMG.py:231).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._cache import DerivedCache, require_inference
+
+
+class SceneContext:
+    """Per-batch bookkeeping for node attention: scene range of every node + packed bias MLP."""
+
+    def __init__(self, batch_ids: torch.Tensor, centres: torch.Tensor, fc_pack: torch.Tensor, num_heads: int):
+        self.seg_start, self.seg_end, self.err_flag = ops.scene_ranges(batch_ids)
+        self.centres = centres.detach().contiguous()
+        self.fc_pack = fc_pack
+        self.num_heads = num_heads
+
+
+class ScaledDotProductAttention(nn.Module):
+    """Parameter container with the reference's names/init (attention.py:11-39)."""
+
+    def __init__(self, d_model, d_k, d_v, h):
+        super().__init__()
+        self.fc_q = nn.Linear(d_model, h * d_k)
+        self.fc_k = nn.Linear(d_model, h * d_k)
+        self.fc_v = nn.Linear(d_model, h * d_v)
+        self.fc_o = nn.Linear(h * d_v, d_model)
+        self.d_model, self.d_k, self.d_v, self.h = d_model, d_k, d_v, h
+        self.init_weights()
+
+    def init_weights(self):
+        for fc in (self.fc_q, self.fc_k, self.fc_v, self.fc_o):
+            nn.init.xavier_uniform_(fc.weight)
+            nn.init.constant_(fc.bias, 0)
+
+
+class MultiHeadAttention(nn.Module):
+    def __init__(self, d_model, d_k, d_v, h, dropout=.1, identity_map_reordering=False, can_be_stateful=False,
+                 attention_module=None, attention_module_kwargs=None):
+        super().__init__()
+        if identity_map_reordering or can_be_stateful or attention_module is not None:
+            raise NotImplementedError("only the plain post-LN MultiHeadAttention used on the VL-SAT hot path is built")
+        if d_k != d_v or h * d_k != d_model:
+            raise NotImplementedError("vlsat_b200 attention kernels need d_k == d_v == d_model / h")
+        self.identity_map_reordering = False
+        self.attention = ScaledDotProductAttention(d_model=d_model, d_k=d_k, d_v=d_v, h=h)
+        self.dropout = nn.Dropout(p=dropout)
+        self.layer_norm = nn.LayerNorm(d_model)
+        self.can_be_stateful = False
+        self._cache = DerivedCache()
+
+    # ---- derived weights -------------------------------------------------------------------------
+    def _w(self, which: str):
+        a = self.attention
+        if which == "qkv":
+            srcs = (a.fc_q.weight, a.fc_k.weight, a.fc_v.weight, a.fc_q.bias, a.fc_k.bias, a.fc_v.bias)
+            return self._cache.get("qkv", srcs, lambda: (torch.cat([a.fc_q.weight, a.fc_k.weight, a.fc_v.weight], 0).contiguous(),
+                                                          torch.cat([a.fc_q.bias, a.fc_k.bias, a.fc_v.bias], 0).contiguous()))
+        if which == "kv":
+            srcs = (a.fc_k.weight, a.fc_v.weight, a.fc_k.bias, a.fc_v.bias)
+            return self._cache.get("kv", srcs, lambda: (torch.cat([a.fc_k.weight, a.fc_v.weight], 0).contiguous(),
+                                                         torch.cat([a.fc_k.bias, a.fc_v.bias], 0).contiguous()))
+        raise KeyError(which)
+
+    def _project(self, q_in: torch.Tensor, kv_in: torch.Tensor, same: bool):
+        a = self.attention
+        d = a.h * a.d_k
+        if same:
+            w, b = self._w("qkv")
+            qkv = ops.linear(q_in, w, b)
+            return qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+        q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach())
+        w, b = self._w("kv")
+        kv = ops.linear(kv_in, w, b)
+        return q, kv[:, :d], kv[:, d:]
+
+    def _finish(self, q_in: torch.Tensor, att: torch.Tensor, relu: bool, out: Optional[torch.Tensor]):
+        a = self.attention
+        # fc_o with the residual folded into the GEMM epilogue, then LayerNorm (attention.py:76,122)
+        pre = ops.linear(att, a.fc_o.weight.detach(), a.fc_o.bias.detach(), residual=q_in, alpha=1.0, beta=1.0)
+        return ops.add_layernorm(pre, None, self.layer_norm.weight.detach(), self.layer_norm.bias.detach(),
+                                 eps=self.layer_norm.eps, relu=relu, out=out)
+
+    # ---- hot-path entry points -------------------------------------------------------------------
+    def attend_scenes(self, q_in, kv_in, ctx: SceneContext, relu: bool = False, out=None) -> torch.Tensor:
+        """LN(q_in + fc_o(softmax_scene(QK^T/sqrt(dk) + bias) V)); q_in, kv_in are [N, d_model]."""
+        require_inference(self, "MultiHeadAttention")
+        if ctx.num_heads != self.attention.h:
+            raise ValueError(f"distance bias has {ctx.num_heads} heads but attention has {self.attention.h} "
+                             "(network_GNN.py:211 hard-codes 8 heads for this reason)")
+        q, k, v = self._project(q_in, kv_in, q_in is kv_in)
+        att = ops.node_attn(q, k, v, ctx.centres, ctx.seg_start, ctx.seg_end, ctx.fc_pack, self.attention.h)
+        return self._finish(q_in, att, relu, out)
+
+    def attend_all(self, q_in, kv_in, relu: bool = False, out=None) -> torch.Tensor:
+        """LN(q_in + fc_o(softmax(QK^T/sqrt(dk)) V)) over all keys, no mask/bias; 2-D inputs."""
+        require_inference(self, "MultiHeadAttention")
+        q, k, v = self._project(q_in, kv_in, q_in is kv_in)
+        att = ops.flash_attn(q, k, v, self.attention.h)
+        return self._finish(q_in, att, relu, out)
+
+    # ---- reference signature -----------------------------------------------------------------------
+    def forward(self, queries, keys, values, attention_mask=None, attention_weights=None, way='mul', use_knn=False,
+                output_attn=False):
+        """Same signature as attention.py:105. Unmasked calls ([b_s, n, d] inputs) run the streaming
+        kernel. Dense ``attention_mask`` / ``attention_weights`` tensors are never built in this
+        implementation (``MMG.forward`` calls ``attend_scenes``), so passing them is an error."""
+        if attention_mask is not None or attention_weights is not None or use_knn or output_attn:
+            raise NotImplementedError(
+                "dense attention_mask/attention_weights/att maps are not materialised by vlsat_b200; "
+                "scene-restricted attention goes through MMG.forward / MultiHeadAttention.attend_scenes")
+        if queries.dim() != 3 or keys is not values and keys.data_ptr() != values.data_ptr():
+            raise NotImplementedError("expected [b_s, n, d] inputs with keys is values (the only use on the path)")
+        outs = [self.attend_all(queries[b], keys[b]) for b in range(queries.shape[0])]
+        return torch.stack(outs, 0)

@@ -1,0 +1,178 @@
+// FP32 FFMA GEMM with the fused epilogue of vlsat_linear_fwd.
+//   y[m,n] = post(act(sum_k x[m,k] w[n,k] + bias[n] + ga[ia[m],n] + gb[ib[m],n]))
+// Both operands are K-major (nn.Linear layout), so one kernel covers every projection on the path.
+// This is the exact-fp32 engine: it serves the shapes the tensor-core engine does not take (tiny K/N,
+// unaligned rows) and is the numerical cross-check for it (tests/test_linear.py).
+#include "common.cuh"
+
+namespace vlsat {
+
+struct LinearArgs {
+    const float* x; int64_t ldx;
+    const float* w; int64_t ldw;
+    float* y; int64_t ldy;
+    int64_t M, N, K;
+    vlsat_epilogue epi;
+};
+
+__device__ __forceinline__ float apply_act(float t, int act) {
+    if (act == VLSAT_ACT_RELU) return fmaxf(t, 0.f);
+    if (act == VLSAT_ACT_SIGMOID) return 1.f / (1.f + expf(-t));
+    return t;
+}
+
+// Shared epilogue for one output element group; used by both GEMM engines.
+__device__ __forceinline__ float epilogue_one(const vlsat_epilogue& e, float acc, int64_t m, int64_t n,
+                                              int64_t ia, int64_t ib, float post_scale) {
+    float t = acc;
+    if (e.bias) t += __ldg(e.bias + n);
+    if (e.gather_a) t += __ldg(e.gather_a + ia * e.ld_gather + n);
+    if (e.gather_b) t += __ldg(e.gather_b + ib * e.ld_gather + n);
+    t = apply_act(t, e.act);
+    if (e.residual) t = e.alpha * t + e.beta * __ldg(e.residual + m * e.ld_res + n);
+    else if (e.alpha != 1.f) t *= e.alpha;
+    return t * post_scale;
+}
+
+// BMxBN tile, BK=16, (BM/T)x(BN/T) threads each owning a TxT register tile. For T=8 the tile is split
+// into two 4-wide halves BM/2 (BN/2) apart so every shared-memory read is a conflict-free LDS.128.
+template <int BM, int BN, int T, bool VEC>
+__global__ void __launch_bounds__((BM / T) * (BN / T))
+linear_simt_kernel(const LinearArgs a) {
+    constexpr int BK = 16;
+    constexpr int NT = (BM / T) * (BN / T);
+    constexpr int H = T / 4;                       // number of 4-wide halves per dimension
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / T), ty = tid / (BN / T);
+    const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+
+    constexpr int A_LD = BM * BK / 4 / NT;         // float4 loads per thread per tile
+    constexpr int B_LD = BN * BK / 4 / NT;
+    static_assert(A_LD >= 1 && B_LD >= 1, "tile too small for the thread count");
+    float4 ra[A_LD], rb[B_LD];
+
+    auto load_tile = [&](int64_t k0) {
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            int idx = tid + i * NT, row = idx / (BK / 4), kq = idx % (BK / 4);
+            int64_t m = m0 + row, k = k0 + kq * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < a.M) {
+                const float* p = a.x + m * a.ldx + k;
+                if (VEC) { if (k < a.K) v = __ldg(reinterpret_cast<const float4*>(p)); }
+                else {
+                    if (k + 0 < a.K) v.x = __ldg(p + 0);
+                    if (k + 1 < a.K) v.y = __ldg(p + 1);
+                    if (k + 2 < a.K) v.z = __ldg(p + 2);
+                    if (k + 3 < a.K) v.w = __ldg(p + 3);
+                }
+            }
+            ra[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < B_LD; ++i) {
+            int idx = tid + i * NT, row = idx / (BK / 4), kq = idx % (BK / 4);
+            int64_t n = n0 + row, k = k0 + kq * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < a.N) {
+                const float* p = a.w + n * a.ldw + k;
+                if (VEC) { if (k < a.K) v = __ldg(reinterpret_cast<const float4*>(p)); }
+                else {
+                    if (k + 0 < a.K) v.x = __ldg(p + 0);
+                    if (k + 1 < a.K) v.y = __ldg(p + 1);
+                    if (k + 2 < a.K) v.z = __ldg(p + 2);
+                    if (k + 3 < a.K) v.w = __ldg(p + 3);
+                }
+            }
+            rb[i] = v;
+        }
+    };
+    auto store_tile = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            int idx = tid + i * NT, row = idx / (BK / 4), kq = idx % (BK / 4);
+            As[buf][kq * 4 + 0][row] = ra[i].x; As[buf][kq * 4 + 1][row] = ra[i].y;
+            As[buf][kq * 4 + 2][row] = ra[i].z; As[buf][kq * 4 + 3][row] = ra[i].w;
+        }
+#pragma unroll
+        for (int i = 0; i < B_LD; ++i) {
+            int idx = tid + i * NT, row = idx / (BK / 4), kq = idx % (BK / 4);
+            Bs[buf][kq * 4 + 0][row] = rb[i].x; Bs[buf][kq * 4 + 1][row] = rb[i].y;
+            Bs[buf][kq * 4 + 2][row] = rb[i].z; Bs[buf][kq * 4 + 3][row] = rb[i].w;
+        }
+    };
+
+    float acc[T][T];
+#pragma unroll
+    for (int i = 0; i < T; ++i)
+#pragma unroll
+        for (int j = 0; j < T; ++j) acc[i][j] = 0.f;
+
+    const int64_t n_tiles = ceil_div(a.K, BK);
+    load_tile(0);
+    store_tile(0);
+    __syncthreads();
+    for (int64_t t = 0; t < n_tiles; ++t) {
+        const int buf = (int)(t & 1);
+        if (t + 1 < n_tiles) load_tile((t + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float av[T], bv[T];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                float4 v = *reinterpret_cast<const float4*>(&As[buf][k][h * (BM / H) + ty * 4]);
+                av[h * 4 + 0] = v.x; av[h * 4 + 1] = v.y; av[h * 4 + 2] = v.z; av[h * 4 + 3] = v.w;
+                float4 u = *reinterpret_cast<const float4*>(&Bs[buf][k][h * (BN / H) + tx * 4]);
+                bv[h * 4 + 0] = u.x; bv[h * 4 + 1] = u.y; bv[h * 4 + 2] = u.z; bv[h * 4 + 3] = u.w;
+            }
+#pragma unroll
+            for (int i = 0; i < T; ++i)
+#pragma unroll
+                for (int j = 0; j < T; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (t + 1 < n_tiles) store_tile(buf ^ 1);
+        __syncthreads();
+    }
+
+    const float post_scale = a.epi.scale_ptr ? expf(__ldg(a.epi.scale_ptr)) : 1.f;
+#pragma unroll
+    for (int i = 0; i < T; ++i) {
+        const int64_t m = m0 + (i / 4) * (BM / H) + ty * 4 + (i % 4);
+        if (m >= a.M) continue;
+        const int64_t ia = a.epi.gather_a ? a.epi.idx_a[m] : 0;
+        const int64_t ib = a.epi.gather_b ? a.epi.idx_b[m] : 0;
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            const int64_t n = n0 + (j / 4) * (BN / H) + tx * 4 + (j % 4);
+            if (n < a.N) a.y[m * a.ldy + n] = epilogue_one(a.epi, acc[i][j], m, n, ia, ib, post_scale);
+        }
+    }
+}
+
+template <int BM, int BN, int T>
+static void launch_simt(const LinearArgs& a, bool vec, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(a.N, BN), (unsigned)ceil_div(a.M, BM));
+    constexpr int NT = (BM / T) * (BN / T);
+    if (vec) linear_simt_kernel<BM, BN, T, true><<<grid, NT, 0, st>>>(a);
+    else     linear_simt_kernel<BM, BN, T, false><<<grid, NT, 0, st>>>(a);
+}
+
+int linear_simt(const float* x, int64_t ldx, const float* w, int64_t ldw, float* y, int64_t ldy,
+                int64_t M, int64_t N, int64_t K, const vlsat_epilogue* epi, cudaStream_t st) {
+    LinearArgs a;
+    a.x = x; a.ldx = ldx; a.w = w; a.ldw = ldw; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.K = K;
+    if (epi) a.epi = *epi;
+    else { a.epi = vlsat_epilogue{}; a.epi.alpha = 1.f; }
+    const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) &&
+                     ((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0);
+    // Big tiles only when they still fill the machine; otherwise 64x64 tiles for more CTAs.
+    const int64_t big_ctas = ceil_div(M, 128) * ceil_div(N, 128);
+    if (big_ctas >= 2 * kNumSMs) launch_simt<128, 128, 8>(a, vec, st);
+    else                         launch_simt<64, 64, 4>(a, vec, st);
+    return finish_launch();
+}
+
+}  // namespace vlsat

@@ -1,0 +1,227 @@
+// A6 + A7: attention between the nodes of one scene, with the distance-bias MLP evaluated on the fly.
+//
+// The reference (network_MMG.py:181-205) loops over scenes in Python, materialises a dense
+// [1,H,N,N] bias and a [1,1,N,N] block-diagonal mask and runs dense N x N attention. Masked scores are
+// -inf, i.e. exactly zero weight, so attention restricted to the scene of the query is the same maths.
+// One CTA per query node; keys stream in tiles of 64 with an online softmax, so a scene may be any size.
+#include "common.cuh"
+#include <float.h>
+
+namespace vlsat {
+
+// packed self_attn_fc weights (floats): see ops.py::pack_attn_fc
+//   w0 [32,4] | b0 [32] | g0 [32] | be0 [32] | w1 [32,32] | b1 [32] | g1 [32] | be1 [32] | w2 [H,32] | b2 [H]
+struct FcOffsets {
+    static constexpr int W0 = 0, B0 = 128, G0 = 160, BE0 = 192, W1 = 224, B1 = 1248, G1 = 1280, BE1 = 1312, W2 = 1344;
+    __host__ __device__ static int b2(int H) { return W2 + 32 * H; }
+    __host__ __device__ static int total(int H) { return W2 + 33 * H; }
+};
+
+__global__ void scene_ranges_kernel(const int64_t* __restrict__ bid, int64_t n, int32_t* seg_start,
+                                    int32_t* seg_end, int32_t* err) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const int64_t me = bid[a];
+    if (a > 0 && bid[a - 1] > me && err) *err = 1;
+    int64_t lo = 0, hi = a;              // first index with bid == me (sorted)
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (bid[mid] < me) lo = mid + 1; else hi = mid; }
+    seg_start[a] = (int32_t)lo;
+    lo = a; hi = n;                      // first index with bid > me
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (bid[mid] <= me) lo = mid + 1; else hi = mid; }
+    seg_end[a] = (int32_t)lo;
+}
+
+constexpr int NA_TK = 64;        // keys per tile
+constexpr int NA_THREADS = 256;
+constexpr int NA_MAXH = 16;
+
+template <int DK>
+__global__ void __launch_bounds__(NA_THREADS)
+node_attn_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
+                 const float* __restrict__ v, int64_t ldv, const float* __restrict__ centres, int64_t ldc,
+                 const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_end,
+                 const float* __restrict__ fc, int H, float* __restrict__ out, int64_t ldo) {
+    extern __shared__ __align__(16) float sm[];
+    float* fcs = sm;                                  // FcOffsets::total(H)
+    float* qs = fcs + ((FcOffsets::total(H) + 3) & ~3); // H*DK
+    float* hbuf = qs + H * DK;                        // NA_TK * 33
+    float* bias_s = hbuf + NA_TK * 33;                // NA_TK * H
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t a = blockIdx.x;
+    const int s0 = seg_start[a], s1 = seg_end[a];
+
+    for (int i = tid; i < FcOffsets::total(H); i += NA_THREADS) fcs[i] = __ldg(fc + i);
+    for (int i = tid; i < H * DK; i += NA_THREADS) qs[i] = __ldg(q + a * ldq + i);
+    const float cax = centres[a * ldc + 0], cay = centres[a * ldc + 1], caz = centres[a * ldc + 2];
+    const float scale = rsqrtf((float)DK);
+
+    constexpr int DPL = DK / 32;                      // output dims per lane
+    constexpr int NHW = NA_MAXH / 8;                  // heads per warp (upper bound)
+    float m_run[NHW], l_run[NHW], acc[NHW][DPL];
+#pragma unroll
+    for (int i = 0; i < NHW; ++i) {
+        m_run[i] = -FLT_MAX; l_run[i] = 0.f;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) acc[i][d] = 0.f;
+    }
+    __syncthreads();
+
+    for (int b0 = s0; b0 < s1; b0 += NA_TK) {
+        const int nb = min(NA_TK, s1 - b0);
+        // ---- distance-bias MLP for the pairs (a, b0 + pr): 4 threads per pair, 8 hidden units each
+        {
+            const int pr = tid >> 2, part = tid & 3;
+            const bool live = pr < nb;
+            const int64_t b = b0 + (live ? pr : 0);
+            const float dx = centres[b * ldc + 0] - cax, dy = centres[b * ldc + 1] - cay, dz = centres[b * ldc + 2] - caz;
+            const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+            float h[8];
+            float s1_ = 0.f, s2_ = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = part * 8 + u;
+                const float* w = fcs + FcOffsets::W0 + j * 4;
+                float t = fcs[FcOffsets::B0 + j] + w[0] * dx + w[1] * dy + w[2] * dz + w[3] * dist;
+                t = fmaxf(t, 0.f);
+                h[u] = t; s1_ += t;
+            }
+            s1_ += __shfl_xor_sync(0xffffffffu, s1_, 1); s1_ += __shfl_xor_sync(0xffffffffu, s1_, 2);
+            float mean = s1_ * (1.f / 32.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { float d = h[u] - mean; s2_ += d * d; }
+            s2_ += __shfl_xor_sync(0xffffffffu, s2_, 1); s2_ += __shfl_xor_sync(0xffffffffu, s2_, 2);
+            float rstd = rsqrtf(s2_ * (1.f / 32.f) + 1e-5f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = part * 8 + u;
+                hbuf[pr * 33 + j] = (h[u] - mean) * rstd * fcs[FcOffsets::G0 + j] + fcs[FcOffsets::BE0 + j];
+            }
+            __syncwarp();
+            s1_ = 0.f; s2_ = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = part * 8 + u;
+                const float* w = fcs + FcOffsets::W1 + j * 32;
+                float t = fcs[FcOffsets::B1 + j];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) t = fmaf(w[i], hbuf[pr * 33 + i], t);
+                t = fmaxf(t, 0.f);
+                h[u] = t; s1_ += t;
+            }
+            s1_ += __shfl_xor_sync(0xffffffffu, s1_, 1); s1_ += __shfl_xor_sync(0xffffffffu, s1_, 2);
+            mean = s1_ * (1.f / 32.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { float d = h[u] - mean; s2_ += d * d; }
+            s2_ += __shfl_xor_sync(0xffffffffu, s2_, 1); s2_ += __shfl_xor_sync(0xffffffffu, s2_, 2);
+            rstd = rsqrtf(s2_ * (1.f / 32.f) + 1e-5f);
+            __syncwarp();                       // everyone has finished reading layer-1 values
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = part * 8 + u;
+                hbuf[pr * 33 + j] = (h[u] - mean) * rstd * fcs[FcOffsets::G1 + j] + fcs[FcOffsets::BE1 + j];
+            }
+            __syncwarp();
+            for (int hh = part; hh < H; hh += 4) {
+                const float* w = fcs + FcOffsets::W2 + hh * 32;
+                float t = fcs[FcOffsets::b2(H) + hh];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) t = fmaf(w[i], hbuf[pr * 33 + i], t);
+                bias_s[pr * H + hh] = t;
+            }
+        }
+        __syncthreads();
+        // ---- scores + online softmax + PV; warp w owns heads w, w+8, ...
+#pragma unroll
+        for (int hi = 0; hi < NHW; ++hi) {
+            const int hh = warp + 8 * hi;
+            if (hh >= H) break;
+            float sc[NA_TK / 32];
+            float tile_max = -FLT_MAX;
+#pragma unroll
+            for (int r = 0; r < NA_TK / 32; ++r) {
+                const int kb = lane + 32 * r;
+                float s = -FLT_MAX;
+                if (kb < nb) {
+                    const float4* kp = reinterpret_cast<const float4*>(k + (int64_t)(b0 + kb) * ldk + hh * DK);
+                    const float4* qp = reinterpret_cast<const float4*>(qs + hh * DK);
+                    float dot = 0.f;
+#pragma unroll
+                    for (int d = 0; d < DK / 4; ++d) {
+                        const float4 kv = __ldg(kp + d), qv = qp[d];
+                        dot = fmaf(kv.x, qv.x, dot); dot = fmaf(kv.y, qv.y, dot);
+                        dot = fmaf(kv.z, qv.z, dot); dot = fmaf(kv.w, qv.w, dot);
+                    }
+                    s = dot * scale + bias_s[kb * H + hh];
+                }
+                sc[r] = s; tile_max = fmaxf(tile_max, s);
+            }
+            tile_max = warp_max(tile_max);
+            const float m_new = fmaxf(m_run[hi], tile_max);
+            const float corr = __expf(m_run[hi] - m_new);
+            float psum = 0.f;
+#pragma unroll
+            for (int r = 0; r < NA_TK / 32; ++r) {
+                const int kb = lane + 32 * r;
+                sc[r] = (kb < nb) ? __expf(sc[r] - m_new) : 0.f;
+                psum += sc[r];
+            }
+            psum = warp_sum(psum);
+            l_run[hi] = l_run[hi] * corr + psum;
+            m_run[hi] = m_new;
+#pragma unroll
+            for (int d = 0; d < DPL; ++d) acc[hi][d] *= corr;
+#pragma unroll
+            for (int r = 0; r < NA_TK / 32; ++r) {
+                for (int j = 0; j < 32; ++j) {
+                    const int kb = j + 32 * r;
+                    if (kb >= nb) break;
+                    const float p = __shfl_sync(0xffffffffu, sc[r], j);
+                    const float* vp = v + (int64_t)(b0 + kb) * ldv + hh * DK;
+#pragma unroll
+                    for (int d = 0; d < DPL; ++d) acc[hi][d] = fmaf(p, __ldg(vp + lane + 32 * d), acc[hi][d]);
+                }
+            }
+        }
+        __syncthreads();   // bias_s / hbuf reused by the next tile
+    }
+#pragma unroll
+    for (int hi = 0; hi < NHW; ++hi) {
+        const int hh = warp + 8 * hi;
+        if (hh >= H) break;
+        const float inv = 1.f / l_run[hi];
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) out[a * ldo + hh * DK + lane + 32 * d] = acc[hi][d] * inv;
+    }
+}
+
+}  // namespace vlsat
+
+using namespace vlsat;
+
+extern "C" int vlsat_scene_ranges(const int64_t* batch_ids, int64_t n_nodes, int32_t* seg_start,
+                                  int32_t* seg_end, int32_t* err_flag, void* stream) {
+    VLSAT_REQUIRE(batch_ids && seg_start && seg_end && n_nodes >= 0);
+    VLSAT_SUPPORT(n_nodes < 0x7fffffff);
+    if (n_nodes == 0) return VLSAT_OK;
+    scene_ranges_kernel<<<(unsigned)ceil_div(n_nodes, 256), 256, 0, (cudaStream_t)stream>>>(
+        batch_ids, n_nodes, seg_start, seg_end, err_flag);
+    return finish_launch();
+}
+
+extern "C" int vlsat_node_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v,
+                                   int64_t ldv, const float* centres, int64_t ld_centres,
+                                   const int32_t* seg_start, const int32_t* seg_end, const float* fc_w,
+                                   int n_heads, int dk, float* out, int64_t ldo, int64_t n_nodes, void* stream) {
+    VLSAT_REQUIRE(q && k && v && centres && seg_start && seg_end && fc_w && out && n_nodes >= 0);
+    VLSAT_SUPPORT(n_heads >= 1 && n_heads <= NA_MAXH && (dk == 64 || dk == 128 || dk == 32));
+    VLSAT_SUPPORT(ldq % 4 == 0 && ldk % 4 == 0 && ((uintptr_t)k % 16 == 0) && n_nodes < 0x7fffffff);
+    if (n_nodes == 0) return VLSAT_OK;
+    const size_t smem = sizeof(float) * (((FcOffsets::total(n_heads) + 3) & ~3) + n_heads * dk + NA_TK * 33 + NA_TK * n_heads);
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)n_nodes;
+#define LAUNCH(DK_) node_attn_kernel<DK_><<<grid, NA_THREADS, smem, st>>>(q, ldq, k, ldk, v, ldv, centres, ld_centres, \
+        seg_start, seg_end, fc_w, n_heads, out, ldo)
+    if (dk == 64) LAUNCH(64); else if (dk == 128) LAUNCH(128); else LAUNCH(32);
+#undef LAUNCH
+    return finish_launch();
+}

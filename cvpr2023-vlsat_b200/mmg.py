@@ -1,0 +1,122 @@
+"""Host-side mirror of ``MMG`` (src/model/model_utils/network_MMG.py:115-250) and of
+``GraphEdgeAttenNetworkLayers`` (src/model/model_utils/network_GNN.py:197-284): same constructor
+arguments, parameter names and forward signatures; execution on the vlsat_b200 kernels.
+
+Differences in execution, not in maths:
+  * the per-scene Python loop that builds a dense [1,H,N,N] bias and [1,1,N,N] mask with a ``.item()``
+    sync (network_MMG.py:181-205) is replaced by per-node scene ranges + a bias MLP evaluated inside
+    the attention kernel - no host sync, no N^2 buffers;
+  * ``cross_attn_rel`` (network_MMG.py:231) streams its softmax instead of materialising E^2 scores;
+  * the inter-layer ReLU (network_MMG.py:236-248) is folded into the producing kernels' epilogues.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+from ._cache import DerivedCache, require_inference
+from .attention import MultiHeadAttention, SceneContext
+from .gat import GraphContext, GraphEdgeAttenNetwork
+
+
+def _bias_mlp(num_heads: int) -> nn.Sequential:
+    return nn.Sequential(nn.Linear(4, 32), nn.ReLU(), nn.LayerNorm(32), nn.Linear(32, 32), nn.ReLU(),
+                         nn.LayerNorm(32), nn.Linear(32, num_heads))
+
+
+class MMG(nn.Module):
+    def __init__(self, dim_node, dim_edge, dim_atten, num_heads=1, aggr='max', use_bn=False,
+                 flow='target_to_source', attention='fat', hidden_size=512, depth=1, use_edge: bool = True, **kwargs):
+        super().__init__()
+        self.num_heads, self.depth = num_heads, depth
+        self.dim_node, self.dim_edge, self.dim_atten, self.flow = dim_node, dim_edge, dim_atten, flow
+        mha = lambda d: MultiHeadAttention(d_model=d, d_k=d // num_heads, d_v=d // num_heads, h=num_heads)
+        self.self_attn = nn.ModuleList(mha(dim_node) for _ in range(depth))
+        self.cross_attn = nn.ModuleList(mha(dim_node) for _ in range(depth))
+        self.cross_attn_rel = nn.ModuleList(mha(dim_edge) for _ in range(depth))
+        self.gcn_2ds = nn.ModuleList()
+        self.gcn_3ds = nn.ModuleList()
+        for _ in range(depth):
+            self.gcn_2ds.append(GraphEdgeAttenNetwork(num_heads, dim_node, dim_edge, dim_atten, aggr, use_bn=use_bn,
+                                                      flow=flow, attention=attention, use_edge=use_edge, **kwargs))
+            self.gcn_3ds.append(GraphEdgeAttenNetwork(num_heads, dim_node, dim_edge, dim_atten, aggr, use_bn=use_bn,
+                                                      flow=flow, attention=attention, use_edge=use_edge, **kwargs))
+        self.self_attn_fc = _bias_mlp(num_heads)
+        self.drop_out = nn.Dropout(kwargs['DROP_OUT_ATTEN'])
+        self._cache = DerivedCache()
+
+    def scene_context(self, batch_ids, obj_center) -> SceneContext:
+        fc = self.self_attn_fc
+        pack = self._cache.get("fc", tuple(fc.parameters()), lambda: ops.pack_attn_fc(fc))
+        return SceneContext(batch_ids, obj_center, pack, self.num_heads)
+
+    def forward(self, obj_feature_3d, obj_feature_2d, edge_feature_3d, edge_feature_2d, edge_index, batch_ids,
+                obj_center=None, discriptor=None, istrain=False):
+        require_inference(self, "MMG")
+        if obj_center is None:
+            raise NotImplementedError("MMG.forward needs obj_center (the reference path without it is broken: "
+                                      "network_MMG.py:207-217 reads an undefined variable)")
+        n = obj_feature_3d.shape[0]
+        dn, da = self.dim_node, self.dim_atten
+        ctx = self.scene_context(batch_ids, obj_center)
+        g = GraphContext(edge_index, n, self.flow)
+        o3, o2 = obj_feature_3d.contiguous(), obj_feature_2d.contiguous()
+        e3, e2 = edge_feature_3d.contiguous(), edge_feature_2d.contiguous()
+        for i in range(self.depth):
+            act = (i < self.depth - 1) or self.depth == 1          # ReLU(+Dropout) after this layer
+            cat3 = torch.empty((n, dn + da), device=o3.device, dtype=torch.float32)
+            cat2 = torch.empty((n, dn + da), device=o3.device, dtype=torch.float32)
+            o3 = self.self_attn[i].attend_scenes(o3, o3, ctx, out=cat3[:, :dn])
+            o2 = self.cross_attn[i].attend_scenes(o2, o3, ctx, out=cat2[:, :dn])
+            o3, e3_raw, _ = self.gcn_3ds[i].forward_fused(cat3, e3, g, relu_nodes=act)
+            o2, e2_raw, _ = self.gcn_2ds[i].forward_fused(cat2, e2, g, relu_nodes=act)
+            e2 = self.cross_attn_rel[i].attend_all(e2_raw, e3_raw, relu=act)
+            e3 = ops.relu(e3_raw) if act else e3_raw
+        return o3, o2, e3, e2
+
+
+class GraphEdgeAttenNetworkLayers(nn.Module):
+    """A sequence of (node self-attention, graph-attention) layers - the SGFN twin (network_GNN.py:197)."""
+
+    def __init__(self, dim_node, dim_edge, dim_atten, num_layers, num_heads=1, aggr='max', use_bn=False,
+                 flow='target_to_source', attention='fat', use_edge: bool = True, **kwargs):
+        super().__init__()
+        self.num_layers, self.num_heads = num_layers, num_heads
+        self.dim_node, self.dim_edge, self.dim_atten, self.flow = dim_node, dim_edge, dim_atten, flow
+        self.gconvs = nn.ModuleList()
+        self.drop_out = nn.Dropout(kwargs['DROP_OUT_ATTEN']) if 'DROP_OUT_ATTEN' in kwargs else None
+        # the reference hard-codes 8 heads here regardless of num_heads (network_GNN.py:211,220)
+        self.self_attn = nn.ModuleList(
+            MultiHeadAttention(d_model=dim_node, d_k=dim_node // 8, d_v=dim_node // 8, h=8) for _ in range(num_layers))
+        self.self_attn_fc = _bias_mlp(8)
+        for _ in range(num_layers):
+            self.gconvs.append(GraphEdgeAttenNetwork(num_heads, dim_node, dim_edge, dim_atten, aggr, use_bn=use_bn,
+                                                     flow=flow, attention=attention, use_edge=use_edge,
+                                                     return_prob=True, **kwargs))
+        self.probs_on_host = True     # network_GNN.py:281 returns prob.cpu() per layer (a D2H sync each)
+        self._cache = DerivedCache()
+
+    def forward(self, node_feature, edge_feature, edges_indices, obj_center, batch_ids):
+        require_inference(self, "GraphEdgeAttenNetworkLayers")
+        if obj_center is None:
+            raise NotImplementedError("obj_center is required (network_GNN.py:260-265 breaks without it)")
+        if self.num_heads != 8:
+            # network_GNN.py:235,253: the bias buffer is sized with num_heads but filled with 8 heads
+            raise RuntimeError("GraphEdgeAttenNetworkLayers: the reference raises a shape error unless num_heads == 8")
+        n = node_feature.shape[0]
+        dn, da = self.dim_node, self.dim_atten
+        fc = self.self_attn_fc
+        pack = self._cache.get("fc", tuple(fc.parameters()), lambda: ops.pack_attn_fc(fc))
+        ctx = SceneContext(batch_ids, obj_center, pack, 8)
+        g = GraphContext(edges_indices, n, self.flow)
+        node, edge = node_feature.contiguous(), edge_feature.contiguous()
+        probs = []
+        for i in range(self.num_layers):
+            act = (i < self.num_layers - 1) or self.num_layers == 1
+            cat = torch.empty((n, dn + da), device=node.device, dtype=torch.float32)
+            self.self_attn[i].attend_scenes(node, node, ctx, out=cat[:, :dn])
+            node, edge_raw, prob = self.gconvs[i].forward_fused(cat, edge, g, relu_nodes=act, want_prob=True)
+            edge = ops.relu(edge_raw) if act else edge_raw
+            probs.append(prob.cpu().detach() if self.probs_on_host else prob)
+        return node, edge, probs

@@ -1,0 +1,287 @@
+"""Thin Python wrappers over the C ABI (include/vlsat_b200.h): argument checking, output allocation
+with torch (device memory + current stream are PyTorch's job here, nothing else), then one C call.
+
+No wrapper has a CPU or PyTorch compute path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Epilogue
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+AGGR = {"max": 0, "add": 1, "mean": 2}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (vlsat_b200 has no CPU path), got {t.device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    return t
+
+
+def _rows(t: torch.Tensor, name: str) -> Tuple[int, int]:
+    """2-D tensor with unit inner stride -> (data_ptr, leading dimension)."""
+    _f32(t, name)
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError(f"{name}: expected a 2-D tensor with contiguous rows, got shape {tuple(t.shape)} strides {t.stride()}")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+    return t.data_ptr(), ld
+
+
+def _i64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda or t.dtype != torch.int64 or not t.is_contiguous():
+        raise TypeError(f"{name}: expected a contiguous CUDA int64 tensor, got {t.dtype} on {t.device}")
+    return t
+
+
+def launch_count() -> int:
+    return int(_lib.load().vlsat_launch_count())
+
+
+def gemm_engine() -> str:
+    return _lib.load().vlsat_gemm_engine().decode()
+
+
+# ------------------------------------------------------------------------------------------ encoders
+def pointnet(x, w1, b1, w2, b2, w3, b3, want_argmax: bool = False):
+    """A1. x [n_obj, c_in, P] -> [n_obj, c_out]; weights are the squeezed Conv1d(k=1) weights."""
+    _f32(x, "x")
+    if x.dim() != 3 or not x.is_contiguous():
+        raise ValueError("pointnet: x must be a contiguous [n_obj, c_in, n_pts] tensor")
+    n_obj, c_in, n_pts = x.shape
+    for n, t in (("w1", w1), ("b1", b1), ("w2", w2), ("b2", b2), ("w3", w3), ("b3", b3)):
+        _f32(t, n)
+        if not t.is_contiguous():
+            raise ValueError(f"pointnet: {n} must be contiguous")
+    c1, c2, c_out = w1.shape[0], w2.shape[0], w3.shape[0]
+    if w1.shape[1] != c_in or w2.shape[1] != c1 or w3.shape[1] != c2:
+        raise ValueError("pointnet: weight shapes do not chain")
+    out = torch.empty((n_obj, c_out), device=x.device, dtype=torch.float32)
+    arg = torch.empty((n_obj, c_out), device=x.device, dtype=torch.int32) if want_argmax else None
+    st = _lib.load().vlsat_pointnet_fwd(x.data_ptr(), n_obj, c_in, n_pts, w1.data_ptr(), b1.data_ptr(), c1,
+                                        w2.data_ptr(), b2.data_ptr(), c2, w3.data_ptr(), b3.data_ptr(), c_out,
+                                        out.data_ptr(), arg.data_ptr() if want_argmax else None, _stream())
+    _lib.check(st, "vlsat_pointnet_fwd")
+    return (out, arg) if want_argmax else out
+
+
+def edge_descriptor(desc: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+    """A2. desc [N, 11], edge_index [2, E] int64 -> [E, 11]."""
+    _f32(desc, "descriptor"); _i64(edge_index, "edge_index")
+    if desc.dim() != 2 or desc.shape[1] != 11 or not desc.is_contiguous():
+        raise ValueError("edge_descriptor: descriptor must be contiguous [N, 11]")
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError("edge_descriptor: edge_index must be [2, E]")
+    e = edge_index.shape[1]
+    out = torch.empty((e, 11), device=desc.device, dtype=torch.float32)
+    _lib.check(_lib.load().vlsat_edge_descriptor_fwd(desc.data_ptr(), desc.shape[0], edge_index.data_ptr(), e,
+                                                     out.data_ptr(), _stream()), "vlsat_edge_descriptor_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------- dense projection
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+           out: Optional[torch.Tensor] = None,
+           gather: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]] = None,
+           residual: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0,
+           scale_ptr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = post(act(x w^T + bias + ga[ia] + gb[ib])), post(t) = (alpha t + beta residual) * exp(scale).
+
+    x [M, K] and w [N, K] may be column-slice views (row stride = leading dimension); ``out`` may be a
+    column slice of a wider buffer."""
+    xp, ldx = _rows(x, "x")
+    wp, ldw = _rows(w, "w")
+    m, k = x.shape
+    n = w.shape[0]
+    if w.shape[1] != k:
+        raise ValueError(f"linear: x is [{m},{k}] but w is {tuple(w.shape)}")
+    if out is None:
+        out = torch.empty((m, n), device=x.device, dtype=torch.float32)
+    elif tuple(out.shape) != (m, n):
+        raise ValueError(f"linear: out has shape {tuple(out.shape)}, expected {(m, n)}")
+    yp, ldy = _rows(out, "out")
+    epi = Epilogue()
+    epi.alpha, epi.beta, epi.act = alpha, beta, act
+    if bias is not None:
+        _f32(bias, "bias")
+        if bias.numel() != n or not bias.is_contiguous():
+            raise ValueError("linear: bias must be contiguous [N]")
+        epi.bias = bias.data_ptr()
+    if gather is not None:
+        ga, ia, gb, ib = gather
+        gap, ldga = _rows(ga, "gather_a"); gbp, ldgb = _rows(gb, "gather_b")
+        _i64(ia, "idx_a"); _i64(ib, "idx_b")
+        if ldga != ldgb or ga.shape[1] != n or gb.shape[1] != n or ia.numel() != m or ib.numel() != m:
+            raise ValueError("linear: gather operands must be [*, N] with equal row strides and [M] indices")
+        epi.gather_a, epi.idx_a, epi.gather_b, epi.idx_b, epi.ld_gather = gap, ia.data_ptr(), gbp, ib.data_ptr(), ldga
+    if residual is not None:
+        rp, ldr = _rows(residual, "residual")
+        if tuple(residual.shape) != (m, n):
+            raise ValueError("linear: residual must be [M, N]")
+        epi.residual, epi.ld_res = rp, ldr
+    if scale_ptr is not None:
+        _f32(scale_ptr, "scale_ptr")
+        epi.scale_ptr = scale_ptr.data_ptr()
+    st = _lib.load().vlsat_linear_fwd(xp, ldx, wp, ldw, yp, ldy, m, n, k, C.byref(epi), _stream())
+    _lib.check(st, "vlsat_linear_fwd")
+    return out
+
+
+def add_layernorm(x: torch.Tensor, res: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
+                  eps: float = 1e-5, relu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    xp, ldx = _rows(x, "x")
+    m, d = x.shape
+    rp, ldr = (None, 0)
+    if res is not None:
+        rp, ldr = _rows(res, "res")
+        if tuple(res.shape) != (m, d):
+            raise ValueError("add_layernorm: res shape mismatch")
+    if out is None:
+        out = torch.empty((m, d), device=x.device, dtype=torch.float32)
+    yp, ldy = _rows(out, "out")
+    _f32(gamma, "gamma"); _f32(beta, "beta")
+    st = _lib.load().vlsat_add_layernorm_fwd(xp, ldx, rp, ldr, gamma.data_ptr(), beta.data_ptr(), yp, ldy, m, d,
+                                             eps, int(relu), _stream())
+    _lib.check(st, "vlsat_add_layernorm_fwd")
+    return out
+
+
+def relu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _f32(x, "x")
+    if not x.is_contiguous():
+        raise ValueError("relu: x must be contiguous")
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.load().vlsat_relu_fwd(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "vlsat_relu_fwd")
+    return out
+
+
+def row_l2norm(x: torch.Tensor) -> torch.Tensor:
+    _f32(x, "x")
+    if x.dim() != 2 or not x.is_contiguous():
+        raise ValueError("row_l2norm: x must be contiguous 2-D")
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().vlsat_row_l2norm_fwd(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream()),
+               "vlsat_row_l2norm_fwd")
+    return out
+
+
+def spatial_tail(desc: torch.Tensor, out: torch.Tensor, col0: int) -> None:
+    _f32(desc, "descriptor")
+    op, ld = _rows(out, "out")
+    if desc.shape[1] != 11 or not desc.is_contiguous() or out.shape[0] != desc.shape[0]:
+        raise ValueError("spatial_tail: descriptor must be contiguous [N, 11] and out [N, >= col0 + 8]")
+    _lib.check(_lib.load().vlsat_spatial_tail_fwd(desc.data_ptr(), op, ld, col0, desc.shape[0], _stream()),
+               "vlsat_spatial_tail_fwd")
+
+
+# -------------------------------------------------------------------------------------------- attention
+FC_PACK_HEAD = 1344   # floats before w2 in the packed self_attn_fc buffer (see csrc/node_attn.cu)
+
+
+def pack_attn_fc(fc: torch.nn.Sequential) -> torch.Tensor:
+    """Pack ``self_attn_fc`` (network_MMG.py:165-173) as
+    w0[32,4] b0 g0 be0 | w1[32,32] b1 g1 be1 | w2[H,32] b2[H] in one fp32 vector."""
+    parts = [fc[0].weight, fc[0].bias, fc[2].weight, fc[2].bias, fc[3].weight, fc[3].bias,
+             fc[5].weight, fc[5].bias, fc[6].weight, fc[6].bias]
+    return torch.cat([p.detach().reshape(-1).float() for p in parts]).contiguous()
+
+
+def scene_ranges(batch_ids: torch.Tensor):
+    """A6 bookkeeping: per-node [start, end) of its scene. Returns (seg_start, seg_end, err_flag)."""
+    b = _i64(batch_ids.reshape(-1), "batch_ids")
+    n = b.numel()
+    seg = torch.empty((2, n), device=b.device, dtype=torch.int32)
+    err = torch.zeros((1,), device=b.device, dtype=torch.int32)
+    _lib.check(_lib.load().vlsat_scene_ranges(b.data_ptr(), n, seg[0].data_ptr(), seg[1].data_ptr(), err.data_ptr(),
+                                              _stream()), "vlsat_scene_ranges")
+    return seg[0], seg[1], err
+
+
+def node_attn(q, k, v, centres, seg_start, seg_end, fc_pack, n_heads: int) -> torch.Tensor:
+    qp, ldq = _rows(q, "q"); kp, ldk = _rows(k, "k"); vp_, ldv = _rows(v, "v")
+    cp, ldc = _rows(centres, "centres")
+    n, d = q.shape
+    dk = d // n_heads
+    if fc_pack.numel() != FC_PACK_HEAD + 33 * n_heads:
+        raise ValueError("node_attn: packed self_attn_fc has the wrong size for this head count")
+    out = torch.empty((n, d), device=q.device, dtype=torch.float32)
+    st = _lib.load().vlsat_node_attn_fwd(qp, ldq, kp, ldk, vp_, ldv, cp, ldc, seg_start.data_ptr(), seg_end.data_ptr(),
+                                         _f32(fc_pack, "fc_pack").data_ptr(), n_heads, dk, out.data_ptr(), d, n, _stream())
+    _lib.check(st, "vlsat_node_attn_fwd")
+    return out
+
+
+def flash_attn(q, k, v, n_heads: int, want_lse: bool = False):
+    qp, ldq = _rows(q, "q"); kp, ldk = _rows(k, "k"); vp_, ldv = _rows(v, "v")
+    nq, d = q.shape
+    nk = k.shape[0]
+    dk = d // n_heads
+    out = torch.empty((nq, d), device=q.device, dtype=torch.float32)
+    lse = torch.empty((n_heads, nq), device=q.device, dtype=torch.float32) if want_lse else None
+    st = _lib.load().vlsat_flash_attn_fwd(qp, ldq, kp, ldk, vp_, ldv, out.data_ptr(), d,
+                                          lse.data_ptr() if want_lse else None, nq, nk, n_heads, dk, _stream())
+    _lib.check(st, "vlsat_flash_attn_fwd")
+    return (out, lse) if want_lse else out
+
+
+# -------------------------------------------------------------------------------------- graph attention
+def build_csr(index_row: torch.Tensor, n_nodes: int):
+    """Stable grouping of edges by ``index_row``: (row_ptr [N+1] int32, perm [E] int32)."""
+    _i64(index_row, "index_row")
+    e = index_row.numel()
+    dev = index_row.device
+    row_ptr = torch.empty((n_nodes + 1,), device=dev, dtype=torch.int32)
+    perm = torch.empty((max(e, 1),), device=dev, dtype=torch.int32)
+    ws = torch.empty((n_nodes + 1 + e,), device=dev, dtype=torch.int32)
+    st = _lib.load().vlsat_build_csr(index_row.data_ptr(), e, n_nodes, row_ptr.data_ptr(), perm.data_ptr(),
+                                     ws.data_ptr(), ws.numel() * 4, _stream())
+    _lib.check(st, "vlsat_build_csr")
+    return row_ptr, perm[:e]
+
+
+def gat_edge(q, v, k, edge_index, row_ptr, perm, c1, c1b, c2, c2b, n_heads: int, aggr: str = "max",
+             use_edge: bool = True, want_prob: bool = False, want_argmax: bool = False,
+             out: Optional[torch.Tensor] = None):
+    """A8 core. q [N, H*d_n], v [N, H*d_o], k [E, H*d_e] (column-slice views allowed) -> xx [N, H*d_o]."""
+    qp, ldq = _rows(q, "q"); vp_, ldv = _rows(v, "v")
+    n = q.shape[0]
+    _i64(edge_index, "edge_index")
+    e = edge_index.shape[1]
+    d_n, d_o = q.shape[1] // n_heads, v.shape[1] // n_heads
+    kp, ldk, d_e = None, 0, 0
+    if use_edge:
+        kp, ldk = _rows(k, "k")
+        d_e = k.shape[1] // n_heads
+        if k.shape[0] != e:
+            raise ValueError("gat_edge: k must have one row per edge")
+    for nme, t in (("c1", c1), ("c1b", c1b), ("c2", c2), ("c2b", c2b)):
+        _f32(t, nme)
+        if not t.is_contiguous():
+            raise ValueError(f"gat_edge: {nme} must be contiguous")
+    hid = c1.shape[0]
+    if c1.shape[1] != d_n + d_e or tuple(c2.shape) != (d_o, hid):
+        raise ValueError(f"gat_edge: MLP weights {tuple(c1.shape)}, {tuple(c2.shape)} do not match d_n={d_n}, d_e={d_e}, d_o={d_o}")
+    d_a = n_heads * d_o
+    if out is None:
+        out = torch.empty((n, d_a), device=q.device, dtype=torch.float32)
+    xp, ldxx = _rows(out, "out")
+    prob = torch.empty((e, d_o, n_heads), device=q.device, dtype=torch.float32) if want_prob else None
+    arg = torch.empty((n, d_a), device=q.device, dtype=torch.int32) if want_argmax else None
+    st = _lib.load().vlsat_gat_edge_fwd(qp, ldq, vp_, ldv, kp, ldk, edge_index.data_ptr(), row_ptr.data_ptr(),
+                                        perm.data_ptr(), c1.data_ptr(), c1b.data_ptr(), c2.data_ptr(), c2b.data_ptr(),
+                                        n, e, n_heads, d_n, d_e, d_o, hid, AGGR[aggr], int(use_edge), xp, ldxx,
+                                        prob.data_ptr() if want_prob else None, arg.data_ptr() if want_argmax else None,
+                                        _stream())
+    _lib.check(st, "vlsat_gat_edge_fwd")
+    return out, prob, arg

@@ -1,0 +1,152 @@
+/*
+ * vlsat_b200 - C ABI of the B200-native VL-SAT hot path (libvlsat_b200.so, sm_100a only).
+ *
+ * Every entry point takes raw DEVICE pointers + sizes + the cudaStream_t to launch on (passed as
+ * void*), launches asynchronously, owns no persistent state, never synchronises, never throws.
+ * Return value: 0 = ok, otherwise a vlsat_status code (vlsat_error_string() decodes it).
+ * All floating-point tensors are fp32, row-major, innermost dimension contiguous unless a leading
+ * dimension (ld*) argument says otherwise. Index tensors are int64 exactly as the reference passes
+ * them (PyG requires int64 edge_index); derived CSR arrays are int32.
+ *
+ * Each declaration cites the reference code (paths relative to the reference root) it replaces.
+ */
+#ifndef VLSAT_B200_H
+#define VLSAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    VLSAT_OK = 0,
+    VLSAT_ERR_INVALID_ARG = 1,   /* null pointer / negative size / inconsistent dims               */
+    VLSAT_ERR_UNSUPPORTED = 2,   /* shape outside what the kernels are built for (loud, no fallback) */
+    VLSAT_ERR_LAUNCH = 3,        /* cudaGetLastError() after launch was not cudaSuccess             */
+    VLSAT_ERR_WORKSPACE = 4      /* workspace_bytes too small                                       */
+} vlsat_status;
+
+#define VLSAT_ACT_NONE 0
+#define VLSAT_ACT_RELU 1
+#define VLSAT_ACT_SIGMOID 2
+
+#define VLSAT_AGGR_MAX 0
+#define VLSAT_AGGR_ADD 1
+#define VLSAT_AGGR_MEAN 2
+
+int vlsat_version(void);
+const char* vlsat_error_string(int status);
+/* Name of the GEMM engine the library was built with ("tcgen05-bf16x3", "simt-fp32", ...). */
+const char* vlsat_gemm_engine(void);
+/* Number of kernel launches issued by this process through the library so far (bench bookkeeping). */
+int64_t vlsat_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * A1 / A3  PointNetfeat.forward  (src/model/model_utils/network_PointNet.py:121-176, batch_norm=False,
+ *          input_transform=False, feature_transform=False, global_feat=True)
+ *   out[o,c] = max_p ReLU(b3[c] + W3[c,:] . ReLU(b2 + W2 . ReLU(b1 + W1 . x[o,:,p])))
+ *   x [n_obj, c_in, n_pts] channels-first; W1 [c1,c_in], W2 [c2,c1], W3 [c_out,c2] (Conv1d k=1 weights
+ *   with the trailing 1 squeezed). argmax (nullable) [n_obj, c_out] int32 = arg max point (for backward).
+ * ---------------------------------------------------------------------------------------------- */
+int vlsat_pointnet_fwd(const float* x, int64_t n_obj, int c_in, int64_t n_pts,
+                       const float* w1, const float* b1, int c1,
+                       const float* w2, const float* b2, int c2,
+                       const float* w3, const float* b3, int c_out,
+                       float* out, int32_t* argmax, void* stream);
+
+/* A2  Gen_edge_descriptor.message (src/utils/op_utils.py:85-97) with flow='target_to_source':
+ *   out[e,0:6] = d[src,0:6]-d[dst,0:6]; out[e,6:11] = log(d[src,6:11]/d[dst,6:11]).  out [E, 11]. */
+int vlsat_edge_descriptor_fwd(const float* desc, int64_t n_nodes, const int64_t* edge_index, int64_t n_edges,
+                              float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense projections (nn.Linear / Conv1d k=1 everywhere on the path: network_MMG.py:31,59-60,77-79,
+ * attention.py:19-22, network_PointNet.py:314-316, SGFN_MMG/model.py:88-111, clip_adapter/model.py:15-17)
+ *   y[m, n] = post( act( sum_k x[m,k] w[n,k] + bias[n] + ga[ia[m], n] + gb[ib[m], n] ) )
+ *   post(t) = (alpha*t + beta*res[m,n]) * (scale_ptr ? expf(*scale_ptr) : 1)
+ * The two row-gather terms implement "project per node, gather per edge" for the concatenations
+ * cat[x_i, e, x_j] (network_MMG.py:87) and cat[o[src], o[dst], e] (SGFN_MMG/model.py:260-265).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* bias;        /* [N] or NULL                                   */
+    const float* gather_a;    /* [*, ld_gather] rows indexed by idx_a, or NULL  */
+    const int64_t* idx_a;     /* [M]                                           */
+    const float* gather_b;
+    const int64_t* idx_b;
+    int64_t ld_gather;
+    const float* residual;    /* [M, ld_res] or NULL                           */
+    int64_t ld_res;
+    float alpha;              /* used only when residual != NULL or alpha != 1 */
+    float beta;
+    const float* scale_ptr;   /* device scalar s: result *= expf(s); or NULL   */
+    int act;                  /* VLSAT_ACT_*                                   */
+} vlsat_epilogue;
+
+int vlsat_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw,
+                     float* y, int64_t ldy, int64_t M, int64_t N, int64_t K,
+                     const vlsat_epilogue* epi, void* stream);
+
+/* LayerNorm(x + res) (attention.py:122-123; eps 1e-5), optional ReLU on the way out
+ * (network_MMG.py:236-248 fused for the streams whose raw value is not needed). */
+int vlsat_add_layernorm_fwd(const float* x, int64_t ldx, const float* res, int64_t ld_res,
+                            const float* gamma, const float* beta, float* y, int64_t ldy,
+                            int64_t M, int D, float eps, int relu, void* stream);
+
+/* Elementwise helpers: y = relu(x) (network_MMG.py:236-248); row L2 normalisation
+ * (SGFN_MMG/model.py:329-330); spatial tail of the 3-D node feature (SGFN_MMG/model.py:296-299):
+ * out[n, col0 + 0:6] = desc[n,3:9], out[n, col0+6:8] = log(desc[n,9:11]). */
+int vlsat_relu_fwd(const float* x, float* y, int64_t numel, void* stream);
+int vlsat_row_l2norm_fwd(const float* x, float* y, int64_t M, int D, void* stream);
+int vlsat_spatial_tail_fwd(const float* desc, float* out, int64_t ld_out, int col0, int64_t n_nodes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A6 + A7  node attention inside scenes (network_MMG.py:181-205,217-218; attention.py:54-77).
+ *   seg_start/seg_end [n] int32: scene range of every node, derived from batch_ids (non-decreasing).
+ *   out[a, h*dk:(h+1)*dk] = sum_b softmax_b( q_a.k_b/sqrt(dk) + MLP([c_b-c_a, |c_b-c_a|])[h] ) v_b,
+ *   b over the scene of a. MLP = Linear(4,32) ReLU LN Linear(32,32) ReLU LN Linear(32,H)
+ *   (network_MMG.py:165-173); fc_w packs its 10 tensors (layout in DESIGN.md / ops.py).
+ *   err_flag (device int32): set to 1 if batch_ids is not non-decreasing.
+ * ---------------------------------------------------------------------------------------------- */
+int vlsat_scene_ranges(const int64_t* batch_ids, int64_t n_nodes, int32_t* seg_start, int32_t* seg_end,
+                       int32_t* err_flag, void* stream);
+int vlsat_node_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                        const float* centres, int64_t ld_centres,
+                        const int32_t* seg_start, const int32_t* seg_end,
+                        const float* fc_w, int n_heads, int dk,
+                        float* out, int64_t ldo, int64_t n_nodes, void* stream);
+
+/* A9  cross_attn_rel core (network_MMG.py:231; attention.py:54-77 without mask/bias): streaming
+ * softmax(QK^T/sqrt(dk)) V over ALL keys, never materialising the [H, nq, nk] score tensor.
+ * lse (nullable) [H, nq] = log-sum-exp per row (saved for backward). */
+int vlsat_flash_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                         float* out, int64_t ldo, float* lse, int64_t nq, int64_t nk, int n_heads, int dk,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A8  graph attention layer core (network_MMG.py:34-41,96-104; network_util.py:50-73).
+ *   vlsat_build_csr: stable counting sort of edges by index_row (= edge_index[0] for
+ *     flow='target_to_source'): row_ptr [n_nodes+1], perm [n_edges] (edge ids grouped by node,
+ *     ascending inside a group). workspace >= (n_nodes+1+n_edges)*4 bytes. Bit-exact integer work.
+ *   vlsat_gat_edge_fwd: for every edge e (src,dst) and head h
+ *       u = [q[src, c*H+h]]_c ++ [k[e, c*H+h]]_c ;  t = C2 . ReLU(C1 . u + c1) + c2 ; p = softmax(t)
+ *       m[e, c*H+h] = p[c] * v[dst, c*H+h]
+ *     xx[n,:] = aggr_{e: src(e)=n} m[e,:]  (max: 0 for nodes without out-edges; add; mean).
+ *     q = proj_query(x) [n_nodes, H*d_n], v = proj_value(x) [n_nodes, H*d_o], k = proj_edge(e)
+ *     [n_edges, H*d_e] (use_edge=0: k ignored, C1 is [hid, d_n]); ldq/ldv/ldk/ld_xx = row strides, so q, v
+ *     may be column slices of one fused node projection and xx a slice of the cat[x, xx] buffer.
+ *     prob (nullable) [n_edges, d_o, H]; argmax (nullable) [n_nodes, H*d_o] int32 edge id or -1.
+ * ---------------------------------------------------------------------------------------------- */
+int vlsat_build_csr(const int64_t* index_row, int64_t n_edges, int64_t n_nodes,
+                    int32_t* row_ptr, int32_t* perm, void* workspace, size_t workspace_bytes, void* stream);
+int vlsat_gat_edge_fwd(const float* q, int64_t ldq, const float* v, int64_t ldv, const float* k, int64_t ldk,
+                       const int64_t* edge_index, const int32_t* row_ptr, const int32_t* perm,
+                       const float* c1, const float* c1_bias, const float* c2, const float* c2_bias,
+                       int64_t n_nodes, int64_t n_edges, int n_heads, int d_n, int d_e, int d_o, int hid,
+                       int aggr, int use_edge, float* xx, int64_t ld_xx, float* prob, int32_t* argmax, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLSAT_B200_H */

@@ -1,0 +1,53 @@
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+# Parity tolerance: the reference's own notion of "equal" (src/utils/op_utils.py:281) and the
+# north_star bar (1e-3 relative, fp32).
+RTOL, ATOL = 1e-3, 1e-5
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    cache = {}
+
+    def load(name):
+        if name not in cache:
+            cache[name] = torch.load(os.path.join(ROOT, "tests", "golden", name + ".pt"), map_location="cpu")
+        return cache[name]
+    return load
+
+
+def assert_close(actual, expected, what="", rtol=RTOL, atol=ATOL):
+    actual = actual.detach().float().cpu()
+    expected = expected.detach().float().cpu()
+    assert actual.shape == expected.shape, f"{what}: shape {tuple(actual.shape)} vs {tuple(expected.shape)}"
+    assert torch.isfinite(actual).all(), f"{what}: non-finite values"
+    err = (actual - expected).abs()
+    tol = atol + rtol * expected.abs()
+    bad = err > tol
+    if bad.any():
+        i = torch.argmax(err - tol)
+        raise AssertionError(f"{what}: {int(bad.sum())}/{bad.numel()} outside rtol={rtol} atol={atol}; worst: "
+                             f"got {actual.flatten()[i].item():.6g} want {expected.flatten()[i].item():.6g} "
+                             f"(max abs err {err.max().item():.3g})")

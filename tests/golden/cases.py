@@ -1,0 +1,100 @@
+"""Seeded inputs of the golden cases. Shared by ``oracle/make_golden.py`` (which feeds them to the
+UNMODIFIED reference modules in the build container and stores the outputs next to this file) and by the
+tests (which feed them to the oracle and to the CUDA path). Nothing here depends on the reference."""
+from __future__ import annotations
+
+import torch
+
+import vlsat_b200  # noqa: F401  (registers the package alias)
+from vlsat_b200 import synth
+
+GOLDEN_DIR = __file__.rsplit("/", 1)[0]
+
+# ---- full-model cases: name -> (model-config overrides, batch builder) -------------------------------
+MMGNET_CASES = {
+    "mmgnet_cfg1": (dict(), lambda: synth.make_config_batch("cfg1", seed=0)),
+    "mmgnet_ragged": (dict(), lambda: synth.make_batch(3, [4, 7, 2], 64, None, seed=3, shuffle_edges=True)),
+    "mmgnet_l3h4": (dict(N_LAYERS=3, NUM_HEADS=4), lambda: synth.make_batch(2, [5, 6], 32, None, seed=5)),
+    "mmgnet_cfg2x2": (dict(), lambda: synth.make_config_batch("cfg2", seed=1, num_scenes=2)),
+    "mmgnet_addaggr": (dict(GCN_AGGR="add", N_LAYERS=1), lambda: synth.make_batch(2, [3, 5], 40, 6, seed=9)),
+}
+MMGNET_WEIGHT_SEED = 0
+
+
+def model_config(overrides: dict) -> dict:
+    cfg = dict(vlsat_b200.DEFAULT_MODEL_CONFIG)
+    cfg.update(overrides)
+    return {"MODEL": cfg}
+
+
+# ---- graph-attention layer cases ---------------------------------------------------------------------
+def gat_graph(seed: int, n_nodes: int, n_edges: int, isolated=()):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, n_nodes, (n_edges,), generator=g)
+    dst = torch.randint(0, n_nodes, (n_edges,), generator=g)
+    for iso in isolated:                      # make sure some nodes have no outgoing / incoming edge at all
+        src[src == iso] = (iso + 1) % n_nodes
+        dst[dst == iso] = (iso + 1) % n_nodes
+    return torch.stack([src, dst], 0)
+
+
+GAT_CASES = {
+    # name: (ctor kwargs, n_nodes, n_edges, isolated nodes, seed)
+    "gat_max_h4": (dict(num_heads=4, dim_node=64, dim_edge=32, dim_atten=32, aggr="max", DROP_OUT_ATTEN=0.5), 9, 40, (2, 5), 11),
+    "gat_add_h4": (dict(num_heads=4, dim_node=64, dim_edge=32, dim_atten=32, aggr="add", DROP_OUT_ATTEN=0.5), 9, 40, (2,), 12),
+    "gat_mean_h2": (dict(num_heads=2, dim_node=32, dim_edge=64, dim_atten=128, aggr="mean", DROP_OUT_ATTEN=0.5), 7, 33, (), 13),
+    "gat_noedge": (dict(num_heads=4, dim_node=64, dim_edge=32, dim_atten=32, aggr="max", use_edge=False, DROP_OUT_ATTEN=0.5), 6, 20, (0,), 14),
+    "gat_s2t": (dict(num_heads=4, dim_node=64, dim_edge=32, dim_atten=32, aggr="max", flow="source_to_target", DROP_OUT_ATTEN=0.5), 8, 30, (3,), 15),
+    "gat_mmg_dims": (dict(num_heads=8, dim_node=512, dim_edge=512, dim_atten=256, aggr="max", DROP_OUT_ATTEN=0.5), 12, 50, (7,), 16),
+    "gat_nodrop": (dict(num_heads=4, dim_node=64, dim_edge=32, dim_atten=32, aggr="max"), 5, 12, (), 17),
+}
+
+
+def gat_inputs(name: str):
+    kw, n, e, iso, seed = GAT_CASES[name]
+    g = torch.Generator().manual_seed(seed + 100)
+    x = torch.randn(n, kw["dim_node"], generator=g)
+    ef = torch.randn(e, kw["dim_edge"], generator=g)
+    return x, ef, gat_graph(seed, n, e, iso)
+
+
+# ---- SGFN twin ---------------------------------------------------------------------------------------
+GNN_CASE = dict(dim_node=512, dim_edge=256, dim_atten=256, num_layers=2, num_heads=8, aggr="max", DROP_OUT_ATTEN=0.5)
+
+
+def gnn_inputs():
+    b = synth.make_batch(3, [5, 3, 6], 16, None, seed=21)
+    g = torch.Generator().manual_seed(22)
+    n, e = b.descriptor.shape[0], b.edge_indices.shape[1]
+    return (torch.randn(n, 512, generator=g), torch.randn(e, 256, generator=g), b.edge_indices,
+            b.descriptor[:, :3].contiguous(), b.batch_ids)
+
+
+# ---- encoders / attention ----------------------------------------------------------------------------
+POINTNET_CASES = {
+    "pointnet_obj": (dict(point_size=3, out_size=768), 5, 100, 31),
+    "pointnet_big": (dict(point_size=3, out_size=768), 3, 257, 32),
+    "pointnet_rel": (dict(point_size=11, out_size=512), 37, 1, 33),
+    "pointnet_rgbn": (dict(point_size=9, out_size=256), 4, 64, 34),
+}
+
+
+def pointnet_inputs(name: str):
+    kw, n, p, seed = POINTNET_CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, kw["point_size"], p, generator=g)
+
+
+MHA_CASES = {"mha_h8": (512, 8, 70, 130, 41), "mha_h4": (512, 4, 33, 65, 42), "mha_self": (512, 8, 64, 64, 43)}
+
+
+def mha_inputs(name: str):
+    d, h, nq, nk, seed = MHA_CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(nq, d, generator=g)
+    kv = q if name == "mha_self" else torch.randn(nk, d, generator=g)
+    return q, kv
+
+
+def seeded_state(module: torch.nn.Module, seed: int):
+    return synth.make_state_dict({k: v.shape for k, v in module.state_dict().items()}, seed)
