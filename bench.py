@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py - scenes/s of the VL-SAT hot path (Mmgnet.forward) on synthetic scenes.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2]
+
+Workload (BASELINE.json configs[1]): 16 synthetic scenes x 40 objects x 256 points, 600 edges per scene
+(sum_N 640, sum_E 9600), mmgnet.json model (2 layers, 8 heads, 512/512/256), fp32 forward, eval mode.
+Under torchrun every rank runs its own 16-scene batch (scenes shard by batch: weak scaling, no
+data-path collective). One JSON line is printed by rank 0.
+
+  value    : scenes/s with the batch resident in HBM, CUDA events per step, L2 flushed between steps
+  e2e      : scenes/s through the public module API from pinned HOST buffers (H2D of the batch and D2H
+             of the four logit tensors inside the timed region, wall clock between device syncs)
+  roofline : dominant kernel of the step (CUDA events around each C-ABI launch in a separate pass)
+  cpu_baseline : the oracle port (plain PyTorch CPU restatement of the reference) on this box's cores
+
+--impl reference times the reference's own algorithm on the host cores (the oracle port: the reference is
+Python and is not present on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "scenes_per_sec_fwd"
+UNIT = "scenes/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower() == "active":
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_kwargs(name: str):
+    from vlsat_b200 import synth
+    return dict(synth.CONFIGS[name])
+
+
+def build_model(device):
+    import vlsat_b200 as V
+    from vlsat_b200 import synth
+    model = V.Mmgnet({"MODEL": V.DEFAULT_MODEL_CONFIG}, 160, 26)
+    synth.load_seeded(model, 0)
+    return model.to(device).eval()
+
+
+# -------------------------------------------------------------------------------------------- oracle arm
+def time_oracle(workload: str, steps: int, warmup: int, budget_s: float):
+    """Reference algorithm on the host cores (oracle port). Returns dict(value, cores, sample, ms_per_step)."""
+    import vlsat_b200 as V
+    from vlsat_b200 import synth
+    from oracle import vlsat_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = V.Mmgnet({"MODEL": V.DEFAULT_MODEL_CONFIG}, 160, 26)
+    synth.load_seeded(model, 0)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    kw = workload_kwargs(workload)
+    scenes = kw["num_scenes"]
+    batch = synth.make_batch(seed=100, **kw)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.mmgnet_forward(sd, *batch.forward_args())
+        first = time.perf_counter() - t0
+        total_steps = steps + max(warmup - 1, 0)
+        if first * total_steps > budget_s and scenes > 4:
+            # cross_attn_rel is O(sum_E^2): shrink the sample to a 4-scene batch of the same scene shape
+            scenes = 4
+            kw["num_scenes"] = 4
+            batch = synth.make_batch(seed=100, **kw)
+            O.mmgnet_forward(sd, *batch.forward_args())
+        for _ in range(max(warmup - 1, 0)):
+            O.mmgnet_forward(sd, *batch.forward_args())
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            O.mmgnet_forward(sd, *batch.forward_args())
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return dict(value=scenes / sec, cores=cores, ms_per_step=sec * 1e3, scenes=scenes,
+                sample=f"{scenes}-scene batch of the {workload} scene shape, {steps} timed forwards after {warmup} warm-up, "
+                       f"torch CPU fp32 with {cores} threads")
+
+
+# ---------------------------------------------------------------------------------------------- main arm
+def run_b200(args):
+    import torch.distributed as dist
+    import vlsat_b200 as V
+    from vlsat_b200 import ops, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    kw = workload_kwargs(args.workload)
+    scenes = kw["num_scenes"]
+    model = build_model(dev)
+    n_batches = 4
+    host = [synth.make_batch(seed=1 + rank * 100 + i, **kw).pin() for i in range(n_batches)]
+    resident = [b.to(dev) for b in host]
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)     # > 126 MB L2
+
+    def step(b):
+        with torch.no_grad():
+            return model(*b.forward_args(), istrain=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(resident[i % n_batches])
+    barrier()
+    # ---- device-resident timing: CUDA events per step, L2 flushed between steps ---------------------------
+    launches0 = ops.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clk:
+        for i in range(args.steps):
+            flush.zero_()
+            ev[i][0].record()
+            step(resident[i % n_batches])
+            ev[i][1].record()
+        barrier()
+    launches = ops.launch_count() - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * scenes * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the module API from pinned host buffers --------------------------------------
+    out_host = None
+    d2h_bytes = 0
+    for i in range(2):                       # warm the copy path
+        outs = step(host[i % n_batches].to(dev, non_blocking=True))
+        if out_host is None:
+            out_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+            d2h_bytes = sum(o.numel() * o.element_size() for o in outs)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        outs = step(host[i % n_batches].to(dev, non_blocking=True))
+        for o, h in zip(outs, out_host):
+            h.copy_(o, non_blocking=True)
+        torch.cuda.synchronize()             # the caller consumes the logits of this step
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = world * scenes * args.steps / e2e_s
+
+    # ---- per-kernel pass for the roofline (rank 0) ------------------------------------------------------
+    roofline, kernels = None, {}
+    if rank == 0:
+        timer = ops.KernelTimer()
+        ops.set_timer(timer)
+        for i in range(min(args.steps, 10)):
+            flush.zero_()
+            step(resident[i % n_batches])
+        torch.cuda.synchronize()
+        ops.set_timer(None)
+        summ = timer.summary()
+        step_ms = sum(d["ms"] for d in summ.values())
+        for name, d in sorted(summ.items(), key=lambda kv: -kv[1]["ms"]):
+            sec = d["ms"] * 1e-3
+            hbm_bound = name in ("vlsat_gat_edge_fwd", "vlsat_add_layernorm_fwd", "vlsat_relu_fwd", "vlsat_edge_descriptor_fwd",
+                                 "vlsat_row_l2norm_fwd", "vlsat_spatial_tail_fwd", "vlsat_build_csr", "vlsat_scene_ranges")
+            if hbm_bound:
+                ach, peak, unit = d["bytes"] / sec / 1e9, peaks["hbm"], "GB/s"
+            else:
+                ach, peak, unit = d["flops"] / sec / 1e12, peaks["tensor"], "TFLOP/s"
+            kernels[name] = dict(bound="hbm" if hbm_bound else "tensor", achieved=round(ach, 3), peak=peak, unit=unit,
+                                 frac=round(ach / peak, 5), share_of_step=round(d["ms"] / step_ms, 4),
+                                 us_per_launch=round(d["ms"] * 1e3 / d["launches"], 2),
+                                 launches_per_step=d["launches"] / min(args.steps, 10))
+        dom = next(iter(kernels))
+        roofline = dict(kernel=dom, **{k: kernels[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")},
+                        traffic=load_traffic(dom), peak_source=peaks["source"])
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = time_oracle(args.workload, steps=2, warmup=1, budget_s=30.0)
+        cpu = dict(value=round(r["value"], 4), unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"])
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {scenes} scenes/GPU x {kw['objects_per_scene']} obj x {kw['points_per_object']} pts, "
+                               f"{kw['edges_per_scene']} edges/scene, mmgnet.json model (L=2, H=8), fp32 forward (eval)",
+                   "global_scenes": world * scenes, "parallelism": f"scene-sharded x{world}, no data-path collective",
+                   "l2": "flushed between timed steps (256 MB write)", "gemm_engine": ops.gemm_engine()},
+        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": host[0].nbytes(), "d2h_bytes_per_step": d2h_bytes},
+        "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_traffic(kernel: str):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json), else null."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
+def run_reference(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = time_oracle(args.workload, steps=args.steps, warmup=max(args.warmup, 1), budget_s=240.0)
+    kw = workload_kwargs(args.workload)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(r["value"], 4), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {r['scenes']} scenes x {kw['objects_per_scene']} obj x {kw['points_per_object']} pts, "
+                               f"{kw['edges_per_scene']} edges/scene, mmgnet.json model, fp32 forward (eval), host CPU"},
+        "cpu_baseline": {"value": round(r["value"], 4), "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": round(r["value"], 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        import __graft_entry__ as g
+        g.build()
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

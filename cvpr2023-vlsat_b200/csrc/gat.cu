@@ -89,6 +89,9 @@ struct GatDims {
 
 __host__ __device__ inline int pad4(int x) { return ((x + 3) & ~3) + 4; }
 
+// WS = true: the shared per-head MLP weights are staged in shared memory (mmgnet.json dims: 80 KB);
+// WS = false: they are too large for it (e.g. 4 heads x 128 channels) and are read through L1/L2.
+template <bool WS>
 __global__ void __launch_bounds__(GAT_THREADS, 1)
 gat_edge_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ v, int64_t ldv,
                 const float* __restrict__ k, int64_t ldk, const int64_t* __restrict__ edge_index, const int32_t* __restrict__ row_ptr,
@@ -98,9 +101,19 @@ gat_edge_kernel(const float* __restrict__ q, int64_t ldq, const float* __restric
                 int64_t n_nodes, int64_t n_edges, GatDims g, int aggr, int use_edge,
                 float* __restrict__ xx, int64_t ld_xx, float* __restrict__ prob, int32_t* __restrict__ argmax) {
     extern __shared__ __align__(16) float sm[];
-    float* c1s = sm;                                   // [hid][s_c1]   C1 rows (K-major)
-    float* c2s = c1s + g.hid * g.s_c1;                 // [d_o][s_c2]
-    float* c1bs = c2s + g.d_o * g.s_c2;                // [hid]
+    const float* c1s;                                  // [hid][s_c1]   C1 rows (K-major)
+    const float* c2s;                                  // [d_o][s_c2]
+    float* c1bs;                                       // [hid]
+    if constexpr (WS) {
+        float* c1w = sm;
+        float* c2w = c1w + g.hid * g.s_c1;
+        c1bs = c2w + g.d_o * g.s_c2;
+        for (int i = threadIdx.x; i < g.hid * g.din; i += GAT_THREADS) c1w[(i / g.din) * g.s_c1 + (i % g.din)] = __ldg(c1 + i);
+        for (int i = threadIdx.x; i < g.d_o * g.hid; i += GAT_THREADS) c2w[(i / g.hid) * g.s_c2 + (i % g.hid)] = __ldg(c2 + i);
+        c1s = c1w; c2s = c2w;
+    } else {
+        c1s = c1; c2s = c2; c1bs = sm;
+    }
     float* c2bs = c1bs + g.hid;                        // [d_o]
     float* qt = c2bs + ((g.d_o + 3) & ~3);             // [H][s_q]      q of this node, de-interleaved
     float* qc = qt + g.H * g.s_q;                      // [H][hid]      C1q . q + c1 bias
@@ -110,9 +123,6 @@ gat_edge_kernel(const float* __restrict__ q, int64_t ldq, const float* __restric
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NW = GAT_THREADS / 32;
 
-    // stage the shared MLP weights once per (persistent) CTA
-    for (int i = tid; i < g.hid * g.din; i += GAT_THREADS) c1s[(i / g.din) * g.s_c1 + (i % g.din)] = __ldg(c1 + i);
-    for (int i = tid; i < g.d_o * g.hid; i += GAT_THREADS) c2s[(i / g.hid) * g.s_c2 + (i % g.hid)] = __ldg(c2 + i);
     for (int i = tid; i < g.hid; i += GAT_THREADS) c1bs[i] = __ldg(c1b + i);
     for (int i = tid; i < g.d_o; i += GAT_THREADS) c2bs[i] = __ldg(c2b + i);
 
@@ -286,14 +296,18 @@ extern "C" int vlsat_gat_edge_fwd(const float* q, int64_t ldq, const float* v, i
     g.H = n_heads; g.d_n = d_n; g.d_e = use_edge ? d_e : 0; g.d_o = d_o; g.hid = hid; g.din = d_n + g.d_e;
     g.D_n = n_heads * d_n; g.D_e = n_heads * g.d_e; g.D_a = n_heads * d_o;
     g.s_c1 = pad4(g.din); g.s_c2 = pad4(hid); g.s_q = pad4(d_n); g.s_k = pad4(g.d_e > 0 ? g.d_e : 4);
-    const size_t floats = (size_t)hid * g.s_c1 + (size_t)d_o * g.s_c2 + hid + ((d_o + 3) & ~3) + (size_t)g.H * g.s_q +
-                          (size_t)g.H * hid + (size_t)GAT_EB * g.H * g.s_k + (size_t)GAT_EB * g.H * hid + (size_t)GAT_EB * g.D_a;
-    const size_t smem = floats * sizeof(float);
+    const size_t work_floats = (size_t)hid + ((d_o + 3) & ~3) + (size_t)g.H * g.s_q + (size_t)g.H * hid +
+                               (size_t)GAT_EB * g.H * g.s_k + (size_t)GAT_EB * g.H * hid + (size_t)GAT_EB * g.D_a;
+    const size_t weight_floats = (size_t)hid * g.s_c1 + (size_t)d_o * g.s_c2;
+    const bool ws = (work_floats + weight_floats) * sizeof(float) <= 200 * 1024;
+    if (!ws) { g.s_c1 = g.din; g.s_c2 = hid; VLSAT_SUPPORT(((uintptr_t)c1 % 16 == 0) && ((uintptr_t)c2 % 16 == 0)); }
+    const size_t smem = (work_floats + (ws ? weight_floats : 0)) * sizeof(float);
     VLSAT_SUPPORT(smem <= 227 * 1024);
-    cudaFuncSetAttribute(gat_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = ws ? gat_edge_kernel<true> : gat_edge_kernel<false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t ctas_per_sm = std::max<int64_t>(1, (int64_t)(227 * 1024) / (int64_t)(smem + 1024));
     const unsigned grid = (unsigned)std::min<int64_t>(n_nodes, ctas_per_sm * kNumSMs);
-    gat_edge_kernel<<<grid, GAT_THREADS, smem, (cudaStream_t)stream>>>(
+    kern<<<grid, GAT_THREADS, smem, (cudaStream_t)stream>>>(
         q, ldq, v, ldv, k, ldk, edge_index, row_ptr, perm, c1, c1_bias, c2, c2_bias, n_nodes, n_edges, g, aggr, use_edge, xx, ld_xx, prob, argmax);
     return finish_launch();
 }

@@ -44,6 +44,43 @@ def _i64(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
+class KernelTimer:
+    """Optional per-entry-point CUDA-event timing (bench.py's roofline leg). Off by default."""
+
+    def __init__(self):
+        self.events = []          # (name, start, end, flops, bytes)
+
+    def summary(self):
+        """name -> dict(ms, launches, flops, bytes): totals over everything recorded."""
+        out = {}
+        for name, a, b, fl, by in self.events:
+            d = out.setdefault(name, dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
+            d["ms"] += a.elapsed_time(b); d["launches"] += 1; d["flops"] += fl; d["bytes"] += by
+        return out
+
+
+_timer: Optional[KernelTimer] = None
+
+
+def set_timer(t: Optional[KernelTimer]) -> None:
+    global _timer
+    _timer = t
+
+
+def _call(name: str, *args, work=(0.0, 0.0)):
+    """One C-ABI call. ``work`` = (algorithmic FLOPs, algorithmic HBM bytes) of this launch, used only
+    by the optional timer (definitions: DESIGN.md section 'Kernels and their rooflines')."""
+    fn = getattr(_lib.load(), name)
+    if _timer is None:
+        return fn(*args)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    st = fn(*args)
+    b.record()
+    _timer.events.append((name, a, b, float(work[0]), float(work[1])))
+    return st
+
+
 def launch_count() -> int:
     return int(_lib.load().vlsat_launch_count())
 
@@ -68,9 +105,10 @@ def pointnet(x, w1, b1, w2, b2, w3, b3, want_argmax: bool = False):
         raise ValueError("pointnet: weight shapes do not chain")
     out = torch.empty((n_obj, c_out), device=x.device, dtype=torch.float32)
     arg = torch.empty((n_obj, c_out), device=x.device, dtype=torch.int32) if want_argmax else None
-    st = _lib.load().vlsat_pointnet_fwd(x.data_ptr(), n_obj, c_in, n_pts, w1.data_ptr(), b1.data_ptr(), c1,
+    st = _call("vlsat_pointnet_fwd", x.data_ptr(), n_obj, c_in, n_pts, w1.data_ptr(), b1.data_ptr(), c1,
                                         w2.data_ptr(), b2.data_ptr(), c2, w3.data_ptr(), b3.data_ptr(), c_out,
-                                        out.data_ptr(), arg.data_ptr() if want_argmax else None, _stream())
+                                        out.data_ptr(), arg.data_ptr() if want_argmax else None, _stream(),
+               work=(2.0 * n_obj * n_pts * (c_in * c1 + c1 * c2 + c2 * c_out), 4.0 * (x.numel() + n_obj * c_out)))
     _lib.check(st, "vlsat_pointnet_fwd")
     return (out, arg) if want_argmax else out
 
@@ -84,7 +122,7 @@ def edge_descriptor(desc: torch.Tensor, edge_index: torch.Tensor) -> torch.Tenso
         raise ValueError("edge_descriptor: edge_index must be [2, E]")
     e = edge_index.shape[1]
     out = torch.empty((e, 11), device=desc.device, dtype=torch.float32)
-    _lib.check(_lib.load().vlsat_edge_descriptor_fwd(desc.data_ptr(), desc.shape[0], edge_index.data_ptr(), e,
+    _lib.check(_call("vlsat_edge_descriptor_fwd", desc.data_ptr(), desc.shape[0], edge_index.data_ptr(), e,
                                                      out.data_ptr(), _stream()), "vlsat_edge_descriptor_fwd")
     return out
 
@@ -132,7 +170,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if scale_ptr is not None:
         _f32(scale_ptr, "scale_ptr")
         epi.scale_ptr = scale_ptr.data_ptr()
-    st = _lib.load().vlsat_linear_fwd(xp, ldx, wp, ldw, yp, ldy, m, n, k, C.byref(epi), _stream())
+    st = _call("vlsat_linear_fwd", xp, ldx, wp, ldw, yp, ldy, m, n, k, C.byref(epi), _stream(),
+               work=(2.0 * m * n * k, 4.0 * (m * k + n * k + m * n)))
     _lib.check(st, "vlsat_linear_fwd")
     return out
 
@@ -150,7 +189,7 @@ def add_layernorm(x: torch.Tensor, res: Optional[torch.Tensor], gamma: torch.Ten
         out = torch.empty((m, d), device=x.device, dtype=torch.float32)
     yp, ldy = _rows(out, "out")
     _f32(gamma, "gamma"); _f32(beta, "beta")
-    st = _lib.load().vlsat_add_layernorm_fwd(xp, ldx, rp, ldr, gamma.data_ptr(), beta.data_ptr(), yp, ldy, m, d,
+    st = _call("vlsat_add_layernorm_fwd", xp, ldx, rp, ldr, gamma.data_ptr(), beta.data_ptr(), yp, ldy, m, d,
                                              eps, int(relu), _stream())
     _lib.check(st, "vlsat_add_layernorm_fwd")
     return out
@@ -162,7 +201,7 @@ def relu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         raise ValueError("relu: x must be contiguous")
     if out is None:
         out = torch.empty_like(x)
-    _lib.check(_lib.load().vlsat_relu_fwd(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "vlsat_relu_fwd")
+    _lib.check(_call("vlsat_relu_fwd", x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "vlsat_relu_fwd")
     return out
 
 
@@ -171,7 +210,7 @@ def row_l2norm(x: torch.Tensor) -> torch.Tensor:
     if x.dim() != 2 or not x.is_contiguous():
         raise ValueError("row_l2norm: x must be contiguous 2-D")
     out = torch.empty_like(x)
-    _lib.check(_lib.load().vlsat_row_l2norm_fwd(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream()),
+    _lib.check(_call("vlsat_row_l2norm_fwd", x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream()),
                "vlsat_row_l2norm_fwd")
     return out
 
@@ -181,7 +220,7 @@ def spatial_tail(desc: torch.Tensor, out: torch.Tensor, col0: int) -> None:
     op, ld = _rows(out, "out")
     if desc.shape[1] != 11 or not desc.is_contiguous() or out.shape[0] != desc.shape[0]:
         raise ValueError("spatial_tail: descriptor must be contiguous [N, 11] and out [N, >= col0 + 8]")
-    _lib.check(_lib.load().vlsat_spatial_tail_fwd(desc.data_ptr(), op, ld, col0, desc.shape[0], _stream()),
+    _lib.check(_call("vlsat_spatial_tail_fwd", desc.data_ptr(), op, ld, col0, desc.shape[0], _stream()),
                "vlsat_spatial_tail_fwd")
 
 
@@ -203,7 +242,7 @@ def scene_ranges(batch_ids: torch.Tensor):
     n = b.numel()
     seg = torch.empty((2, n), device=b.device, dtype=torch.int32)
     err = torch.zeros((1,), device=b.device, dtype=torch.int32)
-    _lib.check(_lib.load().vlsat_scene_ranges(b.data_ptr(), n, seg[0].data_ptr(), seg[1].data_ptr(), err.data_ptr(),
+    _lib.check(_call("vlsat_scene_ranges", b.data_ptr(), n, seg[0].data_ptr(), seg[1].data_ptr(), err.data_ptr(),
                                               _stream()), "vlsat_scene_ranges")
     return seg[0], seg[1], err
 
@@ -216,7 +255,7 @@ def node_attn(q, k, v, centres, seg_start, seg_end, fc_pack, n_heads: int) -> to
     if fc_pack.numel() != FC_PACK_HEAD + 33 * n_heads:
         raise ValueError("node_attn: packed self_attn_fc has the wrong size for this head count")
     out = torch.empty((n, d), device=q.device, dtype=torch.float32)
-    st = _lib.load().vlsat_node_attn_fwd(qp, ldq, kp, ldk, vp_, ldv, cp, ldc, seg_start.data_ptr(), seg_end.data_ptr(),
+    st = _call("vlsat_node_attn_fwd", qp, ldq, kp, ldk, vp_, ldv, cp, ldc, seg_start.data_ptr(), seg_end.data_ptr(),
                                          _f32(fc_pack, "fc_pack").data_ptr(), n_heads, dk, out.data_ptr(), d, n, _stream())
     _lib.check(st, "vlsat_node_attn_fwd")
     return out
@@ -229,8 +268,9 @@ def flash_attn(q, k, v, n_heads: int, want_lse: bool = False):
     dk = d // n_heads
     out = torch.empty((nq, d), device=q.device, dtype=torch.float32)
     lse = torch.empty((n_heads, nq), device=q.device, dtype=torch.float32) if want_lse else None
-    st = _lib.load().vlsat_flash_attn_fwd(qp, ldq, kp, ldk, vp_, ldv, out.data_ptr(), d,
-                                          lse.data_ptr() if want_lse else None, nq, nk, n_heads, dk, _stream())
+    st = _call("vlsat_flash_attn_fwd", qp, ldq, kp, ldk, vp_, ldv, out.data_ptr(), d,
+                                          lse.data_ptr() if want_lse else None, nq, nk, n_heads, dk, _stream(),
+               work=(4.0 * nq * nk * d, 4.0 * (2 * nq * d + 2 * nk * d)))
     _lib.check(st, "vlsat_flash_attn_fwd")
     return (out, lse) if want_lse else out
 
@@ -244,7 +284,7 @@ def build_csr(index_row: torch.Tensor, n_nodes: int):
     row_ptr = torch.empty((n_nodes + 1,), device=dev, dtype=torch.int32)
     perm = torch.empty((max(e, 1),), device=dev, dtype=torch.int32)
     ws = torch.empty((n_nodes + 1 + e,), device=dev, dtype=torch.int32)
-    st = _lib.load().vlsat_build_csr(index_row.data_ptr(), e, n_nodes, row_ptr.data_ptr(), perm.data_ptr(),
+    st = _call("vlsat_build_csr", index_row.data_ptr(), e, n_nodes, row_ptr.data_ptr(), perm.data_ptr(),
                                      ws.data_ptr(), ws.numel() * 4, _stream())
     _lib.check(st, "vlsat_build_csr")
     return row_ptr, perm[:e]
@@ -278,10 +318,13 @@ def gat_edge(q, v, k, edge_index, row_ptr, perm, c1, c1b, c2, c2b, n_heads: int,
     xp, ldxx = _rows(out, "out")
     prob = torch.empty((e, d_o, n_heads), device=q.device, dtype=torch.float32) if want_prob else None
     arg = torch.empty((n, d_a), device=q.device, dtype=torch.int32) if want_argmax else None
-    st = _lib.load().vlsat_gat_edge_fwd(qp, ldq, vp_, ldv, kp, ldk, edge_index.data_ptr(), row_ptr.data_ptr(),
+    st = _call("vlsat_gat_edge_fwd", qp, ldq, vp_, ldv, kp, ldk, edge_index.data_ptr(), row_ptr.data_ptr(),
                                         perm.data_ptr(), c1.data_ptr(), c1b.data_ptr(), c2.data_ptr(), c2b.data_ptr(),
                                         n, e, n_heads, d_n, d_e, d_o, hid, AGGR[aggr], int(use_edge), xp, ldxx,
                                         prob.data_ptr() if want_prob else None, arg.data_ptr() if want_argmax else None,
-                                        _stream())
+                                        _stream(),
+               # edge row + int64 index pair per edge; q, v read and xx written once per node
+               work=(2.0 * e * n_heads * (hid * (d_n + d_e) + d_o * hid),
+                     e * (n_heads * d_e * 4.0 + 16.0) + n * (n_heads * d_n + 2.0 * d_a) * 4.0))
     _lib.check(st, "vlsat_gat_edge_fwd")
     return out, prob, arg
