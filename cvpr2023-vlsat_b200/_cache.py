@@ -21,11 +21,26 @@ class DerivedCache:
             return hit[1]
         with torch.no_grad():
             val = build()
+            if hit is not None:
+                # refresh IN PLACE when shapes allow: stable addresses keep downstream caches (the tf32
+                # splits keyed on data_ptr + version) bounded during training.
+                val = _copy_into(hit[1], val)
         self._store[key] = (sig, val)
         return val
 
     def clear(self) -> None:
         self._store.clear()
+
+
+def _copy_into(old, new):
+    if isinstance(old, torch.Tensor) and isinstance(new, torch.Tensor):
+        if old.shape == new.shape and old.device == new.device and old.dtype == new.dtype:
+            old.copy_(new)
+            return old
+        return new
+    if isinstance(old, tuple) and isinstance(new, tuple) and len(old) == len(new):
+        return tuple(_copy_into(o, n) for o, n in zip(old, new))
+    return new
 
 
 def require_inference(module: torch.nn.Module, what: str) -> None:

@@ -18,7 +18,13 @@ class Epilogue(C.Structure):
     """Mirror of ``vlsat_epilogue`` (include/vlsat_b200.h)."""
     _fields_ = [("bias", vp), ("gather_a", vp), ("idx_a", vp), ("gather_b", vp), ("idx_b", vp),
                 ("ld_gather", i64), ("residual", vp), ("ld_res", i64), ("alpha", f32), ("beta", f32),
-                ("scale_ptr", vp), ("act", i32)]
+                ("scale_ptr", vp), ("act", i32), ("bias_per_row", i32)]
+
+
+class LinearOpts(C.Structure):
+    """Mirror of ``vlsat_linear_opts``."""
+    _fields_ = [("engine", i32), ("x_hi", vp), ("x_lo", vp), ("w_hi", vp), ("w_lo", vp), ("workspace", vp),
+                ("workspace_bytes", sz)]
 
 
 # name -> argtypes ; every function returns int status unless listed in _RESTYPES
@@ -29,7 +35,9 @@ SIGNATURES = {
     "vlsat_launch_count": [],
     "vlsat_pointnet_fwd": [vp, i64, i32, i64, vp, vp, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp],
     "vlsat_edge_descriptor_fwd": [vp, i64, vp, i64, vp, vp],
-    "vlsat_linear_fwd": [vp, i64, vp, i64, vp, i64, i64, i64, i64, C.POINTER(Epilogue), vp],
+    "vlsat_linear_fwd": [vp, i64, vp, i64, vp, i64, i64, i64, i64, C.POINTER(Epilogue), C.POINTER(LinearOpts), vp],
+    "vlsat_linear_workspace_bytes": [i64, i64, i64, i32, i32],
+    "vlsat_tf32_split": [vp, i64, i64, i64, vp, vp, vp],
     "vlsat_add_layernorm_fwd": [vp, i64, vp, i64, vp, vp, vp, i64, i64, i32, f32, i32, vp],
     "vlsat_relu_fwd": [vp, vp, i64, vp],
     "vlsat_row_l2norm_fwd": [vp, vp, i64, i32, vp],
@@ -37,11 +45,12 @@ SIGNATURES = {
     "vlsat_scene_ranges": [vp, i64, vp, vp, vp, vp],
     "vlsat_node_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, vp, i64, i64, vp],
     "vlsat_flash_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp],
+    "vlsat_flash_attn_tc_fwd": [vp, vp, i64, vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp],
     "vlsat_build_csr": [vp, i64, i64, vp, vp, vp, sz, vp],
     "vlsat_gat_edge_fwd": [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64,
                            i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, vp, vp],
 }
-_RESTYPES = {"vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
+_RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
 
 _lib = None
 

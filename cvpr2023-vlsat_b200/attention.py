@@ -108,8 +108,21 @@ class MultiHeadAttention(nn.Module):
     def attend_all(self, q_in, kv_in, relu: bool = False, out=None) -> torch.Tensor:
         """LN(q_in + fc_o(softmax(QK^T/sqrt(dk)) V)) over all keys, no mask/bias; 2-D inputs."""
         require_inference(self, "MultiHeadAttention")
-        q, k, v = self._project(q_in, kv_in, q_in is kv_in)
-        att = ops.flash_attn(q, k, v, self.attention.h)
+        a = self.attention
+        if a.d_k == 64 and ops.tensor_cores_enabled() and kv_in.shape[1] % 4 == 0 and kv_in.shape[1] >= 32:
+            # tensor-core path: Q, K row-major; the value projection is emitted transposed (V^T = W_v x^T)
+            nk = kv_in.shape[0]
+            q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach())
+            k = ops.linear(kv_in, a.fc_k.weight.detach(), a.fc_k.bias.detach())
+            vt = torch.empty((a.h * a.d_v, (nk + 3) // 4 * 4), device=q.device, dtype=torch.float32)
+            if vt.shape[1] != nk:
+                vt[:, nk:].zero_()
+            ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), out=vt[:, :nk], bias_per_row=True,
+                       x_is_weight=True)
+            att = ops.flash_attn_tc(q, k, vt, nk, a.h)
+        else:
+            q, k, v = self._project(q_in, kv_in, q_in is kv_in)
+            att = ops.flash_attn(q, k, v, a.h)
         return self._finish(q_in, att, relu, out)
 
     # ---- reference signature -----------------------------------------------------------------------

@@ -8,6 +8,13 @@ namespace vlsat {
 long long g_launch_count = 0;
 int linear_simt(const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int64_t, int64_t,
                 const vlsat_epilogue*, cudaStream_t);
+bool linear_tc_eligible(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t);
+size_t linear_tc_workspace_bytes(int64_t, int64_t, int64_t, bool, bool);
+int tf32_split(const float*, int64_t, int64_t, int64_t, float*, float*, cudaStream_t);
+int linear_tc(const float*, const float*, const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t,
+              const vlsat_epilogue*, int, cudaStream_t);
+int flash_attn_tc(const float*, const float*, int64_t, const float*, const float*, int64_t, const float*, const float*,
+                  int64_t, float*, int64_t, float*, int64_t, int64_t, int, int, cudaStream_t);
 int flash_attn_simt(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
                     int64_t, int64_t, int, int, cudaStream_t);
 }  // namespace vlsat
@@ -27,12 +34,25 @@ extern "C" const char* vlsat_error_string(int status) {
     }
 }
 
-extern "C" const char* vlsat_gemm_engine(void) { return "simt-fp32"; }
+extern "C" const char* vlsat_gemm_engine(void) { return "tcgen05-3xtf32 (ffma-fp32 for non-TMA shapes)"; }
 
 extern "C" int64_t vlsat_launch_count(void) { return g_launch_count; }
 
+extern "C" size_t vlsat_linear_workspace_bytes(int64_t M, int64_t N, int64_t K, int need_x_split, int need_w_split) {
+    return linear_tc_workspace_bytes(M, N, K, need_x_split != 0, need_w_split != 0);
+}
+
+extern "C" int vlsat_tf32_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, void* stream) {
+    VLSAT_REQUIRE(rows >= 0 && cols >= 0);
+    if (rows == 0 || cols == 0) return VLSAT_OK;
+    VLSAT_REQUIRE(x && hi && lo && ldx >= cols);
+    VLSAT_SUPPORT(cols % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)hi % 16 == 0) && ((uintptr_t)lo % 16 == 0));
+    return tf32_split(x, ldx, rows, cols, hi, lo, (cudaStream_t)stream);
+}
+
 extern "C" int vlsat_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, float* y, int64_t ldy,
-                                int64_t M, int64_t N, int64_t K, const vlsat_epilogue* epi, void* stream) {
+                                int64_t M, int64_t N, int64_t K, const vlsat_epilogue* epi,
+                                const vlsat_linear_opts* opts, void* stream) {
     VLSAT_REQUIRE(M >= 0 && N >= 1 && K >= 1);
     if (M == 0) return VLSAT_OK;
     VLSAT_REQUIRE(x && w && y && ldx >= K && ldw >= K && ldy >= N);
@@ -42,7 +62,33 @@ extern "C" int vlsat_linear_fwd(const float* x, int64_t ldx, const float* w, int
         VLSAT_REQUIRE(!(epi->gather_a || epi->gather_b) || epi->ld_gather >= N);
         VLSAT_REQUIRE(!epi->residual || epi->ld_res >= N);
     }
-    return linear_simt(x, ldx, w, ldw, y, ldy, M, N, K, epi, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int engine = opts ? opts->engine : VLSAT_ENGINE_AUTO;
+    VLSAT_REQUIRE(engine >= VLSAT_ENGINE_AUTO && engine <= VLSAT_ENGINE_TC_1PASS);
+    const bool eligible = linear_tc_eligible(x, ldx, w, ldw, M, N, K);
+    if (engine == VLSAT_ENGINE_SIMT || (engine == VLSAT_ENGINE_AUTO && (!eligible || !opts)))
+        return linear_simt(x, ldx, w, ldw, y, ldy, M, N, K, epi, st);
+    VLSAT_SUPPORT(eligible);
+    const int passes = engine == VLSAT_ENGINE_TC_1PASS ? 1 : 3;
+    const float *xh = opts->x_hi, *xl = opts->x_lo, *wh = opts->w_hi, *wl = opts->w_lo;
+    VLSAT_REQUIRE((xh == nullptr) == (xl == nullptr) && (wh == nullptr) == (wl == nullptr));
+    const size_t need = linear_tc_workspace_bytes(M, N, K, xh == nullptr, wh == nullptr);
+    if (need > 0 && (!opts->workspace || opts->workspace_bytes < need)) return VLSAT_ERR_WORKSPACE;
+    float* ws = (float*)opts->workspace;
+    if (need > 0) VLSAT_SUPPORT((uintptr_t)ws % 16 == 0);
+    if (!xh) {
+        float* h = ws; float* l = ws + M * K; ws += 2 * M * K;
+        int rc = tf32_split(x, ldx, M, K, h, l, st);
+        if (rc) return rc;
+        xh = h; xl = l;
+    }
+    if (!wh) {
+        float* h = ws; float* l = ws + N * K;
+        int rc = tf32_split(w, ldw, N, K, h, l, st);
+        if (rc) return rc;
+        wh = h; wl = l;
+    }
+    return linear_tc(xh, xl, wh, wl, y, ldy, M, N, K, epi, passes, st);
 }
 
 extern "C" int vlsat_flash_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
@@ -54,4 +100,19 @@ extern "C" int vlsat_flash_attn_fwd(const float* q, int64_t ldq, const float* k,
     VLSAT_SUPPORT(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0);
     VLSAT_SUPPORT(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) && ((uintptr_t)out % 16 == 0));
     return flash_attn_simt(q, ldq, k, ldk, v, ldv, out, ldo, lse, nq, nk, n_heads, dk, (cudaStream_t)stream);
+}
+
+extern "C" int vlsat_flash_attn_tc_fwd(const float* q_hi, const float* q_lo, int64_t ldq, const float* k_hi,
+                                       const float* k_lo, int64_t ldk, const float* vt_hi, const float* vt_lo,
+                                       int64_t ldvt, float* out, int64_t ldo, float* lse, int64_t nq, int64_t nk,
+                                       int n_heads, int dk, void* stream) {
+    VLSAT_REQUIRE(nq >= 0 && nk >= 1 && n_heads >= 1);
+    if (nq == 0) return VLSAT_OK;
+    VLSAT_REQUIRE(q_hi && q_lo && k_hi && k_lo && vt_hi && vt_lo && out);
+    VLSAT_REQUIRE(ldq >= (int64_t)n_heads * dk && ldk >= (int64_t)n_heads * dk && ldvt >= nk && ldo >= (int64_t)n_heads * dk);
+    const uintptr_t all = (uintptr_t)q_hi | (uintptr_t)q_lo | (uintptr_t)k_hi | (uintptr_t)k_lo | (uintptr_t)vt_hi |
+                          (uintptr_t)vt_lo | (uintptr_t)out;
+    VLSAT_SUPPORT(all % 16 == 0);
+    return flash_attn_tc(q_hi, q_lo, ldq, k_hi, k_lo, ldk, vt_hi, vt_lo, ldvt, out, ldo, lse, nq, nk, n_heads, dk,
+                         (cudaStream_t)stream);
 }

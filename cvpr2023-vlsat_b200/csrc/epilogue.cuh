@@ -1,0 +1,34 @@
+// Arguments and fused epilogue shared by the two dense-projection engines (FFMA and tcgen05).
+#pragma once
+#include "common.cuh"
+
+namespace vlsat {
+
+struct LinearArgs {
+    const float* x; int64_t ldx;
+    const float* w; int64_t ldw;
+    float* y; int64_t ldy;
+    int64_t M, N, K;
+    vlsat_epilogue epi;
+};
+
+__device__ __forceinline__ float apply_act(float t, int act) {
+    if (act == VLSAT_ACT_RELU) return fmaxf(t, 0.f);
+    if (act == VLSAT_ACT_SIGMOID) return 1.f / (1.f + expf(-t));
+    return t;
+}
+
+// Shared epilogue for one output element group; used by both GEMM engines.
+__device__ __forceinline__ float epilogue_one(const vlsat_epilogue& e, float acc, int64_t m, int64_t n,
+                                              int64_t ia, int64_t ib, float post_scale) {
+    float t = acc;
+    if (e.bias) t += __ldg(e.bias + (e.bias_per_row ? m : n));
+    if (e.gather_a) t += __ldg(e.gather_a + ia * e.ld_gather + n);
+    if (e.gather_b) t += __ldg(e.gather_b + ib * e.ld_gather + n);
+    t = apply_act(t, e.act);
+    if (e.residual) t = e.alpha * t + e.beta * __ldg(e.residual + m * e.ld_res + n);
+    else if (e.alpha != 1.f) t *= e.alpha;
+    return t * post_scale;
+}
+
+}  // namespace vlsat

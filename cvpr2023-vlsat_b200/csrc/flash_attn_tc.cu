@@ -1,0 +1,252 @@
+// A9 on the tensor cores: streaming softmax(Q K^T / sqrt(dk)) V for cross_attn_rel (network_MMG.py:231),
+// fp32-accurate through the same 3xTF32 operand split as the dense projections.
+//
+// One CTA = 128 queries of one head (dk = 64). KV tiles of 64 keys stream through a 2-stage TMA ring.
+//   warp 0     : TMA producer. Q (hi, lo) once; per tile K (hi, lo) as [64 keys x 64] K-major and
+//                V^T (hi, lo) as [64 dims x 64 keys] K-major (the value projection is produced transposed
+//                by the GEMM, so both MMAs use the plain K-major shared-memory descriptor).
+//   warp 1     : tcgen05.mma issue. S = Q K^T into TMEM (128 lanes x 64 cols); after the softmax warps
+//                have written P (hi, lo) back to TMEM, PV = P V^T^T with the A operand read from TMEM.
+//   warps 2..5 : one query row per thread: tcgen05.ld S, online softmax in the exp2 domain, split P into
+//                tf32 hi/lo, tcgen05.st to TMEM; then fold the tile's P.V into the fp32 row accumulator
+//                kept in registers (o = o * corr + pv), so no TMEM read-modify-write is needed.
+// TMEM columns: S [0,64) | P_hi [64,128) | P_lo [128,192) | PV [192,256).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <float.h>
+
+namespace vlsat {
+
+using namespace tc;
+
+constexpr int FT_BQ = 128, FT_BKV = 64, FT_DK = 64, FT_THREADS = 192, FT_STAGES = 2;
+constexpr int FT_Q_BYTES = 4 * FT_BQ * 128;              // Q_hi, Q_lo x two 32-float halves
+constexpr int FT_KV_STAGE = 8 * FT_BKV * 128;            // K_hi/lo + Vt_hi/lo, two halves each, 64 rows x 128 B
+constexpr uint32_t FT_TMEM_COLS = 256;
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]   (A operand read from tensor memory: one lane per row, one column per tf32)
+__device__ __forceinline__ void mma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 1)
+flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
+                     const __grid_constant__ CUtensorMap tm_khi, const __grid_constant__ CUtensorMap tm_klo,
+                     const __grid_constant__ CUtensorMap tm_vhi, const __grid_constant__ CUtensorMap tm_vlo,
+                     float* __restrict__ out, int64_t ldo, float* __restrict__ lse, int nq, int nk, float scale_log2e) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* q_smem = smem;                                  // [Q_hi h0 | Q_hi h1 | Q_lo h0 | Q_lo h1] x 16 KB
+    uint8_t* kv_smem = smem + FT_Q_BYTES;                    // stages x [K_hi h0,h1 | K_lo h0,h1 | Vt_hi k0,k1 | Vt_lo k0,k1] x 8 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + FT_STAGES * FT_KV_STAGE);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;                            // [STAGES]
+    uint64_t* kv_empty = kv_full + FT_STAGES;                // [STAGES]
+    uint64_t* s_full = kv_empty + FT_STAGES;
+    uint64_t* p_ready = s_full + 1;
+    uint64_t* pv_full = p_ready + 1;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = blockIdx.y;
+    const int q0 = blockIdx.x * FT_BQ;
+    const int n_tiles = (nk + FT_BKV - 1) / FT_BKV;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_qhi); prefetch_tmap(&tm_qlo); prefetch_tmap(&tm_khi);
+        prefetch_tmap(&tm_klo); prefetch_tmap(&tm_vhi); prefetch_tmap(&tm_vlo);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < FT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(p_ready, 128);
+        mbar_init(pv_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_holder, FT_TMEM_COLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t t_s = tmem_base, t_phi = tmem_base + 64, t_plo = tmem_base + 128, t_pv = tmem_base + 192;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, FT_Q_BYTES);
+            for (int h = 0; h < 2; ++h) {
+                tma_load_2d(q_smem + h * 16384, &tm_qhi, q_full, head * FT_DK + h * 32, q0);
+                tma_load_2d(q_smem + 32768 + h * 16384, &tm_qlo, q_full, head * FT_DK + h * 32, q0);
+            }
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t % FT_STAGES;
+                const uint32_t ph = (t / FT_STAGES) & 1;
+                mbar_wait(&kv_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], FT_KV_STAGE);
+                uint8_t* st = kv_smem + s * FT_KV_STAGE;
+                const int k0 = t * FT_BKV;
+                for (int h = 0; h < 2; ++h) {
+                    tma_load_2d(st + h * 8192, &tm_khi, &kv_full[s], head * FT_DK + h * 32, k0);              // K rows = keys
+                    tma_load_2d(st + 16384 + h * 8192, &tm_klo, &kv_full[s], head * FT_DK + h * 32, k0);
+                    tma_load_2d(st + 32768 + h * 8192, &tm_vhi, &kv_full[s], k0 + h * 32, head * FT_DK);      // V^T rows = dims
+                    tma_load_2d(st + 49152 + h * 8192, &tm_vlo, &kv_full[s], k0 + h * 32, head * FT_DK);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc<Kind::TF32>(FT_BQ, 64);
+            const uint32_t qa = smem_u32(q_smem);
+            auto issue_s = [&](int t) {
+                const int s = t % FT_STAGES;
+                mbar_wait(&kv_full[s], (t / FT_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t kb = smem_u32(kv_smem + s * FT_KV_STAGE);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {                 // 8 dims per MMA
+                    const uint32_t off_a = (kk >> 2) * 16384 + (kk & 3) * 32, off_b = (kk >> 2) * 8192 + (kk & 3) * 32;
+                    const uint64_t qh = make_sdesc_k128(qa + off_a), ql = make_sdesc_k128(qa + 32768 + off_a);
+                    const uint64_t kh = make_sdesc_k128(kb + off_b), kl = make_sdesc_k128(kb + 16384 + off_b);
+                    mma_ss<Kind::TF32>(t_s, ql, kh, idesc, kk > 0);
+                    mma_ss<Kind::TF32>(t_s, qh, kl, idesc, 1);
+                    mma_ss<Kind::TF32>(t_s, qh, kh, idesc, 1);
+                }
+                tc_commit(s_full);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t % FT_STAGES;
+                mbar_wait(p_ready, t & 1);                       // P(t) is in TMEM, S(t) has been consumed
+                tc_fence_after();
+                const uint32_t vb = smem_u32(kv_smem + s * FT_KV_STAGE + 32768);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {                 // 8 keys per MMA
+                    const uint32_t off_b = (kk >> 2) * 8192 + (kk & 3) * 32;
+                    const uint64_t vh = make_sdesc_k128(vb + off_b), vl = make_sdesc_k128(vb + 16384 + off_b);
+                    mma_ts_tf32(t_pv, t_plo + kk * 8, vh, idesc, kk > 0);
+                    mma_ts_tf32(t_pv, t_phi + kk * 8, vl, idesc, 1);
+                    mma_ts_tf32(t_pv, t_phi + kk * 8, vh, idesc, 1);
+                }
+                tc_commit(&kv_empty[s]);                         // K/V stage free once PV(t) retires
+                tc_commit(pv_full);
+                if (t + 1 < n_tiles) issue_s(t + 1);             // overlaps the softmax warps' rescale of tile t
+            }
+        }
+        __syncwarp();
+    } else {
+        const int qd = warp & 3;
+        const int row = q0 + qd * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        float o[FT_DK];
+#pragma unroll
+        for (int d = 0; d < FT_DK; ++d) o[d] = 0.f;
+        float m_run = -FLT_MAX, l_run = 0.f;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int k0 = t * FT_BKV;
+            mbar_wait(s_full, t & 1);
+            tc_fence_after();
+            uint32_t r[32], r2[32];
+            tmem_ld_32x32(t_s + lane_off, r);
+            tmem_ld_32x32(t_s + lane_off + 32, r2);
+            tmem_ld_wait();
+            float mx = -FLT_MAX;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float a = (k0 + j < nk) ? __uint_as_float(r[j]) * scale_log2e : -FLT_MAX;
+                float b = (k0 + 32 + j < nk) ? __uint_as_float(r2[j]) * scale_log2e : -FLT_MAX;
+                r[j] = __float_as_uint(a); r2[j] = __float_as_uint(b);
+                mx = fmaxf(mx, fmaxf(a, b));
+            }
+            const float m_new = fmaxf(m_run, mx);
+            const float corr = exp2f(m_run - m_new);
+            float rs = 0.f;
+            uint32_t lo[32];
+            // first half of the tile's keys
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float p = (k0 + j < nk) ? exp2f(__uint_as_float(r[j]) - m_new) : 0.f;
+                rs += p;
+                uint32_t h;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(p));
+                r[j] = h; lo[j] = __float_as_uint(p - __uint_as_float(h));
+            }
+            tmem_st_32x32(t_phi + lane_off, r);
+            tmem_st_32x32(t_plo + lane_off, lo);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float p = (k0 + 32 + j < nk) ? exp2f(__uint_as_float(r2[j]) - m_new) : 0.f;
+                rs += p;
+                uint32_t h;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(p));
+                r2[j] = h; lo[j] = __float_as_uint(p - __uint_as_float(h));
+            }
+            tmem_st_32x32(t_phi + lane_off + 32, r2);
+            tmem_st_32x32(t_plo + lane_off + 32, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(p_ready);
+            l_run = l_run * corr + rs;
+            m_run = m_new;
+            // fold P.V of this tile into the register accumulator
+            mbar_wait(pv_full, t & 1);
+            tc_fence_after();
+            tmem_ld_32x32(t_pv + lane_off, r);
+            tmem_ld_32x32(t_pv + lane_off + 32, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) {
+                o[d] = fmaf(o[d], corr, __uint_as_float(r[d]));
+                o[32 + d] = fmaf(o[32 + d], corr, __uint_as_float(r2[d]));
+            }
+            tc_fence_before();
+        }
+        if (row < nq) {
+            const float inv = 1.f / l_run;
+            float* orow = out + (int64_t)row * ldo + head * FT_DK;
+#pragma unroll
+            for (int d = 0; d < FT_DK; d += 4)
+                *reinterpret_cast<float4*>(orow + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+            if (lse) lse[(int64_t)head * nq + row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, FT_TMEM_COLS);
+}
+
+// q_hi/q_lo [nq, >= H*64] (row stride ldq), k_hi/k_lo [nk, ...] (ldk), vt_hi/vt_lo [H*64, nk] (row stride ldvt).
+int flash_attn_tc(const float* q_hi, const float* q_lo, int64_t ldq, const float* k_hi, const float* k_lo, int64_t ldk,
+                  const float* vt_hi, const float* vt_lo, int64_t ldvt, float* out, int64_t ldo, float* lse,
+                  int64_t nq, int64_t nk, int n_heads, int dk, cudaStream_t st) {
+    if (dk != FT_DK || nq >= (1ll << 31) || nk >= (1ll << 31)) return VLSAT_ERR_UNSUPPORTED;
+    if ((ldq | ldk | ldvt | ldo) % 4) return VLSAT_ERR_UNSUPPORTED;
+    CUtensorMap tq, tql, tk, tkl, tv, tvl;
+    const uint64_t d = (uint64_t)n_heads * dk;
+    const auto F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    bool ok = make_tmap_2d(&tq, q_hi, F32, 4, nq, d, ldq, 32, FT_BQ) && make_tmap_2d(&tql, q_lo, F32, 4, nq, d, ldq, 32, FT_BQ) &&
+              make_tmap_2d(&tk, k_hi, F32, 4, nk, d, ldk, 32, FT_BKV) && make_tmap_2d(&tkl, k_lo, F32, 4, nk, d, ldk, 32, FT_BKV) &&
+              make_tmap_2d(&tv, vt_hi, F32, 4, d, nk, ldvt, 32, FT_DK) && make_tmap_2d(&tvl, vt_lo, F32, 4, d, nk, ldvt, 32, FT_DK);
+    if (!ok) return VLSAT_ERR_UNSUPPORTED;
+    const size_t smem = FT_Q_BYTES + FT_STAGES * FT_KV_STAGE + 1024 + 256;
+    cudaFuncSetAttribute(flash_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((unsigned)ceil_div(nq, FT_BQ), (unsigned)n_heads);
+    const float scale_log2e = 1.4426950408889634f / sqrtf((float)dk);
+    flash_attn_tc_kernel<<<grid, FT_THREADS, smem, st>>>(tq, tql, tk, tkl, tv, tvl, out, ldo, lse, (int)nq, (int)nk, scale_log2e);
+    return finish_launch();
+}
+
+}  // namespace vlsat

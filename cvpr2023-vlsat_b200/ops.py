@@ -6,12 +6,13 @@ No wrapper has a CPU or PyTorch compute path: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
 
 from . import _lib
-from ._lib import Epilogue
+from ._lib import Epilogue, LinearOpts
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 AGGR = {"max": 0, "add": 1, "mean": 2}
@@ -128,15 +129,52 @@ def edge_descriptor(desc: torch.Tensor, edge_index: torch.Tensor) -> torch.Tenso
 
 
 # ------------------------------------------------------------------------------------- dense projection
+ENGINES = {"auto": 0, "simt": 1, "tc": 2, "tc1": 3}
+_engine = ENGINES[os.environ.get("VLSAT_GEMM_ENGINE", "auto")]
+_weight_splits = {}
+
+
+def set_gemm_engine(name: str) -> None:
+    """'auto' (tcgen05 3xTF32 where TMA-addressable, FFMA otherwise), 'simt' (exact fp32 FFMA everywhere),
+    'tc' (force tensor cores; ineligible shapes raise), 'tc1' (single-pass TF32, not fp32-accurate)."""
+    global _engine
+    _engine = ENGINES[name]
+
+
+def tensor_cores_enabled() -> bool:
+    return _engine != ENGINES["simt"]
+
+
+def _tc_eligible(x, ldx, w, ldw, n, k) -> bool:
+    return (k % 4 == 0 and k >= 32 and ldx % 4 == 0 and ldw % 4 == 0 and x.data_ptr() % 16 == 0
+            and w.data_ptr() % 16 == 0 and n >= 8)
+
+
+def _weight_split(w: torch.Tensor, ldw: int):
+    """tf32 hi/lo copies of a weight (view), cached until the parameter is written again."""
+    key = (w.data_ptr(), tuple(w.shape), ldw)
+    ent = _weight_splits.get(key)
+    if ent is not None and ent[0] == w._version:
+        return ent[1]
+    n, k = w.shape
+    hl = ent[1] if ent is not None else torch.empty((2, n, k), device=w.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_tf32_split", w.data_ptr(), ldw, n, k, hl[0].data_ptr(), hl[1].data_ptr(), _stream()),
+               "vlsat_tf32_split")
+    _weight_splits[key] = (w._version, hl, w)        # holding w keeps its storage (and this key) unique
+    return hl
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
            out: Optional[torch.Tensor] = None,
            gather: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]] = None,
            residual: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0,
-           scale_ptr: Optional[torch.Tensor] = None) -> torch.Tensor:
+           scale_ptr: Optional[torch.Tensor] = None, bias_per_row: bool = False,
+           x_is_weight: bool = False) -> torch.Tensor:
     """y = post(act(x w^T + bias + ga[ia] + gb[ib])), post(t) = (alpha t + beta residual) * exp(scale).
 
     x [M, K] and w [N, K] may be column-slice views (row stride = leading dimension); ``out`` may be a
-    column slice of a wider buffer."""
+    column slice of a wider buffer. ``x_is_weight=True`` swaps the roles for the tf32-split cache: x is
+    a parameter (split cached), w an activation (split per call) - used to emit y^T = W x^T."""
     xp, ldx = _rows(x, "x")
     wp, ldw = _rows(w, "w")
     m, k = x.shape
@@ -152,9 +190,10 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     epi.alpha, epi.beta, epi.act = alpha, beta, act
     if bias is not None:
         _f32(bias, "bias")
-        if bias.numel() != n or not bias.is_contiguous():
-            raise ValueError("linear: bias must be contiguous [N]")
+        if bias.numel() != (m if bias_per_row else n) or not bias.is_contiguous():
+            raise ValueError("linear: bias must be contiguous [N] (or [M] with bias_per_row)")
         epi.bias = bias.data_ptr()
+        epi.bias_per_row = int(bias_per_row)
     if gather is not None:
         ga, ia, gb, ib = gather
         gap, ldga = _rows(ga, "gather_a"); gbp, ldgb = _rows(gb, "gather_b")
@@ -170,7 +209,20 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if scale_ptr is not None:
         _f32(scale_ptr, "scale_ptr")
         epi.scale_ptr = scale_ptr.data_ptr()
-    st = _call("vlsat_linear_fwd", xp, ldx, wp, ldw, yp, ldy, m, n, k, C.byref(epi), _stream(),
+    opts = LinearOpts()
+    opts.engine = _engine
+    ws = None
+    if _engine != ENGINES["simt"] and m > 0 and _tc_eligible(x, ldx, w, ldw, n, k):
+        if x_is_weight:
+            hl = _weight_split(x, ldx)
+            opts.x_hi, opts.x_lo = hl[0].data_ptr(), hl[1].data_ptr()
+            ws = torch.empty((2 * n * k,), device=x.device, dtype=torch.float32)
+        else:
+            hl = _weight_split(w, ldw)
+            opts.w_hi, opts.w_lo = hl[0].data_ptr(), hl[1].data_ptr()
+            ws = torch.empty((2 * m * k,), device=x.device, dtype=torch.float32)
+        opts.workspace, opts.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    st = _call("vlsat_linear_fwd", xp, ldx, wp, ldw, yp, ldy, m, n, k, C.byref(epi), C.byref(opts), _stream(),
                work=(2.0 * m * n * k, 4.0 * (m * k + n * k + m * n)))
     _lib.check(st, "vlsat_linear_fwd")
     return out
@@ -272,6 +324,33 @@ def flash_attn(q, k, v, n_heads: int, want_lse: bool = False):
                                           lse.data_ptr() if want_lse else None, nq, nk, n_heads, dk, _stream(),
                work=(4.0 * nq * nk * d, 4.0 * (2 * nq * d + 2 * nk * d)))
     _lib.check(st, "vlsat_flash_attn_fwd")
+    return (out, lse) if want_lse else out
+
+
+def tf32_split(x: torch.Tensor):
+    """(hi, lo) with hi = tf32-rounded x and lo = x - hi, both compact [rows, cols]; cols % 4 == 0."""
+    xp, ldx = _rows(x, "x")
+    r, c = x.shape
+    hl = torch.empty((2, r, c), device=x.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_tf32_split", xp, ldx, r, c, hl[0].data_ptr(), hl[1].data_ptr(), _stream()), "vlsat_tf32_split")
+    return hl[0], hl[1]
+
+
+def flash_attn_tc(q, k, vt, nk: int, n_heads: int, want_lse: bool = False):
+    """Tensor-core streaming attention. q [nq, D], k [nk, D], vt [D, >= nk] = transposed values with a
+    row stride that is a multiple of 4 (column slices allowed); D = n_heads * 64."""
+    nq, d = q.shape
+    if d != n_heads * 64:
+        raise ValueError("flash_attn_tc needs head size 64")
+    qh, ql = tf32_split(q)
+    kh, kl = tf32_split(k)
+    vh, vl = tf32_split(vt)
+    out = torch.empty((nq, d), device=q.device, dtype=torch.float32)
+    lse = torch.empty((n_heads, nq), device=q.device, dtype=torch.float32) if want_lse else None
+    st = _call("vlsat_flash_attn_tc_fwd", qh.data_ptr(), ql.data_ptr(), d, kh.data_ptr(), kl.data_ptr(), d,
+               vh.data_ptr(), vl.data_ptr(), vt.shape[1], out.data_ptr(), d, lse.data_ptr() if want_lse else None,
+               nq, nk, n_heads, 64, _stream(), work=(4.0 * nq * nk * d, 4.0 * (2 * nq * d + 2 * nk * d)))
+    _lib.check(st, "vlsat_flash_attn_tc_fwd")
     return (out, lse) if want_lse else out
 
 

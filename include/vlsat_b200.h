@@ -82,11 +82,34 @@ typedef struct {
     float beta;
     const float* scale_ptr;   /* device scalar s: result *= expf(s); or NULL   */
     int act;                  /* VLSAT_ACT_*                                   */
+    int bias_per_row;         /* 1: bias is [M] and added per output ROW (used to emit y^T = w x^T) */
 } vlsat_epilogue;
+
+/* Engine selection. AUTO = tcgen05 3xTF32 (fp32-accurate split, see csrc/gemm_tc.cu) whenever the operands
+ * are TMA-addressable (K % 4 == 0, K >= 32, 16-byte aligned rows), else the exact-fp32 FFMA engine.
+ * TC forced on an ineligible shape returns VLSAT_ERR_UNSUPPORTED. TC_1PASS = plain TF32 (10-bit mantissa). */
+#define VLSAT_ENGINE_AUTO 0
+#define VLSAT_ENGINE_SIMT 1
+#define VLSAT_ENGINE_TC 2
+#define VLSAT_ENGINE_TC_1PASS 3
+
+typedef struct {
+    int engine;               /* VLSAT_ENGINE_*                                                        */
+    const float* x_hi;        /* optional pre-split activations, compact [M, K] (vlsat_tf32_split)     */
+    const float* x_lo;
+    const float* w_hi;        /* optional pre-split weights, compact [N, K] (cache them per parameter)  */
+    const float* w_lo;
+    void* workspace;          /* device scratch for the splits that were not supplied                  */
+    size_t workspace_bytes;   /* >= vlsat_linear_workspace_bytes(M, N, K, x_hi == NULL, w_hi == NULL)   */
+} vlsat_linear_opts;
 
 int vlsat_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw,
                      float* y, int64_t ldy, int64_t M, int64_t N, int64_t K,
-                     const vlsat_epilogue* epi, void* stream);
+                     const vlsat_epilogue* epi, const vlsat_linear_opts* opts, void* stream);
+size_t vlsat_linear_workspace_bytes(int64_t M, int64_t N, int64_t K, int need_x_split, int need_w_split);
+/* hi = tf32-rounded x (round to nearest), lo = x - hi; x [rows, cols] with row stride ldx, cols % 4 == 0,
+ * outputs compact [rows, cols]. */
+int vlsat_tf32_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, void* stream);
 
 /* LayerNorm(x + res) (attention.py:122-123; eps 1e-5), optional ReLU on the way out
  * (network_MMG.py:236-248 fused for the streams whose raw value is not needed). */
@@ -123,6 +146,16 @@ int vlsat_node_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk
 int vlsat_flash_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                          float* out, int64_t ldo, float* lse, int64_t nq, int64_t nk, int n_heads, int dk,
                          void* stream);
+
+/* Tensor-core engine of the same operation (3xTF32, fp32-accurate; dk must be 64): operands are the tf32
+ * hi/lo splits (vlsat_tf32_split) of Q [nq, H*64], K [nk, H*64] and of the TRANSPOSED value projection
+ * V^T [H*64, nk] (row stride ldvt, a multiple of 4), which the dense projection emits directly by swapping
+ * its operands (y^T = W_v x^T with bias_per_row). */
+int vlsat_flash_attn_tc_fwd(const float* q_hi, const float* q_lo, int64_t ldq,
+                            const float* k_hi, const float* k_lo, int64_t ldk,
+                            const float* vt_hi, const float* vt_lo, int64_t ldvt,
+                            float* out, int64_t ldo, float* lse, int64_t nq, int64_t nk, int n_heads, int dk,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * A8  graph attention layer core (network_MMG.py:34-41,96-104; network_util.py:50-73).

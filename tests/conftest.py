@@ -38,9 +38,17 @@ def golden():
     return load
 
 
-def assert_close(actual, expected, what="", rtol=RTOL, atol=ATOL):
+# Un-normalised feature tensors (values of either sign, crossing zero) are compared with an absolute floor
+# that scales with the tensor: |err| <= 1e-3 |ref| + 1e-4 max|ref|. The tcgen05 engine accumulates in fp32
+# with truncation, so its noise floor sits ~5x above the FFMA engine's (still ~2e-5 of the tensor scale).
+FEATURE_ATOL_SCALE = 1e-4
+
+
+def assert_close(actual, expected, what="", rtol=RTOL, atol=ATOL, atol_scale=None):
     actual = actual.detach().float().cpu()
     expected = expected.detach().float().cpu()
+    if atol_scale is not None and expected.numel():
+        atol = max(atol, atol_scale * expected.abs().max().item())
     assert actual.shape == expected.shape, f"{what}: shape {tuple(actual.shape)} vs {tuple(expected.shape)}"
     assert torch.isfinite(actual).all(), f"{what}: non-finite values"
     err = (actual - expected).abs()

@@ -43,8 +43,8 @@ def test_version_and_error_strings(lib):
 
 def test_argument_validation_without_a_gpu(lib):
     # null pointers / bad sizes are rejected before any launch, so these calls are safe on a CPU-only host
-    assert lib.vlsat_linear_fwd(None, 4, None, 4, None, 4, 2, 2, 4, None, None) == 1
-    assert lib.vlsat_linear_fwd(None, 4, None, 4, None, 4, 0, 2, 4, None, None) == 0      # empty batch is a no-op
+    assert lib.vlsat_linear_fwd(None, 4, None, 4, None, 4, 2, 2, 4, None, None, None) == 1
+    assert lib.vlsat_linear_fwd(None, 4, None, 4, None, 4, 0, 2, 4, None, None, None) == 0      # empty batch is a no-op
     assert lib.vlsat_pointnet_fwd(None, 1, 3, 8, None, None, 64, None, None, 128, None, None, 768, None, None, None) == 1
     assert lib.vlsat_build_csr(None, 5, 3, None, None, None, 0, None) == 1
     assert lib.vlsat_flash_attn_fwd(None, 512, None, 512, None, 512, None, 512, None, 0, 1, 8, 64, None) == 0
@@ -52,6 +52,6 @@ def test_argument_validation_without_a_gpu(lib):
 
 def test_struct_layout_matches_header():
     from vlsat_b200._lib import Epilogue
-    # 5 pointers, int64, pointer, int64, 2 floats, pointer, int (+pad) = 88 bytes on LP64
+    # 5 pointers, int64, pointer, int64, 2 floats, pointer, 2 ints = 88 bytes on LP64
     assert ctypes.sizeof(Epilogue) == 88
     assert Epilogue.alpha.offset == 64 and Epilogue.scale_ptr.offset == 72 and Epilogue.act.offset == 80
