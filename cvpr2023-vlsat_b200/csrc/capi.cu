@@ -19,7 +19,12 @@ int flash_attn_simt(const float*, int64_t, const float*, int64_t, const float*, 
                     int64_t, int64_t, int, int, cudaStream_t);
 }  // namespace vlsat
 
+namespace vlsat { extern long long* g_trace; }
 using namespace vlsat;
+
+// Debug only (not part of the public header): device buffer of >= 128 int64 that CTA (0,0) of the next
+// tensor-core GEMM launches fills with clock64 stamps; pass NULL to switch tracing off.
+extern "C" void vlsat_debug_set_trace(long long* device_buffer) { g_trace = device_buffer; }
 
 extern "C" int vlsat_version(void) { return 100; }
 

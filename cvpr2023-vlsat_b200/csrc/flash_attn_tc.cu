@@ -10,7 +10,8 @@
 //   warps 2..5 : one query row per thread: tcgen05.ld S, online softmax in the exp2 domain, split P into
 //                tf32 hi/lo, tcgen05.st to TMEM; then fold the tile's P.V into the fp32 row accumulator
 //                kept in registers (o = o * corr + pv), so no TMEM read-modify-write is needed.
-// TMEM columns: S [0,64) | P_hi [64,128) | P_lo [128,192) | PV [192,256).
+// S, P and the per-tile P.V accumulator are double-buffered in TMEM (512 columns), so the tensor pipe
+// computes S(t+1) while the softmax warps work on tile t, and the fold runs one tile behind.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <float.h>
@@ -21,8 +22,9 @@ using namespace tc;
 
 constexpr int FT_BQ = 128, FT_BKV = 64, FT_DK = 64, FT_THREADS = 192, FT_STAGES = 2;
 constexpr int FT_Q_BYTES = 4 * FT_BQ * 128;              // Q_hi, Q_lo x two 32-float halves
-constexpr int FT_KV_STAGE = 8 * FT_BKV * 128;            // K_hi/lo + Vt_hi/lo, two halves each, 64 rows x 128 B
-constexpr uint32_t FT_TMEM_COLS = 256;
+constexpr int FT_K_STAGE = 4 * FT_BKV * 128;             // K_hi h0,h1 | K_lo h0,h1   (64 rows x 128 B each)
+constexpr int FT_V_STAGE = 4 * FT_DK * 128;              // Vt_hi k0,k1 | Vt_lo k0,k1
+constexpr uint32_t FT_TMEM_COLS = 512;
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -44,6 +46,14 @@ __device__ __forceinline__ void mma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, ui
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// TMEM columns (all double-buffered by tile parity b = t & 1):
+//   S[b] = 64 b | P_hi[b] = 128 + 64 b | P_lo[b] = 256 + 64 b | PV[b] = 384 + 64 b
 __global__ void __launch_bounds__(FT_THREADS, 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
                      const __grid_constant__ CUtensorMap tm_khi, const __grid_constant__ CUtensorMap tm_klo,
@@ -52,15 +62,18 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* q_smem = smem;                                  // [Q_hi h0 | Q_hi h1 | Q_lo h0 | Q_lo h1] x 16 KB
-    uint8_t* kv_smem = smem + FT_Q_BYTES;                    // stages x [K_hi h0,h1 | K_lo h0,h1 | Vt_hi k0,k1 | Vt_lo k0,k1] x 8 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + FT_STAGES * FT_KV_STAGE);
+    uint8_t* k_smem = smem + FT_Q_BYTES;                     // stages x FT_K_STAGE
+    uint8_t* v_smem = k_smem + FT_STAGES * FT_K_STAGE;       // stages x FT_V_STAGE
+    uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + FT_STAGES * FT_V_STAGE);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;                            // [STAGES]
-    uint64_t* kv_empty = kv_full + FT_STAGES;                // [STAGES]
-    uint64_t* s_full = kv_empty + FT_STAGES;
-    uint64_t* p_ready = s_full + 1;
-    uint64_t* pv_full = p_ready + 1;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_full + 1);
+    uint64_t* k_full = bars + 1;                             // [2]
+    uint64_t* k_empty = bars + 3;                            // [2]
+    uint64_t* v_full = bars + 5;                             // [2]
+    uint64_t* v_empty = bars + 7;                            // [2]
+    uint64_t* s_full = bars + 9;                             // [2]
+    uint64_t* p_ready = bars + 11;                           // [2]
+    uint64_t* pv_full = bars + 13;                           // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
@@ -71,10 +84,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_co
         prefetch_tmap(&tm_qhi); prefetch_tmap(&tm_qlo); prefetch_tmap(&tm_khi);
         prefetch_tmap(&tm_klo); prefetch_tmap(&tm_vhi); prefetch_tmap(&tm_vlo);
         mbar_init(q_full, 1);
-        for (int s = 0; s < FT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        mbar_init(s_full, 1);
-        mbar_init(p_ready, 128);
-        mbar_init(pv_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+            mbar_init(&s_full[s], 1); mbar_init(&p_ready[s], 128); mbar_init(&pv_full[s], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_holder, FT_TMEM_COLS); tmem_relinquish(); }
@@ -82,71 +95,90 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const uint32_t t_s = tmem_base, t_phi = tmem_base + 64, t_plo = tmem_base + 128, t_pv = tmem_base + 192;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(q_full, FT_Q_BYTES);
             for (int h = 0; h < 2; ++h) {
                 tma_load_2d(q_smem + h * 16384, &tm_qhi, q_full, head * FT_DK + h * 32, q0);
                 tma_load_2d(q_smem + 32768 + h * 16384, &tm_qlo, q_full, head * FT_DK + h * 32, q0);
             }
-            for (int t = 0; t < n_tiles; ++t) {
-                const int s = t % FT_STAGES;
-                const uint32_t ph = (t / FT_STAGES) & 1;
-                mbar_wait(&kv_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&kv_full[s], FT_KV_STAGE);
-                uint8_t* st = kv_smem + s * FT_KV_STAGE;
-                const int k0 = t * FT_BKV;
-                for (int h = 0; h < 2; ++h) {
-                    tma_load_2d(st + h * 8192, &tm_khi, &kv_full[s], head * FT_DK + h * 32, k0);              // K rows = keys
-                    tma_load_2d(st + 16384 + h * 8192, &tm_klo, &kv_full[s], head * FT_DK + h * 32, k0);
-                    tma_load_2d(st + 32768 + h * 8192, &tm_vhi, &kv_full[s], k0 + h * 32, head * FT_DK);      // V^T rows = dims
-                    tma_load_2d(st + 49152 + h * 8192, &tm_vlo, &kv_full[s], k0 + h * 32, head * FT_DK);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc<Kind::TF32>(FT_BQ, 64);
-            const uint32_t qa = smem_u32(q_smem);
-            auto issue_s = [&](int t) {
-                const int s = t % FT_STAGES;
-                mbar_wait(&kv_full[s], (t / FT_STAGES) & 1);
-                tc_fence_after();
-                const uint32_t kb = smem_u32(kv_smem + s * FT_KV_STAGE);
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {                 // 8 dims per MMA
-                    const uint32_t off_a = (kk >> 2) * 16384 + (kk & 3) * 32, off_b = (kk >> 2) * 8192 + (kk & 3) * 32;
-                    const uint64_t qh = make_sdesc_k128(qa + off_a), ql = make_sdesc_k128(qa + 32768 + off_a);
-                    const uint64_t kh = make_sdesc_k128(kb + off_b), kl = make_sdesc_k128(kb + 16384 + off_b);
-                    mma_ss<Kind::TF32>(t_s, ql, kh, idesc, kk > 0);
-                    mma_ss<Kind::TF32>(t_s, qh, kl, idesc, 1);
-                    mma_ss<Kind::TF32>(t_s, qh, kh, idesc, 1);
-                }
-                tc_commit(s_full);
-            };
-            mbar_wait(q_full, 0);
-            issue_s(0);
-            for (int t = 0; t < n_tiles; ++t) {
-                const int s = t % FT_STAGES;
-                mbar_wait(p_ready, t & 1);                       // P(t) is in TMEM, S(t) has been consumed
-                tc_fence_after();
-                const uint32_t vb = smem_u32(kv_smem + s * FT_KV_STAGE + 32768);
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {                 // 8 keys per MMA
-                    const uint32_t off_b = (kk >> 2) * 8192 + (kk & 3) * 32;
-                    const uint64_t vh = make_sdesc_k128(vb + off_b), vl = make_sdesc_k128(vb + 16384 + off_b);
-                    mma_ts_tf32(t_pv, t_plo + kk * 8, vh, idesc, kk > 0);
-                    mma_ts_tf32(t_pv, t_phi + kk * 8, vl, idesc, 1);
-                    mma_ts_tf32(t_pv, t_phi + kk * 8, vh, idesc, 1);
-                }
-                tc_commit(&kv_empty[s]);                         // K/V stage free once PV(t) retires
-                tc_commit(pv_full);
-                if (t + 1 < n_tiles) issue_s(t + 1);             // overlaps the softmax warps' rescale of tile t
-            }
         }
         __syncwarp();
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s = t & 1;
+            const uint32_t ph = (t >> 1) & 1;
+            const int k0 = t * FT_BKV;
+            mbar_wait(&k_empty[s], ph ^ 1);
+            if (elect_one()) {
+                uint8_t* st = k_smem + s * FT_K_STAGE;
+                mbar_arrive_expect_tx(&k_full[s], FT_K_STAGE);
+                for (int h = 0; h < 2; ++h) {                   // K rows = keys, columns = this head's dims
+                    tma_load_2d(st + h * 8192, &tm_khi, &k_full[s], head * FT_DK + h * 32, k0);
+                    tma_load_2d(st + 16384 + h * 8192, &tm_klo, &k_full[s], head * FT_DK + h * 32, k0);
+                }
+            }
+            __syncwarp();
+            mbar_wait(&v_empty[s], ph ^ 1);
+            if (elect_one()) {
+                uint8_t* st = v_smem + s * FT_V_STAGE;
+                mbar_arrive_expect_tx(&v_full[s], FT_V_STAGE);
+                for (int h = 0; h < 2; ++h) {                   // V^T rows = dims, columns = keys
+                    tma_load_2d(st + h * 8192, &tm_vhi, &v_full[s], k0 + h * 32, head * FT_DK);
+                    tma_load_2d(st + 16384 + h * 8192, &tm_vlo, &v_full[s], k0 + h * 32, head * FT_DK);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc<Kind::TF32>(FT_BQ, 64);
+        const uint64_t dq = make_sdesc_k128(smem_u32(q_smem));
+        const uint64_t dk0 = make_sdesc_k128(smem_u32(k_smem));
+        const uint64_t dv0 = make_sdesc_k128(smem_u32(v_smem));
+        // S(t) = Q K(t)^T into S[t & 1]; releases the K stage when done
+        auto issue_s = [&](int t) {
+            const int s = t & 1;
+            mbar_wait(&k_full[s], (t >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t dk = dk0 + (uint64_t)(s * (FT_K_STAGE >> 4));
+                const uint32_t ts = tmem_base + 64 * s;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {                 // 8 dims per MMA
+                    const uint32_t oa = (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, ob = (kk >> 2) * (8192 >> 4) + (kk & 3) * 2;
+                    mma_ss<Kind::TF32>(ts, dq + (32768 >> 4) + oa, dk + ob, idesc, kk > 0);       // Q_lo K_hi
+                    mma_ss<Kind::TF32>(ts, dq + oa, dk + (16384 >> 4) + ob, idesc, 1);            // Q_hi K_lo
+                    mma_ss<Kind::TF32>(ts, dq + oa, dk + ob, idesc, 1);                           // Q_hi K_hi
+                }
+                tc_commit(&k_empty[s]);
+                tc_commit(&s_full[s]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_s(0);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s = t & 1;
+            const uint32_t ph = (t >> 1) & 1;
+            if (t + 1 < n_tiles) issue_s(t + 1);                 // runs while the softmax warps work on tile t
+            mbar_wait(&v_full[s], ph);
+            mbar_wait(&p_ready[s], ph);                          // P(t) is in TMEM
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t dv = dv0 + (uint64_t)(s * (FT_V_STAGE >> 4));
+                const uint32_t tphi = tmem_base + 128 + 64 * s, tplo = tmem_base + 256 + 64 * s, tpv = tmem_base + 384 + 64 * s;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {                 // 8 keys per MMA
+                    const uint32_t ob = (kk >> 2) * (8192 >> 4) + (kk & 3) * 2;
+                    mma_ts_tf32(tpv, tplo + kk * 8, dv + ob, idesc, kk > 0);                     // P_lo V_hi
+                    mma_ts_tf32(tpv, tphi + kk * 8, dv + (16384 >> 4) + ob, idesc, 1);          // P_hi V_lo
+                    mma_ts_tf32(tpv, tphi + kk * 8, dv + ob, idesc, 1);                         // P_hi V_hi
+                }
+                tc_commit(&v_empty[s]);
+                tc_commit(&pv_full[s]);
+            }
+            __syncwarp();
+        }
     } else {
         const int qd = warp & 3;
         const int row = q0 + qd * 32 + lane;
@@ -154,58 +186,15 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_co
         float o[FT_DK];
 #pragma unroll
         for (int d = 0; d < FT_DK; ++d) o[d] = 0.f;
-        float m_run = -FLT_MAX, l_run = 0.f;
-        for (int t = 0; t < n_tiles; ++t) {
-            const int k0 = t * FT_BKV;
-            mbar_wait(s_full, t & 1);
+        float m_run = -FLT_MAX, l_run = 0.f, corr_prev = 1.f;
+        uint32_t r[32], r2[32], lo[32];
+        // o <- o * corr + P(t) V(t), one tile behind the softmax so the MMA pipe never waits for it
+        auto fold = [&](int t, float corr) {
+            const int s = t & 1;
+            mbar_wait(&pv_full[s], (t >> 1) & 1);
             tc_fence_after();
-            uint32_t r[32], r2[32];
-            tmem_ld_32x32(t_s + lane_off, r);
-            tmem_ld_32x32(t_s + lane_off + 32, r2);
-            tmem_ld_wait();
-            float mx = -FLT_MAX;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float a = (k0 + j < nk) ? __uint_as_float(r[j]) * scale_log2e : -FLT_MAX;
-                float b = (k0 + 32 + j < nk) ? __uint_as_float(r2[j]) * scale_log2e : -FLT_MAX;
-                r[j] = __float_as_uint(a); r2[j] = __float_as_uint(b);
-                mx = fmaxf(mx, fmaxf(a, b));
-            }
-            const float m_new = fmaxf(m_run, mx);
-            const float corr = exp2f(m_run - m_new);
-            float rs = 0.f;
-            uint32_t lo[32];
-            // first half of the tile's keys
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float p = (k0 + j < nk) ? exp2f(__uint_as_float(r[j]) - m_new) : 0.f;
-                rs += p;
-                uint32_t h;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(p));
-                r[j] = h; lo[j] = __float_as_uint(p - __uint_as_float(h));
-            }
-            tmem_st_32x32(t_phi + lane_off, r);
-            tmem_st_32x32(t_plo + lane_off, lo);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float p = (k0 + 32 + j < nk) ? exp2f(__uint_as_float(r2[j]) - m_new) : 0.f;
-                rs += p;
-                uint32_t h;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(p));
-                r2[j] = h; lo[j] = __float_as_uint(p - __uint_as_float(h));
-            }
-            tmem_st_32x32(t_phi + lane_off + 32, r2);
-            tmem_st_32x32(t_plo + lane_off + 32, lo);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(p_ready);
-            l_run = l_run * corr + rs;
-            m_run = m_new;
-            // fold P.V of this tile into the register accumulator
-            mbar_wait(pv_full, t & 1);
-            tc_fence_after();
-            tmem_ld_32x32(t_pv + lane_off, r);
-            tmem_ld_32x32(t_pv + lane_off + 32, r2);
+            tmem_ld_32x32(tmem_base + 384 + 64 * s + lane_off, r);
+            tmem_ld_32x32(tmem_base + 384 + 64 * s + lane_off + 32, r2);
             tmem_ld_wait();
 #pragma unroll
             for (int d = 0; d < 32; ++d) {
@@ -213,7 +202,59 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_co
                 o[32 + d] = fmaf(o[32 + d], corr, __uint_as_float(r2[d]));
             }
             tc_fence_before();
+        };
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s = t & 1;
+            const int k0 = t * FT_BKV;
+            mbar_wait(&s_full[s], (t >> 1) & 1);
+            tc_fence_after();
+            tmem_ld_32x32(tmem_base + 64 * s + lane_off, r);
+            tmem_ld_32x32(tmem_base + 64 * s + lane_off + 32, r2);
+            tmem_ld_wait();
+            const bool tail = k0 + FT_BKV > nk;                  // only the last tile can be ragged
+            float mx = -FLT_MAX;
+            if (tail) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (k0 + j >= nk) r[j] = __float_as_uint(-FLT_MAX);
+                    if (k0 + 32 + j >= nk) r2[j] = __float_as_uint(-FLT_MAX);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+            const float m_new = fmaxf(m_run, mx * scale_log2e);  // scale > 0 commutes with max
+            const float corr = ex2(m_run - m_new);
+            const float neg_m = -m_new;
+            float rs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float p = ex2(fmaf(__uint_as_float(r[j]), scale_log2e, neg_m));
+                rs += p;
+                uint32_t h;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(p));
+                r[j] = h; lo[j] = __float_as_uint(p - __uint_as_float(h));
+            }
+            tmem_st_32x32(tmem_base + 128 + 64 * s + lane_off, r);
+            tmem_st_32x32(tmem_base + 256 + 64 * s + lane_off, lo);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float p = ex2(fmaf(__uint_as_float(r2[j]), scale_log2e, neg_m));
+                rs += p;
+                uint32_t h;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(p));
+                r2[j] = h; lo[j] = __float_as_uint(p - __uint_as_float(h));
+            }
+            tmem_st_32x32(tmem_base + 128 + 64 * s + lane_off + 32, r2);
+            tmem_st_32x32(tmem_base + 256 + 64 * s + lane_off + 32, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_ready[s]);
+            l_run = l_run * corr + rs;
+            m_run = m_new;
+            if (t > 0) fold(t - 1, corr_prev);
+            corr_prev = corr;
         }
+        fold(n_tiles - 1, corr_prev);
         if (row < nq) {
             const float inv = 1.f / l_run;
             float* orow = out + (int64_t)row * ldo + head * FT_DK;
@@ -241,7 +282,7 @@ int flash_attn_tc(const float* q_hi, const float* q_lo, int64_t ldq, const float
               make_tmap_2d(&tk, k_hi, F32, 4, nk, d, ldk, 32, FT_BKV) && make_tmap_2d(&tkl, k_lo, F32, 4, nk, d, ldk, 32, FT_BKV) &&
               make_tmap_2d(&tv, vt_hi, F32, 4, d, nk, ldvt, 32, FT_DK) && make_tmap_2d(&tvl, vt_lo, F32, 4, d, nk, ldvt, 32, FT_DK);
     if (!ok) return VLSAT_ERR_UNSUPPORTED;
-    const size_t smem = FT_Q_BYTES + FT_STAGES * FT_KV_STAGE + 1024 + 256;
+    const size_t smem = FT_Q_BYTES + FT_STAGES * (FT_K_STAGE + FT_V_STAGE) + 1024 + 256;
     cudaFuncSetAttribute(flash_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((unsigned)ceil_div(nq, FT_BQ), (unsigned)n_heads);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)dk);

@@ -20,6 +20,8 @@ namespace vlsat {
 
 using namespace tc;
 
+__device__ __forceinline__ long long gtime() { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); return (long long)g; }
+
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                 // fp32 elements per K block = 128 bytes
 constexpr int TC_THREADS = 192;
@@ -61,6 +63,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+    long long* trace = (blockIdx.x == 0 && blockIdx.y == 0) ? a.trace : nullptr;
+    if (trace && threadIdx.x == 0) trace[0] = clock64();
+    const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+    if (a.trace && threadIdx.x == 0 && cta_lin < 600) {
+        unsigned long long gt; unsigned smid;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        a.trace[128 + 3 * cta_lin] = (long long)gt; a.trace[128 + 3 * cta_lin + 2] = smid;
+    }
     const int num_kb = (int)((a.K + TC_BK - 1) / TC_BK);
 
     auto a_hi = [&](int s) { return smem + s * STAGE_BYTES; };
@@ -80,13 +91,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    if (trace && threadIdx.x == 0) { trace[1] = clock64(); trace[100] = gtime(); }
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
+        // warp-uniform loop; one elected lane issues (keeps the TMA / MMA issue on the uniform datapath
+        // without per-instruction divergence handling)
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            if (trace && lane == 0 && kb < 40) trace[8 + 3 * kb] = clock64();
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                 tma_load_2d(a_hi(s), &tm_ahi, &full_bar[s], kb * TC_BK, m0);
                 tma_load_2d(b_hi(s), &tm_bhi, &full_bar[s], kb * TC_BK, n0);
@@ -95,76 +110,144 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                     tma_load_2d(b_lo(s), &tm_blo, &full_bar[s], kb * TC_BK, n0);
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc<Kind::TF32>(TC_BM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t ah = smem_u32(a_hi(s)), bh = smem_u32(b_hi(s));
-                const uint32_t al = smem_u32(a_lo(s)), bl = smem_u32(b_lo(s));
+        constexpr uint32_t idesc = make_idesc<Kind::TF32>(TC_BM, BN);
+        // descriptors differ only in the 14-bit start-address field: build one, then add offsets (>>4)
+        const uint64_t desc0 = make_sdesc_k128(smem_u32(smem));
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (trace && lane == 0 && kb < 40) { trace[8 + 3 * kb + 1] = clock64(); if (kb == 0) trace[101] = gtime(); if (kb == num_kb - 1) trace[102] = gtime(); }
+            if (elect_one()) {
+                const uint64_t dah = desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
+                const uint64_t dbh = dah + (TC_A_TILE >> 4);
+                const uint64_t dal = dah + ((TC_A_TILE + B_TILE) >> 4);
+                const uint64_t dbl = dah + ((2 * TC_A_TILE + B_TILE) >> 4);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {           // UMMA_K = 8 for tf32 (32 bytes)
-                    const uint64_t dah = make_sdesc_k128(ah + k * 32), dbh = make_sdesc_k128(bh + k * 32);
+                for (int k = 0; k < TC_BK / 8; ++k) {           // UMMA_K = 8 for tf32 (32 bytes = 2 x 16 B)
+                    const uint32_t acc = (k > 0) ? 1u : (kb > 0 ? 1u : 0u);
                     if (PASSES == 3) {
-                        const uint64_t dal = make_sdesc_k128(al + k * 32), dbl = make_sdesc_k128(bl + k * 32);
                         // small terms first, then the leading product
-                        mma_ss<Kind::TF32>(tmem_base, dal, dbh, idesc, (kb | k) > 0);
-                        mma_ss<Kind::TF32>(tmem_base, dah, dbl, idesc, 1);
-                        mma_ss<Kind::TF32>(tmem_base, dah, dbh, idesc, 1);
+                        mma_ss<Kind::TF32>(tmem_base, dal + 2 * k, dbh + 2 * k, idesc, acc);
+                        mma_ss<Kind::TF32>(tmem_base, dah + 2 * k, dbl + 2 * k, idesc, 1);
+                        mma_ss<Kind::TF32>(tmem_base, dah + 2 * k, dbh + 2 * k, idesc, 1);
                     } else {
-                        mma_ss<Kind::TF32>(tmem_base, dah, dbh, idesc, (kb | k) > 0);
+                        mma_ss<Kind::TF32>(tmem_base, dah + 2 * k, dbh + 2 * k, idesc, acc);
                     }
                 }
                 tc_commit(&empty_bar[s]);                        // stage reusable once these MMAs retire
             }
-            tc_commit(accum_bar);                                // accumulator complete
+            __syncwarp();
+            if (trace && lane == 0 && kb < 40) trace[8 + 3 * kb + 2] = clock64();
         }
+        if (elect_one()) tc_commit(accum_bar);                   // accumulator complete
         __syncwarp();
     } else {
         const int q = warp & 3;                                  // TMEM lane quarter owned by this warp
         const int64_t m = (int64_t)m0 + q * 32 + lane;
         mbar_wait(accum_bar, 0);
         tc_fence_after();
+        if (trace && threadIdx.x == 64) { trace[2] = clock64(); trace[103] = gtime(); }
         const bool row_ok = m < a.M;
         const int64_t ia = (row_ok && a.epi.gather_a) ? a.epi.idx_a[m] : 0;
         const int64_t ib = (row_ok && a.epi.gather_b) ? a.epi.idx_b[m] : 0;
         const float post_scale = a.epi.scale_ptr ? expf(__ldg(a.epi.scale_ptr)) : 1.f;
-        const bool vec_ok = (a.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0);
+        const vlsat_epilogue& e = a.epi;
+        auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+        // fully vectorised epilogue when every operand row is 16-byte addressable
+        const bool vec_ok = (a.ldy % 4 == 0) && al16(a.y) && (n0 % 4 == 0) &&
+                            (!e.bias || e.bias_per_row || al16(e.bias)) &&
+                            (!(e.gather_a || e.gather_b) || (e.ld_gather % 4 == 0 && al16(e.gather_a) && al16(e.gather_b))) &&
+                            (!e.residual || (e.ld_res % 4 == 0 && al16(e.residual)));
+        const float row_bias = (row_ok && e.bias && e.bias_per_row) ? __ldg(e.bias + m) : 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             if (n0 + c0 >= a.N) break;                           // warp-uniform
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             tmem_ld_wait();
-            if (row_ok) {
-                float* yrow = a.y + m * a.ldy + n0 + c0;
-                if (vec_ok && n0 + c0 + 32 <= a.N) {
+            if (!row_ok) continue;
+            const int64_t nb = n0 + c0;
+            float* yrow = a.y + m * a.ldy + nb;
+            if (vec_ok && nb + 32 <= a.N) {
+                // every branch below is warp-uniform and sits OUTSIDE the element loops, so the sigmoid's
+                // exp/divide are never executed (or if-converted) on the ReLU / identity paths
+                float t[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o;
-                        o.x = epilogue_one(a.epi, __uint_as_float(r[j + 0]), m, n0 + c0 + j + 0, ia, ib, post_scale);
-                        o.y = epilogue_one(a.epi, __uint_as_float(r[j + 1]), m, n0 + c0 + j + 1, ia, ib, post_scale);
-                        o.z = epilogue_one(a.epi, __uint_as_float(r[j + 2]), m, n0 + c0 + j + 2, ia, ib, post_scale);
-                        o.w = epilogue_one(a.epi, __uint_as_float(r[j + 3]), m, n0 + c0 + j + 3, ia, ib, post_scale);
-                        *reinterpret_cast<float4*>(yrow + j) = o;
+                for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(r[j]);
+                if (e.bias) {
+                    if (e.bias_per_row) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) t[j] += row_bias;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + nb + j));
+                            t[j] += b.x; t[j + 1] += b.y; t[j + 2] += b.z; t[j + 3] += b.w;
+                        }
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + c0 + j < a.N)
-                            yrow[j] = epilogue_one(a.epi, __uint_as_float(r[j]), m, n0 + c0 + j, ia, ib, post_scale);
                 }
+                if (e.gather_a) {
+                    const float4* ga = reinterpret_cast<const float4*>(e.gather_a + ia * e.ld_gather + nb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const float4 g = __ldg(ga + j); t[4 * j] += g.x; t[4 * j + 1] += g.y; t[4 * j + 2] += g.z; t[4 * j + 3] += g.w; }
+                }
+                if (e.gather_b) {
+                    const float4* gb = reinterpret_cast<const float4*>(e.gather_b + ib * e.ld_gather + nb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const float4 g = __ldg(gb + j); t[4 * j] += g.x; t[4 * j + 1] += g.y; t[4 * j + 2] += g.z; t[4 * j + 3] += g.w; }
+                }
+                if (e.act == VLSAT_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t[j] = fmaxf(t[j], 0.f);
+                } else if (e.act == VLSAT_ACT_SIGMOID) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t[j] = 1.f / (1.f + expf(-t[j]));
+                }
+                if (e.residual) {
+                    const float4* rr = reinterpret_cast<const float4*>(e.residual + m * e.ld_res + nb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 g = __ldg(rr + j);
+                        t[4 * j] = e.alpha * t[4 * j] + e.beta * g.x; t[4 * j + 1] = e.alpha * t[4 * j + 1] + e.beta * g.y;
+                        t[4 * j + 2] = e.alpha * t[4 * j + 2] + e.beta * g.z; t[4 * j + 3] = e.alpha * t[4 * j + 3] + e.beta * g.w;
+                    }
+                } else if (e.alpha != 1.f) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t[j] *= e.alpha;
+                }
+                if (e.scale_ptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t[j] *= post_scale;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(yrow + j) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
+            } else {
+#pragma unroll 4
+                for (int j = 0; j < 32; ++j)
+                    if (nb + j < a.N)
+                        yrow[j] = epilogue_one(e, __uint_as_float(r[j]), m, nb + j, ia, ib, post_scale);
             }
         }
     }
+    if (trace && threadIdx.x == 64) trace[104] = gtime();
     tc_fence_before();
     __syncthreads();
+    if (trace && threadIdx.x == 0) { trace[3] = clock64(); trace[105] = gtime(); }
+    if (a.trace && threadIdx.x == 0 && cta_lin < 600) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        a.trace[128 + 3 * cta_lin + 1] = (long long)gt;
+    }
     if (warp == 1) tmem_dealloc(tmem_base, BN);
 }
+
+long long* g_trace = nullptr;
 
 bool linear_tc_eligible(const float* x, int64_t ldx, const float* w, int64_t ldw, int64_t M, int64_t N, int64_t K) {
     return (K % 4 == 0) && K >= 32 && (ldx % 4 == 0) && (ldw % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
@@ -201,6 +284,7 @@ int linear_tc(const float* x_hi, const float* x_lo, const float* w_hi, const flo
     a.x = x_hi; a.ldx = K; a.w = w_hi; a.ldw = K; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.K = K;
     if (epi) a.epi = *epi;
     else { a.epi = vlsat_epilogue{}; a.epi.alpha = 1.f; }
+    a.trace = g_trace;
     const int bn = (N <= 64) ? 64 : 128;
     CUtensorMap ta, tal, tb, tbl;
     bool ok = make_tmap_2d(&ta, x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, K, K, TC_BK, TC_BM) &&
