@@ -72,13 +72,24 @@ class GraphContext:
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
             raise TypeError("edge_index must be an int64 [2, E] tensor (PyG MessagePassing contract)")
         i, _ = _flow_rows(flow)
-        ei = edge_index if i == 0 else edge_index.flip(0)
-        self.edge_index = ei.contiguous()
+        ei = (edge_index if i == 0 else edge_index.flip(0)).contiguous()
         self.num_nodes = num_nodes
         self.num_edges = ei.shape[1]
+        # perm[i] = original id of the i-th edge in source-sorted (CSR) order (stable). Every per-edge tensor
+        # is processed in that order (``to_sorted`` / ``to_original``): all per-edge maths is row-wise and the
+        # edge cross-attention is permutation-equivariant, so this is exact - and it is the identity for the
+        # reference's own data, whose edge lists are always grouped by subject (dataset_3dssg.py:263-266).
+        self.row_ptr, self.perm = ops.build_csr(ei[0], num_nodes)
+        self.edge_index = ops.permute_edges(ei, self.perm) if self.num_edges else ei
         self.src = self.edge_index[0]
         self.dst = self.edge_index[1]
-        self.row_ptr, self.perm = ops.build_csr(self.src, num_nodes)
+        self.identity = torch.arange(self.num_edges, device=ei.device, dtype=torch.int32)
+
+    def to_sorted(self, edge_rows: torch.Tensor) -> torch.Tensor:
+        return ops.permute_rows(edge_rows, self.perm, gather=True) if self.num_edges else edge_rows
+
+    def to_original(self, edge_rows: torch.Tensor) -> torch.Tensor:
+        return ops.permute_rows(edge_rows, self.perm, gather=False) if self.num_edges else edge_rows
 
 
 class Gen_Index(nn.Module):
@@ -160,12 +171,68 @@ class MultiHeadedEdgeAttention(nn.Module):
             return w, b
         return self._cache.get("node", (wq.weight, wq.bias, wv.weight, wv.bias, w1.weight), build)
 
+    def tc_weights(self):
+        """Head-major derived weights of the tensor-core edge kernel (csrc/gat_tc.cu):
+        node projection  [W_qc ; W_v' ; W1[:, :D_n] ; W1[:, D_n+D_e:]]  with
+          W_qc[h*hid + j, :] = sum_c C1[j, c] W_q[c*H + h, :]   (proj_query folded into the first MLP layer),
+          W_v'[h*d_o + c, :] = W_v[c*H + h, :];
+        edge projection  W_pe'[h*d_e + c, :] = W_pe[c*H + h, :];  C1k = C1[:, d_n:] and C2 as tf32 splits."""
+        wq, wv, w1, pe = self.proj_query[0], self.proj_value[0], self.nn_edge[0], self.proj_edge[0]
+        c1, c2 = self._convs()
+        H, dn, de, do = self.num_heads, self.d_n, self.d_e, self.d_o
+        Dn, De = self.dim_node, self.dim_edge
+
+        def build():
+            C1 = c1.weight.squeeze(-1)
+            hid = C1.shape[0]
+            w_qc = torch.einsum("jc,chi->hji", C1[:, :dn], wq.weight.view(dn, H, Dn)).reshape(H * hid, Dn)
+            b_qc = (torch.einsum("jc,ch->hj", C1[:, :dn], wq.bias.view(dn, H)) + c1.bias.view(1, hid)).reshape(H * hid)
+            w_v = wv.weight.view(do, H, Dn).permute(1, 0, 2).reshape(H * do, Dn)
+            b_v = wv.bias.view(do, H).t().reshape(H * do)
+            hid1 = w1.weight.shape[0]
+            w_node = torch.cat([w_qc, w_v, w1.weight[:, :Dn], w1.weight[:, Dn + De:]], 0).contiguous()
+            b_node = torch.cat([b_qc, b_v, torch.zeros(2 * hid1, device=w_node.device, dtype=w_node.dtype)], 0).contiguous()
+            w_pe = pe.weight.view(de, H, De).permute(1, 0, 2).reshape(H * de, De).contiguous()
+            b_pe = pe.bias.view(de, H).t().reshape(H * de).contiguous()
+            c1k = C1[:, dn:].contiguous()
+            c2w = c2.weight.squeeze(-1).contiguous()
+            return dict(w_node=w_node, b_node=b_node, w_pe=w_pe, b_pe=b_pe, c1k=ops.tf32_split(c1k), c2=ops.tf32_split(c2w),
+                        c2b=c2.bias.detach().clone().contiguous(), hid=hid)
+        srcs = (wq.weight, wq.bias, wv.weight, wv.bias, w1.weight, pe.weight, pe.bias, c1.weight, c1.bias, c2.weight, c2.bias)
+        return self._cache.get("tc", srcs, build)
+
+    def tc_eligible(self) -> bool:
+        hid = self._convs()[0].weight.shape[0]
+        return (self.use_edge and g_aggr(self) == "max" and ops.gat_tc_supported(self.num_heads, self.d_e, hid, self.d_o)
+                and self.dim_node % 4 == 0 and self.dim_edge % 4 == 0)
+
+    def fused_tc(self, x: torch.Tensor, edge: torch.Tensor, g: GraphContext, xx_out: torch.Tensor, want_prob: bool = False):
+        """Tensor-core version of ``fused`` (same contract; ``edge`` and ``g`` in CSR edge order)."""
+        require_inference(self, "MultiHeadedEdgeAttention")
+        w = self.tc_weights()
+        H, hid, da, de = self.num_heads, w["hid"], self.dim_atten, self.dim_edge
+        dn = self.dim_node
+        hid1 = self.nn_edge[0].weight.shape[0]
+        node = ops.linear(x, w["w_node"], w["b_node"])             # [N, H*hid + D_a + 2*hid1]
+        qc, v_hm = node[:, :H * hid], node[:, H * hid:H * hid + da]
+        a_src, b_dst = node[:, H * hid + da:H * hid + da + hid1], node[:, H * hid + da + hid1:]
+        w1, w2 = self.nn_edge[0], self.nn_edge[2]
+        h = ops.linear(edge, w1.weight.detach()[:, dn:dn + de], w1.bias.detach(), act=ops.ACT_RELU,
+                       gather=(a_src, g.src, b_dst, g.dst))
+        new_edge = ops.linear(h, w2.weight.detach(), w2.bias.detach())
+        k_hm = ops.linear(edge, w["w_pe"], w["b_pe"])              # [E, H*d_e], row (e, h) contiguous
+        _, prob = ops.gat_edge_tc(k_hm, qc, v_hm, g.src, g.dst, w["c1k"], w["c2"], w["c2b"], g.num_nodes, H, xx_out,
+                                  want_prob=want_prob, d_n=self.d_n)
+        return new_edge, prob
+
     # ---- fused path ------------------------------------------------------------------------------
     def fused(self, x: torch.Tensor, edge: torch.Tensor, g: GraphContext, xx_out: torch.Tensor,
               want_prob: bool = False):
-        """x [N, D_n] (may be a column slice), edge [E, D_e] -> writes the aggregate into ``xx_out``
-        [N, D_a]; returns (new edge feature [E, D_e], prob or None)."""
+        """x [N, D_n] (may be a column slice), edge [E, D_e] in CSR edge order -> writes the aggregate into
+        ``xx_out`` [N, D_a]; returns (new edge feature [E, D_e], prob or None), both in CSR edge order."""
         require_inference(self, "MultiHeadedEdgeAttention")
+        if self.tc_eligible():
+            return self.fused_tc(x, edge, g, xx_out, want_prob)
         dn, de, da = self.dim_node, self.dim_edge, self.dim_atten
         hid1 = self.nn_edge[0].weight.shape[0]
         w_node, b_node = self.node_projection_weights()
@@ -182,7 +249,7 @@ class MultiHeadedEdgeAttention(nn.Module):
             pe = self.proj_edge[0]
             k = ops.linear(edge, pe.weight.detach(), pe.bias.detach())
         c1, c1b, c2, c2b = self.attn_mlp_weights()
-        _, prob, _ = ops.gat_edge(q, v, k, g.edge_index, g.row_ptr, g.perm, c1, c1b, c2, c2b, self.num_heads,
+        _, prob, _ = ops.gat_edge(q, v, k, g.edge_index, g.row_ptr, g.identity, c1, c1b, c2, c2b, self.num_heads,
                                   aggr=g_aggr(self), use_edge=self.use_edge, want_prob=want_prob, out=xx_out)
         return new_edge, prob
 
@@ -201,7 +268,7 @@ class MultiHeadedEdgeAttention(nn.Module):
         k = ops.linear(edge.contiguous(), self.proj_edge[0].weight.detach(), self.proj_edge[0].bias.detach()) if self.use_edge else None
         g = GraphContext(torch.stack([ar, ar], 0), e_cnt)
         c1, c1b, c2, c2b = self.attn_mlp_weights()
-        x, prob, _ = ops.gat_edge(q, v, k, g.edge_index, g.row_ptr, g.perm, c1, c1b, c2, c2b, self.num_heads,
+        x, prob, _ = ops.gat_edge(q, v, k, g.edge_index, g.row_ptr, g.identity, c1, c1b, c2, c2b, self.num_heads,
                                   aggr="add", use_edge=self.use_edge, want_prob=True)
         return x, new_edge, prob
 
@@ -249,7 +316,10 @@ class GraphEdgeAttenNetwork(nn.Module):
         g = GraphContext(edge_index, x.shape[0], self.flow)
         cat_buf = torch.empty((x.shape[0], self.dim_node + self.dim_atten), device=x.device, dtype=torch.float32)
         cat_buf[:, :self.dim_node].copy_(x)
-        out, new_edge, prob = self.forward_fused(cat_buf, edge_feature.contiguous(), g, want_prob=self.return_prob)
+        out, new_edge, prob = self.forward_fused(cat_buf, g.to_sorted(edge_feature.contiguous()), g, want_prob=self.return_prob)
+        new_edge = g.to_original(new_edge)
         if self.return_prob:
+            e = prob.shape[0]
+            prob = g.to_original(prob.view(e, -1)).view(prob.shape) if e else prob
             return out, new_edge, prob
         return out, new_edge

@@ -62,7 +62,7 @@ class MMG(nn.Module):
         ctx = self.scene_context(batch_ids, obj_center)
         g = GraphContext(edge_index, n, self.flow)
         o3, o2 = obj_feature_3d.contiguous(), obj_feature_2d.contiguous()
-        e3, e2 = edge_feature_3d.contiguous(), edge_feature_2d.contiguous()
+        e3, e2 = g.to_sorted(edge_feature_3d.contiguous()), g.to_sorted(edge_feature_2d.contiguous())   # CSR edge order
         for i in range(self.depth):
             act = (i < self.depth - 1) or self.depth == 1          # ReLU(+Dropout) after this layer
             cat3 = torch.empty((n, dn + da), device=o3.device, dtype=torch.float32)
@@ -73,7 +73,7 @@ class MMG(nn.Module):
             o2, e2_raw, _ = self.gcn_2ds[i].forward_fused(cat2, e2, g, relu_nodes=act)
             e2 = self.cross_attn_rel[i].attend_all(e2_raw, e3_raw, relu=act)
             e3 = ops.relu(e3_raw) if act else e3_raw
-        return o3, o2, e3, e2
+        return o3, o2, g.to_original(e3), g.to_original(e2)
 
 
 class GraphEdgeAttenNetworkLayers(nn.Module):
@@ -110,7 +110,7 @@ class GraphEdgeAttenNetworkLayers(nn.Module):
         pack = self._cache.get("fc", tuple(fc.parameters()), lambda: ops.pack_attn_fc(fc))
         ctx = SceneContext(batch_ids, obj_center, pack, 8)
         g = GraphContext(edges_indices, n, self.flow)
-        node, edge = node_feature.contiguous(), edge_feature.contiguous()
+        node, edge = node_feature.contiguous(), g.to_sorted(edge_feature.contiguous())
         probs = []
         for i in range(self.num_layers):
             act = (i < self.num_layers - 1) or self.num_layers == 1
@@ -118,5 +118,7 @@ class GraphEdgeAttenNetworkLayers(nn.Module):
             self.self_attn[i].attend_scenes(node, node, ctx, out=cat[:, :dn])
             node, edge_raw, prob = self.gconvs[i].forward_fused(cat, edge, g, relu_nodes=act, want_prob=True)
             edge = ops.relu(edge_raw) if act else edge_raw
+            if prob.shape[0]:
+                prob = g.to_original(prob.view(prob.shape[0], -1)).view(prob.shape)
             probs.append(prob.cpu().detach() if self.probs_on_host else prob)
-        return node, edge, probs
+        return node, g.to_original(edge), probs

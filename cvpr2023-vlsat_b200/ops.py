@@ -407,3 +407,56 @@ def gat_edge(q, v, k, edge_index, row_ptr, perm, c1, c1b, c2, c2b, n_heads: int,
                      e * (n_heads * d_e * 4.0 + 16.0) + n * (n_heads * d_n + 2.0 * d_a) * 4.0))
     _lib.check(st, "vlsat_gat_edge_fwd")
     return out, prob, arg
+
+
+def permute_rows(x: torch.Tensor, idx: torch.Tensor, gather: bool = True) -> torch.Tensor:
+    """gather: out[i] = x[idx[i]];  scatter (gather=False): out[idx[i]] = x[i].  idx int32 permutation."""
+    xp, ldx = _rows(x, "x")
+    m, d = x.shape
+    out = torch.empty((m, d), device=x.device, dtype=torch.float32)
+    if idx.dtype != torch.int32 or not idx.is_cuda:
+        raise TypeError("permute_rows: idx must be a CUDA int32 tensor")
+    _lib.check(_call("vlsat_permute_rows", xp, ldx, idx.data_ptr(), m, d, out.data_ptr(), d, int(gather), _stream()),
+               "vlsat_permute_rows")
+    return out
+
+
+def permute_edges(edge_index: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    _i64(edge_index, "edge_index")
+    e = edge_index.shape[1]
+    out = torch.empty_like(edge_index)
+    _lib.check(_call("vlsat_permute_edges", edge_index.data_ptr(), perm.data_ptr(), e, out.data_ptr(), _stream()),
+               "vlsat_permute_edges")
+    return out
+
+
+def gat_tc_supported(n_heads: int, d_e: int, hid: int, d_o: int) -> bool:
+    return (tensor_cores_enabled() and 128 % n_heads == 0 and d_e % 32 == 0 and 32 <= d_e <= 256 and hid % 32 == 0
+            and d_o % 32 == 0 and 3 * hid + d_o <= 512 and hid <= 256)
+
+
+def gat_edge_tc(k_hm, qc, v_hm, src, dst, c1k_split, c2_split, c2b, n_nodes: int, n_heads: int, out: torch.Tensor,
+                want_prob: bool = False, d_n: int = 0):
+    """Tensor-core A8 core (max aggregation). k_hm [E, H*d_e] head-major proj_edge output (CSR edge order),
+    qc [N, H*hid] / v_hm [N, H*d_o] head-major node operands (column-slice views allowed)."""
+    e = k_hm.shape[0]
+    d_e = k_hm.shape[1] // n_heads
+    hid = qc.shape[1] // n_heads
+    d_o = v_hm.shape[1] // n_heads
+    qp, ldq = _rows(qc, "qc"); vp_, ldv = _rows(v_hm, "v_hm")
+    xp, ldxx = _rows(out, "out")
+    kh = kl = None
+    if e > 0:
+        kh, kl = tf32_split(k_hm)
+    prob = torch.empty((e, d_o, n_heads), device=out.device, dtype=torch.float32) if want_prob else None
+    ws = torch.empty((n_nodes * n_heads * d_o,), device=out.device, dtype=torch.int32)
+    st = _call("vlsat_gat_edge_tc_fwd", kh.data_ptr() if e else None, kl.data_ptr() if e else None, qp, ldq, vp_, ldv,
+               src.data_ptr() if e else None, dst.data_ptr() if e else None,
+               c1k_split[0].data_ptr(), c1k_split[1].data_ptr(), c2_split[0].data_ptr(), c2_split[1].data_ptr(),
+               c2b.data_ptr(), n_nodes, e, n_heads, d_e, hid, d_o, xp, ldxx, prob.data_ptr() if want_prob else None,
+               ws.data_ptr(), ws.numel() * 4, _stream(),
+               # same algorithmic work as vlsat_gat_edge_fwd (SURVEY.md 8d), independent of the node-side folding
+               work=(2.0 * e * n_heads * (hid * ((d_n or d_e) + d_e) + d_o * hid),
+                     e * (n_heads * d_e * 4.0 + 16.0) + n_nodes * (n_heads * (d_n or d_e) + 2.0 * n_heads * d_o) * 4.0))
+    _lib.check(st, "vlsat_gat_edge_tc_fwd")
+    return out, prob
