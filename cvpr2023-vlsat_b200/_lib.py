@@ -18,7 +18,8 @@ class Epilogue(C.Structure):
     """Mirror of ``vlsat_epilogue`` (include/vlsat_b200.h)."""
     _fields_ = [("bias", vp), ("gather_a", vp), ("idx_a", vp), ("gather_b", vp), ("idx_b", vp),
                 ("ld_gather", i64), ("residual", vp), ("ld_res", i64), ("alpha", f32), ("beta", f32),
-                ("scale_ptr", vp), ("act", i32), ("bias_per_row", i32)]
+                ("scale_ptr", vp), ("act", i32), ("bias_per_row", i32),
+                ("split_hi", vp), ("split_lo", vp), ("ld_split", i64)]
 
 
 class LinearOpts(C.Structure):
@@ -34,6 +35,7 @@ SIGNATURES = {
     "vlsat_gemm_engine": [],
     "vlsat_launch_count": [],
     "vlsat_pointnet_fwd": [vp, i64, i32, i64, vp, vp, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp],
+    "vlsat_pointnet_tc_fwd": [vp, i64, i32, i64, vp, vp, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp],
     "vlsat_edge_descriptor_fwd": [vp, i64, vp, i64, vp, vp],
     "vlsat_linear_fwd": [vp, i64, vp, i64, vp, i64, i64, i64, i64, C.POINTER(Epilogue), C.POINTER(LinearOpts), vp],
     "vlsat_linear_workspace_bytes": [i64, i64, i64, i32, i32],

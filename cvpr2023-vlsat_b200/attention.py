@@ -105,20 +105,26 @@ class MultiHeadAttention(nn.Module):
         att = ops.node_attn(q, k, v, ctx.centres, ctx.seg_start, ctx.seg_end, ctx.fc_pack, self.attention.h)
         return self._finish(q_in, att, relu, out)
 
-    def attend_all(self, q_in, kv_in, relu: bool = False, out=None) -> torch.Tensor:
-        """LN(q_in + fc_o(softmax(QK^T/sqrt(dk)) V)) over all keys, no mask/bias; 2-D inputs."""
+    def attend_all(self, q_in, kv_in, relu: bool = False, out=None, q_split=None, kv_split=None) -> torch.Tensor:
+        """LN(q_in + fc_o(softmax(QK^T/sqrt(dk)) V)) over all keys, no mask/bias; 2-D inputs.
+        ``q_split`` / ``kv_split``: tf32 splits of the inputs if the producer already emitted them."""
         require_inference(self, "MultiHeadAttention")
         a = self.attention
         if a.d_k == 64 and ops.tensor_cores_enabled() and kv_in.shape[1] % 4 == 0 and kv_in.shape[1] >= 32:
-            # tensor-core path: Q, K row-major; the value projection is emitted transposed (V^T = W_v x^T)
+            # tensor-core path: Q, K row-major; the value projection is emitted transposed (V^T = W_v x^T).
+            # The projections write the tf32 splits the attention kernel consumes directly from their epilogues.
             nk = kv_in.shape[0]
-            q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach())
-            k = ops.linear(kv_in, a.fc_k.weight.detach(), a.fc_k.bias.detach())
-            vt = torch.empty((a.h * a.d_v, (nk + 3) // 4 * 4), device=q.device, dtype=torch.float32)
-            if vt.shape[1] != nk:
-                vt[:, nk:].zero_()
-            ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), out=vt[:, :nk], bias_per_row=True,
-                       x_is_weight=True)
+            if kv_split is None:
+                kv_split = ops.tf32_split(kv_in)
+            _, q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach(), x_split=q_split, emit_split=True, want_y=False)
+            _, k = ops.linear(kv_in, a.fc_k.weight.detach(), a.fc_k.bias.detach(), x_split=kv_split, emit_split=True, want_y=False)
+            if nk % 4 == 0:
+                _, vt = ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), bias_per_row=True, x_is_weight=True,
+                                   w_split=kv_split, emit_split=True, want_y=False)
+            else:
+                vt = torch.zeros((a.h * a.d_v, (nk + 3) // 4 * 4), device=q_in.device, dtype=torch.float32)
+                ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), out=vt[:, :nk], bias_per_row=True,
+                           x_is_weight=True, w_split=kv_split)
             att = ops.flash_attn_tc(q, k, vt, nk, a.h)
         else:
             q, k, v = self._project(q_in, kv_in, q_in is kv_in)

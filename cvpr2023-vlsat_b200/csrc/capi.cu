@@ -13,6 +13,9 @@ size_t linear_tc_workspace_bytes(int64_t, int64_t, int64_t, bool, bool);
 int tf32_split(const float*, int64_t, int64_t, int64_t, float*, float*, cudaStream_t);
 int linear_tc(const float*, const float*, const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t,
               const vlsat_epilogue*, int, cudaStream_t);
+bool pointnet_tc_eligible(int, int, int, int, int64_t);
+int pointnet_tc(const float*, int64_t, int, int64_t, const float*, const float*, const float*, const float*, const float*,
+                const float*, int, float*, int32_t*, cudaStream_t);
 int flash_attn_tc(const float*, const float*, int64_t, const float*, const float*, int64_t, const float*, const float*,
                   int64_t, float*, int64_t, float*, int64_t, int64_t, int, int, cudaStream_t);
 int flash_attn_simt(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
@@ -60,8 +63,11 @@ extern "C" int vlsat_linear_fwd(const float* x, int64_t ldx, const float* w, int
                                 const vlsat_linear_opts* opts, void* stream) {
     VLSAT_REQUIRE(M >= 0 && N >= 1 && K >= 1);
     if (M == 0) return VLSAT_OK;
-    VLSAT_REQUIRE(x && w && y && ldx >= K && ldw >= K && ldy >= N);
+    VLSAT_REQUIRE(x && w && ldx >= K && ldw >= K);
+    VLSAT_REQUIRE((y && ldy >= N) || (epi && epi->split_hi));
     if (epi) {
+        VLSAT_REQUIRE((epi->split_hi == nullptr) == (epi->split_lo == nullptr));
+        VLSAT_REQUIRE(!epi->split_hi || epi->ld_split >= N);
         VLSAT_REQUIRE(!epi->gather_a || epi->idx_a);
         VLSAT_REQUIRE(!epi->gather_b || epi->idx_b);
         VLSAT_REQUIRE(!(epi->gather_a || epi->gather_b) || epi->ld_gather >= N);
@@ -120,4 +126,14 @@ extern "C" int vlsat_flash_attn_tc_fwd(const float* q_hi, const float* q_lo, int
     VLSAT_SUPPORT(all % 16 == 0);
     return flash_attn_tc(q_hi, q_lo, ldq, k_hi, k_lo, ldk, vt_hi, vt_lo, ldvt, out, ldo, lse, nq, nk, n_heads, dk,
                          (cudaStream_t)stream);
+}
+
+extern "C" int vlsat_pointnet_tc_fwd(const float* x, int64_t n_obj, int c_in, int64_t n_pts,
+                                     const float* w1, const float* b1, int c1, const float* w2, const float* b2, int c2,
+                                     const float* w3, const float* b3, int c_out, float* out, int32_t* argmax, void* stream) {
+    VLSAT_REQUIRE(x && w1 && b1 && w2 && b2 && w3 && b3 && out);
+    VLSAT_REQUIRE(n_obj >= 0 && n_pts >= 1 && c_in >= 1 && c_out >= 1);
+    VLSAT_SUPPORT(pointnet_tc_eligible(c_in, c1, c2, c_out, n_pts) && n_pts < (1ll << 31));
+    if (n_obj == 0) return VLSAT_OK;
+    return pointnet_tc(x, n_obj, c_in, n_pts, w1, b1, w2, b2, w3, b3, c_out, out, argmax, (cudaStream_t)stream);
 }

@@ -38,4 +38,12 @@ __device__ __forceinline__ float epilogue_one(const vlsat_epilogue& e, float acc
     return t * post_scale;
 }
 
+// tf32 split of one value: hi = round-to-nearest tf32, lo = v - hi
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    hi = __uint_as_float(u);
+    lo = v - hi;
+}
+
 }  // namespace vlsat

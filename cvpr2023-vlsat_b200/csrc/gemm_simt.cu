@@ -120,7 +120,11 @@ linear_simt_kernel(const LinearArgs a) {
 #pragma unroll
         for (int j = 0; j < T; ++j) {
             const int64_t n = n0 + (j / 4) * (BN / H) + tx * 4 + (j % 4);
-            if (n < a.N) a.y[m * a.ldy + n] = epilogue_one(a.epi, acc[i][j], m, n, ia, ib, post_scale);
+            if (n < a.N) {
+                const float v = epilogue_one(a.epi, acc[i][j], m, n, ia, ib, post_scale);
+                if (a.y) a.y[m * a.ldy + n] = v;
+                if (a.epi.split_hi) split_tf32(v, a.epi.split_hi[m * a.epi.ld_split + n], a.epi.split_lo[m * a.epi.ld_split + n]);
+            }
         }
     }
 }

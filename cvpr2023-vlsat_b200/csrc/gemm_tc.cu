@@ -15,6 +15,7 @@
 // Tails in M, N and K are handled by TMA out-of-bounds zero fill plus masking in the epilogue.
 #include "epilogue.cuh"
 #include "tc_common.cuh"
+#include <algorithm>
 
 namespace vlsat {
 
@@ -47,6 +48,9 @@ __global__ void tf32_split_kernel(const float* __restrict__ x, int64_t ldx, int6
     *reinterpret_cast<float4*>(lo + r * cols + c) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
+// Persistent kernel: gridDim.x CTAs walk the output tiles round-robin (n fastest, so the CTAs that run
+// together share A row-tiles in L2). Two TMEM accumulators: the epilogue of tile i overlaps the main loop
+// of tile i+1.
 template <int BN, int STAGES, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
@@ -54,197 +58,182 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                  const LinearArgs a) {
     constexpr int B_TILE = BN * 128;
     constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TC_A_TILE + B_TILE);
+    constexpr int SCR_LD = 36;                              // floats per scratch row (32 + pad, 16 B aligned)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    float* scratch = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);       // [4 warps][32][SCR_LD]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(scratch + 4 * 32 * SCR_LD);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* acc_full = empty_bar + STAGES;                // [2]
+    uint64_t* acc_empty = acc_full + 2;                     // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-    long long* trace = (blockIdx.x == 0 && blockIdx.y == 0) ? a.trace : nullptr;
-    if (trace && threadIdx.x == 0) trace[0] = clock64();
-    const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
-    if (a.trace && threadIdx.x == 0 && cta_lin < 600) {
-        unsigned long long gt; unsigned smid;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-        a.trace[128 + 3 * cta_lin] = (long long)gt; a.trace[128 + 3 * cta_lin + 2] = smid;
-    }
     const int num_kb = (int)((a.K + TC_BK - 1) / TC_BK);
-
-    auto a_hi = [&](int s) { return smem + s * STAGE_BYTES; };
-    auto b_hi = [&](int s) { return smem + s * STAGE_BYTES + TC_A_TILE; };
-    auto a_lo = [&](int s) { return smem + s * STAGE_BYTES + TC_A_TILE + B_TILE; };
-    auto b_lo = [&](int s) { return smem + s * STAGE_BYTES + 2 * TC_A_TILE + B_TILE; };
+    const int tiles_n = (int)((a.N + BN - 1) / BN), tiles_m = (int)((a.M + TC_BM - 1) / TC_BM);
+    const int n_tiles = tiles_m * tiles_n;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_ahi); prefetch_tmap(&tm_bhi);
         if (PASSES == 3) { prefetch_tmap(&tm_alo); prefetch_tmap(&tm_blo); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
         fence_barrier_init();
     }
-    if (warp == 1) { tmem_alloc(tmem_holder, BN); tmem_relinquish(); }
+    if (warp == 1) { tmem_alloc(tmem_holder, 2 * BN); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    if (trace && threadIdx.x == 0) { trace[1] = clock64(); trace[100] = gtime(); }
 
     if (warp == 0) {
-        // warp-uniform loop; one elected lane issues (keeps the TMA / MMA issue on the uniform datapath
-        // without per-instruction divergence handling)
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            if (trace && lane == 0 && kb < 40) trace[8 + 3 * kb] = clock64();
-            if (elect_one()) {
-                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_2d(a_hi(s), &tm_ahi, &full_bar[s], kb * TC_BK, m0);
-                tma_load_2d(b_hi(s), &tm_bhi, &full_bar[s], kb * TC_BK, n0);
-                if (PASSES == 3) {
-                    tma_load_2d(a_lo(s), &tm_alo, &full_bar[s], kb * TC_BK, m0);
-                    tma_load_2d(b_lo(s), &tm_blo, &full_bar[s], kb * TC_BK, n0);
+        // warp-uniform loops; one elected lane issues (keeps TMA / MMA issue on the uniform datapath)
+        int g = 0;                                          // k-block counter across tiles -> ring position
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * BN;
+            for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                const int s = g % STAGES;
+                mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+                if (elect_one()) {
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    tma_load_2d(st, &tm_ahi, &full_bar[s], kb * TC_BK, m0);
+                    tma_load_2d(st + TC_A_TILE, &tm_bhi, &full_bar[s], kb * TC_BK, n0);
+                    if (PASSES == 3) {
+                        tma_load_2d(st + TC_A_TILE + B_TILE, &tm_alo, &full_bar[s], kb * TC_BK, m0);
+                        tma_load_2d(st + 2 * TC_A_TILE + B_TILE, &tm_blo, &full_bar[s], kb * TC_BK, n0);
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc<Kind::TF32>(TC_BM, BN);
         // descriptors differ only in the 14-bit start-address field: build one, then add offsets (>>4)
         const uint64_t desc0 = make_sdesc_k128(smem_u32(smem));
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(&full_bar[s], ph);
+        int g = 0, i = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int buf = i & 1;
+            mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
             tc_fence_after();
-            if (trace && lane == 0 && kb < 40) { trace[8 + 3 * kb + 1] = clock64(); if (kb == 0) trace[101] = gtime(); if (kb == num_kb - 1) trace[102] = gtime(); }
-            if (elect_one()) {
-                const uint64_t dah = desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
-                const uint64_t dbh = dah + (TC_A_TILE >> 4);
-                const uint64_t dal = dah + ((TC_A_TILE + B_TILE) >> 4);
-                const uint64_t dbl = dah + ((2 * TC_A_TILE + B_TILE) >> 4);
+            const uint32_t tacc = tmem_base + buf * BN;
+            for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                const int s = g % STAGES;
+                mbar_wait(&full_bar[s], (g / STAGES) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t dah = desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
+                    const uint64_t dbh = dah + (TC_A_TILE >> 4);
+                    const uint64_t dal = dah + ((TC_A_TILE + B_TILE) >> 4);
+                    const uint64_t dbl = dah + ((2 * TC_A_TILE + B_TILE) >> 4);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {           // UMMA_K = 8 for tf32 (32 bytes = 2 x 16 B)
-                    const uint32_t acc = (k > 0) ? 1u : (kb > 0 ? 1u : 0u);
-                    if (PASSES == 3) {
-                        // small terms first, then the leading product
-                        mma_ss<Kind::TF32>(tmem_base, dal + 2 * k, dbh + 2 * k, idesc, acc);
-                        mma_ss<Kind::TF32>(tmem_base, dah + 2 * k, dbl + 2 * k, idesc, 1);
-                        mma_ss<Kind::TF32>(tmem_base, dah + 2 * k, dbh + 2 * k, idesc, 1);
-                    } else {
-                        mma_ss<Kind::TF32>(tmem_base, dah + 2 * k, dbh + 2 * k, idesc, acc);
+                    for (int k = 0; k < TC_BK / 8; ++k) {       // UMMA_K = 8 for tf32 (32 bytes = 2 x 16 B)
+                        const uint32_t acc = (k > 0) ? 1u : (kb > 0 ? 1u : 0u);
+                        if (PASSES == 3) {
+                            // small terms first, then the leading product
+                            mma_ss<Kind::TF32>(tacc, dal + 2 * k, dbh + 2 * k, idesc, acc);
+                            mma_ss<Kind::TF32>(tacc, dah + 2 * k, dbl + 2 * k, idesc, 1);
+                            mma_ss<Kind::TF32>(tacc, dah + 2 * k, dbh + 2 * k, idesc, 1);
+                        } else {
+                            mma_ss<Kind::TF32>(tacc, dah + 2 * k, dbh + 2 * k, idesc, acc);
+                        }
                     }
+                    tc_commit(&empty_bar[s]);                    // stage reusable once these MMAs retire
+                    if (kb == num_kb - 1) tc_commit(&acc_full[buf]);
                 }
-                tc_commit(&empty_bar[s]);                        // stage reusable once these MMAs retire
+                __syncwarp();
             }
-            __syncwarp();
-            if (trace && lane == 0 && kb < 40) trace[8 + 3 * kb + 2] = clock64();
         }
-        if (elect_one()) tc_commit(accum_bar);                   // accumulator complete
-        __syncwarp();
     } else {
-        const int q = warp & 3;                                  // TMEM lane quarter owned by this warp
-        const int64_t m = (int64_t)m0 + q * 32 + lane;
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        if (trace && threadIdx.x == 64) { trace[2] = clock64(); trace[103] = gtime(); }
-        const bool row_ok = m < a.M;
-        const int64_t ia = (row_ok && a.epi.gather_a) ? a.epi.idx_a[m] : 0;
-        const int64_t ib = (row_ok && a.epi.gather_b) ? a.epi.idx_b[m] : 0;
-        const float post_scale = a.epi.scale_ptr ? expf(__ldg(a.epi.scale_ptr)) : 1.f;
+        const int q = warp & 3;                              // TMEM lane quarter owned by this warp
+        float* scr = scratch + q * 32 * SCR_LD;
         const vlsat_epilogue& e = a.epi;
         auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
         // fully vectorised epilogue when every operand row is 16-byte addressable
-        const bool vec_ok = (a.ldy % 4 == 0) && al16(a.y) && (n0 % 4 == 0) &&
+        const bool vec_ok = (a.ldy % 4 == 0) && al16(a.y) && (BN % 4 == 0) &&
+                            (!e.split_hi || (e.ld_split % 4 == 0 && al16(e.split_hi) && al16(e.split_lo))) &&
                             (!e.bias || e.bias_per_row || al16(e.bias)) &&
                             (!(e.gather_a || e.gather_b) || (e.ld_gather % 4 == 0 && al16(e.gather_a) && al16(e.gather_b))) &&
                             (!e.residual || (e.ld_res % 4 == 0 && al16(e.residual)));
-        const float row_bias = (row_ok && e.bias && e.bias_per_row) ? __ldg(e.bias + m) : 0.f;
+        const float post_scale = e.scale_ptr ? expf(__ldg(e.scale_ptr)) : 1.f;
+        const int sub = lane >> 3, c4 = (lane & 7) * 4;      // transposed domain: 4 rows x 8 float4 per instruction
+        int i = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int buf = i & 1;
+            const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * BN;
+            const int64_t m_own = (int64_t)m0 + q * 32 + lane;
+            const bool own_ok = m_own < a.M;
+            const int64_t ia_own = (own_ok && e.gather_a) ? e.idx_a[m_own] : 0;
+            const int64_t ib_own = (own_ok && e.gather_b) ? e.idx_b[m_own] : 0;
+            mbar_wait(&acc_full[buf], (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            if (n0 + c0 >= a.N) break;                           // warp-uniform
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            tmem_ld_wait();
-            if (!row_ok) continue;
-            const int64_t nb = n0 + c0;
-            float* yrow = a.y + m * a.ldy + nb;
-            if (vec_ok && nb + 32 <= a.N) {
-                // every branch below is warp-uniform and sits OUTSIDE the element loops, so the sigmoid's
-                // exp/divide are never executed (or if-converted) on the ReLU / identity paths
-                float t[32];
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int64_t nb = (int64_t)n0 + c0;
+                if (nb >= a.N) break;                        // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32(tacc + (uint32_t)c0, r);
+                tmem_ld_wait();
+                if (vec_ok && nb + 32 <= a.N) {
+                    // stage the 32x32 block through shared memory so that every global access of the warp
+                    // covers 4 complete 128-byte rows instead of 32 partial ones
 #pragma unroll
-                for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(r[j]);
-                if (e.bias) {
-                    if (e.bias_per_row) {
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(scr + lane * SCR_LD + j) =
+                            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    __syncwarp();
+                    const int64_t n = nb + c4;
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e.bias && !e.bias_per_row) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) t[j] += row_bias;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + nb + j));
-                            t[j] += b.x; t[j + 1] += b.y; t[j + 2] += b.z; t[j + 3] += b.w;
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + sub;
+                        const int64_t m = (int64_t)m0 + q * 32 + rr;
+                        const int64_t ia = __shfl_sync(0xffffffffu, ia_own, rr), ib = __shfl_sync(0xffffffffu, ib_own, rr);
+                        if (m >= a.M) continue;
+                        float4 v = *reinterpret_cast<const float4*>(scr + rr * SCR_LD + c4);
+                        if (e.bias) {
+                            if (e.bias_per_row) { const float b = __ldg(e.bias + m); v.x += b; v.y += b; v.z += b; v.w += b; }
+                            else { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+                        }
+                        if (e.gather_a) { const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.gather_a + ia * e.ld_gather + n)); v.x += g4.x; v.y += g4.y; v.z += g4.z; v.w += g4.w; }
+                        if (e.gather_b) { const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.gather_b + ib * e.ld_gather + n)); v.x += g4.x; v.y += g4.y; v.z += g4.z; v.w += g4.w; }
+                        if (e.act == VLSAT_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        else if (e.act == VLSAT_ACT_SIGMOID) { v.x = apply_act(v.x, e.act); v.y = apply_act(v.y, e.act); v.z = apply_act(v.z, e.act); v.w = apply_act(v.w, e.act); }
+                        if (e.residual) {
+                            const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.residual + m * e.ld_res + n));
+                            v.x = e.alpha * v.x + e.beta * g4.x; v.y = e.alpha * v.y + e.beta * g4.y;
+                            v.z = e.alpha * v.z + e.beta * g4.z; v.w = e.alpha * v.w + e.beta * g4.w;
+                        } else if (e.alpha != 1.f) { v.x *= e.alpha; v.y *= e.alpha; v.z *= e.alpha; v.w *= e.alpha; }
+                        if (e.scale_ptr) { v.x *= post_scale; v.y *= post_scale; v.z *= post_scale; v.w *= post_scale; }
+                        if (a.y) *reinterpret_cast<float4*>(a.y + m * a.ldy + n) = v;
+                        if (e.split_hi) {
+                            float4 hi, lo;
+                            split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+                            split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+                            *reinterpret_cast<float4*>(e.split_hi + m * e.ld_split + n) = hi;
+                            *reinterpret_cast<float4*>(e.split_lo + m * e.ld_split + n) = lo;
                         }
                     }
-                }
-                if (e.gather_a) {
-                    const float4* ga = reinterpret_cast<const float4*>(e.gather_a + ia * e.ld_gather + nb);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { const float4 g = __ldg(ga + j); t[4 * j] += g.x; t[4 * j + 1] += g.y; t[4 * j + 2] += g.z; t[4 * j + 3] += g.w; }
-                }
-                if (e.gather_b) {
-                    const float4* gb = reinterpret_cast<const float4*>(e.gather_b + ib * e.ld_gather + nb);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { const float4 g = __ldg(gb + j); t[4 * j] += g.x; t[4 * j + 1] += g.y; t[4 * j + 2] += g.z; t[4 * j + 3] += g.w; }
-                }
-                if (e.act == VLSAT_ACT_RELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) t[j] = fmaxf(t[j], 0.f);
-                } else if (e.act == VLSAT_ACT_SIGMOID) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) t[j] = 1.f / (1.f + expf(-t[j]));
-                }
-                if (e.residual) {
-                    const float4* rr = reinterpret_cast<const float4*>(e.residual + m * e.ld_res + nb);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 g = __ldg(rr + j);
-                        t[4 * j] = e.alpha * t[4 * j] + e.beta * g.x; t[4 * j + 1] = e.alpha * t[4 * j + 1] + e.beta * g.y;
-                        t[4 * j + 2] = e.alpha * t[4 * j + 2] + e.beta * g.z; t[4 * j + 3] = e.alpha * t[4 * j + 3] + e.beta * g.w;
-                    }
-                } else if (e.alpha != 1.f) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) t[j] *= e.alpha;
-                }
-                if (e.scale_ptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) t[j] *= post_scale;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(yrow + j) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
-            } else {
+                    __syncwarp();
+                } else if (own_ok) {
 #pragma unroll 4
-                for (int j = 0; j < 32; ++j)
-                    if (nb + j < a.N)
-                        yrow[j] = epilogue_one(e, __uint_as_float(r[j]), m, nb + j, ia, ib, post_scale);
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < a.N) {
+                            const float v = epilogue_one(e, __uint_as_float(r[j]), m_own, nb + j, ia_own, ib_own, post_scale);
+                            if (a.y) a.y[m_own * a.ldy + nb + j] = v;
+                            if (e.split_hi) split_tf32(v, e.split_hi[m_own * e.ld_split + nb + j], e.split_lo[m_own * e.ld_split + nb + j]);
+                        }
+                }
             }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);                    // 128 arrivals free the accumulator
         }
     }
-    if (trace && threadIdx.x == 64) trace[104] = gtime();
     tc_fence_before();
     __syncthreads();
-    if (trace && threadIdx.x == 0) { trace[3] = clock64(); trace[105] = gtime(); }
-    if (a.trace && threadIdx.x == 0 && cta_lin < 600) {
-        unsigned long long gt;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-        a.trace[128 + 3 * cta_lin + 1] = (long long)gt;
-    }
-    if (warp == 1) tmem_dealloc(tmem_base, BN);
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 long long* g_trace = nullptr;
@@ -269,10 +258,11 @@ template <int BN, int STAGES, int PASSES>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tal, const CUtensorMap& tb, const CUtensorMap& tbl,
                      const LinearArgs& a, cudaStream_t st) {
     constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TC_A_TILE + BN * 128);
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 4 * 32 * 36 * 4 /*epilogue scratch*/ + 1024 /*align*/ + 256 /*barriers*/;
     auto kern = linear_tc_kernel<BN, STAGES, PASSES>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((unsigned)ceil_div(a.N, BN), (unsigned)ceil_div(a.M, TC_BM));
+    const int64_t n_tiles = ceil_div(a.N, BN) * ceil_div(a.M, TC_BM);
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, kNumSMs);
     kern<<<grid, TC_THREADS, smem, st>>>(ta, tal, tb, tbl, a);
     return finish_launch();
 }

@@ -148,6 +148,7 @@ class MultiHeadedEdgeAttention(nn.Module):
         self.proj_query = build_mlp([dim_node, dim_node])
         self.proj_value = build_mlp([dim_node, dim_atten])
         self._cache = DerivedCache()
+        self.last_edge_split = None      # tf32 split of the last new edge feature (tensor-core path), else None
 
     # ---- derived weights -------------------------------------------------------------------------
     def _convs(self):
@@ -206,8 +207,11 @@ class MultiHeadedEdgeAttention(nn.Module):
         return (self.use_edge and g_aggr(self) == "max" and ops.gat_tc_supported(self.num_heads, self.d_e, hid, self.d_o)
                 and self.dim_node % 4 == 0 and self.dim_edge % 4 == 0)
 
-    def fused_tc(self, x: torch.Tensor, edge: torch.Tensor, g: GraphContext, xx_out: torch.Tensor, want_prob: bool = False):
-        """Tensor-core version of ``fused`` (same contract; ``edge`` and ``g`` in CSR edge order)."""
+    def fused_tc(self, x: torch.Tensor, edge: torch.Tensor, g: GraphContext, xx_out: torch.Tensor, want_prob: bool = False,
+                 edge_split=None):
+        """Tensor-core version of ``fused`` (same contract; ``edge`` and ``g`` in CSR edge order). Intermediate
+        activations that only feed another projection are never stored unsplit: the producing epilogue emits
+        the tf32 (hi, lo) pair the consumer reads. Also returns the split of the new edge feature."""
         require_inference(self, "MultiHeadedEdgeAttention")
         w = self.tc_weights()
         H, hid, da, de = self.num_heads, w["hid"], self.dim_atten, self.dim_edge
@@ -217,10 +221,18 @@ class MultiHeadedEdgeAttention(nn.Module):
         qc, v_hm = node[:, :H * hid], node[:, H * hid:H * hid + da]
         a_src, b_dst = node[:, H * hid + da:H * hid + da + hid1], node[:, H * hid + da + hid1:]
         w1, w2 = self.nn_edge[0], self.nn_edge[2]
-        h = ops.linear(edge, w1.weight.detach()[:, dn:dn + de], w1.bias.detach(), act=ops.ACT_RELU,
-                       gather=(a_src, g.src, b_dst, g.dst))
-        new_edge = ops.linear(h, w2.weight.detach(), w2.bias.detach())
-        k_hm = ops.linear(edge, w["w_pe"], w["b_pe"])              # [E, H*d_e], row (e, h) contiguous
+        if g.num_edges == 0:
+            new_edge = torch.empty((0, de), device=x.device, dtype=torch.float32)
+            ops.gat_edge_tc(torch.empty((0, H * self.d_e), device=x.device), qc, v_hm, g.src, g.dst, w["c1k"], w["c2"], w["c2b"],
+                            g.num_nodes, H, xx_out, d_n=self.d_n)
+            self.last_edge_split = None
+            return new_edge, (torch.empty((0, self.d_o, H), device=x.device) if want_prob else None)
+        if edge_split is None:
+            edge_split = ops.tf32_split(edge)
+        _, h = ops.linear(edge, w1.weight.detach()[:, dn:dn + de], w1.bias.detach(), act=ops.ACT_RELU,
+                          gather=(a_src, g.src, b_dst, g.dst), x_split=edge_split, emit_split=True, want_y=False)
+        new_edge, self.last_edge_split = ops.linear(h, w2.weight.detach(), w2.bias.detach(), emit_split=True)
+        _, k_hm = ops.linear(edge, w["w_pe"], w["b_pe"], x_split=edge_split, emit_split=True, want_y=False)   # rows (e, h)
         _, prob = ops.gat_edge_tc(k_hm, qc, v_hm, g.src, g.dst, w["c1k"], w["c2"], w["c2b"], g.num_nodes, H, xx_out,
                                   want_prob=want_prob, d_n=self.d_n)
         return new_edge, prob
@@ -231,6 +243,7 @@ class MultiHeadedEdgeAttention(nn.Module):
         """x [N, D_n] (may be a column slice), edge [E, D_e] in CSR edge order -> writes the aggregate into
         ``xx_out`` [N, D_a]; returns (new edge feature [E, D_e], prob or None), both in CSR edge order."""
         require_inference(self, "MultiHeadedEdgeAttention")
+        self.last_edge_split = None
         if self.tc_eligible():
             return self.fused_tc(x, edge, g, xx_out, want_prob)
         dn, de, da = self.dim_node, self.dim_edge, self.dim_atten

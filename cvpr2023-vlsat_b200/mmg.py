@@ -71,7 +71,9 @@ class MMG(nn.Module):
             o2 = self.cross_attn[i].attend_scenes(o2, o3, ctx, out=cat2[:, :dn])
             o3, e3_raw, _ = self.gcn_3ds[i].forward_fused(cat3, e3, g, relu_nodes=act)
             o2, e2_raw, _ = self.gcn_2ds[i].forward_fused(cat2, e2, g, relu_nodes=act)
-            e2 = self.cross_attn_rel[i].attend_all(e2_raw, e3_raw, relu=act)
+            e2 = self.cross_attn_rel[i].attend_all(e2_raw, e3_raw, relu=act,
+                                                   q_split=self.gcn_2ds[i].edgeatten.last_edge_split,
+                                                   kv_split=self.gcn_3ds[i].edgeatten.last_edge_split)
             e3 = ops.relu(e3_raw) if act else e3_raw
         return o3, o2, g.to_original(e3), g.to_original(e2)
 

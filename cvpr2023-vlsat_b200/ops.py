@@ -106,11 +106,12 @@ def pointnet(x, w1, b1, w2, b2, w3, b3, want_argmax: bool = False):
         raise ValueError("pointnet: weight shapes do not chain")
     out = torch.empty((n_obj, c_out), device=x.device, dtype=torch.float32)
     arg = torch.empty((n_obj, c_out), device=x.device, dtype=torch.int32) if want_argmax else None
-    st = _call("vlsat_pointnet_fwd", x.data_ptr(), n_obj, c_in, n_pts, w1.data_ptr(), b1.data_ptr(), c1,
+    use_tc = tensor_cores_enabled() and c1 == 64 and c2 == 128 and c_in <= 16 and c_out % 128 == 0
+    st = _call("vlsat_pointnet_tc_fwd" if use_tc else "vlsat_pointnet_fwd", x.data_ptr(), n_obj, c_in, n_pts, w1.data_ptr(), b1.data_ptr(), c1,
                                         w2.data_ptr(), b2.data_ptr(), c2, w3.data_ptr(), b3.data_ptr(), c_out,
                                         out.data_ptr(), arg.data_ptr() if want_argmax else None, _stream(),
                work=(2.0 * n_obj * n_pts * (c_in * c1 + c1 * c2 + c2 * c_out), 4.0 * (x.numel() + n_obj * c_out)))
-    _lib.check(st, "vlsat_pointnet_fwd")
+    _lib.check(st, "vlsat_pointnet_tc_fwd" if use_tc else "vlsat_pointnet_fwd")
     return (out, arg) if want_argmax else out
 
 
@@ -169,24 +170,45 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            gather: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]] = None,
            residual: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0,
            scale_ptr: Optional[torch.Tensor] = None, bias_per_row: bool = False,
-           x_is_weight: bool = False) -> torch.Tensor:
+           x_is_weight: bool = False, x_split=None, w_split=None, emit_split: bool = False, want_y: bool = True):
     """y = post(act(x w^T + bias + ga[ia] + gb[ib])), post(t) = (alpha t + beta residual) * exp(scale).
 
     x [M, K] and w [N, K] may be column-slice views (row stride = leading dimension); ``out`` may be a
     column slice of a wider buffer. ``x_is_weight=True`` swaps the roles for the tf32-split cache: x is
-    a parameter (split cached), w an activation (split per call) - used to emit y^T = W x^T."""
+    a parameter (split cached), w an activation (split per call) - used to emit y^T = W x^T.
+    ``x_split=(hi, lo)``: tf32 split of x already available (compact [M, K]) - skips the split pass.
+    ``emit_split=True``: the epilogue also writes the tf32 split of y and the call returns ``(y, (hi, lo))``
+    (``want_y=False``: only the split is written, y is None). ``x`` itself may be such a ``(hi, lo)`` pair
+    when the unsplit activation was never materialised (tensor-core engine only)."""
+    if isinstance(x, tuple):
+        x_split = x
+        x = x_split[0]
+        if not (tensor_cores_enabled() and x.shape[1] % 4 == 0 and x.shape[1] >= 32 and w.shape[0] >= 8):
+            raise RuntimeError("linear: a pre-split activation can only feed the tensor-core engine")
     xp, ldx = _rows(x, "x")
     wp, ldw = _rows(w, "w")
     m, k = x.shape
     n = w.shape[0]
     if w.shape[1] != k:
         raise ValueError(f"linear: x is [{m},{k}] but w is {tuple(w.shape)}")
-    if out is None:
-        out = torch.empty((m, n), device=x.device, dtype=torch.float32)
-    elif tuple(out.shape) != (m, n):
-        raise ValueError(f"linear: out has shape {tuple(out.shape)}, expected {(m, n)}")
-    yp, ldy = _rows(out, "out")
+    if not want_y and not emit_split:
+        raise ValueError("linear: nothing to compute")
+    yp, ldy = None, n
+    if want_y:
+        if out is None:
+            out = torch.empty((m, n), device=x.device, dtype=torch.float32)
+        elif tuple(out.shape) != (m, n):
+            raise ValueError(f"linear: out has shape {tuple(out.shape)}, expected {(m, n)}")
+        yp, ldy = _rows(out, "out")
+    else:
+        out = None
     epi = Epilogue()
+    y_split = None
+    if emit_split:
+        if n % 4:
+            raise ValueError("linear: emit_split needs N % 4 == 0")
+        y_split = torch.empty((2, m, n), device=x.device, dtype=torch.float32)
+        epi.split_hi, epi.split_lo, epi.ld_split = y_split[0].data_ptr(), y_split[1].data_ptr(), n
     epi.alpha, epi.beta, epi.act = alpha, beta, act
     if bias is not None:
         _f32(bias, "bias")
@@ -216,15 +238,24 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         if x_is_weight:
             hl = _weight_split(x, ldx)
             opts.x_hi, opts.x_lo = hl[0].data_ptr(), hl[1].data_ptr()
-            ws = torch.empty((2 * n * k,), device=x.device, dtype=torch.float32)
+            if w_split is not None:
+                opts.w_hi, opts.w_lo = w_split[0].data_ptr(), w_split[1].data_ptr()
+            else:
+                ws = torch.empty((2 * n * k,), device=x.device, dtype=torch.float32)
         else:
             hl = _weight_split(w, ldw)
             opts.w_hi, opts.w_lo = hl[0].data_ptr(), hl[1].data_ptr()
-            ws = torch.empty((2 * m * k,), device=x.device, dtype=torch.float32)
-        opts.workspace, opts.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+            if x_split is not None:
+                opts.x_hi, opts.x_lo = x_split[0].data_ptr(), x_split[1].data_ptr()
+            else:
+                ws = torch.empty((2 * m * k,), device=x.device, dtype=torch.float32)
+        if ws is not None:
+            opts.workspace, opts.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     st = _call("vlsat_linear_fwd", xp, ldx, wp, ldw, yp, ldy, m, n, k, C.byref(epi), C.byref(opts), _stream(),
                work=(2.0 * m * n * k, 4.0 * (m * k + n * k + m * n)))
     _lib.check(st, "vlsat_linear_fwd")
+    if emit_split:
+        return out, (y_split[0], y_split[1])
     return out
 
 
@@ -338,15 +369,17 @@ def tf32_split(x: torch.Tensor):
 
 def flash_attn_tc(q, k, vt, nk: int, n_heads: int, want_lse: bool = False):
     """Tensor-core streaming attention. q [nq, D], k [nk, D], vt [D, >= nk] = transposed values with a
-    row stride that is a multiple of 4 (column slices allowed); D = n_heads * 64."""
-    nq, d = q.shape
+    row stride that is a multiple of 4 (column slices allowed); D = n_heads * 64. Each operand may also be
+    given as its tf32 ``(hi, lo)`` split (as emitted by ``linear(..., emit_split=True)``)."""
+    qh, ql = q if isinstance(q, tuple) else tf32_split(q)
+    kh, kl = k if isinstance(k, tuple) else tf32_split(k)
+    vh, vl = vt if isinstance(vt, tuple) else tf32_split(vt)
+    vt = vh
+    nq, d = qh.shape
     if d != n_heads * 64:
         raise ValueError("flash_attn_tc needs head size 64")
-    qh, ql = tf32_split(q)
-    kh, kl = tf32_split(k)
-    vh, vl = tf32_split(vt)
-    out = torch.empty((nq, d), device=q.device, dtype=torch.float32)
-    lse = torch.empty((n_heads, nq), device=q.device, dtype=torch.float32) if want_lse else None
+    out = torch.empty((nq, d), device=qh.device, dtype=torch.float32)
+    lse = torch.empty((n_heads, nq), device=qh.device, dtype=torch.float32) if want_lse else None
     st = _call("vlsat_flash_attn_tc_fwd", qh.data_ptr(), ql.data_ptr(), d, kh.data_ptr(), kl.data_ptr(), d,
                vh.data_ptr(), vl.data_ptr(), vt.shape[1], out.data_ptr(), d, lse.data_ptr() if want_lse else None,
                nq, nk, n_heads, 64, _stream(), work=(4.0 * nq * nk * d, 4.0 * (2 * nq * d + 2 * nk * d)))
@@ -439,6 +472,9 @@ def gat_edge_tc(k_hm, qc, v_hm, src, dst, c1k_split, c2_split, c2b, n_nodes: int
                 want_prob: bool = False, d_n: int = 0):
     """Tensor-core A8 core (max aggregation). k_hm [E, H*d_e] head-major proj_edge output (CSR edge order),
     qc [N, H*hid] / v_hm [N, H*d_o] head-major node operands (column-slice views allowed)."""
+    k_split = k_hm if isinstance(k_hm, tuple) else None
+    if k_split is not None:
+        k_hm = k_split[0]
     e = k_hm.shape[0]
     d_e = k_hm.shape[1] // n_heads
     hid = qc.shape[1] // n_heads
@@ -447,7 +483,7 @@ def gat_edge_tc(k_hm, qc, v_hm, src, dst, c1k_split, c2_split, c2b, n_nodes: int
     xp, ldxx = _rows(out, "out")
     kh = kl = None
     if e > 0:
-        kh, kl = tf32_split(k_hm)
+        kh, kl = k_split if k_split is not None else tf32_split(k_hm)
     prob = torch.empty((e, d_o, n_heads), device=out.device, dtype=torch.float32) if want_prob else None
     ws = torch.empty((n_nodes * n_heads * d_o,), device=out.device, dtype=torch.int32)
     st = _call("vlsat_gat_edge_tc_fwd", kh.data_ptr() if e else None, kl.data_ptr() if e else None, qp, ldq, vp_, ldv,

@@ -56,6 +56,14 @@ int vlsat_pointnet_fwd(const float* x, int64_t n_obj, int c_in, int64_t n_pts,
                        const float* w3, const float* b3, int c_out,
                        float* out, int32_t* argmax, void* stream);
 
+/* Tensor-core engine of the same operation (3xTF32, fp32-accurate): requires c1 == 64, c2 == 128, c_in <= 16 and
+ * c_out % 128 == 0 (768 / 512 / 256 on the path); other shapes -> VLSAT_ERR_UNSUPPORTED. */
+int vlsat_pointnet_tc_fwd(const float* x, int64_t n_obj, int c_in, int64_t n_pts,
+                          const float* w1, const float* b1, int c1,
+                          const float* w2, const float* b2, int c2,
+                          const float* w3, const float* b3, int c_out,
+                          float* out, int32_t* argmax, void* stream);
+
 /* A2  Gen_edge_descriptor.message (src/utils/op_utils.py:85-97) with flow='target_to_source':
  *   out[e,0:6] = d[src,0:6]-d[dst,0:6]; out[e,6:11] = log(d[src,6:11]/d[dst,6:11]).  out [E, 11]. */
 int vlsat_edge_descriptor_fwd(const float* desc, int64_t n_nodes, const int64_t* edge_index, int64_t n_edges,
@@ -83,6 +91,9 @@ typedef struct {
     const float* scale_ptr;   /* device scalar s: result *= expf(s); or NULL   */
     int act;                  /* VLSAT_ACT_*                                   */
     int bias_per_row;         /* 1: bias is [M] and added per output ROW (used to emit y^T = w x^T) */
+    float* split_hi;          /* optional: also emit the tf32 split of the result, compact [M, ld_split],   */
+    float* split_lo;          /*   so a consuming projection / attention needs no separate split pass       */
+    int64_t ld_split;         /*   (>= N, multiple of 4). y itself may then be NULL.                        */
 } vlsat_epilogue;
 
 /* Engine selection. AUTO = tcgen05 3xTF32 (fp32-accurate split, see csrc/gemm_tc.cu) whenever the operands
