@@ -11,6 +11,7 @@ struct LinearArgs {
     int64_t M, N, K;
     vlsat_epilogue epi;
     long long* trace;      // debug: per-phase clock64 stamps of CTA (0,0); nullptr in normal use
+    int tma_store;         // tensor-core engine: outputs leave through TMA stores (all rows 16-byte addressable)
 };
 
 __device__ __forceinline__ float apply_act(float t, int act) {

@@ -60,6 +60,7 @@ __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_
 }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+template <int DO>      // d_o (channels per head of the attention output): 32 or 64
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_constant__ CUtensorMap tm_klo,
                    const __grid_constant__ CUtensorMap tm_c1hi, const __grid_constant__ CUtensorMap tm_c1lo,
@@ -76,11 +77,10 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
     uint8_t* c2lo_s = c2hi_s + hc * c2_box;
     uint8_t* khi_s = c2lo_s + hc * c2_box;
     uint8_t* klo_s = khi_s + kh * k_box;
-    float* msg = reinterpret_cast<float*>(klo_s + kh * k_box);           // [128][d_o + 1]
-    int64_t* s_src = reinterpret_cast<int64_t*>(msg + GT_ROWS * (p.d_o + 1) + 2);
-    s_src = reinterpret_cast<int64_t*>((reinterpret_cast<uintptr_t>(s_src) + 7) & ~(uintptr_t)7);
+    float* msg = reinterpret_cast<float*>(klo_s + kh * k_box);           // [128][DO + 1]
+    int* s_src = reinterpret_cast<int*>(msg + GT_ROWS * (DO + 1));       // [128] source node of each edge of the tile
     float* s_c2b = reinterpret_cast<float*>(s_src + GT_ROWS);
-    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_c2b + p.d_o) + 7) & ~(uintptr_t)7);
+    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_c2b + DO) + 7) & ~(uintptr_t)7);
     uint64_t* w_full = bars; uint64_t* k_full = bars + 1; uint64_t* k_empty = bars + 2;
     uint64_t* acc1_full = bars + 3; uint64_t* a2_ready = bars + 4; uint64_t* acc2_full = bars + 5;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
@@ -174,9 +174,9 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
         const int r = qd * 32 + lane;                    // row of the tile = TMEM lane
         const int et = threadIdx.x - 64;                 // 0..127 among the epilogue threads
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const int D_a = p.H * p.d_o;
-        const int ms = p.d_o + 1;
-        for (int i = et; i < p.d_o; i += 128) s_c2b[i] = __ldg(p.c2_bias + i);
+        const int D_a = p.H * DO;
+        constexpr int MS = DO + 1;
+        for (int i = et; i < DO; i += 128) s_c2b[i] = __ldg(p.c2_bias + i);
         int it = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int64_t row_g = (int64_t)t * GT_ROWS + r;
@@ -184,79 +184,91 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
             const int64_t e = valid ? row_g / p.H : 0;
             const int h = (int)(row_g % p.H);
             const int64_t e0 = (int64_t)t * ept;
-            if (et < ept) s_src[et] = (e0 + et < p.n_edges) ? p.src[e0 + et] : -1;
+            if (et < ept) s_src[et] = (e0 + et < p.n_edges) ? (int)p.src[e0 + et] : -1;
             const int64_t src = valid ? p.src[e] : 0, dst = valid ? p.dst[e] : 0;
+            // operands gathered per row: issue the loads now, they land while the tensor core runs MMA1
+            const float4* qrow = reinterpret_cast<const float4*>(p.qc + src * p.ld_qc + (int64_t)h * p.hid);
+            const float4* vrow = reinterpret_cast<const float4*>(p.v + dst * p.ld_v + (int64_t)h * DO);
+            float4 vv[DO / 4], qv[8];
+#pragma unroll
+            for (int j = 0; j < DO / 4; ++j) vv[j] = valid ? __ldg(vrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) qv[j] = valid ? __ldg(qrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
             // ---- epilogue 1: hidden = relu(acc1 + QC[src, h]) -> tf32 hi / lo -> TMEM
             mbar_wait(acc1_full, it & 1);
             tc_fence_after();
-            const float* qrow = p.qc + src * p.ld_qc + (int64_t)h * p.hid;
             for (int c0 = 0; c0 < p.hid; c0 += 32) {
                 uint32_t a[32], lo[32];
                 tmem_ld_32x32(t_acc1 + lane_off + c0, a);
+                float4 qn[8];                            // next chunk's QC values, in flight while this chunk is processed
+                const bool more = c0 + 32 < p.hid;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) qn[j] = (valid && more) ? __ldg(qrow + (c0 + 32) / 4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid) qv = __ldg(reinterpret_cast<const float4*>(qrow + c0 + j));
-                    const float hv[4] = {fmaxf(__uint_as_float(a[j]) + qv.x, 0.f), fmaxf(__uint_as_float(a[j + 1]) + qv.y, 0.f),
-                                         fmaxf(__uint_as_float(a[j + 2]) + qv.z, 0.f), fmaxf(__uint_as_float(a[j + 3]) + qv.w, 0.f)};
+                for (int j = 0; j < 8; ++j) {
+                    const float hv[4] = {fmaxf(__uint_as_float(a[4 * j]) + qv[j].x, 0.f), fmaxf(__uint_as_float(a[4 * j + 1]) + qv[j].y, 0.f),
+                                         fmaxf(__uint_as_float(a[4 * j + 2]) + qv[j].z, 0.f), fmaxf(__uint_as_float(a[4 * j + 3]) + qv[j].w, 0.f)};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         uint32_t hi;
                         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(hv[u]));
-                        a[j + u] = hi; lo[j + u] = __float_as_uint(hv[u] - __uint_as_float(hi));
+                        a[4 * j + u] = hi; lo[4 * j + u] = __float_as_uint(hv[u] - __uint_as_float(hi));
                     }
                 }
                 tmem_st_32(t_a2hi + lane_off + c0, a);
                 tmem_st_32(t_a2lo + lane_off + c0, lo);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) qv[j] = qn[j];
             }
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(a2_ready);
-            // ---- epilogue 2: softmax over d_o, times value, segmented max
+            // ---- epilogue 2: softmax over d_o in registers, times value, segmented max
             mbar_wait(acc2_full, it & 1);
             tc_fence_after();
-            const float* vrow = p.v + dst * p.ld_v + (int64_t)h * p.d_o;
-            for (int c0 = 0; c0 < p.d_o; c0 += 32) {   // d_o == 32 in every shipped config; the loop keeps it general
+            float tl[DO];
+#pragma unroll
+            for (int c0 = 0; c0 < DO; c0 += 32) {
                 uint32_t a[32];
                 tmem_ld_32x32(t_acc2 + lane_off + c0, a);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) msg[r * ms + c0 + j] = __uint_as_float(a[j]) + s_c2b[c0 + j];
+                for (int j = 0; j < 32; ++j) tl[c0 + j] = __uint_as_float(a[j]) + s_c2b[c0 + j];
             }
             tc_fence_before();
-            {
-                float mx = -FLT_MAX;
-                for (int c = 0; c < p.d_o; ++c) mx = fmaxf(mx, msg[r * ms + c]);
-                float sum = 0.f;
-                for (int c = 0; c < p.d_o; ++c) { const float ex = __expf(msg[r * ms + c] - mx); msg[r * ms + c] = ex; sum += ex; }
-                const float inv = 1.f / sum;
-                for (int c = 0; c < p.d_o; c += 4) {
-                    float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid) vv = __ldg(reinterpret_cast<const float4*>(vrow + c));
-                    const float pr[4] = {msg[r * ms + c] * inv, msg[r * ms + c + 1] * inv, msg[r * ms + c + 2] * inv, msg[r * ms + c + 3] * inv};
-                    if (p.prob && valid) {
+            float mx = -FLT_MAX;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) p.prob[(e * p.d_o + c + u) * p.H + h] = pr[u];
-                    }
-                    msg[r * ms + c] = pr[0] * vv.x; msg[r * ms + c + 1] = pr[1] * vv.y;
-                    msg[r * ms + c + 2] = pr[2] * vv.z; msg[r * ms + c + 3] = pr[3] * vv.w;
-                }
+            for (int c = 0; c < DO; ++c) mx = fmaxf(mx, tl[c]);
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < DO; ++c) { tl[c] = __expf(tl[c] - mx); sum += tl[c]; }
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int c = 0; c < DO; ++c) tl[c] *= inv;
+            if (p.prob && valid) {
+#pragma unroll
+                for (int c = 0; c < DO; ++c) p.prob[(e * DO + c) * p.H + h] = tl[c];
+            }
+#pragma unroll
+            for (int j = 0; j < DO / 4; ++j) {
+                msg[r * MS + 4 * j] = tl[4 * j] * vv[j].x; msg[r * MS + 4 * j + 1] = tl[4 * j + 1] * vv[j].y;
+                msg[r * MS + 4 * j + 2] = tl[4 * j + 2] * vv[j].z; msg[r * MS + 4 * j + 3] = tl[4 * j + 3] * vv[j].w;
             }
             epi_barrier();
             for (int f = et; f < D_a; f += 128) {
-                const int fh = f / p.d_o, fc = f % p.d_o;
+                const int fh = f / DO, fc = f % DO;      // DO is a power of two: shifts
                 float best = -FLT_MAX;
-                int64_t cur = s_src[0];
+                int cur = s_src[0];
                 for (int i = 0; i < ept; ++i) {
-                    const int64_t s = s_src[i];
-                    if (s != cur) {
-                        if (cur >= 0) atomicMax(p.xx_enc + cur * D_a + f, enc_ordered(best));
-                        cur = s; best = -FLT_MAX;
+                    const int sn = s_src[i];
+                    if (sn != cur) {
+                        if (cur >= 0) atomicMax(p.xx_enc + (int64_t)cur * D_a + f, enc_ordered(best));
+                        cur = sn; best = -FLT_MAX;
                     }
-                    if (s >= 0) best = fmaxf(best, msg[(i * p.H + fh) * ms + fc]);
+                    if (sn >= 0) best = fmaxf(best, msg[(i * p.H + fh) * MS + fc]);
                 }
-                if (cur >= 0) atomicMax(p.xx_enc + cur * D_a + f, enc_ordered(best));
+                if (cur >= 0) atomicMax(p.xx_enc + (int64_t)cur * D_a + f, enc_ordered(best));
             }
             epi_barrier();                               // msg / s_src are reused by the next tile
         }
@@ -333,7 +345,7 @@ extern "C" int vlsat_gat_edge_tc_fwd(const float* k_hi, const float* k_lo, const
     if (n_nodes == 0) return VLSAT_OK;
     VLSAT_REQUIRE(xx && ld_xx >= (int64_t)n_heads * d_o);
     VLSAT_SUPPORT(GT_ROWS % n_heads == 0 && d_e % 32 == 0 && d_e >= 32 && d_e <= 256 && hid % 32 == 0 && hid >= 32 &&
-                  d_o % 32 == 0 && 3 * hid + d_o <= 512 && hid <= 256 && d_o <= 256);
+                  (d_o == 32 || d_o == 64) && 3 * hid + d_o <= 512 && hid <= 256);
     VLSAT_SUPPORT(n_edges * n_heads < (1ll << 31) && n_nodes * n_heads * d_o < (1ll << 31));
     const int D_a = n_heads * d_o;
     const size_t need = (size_t)n_nodes * D_a * sizeof(int);
@@ -356,13 +368,14 @@ extern "C" int vlsat_gat_edge_tc_fwd(const float* k_hi, const float* k_lo, const
         const size_t smem = (size_t)2 * kh * hid * 128 + (size_t)2 * hc * d_o * 128 + (size_t)2 * kh * GT_ROWS * 128 +
                             (size_t)GT_ROWS * (d_o + 1) * 4 + 16 + GT_ROWS * 8 + (size_t)d_o * 4 + 128 + 1024;
         VLSAT_SUPPORT(smem <= 227 * 1024);
-        cudaFuncSetAttribute(gat_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kern = d_o == 32 ? gat_edge_tc_kernel<32> : gat_edge_tc_kernel<64>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         GatTcParams p;
         p.qc = qc; p.ld_qc = ld_qc; p.v = v; p.ld_v = ld_v; p.src = src_sorted; p.dst = dst_sorted; p.c2_bias = c2_bias;
         p.xx_enc = enc; p.prob = prob; p.n_edges = n_edges; p.H = n_heads; p.d_e = d_e; p.hid = hid; p.d_o = d_o;
         const int64_t n_tiles = ceil_div(n_edges * n_heads, GT_ROWS);
         const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, kNumSMs);
-        gat_edge_tc_kernel<<<grid, GT_THREADS, smem, st>>>(tk, tkl, t1, t1l, t2, t2l, p);
+        kern<<<grid, GT_THREADS, smem, st>>>(tk, tkl, t1, t1l, t2, t2l, p);
         ++launches;
     }
     gat_finalize_kernel<<<(unsigned)ceil_div(n_nodes * D_a, 256), 256, 0, st>>>(enc, xx, ld_xx, n_nodes, n_heads, d_o);

@@ -143,7 +143,7 @@ int linear_simt(const float* x, int64_t ldx, const float* w, int64_t ldw, float*
     a.x = x; a.ldx = ldx; a.w = w; a.ldw = ldw; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.K = K;
     if (epi) a.epi = *epi;
     else { a.epi = vlsat_epilogue{}; a.epi.alpha = 1.f; }
-    a.trace = nullptr;
+    a.trace = nullptr; a.tma_store = 0;
     const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) &&
                      ((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0);
     // Big tiles only when they still fill the machine; otherwise 64x64 tiles for more CTAs.

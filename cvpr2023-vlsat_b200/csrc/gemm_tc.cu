@@ -55,14 +55,15 @@ template <int BN, int STAGES, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                  const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
-                 const LinearArgs a) {
+                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_shi,
+                 const __grid_constant__ CUtensorMap tm_slo, const LinearArgs a) {
     constexpr int B_TILE = BN * 128;
     constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TC_A_TILE + B_TILE);
-    constexpr int SCR_LD = 36;                              // floats per scratch row (32 + pad, 16 B aligned)
+    constexpr int STG_BYTES = TC_BM * 128;                  // one staged [128 rows x 32 cols] output block
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* scratch = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);       // [4 warps][32][SCR_LD]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(scratch + 4 * 32 * SCR_LD);
+    uint8_t* staging = smem + STAGES * STAGE_BYTES;         // 2 ping-pong blocks, 128B-swizzled, read by TMA stores
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * STG_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_full = empty_bar + STAGES;                // [2]
     uint64_t* acc_empty = acc_full + 2;                     // [2]
@@ -116,6 +117,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
             const int buf = i & 1;
             mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
             tc_fence_after();
+            if (a.trace && blockIdx.x == 0 && lane == 0 && i < 8) a.trace[i * 4 + 0] = gtime();
             const uint32_t tacc = tmem_base + buf * BN;
             for (int kb = 0; kb < num_kb; ++kb, ++g) {
                 const int s = g % STAGES;
@@ -143,20 +145,36 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                 }
                 __syncwarp();
             }
+            if (a.trace && blockIdx.x == 0 && lane == 0 && i < 8) a.trace[i * 4 + 1] = gtime();
         }
     } else {
         const int q = warp & 3;                              // TMEM lane quarter owned by this warp
-        float* scr = scratch + q * 32 * SCR_LD;
+        const int et = threadIdx.x - 64;                     // 0..127 among the epilogue threads
+        const int srow = q * 32 + lane;                      // row of the tile owned by this thread
+        int sidx = 0;                                        // staging ping-pong counter
         const vlsat_epilogue& e = a.epi;
+        if (a.tma_store && et == 0) { prefetch_tmap(&tm_y); prefetch_tmap(&tm_shi); prefetch_tmap(&tm_slo); }
+        // stage one 128x32 block (this thread's row) and let one thread hand it to the TMA store engine
+        auto stage_store = [&](const CUtensorMap* tm, const float4 (&vals)[8], int col0, int row0) {
+            uint8_t* sb = staging + (sidx & 1) * STG_BYTES;
+            if (et == 0) bulk_wait_read<1>();                // the store that last read this block has drained it
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(sb + srow * 128 + ((c ^ (srow & 7)) << 4)) = vals[c];
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) { tma_store_2d(tm, sb, col0, row0); bulk_commit(); }
+            ++sidx;
+        };
         auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
         // fully vectorised epilogue when every operand row is 16-byte addressable
-        const bool vec_ok = (a.ldy % 4 == 0) && al16(a.y) && (BN % 4 == 0) &&
+        const bool vec_ok = a.tma_store && (BN % 4 == 0) &&
                             (!e.split_hi || (e.ld_split % 4 == 0 && al16(e.split_hi) && al16(e.split_lo))) &&
                             (!e.bias || e.bias_per_row || al16(e.bias)) &&
                             (!(e.gather_a || e.gather_b) || (e.ld_gather % 4 == 0 && al16(e.gather_a) && al16(e.gather_b))) &&
                             (!e.residual || (e.ld_res % 4 == 0 && al16(e.residual)));
         const float post_scale = e.scale_ptr ? expf(__ldg(e.scale_ptr)) : 1.f;
-        const int sub = lane >> 3, c4 = (lane & 7) * 4;      // transposed domain: 4 rows x 8 float4 per instruction
         int i = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int buf = i & 1;
@@ -165,8 +183,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
             const bool own_ok = m_own < a.M;
             const int64_t ia_own = (own_ok && e.gather_a) ? e.idx_a[m_own] : 0;
             const int64_t ib_own = (own_ok && e.gather_b) ? e.idx_b[m_own] : 0;
+            const float row_bias = (own_ok && e.bias && e.bias_per_row) ? __ldg(e.bias + m_own) : 0.f;
             mbar_wait(&acc_full[buf], (i >> 1) & 1);
             tc_fence_after();
+            if (a.trace && blockIdx.x == 0 && threadIdx.x == 64 && i < 8) a.trace[i * 4 + 2] = gtime();
             const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -176,47 +196,63 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                 tmem_ld_32x32(tacc + (uint32_t)c0, r);
                 tmem_ld_wait();
                 if (vec_ok && nb + 32 <= a.N) {
-                    // stage the 32x32 block through shared memory so that every global access of the warp
-                    // covers 4 complete 128-byte rows instead of 32 partial ones
+                    // One output row per thread (its TMEM lane), 32 consecutive columns. All global loads of the
+                    // chunk are issued before any is consumed so their L2 latencies overlap; results leave through
+                    // 128B-swizzled staging blocks + TMA stores (whole 128-byte lines, tails clipped by the TMA unit).
+                    float4 v[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(scr + lane * SCR_LD + j) =
-                            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                    __syncwarp();
-                    const int64_t n = nb + c4;
-                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (e.bias && !e.bias_per_row) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+                    for (int j = 0; j < 8; ++j)
+                        v[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    if (own_ok) {
+                        float4 b4[8], ga4[8], gb4[8];
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rr = it * 4 + sub;
-                        const int64_t m = (int64_t)m0 + q * 32 + rr;
-                        const int64_t ia = __shfl_sync(0xffffffffu, ia_own, rr), ib = __shfl_sync(0xffffffffu, ib_own, rr);
-                        if (m >= a.M) continue;
-                        float4 v = *reinterpret_cast<const float4*>(scr + rr * SCR_LD + c4);
-                        if (e.bias) {
-                            if (e.bias_per_row) { const float b = __ldg(e.bias + m); v.x += b; v.y += b; v.z += b; v.w += b; }
-                            else { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+                        for (int j = 0; j < 8; ++j) {
+                            const int64_t n = nb + j * 4;
+                            b4[j] = (e.bias && !e.bias_per_row) ? __ldg(reinterpret_cast<const float4*>(e.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            ga4[j] = e.gather_a ? __ldg(reinterpret_cast<const float4*>(e.gather_a + ia_own * e.ld_gather + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            gb4[j] = e.gather_b ? __ldg(reinterpret_cast<const float4*>(e.gather_b + ib_own * e.ld_gather + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
-                        if (e.gather_a) { const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.gather_a + ia * e.ld_gather + n)); v.x += g4.x; v.y += g4.y; v.z += g4.z; v.w += g4.w; }
-                        if (e.gather_b) { const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.gather_b + ib * e.ld_gather + n)); v.x += g4.x; v.y += g4.y; v.z += g4.z; v.w += g4.w; }
-                        if (e.act == VLSAT_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                        else if (e.act == VLSAT_ACT_SIGMOID) { v.x = apply_act(v.x, e.act); v.y = apply_act(v.y, e.act); v.z = apply_act(v.z, e.act); v.w = apply_act(v.w, e.act); }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            v[j].x += b4[j].x + row_bias + ga4[j].x + gb4[j].x; v[j].y += b4[j].y + row_bias + ga4[j].y + gb4[j].y;
+                            v[j].z += b4[j].z + row_bias + ga4[j].z + gb4[j].z; v[j].w += b4[j].w + row_bias + ga4[j].w + gb4[j].w;
+                        }
+                        if (e.act == VLSAT_ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); v[j].z = fmaxf(v[j].z, 0.f); v[j].w = fmaxf(v[j].w, 0.f); }
+                        } else if (e.act == VLSAT_ACT_SIGMOID) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { v[j].x = apply_act(v[j].x, e.act); v[j].y = apply_act(v[j].y, e.act); v[j].z = apply_act(v[j].z, e.act); v[j].w = apply_act(v[j].w, e.act); }
+                        }
                         if (e.residual) {
-                            const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.residual + m * e.ld_res + n));
-                            v.x = e.alpha * v.x + e.beta * g4.x; v.y = e.alpha * v.y + e.beta * g4.y;
-                            v.z = e.alpha * v.z + e.beta * g4.z; v.w = e.alpha * v.w + e.beta * g4.w;
-                        } else if (e.alpha != 1.f) { v.x *= e.alpha; v.y *= e.alpha; v.z *= e.alpha; v.w *= e.alpha; }
-                        if (e.scale_ptr) { v.x *= post_scale; v.y *= post_scale; v.z *= post_scale; v.w *= post_scale; }
-                        if (a.y) *reinterpret_cast<float4*>(a.y + m * a.ldy + n) = v;
-                        if (e.split_hi) {
-                            float4 hi, lo;
-                            split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
-                            split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-                            *reinterpret_cast<float4*>(e.split_hi + m * e.ld_split + n) = hi;
-                            *reinterpret_cast<float4*>(e.split_lo + m * e.ld_split + n) = lo;
+                            float4 rs4[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) rs4[j] = __ldg(reinterpret_cast<const float4*>(e.residual + m_own * e.ld_res + nb + j * 4));
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                v[j].x = e.alpha * v[j].x + e.beta * rs4[j].x; v[j].y = e.alpha * v[j].y + e.beta * rs4[j].y;
+                                v[j].z = e.alpha * v[j].z + e.beta * rs4[j].z; v[j].w = e.alpha * v[j].w + e.beta * rs4[j].w;
+                            }
+                        } else if (e.alpha != 1.f) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { v[j].x *= e.alpha; v[j].y *= e.alpha; v[j].z *= e.alpha; v[j].w *= e.alpha; }
+                        }
+                        if (e.scale_ptr) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { v[j].x *= post_scale; v[j].y *= post_scale; v[j].z *= post_scale; v[j].w *= post_scale; }
                         }
                     }
-                    __syncwarp();
+                    if (a.y) stage_store(&tm_y, v, (int)nb, m0);
+                    if (e.split_hi) {
+                        float4 hi[8], lo[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            split_tf32(v[j].x, hi[j].x, lo[j].x); split_tf32(v[j].y, hi[j].y, lo[j].y);
+                            split_tf32(v[j].z, hi[j].z, lo[j].z); split_tf32(v[j].w, hi[j].w, lo[j].w);
+                        }
+                        stage_store(&tm_shi, hi, (int)nb, m0);
+                        stage_store(&tm_slo, lo, (int)nb, m0);
+                    }
                 } else if (own_ok) {
 #pragma unroll 4
                     for (int j = 0; j < 32; ++j)
@@ -228,8 +264,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                 }
             }
             tc_fence_before();
+            if (a.trace && blockIdx.x == 0 && threadIdx.x == 64 && i < 8) a.trace[i * 4 + 3] = gtime();
             mbar_arrive(&acc_empty[buf]);                    // 128 arrivals free the accumulator
         }
+        if (et == 0) bulk_wait_all();                        // every TMA store has landed before the CTA retires
     }
     tc_fence_before();
     __syncthreads();
@@ -256,14 +294,15 @@ int tf32_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* h
 
 template <int BN, int STAGES, int PASSES>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tal, const CUtensorMap& tb, const CUtensorMap& tbl,
+                     const CUtensorMap& ty, const CUtensorMap& tsh, const CUtensorMap& tsl,
                      const LinearArgs& a, cudaStream_t st) {
     constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TC_A_TILE + BN * 128);
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + 4 * 32 * 36 * 4 /*epilogue scratch*/ + 1024 /*align*/ + 256 /*barriers*/;
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 2 * TC_BM * 128 /*store staging*/ + 1024 /*align*/ + 256 /*barriers*/;
     auto kern = linear_tc_kernel<BN, STAGES, PASSES>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t n_tiles = ceil_div(a.N, BN) * ceil_div(a.M, TC_BM);
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, kNumSMs);
-    kern<<<grid, TC_THREADS, smem, st>>>(ta, tal, tb, tbl, a);
+    kern<<<grid, TC_THREADS, smem, st>>>(ta, tal, tb, tbl, ty, tsh, tsl, a);
     return finish_launch();
 }
 
@@ -284,8 +323,21 @@ int linear_tc(const float* x_hi, const float* x_lo, const float* w_hi, const flo
              make_tmap_2d(&tbl, w_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, N, K, K, TC_BK, bn);
     else { tal = ta; tbl = tb; }
     if (!ok) return VLSAT_ERR_UNSUPPORTED;
-    if (passes == 3) return bn == 64 ? launch_tc<64, 4, 3>(ta, tal, tb, tbl, a, st) : launch_tc<128, 3, 3>(ta, tal, tb, tbl, a, st);
-    return bn == 64 ? launch_tc<64, 6, 1>(ta, tal, tb, tbl, a, st) : launch_tc<128, 6, 1>(ta, tal, tb, tbl, a, st);
+    // output tensor maps (TMA stores): possible when every output row is 16-byte addressable
+    auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    const vlsat_epilogue& e = a.epi;
+    bool tma_out = (!y || (ldy % 4 == 0 && al16(y))) && (!e.split_hi || (e.ld_split % 4 == 0 && al16(e.split_hi) && al16(e.split_lo))) &&
+                   (!e.bias || e.bias_per_row || al16(e.bias)) &&
+                   (!(e.gather_a || e.gather_b) || (e.ld_gather % 4 == 0 && al16(e.gather_a) && al16(e.gather_b))) &&
+                   (!e.residual || (e.ld_res % 4 == 0 && al16(e.residual)));
+    CUtensorMap ty = ta, tsh = ta, tsl = ta;
+    if (tma_out && y) tma_out = make_tmap_2d(&ty, y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldy, 32, TC_BM);
+    if (tma_out && e.split_hi)
+        tma_out = make_tmap_2d(&tsh, e.split_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_split, 32, TC_BM) &&
+                  make_tmap_2d(&tsl, e.split_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_split, 32, TC_BM);
+    a.tma_store = tma_out ? 1 : 0;
+    if (passes == 3) return bn == 64 ? launch_tc<64, 4, 3>(ta, tal, tb, tbl, ty, tsh, tsl, a, st) : launch_tc<128, 3, 3>(ta, tal, tb, tbl, ty, tsh, tsl, a, st);
+    return bn == 64 ? launch_tc<64, 6, 1>(ta, tal, tb, tbl, ty, tsh, tsl, a, st) : launch_tc<128, 6, 1>(ta, tal, tb, tbl, ty, tsh, tsl, a, st);
 }
 
 }  // namespace vlsat

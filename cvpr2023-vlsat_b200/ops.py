@@ -465,7 +465,7 @@ def permute_edges(edge_index: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
 
 def gat_tc_supported(n_heads: int, d_e: int, hid: int, d_o: int) -> bool:
     return (tensor_cores_enabled() and 128 % n_heads == 0 and d_e % 32 == 0 and 32 <= d_e <= 256 and hid % 32 == 0
-            and d_o % 32 == 0 and 3 * hid + d_o <= 512 and hid <= 256)
+            and d_o in (32, 64) and 3 * hid + d_o <= 512 and hid <= 256)
 
 
 def gat_edge_tc(k_hm, qc, v_hm, src, dst, c1k_split, c2_split, c2b, n_nodes: int, n_heads: int, out: torch.Tensor,

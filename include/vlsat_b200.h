@@ -199,7 +199,7 @@ int vlsat_gat_edge_fwd(const float* q, int64_t ldq, const float* v, int64_t ldv,
  *   c2 [d_o, hid] as tf32 splits.  xx [n_nodes, H*d_o] (row stride ld_xx) is written in the reference's
  *   interleaved order c*H + h; nodes without outgoing edges get 0.  prob (nullable) [E, d_o, H] in sorted order.
  * workspace >= n_nodes * H * d_o * 4 bytes.  Constraints: 128 % H == 0, d_e % 32 == 0, hid % 32 == 0,
- * d_o % 32 == 0, 3*hid + d_o <= 512 (TMEM columns); other shapes -> VLSAT_ERR_UNSUPPORTED (use vlsat_gat_edge_fwd). */
+ * d_o in {32, 64}, 3*hid + d_o <= 512 (TMEM columns); other shapes -> VLSAT_ERR_UNSUPPORTED (use vlsat_gat_edge_fwd). */
 int vlsat_gat_edge_tc_fwd(const float* k_hi, const float* k_lo, const float* qc, int64_t ld_qc,
                           const float* v, int64_t ld_v, const int64_t* src_sorted, const int64_t* dst_sorted,
                           const float* c1k_hi, const float* c1k_lo, const float* c2_hi, const float* c2_lo,
