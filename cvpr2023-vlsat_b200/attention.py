@@ -116,6 +116,16 @@ class MultiHeadAttention(nn.Module):
             nk = kv_in.shape[0]
             if kv_split is None:
                 kv_split = ops.tf32_split(kv_in)
+            if ops.ATTN_ENGINE == "bf16x3":
+                # projections in 3xTF32 (fp32 outputs), attention operands as bf16 (hi, lo) pairs: the attention
+                # kernel is L2-bandwidth bound and bf16 pairs halve its traffic (csrc/flash_attn_bf16.cu)
+                q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach(), x_split=q_split)
+                k = ops.linear(kv_in, a.fc_k.weight.detach(), a.fc_k.bias.detach(), x_split=kv_split)
+                vt = torch.empty((a.h * a.d_v, (nk + 3) // 4 * 4), device=q_in.device, dtype=torch.float32)
+                ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), out=vt[:, :nk], bias_per_row=True,
+                           x_is_weight=True, w_split=kv_split)
+                att = ops.flash_attn_bf16(q, k, vt, nk, a.h)
+                return self._finish(q_in, att, relu, out)
             _, q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach(), x_split=q_split, emit_split=True, want_y=False)
             _, k = ops.linear(kv_in, a.fc_k.weight.detach(), a.fc_k.bias.detach(), x_split=kv_split, emit_split=True, want_y=False)
             if nk % 4 == 0:

@@ -18,6 +18,9 @@ int pointnet_tc(const float*, int64_t, int, int64_t, const float*, const float*,
                 const float*, int, float*, int32_t*, cudaStream_t);
 int flash_attn_tc(const float*, const float*, int64_t, const float*, const float*, int64_t, const float*, const float*,
                   int64_t, float*, int64_t, float*, int64_t, int64_t, int, int, cudaStream_t);
+int bf16_split(const float*, int64_t, int64_t, int64_t, uint16_t*, uint16_t*, int64_t, cudaStream_t);
+int flash_attn_bf16(const uint16_t*, const uint16_t*, int64_t, const uint16_t*, const uint16_t*, int64_t, const uint16_t*,
+                    const uint16_t*, int64_t, float*, int64_t, float*, int64_t, int64_t, int, int, cudaStream_t);
 int flash_attn_simt(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
                     int64_t, int64_t, int, int, cudaStream_t);
 }  // namespace vlsat
@@ -136,4 +139,28 @@ extern "C" int vlsat_pointnet_tc_fwd(const float* x, int64_t n_obj, int c_in, in
     VLSAT_SUPPORT(pointnet_tc_eligible(c_in, c1, c2, c_out, n_pts) && n_pts < (1ll << 31));
     if (n_obj == 0) return VLSAT_OK;
     return pointnet_tc(x, n_obj, c_in, n_pts, w1, b1, w2, b2, w3, b3, c_out, out, argmax, (cudaStream_t)stream);
+}
+
+extern "C" int vlsat_bf16_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, void* hi, void* lo, int64_t ld_out,
+                                void* stream) {
+    VLSAT_REQUIRE(rows >= 0 && cols >= 0);
+    if (rows == 0 || cols == 0) return VLSAT_OK;
+    VLSAT_REQUIRE(x && hi && lo && ldx >= cols && ld_out >= cols);
+    VLSAT_SUPPORT(ld_out % 8 == 0 && ((uintptr_t)hi % 16 == 0) && ((uintptr_t)lo % 16 == 0));
+    return bf16_split(x, ldx, rows, cols, (uint16_t*)hi, (uint16_t*)lo, ld_out, (cudaStream_t)stream);
+}
+
+extern "C" int vlsat_flash_attn_bf16x3_fwd(const void* q_hi, const void* q_lo, int64_t ldq, const void* k_hi, const void* k_lo,
+                                           int64_t ldk, const void* vt_hi, const void* vt_lo, int64_t ldvt, float* out,
+                                           int64_t ldo, float* lse, int64_t nq, int64_t nk, int n_heads, int dk, void* stream) {
+    VLSAT_REQUIRE(nq >= 0 && nk >= 1 && n_heads >= 1);
+    if (nq == 0) return VLSAT_OK;
+    VLSAT_REQUIRE(q_hi && q_lo && k_hi && k_lo && vt_hi && vt_lo && out);
+    VLSAT_REQUIRE(ldq >= (int64_t)n_heads * dk && ldk >= (int64_t)n_heads * dk && ldvt >= nk && ldo >= (int64_t)n_heads * dk);
+    const uintptr_t all = (uintptr_t)q_hi | (uintptr_t)q_lo | (uintptr_t)k_hi | (uintptr_t)k_lo | (uintptr_t)vt_hi |
+                          (uintptr_t)vt_lo | (uintptr_t)out;
+    VLSAT_SUPPORT(all % 16 == 0);
+    return flash_attn_bf16((const uint16_t*)q_hi, (const uint16_t*)q_lo, ldq, (const uint16_t*)k_hi, (const uint16_t*)k_lo, ldk,
+                           (const uint16_t*)vt_hi, (const uint16_t*)vt_lo, ldvt, out, ldo, lse, nq, nk, n_heads, dk,
+                           (cudaStream_t)stream);
 }

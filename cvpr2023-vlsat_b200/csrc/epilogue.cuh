@@ -1,6 +1,7 @@
 // Arguments and fused epilogue shared by the two dense-projection engines (FFMA and tcgen05).
 #pragma once
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace vlsat {
 
@@ -42,7 +43,7 @@ __device__ __forceinline__ float epilogue_one(const vlsat_epilogue& e, float acc
 // tf32 split of one value: hi = round-to-nearest tf32, lo = v - hi
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    u = tc::tf32_rna_bits(v);
     hi = __uint_as_float(u);
     lo = v - hi;
 }

@@ -1,0 +1,317 @@
+// A9 on the tensor cores, BF16x3 variant: streaming softmax(Q K^T / sqrt(dk)) V with every operand split into
+// bf16 (hi, lo) pairs and three kind::f16 MMAs per K step (lo*hi + hi*lo + hi*hi) into fp32 TMEM accumulators.
+//
+// Why not the 3xTF32 split of the projections here: the attention kernel re-reads K and V once per 128-query tile,
+// so it is bound by L2 -> SM bandwidth (~6.5 TB/s aggregate, measured); fp32 hi/lo pairs cost 8 B per element,
+// bf16 pairs 4 B, and the bf16 MMA retires twice the K per instruction. The bf16x3 product error is 2^-17
+// relative per term; through the softmax (64-term dot products scaled by 1/8, convex combination of V) that
+// is <= ~1e-5 of the output scale, the same noise floor the fp32-accumulating tensor core already has.
+//
+// One CTA = 128 queries of one head (dk = 64), KV tiles of 64 keys on a 2-stage TMA ring.
+//   warp 0          TMA producer: Q (hi, lo) once; per tile K (hi, lo) [64 keys x 64] and V^T (hi, lo) [64 dims x 64 keys],
+//                   all K-major rows of exactly 128 bytes (64 bf16) with the 128B swizzle
+//   warp 1          tcgen05.mma issue: S(t) = Q K(t)^T (SS) into TMEM S[t&1]; PV(t) = P(t) V(t) (SS) into TMEM PV[t&1]
+//   warps 2-5, 6-9  two softmax warpgroups (tile parity), one query row per thread: tcgen05.ld S, online softmax in
+//                   the exp2 domain, P split to bf16 hi/lo and written as a swizzled K-major smem operand; the tile's
+//                   P.V is folded into a per-warpgroup fp32 row accumulator; states merged at the end.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <float.h>
+
+namespace vlsat {
+
+using namespace tc;
+
+constexpr int FB_BQ = 128, FB_BKV = 64, FB_DK = 64, FB_THREADS = 320;
+constexpr int FB_Q_BYTES = 2 * FB_BQ * 128;              // Q_hi | Q_lo, 128 rows x 128 B
+constexpr int FB_K_STAGE = 2 * FB_BKV * 128;             // K_hi | K_lo, 64 rows x 128 B
+constexpr int FB_V_STAGE = 2 * FB_DK * 128;              // Vt_hi | Vt_lo
+constexpr int FB_P_BUF = 2 * FB_BQ * 128;                // P_hi | P_lo, 128 rows x 128 B
+constexpr uint32_t FB_TMEM_COLS = 256;                   // S[2] x 64 | PV[2] x 64
+
+__device__ __forceinline__ float fb_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// two floats -> packed bf16x2 (round to nearest even); low half = first argument
+__device__ __forceinline__ uint32_t fb_pack_bf16(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+
+__global__ void bf16_split_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int64_t cols,
+                                  uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t ld_out) {
+    const int64_t c4 = (cols + 3) >> 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * c4) return;
+    const int64_t r = idx / c4, c = (idx % c4) * 4;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (c + i < cols) ? __ldg(x + r * ldx + c + i) : 0.f;
+    uint32_t h01 = fb_pack_bf16(v[0], v[1]), h23 = fb_pack_bf16(v[2], v[3]);
+    const float l0 = v[0] - __uint_as_float(h01 << 16), l1 = v[1] - __uint_as_float(h01 & 0xffff0000u);
+    const float l2 = v[2] - __uint_as_float(h23 << 16), l3 = v[3] - __uint_as_float(h23 & 0xffff0000u);
+    const uint32_t q01 = fb_pack_bf16(l0, l1), q23 = fb_pack_bf16(l2, l3);
+    if (c + 3 < ld_out) {
+        *reinterpret_cast<uint2*>(hi + r * ld_out + c) = make_uint2(h01, h23);
+        *reinterpret_cast<uint2*>(lo + r * ld_out + c) = make_uint2(q01, q23);
+    }
+}
+
+__global__ void __launch_bounds__(FB_THREADS, 1)
+flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
+                       const __grid_constant__ CUtensorMap tm_khi, const __grid_constant__ CUtensorMap tm_klo,
+                       const __grid_constant__ CUtensorMap tm_vhi, const __grid_constant__ CUtensorMap tm_vlo,
+                       float* __restrict__ out, int64_t ldo, float* __restrict__ lse, int nq, int nk, float scale_log2e) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* q_smem = smem;                                  // Q_hi | Q_lo
+    uint8_t* k_smem = q_smem + FB_Q_BYTES;                   // 2 stages x (K_hi | K_lo)
+    uint8_t* v_smem = k_smem + 2 * FB_K_STAGE;               // 2 stages x (Vt_hi | Vt_lo)
+    uint8_t* p_smem = v_smem + 2 * FB_V_STAGE;               // 2 buffers x (P_hi | P_lo)
+    float* mrg = reinterpret_cast<float*>(p_smem + 2 * FB_P_BUF);       // [128][66] merge scratch
+    uint64_t* bars = reinterpret_cast<uint64_t*>(mrg + FB_BQ * 66);
+    uint64_t* q_full = bars;
+    uint64_t* k_full = bars + 1; uint64_t* k_empty = bars + 3;
+    uint64_t* v_full = bars + 5; uint64_t* v_empty = bars + 7;
+    uint64_t* s_full = bars + 9; uint64_t* p_ready = bars + 11; uint64_t* pv_full = bars + 13;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = blockIdx.y;
+    const int q0 = blockIdx.x * FB_BQ;
+    const int n_tiles = (nk + FB_BKV - 1) / FB_BKV;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_qhi); prefetch_tmap(&tm_qlo); prefetch_tmap(&tm_khi);
+        prefetch_tmap(&tm_klo); prefetch_tmap(&tm_vhi); prefetch_tmap(&tm_vlo);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+            mbar_init(&s_full[s], 1); mbar_init(&p_ready[s], 128); mbar_init(&pv_full[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_holder, FB_TMEM_COLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, FB_Q_BYTES);
+            tma_load_2d(q_smem, &tm_qhi, q_full, head * FB_DK, q0);
+            tma_load_2d(q_smem + FB_BQ * 128, &tm_qlo, q_full, head * FB_DK, q0);
+        }
+        __syncwarp();
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s = t & 1;
+            const uint32_t ph = (t >> 1) & 1;
+            const int k0 = t * FB_BKV;
+            mbar_wait(&k_empty[s], ph ^ 1);
+            if (elect_one()) {
+                uint8_t* st = k_smem + s * FB_K_STAGE;
+                mbar_arrive_expect_tx(&k_full[s], FB_K_STAGE);
+                tma_load_2d(st, &tm_khi, &k_full[s], head * FB_DK, k0);                  // rows = keys
+                tma_load_2d(st + FB_BKV * 128, &tm_klo, &k_full[s], head * FB_DK, k0);
+            }
+            __syncwarp();
+            mbar_wait(&v_empty[s], ph ^ 1);
+            if (elect_one()) {
+                uint8_t* st = v_smem + s * FB_V_STAGE;
+                mbar_arrive_expect_tx(&v_full[s], FB_V_STAGE);
+                tma_load_2d(st, &tm_vhi, &v_full[s], k0, head * FB_DK);                  // rows = dims, cols = keys
+                tma_load_2d(st + FB_DK * 128, &tm_vlo, &v_full[s], k0, head * FB_DK);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc<Kind::BF16>(FB_BQ, 64);
+        const uint64_t dq = make_sdesc_k128(smem_u32(q_smem));
+        const uint64_t dk0 = make_sdesc_k128(smem_u32(k_smem));
+        const uint64_t dv0 = make_sdesc_k128(smem_u32(v_smem));
+        const uint64_t dp0 = make_sdesc_k128(smem_u32(p_smem));
+        auto issue_s = [&](int t) {
+            const int s = t & 1;
+            mbar_wait(&k_full[s], (t >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t dk = dk0 + (uint64_t)(s * (FB_K_STAGE >> 4));
+                const uint32_t ts = tmem_base + 64 * s;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {                 // 16 dims (32 bytes) per MMA
+                    mma_ss<Kind::BF16>(ts, dq + ((FB_BQ * 128) >> 4) + 2 * kk, dk + 2 * kk, idesc, kk > 0);            // Q_lo K_hi
+                    mma_ss<Kind::BF16>(ts, dq + 2 * kk, dk + ((FB_BKV * 128) >> 4) + 2 * kk, idesc, 1);                // Q_hi K_lo
+                    mma_ss<Kind::BF16>(ts, dq + 2 * kk, dk + 2 * kk, idesc, 1);                                        // Q_hi K_hi
+                }
+                tc_commit(&k_empty[s]);
+                tc_commit(&s_full[s]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_s(0);
+        if (n_tiles > 1) issue_s(1);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s = t & 1;
+            const uint32_t ph = (t >> 1) & 1;
+            mbar_wait(&v_full[s], ph);
+            mbar_wait(&p_ready[s], ph);                          // P(t) is in smem; S[s] and PV[s] are drained
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t dv = dv0 + (uint64_t)(s * (FB_V_STAGE >> 4));
+                const uint64_t dp = dp0 + (uint64_t)(s * (FB_P_BUF >> 4));
+                const uint32_t tpv = tmem_base + 128 + 64 * s;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {                 // 16 keys per MMA
+                    mma_ss<Kind::BF16>(tpv, dp + ((FB_BQ * 128) >> 4) + 2 * kk, dv + 2 * kk, idesc, kk > 0);           // P_lo V_hi
+                    mma_ss<Kind::BF16>(tpv, dp + 2 * kk, dv + ((FB_DK * 128) >> 4) + 2 * kk, idesc, 1);                // P_hi V_lo
+                    mma_ss<Kind::BF16>(tpv, dp + 2 * kk, dv + 2 * kk, idesc, 1);                                       // P_hi V_hi
+                }
+                tc_commit(&v_empty[s]);
+                tc_commit(&pv_full[s]);
+            }
+            __syncwarp();
+            if (t + 2 < n_tiles) issue_s(t + 2);
+        }
+    } else {
+        const int wg = (warp - 2) >> 2;                          // softmax warpgroup = tile parity = buffer index
+        const int qd = warp & 3;
+        const int row_l = qd * 32 + lane;
+        const int row = q0 + row_l;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const uint32_t t_s = tmem_base + 64 * wg, t_pv = tmem_base + 128 + 64 * wg;
+        uint8_t* p_hi = p_smem + wg * FB_P_BUF + row_l * 128;
+        uint8_t* p_lo = p_hi + FB_BQ * 128;
+        const int sw = row_l & 7;
+        float o[FB_DK];
+#pragma unroll
+        for (int d = 0; d < FB_DK; ++d) o[d] = 0.f;
+        float m_run = -FLT_MAX, l_run = 0.f, corr_prev = 1.f;
+        auto fold = [&](int t, float corr) {
+            mbar_wait(&pv_full[wg], (t >> 1) & 1);
+            tc_fence_after();
+            uint32_t a[32];
+            tmem_ld_32x32(t_pv + lane_off, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], corr, __uint_as_float(a[d]));
+            tmem_ld_32x32(t_pv + lane_off + 32, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o[32 + d] = fmaf(o[32 + d], corr, __uint_as_float(a[d]));
+            tc_fence_before();
+        };
+        int last = -1;
+        for (int t = wg; t < n_tiles; t += 2) {
+            const int k0 = t * FB_BKV;
+            uint32_t r[32], r2[32];
+            mbar_wait(&s_full[wg], (t >> 1) & 1);
+            tc_fence_after();
+            tmem_ld_32x32(t_s + lane_off, r);
+            tmem_ld_32x32(t_s + lane_off + 32, r2);
+            tmem_ld_wait();
+            tc_fence_before();
+            if (k0 + FB_BKV > nk) {                              // ragged last tile
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (k0 + j >= nk) r[j] = __float_as_uint(-FLT_MAX);
+                    if (k0 + 32 + j >= nk) r2[j] = __float_as_uint(-FLT_MAX);
+                }
+            }
+            float mx = -FLT_MAX;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+            const float m_new = fmaxf(m_run, mx * scale_log2e);
+            const float corr = fb_ex2(m_run - m_new);
+            const float neg_m = -m_new;
+            if (last >= 0) fold(last, corr_prev);                // PV[wg] drained => P[wg] is no longer read
+            float rs = 0.f;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {                    // 8 keys = one 16-byte chunk of the P row
+                    float p[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t sv = half ? r2[c * 8 + u] : r[c * 8 + u];
+                        p[u] = fb_ex2(fmaf(__uint_as_float(sv), scale_log2e, neg_m));
+                        rs += p[u];
+                    }
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        h[u] = fb_pack_bf16(p[2 * u], p[2 * u + 1]);
+                        l[u] = fb_pack_bf16(p[2 * u] - __uint_as_float(h[u] << 16), p[2 * u + 1] - __uint_as_float(h[u] & 0xffff0000u));
+                    }
+                    const int pos = (((half * 4 + c) ^ sw) << 4);
+                    *reinterpret_cast<uint4*>(p_hi + pos) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4*>(p_lo + pos) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+            }
+            fence_proxy_async();                                 // generic smem writes -> visible to the tensor core
+            mbar_arrive(&p_ready[wg]);
+            l_run = l_run * corr + rs;
+            m_run = m_new;
+            corr_prev = corr;
+            last = t;
+        }
+        if (last >= 0) fold(last, corr_prev);
+        if (wg == 1) {
+            mrg[row_l * 66 + 0] = m_run; mrg[row_l * 66 + 1] = l_run;
+#pragma unroll
+            for (int d = 0; d < FB_DK; ++d) mrg[row_l * 66 + 2 + d] = o[d];
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (wg == 0 && row < nq) {
+            const float m1 = mrg[row_l * 66 + 0], l1 = mrg[row_l * 66 + 1];
+            const float m = fmaxf(m_run, m1);
+            const float c0 = fb_ex2(m_run - m), c1 = fb_ex2(m1 - m);
+            const float l = l_run * c0 + l1 * c1;
+            const float inv = 1.f / l;
+            float* orow = out + (int64_t)row * ldo + head * FB_DK;
+#pragma unroll
+            for (int d = 0; d < FB_DK; d += 4) {
+                float4 res;
+                res.x = (o[d] * c0 + mrg[row_l * 66 + 2 + d] * c1) * inv;
+                res.y = (o[d + 1] * c0 + mrg[row_l * 66 + 3 + d] * c1) * inv;
+                res.z = (o[d + 2] * c0 + mrg[row_l * 66 + 4 + d] * c1) * inv;
+                res.w = (o[d + 3] * c0 + mrg[row_l * 66 + 5 + d] * c1) * inv;
+                *reinterpret_cast<float4*>(orow + d) = res;
+            }
+            if (lse) lse[(int64_t)head * nq + row] = (m + log2f(l)) * 0.6931471805599453f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
+}
+
+int bf16_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ld_out, cudaStream_t st) {
+    const int64_t n = rows * ((cols + 3) / 4);
+    if (n == 0) return VLSAT_OK;
+    bf16_split_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(x, ldx, rows, cols, hi, lo, ld_out);
+    return finish_launch();
+}
+
+// q_* [nq, H*64] bf16 (row stride ldq elements), k_* [nk, H*64], vt_* [H*64, nk] (row stride ldvt, multiple of 8)
+int flash_attn_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq, const uint16_t* k_hi, const uint16_t* k_lo, int64_t ldk,
+                    const uint16_t* vt_hi, const uint16_t* vt_lo, int64_t ldvt, float* out, int64_t ldo, float* lse,
+                    int64_t nq, int64_t nk, int n_heads, int dk, cudaStream_t st) {
+    if (dk != FB_DK || nq >= (1ll << 31) || nk >= (1ll << 31)) return VLSAT_ERR_UNSUPPORTED;
+    if ((ldq | ldk | ldvt) % 8 || ldo % 4) return VLSAT_ERR_UNSUPPORTED;
+    CUtensorMap tq, tql, tk, tkl, tv, tvl;
+    const uint64_t d = (uint64_t)n_heads * dk;
+    const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    bool ok = make_tmap_2d(&tq, q_hi, BF, 2, nq, d, ldq, 64, FB_BQ) && make_tmap_2d(&tql, q_lo, BF, 2, nq, d, ldq, 64, FB_BQ) &&
+              make_tmap_2d(&tk, k_hi, BF, 2, nk, d, ldk, 64, FB_BKV) && make_tmap_2d(&tkl, k_lo, BF, 2, nk, d, ldk, 64, FB_BKV) &&
+              make_tmap_2d(&tv, vt_hi, BF, 2, d, nk, ldvt, 64, FB_DK) && make_tmap_2d(&tvl, vt_lo, BF, 2, d, nk, ldvt, 64, FB_DK);
+    if (!ok) return VLSAT_ERR_UNSUPPORTED;
+    const size_t smem = FB_Q_BYTES + 2 * FB_K_STAGE + 2 * FB_V_STAGE + 2 * FB_P_BUF + FB_BQ * 66 * 4 + 1024 + 256;
+    cudaFuncSetAttribute(flash_attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((unsigned)ceil_div(nq, FB_BQ), (unsigned)n_heads);
+    const float scale_log2e = 1.4426950408889634f / sqrtf((float)dk);
+    flash_attn_bf16_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tql, tk, tkl, tv, tvl, out, ldo, lse, (int)nq, (int)nk, scale_log2e);
+    return finish_launch();
+}
+
+}  // namespace vlsat

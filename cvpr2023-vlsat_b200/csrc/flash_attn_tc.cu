@@ -7,11 +7,12 @@
 //                by the GEMM, so both MMAs use the plain K-major shared-memory descriptor).
 //   warp 1     : tcgen05.mma issue. S = Q K^T into TMEM (128 lanes x 64 cols); after the softmax warps
 //                have written P (hi, lo) back to TMEM, PV = P V^T^T with the A operand read from TMEM.
-//   warps 2..5 : one query row per thread: tcgen05.ld S, online softmax in the exp2 domain, split P into
-//                tf32 hi/lo, tcgen05.st to TMEM; then fold the tile's P.V into the fp32 row accumulator
-//                kept in registers (o = o * corr + pv), so no TMEM read-modify-write is needed.
-// S, P and the per-tile P.V accumulator are double-buffered in TMEM (512 columns), so the tensor pipe
-// computes S(t+1) while the softmax warps work on tile t, and the fold runs one tile behind.
+//   warps 2..5, 6..9 : two softmax warpgroups, one query row per thread each. Warpgroup g owns the tiles with
+//                t & 1 == g and TMEM buffer g (S, P_hi, P_lo, PV double-buffered = 512 columns): tcgen05.ld S,
+//                online softmax in the exp2 domain, split P into tf32 hi/lo, tcgen05.st to TMEM; the tile's P.V
+//                is folded into a per-warpgroup fp32 row accumulator in registers (o = o * corr + pv). The two
+//                partial (m, l, o) states are merged through shared memory at the end.
+// The softmax is quarter-rate (ex2) bound, so two warpgroups keep the tensor pipe (S(t+2), PV(t+1), ...) busy.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <float.h>
@@ -20,7 +21,7 @@ namespace vlsat {
 
 using namespace tc;
 
-constexpr int FT_BQ = 128, FT_BKV = 64, FT_DK = 64, FT_THREADS = 192, FT_STAGES = 2;
+constexpr int FT_BQ = 128, FT_BKV = 64, FT_DK = 64, FT_THREADS = 320, FT_STAGES = 2;
 constexpr int FT_Q_BYTES = 4 * FT_BQ * 128;              // Q_hi, Q_lo x two 32-float halves
 constexpr int FT_K_STAGE = 4 * FT_BKV * 128;             // K_hi h0,h1 | K_lo h0,h1   (64 rows x 128 B each)
 constexpr int FT_V_STAGE = 4 * FT_DK * 128;              // Vt_hi k0,k1 | Vt_lo k0,k1
@@ -73,7 +74,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_co
     uint64_t* s_full = bars + 9;                             // [2]
     uint64_t* p_ready = bars + 11;                           // [2]
     uint64_t* pv_full = bars + 13;                           // [2]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* all_done = bars + 15;                          // every MMA of this CTA has retired
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
@@ -84,6 +86,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_co
         prefetch_tmap(&tm_qhi); prefetch_tmap(&tm_qlo); prefetch_tmap(&tm_khi);
         prefetch_tmap(&tm_klo); prefetch_tmap(&tm_vhi); prefetch_tmap(&tm_vlo);
         mbar_init(q_full, 1);
+        mbar_init(all_done, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
             mbar_init(&s_full[s], 1); mbar_init(&p_ready[s], 128); mbar_init(&pv_full[s], 1);
@@ -157,12 +160,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_co
         };
         mbar_wait(q_full, 0);
         issue_s(0);
+        if (n_tiles > 1) issue_s(1);
         for (int t = 0; t < n_tiles; ++t) {
             const int s = t & 1;
             const uint32_t ph = (t >> 1) & 1;
-            if (t + 1 < n_tiles) issue_s(t + 1);                 // runs while the softmax warps work on tile t
             mbar_wait(&v_full[s], ph);
-            mbar_wait(&p_ready[s], ph);                          // P(t) is in TMEM
+            mbar_wait(&p_ready[s], ph);                          // P(t) is in TMEM, S[s] and PV[s] are drained
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t dv = dv0 + (uint64_t)(s * (FT_V_STAGE >> 4));
@@ -178,41 +181,47 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_co
                 tc_commit(&pv_full[s]);
             }
             __syncwarp();
+            if (t + 2 < n_tiles) issue_s(t + 2);                 // same buffer as tile t: its S has been consumed
         }
+        if (elect_one()) tc_commit(all_done);
+        __syncwarp();
     } else {
+        const int wg = (warp - 2) >> 2;                          // softmax warpgroup 0 / 1 = TMEM buffer = tile parity
         const int qd = warp & 3;
-        const int row = q0 + qd * 32 + lane;
+        const int row_l = qd * 32 + lane;
+        const int row = q0 + row_l;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const uint32_t t_s = tmem_base + 64 * wg, t_phi = tmem_base + 128 + 64 * wg, t_plo = tmem_base + 256 + 64 * wg,
+                       t_pv = tmem_base + 384 + 64 * wg;
         float o[FT_DK];
 #pragma unroll
         for (int d = 0; d < FT_DK; ++d) o[d] = 0.f;
         float m_run = -FLT_MAX, l_run = 0.f, corr_prev = 1.f;
-        uint32_t r[32], r2[32], lo[32];
-        // o <- o * corr + P(t) V(t), one tile behind the softmax so the MMA pipe never waits for it
+        uint32_t r[32], r2[32];
+        // o <- o * corr + P(t) V(t) for this warpgroup's previous tile (its PV buffer must be drained before P is rewritten)
         auto fold = [&](int t, float corr) {
-            const int s = t & 1;
-            mbar_wait(&pv_full[s], (t >> 1) & 1);
+            mbar_wait(&pv_full[wg], (t >> 1) & 1);
             tc_fence_after();
-            tmem_ld_32x32(tmem_base + 384 + 64 * s + lane_off, r);
-            tmem_ld_32x32(tmem_base + 384 + 64 * s + lane_off + 32, r2);
+            uint32_t a[32];
+            tmem_ld_32x32(t_pv + lane_off, a);
             tmem_ld_wait();
 #pragma unroll
-            for (int d = 0; d < 32; ++d) {
-                o[d] = fmaf(o[d], corr, __uint_as_float(r[d]));
-                o[32 + d] = fmaf(o[32 + d], corr, __uint_as_float(r2[d]));
-            }
+            for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], corr, __uint_as_float(a[d]));
+            tmem_ld_32x32(t_pv + lane_off + 32, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o[32 + d] = fmaf(o[32 + d], corr, __uint_as_float(a[d]));
             tc_fence_before();
         };
-        for (int t = 0; t < n_tiles; ++t) {
-            const int s = t & 1;
+        int last = -1;
+        for (int t = wg; t < n_tiles; t += 2) {
             const int k0 = t * FT_BKV;
-            mbar_wait(&s_full[s], (t >> 1) & 1);
+            mbar_wait(&s_full[wg], (t >> 1) & 1);
             tc_fence_after();
-            tmem_ld_32x32(tmem_base + 64 * s + lane_off, r);
-            tmem_ld_32x32(tmem_base + 64 * s + lane_off + 32, r2);
+            tmem_ld_32x32(t_s + lane_off, r);
+            tmem_ld_32x32(t_s + lane_off + 32, r2);
             tmem_ld_wait();
             const bool tail = k0 + FT_BKV > nk;                  // only the last tile can be ragged
-            float mx = -FLT_MAX;
             if (tail) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -220,48 +229,84 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_co
                     if (k0 + 32 + j >= nk) r2[j] = __float_as_uint(-FLT_MAX);
                 }
             }
+            float mx = -FLT_MAX;
 #pragma unroll
             for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
             const float m_new = fmaxf(m_run, mx * scale_log2e);  // scale > 0 commutes with max
             const float corr = ex2(m_run - m_new);
             const float neg_m = -m_new;
+            if (last >= 0) fold(last, corr_prev);                // drains PV[wg] and guarantees P[wg] is no longer read
             float rs = 0.f;
+            {
+                uint32_t lo[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float p = ex2(fmaf(__uint_as_float(r[j]), scale_log2e, neg_m));
-                rs += p;
-                uint32_t h;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(p));
-                r[j] = h; lo[j] = __float_as_uint(p - __uint_as_float(h));
-            }
-            tmem_st_32x32(tmem_base + 128 + 64 * s + lane_off, r);
-            tmem_st_32x32(tmem_base + 256 + 64 * s + lane_off, lo);
+                for (int j = 0; j < 32; ++j) {
+                    const float p = ex2(fmaf(__uint_as_float(r[j]), scale_log2e, neg_m));
+                    rs += p;
+                    const uint32_t h = tc::tf32_rna_bits(p);
+                    r[j] = h; lo[j] = __float_as_uint(p - __uint_as_float(h));
+                }
+                tmem_st_32x32(t_phi + lane_off, r);
+                tmem_st_32x32(t_plo + lane_off, lo);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float p = ex2(fmaf(__uint_as_float(r2[j]), scale_log2e, neg_m));
-                rs += p;
-                uint32_t h;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(p));
-                r2[j] = h; lo[j] = __float_as_uint(p - __uint_as_float(h));
+                for (int j = 0; j < 32; ++j) {
+                    const float p = ex2(fmaf(__uint_as_float(r2[j]), scale_log2e, neg_m));
+                    rs += p;
+                    const uint32_t h = tc::tf32_rna_bits(p);
+                    r2[j] = h; lo[j] = __float_as_uint(p - __uint_as_float(h));
+                }
+                tmem_st_32x32(t_phi + lane_off + 32, r2);
+                tmem_st_32x32(t_plo + lane_off + 32, lo);
             }
-            tmem_st_32x32(tmem_base + 128 + 64 * s + lane_off + 32, r2);
-            tmem_st_32x32(tmem_base + 256 + 64 * s + lane_off + 32, lo);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&p_ready[s]);
+            mbar_arrive(&p_ready[wg]);
             l_run = l_run * corr + rs;
             m_run = m_new;
-            if (t > 0) fold(t - 1, corr_prev);
             corr_prev = corr;
+            last = t;
         }
-        fold(n_tiles - 1, corr_prev);
-        if (row < nq) {
-            const float inv = 1.f / l_run;
+        if (last >= 0) {
+            // the correction for the last tile's P.V is 1 relative to the final running max of this warpgroup
+            mbar_wait(&pv_full[wg], (last >> 1) & 1);
+            tc_fence_after();
+            uint32_t a[32];
+            tmem_ld_32x32(t_pv + lane_off, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], corr_prev, __uint_as_float(a[d]));
+            tmem_ld_32x32(t_pv + lane_off + 32, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o[32 + d] = fmaf(o[32 + d], corr_prev, __uint_as_float(a[d]));
+            tc_fence_before();
+        }
+        // ---- merge the two warpgroups' partial softmax states (K staging memory is free by now)
+        float* mrg = reinterpret_cast<float*>(k_smem);           // [128][66]: m, l, o[64]
+        if (wg == 1) {
+            mbar_wait(all_done, 0);                              // K staging is reused: no MMA may still read it
+            mrg[row_l * 66 + 0] = m_run; mrg[row_l * 66 + 1] = l_run;
+#pragma unroll
+            for (int d = 0; d < FT_DK; ++d) mrg[row_l * 66 + 2 + d] = o[d];
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (wg == 0 && row < nq) {
+            const float m1 = mrg[row_l * 66 + 0], l1 = mrg[row_l * 66 + 1];
+            const float m = fmaxf(m_run, m1);
+            const float c0 = ex2(m_run - m), c1 = ex2(m1 - m);
+            const float l = l_run * c0 + l1 * c1;
+            const float inv = 1.f / l;
             float* orow = out + (int64_t)row * ldo + head * FT_DK;
 #pragma unroll
-            for (int d = 0; d < FT_DK; d += 4)
-                *reinterpret_cast<float4*>(orow + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
-            if (lse) lse[(int64_t)head * nq + row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+            for (int d = 0; d < FT_DK; d += 4) {
+                float4 res;
+                res.x = (o[d] * c0 + mrg[row_l * 66 + 2 + d] * c1) * inv;
+                res.y = (o[d + 1] * c0 + mrg[row_l * 66 + 3 + d] * c1) * inv;
+                res.z = (o[d + 2] * c0 + mrg[row_l * 66 + 4 + d] * c1) * inv;
+                res.w = (o[d + 3] * c0 + mrg[row_l * 66 + 5 + d] * c1) * inv;
+                *reinterpret_cast<float4*>(orow + d) = res;
+            }
+            if (lse) lse[(int64_t)head * nq + row] = (m + log2f(l)) * 0.6931471805599453f;
         }
     }
     tc_fence_before();

@@ -212,7 +212,7 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         uint32_t hi;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(hv[u]));
+                        hi = tc::tf32_rna_bits(hv[u]);
                         a[4 * j + u] = hi; lo[4 * j + u] = __float_as_uint(hv[u] - __uint_as_float(hi));
                     }
                 }

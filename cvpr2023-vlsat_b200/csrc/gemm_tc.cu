@@ -40,7 +40,7 @@ __global__ void tf32_split_kernel(const float* __restrict__ x, int64_t ldx, int6
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         uint32_t u;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(in[i]));
+        u = tc::tf32_rna_bits(in[i]);
         h[i] = __uint_as_float(u);
         l[i] = in[i] - h[i];
     }

@@ -47,7 +47,7 @@ __device__ __forceinline__ void pt_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void pt_split(float v, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+    hi = tc::tf32_rna_bits(v);
     lo = __float_as_uint(v - __uint_as_float(hi));
 }
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }

@@ -73,6 +73,10 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// round-to-nearest (ties away from zero) to tf32 = cvt.rna.tf32.f32, done with two full-rate integer ops instead
+// of the quarter-rate conversion pipe: add half an ulp of the 10-bit mantissa to the magnitude, clear 13 bits.
+__device__ __forceinline__ uint32_t tf32_rna_bits(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
+
 enum class Kind { TF32, BF16 };
 
 template <Kind K>

@@ -387,6 +387,37 @@ def flash_attn_tc(q, k, vt, nk: int, n_heads: int, want_lse: bool = False):
     return (out, lse) if want_lse else out
 
 
+ATTN_ENGINE = os.environ.get("VLSAT_ATTN_ENGINE", "bf16x3")      # 'bf16x3' (default) or 'tf32x3'
+
+
+def bf16_split(x: torch.Tensor):
+    """(hi, lo) bf16 pair of an fp32 matrix: hi = bf16(x), lo = bf16(x - hi); compact, row stride padded to 8."""
+    xp, ldx = _rows(x, "x")
+    r, c = x.shape
+    ld = (c + 7) // 8 * 8
+    hl = torch.empty((2, r, ld), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_call("vlsat_bf16_split", xp, ldx, r, c, hl[0].data_ptr(), hl[1].data_ptr(), ld, _stream()), "vlsat_bf16_split")
+    return hl[0], hl[1]
+
+
+def flash_attn_bf16(q, k, vt, nk: int, n_heads: int, want_lse: bool = False):
+    """Tensor-core streaming attention, BF16x3 operands. q [nq, D], k [nk, D], vt [D, >= nk] fp32 (column-slice views
+    allowed); D = n_heads * 64."""
+    nq, d = q.shape
+    if d != n_heads * 64:
+        raise ValueError("flash_attn_bf16 needs head size 64")
+    qh, ql = bf16_split(q)
+    kh, kl = bf16_split(k)
+    vh, vl = bf16_split(vt[:, :nk])
+    out = torch.empty((nq, d), device=q.device, dtype=torch.float32)
+    lse = torch.empty((n_heads, nq), device=q.device, dtype=torch.float32) if want_lse else None
+    st = _call("vlsat_flash_attn_bf16x3_fwd", qh.data_ptr(), ql.data_ptr(), qh.shape[1], kh.data_ptr(), kl.data_ptr(), kh.shape[1],
+               vh.data_ptr(), vl.data_ptr(), vh.shape[1], out.data_ptr(), d, lse.data_ptr() if want_lse else None,
+               nq, nk, n_heads, 64, _stream(), work=(4.0 * nq * nk * d, 4.0 * (2 * nq * d + 2 * nk * d)))
+    _lib.check(st, "vlsat_flash_attn_bf16x3_fwd")
+    return (out, lse) if want_lse else out
+
+
 # -------------------------------------------------------------------------------------- graph attention
 def build_csr(index_row: torch.Tensor, n_nodes: int):
     """Stable grouping of edges by ``index_row``: (row_ptr [N+1] int32, perm [E] int32)."""

@@ -168,6 +168,18 @@ int vlsat_flash_attn_tc_fwd(const float* q_hi, const float* q_lo, int64_t ldq,
                             float* out, int64_t ldo, float* lse, int64_t nq, int64_t nk, int n_heads, int dk,
                             void* stream);
 
+/* BF16x3 engine of the same operation (default for dk = 64): operands are bf16 (hi, lo) pairs (vlsat_bf16_split:
+ * hi = bf16(x), lo = bf16(x - hi); uint16 storage) of Q [nq, H*64], K [nk, H*64], V^T [H*64, nk]; row strides in
+ * elements, multiples of 8. Halves the L2->SM traffic that bounds this kernel and doubles the MMA rate relative
+ * to the 3xTF32 form; product error 2^-17 relative (see csrc/flash_attn_bf16.cu). */
+int vlsat_bf16_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, void* hi, void* lo, int64_t ld_out,
+                     void* stream);
+int vlsat_flash_attn_bf16x3_fwd(const void* q_hi, const void* q_lo, int64_t ldq,
+                                const void* k_hi, const void* k_lo, int64_t ldk,
+                                const void* vt_hi, const void* vt_lo, int64_t ldvt,
+                                float* out, int64_t ldo, float* lse, int64_t nq, int64_t nk, int n_heads, int dk,
+                                void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * A8  graph attention layer core (network_MMG.py:34-41,96-104; network_util.py:50-73).
  *   vlsat_build_csr: stable counting sort of edges by index_row (= edge_index[0] for

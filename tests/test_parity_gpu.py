@@ -355,3 +355,20 @@ def test_tensor_core_flash_attention_against_fp64(nq, nk):
     got, lse = ops.flash_attn_tc(q.to(DEV), k.to(DEV), vt.to(DEV), nk, h, want_lse=True)
     assert_close(got, want, "tensor-core flash attention", rtol=1e-4, atol=1e-5)
     assert_close(lse, torch.logsumexp(sc, -1).float(), "lse", rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("nq,nk", [(128, 64), (1, 1), (100, 257), (2400, 2400), (130, 30), (64, 1000), (300, 129)])
+def test_bf16x3_flash_attention_against_fp64(nq, nk):
+    """The BF16x3 attention engine (default for cross_attn_rel): product error 2^-17, checked against fp64."""
+    h, dk = 8, 64
+    g = torch.Generator().manual_seed(nq * 5 + nk)
+    q, k, v = (torch.randn(n, 512, generator=g) * 1.5 for n in (nq, nk, nk))
+    qh, kh, vh = (t.double().view(-1, h, dk).permute(1, 0, 2) for t in (q, k, v))
+    sc = qh @ kh.transpose(1, 2) / dk ** 0.5
+    want = (torch.softmax(sc, -1) @ vh).permute(1, 0, 2).reshape(nq, 512).float()
+    pad = (nk + 3) // 4 * 4
+    vt = torch.zeros(512, pad)
+    vt[:, :nk] = v.t()
+    got, lse = ops.flash_attn_bf16(q.to(DEV), k.to(DEV), vt.to(DEV), nk, h, want_lse=True)
+    assert_close(got, want, "bf16x3 flash attention", rtol=1e-3, atol=5e-5)
+    assert_close(lse, torch.logsumexp(sc, -1).float(), "lse", rtol=1e-4, atol=5e-5)
