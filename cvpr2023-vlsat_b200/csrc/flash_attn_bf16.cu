@@ -22,12 +22,12 @@ namespace vlsat {
 
 using namespace tc;
 
-constexpr int FB_BQ = 128, FB_BKV = 64, FB_DK = 64, FB_THREADS = 320;
+constexpr int FB_BQ = 128, FB_BKV = 64, FB_DK = 64, FB_THREADS = 352;   // + warp 10: V producer
 constexpr int FB_Q_BYTES = 2 * FB_BQ * 128;              // Q_hi | Q_lo, 128 rows x 128 B
 constexpr int FB_K_STAGE = 2 * FB_BKV * 128;             // K_hi | K_lo, 64 rows x 128 B
 constexpr int FB_V_STAGE = 2 * FB_DK * 128;              // Vt_hi | Vt_lo
 constexpr int FB_P_BUF = 2 * FB_BQ * 128;                // P_hi | P_lo, 128 rows x 128 B
-constexpr uint32_t FB_TMEM_COLS = 256;                   // S[2] x 64 | PV[2] x 64
+constexpr uint32_t FB_TMEM_COLS = 512;                   // S[4] x 64 (two tiles ahead per warpgroup) | PV[2] x 64 at 256
 
 __device__ __forceinline__ float fb_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // two floats -> packed bf16x2 (round to nearest even); low half = first argument
@@ -72,8 +72,8 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1; uint64_t* k_empty = bars + 3;
     uint64_t* v_full = bars + 5; uint64_t* v_empty = bars + 7;
-    uint64_t* s_full = bars + 9; uint64_t* p_ready = bars + 11; uint64_t* pv_full = bars + 13;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* s_full = bars + 9;  /* [4] */ uint64_t* p_ready = bars + 13; uint64_t* pv_full = bars + 15;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
@@ -86,7 +86,7 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
         mbar_init(q_full, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-            mbar_init(&s_full[s], 1); mbar_init(&p_ready[s], 128); mbar_init(&pv_full[s], 1);
+            mbar_init(&s_full[s], 1); mbar_init(&s_full[2 + s], 1); mbar_init(&p_ready[s], 128); mbar_init(&pv_full[s], 1);
         }
         fence_barrier_init();
     }
@@ -106,21 +106,27 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
         for (int t = 0; t < n_tiles; ++t) {
             const int s = t & 1;
             const uint32_t ph = (t >> 1) & 1;
-            const int k0 = t * FB_BKV;
             mbar_wait(&k_empty[s], ph ^ 1);
             if (elect_one()) {
                 uint8_t* st = k_smem + s * FB_K_STAGE;
                 mbar_arrive_expect_tx(&k_full[s], FB_K_STAGE);
-                tma_load_2d(st, &tm_khi, &k_full[s], head * FB_DK, k0);                  // rows = keys
-                tma_load_2d(st + FB_BKV * 128, &tm_klo, &k_full[s], head * FB_DK, k0);
+                tma_load_2d(st, &tm_khi, &k_full[s], head * FB_DK, t * FB_BKV);                  // rows = keys
+                tma_load_2d(st + FB_BKV * 128, &tm_klo, &k_full[s], head * FB_DK, t * FB_BKV);
             }
             __syncwarp();
+        }
+    } else if (warp == 10) {
+        // V producer on its own warp: K runs up to four tiles ahead of V (S is issued early), so one in-order
+        // producer would deadlock on the V ring while the MMA warp waits for K
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s = t & 1;
+            const uint32_t ph = (t >> 1) & 1;
             mbar_wait(&v_empty[s], ph ^ 1);
             if (elect_one()) {
                 uint8_t* st = v_smem + s * FB_V_STAGE;
                 mbar_arrive_expect_tx(&v_full[s], FB_V_STAGE);
-                tma_load_2d(st, &tm_vhi, &v_full[s], k0, head * FB_DK);                  // rows = dims, cols = keys
-                tma_load_2d(st + FB_DK * 128, &tm_vlo, &v_full[s], k0, head * FB_DK);
+                tma_load_2d(st, &tm_vhi, &v_full[s], t * FB_BKV, head * FB_DK);                  // rows = dims, cols = keys
+                tma_load_2d(st + FB_DK * 128, &tm_vlo, &v_full[s], t * FB_BKV, head * FB_DK);
             }
             __syncwarp();
         }
@@ -136,7 +142,7 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t dk = dk0 + (uint64_t)(s * (FB_K_STAGE >> 4));
-                const uint32_t ts = tmem_base + 64 * s;
+                const uint32_t ts = tmem_base + 64 * (t & 3);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {                 // 16 dims (32 bytes) per MMA
                     mma_ss<Kind::BF16>(ts, dq + ((FB_BQ * 128) >> 4) + 2 * kk, dk + 2 * kk, idesc, kk > 0);            // Q_lo K_hi
@@ -144,23 +150,22 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
                     mma_ss<Kind::BF16>(ts, dq + 2 * kk, dk + 2 * kk, idesc, 1);                                        // Q_hi K_hi
                 }
                 tc_commit(&k_empty[s]);
-                tc_commit(&s_full[s]);
+                tc_commit(&s_full[t & 3]);
             }
             __syncwarp();
         };
         mbar_wait(q_full, 0);
-        issue_s(0);
-        if (n_tiles > 1) issue_s(1);
+        for (int t = 0; t < 4 && t < n_tiles; ++t) issue_s(t);  // every warpgroup always has its next S tile ready
         for (int t = 0; t < n_tiles; ++t) {
             const int s = t & 1;
             const uint32_t ph = (t >> 1) & 1;
             mbar_wait(&v_full[s], ph);
-            mbar_wait(&p_ready[s], ph);                          // P(t) is in smem; S[s] and PV[s] are drained
+            mbar_wait(&p_ready[s], ph);                          // P(t) is in smem; S[t&3] and PV[s] are drained
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t dv = dv0 + (uint64_t)(s * (FB_V_STAGE >> 4));
                 const uint64_t dp = dp0 + (uint64_t)(s * (FB_P_BUF >> 4));
-                const uint32_t tpv = tmem_base + 128 + 64 * s;
+                const uint32_t tpv = tmem_base + 256 + 64 * s;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {                 // 16 keys per MMA
                     mma_ss<Kind::BF16>(tpv, dp + ((FB_BQ * 128) >> 4) + 2 * kk, dv + 2 * kk, idesc, kk > 0);           // P_lo V_hi
@@ -171,7 +176,7 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
                 tc_commit(&pv_full[s]);
             }
             __syncwarp();
-            if (t + 2 < n_tiles) issue_s(t + 2);
+            if (t + 4 < n_tiles) issue_s(t + 4);                 // reuses S[t & 3], consumed by the softmax of tile t
         }
     } else {
         const int wg = (warp - 2) >> 2;                          // softmax warpgroup = tile parity = buffer index
@@ -179,7 +184,7 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
         const int row_l = qd * 32 + lane;
         const int row = q0 + row_l;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const uint32_t t_s = tmem_base + 64 * wg, t_pv = tmem_base + 128 + 64 * wg;
+        const uint32_t t_pv = tmem_base + 256 + 64 * wg;
         uint8_t* p_hi = p_smem + wg * FB_P_BUF + row_l * 128;
         uint8_t* p_lo = p_hi + FB_BQ * 128;
         const int sw = row_l & 7;
@@ -205,7 +210,8 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
         for (int t = wg; t < n_tiles; t += 2) {
             const int k0 = t * FB_BKV;
             uint32_t r[32], r2[32];
-            mbar_wait(&s_full[wg], (t >> 1) & 1);
+            const uint32_t t_s = tmem_base + 64 * (t & 3);
+            mbar_wait(&s_full[t & 3], (t >> 2) & 1);
             tc_fence_after();
             tmem_ld_32x32(t_s + lane_off, r);
             tmem_ld_32x32(t_s + lane_off + 32, r2);
@@ -240,8 +246,14 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
                     uint32_t h[4], l[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        h[u] = fb_pack_bf16(p[2 * u], p[2 * u + 1]);
-                        l[u] = fb_pack_bf16(p[2 * u] - __uint_as_float(h[u] << 16), p[2 * u + 1] - __uint_as_float(h[u] & 0xffff0000u));
+                        // bf16 split with full-rate integer ops (the conversion pipe is shared with ex2): round half up
+                        // on the magnitude, keep the upper 16 bits; lo = p - hi is exact in fp32 and rounded the same way
+                        const uint32_t ha = (__float_as_uint(p[2 * u]) + 0x8000u) & 0xffff0000u;
+                        const uint32_t hb = (__float_as_uint(p[2 * u + 1]) + 0x8000u) & 0xffff0000u;
+                        const uint32_t la = __float_as_uint(p[2 * u] - __uint_as_float(ha)) + 0x8000u;
+                        const uint32_t lb = __float_as_uint(p[2 * u + 1] - __uint_as_float(hb)) + 0x8000u;
+                        h[u] = __byte_perm(ha, hb, 0x7632);      // {hb.hi16, ha.hi16}: lower address = even key
+                        l[u] = __byte_perm(la, lb, 0x7632);
                     }
                     const int pos = (((half * 4 + c) ^ sw) << 4);
                     *reinterpret_cast<uint4*>(p_hi + pos) = make_uint4(h[0], h[1], h[2], h[3]);
