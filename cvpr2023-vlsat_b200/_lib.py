@@ -53,12 +53,13 @@ SIGNATURES = {
     "vlsat_permute_rows": [vp, i64, vp, i64, i32, vp, i64, i32, vp],
     "vlsat_permute_edges": [vp, vp, i64, vp, vp],
     "vlsat_bf16_split": [vp, i64, i64, i64, vp, vp, i64, vp],
-    "vlsat_flash_attn_bf16x3_fwd": [vp, vp, i64, vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp],
+    "vlsat_flash_attn_bf16x3_fwd": [vp, vp, i64, vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, sz, vp],
+    "vlsat_flash_attn_bf16x3_workspace_bytes": [i64, i64, i32],
     "vlsat_build_csr": [vp, i64, i64, vp, vp, vp, sz, vp],
     "vlsat_gat_edge_fwd": [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64,
                            i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, vp, vp],
 }
-_RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
+_RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
 
 _lib = None
 

@@ -20,7 +20,8 @@ int flash_attn_tc(const float*, const float*, int64_t, const float*, const float
                   int64_t, float*, int64_t, float*, int64_t, int64_t, int, int, cudaStream_t);
 int bf16_split(const float*, int64_t, int64_t, int64_t, uint16_t*, uint16_t*, int64_t, cudaStream_t);
 int flash_attn_bf16(const uint16_t*, const uint16_t*, int64_t, const uint16_t*, const uint16_t*, int64_t, const uint16_t*,
-                    const uint16_t*, int64_t, float*, int64_t, float*, int64_t, int64_t, int, int, cudaStream_t);
+                    const uint16_t*, int64_t, float*, int64_t, float*, int64_t, int64_t, int, int, void*, size_t, cudaStream_t);
+size_t flash_attn_bf16_workspace_bytes(int64_t, int64_t, int, int*);
 int flash_attn_simt(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
                     int64_t, int64_t, int, int, cudaStream_t);
 }  // namespace vlsat
@@ -152,15 +153,20 @@ extern "C" int vlsat_bf16_split(const float* x, int64_t ldx, int64_t rows, int64
 
 extern "C" int vlsat_flash_attn_bf16x3_fwd(const void* q_hi, const void* q_lo, int64_t ldq, const void* k_hi, const void* k_lo,
                                            int64_t ldk, const void* vt_hi, const void* vt_lo, int64_t ldvt, float* out,
-                                           int64_t ldo, float* lse, int64_t nq, int64_t nk, int n_heads, int dk, void* stream) {
+                                           int64_t ldo, float* lse, int64_t nq, int64_t nk, int n_heads, int dk,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
     VLSAT_REQUIRE(nq >= 0 && nk >= 1 && n_heads >= 1);
     if (nq == 0) return VLSAT_OK;
     VLSAT_REQUIRE(q_hi && q_lo && k_hi && k_lo && vt_hi && vt_lo && out);
     VLSAT_REQUIRE(ldq >= (int64_t)n_heads * dk && ldk >= (int64_t)n_heads * dk && ldvt >= nk && ldo >= (int64_t)n_heads * dk);
     const uintptr_t all = (uintptr_t)q_hi | (uintptr_t)q_lo | (uintptr_t)k_hi | (uintptr_t)k_lo | (uintptr_t)vt_hi |
-                          (uintptr_t)vt_lo | (uintptr_t)out;
+                          (uintptr_t)vt_lo | (uintptr_t)out | (uintptr_t)workspace;
     VLSAT_SUPPORT(all % 16 == 0);
     return flash_attn_bf16((const uint16_t*)q_hi, (const uint16_t*)q_lo, ldq, (const uint16_t*)k_hi, (const uint16_t*)k_lo, ldk,
                            (const uint16_t*)vt_hi, (const uint16_t*)vt_lo, ldvt, out, ldo, lse, nq, nk, n_heads, dk,
-                           (cudaStream_t)stream);
+                           workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t vlsat_flash_attn_bf16x3_workspace_bytes(int64_t nq, int64_t nk, int n_heads) {
+    return flash_attn_bf16_workspace_bytes(nq, nk, n_heads, nullptr);
 }

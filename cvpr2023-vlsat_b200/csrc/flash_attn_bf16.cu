@@ -7,7 +7,7 @@
 // relative per term; through the softmax (64-term dot products scaled by 1/8, convex combination of V) that
 // is <= ~1e-5 of the output scale, the same noise floor the fp32-accumulating tensor core already has.
 //
-// One CTA = 128 queries of one head (dk = 64), KV tiles of 64 keys on a 2-stage TMA ring.
+// One CTA = 256 queries (two Q tiles) of one head (dk = 64), KV tiles of 64 keys on 2-stage TMA rings, optional KV split.
 //   warp 0          TMA producer: Q (hi, lo) once; per tile K (hi, lo) [64 keys x 64] and V^T (hi, lo) [64 dims x 64 keys],
 //                   all K-major rows of exactly 128 bytes (64 bf16) with the 128B swizzle
 //   warp 1          tcgen05.mma issue: S(t) = Q K(t)^T (SS) into TMEM S[t&1]; PV(t) = P(t) V(t) (SS) into TMEM PV[t&1]
@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 namespace vlsat {
 
@@ -27,7 +28,7 @@ constexpr int FB_Q_BYTES = 2 * FB_BQ * 128;              // Q_hi | Q_lo, 128 row
 constexpr int FB_K_STAGE = 2 * FB_BKV * 128;             // K_hi | K_lo, 64 rows x 128 B
 constexpr int FB_V_STAGE = 2 * FB_DK * 128;              // Vt_hi | Vt_lo
 constexpr int FB_P_BUF = 2 * FB_BQ * 128;                // P_hi | P_lo, 128 rows x 128 B
-constexpr uint32_t FB_TMEM_COLS = 512;                   // S[4] x 64 (two tiles ahead per warpgroup) | PV[2] x 64 at 256
+constexpr uint32_t FB_TMEM_COLS = 512;                   // S[g][b] x 64 at 64*(2g+b) | PV[g] x 64 at 256 + 64 g
 
 __device__ __forceinline__ float fb_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // two floats -> packed bf16x2 (round to nearest even); low half = first argument
@@ -56,29 +57,43 @@ __global__ void bf16_split_kernel(const float* __restrict__ x, int64_t ldx, int6
     }
 }
 
+// Partial softmax state of one KV split: o (un-normalised, relative to m), m (running max, exp2 domain), l (sum).
+struct FlashPartial {
+    float* o;          // [splits, nq, H*64]
+    float* m;          // [splits, H, nq]
+    float* l;          // [splits, H, nq]
+};
+
+// One CTA = 256 queries (two 128-row Q tiles, one per softmax warpgroup) of one head over the KV tiles
+// [tile_begin, tile_end) of split blockIdx.z: every K / V tile fetched from L2 serves both Q tiles, which halves
+// the L2 -> SM traffic that bounds this kernel.
 __global__ void __launch_bounds__(FB_THREADS, 1)
 flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
                        const __grid_constant__ CUtensorMap tm_khi, const __grid_constant__ CUtensorMap tm_klo,
                        const __grid_constant__ CUtensorMap tm_vhi, const __grid_constant__ CUtensorMap tm_vlo,
-                       float* __restrict__ out, int64_t ldo, float* __restrict__ lse, int nq, int nk, float scale_log2e) {
+                       float* __restrict__ out, int64_t ldo, float* __restrict__ lse, FlashPartial part,
+                       int nq, int nk, int n_heads, int tiles_per_split, float scale_log2e) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* q_smem = smem;                                  // Q_hi | Q_lo
-    uint8_t* k_smem = q_smem + FB_Q_BYTES;                   // 2 stages x (K_hi | K_lo)
+    uint8_t* q_smem = smem;                                  // [g][Q_hi | Q_lo], g = 0, 1
+    uint8_t* k_smem = q_smem + 2 * FB_Q_BYTES;               // 2 stages x (K_hi | K_lo)
     uint8_t* v_smem = k_smem + 2 * FB_K_STAGE;               // 2 stages x (Vt_hi | Vt_lo)
-    uint8_t* p_smem = v_smem + 2 * FB_V_STAGE;               // 2 buffers x (P_hi | P_lo)
-    float* mrg = reinterpret_cast<float*>(p_smem + 2 * FB_P_BUF);       // [128][66] merge scratch
-    uint64_t* bars = reinterpret_cast<uint64_t*>(mrg + FB_BQ * 66);
+    uint8_t* p_smem = v_smem + 2 * FB_V_STAGE;               // [g][P_hi | P_lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + 2 * FB_P_BUF);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1; uint64_t* k_empty = bars + 3;
     uint64_t* v_full = bars + 5; uint64_t* v_empty = bars + 7;
-    uint64_t* s_full = bars + 9;  /* [4] */ uint64_t* p_ready = bars + 13; uint64_t* pv_full = bars + 15;
+    uint64_t* s_full = bars + 9;      // [g * 2 + b]
+    uint64_t* p_ready = bars + 13;    // [g]
+    uint64_t* pv_full = bars + 15;    // [g]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
-    const int q0 = blockIdx.x * FB_BQ;
-    const int n_tiles = (nk + FB_BKV - 1) / FB_BKV;
+    const int q0 = blockIdx.x * 2 * FB_BQ;
+    const int n_tiles_all = (nk + FB_BKV - 1) / FB_BKV;
+    const int tile_begin = blockIdx.z * tiles_per_split;
+    const int n_tiles = max(0, min(n_tiles_all, tile_begin + tiles_per_split) - tile_begin);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_qhi); prefetch_tmap(&tm_qlo); prefetch_tmap(&tm_khi);
@@ -98,102 +113,108 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
 
     if (warp == 0) {
         if (elect_one()) {
-            mbar_arrive_expect_tx(q_full, FB_Q_BYTES);
-            tma_load_2d(q_smem, &tm_qhi, q_full, head * FB_DK, q0);
-            tma_load_2d(q_smem + FB_BQ * 128, &tm_qlo, q_full, head * FB_DK, q0);
+            mbar_arrive_expect_tx(q_full, 2 * FB_Q_BYTES);
+            for (int g = 0; g < 2; ++g) {
+                tma_load_2d(q_smem + g * FB_Q_BYTES, &tm_qhi, q_full, head * FB_DK, q0 + g * FB_BQ);
+                tma_load_2d(q_smem + g * FB_Q_BYTES + FB_BQ * 128, &tm_qlo, q_full, head * FB_DK, q0 + g * FB_BQ);
+            }
         }
         __syncwarp();
-        for (int t = 0; t < n_tiles; ++t) {
-            const int s = t & 1;
-            const uint32_t ph = (t >> 1) & 1;
-            mbar_wait(&k_empty[s], ph ^ 1);
+        for (int i = 0; i < n_tiles; ++i) {
+            const int s = i & 1;
+            mbar_wait(&k_empty[s], ((i >> 1) & 1) ^ 1);
             if (elect_one()) {
                 uint8_t* st = k_smem + s * FB_K_STAGE;
                 mbar_arrive_expect_tx(&k_full[s], FB_K_STAGE);
-                tma_load_2d(st, &tm_khi, &k_full[s], head * FB_DK, t * FB_BKV);                  // rows = keys
-                tma_load_2d(st + FB_BKV * 128, &tm_klo, &k_full[s], head * FB_DK, t * FB_BKV);
+                tma_load_2d(st, &tm_khi, &k_full[s], head * FB_DK, (tile_begin + i) * FB_BKV);          // rows = keys
+                tma_load_2d(st + FB_BKV * 128, &tm_klo, &k_full[s], head * FB_DK, (tile_begin + i) * FB_BKV);
             }
             __syncwarp();
         }
     } else if (warp == 10) {
-        // V producer on its own warp: K runs up to four tiles ahead of V (S is issued early), so one in-order
-        // producer would deadlock on the V ring while the MMA warp waits for K
-        for (int t = 0; t < n_tiles; ++t) {
-            const int s = t & 1;
-            const uint32_t ph = (t >> 1) & 1;
-            mbar_wait(&v_empty[s], ph ^ 1);
+        // V producer on its own warp: S tiles are issued ahead of the P.V products, so one in-order producer would
+        // stall the K ring behind the V ring while the MMA warp waits for K
+        for (int i = 0; i < n_tiles; ++i) {
+            const int s = i & 1;
+            mbar_wait(&v_empty[s], ((i >> 1) & 1) ^ 1);
             if (elect_one()) {
                 uint8_t* st = v_smem + s * FB_V_STAGE;
                 mbar_arrive_expect_tx(&v_full[s], FB_V_STAGE);
-                tma_load_2d(st, &tm_vhi, &v_full[s], t * FB_BKV, head * FB_DK);                  // rows = dims, cols = keys
-                tma_load_2d(st + FB_DK * 128, &tm_vlo, &v_full[s], t * FB_BKV, head * FB_DK);
+                tma_load_2d(st, &tm_vhi, &v_full[s], (tile_begin + i) * FB_BKV, head * FB_DK);          // rows = dims, cols = keys
+                tma_load_2d(st + FB_DK * 128, &tm_vlo, &v_full[s], (tile_begin + i) * FB_BKV, head * FB_DK);
             }
             __syncwarp();
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc<Kind::BF16>(FB_BQ, 64);
-        const uint64_t dq = make_sdesc_k128(smem_u32(q_smem));
+        const uint64_t dq0 = make_sdesc_k128(smem_u32(q_smem));
         const uint64_t dk0 = make_sdesc_k128(smem_u32(k_smem));
         const uint64_t dv0 = make_sdesc_k128(smem_u32(v_smem));
         const uint64_t dp0 = make_sdesc_k128(smem_u32(p_smem));
-        auto issue_s = [&](int t) {
-            const int s = t & 1;
-            mbar_wait(&k_full[s], (t >> 1) & 1);
+        // S(g, i) = Q_g K(i)^T for both Q tiles; releases the K stage afterwards
+        auto issue_s = [&](int i) {
+            const int s = i & 1;
+            mbar_wait(&k_full[s], (i >> 1) & 1);
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t dk = dk0 + (uint64_t)(s * (FB_K_STAGE >> 4));
-                const uint32_t ts = tmem_base + 64 * (t & 3);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {                 // 16 dims (32 bytes) per MMA
-                    mma_ss<Kind::BF16>(ts, dq + ((FB_BQ * 128) >> 4) + 2 * kk, dk + 2 * kk, idesc, kk > 0);            // Q_lo K_hi
-                    mma_ss<Kind::BF16>(ts, dq + 2 * kk, dk + ((FB_BKV * 128) >> 4) + 2 * kk, idesc, 1);                // Q_hi K_lo
-                    mma_ss<Kind::BF16>(ts, dq + 2 * kk, dk + 2 * kk, idesc, 1);                                        // Q_hi K_hi
+                for (int g = 0; g < 2; ++g) {
+                    const uint64_t dq = dq0 + (uint64_t)(g * (FB_Q_BYTES >> 4));
+                    const uint32_t ts = tmem_base + 64 * (2 * g + s);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {             // 16 dims (32 bytes) per MMA
+                        mma_ss<Kind::BF16>(ts, dq + ((FB_BQ * 128) >> 4) + 2 * kk, dk + 2 * kk, idesc, kk > 0);        // Q_lo K_hi
+                        mma_ss<Kind::BF16>(ts, dq + 2 * kk, dk + ((FB_BKV * 128) >> 4) + 2 * kk, idesc, 1);            // Q_hi K_lo
+                        mma_ss<Kind::BF16>(ts, dq + 2 * kk, dk + 2 * kk, idesc, 1);                                    // Q_hi K_hi
+                    }
+                    tc_commit(&s_full[2 * g + s]);
                 }
                 tc_commit(&k_empty[s]);
-                tc_commit(&s_full[t & 3]);
             }
             __syncwarp();
         };
         mbar_wait(q_full, 0);
-        for (int t = 0; t < 4 && t < n_tiles; ++t) issue_s(t);  // every warpgroup always has its next S tile ready
-        for (int t = 0; t < n_tiles; ++t) {
-            const int s = t & 1;
-            const uint32_t ph = (t >> 1) & 1;
-            mbar_wait(&v_full[s], ph);
-            mbar_wait(&p_ready[s], ph);                          // P(t) is in smem; S[t&3] and PV[s] are drained
-            tc_fence_after();
-            if (elect_one()) {
-                const uint64_t dv = dv0 + (uint64_t)(s * (FB_V_STAGE >> 4));
-                const uint64_t dp = dp0 + (uint64_t)(s * (FB_P_BUF >> 4));
-                const uint32_t tpv = tmem_base + 256 + 64 * s;
+        for (int i = 0; i < 2 && i < n_tiles; ++i) issue_s(i);
+        for (int i = 0; i < n_tiles; ++i) {
+            const int s = i & 1;
+            mbar_wait(&v_full[s], (i >> 1) & 1);
+            for (int g = 0; g < 2; ++g) {
+                mbar_wait(&p_ready[g], i & 1);                   // P_g(i) is in smem; S_g[s] and PV_g are drained
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t dv = dv0 + (uint64_t)(s * (FB_V_STAGE >> 4));
+                    const uint64_t dp = dp0 + (uint64_t)(g * (FB_P_BUF >> 4));
+                    const uint32_t tpv = tmem_base + 256 + 64 * g;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {                 // 16 keys per MMA
-                    mma_ss<Kind::BF16>(tpv, dp + ((FB_BQ * 128) >> 4) + 2 * kk, dv + 2 * kk, idesc, kk > 0);           // P_lo V_hi
-                    mma_ss<Kind::BF16>(tpv, dp + 2 * kk, dv + ((FB_DK * 128) >> 4) + 2 * kk, idesc, 1);                // P_hi V_lo
-                    mma_ss<Kind::BF16>(tpv, dp + 2 * kk, dv + 2 * kk, idesc, 1);                                       // P_hi V_hi
+                    for (int kk = 0; kk < 4; ++kk) {             // 16 keys per MMA
+                        mma_ss<Kind::BF16>(tpv, dp + ((FB_BQ * 128) >> 4) + 2 * kk, dv + 2 * kk, idesc, kk > 0);       // P_lo V_hi
+                        mma_ss<Kind::BF16>(tpv, dp + 2 * kk, dv + ((FB_DK * 128) >> 4) + 2 * kk, idesc, 1);            // P_hi V_lo
+                        mma_ss<Kind::BF16>(tpv, dp + 2 * kk, dv + 2 * kk, idesc, 1);                                   // P_hi V_hi
+                    }
+                    tc_commit(&pv_full[g]);
+                    if (g == 1) tc_commit(&v_empty[s]);
                 }
-                tc_commit(&v_empty[s]);
-                tc_commit(&pv_full[s]);
+                __syncwarp();
             }
-            __syncwarp();
-            if (t + 4 < n_tiles) issue_s(t + 4);                 // reuses S[t & 3], consumed by the softmax of tile t
+            if (i + 2 < n_tiles) issue_s(i + 2);                 // S buffers of parity s were consumed by the softmax of tile i
         }
     } else {
-        const int wg = (warp - 2) >> 2;                          // softmax warpgroup = tile parity = buffer index
+        const int g = (warp - 2) >> 2;                           // softmax warpgroup = Q tile
         const int qd = warp & 3;
         const int row_l = qd * 32 + lane;
-        const int row = q0 + row_l;
+        const int row = q0 + g * FB_BQ + row_l;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const uint32_t t_pv = tmem_base + 256 + 64 * wg;
-        uint8_t* p_hi = p_smem + wg * FB_P_BUF + row_l * 128;
+        const uint32_t t_pv = tmem_base + 256 + 64 * g;
+        uint8_t* p_hi = p_smem + g * FB_P_BUF + row_l * 128;
         uint8_t* p_lo = p_hi + FB_BQ * 128;
         const int sw = row_l & 7;
         float o[FB_DK];
 #pragma unroll
         for (int d = 0; d < FB_DK; ++d) o[d] = 0.f;
         float m_run = -FLT_MAX, l_run = 0.f, corr_prev = 1.f;
-        auto fold = [&](int t, float corr) {
-            mbar_wait(&pv_full[wg], (t >> 1) & 1);
+        auto fold = [&](int i, float corr) {                     // o <- o * corr + P_g(i) V(i)
+            mbar_wait(&pv_full[g], i & 1);
             tc_fence_after();
             uint32_t a[32];
             tmem_ld_32x32(t_pv + lane_off, a);
@@ -206,12 +227,11 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
             for (int d = 0; d < 32; ++d) o[32 + d] = fmaf(o[32 + d], corr, __uint_as_float(a[d]));
             tc_fence_before();
         };
-        int last = -1;
-        for (int t = wg; t < n_tiles; t += 2) {
-            const int k0 = t * FB_BKV;
+        for (int i = 0; i < n_tiles; ++i) {
+            const int k0 = (tile_begin + i) * FB_BKV;
             uint32_t r[32], r2[32];
-            const uint32_t t_s = tmem_base + 64 * (t & 3);
-            mbar_wait(&s_full[t & 3], (t >> 2) & 1);
+            const uint32_t t_s = tmem_base + 64 * (2 * g + (i & 1));
+            mbar_wait(&s_full[2 * g + (i & 1)], (i >> 1) & 1);
             tc_fence_after();
             tmem_ld_32x32(t_s + lane_off, r);
             tmem_ld_32x32(t_s + lane_off + 32, r2);
@@ -224,14 +244,16 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
                     if (k0 + 32 + j >= nk) r2[j] = __float_as_uint(-FLT_MAX);
                 }
             }
-            float mx = -FLT_MAX;
+            // four independent partial maxima / sums: the softmax warps have little TLP, so keep the chains short
+            float mxp[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+            for (int j = 0; j < 32; ++j) mxp[j & 3] = fmaxf(mxp[j & 3], fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+            const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
             const float m_new = fmaxf(m_run, mx * scale_log2e);
             const float corr = fb_ex2(m_run - m_new);
             const float neg_m = -m_new;
-            if (last >= 0) fold(last, corr_prev);                // PV[wg] drained => P[wg] is no longer read
-            float rs = 0.f;
+            if (i > 0) fold(i - 1, corr_prev);                   // PV_g drained => the P_g buffer is no longer read
+            float rsp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -241,7 +263,7 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
                     for (int u = 0; u < 8; ++u) {
                         const uint32_t sv = half ? r2[c * 8 + u] : r[c * 8 + u];
                         p[u] = fb_ex2(fmaf(__uint_as_float(sv), scale_log2e, neg_m));
-                        rs += p[u];
+                        rsp[u & 3] += p[u];
                     }
                     uint32_t h[4], l[4];
 #pragma unroll
@@ -261,41 +283,60 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
                 }
             }
             fence_proxy_async();                                 // generic smem writes -> visible to the tensor core
-            mbar_arrive(&p_ready[wg]);
+            mbar_arrive(&p_ready[g]);
+            const float rs = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
             l_run = l_run * corr + rs;
             m_run = m_new;
             corr_prev = corr;
-            last = t;
         }
-        if (last >= 0) fold(last, corr_prev);
-        if (wg == 1) {
-            mrg[row_l * 66 + 0] = m_run; mrg[row_l * 66 + 1] = l_run;
+        if (n_tiles > 0) fold(n_tiles - 1, corr_prev);
+        if (row < nq) {
+            if (gridDim.z == 1) {
+                const float inv = 1.f / l_run;
+                float* orow = out + (int64_t)row * ldo + head * FB_DK;
 #pragma unroll
-            for (int d = 0; d < FB_DK; ++d) mrg[row_l * 66 + 2 + d] = o[d];
-        }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (wg == 0 && row < nq) {
-            const float m1 = mrg[row_l * 66 + 0], l1 = mrg[row_l * 66 + 1];
-            const float m = fmaxf(m_run, m1);
-            const float c0 = fb_ex2(m_run - m), c1 = fb_ex2(m1 - m);
-            const float l = l_run * c0 + l1 * c1;
-            const float inv = 1.f / l;
-            float* orow = out + (int64_t)row * ldo + head * FB_DK;
+                for (int d = 0; d < FB_DK; d += 4)
+                    *reinterpret_cast<float4*>(orow + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+                if (lse) lse[(int64_t)head * nq + row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+            } else {
+                const int64_t D = (int64_t)n_heads * FB_DK;
+                float* orow = part.o + ((int64_t)blockIdx.z * nq + row) * D + head * FB_DK;
 #pragma unroll
-            for (int d = 0; d < FB_DK; d += 4) {
-                float4 res;
-                res.x = (o[d] * c0 + mrg[row_l * 66 + 2 + d] * c1) * inv;
-                res.y = (o[d + 1] * c0 + mrg[row_l * 66 + 3 + d] * c1) * inv;
-                res.z = (o[d + 2] * c0 + mrg[row_l * 66 + 4 + d] * c1) * inv;
-                res.w = (o[d + 3] * c0 + mrg[row_l * 66 + 5 + d] * c1) * inv;
-                *reinterpret_cast<float4*>(orow + d) = res;
+                for (int d = 0; d < FB_DK; d += 4)
+                    *reinterpret_cast<float4*>(orow + d) = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
+                part.m[((int64_t)blockIdx.z * n_heads + head) * nq + row] = m_run;
+                part.l[((int64_t)blockIdx.z * n_heads + head) * nq + row] = l_run;
             }
-            if (lse) lse[(int64_t)head * nq + row] = (m + log2f(l)) * 0.6931471805599453f;
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
+}
+
+// Combine the KV splits: out = sum_s o_s 2^(m_s - m) / sum_s l_s 2^(m_s - m)
+__global__ void flash_merge_kernel(FlashPartial part, int splits, int nq, int n_heads, float* __restrict__ out, int64_t ldo,
+                                   float* __restrict__ lse) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (q, head, 4-dim group)
+    const int groups = FB_DK / 4;
+    if (idx >= (int64_t)nq * n_heads * groups) return;
+    const int gidx = (int)(idx % groups);
+    const int head = (int)((idx / groups) % n_heads);
+    const int64_t q = idx / (groups * n_heads);
+    const int64_t D = (int64_t)n_heads * FB_DK;
+    float m = -FLT_MAX;
+    for (int s = 0; s < splits; ++s) m = fmaxf(m, part.m[((int64_t)s * n_heads + head) * nq + q]);
+    float l = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+        const float w = exp2f(part.m[((int64_t)s * n_heads + head) * nq + q] - m);
+        l += part.l[((int64_t)s * n_heads + head) * nq + q] * w;
+        const float4 v = *reinterpret_cast<const float4*>(part.o + ((int64_t)s * nq + q) * D + head * FB_DK + gidx * 4);
+        acc.x += v.x * w; acc.y += v.y * w; acc.z += v.z * w; acc.w += v.w * w;
+    }
+    const float inv = 1.f / l;
+    *reinterpret_cast<float4*>(out + q * ldo + head * FB_DK + gidx * 4) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    if (lse && gidx == 0) lse[(int64_t)head * nq + q] = (m + log2f(l)) * 0.6931471805599453f;
 }
 
 int bf16_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ld_out, cudaStream_t st) {
@@ -305,12 +346,34 @@ int bf16_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t
     return finish_launch();
 }
 
+size_t flash_attn_bf16_workspace_bytes(int64_t nq, int64_t nk, int n_heads, int* splits_out) {
+    // KV splits so that (256-query blocks x heads x splits) fills the 148 SMs in whole rounds
+    const int64_t items = ceil_div(nq, 2 * FB_BQ) * n_heads;
+    const int64_t n_tiles = ceil_div(nk, FB_BKV);
+    int best = 1; double best_cost = 1e30;
+    const char* forced = getenv("VLSAT_FLASH_SPLITS");           // experiments only
+    for (int s = 1; s <= 4; ++s) {
+        if (s > n_tiles) break;
+        const double rounds = (double)ceil_div(items * s, kNumSMs);
+        // tile-rounds of the main kernel + the partial-state write/merge traffic of every extra split
+        const double cost = rounds * (double)ceil_div(n_tiles, s) + (s - 1) * (4.0 + 0.03 * n_tiles);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+    }
+    if (forced && atoi(forced) >= 1 && atoi(forced) <= 4 && atoi(forced) <= n_tiles) best = atoi(forced);
+    if (splits_out) *splits_out = best;
+    if (best == 1) return 0;
+    return (size_t)best * (size_t)nq * ((size_t)n_heads * FB_DK + 2 * (size_t)n_heads) * sizeof(float);
+}
+
 // q_* [nq, H*64] bf16 (row stride ldq elements), k_* [nk, H*64], vt_* [H*64, nk] (row stride ldvt, multiple of 8)
 int flash_attn_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq, const uint16_t* k_hi, const uint16_t* k_lo, int64_t ldk,
                     const uint16_t* vt_hi, const uint16_t* vt_lo, int64_t ldvt, float* out, int64_t ldo, float* lse,
-                    int64_t nq, int64_t nk, int n_heads, int dk, cudaStream_t st) {
+                    int64_t nq, int64_t nk, int n_heads, int dk, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (dk != FB_DK || nq >= (1ll << 31) || nk >= (1ll << 31)) return VLSAT_ERR_UNSUPPORTED;
     if ((ldq | ldk | ldvt) % 8 || ldo % 4) return VLSAT_ERR_UNSUPPORTED;
+    int splits = 1;
+    const size_t need = flash_attn_bf16_workspace_bytes(nq, nk, n_heads, &splits);
+    if (need > 0 && (!workspace || workspace_bytes < need)) return VLSAT_ERR_WORKSPACE;
     CUtensorMap tq, tql, tk, tkl, tv, tvl;
     const uint64_t d = (uint64_t)n_heads * dk;
     const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -318,12 +381,27 @@ int flash_attn_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq, con
               make_tmap_2d(&tk, k_hi, BF, 2, nk, d, ldk, 64, FB_BKV) && make_tmap_2d(&tkl, k_lo, BF, 2, nk, d, ldk, 64, FB_BKV) &&
               make_tmap_2d(&tv, vt_hi, BF, 2, d, nk, ldvt, 64, FB_DK) && make_tmap_2d(&tvl, vt_lo, BF, 2, d, nk, ldvt, 64, FB_DK);
     if (!ok) return VLSAT_ERR_UNSUPPORTED;
-    const size_t smem = FB_Q_BYTES + 2 * FB_K_STAGE + 2 * FB_V_STAGE + 2 * FB_P_BUF + FB_BQ * 66 * 4 + 1024 + 256;
+    FlashPartial part{nullptr, nullptr, nullptr};
+    if (splits > 1) {
+        part.o = (float*)workspace;
+        part.m = part.o + (size_t)splits * nq * d;
+        part.l = part.m + (size_t)splits * n_heads * nq;
+    }
+    const int n_tiles = (int)ceil_div(nk, FB_BKV);
+    const int tiles_per_split = (int)ceil_div(n_tiles, splits);
+    const size_t smem = 2 * FB_Q_BYTES + 2 * FB_K_STAGE + 2 * FB_V_STAGE + 2 * FB_P_BUF + 1024 + 256;
     cudaFuncSetAttribute(flash_attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((unsigned)ceil_div(nq, FB_BQ), (unsigned)n_heads);
+    dim3 grid((unsigned)ceil_div(nq, 2 * FB_BQ), (unsigned)n_heads, (unsigned)splits);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)dk);
-    flash_attn_bf16_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tql, tk, tkl, tv, tvl, out, ldo, lse, (int)nq, (int)nk, scale_log2e);
-    return finish_launch();
+    flash_attn_bf16_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tql, tk, tkl, tv, tvl, out, ldo, lse, part, (int)nq, (int)nk,
+                                                           n_heads, tiles_per_split, scale_log2e);
+    int launches = 1;
+    if (splits > 1) {
+        const int64_t n = nq * n_heads * (FB_DK / 4);
+        flash_merge_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(part, splits, (int)nq, n_heads, out, ldo, lse);
+        ++launches;
+    }
+    return finish_launch(launches);
 }
 
 }  // namespace vlsat

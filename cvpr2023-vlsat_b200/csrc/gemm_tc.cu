@@ -184,6 +184,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
             const int64_t ia_own = (own_ok && e.gather_a) ? e.idx_a[m_own] : 0;
             const int64_t ib_own = (own_ok && e.gather_b) ? e.idx_b[m_own] : 0;
             const float row_bias = (own_ok && e.bias && e.bias_per_row) ? __ldg(e.bias + m_own) : 0.f;
+            // row-gather / residual operands of the NEXT 32-column chunk are always in flight while the current one
+            // is processed (and chunk 0's while the main loop of this tile still runs)
+            float4 ga_n[8], gb_n[8], rs_n[8];
+            auto issue_row_loads = [&](int64_t nbn) {
+                const bool go = vec_ok && own_ok && nbn + 32 <= a.N;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    ga_n[j] = (go && e.gather_a) ? __ldg(reinterpret_cast<const float4*>(e.gather_a + ia_own * e.ld_gather + nbn) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    gb_n[j] = (go && e.gather_b) ? __ldg(reinterpret_cast<const float4*>(e.gather_b + ib_own * e.ld_gather + nbn) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    rs_n[j] = (go && e.residual) ? __ldg(reinterpret_cast<const float4*>(e.residual + m_own * e.ld_res + nbn) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            issue_row_loads(n0);
             mbar_wait(&acc_full[buf], (i >> 1) & 1);
             tc_fence_after();
             if (a.trace && blockIdx.x == 0 && threadIdx.x == 64 && i < 8) a.trace[i * 4 + 2] = gtime();
@@ -194,6 +207,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                 if (nb >= a.N) break;                        // warp-uniform
                 uint32_t r[32];
                 tmem_ld_32x32(tacc + (uint32_t)c0, r);
+                float4 ga4[8], gb4[8], rs4[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { ga4[j] = ga_n[j]; gb4[j] = gb_n[j]; rs4[j] = rs_n[j]; }
+                if (c0 + 32 < BN) issue_row_loads(nb + 32);
                 tmem_ld_wait();
                 if (vec_ok && nb + 32 <= a.N) {
                     // One output row per thread (its TMEM lane), 32 consecutive columns. All global loads of the
@@ -204,14 +221,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                     for (int j = 0; j < 8; ++j)
                         v[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
                     if (own_ok) {
-                        float4 b4[8], ga4[8], gb4[8];
+                        float4 b4[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int64_t n = nb + j * 4;
-                            b4[j] = (e.bias && !e.bias_per_row) ? __ldg(reinterpret_cast<const float4*>(e.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            ga4[j] = e.gather_a ? __ldg(reinterpret_cast<const float4*>(e.gather_a + ia_own * e.ld_gather + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            gb4[j] = e.gather_b ? __ldg(reinterpret_cast<const float4*>(e.gather_b + ib_own * e.ld_gather + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
+                        for (int j = 0; j < 8; ++j)
+                            b4[j] = (e.bias && !e.bias_per_row) ? __ldg(reinterpret_cast<const float4*>(e.bias + nb + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             v[j].x += b4[j].x + row_bias + ga4[j].x + gb4[j].x; v[j].y += b4[j].y + row_bias + ga4[j].y + gb4[j].y;
@@ -225,9 +238,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                             for (int j = 0; j < 8; ++j) { v[j].x = apply_act(v[j].x, e.act); v[j].y = apply_act(v[j].y, e.act); v[j].z = apply_act(v[j].z, e.act); v[j].w = apply_act(v[j].w, e.act); }
                         }
                         if (e.residual) {
-                            float4 rs4[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) rs4[j] = __ldg(reinterpret_cast<const float4*>(e.residual + m_own * e.ld_res + nb + j * 4));
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 v[j].x = e.alpha * v[j].x + e.beta * rs4[j].x; v[j].y = e.alpha * v[j].y + e.beta * rs4[j].y;

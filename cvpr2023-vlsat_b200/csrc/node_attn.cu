@@ -172,13 +172,24 @@ node_attn_kernel(const float* __restrict__ q, int64_t ldq, const float* __restri
             for (int d = 0; d < DPL; ++d) acc[hi][d] *= corr;
 #pragma unroll
             for (int r = 0; r < NA_TK / 32; ++r) {
-                for (int j = 0; j < 32; ++j) {
-                    const int kb = j + 32 * r;
-                    if (kb >= nb) break;
-                    const float p = __shfl_sync(0xffffffffu, sc[r], j);
-                    const float* vp = v + (int64_t)(b0 + kb) * ldv + hh * DK;
+                // keys in groups of 8: all value loads of a group are issued before the FMAs consume them, so
+                // their L2 latencies overlap instead of adding up (a scene has tens of keys, the loop is latency bound)
+                for (int j0 = 0; j0 < 32; j0 += 8) {
+                    if (j0 + 32 * r >= nb) break;                // warp-uniform
+                    float vv[8][DPL], pp[8];
 #pragma unroll
-                    for (int d = 0; d < DPL; ++d) acc[hi][d] = fmaf(p, __ldg(vp + lane + 32 * d), acc[hi][d]);
+                    for (int u = 0; u < 8; ++u) {
+                        const int kb = j0 + u + 32 * r;
+                        pp[u] = __shfl_sync(0xffffffffu, sc[r], j0 + u);
+                        const float* vp = v + (int64_t)(b0 + min(kb, nb - 1)) * ldv + hh * DK;
+#pragma unroll
+                        for (int d = 0; d < DPL; ++d) vv[u][d] = __ldg(vp + lane + 32 * d);
+                        if (kb >= nb) pp[u] = 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+#pragma unroll
+                        for (int d = 0; d < DPL; ++d) acc[hi][d] = fmaf(pp[u], vv[u][d], acc[hi][d]);
                 }
             }
         }

@@ -411,9 +411,11 @@ def flash_attn_bf16(q, k, vt, nk: int, n_heads: int, want_lse: bool = False):
     vh, vl = bf16_split(vt[:, :nk])
     out = torch.empty((nq, d), device=q.device, dtype=torch.float32)
     lse = torch.empty((n_heads, nq), device=q.device, dtype=torch.float32) if want_lse else None
+    ws_bytes = int(_lib.load().vlsat_flash_attn_bf16x3_workspace_bytes(nq, nk, n_heads))
+    ws = torch.empty((ws_bytes // 4,), device=q.device, dtype=torch.float32) if ws_bytes else None
     st = _call("vlsat_flash_attn_bf16x3_fwd", qh.data_ptr(), ql.data_ptr(), qh.shape[1], kh.data_ptr(), kl.data_ptr(), kh.shape[1],
                vh.data_ptr(), vl.data_ptr(), vh.shape[1], out.data_ptr(), d, lse.data_ptr() if want_lse else None,
-               nq, nk, n_heads, 64, _stream(), work=(4.0 * nq * nk * d, 4.0 * (2 * nq * d + 2 * nk * d)))
+               nq, nk, n_heads, 64, ws.data_ptr() if ws is not None else None, ws_bytes, _stream(), work=(4.0 * nq * nk * d, 4.0 * (2 * nq * d + 2 * nk * d)))
     _lib.check(st, "vlsat_flash_attn_bf16x3_fwd")
     return (out, lse) if want_lse else out
 

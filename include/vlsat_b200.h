@@ -178,7 +178,10 @@ int vlsat_flash_attn_bf16x3_fwd(const void* q_hi, const void* q_lo, int64_t ldq,
                                 const void* k_hi, const void* k_lo, int64_t ldk,
                                 const void* vt_hi, const void* vt_lo, int64_t ldvt,
                                 float* out, int64_t ldo, float* lse, int64_t nq, int64_t nk, int n_heads, int dk,
-                                void* stream);
+                                void* workspace, size_t workspace_bytes, void* stream);
+/* The kernel splits the key range over CTAs when that fills the 148 SMs in fewer rounds; the partial softmax
+ * states then go through `workspace` (16-byte aligned, size below; 0 = no split needed). */
+size_t vlsat_flash_attn_bf16x3_workspace_bytes(int64_t nq, int64_t nk, int n_heads);
 
 /* ------------------------------------------------------------------------------------------------
  * A8  graph attention layer core (network_MMG.py:34-41,96-104; network_util.py:50-73).

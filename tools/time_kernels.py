@@ -29,7 +29,10 @@ for (m, n, k) in [(9600, 512, 512), (9600, 1024, 512), (9600, 512, 1024), (640, 
 q, k_ = torch.randn(9600, 512, generator=g).to(dev), torch.randn(9600, 512, generator=g).to(dev)
 vt = torch.randn(512, 9600, generator=g).to(dev)
 timeit("flash_attn_tc 9600x9600 h8 (3 splits + attn)", lambda: ops.flash_attn_tc(q, k_, vt, 9600, 8), 4.0 * 9600 * 9600 * 512)
-timeit("flash_attn_bf16 9600x9600 h8 (3 splits + attn)", lambda: ops.flash_attn_bf16(q, k_, vt, 9600, 8), 4.0 * 9600 * 9600 * 512)
+for sp in ("1", "2", "3", "4", ""):
+    os.environ["VLSAT_FLASH_SPLITS"] = sp
+    if not sp: del os.environ["VLSAT_FLASH_SPLITS"]
+    timeit(f"flash_attn_bf16 9600x9600 h8 kv-splits={sp or 'auto'} (3 operand splits + attn)", lambda: ops.flash_attn_bf16(q, k_, vt, 9600, 8), 4.0 * 9600 * 9600 * 512)
 model = V.Mmgnet({"MODEL": V.DEFAULT_MODEL_CONFIG}, 160, 26)
 synth.load_seeded(model, 0)
 model = model.to(dev).eval()
