@@ -44,9 +44,9 @@ def _copy_into(old, new):
 
 
 def require_inference(module: torch.nn.Module, what: str) -> None:
-    """The CUDA path implements the eval-mode forward. Training-mode dropout (six sites on the path) and
-    the backward kernels are not built yet: refuse loudly instead of silently differing."""
+    """Guard of the fused inference-only entry points (``attend_scenes``, ``fused`` ...): training mode and autograd
+    go through the modules' ``forward`` (-> train_path.py), never through these. There is no PyTorch fallback."""
     if module.training:
         raise NotImplementedError(
-            f"{what}: training mode (dropout masks, BatchNorm batch statistics, backward) is not implemented in "
-            "vlsat_b200 yet; call .eval(). There is no PyTorch fallback by design.")
+            f"{what}: this is a fused inference entry point; in training mode call the module's forward "
+            "(differentiable vlsat_b200 path, train_path.py).")

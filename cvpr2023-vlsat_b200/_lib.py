@@ -58,6 +58,26 @@ SIGNATURES = {
     "vlsat_build_csr": [vp, i64, i64, vp, vp, vp, sz, vp],
     "vlsat_gat_edge_fwd": [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64,
                            i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, vp, vp],
+    "vlsat_transpose": [vp, i64, i64, vp, i64, i64, i64, i64, i64, vp],
+    "vlsat_act_bwd": [vp, i64, vp, i64, i32, f32, vp, vp, i64, vp, i64, i64, vp],
+    "vlsat_wgrad_small": [vp, i64, vp, i64, i64, i32, i32, vp, i64, vp],
+    "vlsat_gather_rows": [vp, i64, vp, i32, i64, i32, vp, i64, vp],
+    "vlsat_scatter_add_rows": [vp, i64, vp, i32, i64, i32, vp, i64, vp],
+    "vlsat_add_layernorm_bwd": [vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, vp, vp, i64, i32, f32, i32, vp],
+    "vlsat_gat_softmax_aggr_fwd": [vp, vp, i64, vp, vp, i64, i64, i32, i32, i32, vp, i64, vp, vp, vp],
+    "vlsat_gat_softmax_aggr_bwd": [vp, i64, vp, vp, i64, vp, vp, vp, i64, i64, i32, i32, i32, vp, vp, i64, vp],
+    "vlsat_attn_prob_bwd": [vp, vp, i64, vp, vp, f32, vp, vp, vp, i64, i64, i64, vp],
+    "vlsat_rowdot_heads": [vp, i64, vp, i64, vp, i64, i32, i32, vp],
+    "vlsat_pair_features": [vp, i64, vp, vp, vp, i64, vp, vp],
+    "vlsat_node_attn_bias_fwd": [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, i32, vp, i64, i64, vp],
+    "vlsat_node_attn_bias_bwd": [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, i64, vp, i64,
+                                 vp, i64, vp, i64, vp],
+    "vlsat_pointnet_pool_bwd": [vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp],
+    "vlsat_dropout": [vp, i64, vp, i64, i64, i64, f32, C.c_uint64, C.c_uint64, vp],
+    "vlsat_batchnorm_fwd": [vp, i64, vp, vp, vp, vp, vp, vp, f32, f32, i32, i32, vp, i64, i64, i64, vp],
+    "vlsat_batchnorm_bwd": [vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, vp, i64, vp, vp, i64, i64, vp],
+    "vlsat_row_l2norm_bwd": [vp, vp, vp, i64, i32, vp],
+    "vlsat_dot_accum": [vp, vp, i64, vp, vp],
 }
 _RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
 

@@ -108,7 +108,12 @@ class MultiHeadAttention(nn.Module):
     def attend_all(self, q_in, kv_in, relu: bool = False, out=None, q_split=None, kv_split=None) -> torch.Tensor:
         """LN(q_in + fc_o(softmax(QK^T/sqrt(dk)) V)) over all keys, no mask/bias; 2-D inputs.
         ``q_split`` / ``kv_split``: tf32 splits of the inputs if the producer already emitted them."""
-        require_inference(self, "MultiHeadAttention")
+        from . import train_path as T
+        if T.differentiable(self):
+            y = T.mha_all(self, q_in, kv_in, relu_out=relu)
+            if out is not None:
+                raise ValueError("attend_all: `out=` is an inference-path option")
+            return y
         a = self.attention
         if a.d_k == 64 and ops.tensor_cores_enabled() and kv_in.shape[1] % 4 == 0 and kv_in.shape[1] >= 32:
             # tensor-core path: Q, K row-major; the value projection is emitted transposed (V^T = W_v x^T).

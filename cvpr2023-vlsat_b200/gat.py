@@ -84,6 +84,16 @@ class GraphContext:
         self.src = self.edge_index[0]
         self.dst = self.edge_index[1]
         self.identity = torch.arange(self.num_edges, device=ei.device, dtype=torch.int32)
+        self._head_rows = {}
+
+    def head_rows(self, num_heads: int) -> torch.Tensor:
+        """int64 [E*H]: row (e, h) of a head-major edge tensor -> row src(e)*H + h of a head-major node tensor."""
+        r = self._head_rows.get(num_heads)
+        if r is None:
+            h = torch.arange(num_heads, device=self.src.device, dtype=torch.int64)
+            r = (self.src.view(-1, 1) * num_heads + h.view(1, -1)).reshape(-1).contiguous()
+            self._head_rows[num_heads] = r
+        return r
 
     def to_sorted(self, edge_rows: torch.Tensor) -> torch.Tensor:
         return ops.permute_rows(edge_rows, self.perm, gather=True) if self.num_edges else edge_rows
@@ -270,9 +280,13 @@ class MultiHeadedEdgeAttention(nn.Module):
     def forward(self, query, edge, value, weight=None, istrain=False):
         """(x_i, edge, x_j) -> (prob * value [E, D_a], new edge feature, prob [E, d_o, H]); every edge is
         treated as its own one-edge node so the same fused kernel serves this entry point."""
-        require_inference(self, "MultiHeadedEdgeAttention")
         e_cnt = query.shape[0]
         ar = torch.arange(e_cnt, device=query.device, dtype=torch.int64)
+        from . import train_path as T
+        if T.differentiable(self):
+            g = GraphContext(torch.stack([ar, ar], 0), e_cnt)
+            x, new_edge, prob = T.edge_attention(self, query.contiguous(), edge.contiguous(), g, x_value=value.contiguous(), aggr="add")
+            return x, new_edge, prob.view(e_cnt, self.num_heads, self.d_o).permute(0, 2, 1).contiguous()
         w1, w2 = self.nn_edge[0], self.nn_edge[2]
         h = ops.linear(torch.cat([query, edge, value], 1), w1.weight.detach(), w1.bias.detach(), act=ops.ACT_RELU)
         new_edge = ops.linear(h, w2.weight.detach(), w2.bias.detach())
@@ -327,6 +341,18 @@ class GraphEdgeAttenNetwork(nn.Module):
         assert x.ndim == 2
         assert edge_feature.ndim == 2
         g = GraphContext(edge_index, x.shape[0], self.flow)
+        from . import train_path as T
+        if T.differentiable(self):
+            from . import autograd as A
+            out, new_edge, prob = T.gat_layer(self, x.contiguous(), A.permute_rows(edge_feature.contiguous(), g.perm, True), g)
+            new_edge = A.permute_rows(new_edge, g.perm, False)
+            if self.return_prob:
+                e, H, do = g.num_edges, self.edgeatten.num_heads, self.edgeatten.d_o
+                pr = prob.view(e, H, do).permute(0, 2, 1).contiguous()
+                if e:
+                    pr = ops.permute_rows(pr.view(e, -1), g.perm, gather=False).view(e, do, H)
+                return out, new_edge, pr
+            return out, new_edge
         cat_buf = torch.empty((x.shape[0], self.dim_node + self.dim_atten), device=x.device, dtype=torch.float32)
         cat_buf[:, :self.dim_node].copy_(x)
         out, new_edge, prob = self.forward_fused(cat_buf, g.to_sorted(edge_feature.contiguous()), g, want_prob=self.return_prob)

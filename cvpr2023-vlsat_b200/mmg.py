@@ -53,10 +53,13 @@ class MMG(nn.Module):
 
     def forward(self, obj_feature_3d, obj_feature_2d, edge_feature_3d, edge_feature_2d, edge_index, batch_ids,
                 obj_center=None, discriptor=None, istrain=False):
-        require_inference(self, "MMG")
         if obj_center is None:
             raise NotImplementedError("MMG.forward needs obj_center (the reference path without it is broken: "
                                       "network_MMG.py:207-217 reads an undefined variable)")
+        from . import train_path as T
+        if T.differentiable(self):
+            return T.mmg_forward(self, obj_feature_3d.contiguous(), obj_feature_2d.contiguous(), edge_feature_3d,
+                                 edge_feature_2d, edge_index, batch_ids, obj_center)
         n = obj_feature_3d.shape[0]
         dn, da = self.dim_node, self.dim_atten
         ctx = self.scene_context(batch_ids, obj_center)
@@ -100,12 +103,14 @@ class GraphEdgeAttenNetworkLayers(nn.Module):
         self._cache = DerivedCache()
 
     def forward(self, node_feature, edge_feature, edges_indices, obj_center, batch_ids):
-        require_inference(self, "GraphEdgeAttenNetworkLayers")
         if obj_center is None:
             raise NotImplementedError("obj_center is required (network_GNN.py:260-265 breaks without it)")
         if self.num_heads != 8:
             # network_GNN.py:235,253: the bias buffer is sized with num_heads but filled with 8 heads
             raise RuntimeError("GraphEdgeAttenNetworkLayers: the reference raises a shape error unless num_heads == 8")
+        from . import train_path as T
+        if T.differentiable(self):
+            return T.gnn_layers_forward(self, node_feature.contiguous(), edge_feature, edges_indices, obj_center, batch_ids)
         n = node_feature.shape[0]
         dn, da = self.dim_node, self.dim_atten
         fc = self.self_attn_fc

@@ -158,7 +158,10 @@ class Mmgnet(nn.Module):
 
     # ---- forward -----------------------------------------------------------------------------------
     def forward(self, obj_points, obj_2d_feats, edge_indices, descriptor=None, batch_ids=None, istrain=False):
-        require_inference(self, "Mmgnet")
+        from . import train_path as T
+        if T.differentiable(self):
+            return T.mmgnet_forward(self, obj_points, obj_2d_feats, edge_indices, descriptor, batch_ids, istrain,
+                                    use_spatial=bool(_need(self.mconfig, "USE_SPATIAL")))
         n = obj_points.shape[0]
         obj_feature = self.obj_encoder(obj_points)                                   # [N, 768]
         obj_feature_3d_mimic = obj_feature[..., :512].clone() if istrain else None

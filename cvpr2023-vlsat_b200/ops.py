@@ -170,7 +170,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            gather: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]] = None,
            residual: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0,
            scale_ptr: Optional[torch.Tensor] = None, bias_per_row: bool = False,
-           x_is_weight: bool = False, x_split=None, w_split=None, emit_split: bool = False, want_y: bool = True):
+           x_is_weight: bool = False, x_split=None, w_split=None, emit_split: bool = False, want_y: bool = True,
+           cache_w: bool = True):
     """y = post(act(x w^T + bias + ga[ia] + gb[ib])), post(t) = (alpha t + beta residual) * exp(scale).
 
     x [M, K] and w [N, K] may be column-slice views (row stride = leading dimension); ``out`` may be a
@@ -178,7 +179,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     a parameter (split cached), w an activation (split per call) - used to emit y^T = W x^T.
     ``x_split=(hi, lo)``: tf32 split of x already available (compact [M, K]) - skips the split pass.
     ``emit_split=True``: the epilogue also writes the tf32 split of y and the call returns ``(y, (hi, lo))``
-    (``want_y=False``: only the split is written, y is None). ``x`` itself may be such a ``(hi, lo)`` pair
+    (``want_y=False``: only the split is written, y is None). ``cache_w=False``: do not cache the tf32 split of
+    ``w`` (it is an activation or a temporary). ``x`` itself may be such a ``(hi, lo)`` pair
     when the unsplit activation was never materialised (tensor-core engine only)."""
     if isinstance(x, tuple):
         x_split = x
@@ -218,11 +220,17 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         epi.bias_per_row = int(bias_per_row)
     if gather is not None:
         ga, ia, gb, ib = gather
-        gap, ldga = _rows(ga, "gather_a"); gbp, ldgb = _rows(gb, "gather_b")
-        _i64(ia, "idx_a"); _i64(ib, "idx_b")
-        if ldga != ldgb or ga.shape[1] != n or gb.shape[1] != n or ia.numel() != m or ib.numel() != m:
-            raise ValueError("linear: gather operands must be [*, N] with equal row strides and [M] indices")
-        epi.gather_a, epi.idx_a, epi.gather_b, epi.idx_b, epi.ld_gather = gap, ia.data_ptr(), gbp, ib.data_ptr(), ldga
+        gap, ldga = _rows(ga, "gather_a")
+        _i64(ia, "idx_a")
+        if ga.shape[1] != n or ia.numel() != m:
+            raise ValueError("linear: gather operands must be [*, N] with [M] indices")
+        epi.gather_a, epi.idx_a, epi.ld_gather = gap, ia.data_ptr(), ldga
+        if gb is not None:                       # second gather term is optional
+            gbp, ldgb = _rows(gb, "gather_b")
+            _i64(ib, "idx_b")
+            if ldga != ldgb or gb.shape[1] != n or ib.numel() != m:
+                raise ValueError("linear: gather operands must be [*, N] with equal row strides and [M] indices")
+            epi.gather_b, epi.idx_b = gbp, ib.data_ptr()
     if residual is not None:
         rp, ldr = _rows(residual, "residual")
         if tuple(residual.shape) != (m, n):
@@ -243,7 +251,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
             else:
                 ws = torch.empty((2 * n * k,), device=x.device, dtype=torch.float32)
         else:
-            hl = _weight_split(w, ldw)
+            # cache_w=False: w is an activation / a per-call temporary (backward GEMMs), never cache its split
+            hl = w_split if w_split is not None else (_weight_split(w, ldw) if cache_w else tf32_split(w))
             opts.w_hi, opts.w_lo = hl[0].data_ptr(), hl[1].data_ptr()
             if x_split is not None:
                 opts.x_hi, opts.x_lo = x_split[0].data_ptr(), x_split[1].data_ptr()
@@ -529,3 +538,222 @@ def gat_edge_tc(k_hm, qc, v_hm, src, dst, c1k_split, c2_split, c2b, n_nodes: int
                      e * (n_heads * d_e * 4.0 + 16.0) + n_nodes * (n_heads * (d_n or d_e) + 2.0 * n_heads * d_o) * 4.0))
     _lib.check(st, "vlsat_gat_edge_tc_fwd")
     return out, prob
+
+
+# ------------------------------------------------------------------ backward / training-mode primitives
+def _round4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """x [R, C] (row stride allowed) -> [C, round4(R)] with the tail columns zero (GEMM operand for a reduction
+    over R). For a 3-D contiguous x [B, R, C] returns [B, C, round4(R)]."""
+    _f32(x, "x")
+    if x.dim() == 2:
+        xp, ldx = _rows(x, "x")
+        r, c = x.shape
+        out = torch.empty((c, _round4(r)), device=x.device, dtype=torch.float32)
+        _lib.check(_call("vlsat_transpose", xp, ldx, 0, out.data_ptr(), out.shape[1], 0, 1, r, c, _stream()), "vlsat_transpose")
+        return out
+    if x.dim() != 3 or not x.is_contiguous():
+        raise ValueError("transpose: expected a 2-D matrix or a contiguous 3-D batch")
+    b, r, c = x.shape
+    out = torch.empty((b, c, _round4(r)), device=x.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_transpose", x.data_ptr(), c, r * c, out.data_ptr(), out.shape[2], c * out.shape[2], b, r, c, _stream()),
+               "vlsat_transpose")
+    return out
+
+
+def act_bwd(dy: torch.Tensor, y: Optional[torch.Tensor], act: int, want_dz: bool = True, want_dbias: bool = True,
+            scale: float = 1.0, scale_ptr: Optional[torch.Tensor] = None):
+    """(dz, dbias): dz = dy * act'(y) * scale * exp(scale_ptr), dbias = column sums of dz."""
+    dp, lddy = _rows(dy, "dy")
+    m, n = dy.shape
+    yp, ldy = (None, 0) if y is None else _rows(y, "y")
+    dz = torch.empty((m, n), device=dy.device, dtype=torch.float32) if want_dz else None
+    db = torch.zeros((n,), device=dy.device, dtype=torch.float32) if want_dbias else None
+    _lib.check(_call("vlsat_act_bwd", dp, lddy, yp, ldy, act, scale, scale_ptr.data_ptr() if scale_ptr is not None else None,
+                     dz.data_ptr() if want_dz else None, n, db.data_ptr() if want_dbias else None, m, n, _stream()), "vlsat_act_bwd")
+    return dz, db
+
+
+def scatter_add_rows(x: torch.Tensor, idx: torch.Tensor, out: torch.Tensor, rows_per_idx: int = 1) -> torch.Tensor:
+    """out[idx[i // R] * R + i % R, :] += x[i, :] (out is accumulated into)."""
+    xp, ldx = _rows(x, "x"); op, ldo = _rows(out, "out")
+    _i64(idx, "idx")
+    if x.shape[1] != out.shape[1] or idx.numel() * rows_per_idx != x.shape[0]:
+        raise ValueError("scatter_add_rows: shape mismatch")
+    _lib.check(_call("vlsat_scatter_add_rows", xp, ldx, idx.data_ptr(), rows_per_idx, x.shape[0], x.shape[1], op, ldo, _stream()),
+               "vlsat_scatter_add_rows")
+    return out
+
+
+def gather_rows(x: torch.Tensor, idx: torch.Tensor, rows_per_idx: int = 1) -> torch.Tensor:
+    xp, ldx = _rows(x, "x")
+    _i64(idx, "idx")
+    rows = idx.numel() * rows_per_idx
+    out = torch.empty((rows, x.shape[1]), device=x.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_gather_rows", xp, ldx, idx.data_ptr(), rows_per_idx, rows, x.shape[1], out.data_ptr(), x.shape[1], _stream()),
+               "vlsat_gather_rows")
+    return out
+
+
+def add_layernorm_bwd(dy, x, res, gamma, beta, eps: float, relu: bool):
+    dp, lddy = _rows(dy, "dy"); xp, ldx = _rows(x, "x")
+    rp, ldr = (None, 0) if res is None else _rows(res, "res")
+    m, d = x.shape
+    dx = torch.empty((m, d), device=x.device, dtype=torch.float32)
+    dg = torch.zeros((d,), device=x.device, dtype=torch.float32)
+    db = torch.zeros((d,), device=x.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_add_layernorm_bwd", dp, lddy, xp, ldx, rp, ldr, gamma.data_ptr(), beta.data_ptr(), dx.data_ptr(), d,
+                     dg.data_ptr(), db.data_ptr(), m, d, eps, int(relu), _stream()), "vlsat_add_layernorm_bwd")
+    return dx, dg, db
+
+
+def gat_softmax_aggr(t, v_hm, dst, row_ptr, n_nodes: int, n_heads: int, aggr: str):
+    """(xx [N, H*d_o] interleaved, prob [E*H, d_o], argmax [N, H*d_o] int32 or None)."""
+    _f32(t, "t")
+    vp_, ldv = _rows(v_hm, "v_hm")
+    d_o = v_hm.shape[1] // n_heads
+    e = t.shape[0] // n_heads
+    if not t.is_contiguous() or t.shape[1] != d_o:
+        raise ValueError("gat_softmax_aggr: t must be contiguous [E*H, d_o]")
+    xx = torch.empty((n_nodes, n_heads * d_o), device=t.device, dtype=torch.float32)
+    prob = torch.empty_like(t)
+    arg = torch.empty((n_nodes, n_heads * d_o), device=t.device, dtype=torch.int32) if aggr == "max" else None
+    _lib.check(_call("vlsat_gat_softmax_aggr_fwd", t.data_ptr() if e else None, vp_, ldv, dst.data_ptr() if e else None,
+                     row_ptr.data_ptr(), n_nodes, e, n_heads, d_o, AGGR[aggr], xx.data_ptr(), xx.shape[1], prob.data_ptr() if e else None,
+                     arg.data_ptr() if arg is not None else None, _stream()), "vlsat_gat_softmax_aggr_fwd")
+    return xx, prob, arg
+
+
+def gat_softmax_aggr_bwd(dxx, prob, v_hm, dst, row_ptr, arg, n_nodes: int, n_heads: int, aggr: str):
+    """(dt [E*H, d_o], dv_hm [N, H*d_o])."""
+    dp, lddxx = _rows(dxx, "dxx"); vp_, ldv = _rows(v_hm, "v_hm")
+    d_o = v_hm.shape[1] // n_heads
+    e = prob.shape[0] // n_heads
+    dt = torch.empty_like(prob)
+    dv = torch.zeros((n_nodes, n_heads * d_o), device=dxx.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_gat_softmax_aggr_bwd", dp, lddxx, prob.data_ptr() if e else None, vp_, ldv, dst.data_ptr() if e else None,
+                     row_ptr.data_ptr(), arg.data_ptr() if arg is not None else None, n_nodes, e, n_heads, d_o, AGGR[aggr],
+                     dt.data_ptr() if e else None, dv.data_ptr(), dv.shape[1], _stream()), "vlsat_gat_softmax_aggr_bwd")
+    return dt, dv
+
+
+def attn_prob_bwd(s, dp, lse, delta, scale: float):
+    """In place on dp: dS. Returns (dS [nq, nk], dS^T [nk, round4(nq)], P^T [nk, round4(nq)])."""
+    nq, nk = s.shape
+    if not (s.is_contiguous() and dp.is_contiguous()):
+        raise ValueError("attn_prob_bwd: s and dp must be contiguous")
+    ldt = _round4(nq)
+    ds_t = torch.empty((nk, ldt), device=s.device, dtype=torch.float32)
+    p_t = torch.empty((nk, ldt), device=s.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_attn_prob_bwd", s.data_ptr(), dp.data_ptr(), nk, lse.data_ptr(), delta.data_ptr(), scale, dp.data_ptr(),
+                     ds_t.data_ptr(), p_t.data_ptr(), ldt, nq, nk, _stream()), "vlsat_attn_prob_bwd")
+    return dp, ds_t, p_t
+
+
+def rowdot_heads(a, b, n_heads: int) -> torch.Tensor:
+    ap, lda = _rows(a, "a"); bp, ldb = _rows(b, "b")
+    m, d = a.shape
+    out = torch.empty((n_heads, m), device=a.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_rowdot_heads", ap, lda, bp, ldb, out.data_ptr(), m, n_heads, d // n_heads, _stream()), "vlsat_rowdot_heads")
+    return out
+
+
+def pair_features(centres, seg_start, seg_end, pair_off, n_pairs: int) -> torch.Tensor:
+    cp, ldc = _rows(centres, "centres")
+    out = torch.empty((n_pairs, 4), device=centres.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_pair_features", cp, ldc, seg_start.data_ptr(), seg_end.data_ptr(), _i64(pair_off, "pair_off").data_ptr(),
+                     centres.shape[0], out.data_ptr(), _stream()), "vlsat_pair_features")
+    return out
+
+
+def node_attn_bias(q, k, v, bias, pair_off, seg_start, seg_end, n_heads: int, max_scene: int) -> torch.Tensor:
+    qp, ldq = _rows(q, "q"); kp, ldk = _rows(k, "k"); vp_, ldv = _rows(v, "v")
+    n, d = q.shape
+    out = torch.empty((n, d), device=q.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_node_attn_bias_fwd", qp, ldq, kp, ldk, vp_, ldv, _f32(bias, "bias").data_ptr(), pair_off.data_ptr(),
+                     seg_start.data_ptr(), seg_end.data_ptr(), n_heads, d // n_heads, max_scene, out.data_ptr(), d, n, _stream()),
+               "vlsat_node_attn_bias_fwd")
+    return out
+
+
+def node_attn_bias_bwd(q, k, v, bias, pair_off, seg_start, seg_end, dout, n_heads: int, max_scene: int):
+    qp, ldq = _rows(q, "q"); kp, ldk = _rows(k, "k"); vp_, ldv = _rows(v, "v"); dp, lddo = _rows(dout, "dout")
+    n, d = q.shape
+    dq = torch.empty((n, d), device=q.device, dtype=torch.float32)
+    dk = torch.zeros((k.shape[0], d), device=q.device, dtype=torch.float32)
+    dv = torch.zeros((v.shape[0], d), device=q.device, dtype=torch.float32)
+    dbias = torch.empty_like(bias)
+    _lib.check(_call("vlsat_node_attn_bias_bwd", qp, ldq, kp, ldk, vp_, ldv, bias.data_ptr(), pair_off.data_ptr(), seg_start.data_ptr(),
+                     seg_end.data_ptr(), dp, lddo, n_heads, d // n_heads, max_scene, dq.data_ptr(), d, dk.data_ptr(), d, dv.data_ptr(), d,
+                     dbias.data_ptr(), n, _stream()), "vlsat_node_attn_bias_bwd")
+    return dq, dk, dv, dbias
+
+
+def pointnet_pool_bwd(dz3, arg, h2, w3, n_pts: int):
+    """(dW3 [c_out, c2], dh2 [n_obj*n_pts, c2])."""
+    n_obj, c_out = dz3.shape
+    c2 = w3.shape[1]
+    dw3 = torch.zeros((c_out, c2), device=dz3.device, dtype=torch.float32)
+    dh2 = torch.zeros((n_obj * n_pts, c2), device=dz3.device, dtype=torch.float32)
+    if not (dz3.is_contiguous() and h2.is_contiguous() and w3.is_contiguous() and arg.is_contiguous()):
+        raise ValueError("pointnet_pool_bwd: operands must be contiguous")
+    _lib.check(_call("vlsat_pointnet_pool_bwd", dz3.data_ptr(), arg.data_ptr(), h2.data_ptr(), w3.data_ptr(), n_obj, n_pts, c_out, c2,
+                     dw3.data_ptr(), dh2.data_ptr(), _stream()), "vlsat_pointnet_pool_bwd")
+    return dw3, dh2
+
+
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int) -> torch.Tensor:
+    xp, ldx = _rows(x, "x")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_dropout", xp, ldx, out.data_ptr(), x.shape[1], x.shape[0], x.shape[1], p, seed, offset, _stream()),
+               "vlsat_dropout")
+    return out
+
+
+def batchnorm(x, gamma, beta, mean, rstd, running_mean, running_var, momentum: float, eps: float, batch_stats: bool, relu: bool):
+    xp, ldx = _rows(x, "x")
+    m, n = x.shape
+    y = torch.empty((m, n), device=x.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_batchnorm_fwd", xp, ldx, gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                     running_mean.data_ptr() if running_mean is not None else None,
+                     running_var.data_ptr() if running_var is not None else None, momentum, eps, int(batch_stats), int(relu),
+                     y.data_ptr(), n, m, n, _stream()), "vlsat_batchnorm_fwd")
+    return y
+
+
+def batchnorm_bwd(dy, x, mean, rstd, gamma, beta, relu: bool, batch_stats: bool):
+    dp, lddy = _rows(dy, "dy"); xp, ldx = _rows(x, "x")
+    m, n = x.shape
+    dx = torch.empty((m, n), device=x.device, dtype=torch.float32)
+    dg = torch.empty((n,), device=x.device, dtype=torch.float32)
+    db = torch.empty((n,), device=x.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_batchnorm_bwd", dp, lddy, xp, ldx, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                     int(relu), int(batch_stats), dx.data_ptr(), n, dg.data_ptr(), db.data_ptr(), m, n, _stream()), "vlsat_batchnorm_bwd")
+    return dx, dg, db
+
+
+def row_l2norm_bwd(dy, x):
+    if not (dy.is_contiguous() and x.is_contiguous()):
+        raise ValueError("row_l2norm_bwd: operands must be contiguous")
+    dx = torch.empty_like(x)
+    _lib.check(_call("vlsat_row_l2norm_bwd", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.shape[0], x.shape[1], _stream()),
+               "vlsat_row_l2norm_bwd")
+    return dx
+
+
+def dot_accum(a, b, out) -> None:
+    _lib.check(_call("vlsat_dot_accum", a.data_ptr(), b.data_ptr(), a.numel(), out.data_ptr(), _stream()), "vlsat_dot_accum")
+
+
+def wgrad_small(dz: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW [N, K] = dz^T x for N, K <= 128 and a tall row count (exact FP32, slab-parallel with atomic accumulation)."""
+    dp, lddz = _rows(dz, "dz"); xp, ldx = _rows(x, "x")
+    m, n = dz.shape
+    k = x.shape[1]
+    dw = torch.zeros((n, k), device=dz.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_wgrad_small", dp, lddz, xp, ldx, m, n, k, dw.data_ptr(), k, _stream(), work=(2.0 * m * n * k, 4.0 * m * (n + k))),
+               "vlsat_wgrad_small")
+    return dw

@@ -57,7 +57,10 @@ class PointNetfeat(nn.Module):
 
     def forward(self, x, return_meta=False):
         assert x.ndim > 2
-        require_inference(self, "PointNetfeat")
+        from . import train_path as T
+        if T.differentiable(self):
+            out = T.pointnet_feat(self, x)
+            return (out, torch.zeros([1]), torch.zeros([1])) if return_meta else out
         w1, b1, w2, b2, w3, b3 = self._weights()
         if x.shape[2] == 1:
             # one "point" per row (the relationship encoders, SGFN_MMG/model.py:305-306): the max is the
@@ -89,7 +92,9 @@ class PointNetRelClsMulti(nn.Module):
             _init_xavier_normal(self)
 
     def forward(self, x):
-        require_inference(self, "PointNetRelClsMulti")
+        from . import train_path as T
+        if T.differentiable(self):
+            return T.rel_classifier(self, x)
         h = ops.linear(x, self.fc1.weight.detach(), self.fc1.bias.detach(), act=ops.ACT_RELU)
         h = ops.linear(h, self.fc2.weight.detach(), self.fc2.bias.detach(), act=ops.ACT_RELU)
         return ops.linear(h, self.fc3.weight.detach(), self.fc3.bias.detach(), act=ops.ACT_SIGMOID)

@@ -228,6 +228,107 @@ int vlsat_permute_rows(const float* in, int64_t ld_in, const int32_t* idx, int64
                        float* out, int64_t ld_out, int gather, void* stream);
 int vlsat_permute_edges(const int64_t* edge_index, const int32_t* perm, int64_t n_edges, int64_t* out, void* stream);
 
+/* ================================================================================================
+ * Backward / training-mode entry points. The reference has no hand-written backward: torch.autograd
+ * over the modules cited above defines it (training step: SGFN_MMG/model.py:337-346,483-488). The
+ * GEMM-shaped parts of every backward (dX = dZ W, dW = dZ^T X) are vlsat_linear_fwd calls on operands
+ * transposed by vlsat_transpose; the entry points below are the remaining memory-bound pieces.
+ * Buffers documented as "accumulated" must be zero-filled by the caller.
+ * ================================================================================================ */
+
+/* out[b, c, r] = in[b, r, c] for `batch` matrices [rows, cols]; ld_out >= rows and the tail columns
+ * [rows, ld_out) of every output row are zero-filled (GEMM reduction lengths are multiples of 4). */
+int vlsat_transpose(const float* in, int64_t ld_in, int64_t batch_stride_in, float* out, int64_t ld_out,
+                    int64_t batch_stride_out, int64_t batch, int64_t rows, int64_t cols, void* stream);
+
+/* Backward of the projection epilogue act(.)*scale*exp(*scale_ptr): dz = dy * act'(y) * scale * exp(*scale_ptr)
+ * (y = forward OUTPUT of the activation; dz nullable, may alias dy) and dbias[n] += sum_m dz[m, n]
+ * (nullable, accumulated). nn.Linear + ReLU / sigmoid sites: network_PointNet.py:328-341, network_MMG.py:31-32,59-60. */
+int vlsat_act_bwd(const float* dy, int64_t lddy, const float* y, int64_t ldy, int act, float scale,
+                  const float* scale_ptr, float* dz, int64_t lddz, float* dbias, int64_t M, int64_t N, void* stream);
+
+/* Weight gradient of a small projection over a tall operand pair: dw[n, k] += sum_m dz[m, n] * x[m, k] (accumulated),
+ * N, K <= 128 (the per-(edge, head) attention MLP network_MMG.py:73 and the PointNet convs network_PointNet.py:99-100,
+ * whose [N, K] result would be a single tensor-core tile). Exact FP32. */
+int vlsat_wgrad_small(const float* dz, int64_t lddz, const float* x, int64_t ldx, int64_t M, int N, int K, float* dw,
+                      int64_t lddw, void* stream);
+
+/* Row gather and its backward. Row i reads / accumulates into row idx[i / R] * R + i % R (R = rows_per_idx;
+ * R = H addresses rows (node, head) of a head-major tensor from rows (edge, head)). Backward of
+ * Gen_Index (network_util.py:50-62) and of the "project per node, gather per edge" epilogue. out accumulated. */
+int vlsat_gather_rows(const float* in, int64_t ld_in, const int64_t* idx, int rows_per_idx, int64_t rows, int cols,
+                      float* out, int64_t ld_out, void* stream);
+int vlsat_scatter_add_rows(const float* in, int64_t ld_in, const int64_t* idx, int rows_per_idx, int64_t rows, int cols,
+                           float* out, int64_t ld_out, void* stream);
+
+/* Backward of vlsat_add_layernorm_fwd (attention.py:122-123): dx = d(x + res); dgamma / dbeta accumulated. */
+int vlsat_add_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* res, int64_t ld_res,
+                            const float* gamma, const float* beta, float* dx, int64_t lddx, float* dgamma, float* dbeta,
+                            int64_t M, int D, float eps, int relu, void* stream);
+
+/* A8, differentiable decomposition (network_MMG.py:96-104 + Aggre_Index network_util.py:64-73). Edges in CSR order.
+ *   t [E*H, d_o]: attention-MLP output of row (e, h);  v: row (n, h) = v + n*ldv + h*d_o (head-major proj_value)
+ *   prob[(e,h), :] = softmax(t[(e,h), :]);  m[e, c*H+h] = prob[(e,h), c] * v[dst(e), h, c];  xx[n, c*H+h] = aggr m
+ *   argmax [n_nodes, H*d_o] int32 (max only): winning edge or -1.
+ * backward: dt [E*H, d_o] written; dv [n_nodes, ld_dv] accumulated. */
+int vlsat_gat_softmax_aggr_fwd(const float* t, const float* v, int64_t ldv, const int64_t* dst_sorted,
+                               const int32_t* row_ptr, int64_t n_nodes, int64_t n_edges, int n_heads, int d_o,
+                               int aggr, float* xx, int64_t ld_xx, float* prob, int32_t* argmax, void* stream);
+int vlsat_gat_softmax_aggr_bwd(const float* dxx, int64_t ld_dxx, const float* prob, const float* v, int64_t ldv,
+                               const int64_t* dst_sorted, const int32_t* row_ptr, const int32_t* argmax,
+                               int64_t n_nodes, int64_t n_edges, int n_heads, int d_o, int aggr, float* dt,
+                               float* dv, int64_t ld_dv, void* stream);
+
+/* A9 backward, score stage for one head and one block of queries (attention.py:54-77): s = Q K^T and dp = dO V^T
+ * are [nq, nk] projection outputs; P = exp(scale*s - lse), dS = P*(dp - delta)*scale. Writes ds [nq, nk] (may alias
+ * dp), ds_t = dS^T and p_t = P^T [nk, ld_t] (columns >= nq zero-filled). delta[i] = dO_i . O_i (vlsat_rowdot_heads,
+ * out [H, M]). */
+int vlsat_attn_prob_bwd(const float* s, const float* dp, int64_t ld, const float* lse, const float* delta, float scale,
+                        float* ds, float* ds_t, float* p_t, int64_t ld_t, int64_t nq, int64_t nk, void* stream);
+int vlsat_rowdot_heads(const float* a, int64_t lda, const float* b, int64_t ldb, float* out, int64_t M, int n_heads,
+                       int dk, void* stream);
+
+/* A6 + A7 with the distance bias as an explicit per-pair tensor (differentiable form of vlsat_node_attn_fwd):
+ * bias row of (query a, key b) = pair_off[a] + (b - seg_start[a]), [*, H]. vlsat_pair_features writes the MLP input
+ * [c_b - c_a, |c_b - c_a|] per pair (network_MMG.py:189-196). max_scene >= the largest scene (host-known bound).
+ * backward: dq written; dk_out, dv_out accumulated; dbias [pairs, H] written. */
+int vlsat_pair_features(const float* centres, int64_t ld_centres, const int32_t* seg_start, const int32_t* seg_end,
+                        const int64_t* pair_off, int64_t n_nodes, float* out, void* stream);
+int vlsat_node_attn_bias_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                             const float* bias, const int64_t* pair_off, const int32_t* seg_start,
+                             const int32_t* seg_end, int n_heads, int dk, int max_scene, float* out, int64_t ldo,
+                             int64_t n_nodes, void* stream);
+int vlsat_node_attn_bias_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                             const float* bias, const int64_t* pair_off, const int32_t* seg_start,
+                             const int32_t* seg_end, const float* dout, int64_t lddo, int n_heads, int dk,
+                             int max_scene, float* dq, int64_t lddq, float* dk_out, int64_t lddk, float* dv_out,
+                             int64_t lddv, float* dbias, int64_t n_nodes, void* stream);
+
+/* A1 backward through the max-pool (network_PointNet.py:164): dz3 [n_obj, c_out] = dOut masked by out > 0,
+ * argmax from the forward, h2 [n_obj*n_pts, c2] = post-ReLU layer-2 activations (recomputed by two projections).
+ * dw3 [c_out, c2] and dh2 [n_obj*n_pts, c2] accumulated. */
+int vlsat_pointnet_pool_bwd(const float* dz3, const int32_t* argmax, const float* h2, const float* w3, int64_t n_obj,
+                            int64_t n_pts, int c_out, int c2, float* dw3, float* dh2, void* stream);
+
+/* nn.Dropout in training mode (8 sites on the path). Counter-based mask: element i is kept iff
+ * hash(seed, offset + i) >= p * 2^32; kept values are scaled by 1/(1-p). The backward is the same call on dy. */
+int vlsat_dropout(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int64_t cols, float p,
+                  uint64_t seed, uint64_t offset, void* stream);
+
+/* nn.BatchNorm1d of mlp_3d (SGFN_MMG/model.py:108). batch_stats = 1: mean / rstd computed from x (biased variance) and
+ * written, running stats (nullable) updated with `momentum` and the unbiased variance; batch_stats = 0: mean / rstd
+ * are inputs (running stats). Optional fused ReLU. backward: dgamma / dbeta written. */
+int vlsat_batchnorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float* mean, float* rstd,
+                        float* running_mean, float* running_var, float momentum, float eps, int batch_stats, int relu,
+                        float* y, int64_t ldy, int64_t M, int64_t N, void* stream);
+int vlsat_batchnorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                        const float* gamma, const float* beta, int relu, int batch_stats, float* dx, int64_t lddx,
+                        float* dgamma, float* dbeta, int64_t M, int64_t N, void* stream);
+
+/* Backward of vlsat_row_l2norm_fwd, and out[0] += a . b (gradient of obj_logit_scale, SGFN_MMG/model.py:327-330). */
+int vlsat_row_l2norm_bwd(const float* dy, const float* x, float* dx, int64_t M, int D, void* stream);
+int vlsat_dot_accum(const float* a, const float* b, int64_t n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

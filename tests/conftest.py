@@ -59,3 +59,39 @@ def assert_close(actual, expected, what="", rtol=RTOL, atol=ATOL, atol_scale=Non
         raise AssertionError(f"{what}: {int(bad.sum())}/{bad.numel()} outside rtol={rtol} atol={atol}; worst: "
                              f"got {actual.flatten()[i].item():.6g} want {expected.flatten()[i].item():.6g} "
                              f"(max abs err {err.max().item():.3g})")
+
+
+# Gradients: rtol 1e-3 plus an absolute floor of GRAD_ATOL_SCALE x max|reference gradient| of the same tensor (gradient
+# entries are sums of many signed terms, so small entries carry the rounding noise of the large ones).
+GRAD_ATOL_SCALE = 2e-4
+
+
+def grad_floor(summaries: dict) -> float:
+    """Absolute floor shared by all gradients of one case: 1e-6 x the largest gradient entry of the case. Some
+    gradients are identically zero in exact arithmetic (e.g. the key bias of a softmax attention), so their fp32
+    values are pure rounding noise of that magnitude."""
+    mx = 0.0
+    for w in summaries.values():
+        mx = max(mx, float(w["full"].abs().max()) if "full" in w else w["absmax"])
+    return 1e-6 * mx
+
+
+def assert_grad_summary_close(got: torch.Tensor, want: dict, what: str, rtol=RTOL, atol_scale=GRAD_ATOL_SCALE, floor=0.0):
+    """Compare a gradient with a ``cases.grad_summary`` fixture (whole tensor, or head + sum + norm)."""
+    g = got.detach().double().cpu().reshape(-1)
+    assert torch.isfinite(g).all(), f"{what}: non-finite gradient"
+    if "full" in want:
+        ref = want["full"].double()
+        assert g.numel() == ref.numel(), f"{what}: {g.numel()} vs {ref.numel()} elements"
+        assert_close(g, ref, what, rtol=rtol, atol=floor, atol_scale=atol_scale)
+        return
+    head = want["head"].double()
+    floor = max(floor, atol_scale * want["absmax"])
+    err = (g[:head.numel()] - head).abs()
+    tol = floor + rtol * head.abs()
+    assert (err <= tol).all(), f"{what}: head differs (max err {err.max().item():.3g}, absmax {want['absmax']:.3g})"
+    assert abs(float(g.norm()) - want["norm"]) <= 2 * rtol * want["norm"] + floor * g.numel() ** 0.5, f"{what}: norm {float(g.norm()):.6g} vs {want['norm']:.6g}"
+    # the plain sum cancels heavily; bound it by the norm-scaled floor
+    n = g.numel()
+    assert abs(float(g.sum()) - want["sum"]) <= rtol * abs(want["sum"]) + floor * n ** 0.5 * 4, \
+        f"{what}: sum {float(g.sum()):.6g} vs {want['sum']:.6g}"

@@ -98,3 +98,27 @@ def mha_inputs(name: str):
 
 def seeded_state(module: torch.nn.Module, seed: int):
     return synth.make_state_dict({k: v.shape for k, v in module.state_dict().items()}, seed)
+
+
+# ---- gradient cases (oracle/make_golden_grads.py) ----------------------------------------------------
+GRAD_MMGNET_CASES = ["mmgnet_cfg1", "mmgnet_ragged", "mmgnet_addaggr"]
+GRAD_GAT_CASES = ["gat_max_h4", "gat_add_h4", "gat_mean_h2", "gat_noedge", "gat_s2t", "gat_mmg_dims"]
+GRAD_FULL_LIMIT = 8192        # gradients up to this many elements are stored whole
+GRAD_HEAD = 512               # larger ones: the first GRAD_HEAD entries + sum + L2 norm
+
+
+def loss_weights(outs, seed: int):
+    """Fixed pseudo-random cotangents: the scalar loss of a gradient case is sum_i <out_i, R_i>."""
+    return [synth.seeded_tensor(f"cotangent.{i}", tuple(o.shape), seed) for i, o in enumerate(outs)]
+
+
+def scalar_loss(outs, seed: int):
+    ws = loss_weights(outs, seed)
+    return sum((o * w.to(o.device, o.dtype)).sum() for o, w in zip(outs, ws))
+
+
+def grad_summary(g: torch.Tensor) -> dict:
+    g = g.detach().double().cpu().reshape(-1)
+    if g.numel() <= GRAD_FULL_LIMIT:
+        return dict(full=g.float())
+    return dict(head=g[:GRAD_HEAD].float(), sum=float(g.sum()), norm=float(g.norm()), absmax=float(g.abs().max()))

@@ -50,11 +50,13 @@ def test_unsupported_configs_fail_loudly():
 def test_no_cpu_fallback():
     m = V.Mmgnet(cases.model_config({}), 160, 26).eval()
     b = synth.make_config_batch("cfg1")
-    with pytest.raises(RuntimeError, match="CUDA"):
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):      # fused inference path
+        m(*b.forward_args())
+    with pytest.raises(RuntimeError, match="CUDA"):                       # differentiable path (grad mode on)
         m(*b.forward_args())
     m.train()
-    with pytest.raises(NotImplementedError):
-        m(*b.forward_args())
+    with pytest.raises(RuntimeError, match="CUDA"):                       # training mode
+        m(*b.forward_args(), istrain=True)
 
 
 def test_synthetic_batch_layout():
