@@ -231,6 +231,53 @@ def run_b200(args):
         e2e_s = float(t.item())
     e2e = world * scenes * args.steps / e2e_s
 
+    # ---- training step: forward + backward (+ NCCL gradient all-reduce at N > 1) ---------------------------------
+    fwd_bwd = None
+    if not args.no_train:
+        from vlsat_b200 import autograd as A
+        from vlsat_b200 import dist as vd
+        model.train()
+        A.DropoutState.manual_seed(1234 + rank)
+        reducer = vd.GradientAllReducer(model.parameters())
+        cot = None
+        n_train = min(args.steps, 10)
+        tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_train)]
+        l0 = ops.launch_count()
+
+        def train_step(b):
+            nonlocal cot
+            model.zero_grad(set_to_none=True)
+            outs = model(*b.forward_args(), istrain=True)
+            if cot is None:       # fixed cotangents stand in for the reference's losses (next row)
+                gen = torch.Generator(device=dev).manual_seed(5)
+                cot = [torch.randn(o.shape, device=dev, generator=gen) / o.numel() for o in outs[:7]]
+            loss = sum((o * c).sum() for o, c in zip(outs[:7], cot))
+            loss.backward()
+            reducer.allreduce()
+            return loss
+        for i in range(2):
+            train_step(resident[i % n_batches])
+        barrier()
+        l0 = ops.launch_count()
+        for i in range(n_train):
+            flush.zero_()
+            tev[i][0].record()
+            train_step(resident[i % n_batches])
+            tev[i][1].record()
+        barrier()
+        train_launches = ops.launch_count() - l0
+        tms = sum(a.elapsed_time(b) for a, b in tev)
+        if world > 1:
+            t = torch.tensor([tms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tms = float(t.item())
+        fwd_bwd = {"value": round(world * scenes * n_train / (tms * 1e-3), 2), "unit": "scenes/s", "ms_per_step": round(tms / n_train, 3),
+                   "steps": n_train, "gpu_launches": train_launches, "grad_allreduce_bytes_per_step": reducer.last_bytes if world > 1 else 0,
+                   "mode": "train(): dropout on, BatchNorm batch statistics, forward(istrain=True) + backward of a fixed-cotangent "
+                           "scalar, eager launches" + (", NCCL all-reduce (mean) of all gradients" if world > 1 else "")}
+        model.zero_grad(set_to_none=True)
+        model.eval()
+
     # ---- per-kernel pass for the roofline (rank 0) ------------------------------------------------------
     roofline, roofline_gat, kernels = None, None, {}
     if rank == 0:
@@ -287,6 +334,7 @@ def run_b200(args):
                    "l2": "flushed between timed steps (256 MB write)", "gemm_engine": ops.gemm_engine(),
                    "launch": "eager C-ABI launches" if args.eager else "CUDA graph replay of the C-ABI launches"},
         "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": host[0].nbytes(), "d2h_bytes_per_step": d2h_bytes},
+        "fwd_bwd": fwd_bwd,
         "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "roofline_gat_scatter": roofline_gat, "kernels": kernels, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
@@ -329,6 +377,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the forward+backward leg")
     ap.add_argument("--eager", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

