@@ -438,8 +438,18 @@ def test_mmgnet_gradients_match_oracle_autograd_on_cfg2_scenes():
     cases.scalar_loss(outs_ref[:7], seed=7).backward()
     outs = model(*b.to(DEV).forward_args(), istrain=True)
     cases.scalar_loss(outs[:7], seed=7).backward()
-    want = {k: cases.grad_summary(sd[k].grad) for k, p in model.named_parameters() if sd[k].grad is not None and p.requires_grad}
-    assert _check_param_grads(model, want, "cfg2x2", mode="norm") >= 100
+    n, bad = 0, []
+    scale = max(sd[k].grad.norm().item() for k, p in model.named_parameters() if sd[k].grad is not None)
+    for k, p in model.named_parameters():
+        r = sd[k].grad
+        if r is None or not p.requires_grad:
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        err = (p.grad.cpu() - r).norm().item()
+        if err > 2e-2 * r.norm().item() + 1e-6 * scale:            # whole tensors: see the arg-max routing note above
+            bad.append(f"{k}: ||g - ref|| = {err:.3g}, ||ref|| = {r.norm().item():.3g}")
+        n += 1
+    assert n >= 100 and not bad, "\n".join(bad)
 
 
 def test_training_mode_with_dropout_runs_and_is_seeded():
@@ -486,7 +496,6 @@ def test_mmg_gradients_tensor_core_engine_float64_oracle():
     cases.scalar_loss(got_out, seed=11).backward()
     for i, (a, r) in enumerate(zip(got_out, ref_out)):
         assert_close(a, r.float(), f"MMG output {i}", atol_scale=FEATURE_ATOL_SCALE)
-    worst = 0.0
     pairs = [(f"input {i}", a.grad, r.grad) for i, (a, r) in enumerate(zip(got_in, ref_in))]
     pairs += [(k, p.grad, sd["mmg." + k].grad) for k, p in m.named_parameters()]
     scale = max(r.norm().item() for _, _, r in pairs if r is not None)
@@ -496,5 +505,3 @@ def test_mmg_gradients_tensor_core_engine_float64_oracle():
         assert a is not None, name
         err = (a.cpu().double() - r).norm().item()
         assert err <= 1e-3 * r.norm().item() + 1e-6 * scale, f"{name}: ||g - ref|| = {err:.3g}, ||ref|| = {r.norm().item():.3g}"
-        worst = max(worst, err / (r.norm().item() + 1e-6 * scale))
-    assert worst < 1e-3
