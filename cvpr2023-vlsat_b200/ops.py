@@ -705,11 +705,13 @@ def pointnet_pool_bwd(dz3, arg, h2, w3, n_pts: int):
     return dw3, dh2
 
 
-def dropout(x: torch.Tensor, p: float, seed: int, offset: int) -> torch.Tensor:
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int, device_step: Optional[torch.Tensor] = None) -> torch.Tensor:
     xp, ldx = _rows(x, "x")
     out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
-    _lib.check(_call("vlsat_dropout", xp, ldx, out.data_ptr(), x.shape[1], x.shape[0], x.shape[1], p, seed, offset, _stream()),
-               "vlsat_dropout")
+    if device_step is not None and (device_step.dtype != torch.int64 or not device_step.is_cuda):
+        raise TypeError("dropout: device_step must be a CUDA int64 scalar tensor")
+    _lib.check(_call("vlsat_dropout", xp, ldx, out.data_ptr(), x.shape[1], x.shape[0], x.shape[1], p, seed, offset,
+                     device_step.data_ptr() if device_step is not None else None, _stream()), "vlsat_dropout")
     return out
 
 

@@ -56,6 +56,18 @@ def rel_classifier(m, x: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------ attention
+_scene_hint = None      # (n_pairs, max_scene) supplied by graph.GraphedTrainStep: no host sync inside a graph capture
+
+
+def scene_stats(batch_ids: torch.Tensor):
+    """(number of same-scene ordered pairs, largest scene) of a batch - one small host sync."""
+    if batch_ids.numel() == 0:
+        return 0, 1
+    counts = torch.bincount(batch_ids.reshape(-1))
+    tot, mx = torch.stack([(counts * counts).sum(), counts.max()]).tolist()
+    return int(tot), max(int(mx), 1)
+
+
 class SceneContextTrain:
     """Scene ranges + the compact same-scene pair list (one host sync per batch for its size)."""
 
@@ -65,7 +77,9 @@ class SceneContextTrain:
         ends = torch.cumsum(sizes, 0)
         self.pair_off = (ends - sizes).contiguous()
         n = sizes.numel()
-        if n:
+        if _scene_hint is not None:
+            tot, mx = _scene_hint
+        elif n:
             tot, mx = torch.stack([ends[-1], sizes.max()]).tolist()      # the one host sync
         else:
             tot, mx = 0, 1

@@ -311,9 +311,11 @@ int vlsat_pointnet_pool_bwd(const float* dz3, const int32_t* argmax, const float
                             int64_t n_pts, int c_out, int c2, float* dw3, float* dh2, void* stream);
 
 /* nn.Dropout in training mode (8 sites on the path). Counter-based mask: element i is kept iff
- * hash(seed, offset + i) >= p * 2^32; kept values are scaled by 1/(1-p). The backward is the same call on dy. */
+ * hash(seed, *device_step, offset + i) >= p * 2^32; kept values are scaled by 1/(1-p). The backward is the same call
+ * on dy. device_step (nullable): uint64 counter in device memory, read at run time - a replayed CUDA graph of the
+ * training step bumps it so that every replay draws fresh masks. */
 int vlsat_dropout(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int64_t cols, float p,
-                  uint64_t seed, uint64_t offset, void* stream);
+                  uint64_t seed, uint64_t offset, const uint64_t* device_step, void* stream);
 
 /* nn.BatchNorm1d of mlp_3d (SGFN_MMG/model.py:108). batch_stats = 1: mean / rstd computed from x (biased variance) and
  * written, running stats (nullable) updated with `momentum` and the unbiased variance; batch_stats = 0: mean / rstd

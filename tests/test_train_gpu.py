@@ -505,3 +505,39 @@ def test_mmg_gradients_tensor_core_engine_float64_oracle():
         assert a is not None, name
         err = (a.cpu().double() - r).norm().item()
         assert err <= 1e-3 * r.norm().item() + 1e-6 * scale, f"{name}: ||g - ref|| = {err:.3g}, ||ref|| = {r.norm().item():.3g}"
+
+
+def test_graphed_train_step_matches_eager_and_redraws_dropout():
+    model = V.Mmgnet(cases.model_config({}), 160, 26)
+    model.load_state_dict(cases.seeded_state(model, cases.MMGNET_WEIGHT_SEED))
+    model = model.to(DEV).train()
+    b = cases.MMGNET_CASES["mmgnet_ragged"][1]().to(DEV)
+    b2 = cases.MMGNET_CASES["mmgnet_ragged"][1]().to(DEV)
+    b2.obj_2d_feats.mul_(0.5)                                  # same shapes / scene composition, different data
+    loss_fn = lambda outs: cases.scalar_loss(outs[:7], seed=7)
+    saved = {m: m.p for m in model.modules() if isinstance(m, torch.nn.Dropout)}
+    _no_dropout(model)
+    step = V.GraphedTrainStep(model, loss_fn)
+    for batch in (b, b2, b):                                   # capture, then replays on new data
+        model.zero_grad(set_to_none=True)
+        loss, outs = step(*batch.forward_args())
+        got = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        got_loss = loss.detach().clone()
+        model.zero_grad(set_to_none=True)
+        model.mlp_3d[1].momentum = 0.0                         # keep BatchNorm running stats fixed for the comparison run
+        ref_loss = loss_fn(model(*batch.forward_args(), istrain=True))
+        ref_loss.backward()
+        model.mlp_3d[1].momentum = 0.1
+        assert torch.allclose(got_loss, ref_loss.detach(), rtol=1e-4, atol=1e-4)
+        assert len(got) >= 100
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                assert torch.allclose(got[k], p.grad, rtol=1e-3, atol=1e-4 * p.grad.abs().max().item() + 1e-7), k
+    assert len(step._graphs) == 1 and step.kernels_per_replay > 500
+    # dropout on: every replay draws new masks
+    for m, p in saved.items():
+        m.p = p
+    step2 = V.GraphedTrainStep(model, loss_fn)
+    l1 = step2(*b.forward_args())[0].detach().clone()
+    l2 = step2(*b.forward_args())[0].detach().clone()
+    assert torch.isfinite(l1) and torch.isfinite(l2) and not torch.equal(l1, l2)
