@@ -112,9 +112,17 @@ def loss_weights(outs, seed: int):
     return [synth.seeded_tensor(f"cotangent.{i}", tuple(o.shape), seed) for i, o in enumerate(outs)]
 
 
+_cotangents = {}
+
+
 def scalar_loss(outs, seed: int):
-    ws = loss_weights(outs, seed)
-    return sum((o * w.to(o.device, o.dtype)).sum() for o, w in zip(outs, ws))
+    """Cotangents are cached per (seed, shapes, device): a second call does no host->device copy, so the loss can be
+    recorded into a CUDA graph after one eager warm-up call."""
+    key = (seed, tuple(tuple(o.shape) for o in outs), str(outs[0].device))
+    ws = _cotangents.get(key)
+    if ws is None:
+        ws = _cotangents[key] = [w.to(o.device, o.dtype) for o, w in zip(outs, loss_weights(outs, seed))]
+    return sum((o * w).sum() for o, w in zip(outs, ws))
 
 
 def grad_summary(g: torch.Tensor) -> dict:
