@@ -19,7 +19,7 @@ class Epilogue(C.Structure):
     _fields_ = [("bias", vp), ("gather_a", vp), ("idx_a", vp), ("gather_b", vp), ("idx_b", vp),
                 ("ld_gather", i64), ("residual", vp), ("ld_res", i64), ("alpha", f32), ("beta", f32),
                 ("scale_ptr", vp), ("act", i32), ("bias_per_row", i32),
-                ("split_hi", vp), ("split_lo", vp), ("ld_split", i64)]
+                ("split_hi", vp), ("split_lo", vp), ("ld_split", i64), ("split_fmt", i32)]
 
 
 class LinearOpts(C.Structure):

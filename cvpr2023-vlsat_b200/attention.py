@@ -107,7 +107,7 @@ class MultiHeadAttention(nn.Module):
 
     def attend_all(self, q_in, kv_in, relu: bool = False, out=None, q_split=None, kv_split=None) -> torch.Tensor:
         """LN(q_in + fc_o(softmax(QK^T/sqrt(dk)) V)) over all keys, no mask/bias; 2-D inputs.
-        ``q_split`` / ``kv_split``: tf32 splits of the inputs if the producer already emitted them."""
+        ``q_split`` / ``kv_split``: (hi, lo) pairs of the inputs if the producer already emitted them."""
         from . import train_path as T
         if T.differentiable(self):
             y = T.mha_all(self, q_in, kv_in, relu_out=relu)
@@ -119,23 +119,31 @@ class MultiHeadAttention(nn.Module):
             # tensor-core path: Q, K row-major; the value projection is emitted transposed (V^T = W_v x^T).
             # The projections write the tf32 splits the attention kernel consumes directly from their epilogues.
             nk = kv_in.shape[0]
-            if kv_split is None:
-                kv_split = ops.tf32_split(kv_in)
             if ops.ATTN_ENGINE == "bf16x3":
-                # projections in 3xTF32 (fp32 outputs), attention operands as bf16 (hi, lo) pairs: the attention
-                # kernel is L2-bandwidth bound and bf16 pairs halve its traffic (csrc/flash_attn_bf16.cu)
-                q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach(), x_split=q_split)
-                k = ops.linear(kv_in, a.fc_k.weight.detach(), a.fc_k.bias.detach(), x_split=kv_split)
-                vt = torch.empty((a.h * a.d_v, (nk + 3) // 4 * 4), device=q_in.device, dtype=torch.float32)
-                ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), out=vt[:, :nk], bias_per_row=True,
-                           x_is_weight=True, w_split=kv_split)
+                # attention operands as bf16 (hi, lo) pairs, written by the projection epilogues: the attention kernel is
+                # L2-bandwidth bound and bf16 pairs halve its traffic (csrc/flash_attn_bf16.cu)
+                if kv_split is None:
+                    kv_split = ops.split_pair(kv_in)
+                _, q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach(), x_split=q_split, emit_split="bf16", want_y=False)
+                _, k = ops.linear(kv_in, a.fc_k.weight.detach(), a.fc_k.bias.detach(), x_split=kv_split, emit_split="bf16", want_y=False)
+                if nk % 8 == 0:
+                    _, vt = ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), bias_per_row=True, x_is_weight=True,
+                                       w_split=kv_split, emit_split="bf16", want_y=False)
+                else:
+                    vt = torch.empty((a.h * a.d_v, (nk + 3) // 4 * 4), device=q_in.device, dtype=torch.float32)
+                    ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), out=vt[:, :nk], bias_per_row=True,
+                               x_is_weight=True, w_split=kv_split)
                 att = ops.flash_attn_bf16(q, k, vt, nk, a.h)
                 return self._finish(q_in, att, relu, out)
-            _, q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach(), x_split=q_split, emit_split=True, want_y=False)
-            _, k = ops.linear(kv_in, a.fc_k.weight.detach(), a.fc_k.bias.detach(), x_split=kv_split, emit_split=True, want_y=False)
+            if kv_split is None or ops.pair_fmt(kv_split) != ops.FMT_TF32:
+                kv_split = ops.tf32_split(kv_in)
+            if q_split is not None and ops.pair_fmt(q_split) != ops.FMT_TF32:
+                q_split = None
+            _, q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach(), x_split=q_split, emit_split="tf32", want_y=False)
+            _, k = ops.linear(kv_in, a.fc_k.weight.detach(), a.fc_k.bias.detach(), x_split=kv_split, emit_split="tf32", want_y=False)
             if nk % 4 == 0:
                 _, vt = ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), bias_per_row=True, x_is_weight=True,
-                                   w_split=kv_split, emit_split=True, want_y=False)
+                                   w_split=kv_split, emit_split="tf32", want_y=False)
             else:
                 vt = torch.zeros((a.h * a.d_v, (nk + 3) // 4 * 4), device=q_in.device, dtype=torch.float32)
                 ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), out=vt[:, :nk], bias_per_row=True,

@@ -8,11 +8,11 @@ namespace vlsat {
 long long g_launch_count = 0;
 int linear_simt(const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int64_t, int64_t,
                 const vlsat_epilogue*, cudaStream_t);
-bool linear_tc_eligible(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t);
+bool linear_tc_eligible(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, int);
 size_t linear_tc_workspace_bytes(int64_t, int64_t, int64_t, bool, bool);
 int tf32_split(const float*, int64_t, int64_t, int64_t, float*, float*, cudaStream_t);
-int linear_tc(const float*, const float*, const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t,
-              const vlsat_epilogue*, int, cudaStream_t);
+int linear_tc(const void*, const void*, const void*, const void*, float*, int64_t, int64_t, int64_t, int64_t,
+              const vlsat_epilogue*, int, int, cudaStream_t);
 bool pointnet_tc_eligible(int, int, int, int, int64_t);
 int pointnet_tc(const float*, int64_t, int, int64_t, const float*, const float*, const float*, const float*, const float*,
                 const float*, int, float*, int32_t*, cudaStream_t);
@@ -46,7 +46,7 @@ extern "C" const char* vlsat_error_string(int status) {
     }
 }
 
-extern "C" const char* vlsat_gemm_engine(void) { return "tcgen05-3xtf32 (ffma-fp32 for non-TMA shapes)"; }
+extern "C" const char* vlsat_gemm_engine(void) { return "tcgen05-bf16x3 (tcgen05-3xtf32 / ffma-fp32 for shapes bf16 pairs cannot address)"; }
 
 extern "C" int64_t vlsat_launch_count(void) { return g_launch_count; }
 
@@ -77,33 +77,40 @@ extern "C" int vlsat_linear_fwd(const float* x, int64_t ldx, const float* w, int
         VLSAT_REQUIRE(!(epi->gather_a || epi->gather_b) || epi->ld_gather >= N);
         VLSAT_REQUIRE(!epi->residual || epi->ld_res >= N);
     }
+    if (epi && epi->split_hi) VLSAT_REQUIRE(epi->split_fmt == VLSAT_SPLIT_TF32 || epi->split_fmt == VLSAT_SPLIT_BF16);
     cudaStream_t st = (cudaStream_t)stream;
-    const int engine = opts ? opts->engine : VLSAT_ENGINE_AUTO;
-    VLSAT_REQUIRE(engine >= VLSAT_ENGINE_AUTO && engine <= VLSAT_ENGINE_TC_1PASS);
-    const bool eligible = linear_tc_eligible(x, ldx, w, ldw, M, N, K);
-    if (engine == VLSAT_ENGINE_SIMT || (engine == VLSAT_ENGINE_AUTO && (!eligible || !opts)))
-        return linear_simt(x, ldx, w, ldw, y, ldy, M, N, K, epi, st);
-    VLSAT_SUPPORT(eligible);
+    int engine = opts ? opts->engine : VLSAT_ENGINE_AUTO;
+    VLSAT_REQUIRE(engine >= VLSAT_ENGINE_AUTO && engine <= VLSAT_ENGINE_TC_BF16X3);
+    if (engine == VLSAT_ENGINE_AUTO) {
+        if (!opts) engine = VLSAT_ENGINE_SIMT;
+        else if (linear_tc_eligible(x, ldx, w, ldw, M, N, K, 1)) engine = VLSAT_ENGINE_TC_BF16X3;
+        else if (linear_tc_eligible(x, ldx, w, ldw, M, N, K, 0)) engine = VLSAT_ENGINE_TC;
+        else engine = VLSAT_ENGINE_SIMT;
+    }
+    if (engine == VLSAT_ENGINE_SIMT) return linear_simt(x, ldx, w, ldw, y, ldy, M, N, K, epi, st);
+    const int kind = engine == VLSAT_ENGINE_TC_BF16X3 ? 1 : 0;
+    VLSAT_SUPPORT(linear_tc_eligible(x, ldx, w, ldw, M, N, K, kind));
     const int passes = engine == VLSAT_ENGINE_TC_1PASS ? 1 : 3;
-    const float *xh = opts->x_hi, *xl = opts->x_lo, *wh = opts->w_hi, *wl = opts->w_lo;
+    const void *xh = opts->x_hi, *xl = opts->x_lo, *wh = opts->w_hi, *wl = opts->w_lo;
     VLSAT_REQUIRE((xh == nullptr) == (xl == nullptr) && (wh == nullptr) == (wl == nullptr));
     const size_t need = linear_tc_workspace_bytes(M, N, K, xh == nullptr, wh == nullptr);
     if (need > 0 && (!opts->workspace || opts->workspace_bytes < need)) return VLSAT_ERR_WORKSPACE;
     float* ws = (float*)opts->workspace;
     if (need > 0) VLSAT_SUPPORT((uintptr_t)ws % 16 == 0);
-    if (!xh) {
-        float* h = ws; float* l = ws + M * K; ws += 2 * M * K;
-        int rc = tf32_split(x, ldx, M, K, h, l, st);
-        if (rc) return rc;
-        xh = h; xl = l;
-    }
-    if (!wh) {
-        float* h = ws; float* l = ws + N * K;
-        int rc = tf32_split(w, ldw, N, K, h, l, st);
-        if (rc) return rc;
-        wh = h; wl = l;
-    }
-    return linear_tc(xh, xl, wh, wl, y, ldy, M, N, K, epi, passes, st);
+    auto split = [&](const float* src, int64_t ld, int64_t rows, const void*& hi, const void*& lo) -> int {
+        // both formats: hi then lo, rows * K elements each; a pair takes rows * K floats
+        if (kind == 1) {
+            uint16_t* h = (uint16_t*)ws; uint16_t* l = h + rows * K;
+            hi = h; lo = l; ws += rows * K;
+            return bf16_split(src, ld, rows, K, h, l, K, st);
+        }
+        float* h = ws; float* l = ws + rows * K;
+        hi = h; lo = l; ws += 2 * rows * K;
+        return tf32_split(src, ld, rows, K, h, l, st);
+    };
+    if (!xh) { int rc = split(x, ldx, M, xh, xl); if (rc) return rc; }
+    if (!wh) { int rc = split(w, ldw, N, wh, wl); if (rc) return rc; }
+    return linear_tc(xh, xl, wh, wl, y, ldy, M, N, K, epi, passes, kind, st);
 }
 
 extern "C" int vlsat_flash_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,

@@ -48,4 +48,28 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     lo = v - hi;
 }
 
+// bf16 pair of two values packed as {lo16 = a, hi16 = b} (cvt.rn.bf16x2: first source goes to the upper half)
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// (hi, lo) bf16 pairs of two values: hi = bf16(v), lo = bf16(v - hi)
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(a, b);
+    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+
+// scalar store of one result's split in the format the epilogue asks for
+__device__ __forceinline__ void store_split(const vlsat_epilogue& e, float v, int64_t m, int64_t n) {
+    if (e.split_fmt == VLSAT_SPLIT_BF16) {
+        uint32_t hi, lo;
+        split_bf16x2(v, 0.f, hi, lo);
+        reinterpret_cast<uint16_t*>(e.split_hi)[m * e.ld_split + n] = (uint16_t)(hi & 0xffffu);
+        reinterpret_cast<uint16_t*>(e.split_lo)[m * e.ld_split + n] = (uint16_t)(lo & 0xffffu);
+    } else {
+        split_tf32(v, reinterpret_cast<float*>(e.split_hi)[m * e.ld_split + n], reinterpret_cast<float*>(e.split_lo)[m * e.ld_split + n]);
+    }
+}
+
 }  // namespace vlsat

@@ -123,7 +123,7 @@ linear_simt_kernel(const LinearArgs a) {
             if (n < a.N) {
                 const float v = epilogue_one(a.epi, acc[i][j], m, n, ia, ib, post_scale);
                 if (a.y) a.y[m * a.ldy + n] = v;
-                if (a.epi.split_hi) split_tf32(v, a.epi.split_hi[m * a.epi.ld_split + n], a.epi.split_lo[m * a.epi.ld_split + n]);
+                if (a.epi.split_hi) store_split(a.epi, v, m, n);
             }
         }
     }

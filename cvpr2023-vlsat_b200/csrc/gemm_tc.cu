@@ -7,7 +7,12 @@
 // conversion of lo are both <= 2^-23 relative, i.e. fp32-level, so results agree with the FFMA engine
 // to ~1e-6 while running on the tensor pipe.
 //
-// Kernel shape: one 128 x BN output tile per CTA, K blocks of 32 fp32 (= one 128-byte swizzle row).
+// BF16x3 variant (KD = Kind::BF16, the default engine): operands are bf16 pairs  hi = bf16(x), lo = bf16(x - hi)  (same
+// 4 bytes per element as fp32) and the three MMAs are kind::f16 with bf16 inputs: twice the tensor rate and twice the
+// K per 128-byte smem row of the tf32 form; |x - hi - lo| <= 2^-17 |x| and the dropped lo*lo term is <= 2^-18, so one
+// product is accurate to ~1e-5 relative (fp32 accumulation) - two orders inside the 1e-3 parity budget.
+//
+// Kernel shape: one 128 x BN output tile per CTA, K blocks of one 128-byte swizzle row (32 tf32 / 64 bf16).
 //   warp 0      : TMA producer (4 operand tiles per stage: A_hi, A_lo, B_hi, B_lo) on an mbarrier ring
 //   warp 1      : TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit releases the stage
 //   warps 2..5  : epilogue - tcgen05.ld the accumulator (one TMEM lane = one output row per thread),
@@ -51,7 +56,7 @@ __global__ void tf32_split_kernel(const float* __restrict__ x, int64_t ldx, int6
 // Persistent kernel: gridDim.x CTAs walk the output tiles round-robin (n fastest, so the CTAs that run
 // together share A row-tiles in L2). Two TMEM accumulators: the epilogue of tile i overlaps the main loop
 // of tile i+1.
-template <int BN, int STAGES, int PASSES>
+template <int BN, int STAGES, int PASSES, Kind KD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                  const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
@@ -70,7 +75,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = (int)((a.K + TC_BK - 1) / TC_BK);
+    constexpr int BK = (KD == Kind::TF32) ? TC_BK : 2 * TC_BK;      // K elements per 128-byte block
+    const int num_kb = (int)((a.K + BK - 1) / BK);
     const int tiles_n = (int)((a.N + BN - 1) / BN), tiles_m = (int)((a.M + TC_BM - 1) / TC_BM);
     const int n_tiles = tiles_m * tiles_n;
 
@@ -98,18 +104,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                 if (elect_one()) {
                     uint8_t* st = smem + s * STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                    tma_load_2d(st, &tm_ahi, &full_bar[s], kb * TC_BK, m0);
-                    tma_load_2d(st + TC_A_TILE, &tm_bhi, &full_bar[s], kb * TC_BK, n0);
+                    tma_load_2d(st, &tm_ahi, &full_bar[s], kb * BK, m0);
+                    tma_load_2d(st + TC_A_TILE, &tm_bhi, &full_bar[s], kb * BK, n0);
                     if (PASSES == 3) {
-                        tma_load_2d(st + TC_A_TILE + B_TILE, &tm_alo, &full_bar[s], kb * TC_BK, m0);
-                        tma_load_2d(st + 2 * TC_A_TILE + B_TILE, &tm_blo, &full_bar[s], kb * TC_BK, n0);
+                        tma_load_2d(st + TC_A_TILE + B_TILE, &tm_alo, &full_bar[s], kb * BK, m0);
+                        tma_load_2d(st + 2 * TC_A_TILE + B_TILE, &tm_blo, &full_bar[s], kb * BK, n0);
                     }
                 }
                 __syncwarp();
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc<Kind::TF32>(TC_BM, BN);
+        constexpr uint32_t idesc = make_idesc<KD>(TC_BM, BN);
         // descriptors differ only in the 14-bit start-address field: build one, then add offsets (>>4)
         const uint64_t desc0 = make_sdesc_k128(smem_u32(smem));
         int g = 0, i = 0;
@@ -129,15 +135,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                     const uint64_t dal = dah + ((TC_A_TILE + B_TILE) >> 4);
                     const uint64_t dbl = dah + ((2 * TC_A_TILE + B_TILE) >> 4);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) {       // UMMA_K = 8 for tf32 (32 bytes = 2 x 16 B)
+                    for (int k = 0; k < 4; ++k) {               // UMMA_K = 8 tf32 / 16 bf16 = 32 bytes = 2 x 16 B
                         const uint32_t acc = (k > 0) ? 1u : (kb > 0 ? 1u : 0u);
                         if (PASSES == 3) {
                             // small terms first, then the leading product
-                            mma_ss<Kind::TF32>(tacc, dal + 2 * k, dbh + 2 * k, idesc, acc);
-                            mma_ss<Kind::TF32>(tacc, dah + 2 * k, dbl + 2 * k, idesc, 1);
-                            mma_ss<Kind::TF32>(tacc, dah + 2 * k, dbh + 2 * k, idesc, 1);
+                            mma_ss<KD>(tacc, dal + 2 * k, dbh + 2 * k, idesc, acc);
+                            mma_ss<KD>(tacc, dah + 2 * k, dbl + 2 * k, idesc, 1);
+                            mma_ss<KD>(tacc, dah + 2 * k, dbh + 2 * k, idesc, 1);
                         } else {
-                            mma_ss<Kind::TF32>(tacc, dah + 2 * k, dbh + 2 * k, idesc, acc);
+                            mma_ss<KD>(tacc, dah + 2 * k, dbh + 2 * k, idesc, acc);
                         }
                     }
                     tc_commit(&empty_bar[s]);                    // stage reusable once these MMAs retire
@@ -167,10 +173,28 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
             if (et == 0) { tma_store_2d(tm, sb, col0, row0); bulk_commit(); }
             ++sidx;
         };
+        // bf16 (hi, lo) pairs of one 128x32 block: two [128 rows x 64 B] halves of one staging block in the 64-byte
+        // swizzle (16-byte chunk c of row r lives at c ^ ((r >> 1) & 3)), one TMA store each
+        auto stage_store_bf16 = [&](const uint32_t (&hp)[16], const uint32_t (&lp)[16], int col0, int row0) {
+            uint8_t* sb = staging + (sidx & 1) * STG_BYTES;
+            if (et == 0) bulk_wait_read<1>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int sw = (srow >> 1) & 3;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                *reinterpret_cast<uint4*>(sb + srow * 64 + ((c ^ sw) << 4)) = make_uint4(hp[4 * c], hp[4 * c + 1], hp[4 * c + 2], hp[4 * c + 3]);
+                *reinterpret_cast<uint4*>(sb + STG_BYTES / 2 + srow * 64 + ((c ^ sw) << 4)) = make_uint4(lp[4 * c], lp[4 * c + 1], lp[4 * c + 2], lp[4 * c + 3]);
+            }
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) { tma_store_2d(&tm_shi, sb, col0, row0); tma_store_2d(&tm_slo, sb + STG_BYTES / 2, col0, row0); bulk_commit(); }
+            ++sidx;
+        };
         auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+        const bool split_bf16 = e.split_fmt == VLSAT_SPLIT_BF16;
         // fully vectorised epilogue when every operand row is 16-byte addressable
         const bool vec_ok = a.tma_store && (BN % 4 == 0) &&
-                            (!e.split_hi || (e.ld_split % 4 == 0 && al16(e.split_hi) && al16(e.split_lo))) &&
+                            (!e.split_hi || (e.ld_split % (split_bf16 ? 8 : 4) == 0 && al16(e.split_hi) && al16(e.split_lo))) &&
                             (!e.bias || e.bias_per_row || al16(e.bias)) &&
                             (!(e.gather_a || e.gather_b) || (e.ld_gather % 4 == 0 && al16(e.gather_a) && al16(e.gather_b))) &&
                             (!e.residual || (e.ld_res % 4 == 0 && al16(e.residual)));
@@ -253,7 +277,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                         }
                     }
                     if (a.y) stage_store(&tm_y, v, (int)nb, m0);
-                    if (e.split_hi) {
+                    if (e.split_hi && split_bf16) {
+                        uint32_t hp[16], lp[16];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            split_bf16x2(v[j].x, v[j].y, hp[2 * j], lp[2 * j]);
+                            split_bf16x2(v[j].z, v[j].w, hp[2 * j + 1], lp[2 * j + 1]);
+                        }
+                        stage_store_bf16(hp, lp, (int)nb, m0);
+                    } else if (e.split_hi) {
                         float4 hi[8], lo[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -269,7 +301,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                         if (nb + j < a.N) {
                             const float v = epilogue_one(e, __uint_as_float(r[j]), m_own, nb + j, ia_own, ib_own, post_scale);
                             if (a.y) a.y[m_own * a.ldy + nb + j] = v;
-                            if (e.split_hi) split_tf32(v, e.split_hi[m_own * e.ld_split + nb + j], e.split_lo[m_own * e.ld_split + nb + j]);
+                            if (e.split_hi) store_split(e, v, m_own, nb + j);
                         }
                 }
             }
@@ -286,11 +318,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
 
 long long* g_trace = nullptr;
 
-bool linear_tc_eligible(const float* x, int64_t ldx, const float* w, int64_t ldw, int64_t M, int64_t N, int64_t K) {
-    return (K % 4 == 0) && K >= 32 && (ldx % 4 == 0) && (ldw % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
-           ((uintptr_t)w % 16 == 0) && M >= 1 && N >= 8 && M < (1ll << 31) && N < (1ll << 31) && encode_fn() != nullptr;
+int bf16_split(const float*, int64_t, int64_t, int64_t, uint16_t*, uint16_t*, int64_t, cudaStream_t);
+
+// kind: 0 = tf32 pairs (K % 4 == 0), 1 = bf16 pairs (K % 8 == 0: compact bf16 rows must stay 16-byte aligned)
+bool linear_tc_eligible(const float* x, int64_t ldx, const float* w, int64_t ldw, int64_t M, int64_t N, int64_t K, int kind) {
+    const bool common = K >= 32 && M >= 1 && N >= 8 && M < (1ll << 31) && N < (1ll << 31) && encode_fn() != nullptr;
+    if (kind == 1) return common && (K % 8 == 0);
+    return common && (K % 4 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0);
 }
 
+// both pair formats take 4 bytes per element and half
 size_t linear_tc_workspace_bytes(int64_t M, int64_t N, int64_t K, bool need_x, bool need_w) {
     return (size_t)((need_x ? 2 * M * K : 0) + (need_w ? 2 * N * K : 0)) * sizeof(float);
 }
@@ -302,13 +339,13 @@ int tf32_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* h
     return finish_launch();
 }
 
-template <int BN, int STAGES, int PASSES>
+template <int BN, int STAGES, int PASSES, Kind KD>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tal, const CUtensorMap& tb, const CUtensorMap& tbl,
                      const CUtensorMap& ty, const CUtensorMap& tsh, const CUtensorMap& tsl,
                      const LinearArgs& a, cudaStream_t st) {
     constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TC_A_TILE + BN * 128);
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 2 * TC_BM * 128 /*store staging*/ + 1024 /*align*/ + 256 /*barriers*/;
-    auto kern = linear_tc_kernel<BN, STAGES, PASSES>;
+    auto kern = linear_tc_kernel<BN, STAGES, PASSES, KD>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t n_tiles = ceil_div(a.N, BN) * ceil_div(a.M, TC_BM);
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, kNumSMs);
@@ -316,38 +353,49 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tal, const CUtens
     return finish_launch();
 }
 
-// x_hi/x_lo and w_hi/w_lo: compact [rows, K] split operands (ld = K). passes = 3 (3xTF32) or 1 (plain TF32).
-int linear_tc(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, float* y, int64_t ldy,
-              int64_t M, int64_t N, int64_t K, const vlsat_epilogue* epi, int passes, cudaStream_t st) {
+// x_hi/x_lo and w_hi/w_lo: compact [rows, K] split operands (ld = K) in the pair format of `kind`
+// (0 = tf32 floats, 1 = bf16). passes = 3 (x3 split product) or 1 (plain TF32, kind 0 only).
+int linear_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* y, int64_t ldy,
+              int64_t M, int64_t N, int64_t K, const vlsat_epilogue* epi, int passes, int kind, cudaStream_t st) {
     LinearArgs a;
-    a.x = x_hi; a.ldx = K; a.w = w_hi; a.ldw = K; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.K = K;
+    a.x = (const float*)x_hi; a.ldx = K; a.w = (const float*)w_hi; a.ldw = K; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.K = K;
     if (epi) a.epi = *epi;
     else { a.epi = vlsat_epilogue{}; a.epi.alpha = 1.f; }
     a.trace = g_trace;
     const int bn = (N <= 64) ? 64 : 128;
+    const auto DT = kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const int eb = kind == 1 ? 2 : 4;
+    const uint32_t bk = 128 / eb;                     // elements per 128-byte K block
+    if (kind == 1 && passes != 3) return VLSAT_ERR_UNSUPPORTED;
     CUtensorMap ta, tal, tb, tbl;
-    bool ok = make_tmap_2d(&ta, x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, K, K, TC_BK, TC_BM) &&
-              make_tmap_2d(&tb, w_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, N, K, K, TC_BK, bn);
+    bool ok = make_tmap_2d(&ta, x_hi, DT, eb, M, K, K, bk, TC_BM) && make_tmap_2d(&tb, w_hi, DT, eb, N, K, K, bk, bn);
     if (passes == 3)
-        ok = ok && make_tmap_2d(&tal, x_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, K, K, TC_BK, TC_BM) &&
-             make_tmap_2d(&tbl, w_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, N, K, K, TC_BK, bn);
+        ok = ok && make_tmap_2d(&tal, x_lo, DT, eb, M, K, K, bk, TC_BM) && make_tmap_2d(&tbl, w_lo, DT, eb, N, K, K, bk, bn);
     else { tal = ta; tbl = tb; }
     if (!ok) return VLSAT_ERR_UNSUPPORTED;
     // output tensor maps (TMA stores): possible when every output row is 16-byte addressable
     auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
     const vlsat_epilogue& e = a.epi;
-    bool tma_out = (!y || (ldy % 4 == 0 && al16(y))) && (!e.split_hi || (e.ld_split % 4 == 0 && al16(e.split_hi) && al16(e.split_lo))) &&
+    const bool sbf = e.split_fmt == VLSAT_SPLIT_BF16;
+    bool tma_out = (!y || (ldy % 4 == 0 && al16(y))) && (!e.split_hi || (e.ld_split % (sbf ? 8 : 4) == 0 && al16(e.split_hi) && al16(e.split_lo))) &&
                    (!e.bias || e.bias_per_row || al16(e.bias)) &&
                    (!(e.gather_a || e.gather_b) || (e.ld_gather % 4 == 0 && al16(e.gather_a) && al16(e.gather_b))) &&
                    (!e.residual || (e.ld_res % 4 == 0 && al16(e.residual)));
     CUtensorMap ty = ta, tsh = ta, tsl = ta;
     if (tma_out && y) tma_out = make_tmap_2d(&ty, y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldy, 32, TC_BM);
-    if (tma_out && e.split_hi)
-        tma_out = make_tmap_2d(&tsh, e.split_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_split, 32, TC_BM) &&
-                  make_tmap_2d(&tsl, e.split_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_split, 32, TC_BM);
+    if (tma_out && e.split_hi) {
+        if (sbf)     // 64-byte wide boxes (32 bf16 columns) in the 64-byte swizzle
+            tma_out = make_tmap_2d(&tsh, e.split_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, e.ld_split, 32, TC_BM, CU_TENSOR_MAP_SWIZZLE_64B) &&
+                      make_tmap_2d(&tsl, e.split_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, e.ld_split, 32, TC_BM, CU_TENSOR_MAP_SWIZZLE_64B);
+        else
+            tma_out = make_tmap_2d(&tsh, e.split_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_split, 32, TC_BM) &&
+                      make_tmap_2d(&tsl, e.split_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_split, 32, TC_BM);
+    }
     a.tma_store = tma_out ? 1 : 0;
-    if (passes == 3) return bn == 64 ? launch_tc<64, 4, 3>(ta, tal, tb, tbl, ty, tsh, tsl, a, st) : launch_tc<128, 3, 3>(ta, tal, tb, tbl, ty, tsh, tsl, a, st);
-    return bn == 64 ? launch_tc<64, 6, 1>(ta, tal, tb, tbl, ty, tsh, tsl, a, st) : launch_tc<128, 6, 1>(ta, tal, tb, tbl, ty, tsh, tsl, a, st);
+    if (kind == 1)
+        return bn == 64 ? launch_tc<64, 4, 3, Kind::BF16>(ta, tal, tb, tbl, ty, tsh, tsl, a, st) : launch_tc<128, 3, 3, Kind::BF16>(ta, tal, tb, tbl, ty, tsh, tsl, a, st);
+    if (passes == 3) return bn == 64 ? launch_tc<64, 4, 3, Kind::TF32>(ta, tal, tb, tbl, ty, tsh, tsl, a, st) : launch_tc<128, 3, 3, Kind::TF32>(ta, tal, tb, tbl, ty, tsh, tsl, a, st);
+    return bn == 64 ? launch_tc<64, 6, 1, Kind::TF32>(ta, tal, tb, tbl, ty, tsh, tsl, a, st) : launch_tc<128, 6, 1, Kind::TF32>(ta, tal, tb, tbl, ty, tsh, tsl, a, st);
 }
 
 }  // namespace vlsat

@@ -158,9 +158,11 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // Row-major [rows, cols] matrix with row stride ld (elements); box = {box_cols (128 B worth), box_rows},
-// 128B swizzle, out-of-bounds elements read as zero (this is what handles the M / N / K tails).
+// 128B swizzle (64B for the 64-byte-wide bf16 store boxes), out-of-bounds elements read as zero (this is what
+// handles the M / N / K tails).
 inline bool make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows,
-                         uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+                         uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows,
+                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t gdim[2] = {cols, rows};
@@ -168,7 +170,7 @@ inline bool make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     return fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace tc

@@ -238,11 +238,11 @@ class MultiHeadedEdgeAttention(nn.Module):
             self.last_edge_split = None
             return new_edge, (torch.empty((0, self.d_o, H), device=x.device) if want_prob else None)
         if edge_split is None:
-            edge_split = ops.tf32_split(edge)
+            edge_split = ops.split_pair(edge)
         _, h = ops.linear(edge, w1.weight.detach()[:, dn:dn + de], w1.bias.detach(), act=ops.ACT_RELU,
                           gather=(a_src, g.src, b_dst, g.dst), x_split=edge_split, emit_split=True, want_y=False)
         new_edge, self.last_edge_split = ops.linear(h, w2.weight.detach(), w2.bias.detach(), emit_split=True)
-        _, k_hm = ops.linear(edge, w["w_pe"], w["b_pe"], x_split=edge_split, emit_split=True, want_y=False)   # rows (e, h)
+        _, k_hm = ops.linear(edge, w["w_pe"], w["b_pe"], x_split=edge_split, emit_split="tf32", want_y=False)   # rows (e, h)
         _, prob = ops.gat_edge_tc(k_hm, qc, v_hm, g.src, g.dst, w["c1k"], w["c2"], w["c2b"], g.num_nodes, H, xx_out,
                                   want_prob=want_prob, d_n=self.d_n)
         return new_edge, prob

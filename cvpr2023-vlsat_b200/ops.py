@@ -130,14 +130,16 @@ def edge_descriptor(desc: torch.Tensor, edge_index: torch.Tensor) -> torch.Tenso
 
 
 # ------------------------------------------------------------------------------------- dense projection
-ENGINES = {"auto": 0, "simt": 1, "tc": 2, "tc1": 3}
+ENGINES = {"auto": 0, "simt": 1, "tc": 2, "tc1": 3, "bf16x3": 4}
+FMT_TF32, FMT_BF16 = 0, 1            # (hi, lo) pair formats: VLSAT_SPLIT_* of include/vlsat_b200.h
 _engine = ENGINES[os.environ.get("VLSAT_GEMM_ENGINE", "auto")]
 _weight_splits = {}
 
 
 def set_gemm_engine(name: str) -> None:
-    """'auto' (tcgen05 3xTF32 where TMA-addressable, FFMA otherwise), 'simt' (exact fp32 FFMA everywhere),
-    'tc' (force tensor cores; ineligible shapes raise), 'tc1' (single-pass TF32, not fp32-accurate)."""
+    """'auto' (tcgen05 BF16x3 where bf16 pairs are TMA-addressable, 3xTF32 next, FFMA otherwise), 'simt' (exact fp32
+    FFMA everywhere), 'bf16x3' / 'tc' (force that tensor-core engine; ineligible shapes fall to the next one),
+    'tc1' (single-pass TF32, not fp32-accurate)."""
     global _engine
     _engine = ENGINES[name]
 
@@ -146,21 +148,43 @@ def tensor_cores_enabled() -> bool:
     return _engine != ENGINES["simt"]
 
 
-def _tc_eligible(x, ldx, w, ldw, n, k) -> bool:
+def pair_fmt(pair) -> int:
+    return FMT_BF16 if pair[0].dtype == torch.bfloat16 else FMT_TF32
+
+
+def default_fmt(k: int) -> int:
+    """Pair format the dense-projection engine wants for an operand with ``k`` columns."""
+    return FMT_BF16 if (_engine in (ENGINES["auto"], ENGINES["bf16x3"]) and k % 8 == 0) else FMT_TF32
+
+
+def split_pair(x: torch.Tensor, fmt: Optional[int] = None):
+    """(hi, lo) pair of an fp32 matrix in format ``fmt`` (default: what ``linear`` wants for this width), compact."""
+    fmt = default_fmt(x.shape[1]) if fmt is None else fmt
+    return bf16_split(x) if fmt == FMT_BF16 else tf32_split(x)
+
+
+def _tc_eligible(x, ldx, w, ldw, n, k, fmt) -> bool:
+    if fmt == FMT_BF16:
+        return k % 8 == 0 and k >= 32 and n >= 8
     return (k % 4 == 0 and k >= 32 and ldx % 4 == 0 and ldw % 4 == 0 and x.data_ptr() % 16 == 0
             and w.data_ptr() % 16 == 0 and n >= 8)
 
 
-def _weight_split(w: torch.Tensor, ldw: int):
-    """tf32 hi/lo copies of a weight (view), cached until the parameter is written again."""
-    key = (w.data_ptr(), tuple(w.shape), ldw)
+def _weight_split(w: torch.Tensor, ldw: int, fmt: int):
+    """(hi, lo) copies of a weight (view) in pair format ``fmt``, cached until the parameter is written again."""
+    key = (w.data_ptr(), tuple(w.shape), ldw, fmt)
     ent = _weight_splits.get(key)
     if ent is not None and ent[0] == w._version:
         return ent[1]
     n, k = w.shape
-    hl = ent[1] if ent is not None else torch.empty((2, n, k), device=w.device, dtype=torch.float32)
-    _lib.check(_call("vlsat_tf32_split", w.data_ptr(), ldw, n, k, hl[0].data_ptr(), hl[1].data_ptr(), _stream()),
-               "vlsat_tf32_split")
+    if fmt == FMT_BF16:
+        hl = ent[1] if ent is not None else torch.empty((2, n, k), device=w.device, dtype=torch.bfloat16)
+        _lib.check(_call("vlsat_bf16_split", w.data_ptr(), ldw, n, k, hl[0].data_ptr(), hl[1].data_ptr(), k, _stream()),
+                   "vlsat_bf16_split")
+    else:
+        hl = ent[1] if ent is not None else torch.empty((2, n, k), device=w.device, dtype=torch.float32)
+        _lib.check(_call("vlsat_tf32_split", w.data_ptr(), ldw, n, k, hl[0].data_ptr(), hl[1].data_ptr(), _stream()),
+                   "vlsat_tf32_split")
     _weight_splits[key] = (w._version, hl, w)        # holding w keeps its storage (and this key) unique
     return hl
 
@@ -170,24 +194,28 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            gather: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]] = None,
            residual: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 1.0,
            scale_ptr: Optional[torch.Tensor] = None, bias_per_row: bool = False,
-           x_is_weight: bool = False, x_split=None, w_split=None, emit_split: bool = False, want_y: bool = True,
+           x_is_weight: bool = False, x_split=None, w_split=None, emit_split=False, want_y: bool = True,
            cache_w: bool = True):
     """y = post(act(x w^T + bias + ga[ia] + gb[ib])), post(t) = (alpha t + beta residual) * exp(scale).
 
     x [M, K] and w [N, K] may be column-slice views (row stride = leading dimension); ``out`` may be a
-    column slice of a wider buffer. ``x_is_weight=True`` swaps the roles for the tf32-split cache: x is
+    column slice of a wider buffer. ``x_is_weight=True`` swaps the roles for the split cache: x is
     a parameter (split cached), w an activation (split per call) - used to emit y^T = W x^T.
-    ``x_split=(hi, lo)``: tf32 split of x already available (compact [M, K]) - skips the split pass.
-    ``emit_split=True``: the epilogue also writes the tf32 split of y and the call returns ``(y, (hi, lo))``
-    (``want_y=False``: only the split is written, y is None). ``cache_w=False``: do not cache the tf32 split of
-    ``w`` (it is an activation or a temporary). ``x`` itself may be such a ``(hi, lo)`` pair
-    when the unsplit activation was never materialised (tensor-core engine only)."""
-    if isinstance(x, tuple):
+    ``x_split=(hi, lo)``: pair of x already available (compact [M, K]; bf16 or tf32 pairs, the engine follows the
+    format) - skips the split pass. ``emit_split``: the epilogue also writes the (hi, lo) pair of y and the call returns
+    ``(y, (hi, lo))`` - ``True`` = the format a following projection wants, or ``FMT_TF32`` / ``FMT_BF16`` given as
+    ``'tf32'`` / ``'bf16'`` (``want_y=False``: only the pair is written, y is None). ``cache_w=False``: do not cache the
+    split of ``w`` (it is an activation or a temporary). ``x`` itself may be such a ``(hi, lo)`` pair when the unsplit
+    activation was never materialised (tensor-core engines only)."""
+    x_pair_only = isinstance(x, tuple)
+    if x_pair_only:
         x_split = x
         x = x_split[0]
         if not (tensor_cores_enabled() and x.shape[1] % 4 == 0 and x.shape[1] >= 32 and w.shape[0] >= 8):
             raise RuntimeError("linear: a pre-split activation can only feed the tensor-core engine")
-    xp, ldx = _rows(x, "x")
+        xp, ldx = x.data_ptr(), x.shape[1]
+    else:
+        xp, ldx = _rows(x, "x")
     wp, ldw = _rows(w, "w")
     m, k = x.shape
     n = w.shape[0]
@@ -207,10 +235,11 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     epi = Epilogue()
     y_split = None
     if emit_split:
-        if n % 4:
-            raise ValueError("linear: emit_split needs N % 4 == 0")
-        y_split = torch.empty((2, m, n), device=x.device, dtype=torch.float32)
-        epi.split_hi, epi.split_lo, epi.ld_split = y_split[0].data_ptr(), y_split[1].data_ptr(), n
+        efmt = default_fmt(n) if emit_split is True else {"tf32": FMT_TF32, "bf16": FMT_BF16}[emit_split]
+        if n % (8 if efmt == FMT_BF16 else 4):
+            raise ValueError("linear: emit_split needs N % 4 == 0 (tf32 pairs) / N % 8 == 0 (bf16 pairs)")
+        y_split = torch.empty((2, m, n), device=x.device, dtype=torch.bfloat16 if efmt == FMT_BF16 else torch.float32)
+        epi.split_hi, epi.split_lo, epi.ld_split, epi.split_fmt = y_split[0].data_ptr(), y_split[1].data_ptr(), n, efmt
     epi.alpha, epi.beta, epi.act = alpha, beta, act
     if bias is not None:
         _f32(bias, "bias")
@@ -240,11 +269,21 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         _f32(scale_ptr, "scale_ptr")
         epi.scale_ptr = scale_ptr.data_ptr()
     opts = LinearOpts()
-    opts.engine = _engine
+    opts.engine = ENGINES["simt"]
     ws = None
-    if _engine != ENGINES["simt"] and m > 0 and _tc_eligible(x, ldx, w, ldw, n, k):
+    # operand pair format: given pairs decide; otherwise the engine's preference for this K
+    given = x_split if x_split is not None else w_split
+    fmt = pair_fmt(given) if given is not None else default_fmt(k)
+    if x_split is not None and w_split is not None and pair_fmt(x_split) != pair_fmt(w_split):
+        raise ValueError("linear: x_split and w_split are in different pair formats")
+    if _engine == ENGINES["tc1"] and given is None:
+        fmt = FMT_TF32
+    if fmt == FMT_BF16 and not _tc_eligible(x, ldx, w, ldw, n, k, FMT_BF16) and given is None:
+        fmt = FMT_TF32
+    if _engine != ENGINES["simt"] and m > 0 and _tc_eligible(x, ldx, w, ldw, n, k, fmt):
+        opts.engine = ENGINES["bf16x3"] if fmt == FMT_BF16 else (ENGINES["tc1"] if _engine == ENGINES["tc1"] else ENGINES["tc"])
         if x_is_weight:
-            hl = _weight_split(x, ldx)
+            hl = _weight_split(x, ldx, fmt)
             opts.x_hi, opts.x_lo = hl[0].data_ptr(), hl[1].data_ptr()
             if w_split is not None:
                 opts.w_hi, opts.w_lo = w_split[0].data_ptr(), w_split[1].data_ptr()
@@ -252,7 +291,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
                 ws = torch.empty((2 * n * k,), device=x.device, dtype=torch.float32)
         else:
             # cache_w=False: w is an activation / a per-call temporary (backward GEMMs), never cache its split
-            hl = w_split if w_split is not None else (_weight_split(w, ldw) if cache_w else tf32_split(w))
+            hl = w_split if w_split is not None else (_weight_split(w, ldw, fmt) if cache_w else split_pair(w, fmt))
             opts.w_hi, opts.w_lo = hl[0].data_ptr(), hl[1].data_ptr()
             if x_split is not None:
                 opts.x_hi, opts.x_lo = x_split[0].data_ptr(), x_split[1].data_ptr()
@@ -260,6 +299,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
                 ws = torch.empty((2 * m * k,), device=x.device, dtype=torch.float32)
         if ws is not None:
             opts.workspace, opts.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    elif x_pair_only:
+        raise RuntimeError("linear: a pre-split activation can only feed the tensor-core engine")
     st = _call("vlsat_linear_fwd", xp, ldx, wp, ldw, yp, ldy, m, n, k, C.byref(epi), C.byref(opts), _stream(),
                work=(2.0 * m * n * k, 4.0 * (m * k + n * k + m * n)))
     _lib.check(st, "vlsat_linear_fwd")
@@ -411,19 +452,22 @@ def bf16_split(x: torch.Tensor):
 
 def flash_attn_bf16(q, k, vt, nk: int, n_heads: int, want_lse: bool = False):
     """Tensor-core streaming attention, BF16x3 operands. q [nq, D], k [nk, D], vt [D, >= nk] fp32 (column-slice views
-    allowed); D = n_heads * 64."""
-    nq, d = q.shape
+    allowed) or, each, the bf16 ``(hi, lo)`` pair a projection epilogue emitted; D = n_heads * 64."""
+    qh, ql = q if isinstance(q, tuple) else bf16_split(q)
+    kh, kl = k if isinstance(k, tuple) else bf16_split(k)
+    vh, vl = vt if isinstance(vt, tuple) else bf16_split(vt[:, :nk])
+    for t in (qh, kh, vh):
+        if t.dtype != torch.bfloat16:
+            raise TypeError("flash_attn_bf16: operand pairs must be bf16 pairs")
+    nq, d = qh.shape
     if d != n_heads * 64:
         raise ValueError("flash_attn_bf16 needs head size 64")
-    qh, ql = bf16_split(q)
-    kh, kl = bf16_split(k)
-    vh, vl = bf16_split(vt[:, :nk])
-    out = torch.empty((nq, d), device=q.device, dtype=torch.float32)
-    lse = torch.empty((n_heads, nq), device=q.device, dtype=torch.float32) if want_lse else None
+    out = torch.empty((nq, d), device=qh.device, dtype=torch.float32)
+    lse = torch.empty((n_heads, nq), device=qh.device, dtype=torch.float32) if want_lse else None
     ws_bytes = int(_lib.load().vlsat_flash_attn_bf16x3_workspace_bytes(nq, nk, n_heads))
-    ws = torch.empty((ws_bytes // 4,), device=q.device, dtype=torch.float32) if ws_bytes else None
-    st = _call("vlsat_flash_attn_bf16x3_fwd", qh.data_ptr(), ql.data_ptr(), qh.shape[1], kh.data_ptr(), kl.data_ptr(), kh.shape[1],
-               vh.data_ptr(), vl.data_ptr(), vh.shape[1], out.data_ptr(), d, lse.data_ptr() if want_lse else None,
+    ws = torch.empty((ws_bytes // 4,), device=qh.device, dtype=torch.float32) if ws_bytes else None
+    st = _call("vlsat_flash_attn_bf16x3_fwd", qh.data_ptr(), ql.data_ptr(), qh.stride(0), kh.data_ptr(), kl.data_ptr(), kh.stride(0),
+               vh.data_ptr(), vl.data_ptr(), vh.stride(0), out.data_ptr(), d, lse.data_ptr() if want_lse else None,
                nq, nk, n_heads, 64, ws.data_ptr() if ws is not None else None, ws_bytes, _stream(), work=(4.0 * nq * nk * d, 4.0 * (2 * nq * d + 2 * nk * d)))
     _lib.check(st, "vlsat_flash_attn_bf16x3_fwd")
     return (out, lse) if want_lse else out

@@ -91,25 +91,35 @@ typedef struct {
     const float* scale_ptr;   /* device scalar s: result *= expf(s); or NULL   */
     int act;                  /* VLSAT_ACT_*                                   */
     int bias_per_row;         /* 1: bias is [M] and added per output ROW (used to emit y^T = w x^T) */
-    float* split_hi;          /* optional: also emit the tf32 split of the result, compact [M, ld_split],   */
-    float* split_lo;          /*   so a consuming projection / attention needs no separate split pass       */
-    int64_t ld_split;         /*   (>= N, multiple of 4). y itself may then be NULL.                        */
+    void* split_hi;           /* optional: also emit the (hi, lo) split of the result, compact [M, ld_split], */
+    void* split_lo;           /*   so a consuming projection / attention needs no separate split pass         */
+    int64_t ld_split;         /*   elements; >= N; multiple of 4 (tf32 pairs) / 8 (bf16 pairs). y may be NULL */
+    int split_fmt;            /* VLSAT_SPLIT_TF32: float pairs (vlsat_tf32_split); VLSAT_SPLIT_BF16: bf16 pairs */
 } vlsat_epilogue;
 
-/* Engine selection. AUTO = tcgen05 3xTF32 (fp32-accurate split, see csrc/gemm_tc.cu) whenever the operands
- * are TMA-addressable (K % 4 == 0, K >= 32, 16-byte aligned rows), else the exact-fp32 FFMA engine.
- * TC forced on an ineligible shape returns VLSAT_ERR_UNSUPPORTED. TC_1PASS = plain TF32 (10-bit mantissa). */
+/* Operand formats of the tensor-core engines. An fp32 value x travels as the pair (hi, lo):
+ *   TF32 pair: hi = x rounded to tf32 (stored as float), lo = x - hi            -> 3 kind::tf32 MMAs, ~2^-22
+ *   BF16 pair: hi = bf16(x), lo = bf16(x - hi)  (same 4 bytes per element)     -> 3 kind::f16 MMAs at twice the
+ *              tensor rate, |x - hi - lo| <= 2^-17 |x|, fp32 range kept (unlike fp16)                          */
+#define VLSAT_SPLIT_TF32 0
+#define VLSAT_SPLIT_BF16 1
+
+/* Engine selection. AUTO = tcgen05 BF16x3 whenever the operands are TMA-addressable as bf16 pairs (K % 8 == 0,
+ * K >= 32), else tcgen05 3xTF32 (K % 4 == 0, 16-byte aligned rows), else the exact-fp32 FFMA engine (see
+ * csrc/gemm_tc.cu). A forced tensor-core engine on an ineligible shape returns VLSAT_ERR_UNSUPPORTED.
+ * TC = 3xTF32 (operands are TF32 pairs), TC_BF16X3 (operands are BF16 pairs), TC_1PASS = plain TF32. */
 #define VLSAT_ENGINE_AUTO 0
 #define VLSAT_ENGINE_SIMT 1
 #define VLSAT_ENGINE_TC 2
 #define VLSAT_ENGINE_TC_1PASS 3
+#define VLSAT_ENGINE_TC_BF16X3 4
 
 typedef struct {
     int engine;               /* VLSAT_ENGINE_*                                                        */
-    const float* x_hi;        /* optional pre-split activations, compact [M, K] (vlsat_tf32_split)     */
-    const float* x_lo;
-    const float* w_hi;        /* optional pre-split weights, compact [N, K] (cache them per parameter)  */
-    const float* w_lo;
+    const void* x_hi;         /* optional pre-split activations, compact [M, K], in the engine's pair format */
+    const void* x_lo;         /*   (vlsat_tf32_split / vlsat_bf16_split or an epilogue-emitted split); with  */
+    const void* w_hi;         /*   AUTO they are taken to be BF16 pairs when K % 8 == 0, else TF32 pairs      */
+    const void* w_lo;         /* optional pre-split weights, compact [N, K] (cache them per parameter)  */
     void* workspace;          /* device scratch for the splits that were not supplied                  */
     size_t workspace_bytes;   /* >= vlsat_linear_workspace_bytes(M, N, K, x_hi == NULL, w_hi == NULL)   */
 } vlsat_linear_opts;

@@ -52,6 +52,6 @@ def test_argument_validation_without_a_gpu(lib):
 
 def test_struct_layout_matches_header():
     from vlsat_b200._lib import Epilogue
-    # 5 pointers, int64, pointer, int64, 2 floats, pointer, 2 ints, 2 pointers, int64 = 112 bytes on LP64
-    assert ctypes.sizeof(Epilogue) == 112 and Epilogue.split_hi.offset == 88
+    # 5 pointers, int64, pointer, int64, 2 floats, pointer, 2 ints, 2 pointers, int64, int (+ pad) = 120 bytes on LP64
+    assert ctypes.sizeof(Epilogue) == 120 and Epilogue.split_hi.offset == 88 and Epilogue.split_fmt.offset == 112
     assert Epilogue.alpha.offset == 64 and Epilogue.scale_ptr.offset == 72 and Epilogue.act.offset == 80

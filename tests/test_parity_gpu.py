@@ -321,8 +321,9 @@ def test_state_dict_round_trip_from_reference_names():
 @pytest.mark.parametrize("m,n,k", [(128, 128, 32), (128, 128, 128), (640, 512, 512), (9600, 1024, 512), (300, 504, 768),
                                    (77, 160, 512), (1000, 26, 256), (50, 64, 36), (129, 136, 100)])
 def test_tensor_core_engine_is_fp32_accurate(m, n, k):
-    """tcgen05 3xTF32 engine vs the FFMA engine vs fp64: the split must keep fp32-level accuracy
-    (error measured against the natural scale |x|.|w| of each output element)."""
+    """tcgen05 BF16x3 / 3xTF32 engines vs the FFMA engine vs fp64: the split products must keep their stated accuracy
+    (error measured against the natural scale |x|.|w| of each output element): 3xTF32 is fp32-level, BF16x3 carries
+    16 mantissa bits per operand (|x - hi - lo| <= 2^-17 |x|, lo*lo dropped), two orders inside the 1e-3 parity budget."""
     g = torch.Generator().manual_seed(m * 7 + n * 3 + k)
     x, w, b = torch.randn(m, k, generator=g) * 3, torch.randn(n, k, generator=g) / k ** 0.5, torch.randn(n, generator=g)
     want = x.double() @ w.double().t() + b.double()
@@ -331,14 +332,43 @@ def test_tensor_core_engine_is_fp32_accurate(m, n, k):
     try:
         ops.set_gemm_engine("tc")
         tc = ops.linear(xd, wd, bd).cpu().double()
+        ops.set_gemm_engine("bf16x3")
+        bf = ops.linear(xd, wd, bd).cpu().double()
         ops.set_gemm_engine("simt")
         simt = ops.linear(xd, wd, bd).cpu().double()
     finally:
         ops.set_gemm_engine("auto")
     err_tc = ((tc - want).abs() / scale).max().item()
+    err_bf = ((bf - want).abs() / scale).max().item()
     err_simt = ((simt - want).abs() / scale).max().item()
     assert err_simt < 5e-7, f"FFMA engine error {err_simt:.3g}"
     assert err_tc < 3e-6, f"3xTF32 engine error {err_tc:.3g} (FFMA: {err_simt:.3g})"
+    assert err_bf < 1e-5, f"BF16x3 engine error {err_bf:.3g} (3xTF32: {err_tc:.3g}, FFMA: {err_simt:.3g})"
+    print(f"[gemm {m}x{n}x{k}] max err / (|x|.|w|): ffma {err_simt:.2e}  3xtf32 {err_tc:.2e}  bf16x3 {err_bf:.2e}")
+
+
+@pytest.mark.parametrize("fmt", ["tf32", "bf16"])
+@pytest.mark.parametrize("m,n,k", [(300, 520, 512), (128, 128, 64), (9600, 512, 1024), (77, 264, 96)])
+def test_linear_emitted_pairs_feed_the_next_projection(fmt, m, n, k):
+    """The (hi, lo) pair an epilogue emits (TMA-stored, M / N tails clipped) reconstructs y and can be the x operand of
+    the next projection without the unsplit tensor ever existing."""
+    g = torch.Generator().manual_seed(m + n + k)
+    x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k ** 0.5, torch.randn(n, generator=g)
+    w2 = torch.randn(72, n, generator=g) / n ** 0.5
+    xd, wd, bd, w2d = x.to(DEV), w.to(DEV), b.to(DEV), w2.to(DEV)
+    y, pair = ops.linear(xd, wd, bd, act=ops.ACT_RELU, emit_split=fmt)
+    none, pair2 = ops.linear(xd, wd, bd, act=ops.ACT_RELU, emit_split=fmt, want_y=False)
+    assert none is None
+    assert pair[0].dtype == (torch.bfloat16 if fmt == "bf16" else torch.float32) and tuple(pair[0].shape) == (m, n)
+    for p in (pair, pair2):
+        rec = p[0].double() + p[1].double()
+        tol = (2.0 ** -16 if fmt == "bf16" else 2.0 ** -23) * y.double().abs() + 1e-30
+        assert ((rec - y.double()).abs() <= tol).all(), f"{fmt} pair does not reconstruct y"
+    want = (y.double() @ w2d.double().t()).float()
+    got = ops.linear(pair, w2d)
+    got_x = ops.linear(y, w2d, x_split=pair2)
+    assert_close(got, want, f"projection fed by an emitted {fmt} pair", rtol=1e-3, atol=1e-4)
+    assert torch.equal(got, got_x)
 
 
 @pytest.mark.parametrize("nq,nk", [(128, 64), (1, 1), (100, 257), (2400, 2400), (130, 30), (64, 1000)])
