@@ -15,8 +15,12 @@
 // Kernel shape: one 128 x BN output tile per CTA, K blocks of one 128-byte swizzle row (32 tf32 / 64 bf16).
 //   warp 0      : TMA producer (4 operand tiles per stage: A_hi, A_lo, B_hi, B_lo) on an mbarrier ring
 //   warp 1      : TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit releases the stage
-//   warps 2..5  : epilogue - tcgen05.ld the accumulator (one TMEM lane = one output row per thread),
-//                 fused bias / row-gather / activation / residual / scale, vectorised global stores
+//   warps 2..9  : epilogue, two warpgroups - tcgen05.ld the accumulator (one TMEM lane = one output row per thread,
+//                 warpgroup g takes the 32-column chunks g, g + 2, ...), fused bias (staged in smem per tile) /
+//                 row-gather / activation / residual / scale, results through swizzled smem + TMA stores.
+//                 The epilogue, not the MMA loop, paces these GEMMs (K <= 1024): its latencies (TMEM load, L2 row
+//                 gathers, store hand-off) only overlap across warps, hence eight of them; GATHER / RESID template
+//                 flags keep the prefetch registers of unused operands out of the common instantiations.
 // Tails in M, N and K are handled by TMA out-of-bounds zero fill plus masking in the epilogue.
 #include "epilogue.cuh"
 #include "tc_common.cuh"
@@ -30,7 +34,8 @@ __device__ __forceinline__ long long gtime() { unsigned long long g; asm volatil
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                 // fp32 elements per K block = 128 bytes
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;            // two epilogue warpgroups: each owns every other 32-column chunk of a tile
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_A_TILE = TC_BM * 128;    // bytes
 
 // hi = round-to-nearest tf32 (low 13 mantissa bits zero), lo = x - hi
@@ -56,7 +61,7 @@ __global__ void tf32_split_kernel(const float* __restrict__ x, int64_t ldx, int6
 // Persistent kernel: gridDim.x CTAs walk the output tiles round-robin (n fastest, so the CTAs that run
 // together share A row-tiles in L2). Two TMEM accumulators: the epilogue of tile i overlaps the main loop
 // of tile i+1.
-template <int BN, int STAGES, int PASSES, Kind KD>
+template <int BN, int STAGES, int PASSES, Kind KD, bool GATHER, bool RESID>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                  const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
@@ -67,8 +72,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
     constexpr int STG_BYTES = TC_BM * 128;                  // one staged [128 rows x 32 cols] output block
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* staging = smem + STAGES * STAGE_BYTES;         // 2 ping-pong blocks, 128B-swizzled, read by TMA stores
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * STG_BYTES);
+    uint8_t* staging = smem + STAGES * STAGE_BYTES;         // one block per epilogue warpgroup, swizzled, read by TMA stores
+    float* bias_s = reinterpret_cast<float*>(staging + 2 * STG_BYTES);      // [2 warpgroups][BN / 2] bias of the current tile
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + BN);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_full = empty_bar + STAGES;                // [2]
     uint64_t* acc_empty = acc_full + 2;                     // [2]
@@ -84,7 +90,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
         prefetch_tmap(&tm_ahi); prefetch_tmap(&tm_bhi);
         if (PASSES == 3) { prefetch_tmap(&tm_alo); prefetch_tmap(&tm_blo); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 32 * TC_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_holder, 2 * BN); tmem_relinquish(); }
@@ -155,30 +161,30 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
         }
     } else {
         const int q = warp & 3;                              // TMEM lane quarter owned by this warp
-        const int et = threadIdx.x - 64;                     // 0..127 among the epilogue threads
+        const int wg = (warp - 2) >> 2;                      // epilogue warpgroup: chunks wg, wg + 2, ...
+        const int et = (threadIdx.x - 64) & 127;             // 0..127 inside the warpgroup
         const int srow = q * 32 + lane;                      // row of the tile owned by this thread
-        int sidx = 0;                                        // staging ping-pong counter
+        uint8_t* sb = staging + wg * STG_BYTES;              // this warpgroup's staging block
+        float* bs = bias_s + wg * (BN / 2);
         const vlsat_epilogue& e = a.epi;
         if (a.tma_store && et == 0) { prefetch_tmap(&tm_y); prefetch_tmap(&tm_shi); prefetch_tmap(&tm_slo); }
+        auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory"); };
         // stage one 128x32 block (this thread's row) and let one thread hand it to the TMA store engine
         auto stage_store = [&](const CUtensorMap* tm, const float4 (&vals)[8], int col0, int row0) {
-            uint8_t* sb = staging + (sidx & 1) * STG_BYTES;
-            if (et == 0) bulk_wait_read<1>();                // the store that last read this block has drained it
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) bulk_wait_read<0>();                // the store that last read this block has drained it
+            wg_sync();
 #pragma unroll
             for (int c = 0; c < 8; ++c)
                 *reinterpret_cast<float4*>(sb + srow * 128 + ((c ^ (srow & 7)) << 4)) = vals[c];
             fence_proxy_async();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            wg_sync();
             if (et == 0) { tma_store_2d(tm, sb, col0, row0); bulk_commit(); }
-            ++sidx;
         };
-        // bf16 (hi, lo) pairs of one 128x32 block: two [128 rows x 64 B] halves of one staging block in the 64-byte
+        // bf16 (hi, lo) pairs of one 128x32 block: two [128 rows x 64 B] halves of the staging block in the 64-byte
         // swizzle (16-byte chunk c of row r lives at c ^ ((r >> 1) & 3)), one TMA store each
         auto stage_store_bf16 = [&](const uint32_t (&hp)[16], const uint32_t (&lp)[16], int col0, int row0) {
-            uint8_t* sb = staging + (sidx & 1) * STG_BYTES;
-            if (et == 0) bulk_wait_read<1>();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) bulk_wait_read<0>();
+            wg_sync();
             const int sw = (srow >> 1) & 3;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -186,18 +192,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                 *reinterpret_cast<uint4*>(sb + STG_BYTES / 2 + srow * 64 + ((c ^ sw) << 4)) = make_uint4(lp[4 * c], lp[4 * c + 1], lp[4 * c + 2], lp[4 * c + 3]);
             }
             fence_proxy_async();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            wg_sync();
             if (et == 0) { tma_store_2d(&tm_shi, sb, col0, row0); tma_store_2d(&tm_slo, sb + STG_BYTES / 2, col0, row0); bulk_commit(); }
-            ++sidx;
         };
         auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
         const bool split_bf16 = e.split_fmt == VLSAT_SPLIT_BF16;
+        const bool has_ga = GATHER && e.gather_a, has_gb = GATHER && e.gather_b, has_res = RESID && e.residual;
         // fully vectorised epilogue when every operand row is 16-byte addressable
         const bool vec_ok = a.tma_store && (BN % 4 == 0) &&
                             (!e.split_hi || (e.ld_split % (split_bf16 ? 8 : 4) == 0 && al16(e.split_hi) && al16(e.split_lo))) &&
-                            (!e.bias || e.bias_per_row || al16(e.bias)) &&
                             (!(e.gather_a || e.gather_b) || (e.ld_gather % 4 == 0 && al16(e.gather_a) && al16(e.gather_b))) &&
                             (!e.residual || (e.ld_res % 4 == 0 && al16(e.residual)));
+        const bool col_bias = e.bias && !e.bias_per_row;
         const float post_scale = e.scale_ptr ? expf(__ldg(e.scale_ptr)) : 1.f;
         int i = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
@@ -208,51 +214,64 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
             const int64_t ia_own = (own_ok && e.gather_a) ? e.idx_a[m_own] : 0;
             const int64_t ib_own = (own_ok && e.gather_b) ? e.idx_b[m_own] : 0;
             const float row_bias = (own_ok && e.bias && e.bias_per_row) ? __ldg(e.bias + m_own) : 0.f;
-            // row-gather / residual operands of the NEXT 32-column chunk are always in flight while the current one
-            // is processed (and chunk 0's while the main loop of this tile still runs)
-            float4 ga_n[8], gb_n[8], rs_n[8];
+            // this warpgroup's bias columns of the tile -> smem while the main loop still runs (et < BN / 2:
+            // chunk (et / 32) * 2 + wg, column et % 32). The previous tile's readers are past their last store barrier.
+            if (et < BN / 2) {
+                const int64_t col = (int64_t)n0 + ((et >> 5) * 2 + wg) * 32 + (et & 31);
+                bs[et] = (col_bias && col < a.N) ? __ldg(e.bias + col) : 0.f;
+            }
+            wg_sync();
+            // row-gather / residual operands of this warpgroup's NEXT chunk are always in flight while the current one
+            // is processed (and its first chunk's while the main loop of this tile still runs)
+            float4 ga_n[GATHER ? 8 : 1], gb_n[GATHER ? 8 : 1], rs_n[RESID ? 8 : 1];
             auto issue_row_loads = [&](int64_t nbn) {
                 const bool go = vec_ok && own_ok && nbn + 32 <= a.N;
+                if constexpr (GATHER) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    ga_n[j] = (go && e.gather_a) ? __ldg(reinterpret_cast<const float4*>(e.gather_a + ia_own * e.ld_gather + nbn) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    gb_n[j] = (go && e.gather_b) ? __ldg(reinterpret_cast<const float4*>(e.gather_b + ib_own * e.ld_gather + nbn) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    rs_n[j] = (go && e.residual) ? __ldg(reinterpret_cast<const float4*>(e.residual + m_own * e.ld_res + nbn) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j = 0; j < 8; ++j) {
+                        ga_n[j] = (go && has_ga) ? __ldg(reinterpret_cast<const float4*>(e.gather_a + ia_own * e.ld_gather + nbn) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        gb_n[j] = (go && has_gb) ? __ldg(reinterpret_cast<const float4*>(e.gather_b + ib_own * e.ld_gather + nbn) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                if constexpr (RESID) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        rs_n[j] = (go && has_res) ? __ldg(reinterpret_cast<const float4*>(e.residual + m_own * e.ld_res + nbn) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
-            issue_row_loads(n0);
+            issue_row_loads((int64_t)n0 + wg * 32);
             mbar_wait(&acc_full[buf], (i >> 1) & 1);
             tc_fence_after();
             if (a.trace && blockIdx.x == 0 && threadIdx.x == 64 && i < 8) a.trace[i * 4 + 2] = gtime();
             const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = wg * 32; c0 < BN; c0 += 64) {
                 const int64_t nb = (int64_t)n0 + c0;
-                if (nb >= a.N) break;                        // warp-uniform
+                if (nb >= a.N) break;                        // warpgroup-uniform
                 uint32_t r[32];
                 tmem_ld_32x32(tacc + (uint32_t)c0, r);
-                float4 ga4[8], gb4[8], rs4[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { ga4[j] = ga_n[j]; gb4[j] = gb_n[j]; rs4[j] = rs_n[j]; }
-                if (c0 + 32 < BN) issue_row_loads(nb + 32);
                 tmem_ld_wait();
                 if (vec_ok && nb + 32 <= a.N) {
                     // One output row per thread (its TMEM lane), 32 consecutive columns. All global loads of the
                     // chunk are issued before any is consumed so their L2 latencies overlap; results leave through
-                    // 128B-swizzled staging blocks + TMA stores (whole 128-byte lines, tails clipped by the TMA unit).
+                    // swizzled staging blocks + TMA stores (whole 128-byte lines, tails clipped by the TMA unit).
                     float4 v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         v[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
                     if (own_ok) {
-                        float4 b4[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            b4[j] = (e.bias && !e.bias_per_row) ? __ldg(reinterpret_cast<const float4*>(e.bias + nb + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4* b4 = reinterpret_cast<const float4*>(bs + (c0 >> 6) * 32);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            v[j].x += b4[j].x + row_bias + ga4[j].x + gb4[j].x; v[j].y += b4[j].y + row_bias + ga4[j].y + gb4[j].y;
-                            v[j].z += b4[j].z + row_bias + ga4[j].z + gb4[j].z; v[j].w += b4[j].w + row_bias + ga4[j].w + gb4[j].w;
+                            const float4 bj = b4[j];
+                            v[j].x += bj.x + row_bias; v[j].y += bj.y + row_bias; v[j].z += bj.z + row_bias; v[j].w += bj.w + row_bias;
+                        }
+                        if constexpr (GATHER) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                v[j].x += ga_n[j].x + gb_n[j].x; v[j].y += ga_n[j].y + gb_n[j].y;
+                                v[j].z += ga_n[j].z + gb_n[j].z; v[j].w += ga_n[j].w + gb_n[j].w;
+                            }
                         }
                         if (e.act == VLSAT_ACT_RELU) {
 #pragma unroll
@@ -261,11 +280,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
 #pragma unroll
                             for (int j = 0; j < 8; ++j) { v[j].x = apply_act(v[j].x, e.act); v[j].y = apply_act(v[j].y, e.act); v[j].z = apply_act(v[j].z, e.act); v[j].w = apply_act(v[j].w, e.act); }
                         }
-                        if (e.residual) {
+                        if (RESID && has_res) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                v[j].x = e.alpha * v[j].x + e.beta * rs4[j].x; v[j].y = e.alpha * v[j].y + e.beta * rs4[j].y;
-                                v[j].z = e.alpha * v[j].z + e.beta * rs4[j].z; v[j].w = e.alpha * v[j].w + e.beta * rs4[j].w;
+                                v[j].x = e.alpha * v[j].x + e.beta * rs_n[j].x; v[j].y = e.alpha * v[j].y + e.beta * rs_n[j].y;
+                                v[j].z = e.alpha * v[j].z + e.beta * rs_n[j].z; v[j].w = e.alpha * v[j].w + e.beta * rs_n[j].w;
                             }
                         } else if (e.alpha != 1.f) {
 #pragma unroll
@@ -276,6 +295,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                             for (int j = 0; j < 8; ++j) { v[j].x *= post_scale; v[j].y *= post_scale; v[j].z *= post_scale; v[j].w *= post_scale; }
                         }
                     }
+                    // the prefetched row operands are consumed: refill them for this warpgroup's next chunk, in flight
+                    // during the store hand-off below and the next TMEM load
+                    if ((GATHER || RESID) && c0 + 64 < BN) issue_row_loads(nb + 64);
                     if (a.y) stage_store(&tm_y, v, (int)nb, m0);
                     if (e.split_hi && split_bf16) {
                         uint32_t hp[16], lp[16];
@@ -307,7 +329,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
             }
             tc_fence_before();
             if (a.trace && blockIdx.x == 0 && threadIdx.x == 64 && i < 8) a.trace[i * 4 + 3] = gtime();
-            mbar_arrive(&acc_empty[buf]);                    // 128 arrivals free the accumulator
+            mbar_arrive(&acc_empty[buf]);                    // every epilogue thread's arrival frees the accumulator
         }
         if (et == 0) bulk_wait_all();                        // every TMA store has landed before the CTA retires
     }
@@ -339,13 +361,13 @@ int tf32_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* h
     return finish_launch();
 }
 
-template <int BN, int STAGES, int PASSES, Kind KD>
+template <int BN, int STAGES, int PASSES, Kind KD, bool GATHER, bool RESID>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tal, const CUtensorMap& tb, const CUtensorMap& tbl,
                      const CUtensorMap& ty, const CUtensorMap& tsh, const CUtensorMap& tsl,
                      const LinearArgs& a, cudaStream_t st) {
     constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TC_A_TILE + BN * 128);
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + 2 * TC_BM * 128 /*store staging*/ + 1024 /*align*/ + 256 /*barriers*/;
-    auto kern = linear_tc_kernel<BN, STAGES, PASSES, KD>;
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 2 * TC_BM * 128 /*store staging*/ + BN * 4 /*bias*/ + 1024 /*align*/ + 256 /*barriers*/;
+    auto kern = linear_tc_kernel<BN, STAGES, PASSES, KD, GATHER, RESID>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t n_tiles = ceil_div(a.N, BN) * ceil_div(a.M, TC_BM);
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, kNumSMs);
@@ -392,10 +414,19 @@ int linear_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
                       make_tmap_2d(&tsl, e.split_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_split, 32, TC_BM);
     }
     a.tma_store = tma_out ? 1 : 0;
-    if (kind == 1)
-        return bn == 64 ? launch_tc<64, 4, 3, Kind::BF16>(ta, tal, tb, tbl, ty, tsh, tsl, a, st) : launch_tc<128, 3, 3, Kind::BF16>(ta, tal, tb, tbl, ty, tsh, tsl, a, st);
-    if (passes == 3) return bn == 64 ? launch_tc<64, 4, 3, Kind::TF32>(ta, tal, tb, tbl, ty, tsh, tsl, a, st) : launch_tc<128, 3, 3, Kind::TF32>(ta, tal, tb, tbl, ty, tsh, tsl, a, st);
-    return bn == 64 ? launch_tc<64, 6, 1, Kind::TF32>(ta, tal, tb, tbl, ty, tsh, tsl, a, st) : launch_tc<128, 6, 1, Kind::TF32>(ta, tal, tb, tbl, ty, tsh, tsl, a, st);
+    const bool g = e.gather_a || e.gather_b, r = e.residual != nullptr;
+#define VLSAT_TC_LAUNCH(BN_, ST_, PS_, KD_, G_, R_) launch_tc<BN_, ST_, PS_, KD_, G_, R_>(ta, tal, tb, tbl, ty, tsh, tsl, a, st)
+    if (kind == 1) {
+        // BF16x3: the engine of the hot path gets epilogue instantiations without the unused prefetch registers
+        if (bn == 64) return VLSAT_TC_LAUNCH(64, 4, 3, Kind::BF16, true, true);
+        if (!g && !r) return VLSAT_TC_LAUNCH(128, 3, 3, Kind::BF16, false, false);
+        if (g && !r) return VLSAT_TC_LAUNCH(128, 3, 3, Kind::BF16, true, false);
+        if (!g && r) return VLSAT_TC_LAUNCH(128, 3, 3, Kind::BF16, false, true);
+        return VLSAT_TC_LAUNCH(128, 3, 3, Kind::BF16, true, true);
+    }
+    if (passes == 3) return bn == 64 ? VLSAT_TC_LAUNCH(64, 4, 3, Kind::TF32, true, true) : VLSAT_TC_LAUNCH(128, 3, 3, Kind::TF32, true, true);
+    return bn == 64 ? VLSAT_TC_LAUNCH(64, 6, 1, Kind::TF32, true, true) : VLSAT_TC_LAUNCH(128, 6, 1, Kind::TF32, true, true);
+#undef VLSAT_TC_LAUNCH
 }
 
 }  // namespace vlsat
