@@ -54,10 +54,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
-// (hi, lo) bf16 pairs of two values: hi = bf16(v), lo = bf16(v - hi)
+// (hi, lo) bf16 pairs of two values: hi = bf16(v), lo = bf16(v - hi), packed {low half = a, high half = b}.
+// Done with full-rate integer ops instead of cvt.rn.bf16x2: the conversion instruction issues on the XU pipe (16 lanes
+// per clock, shared with ex2 / rcp) and a 128 x 128 tile needs 2 x 8192 of them - measured as the busiest pipe of the
+// epilogues that emit pairs. Rounding is half-up on the magnitude (add half an ulp of the 8-bit mantissa, keep the upper
+// 16 bits); lo = v - hi is exact in fp32 and absorbs the difference to round-to-nearest-even.
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    hi = pack_bf16x2(a, b);
-    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    const uint32_t ha = (__float_as_uint(a) + 0x8000u) & 0xffff0000u, hb = (__float_as_uint(b) + 0x8000u) & 0xffff0000u;
+    const uint32_t la = __float_as_uint(a - __uint_as_float(ha)) + 0x8000u, lb = __float_as_uint(b - __uint_as_float(hb)) + 0x8000u;
+    hi = __byte_perm(ha, hb, 0x7632);      // {hb.hi16, ha.hi16}: lower address = first value
+    lo = __byte_perm(la, lb, 0x7632);
 }
 
 // scalar store of one result's split in the format the epilogue asks for

@@ -74,7 +74,7 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
                        float* __restrict__ out, int64_t ldo, float* __restrict__ lse, FlashPartial part,
                        int nq, int nk, int n_heads, int tiles_per_split, float scale_log2e) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps LDS/STS
     uint8_t* q_smem = smem;                                  // [g][Q_hi | Q_lo], g = 0, 1
     uint8_t* k_smem = q_smem + 2 * FB_Q_BYTES;               // 2 stages x (K_hi | K_lo)
     uint8_t* v_smem = k_smem + 2 * FB_K_STAGE;               // 2 stages x (Vt_hi | Vt_lo)

@@ -61,7 +61,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_co
                      const __grid_constant__ CUtensorMap tm_vhi, const __grid_constant__ CUtensorMap tm_vlo,
                      float* __restrict__ out, int64_t ldo, float* __restrict__ lse, int nq, int nk, float scale_log2e) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps LDS/STS
     uint8_t* q_smem = smem;                                  // [Q_hi h0 | Q_hi h1 | Q_lo h0 | Q_lo h1] x 16 KB
     uint8_t* k_smem = smem + FT_Q_BYTES;                     // stages x FT_K_STAGE
     uint8_t* v_smem = k_smem + FT_STAGES * FT_K_STAGE;       // stages x FT_V_STAGE

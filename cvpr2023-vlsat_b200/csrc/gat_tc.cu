@@ -1,43 +1,62 @@
-// A8 on the tensor cores: the fused graph-attention edge kernel (max aggregation, use_edge=True).
+// A8 on the tensor cores: the fused graph-attention edge kernel (max aggregation, use_edge=True), BF16x3.
 //
 // Rows are (edge, head) pairs in source-sorted (CSR) edge order: row = e * H + h. With the head-major
 // operand layouts prepared by the host (proj_edge / proj_value / the C1q.proj_query fold with permuted weight
 // rows) every per-row operand is a contiguous segment:
-//   K'  [E*H, d_e]   : proj_edge(e) de-interleaved, tf32 hi/lo split          (TMA, 2-D, K-major)
-//   QC  [N*H, hid]   : C1[:, :d_n] . q3[n, :, h] + c1_bias  per (node, head)    (gathered by src)
+//   K'  [E*H, 64]    : proj_edge(e) de-interleaved, bf16 (hi, lo) pair = 4 B / element, exactly the algorithmic
+//                      edge bytes; emitted by the producing GEMM epilogue                     (TMA, 128-byte rows)
+//   QC  [N*H, hid]   : C1[:, :d_n] . q3[n, :, h] + c1_bias  per (node, head)    (gathered by src; CSR order makes
+//                      the 16 edges of a tile share 1-2 sources, so these rows are L1 hits)
 //   V'  [N*H, d_o]   : proj_value(x) de-interleaved                             (gathered by dst)
-// Per 128-row tile (= 128/H edges), persistent CTAs:
-//   MMA1 (SS, 3xTF32)   acc1[128, hid]  = K' C1k^T                      C1k = C1[:, d_n:]  resident in smem
-//   epilogue 1          hidden = relu(acc1 + QC[src, h]) -> tf32 hi/lo -> TMEM (A operand of MMA2)
-//   MMA2 (TS, 3xTF32)   acc2[128, d_o] = hidden C2^T                    C2 resident in smem
-//   epilogue 2          p = softmax_c(acc2 + c2_bias); m = p * V'[dst, h]; segmented max over the edges of a
-//                       source inside the tile, then one atomicMax (order-preserving int encoding) per
-//                       (segment, feature) into xx_enc[N, H*d_o].
-// A finalize kernel decodes xx_enc (untouched rows -> 0, "empty max = 0" semantics of the reference),
-// and writes xx back in the reference's interleaved feature order c*H + h.
-// HBM traffic = the algorithmic minimum: K' once (hi+lo), QC/V' rows (L2-resident re-reads), xx once.
+// Per 128-row tile (= 128/H edges), persistent CTAs, every product as lo*hi + hi*lo + hi*hi (kind::f16, bf16):
+//   MMA1 (SS)    acc1[128, hid]  = K' C1k^T                      C1k = C1[:, d_n:]  resident in smem
+//   epilogue 1   hidden = relu(acc1 + QC[src, h]) -> bf16 pair written IN PLACE over the accumulator columns
+//                (32 fp32 columns -> 16 packed hi words + 16 packed lo words): the A operand of MMA2 in TMEM
+//   MMA2 (TS)    acc2[128, d_o] = hidden C2^T                    C2 resident in smem
+//   epilogue 2   p = softmax_c(acc2 + c2_bias); m = p * V'[dst, h]; segmented max over the edges of a
+//                source inside the tile, then one atomicMax (order-preserving int encoding) per
+//                (segment, feature) into xx_enc[N, H*d_o].
+// Pipelining: GT_WG epilogue warpgroups, each with its own TMEM buffer (acc1/hidden + acc2) and message buffer,
+// take tiles round-robin and run both epilogues of their tile; the MMA warp issues MMA1 of the next tiles while
+// they work, so a tile's latency chain (TMA -> MMA1 -> epi1 -> MMA2 -> epi2) overlaps with GT_WG - 1 others.
+// A finalize kernel decodes xx_enc (untouched rows -> 0, "empty max = 0" semantics of the reference), restores the
+// INT_MIN fill of the workspace (a caller that keeps it passes workspace_ready = 1 and saves the fill) and writes xx back in the reference's interleaved feature order c*H + h.
+// HBM traffic = the algorithmic minimum: K' once, QC/V' rows (cache-resident re-reads), xx once.
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "tc_common.cuh"
 #include <float.h>
 #include <limits.h>
+#include <stdlib.h>
 
 namespace vlsat {
 
 using namespace tc;
 
-constexpr int GT_THREADS = 192;
+constexpr int GT_WG = 2;                      // epilogue warpgroups = tiles in flight per CTA
+constexpr int GT_THREADS = 64 + 128 * GT_WG;
 constexpr int GT_ROWS = 128;
+constexpr int GT_DE = 64;                     // proj_edge channels per head: one 128-byte bf16 row
+constexpr int GT_STAGES = 3;                  // K' tile ring
+constexpr int GT_K_TILE = 2 * GT_ROWS * 128;  // K'_hi | K'_lo
+constexpr int GT_QN = 4;                      // QC rows of up to this many consecutive source nodes are staged in smem per tile
 
 struct GatTcParams {
     const float* qc; int64_t ld_qc;      // QC row of (node n, head h) = qc + n * ld_qc + h * hid
     const float* v; int64_t ld_v;        // V' row                      = v  + n * ld_v  + h * d_o
     const int64_t* src; const int64_t* dst;   // CSR-sorted edge endpoints [E]
     const float* c2_bias;
-    int* xx_enc;                         // [N, H * d_o] order-preserving int encoding, pre-set to INT_MIN
+    int* xx_enc;                         // [N, H * d_o] order-preserving int encoding, holds INT_MIN on entry
     float* prob;                         // optional [E, d_o, H]
     int64_t n_edges;
-    int H, d_e, hid, d_o;
+    int H, hid, d_o;
+    int dbg;                             // debug experiments (VLSAT_GAT_DBG): 1 no atomics, 2 no QC loads, 4 no smem staging of QC rows
+    long long* trace;                    // debug: globaltimer stamps of CTA 0 / warpgroup 0 (6 per tile), nullptr in normal use
 };
+
+extern long long* g_trace;               // csrc/gemm_tc.cu (vlsat_debug_set_trace)
+__device__ __forceinline__ long long gt_time() { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); return (long long)g; }
+#define GT_STAMP(k) do { if (p.trace && blockIdx.x == 0 && g == 0 && et == 0 && j < 16) p.trace[j * 12 + (k)] = gt_time(); } while (0)
 
 __device__ __forceinline__ int enc_ordered(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 
@@ -52,13 +71,14 @@ __device__ __forceinline__ void tmem_st_32(uint32_t taddr, const uint32_t (&r)[3
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
-__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] . B[smem]^T, bf16 inputs: the A operand is read from tensor memory (lane = row, each 32-bit
+// column holds two consecutive K elements)
+__device__ __forceinline__ void mma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int DO>      // d_o (channels per head of the attention output): 32 or 64
 __global__ void __launch_bounds__(GT_THREADS, 1)
@@ -67,34 +87,41 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
                    const __grid_constant__ CUtensorMap tm_c2hi, const __grid_constant__ CUtensorMap tm_c2lo,
                    const GatTcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int kh = p.d_e / 32;                         // 128-byte column blocks of K' / C1k
-    const int hc = p.hid / 32;                         // 128-byte column blocks of C2
-    const uint32_t c1_box = (uint32_t)p.hid * 128, c2_box = (uint32_t)p.d_o * 128, k_box = GT_ROWS * 128;
-    uint8_t* c1hi_s = smem;
-    uint8_t* c1lo_s = c1hi_s + kh * c1_box;
-    uint8_t* c2hi_s = c1lo_s + kh * c1_box;
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps LDS/STS
+    const int hc = (p.hid + 63) / 64;                        // 128-byte (64 bf16) column blocks of C2
+    const uint32_t c1_box = (uint32_t)p.hid * 128, c2_box = (uint32_t)DO * 128;
+    uint8_t* c1hi_s = smem;                                  // [hid rows x 128 B]
+    uint8_t* c1lo_s = c1hi_s + c1_box;
+    uint8_t* c2hi_s = c1lo_s + c1_box;                       // hc x [DO rows x 128 B]
     uint8_t* c2lo_s = c2hi_s + hc * c2_box;
-    uint8_t* khi_s = c2lo_s + hc * c2_box;
-    uint8_t* klo_s = khi_s + kh * k_box;
-    float* msg = reinterpret_cast<float*>(klo_s + kh * k_box);           // [128][DO + 1]
-    int* s_src = reinterpret_cast<int*>(msg + GT_ROWS * (DO + 1));       // [128] source node of each edge of the tile
-    float* s_c2b = reinterpret_cast<float*>(s_src + GT_ROWS);
-    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_c2b + DO) + 7) & ~(uintptr_t)7);
-    uint64_t* w_full = bars; uint64_t* k_full = bars + 1; uint64_t* k_empty = bars + 2;
-    uint64_t* acc1_full = bars + 3; uint64_t* a2_ready = bars + 4; uint64_t* acc2_full = bars + 5;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
+    uint8_t* k_s = c2lo_s + hc * c2_box;                     // GT_STAGES x (K'_hi | K'_lo)
+    float* s_c2b = reinterpret_cast<float*>(k_s + GT_STAGES * GT_K_TILE);   // [DO] second-layer bias
+    float* tp_all = s_c2b + DO;                              // [epilogue warps][32 rows][DO + 1] run-maxima transpose
+    float* qs_all = tp_all + 4 * GT_WG * 32 * (DO + 1);      // [GT_WG][GT_QN nodes][H heads][hid + 4] staged QC rows
+    const int qs_words = GT_QN * p.H * (p.hid + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(qs_all + GT_WG * qs_words) + 7) & ~(uintptr_t)7);
+    uint64_t* w_full = bars;
+    uint64_t* k_full = bars + 1;                             // [GT_STAGES]
+    uint64_t* k_empty = k_full + GT_STAGES;                  // [GT_STAGES]
+    uint64_t* acc1_full = k_empty + GT_STAGES;               // [GT_WG]
+    uint64_t* hid_ready = acc1_full + GT_WG;                 // [GT_WG]
+    uint64_t* acc2_full = hid_ready + GT_WG;                 // [GT_WG]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc2_full + GT_WG);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t total_rows = p.n_edges * p.H;
+    const int64_t total_rows = p.n_edges * p.H;          // < 2^31 (checked by the launcher)
     const int n_tiles = (int)((total_rows + GT_ROWS - 1) / GT_ROWS);
     const int ept = GT_ROWS / p.H;                     // edges per tile
+    int n_local = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) ++n_local;
+    const uint32_t buf_cols = (uint32_t)p.hid + DO;    // TMEM columns of one buffer: acc1 / hidden pair, then acc2
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_khi); prefetch_tmap(&tm_klo); prefetch_tmap(&tm_c1hi);
         prefetch_tmap(&tm_c1lo); prefetch_tmap(&tm_c2hi); prefetch_tmap(&tm_c2lo);
-        mbar_init(w_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1);
-        mbar_init(acc1_full, 1); mbar_init(a2_ready, 128); mbar_init(acc2_full, 1);
+        mbar_init(w_full, 1);
+        for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+        for (int g = 0; g < GT_WG; ++g) { mbar_init(&acc1_full[g], 1); mbar_init(&hid_ready[g], 128); mbar_init(&acc2_full[g], 1); }
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_holder, 512); tmem_relinquish(); }
@@ -102,175 +129,270 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const uint32_t t_acc1 = tmem_base, t_a2hi = tmem_base + p.hid, t_a2lo = tmem_base + 2 * p.hid, t_acc2 = tmem_base + 3 * p.hid;
 
     if (warp == 0) {
         if (elect_one()) {
-            mbar_arrive_expect_tx(w_full, 2 * kh * c1_box + 2 * hc * c2_box);
-            for (int b = 0; b < kh; ++b) {
-                tma_load_2d(c1hi_s + b * c1_box, &tm_c1hi, w_full, b * 32, 0);
-                tma_load_2d(c1lo_s + b * c1_box, &tm_c1lo, w_full, b * 32, 0);
-            }
+            mbar_arrive_expect_tx(w_full, 2 * c1_box + 2 * hc * c2_box);
+            tma_load_2d(c1hi_s, &tm_c1hi, w_full, 0, 0);
+            tma_load_2d(c1lo_s, &tm_c1lo, w_full, 0, 0);
             for (int b = 0; b < hc; ++b) {
-                tma_load_2d(c2hi_s + b * c2_box, &tm_c2hi, w_full, b * 32, 0);
-                tma_load_2d(c2lo_s + b * c2_box, &tm_c2lo, w_full, b * 32, 0);
+                tma_load_2d(c2hi_s + b * c2_box, &tm_c2hi, w_full, b * 64, 0);
+                tma_load_2d(c2lo_s + b * c2_box, &tm_c2lo, w_full, b * 64, 0);
             }
         }
         __syncwarp();
         int it = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            mbar_wait(k_empty, (it & 1) ^ 1);
+            const int s = it % GT_STAGES;
+            mbar_wait(&k_empty[s], ((it / GT_STAGES) & 1) ^ 1);
             if (elect_one()) {
-                mbar_arrive_expect_tx(k_full, 2 * kh * k_box);
-                for (int b = 0; b < kh; ++b) {
-                    tma_load_2d(khi_s + b * k_box, &tm_khi, k_full, b * 32, t * GT_ROWS);
-                    tma_load_2d(klo_s + b * k_box, &tm_klo, k_full, b * 32, t * GT_ROWS);
-                }
+                mbar_arrive_expect_tx(&k_full[s], GT_K_TILE);
+                tma_load_2d(k_s + s * GT_K_TILE, &tm_khi, &k_full[s], 0, t * GT_ROWS);
+                tma_load_2d(k_s + s * GT_K_TILE + GT_ROWS * 128, &tm_klo, &k_full[s], 0, t * GT_ROWS);
             }
             __syncwarp();
         }
     } else if (warp == 1) {
-        const uint32_t idesc1 = make_idesc<Kind::TF32>(GT_ROWS, p.hid), idesc2 = make_idesc<Kind::TF32>(GT_ROWS, p.d_o);
-        const uint64_t d_khi = make_sdesc_k128(smem_u32(khi_s)), d_klo = make_sdesc_k128(smem_u32(klo_s));
+        const uint32_t idesc1 = make_idesc<Kind::BF16>(GT_ROWS, p.hid), idesc2 = make_idesc<Kind::BF16>(GT_ROWS, DO);
+        const uint64_t d_k0 = make_sdesc_k128(smem_u32(k_s));
         const uint64_t d_c1hi = make_sdesc_k128(smem_u32(c1hi_s)), d_c1lo = make_sdesc_k128(smem_u32(c1lo_s));
         const uint64_t d_c2hi = make_sdesc_k128(smem_u32(c2hi_s)), d_c2lo = make_sdesc_k128(smem_u32(c2lo_s));
-        const int ks1 = p.d_e / 8, ks2 = p.hid / 8;
+        const int ks2 = p.hid / 16;
         auto issue_mma1 = [&](int it) {
-            mbar_wait(k_full, it & 1);
+            const int s = it % GT_STAGES, b = it % GT_WG;
+            mbar_wait(&k_full[s], (it / GT_STAGES) & 1);
             tc_fence_after();
             if (elect_one()) {
-                for (int kk = 0; kk < ks1; ++kk) {
-                    const uint32_t oa = (kk >> 2) * (k_box >> 4) + (kk & 3) * 2, ob = (kk >> 2) * (c1_box >> 4) + (kk & 3) * 2;
-                    mma_ss<Kind::TF32>(t_acc1, d_klo + oa, d_c1hi + ob, idesc1, kk > 0);
-                    mma_ss<Kind::TF32>(t_acc1, d_khi + oa, d_c1lo + ob, idesc1, 1);
-                    mma_ss<Kind::TF32>(t_acc1, d_khi + oa, d_c1hi + ob, idesc1, 1);
+                const uint64_t d_khi = d_k0 + (uint64_t)(s * (GT_K_TILE >> 4)), d_klo = d_khi + ((GT_ROWS * 128) >> 4);
+                const uint32_t t_acc1 = tmem_base + b * buf_cols;
+#pragma unroll
+                for (int kk = 0; kk < GT_DE / 16; ++kk) {       // 16 channels (32 bytes) per MMA
+                    mma_ss<Kind::BF16>(t_acc1, d_klo + 2 * kk, d_c1hi + 2 * kk, idesc1, kk > 0);
+                    mma_ss<Kind::BF16>(t_acc1, d_khi + 2 * kk, d_c1lo + 2 * kk, idesc1, 1);
+                    mma_ss<Kind::BF16>(t_acc1, d_khi + 2 * kk, d_c1hi + 2 * kk, idesc1, 1);
                 }
-                tc_commit(k_empty);
-                tc_commit(acc1_full);
+                tc_commit(&k_empty[s]);
+                tc_commit(&acc1_full[b]);
             }
             __syncwarp();
         };
         mbar_wait(w_full, 0);
-        int n_local = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) ++n_local;
-        if (n_local > 0) issue_mma1(0);
+        for (int it = 0; it < GT_WG && it < n_local; ++it) issue_mma1(it);
         for (int it = 0; it < n_local; ++it) {
-            mbar_wait(a2_ready, it & 1);                 // hidden (hi, lo) is in TMEM; acc1 has been drained
+            const int b = it % GT_WG;
+            mbar_wait(&hid_ready[b], (it / GT_WG) & 1);        // hidden (hi, lo) is in TMEM; acc1 / acc2 of this buffer are drained
             tc_fence_after();
             if (elect_one()) {
-                for (int kk = 0; kk < ks2; ++kk) {
+                const uint32_t t_hid = tmem_base + b * buf_cols, t_acc2 = t_hid + p.hid;
+                for (int kk = 0; kk < ks2; ++kk) {              // 16 hidden units per MMA = 8 packed columns
+                    const uint32_t a_hi = t_hid + 32 * (kk >> 1) + 8 * (kk & 1), a_lo = a_hi + 16;
                     const uint32_t ob = (kk >> 2) * (c2_box >> 4) + (kk & 3) * 2;
-                    mma_ts(t_acc2, t_a2lo + kk * 8, d_c2hi + ob, idesc2, kk > 0);
-                    mma_ts(t_acc2, t_a2hi + kk * 8, d_c2lo + ob, idesc2, 1);
-                    mma_ts(t_acc2, t_a2hi + kk * 8, d_c2hi + ob, idesc2, 1);
+                    mma_ts_bf16(t_acc2, a_lo, d_c2hi + ob, idesc2, kk > 0);
+                    mma_ts_bf16(t_acc2, a_hi, d_c2lo + ob, idesc2, 1);
+                    mma_ts_bf16(t_acc2, a_hi, d_c2hi + ob, idesc2, 1);
                 }
-                tc_commit(acc2_full);
+                tc_commit(&acc2_full[b]);
             }
             __syncwarp();
-            if (it + 1 < n_local) issue_mma1(it + 1);    // overlaps epilogue 2 of this tile
+            if (it + GT_WG < n_local) issue_mma1(it + GT_WG);  // ordered behind MMA2(it): may overwrite its hidden operand
         }
     } else {
+        const int g = (warp - 2) >> 2;                       // epilogue warpgroup = TMEM buffer
         const int qd = warp & 3;
-        const int r = qd * 32 + lane;                    // row of the tile = TMEM lane
-        const int et = threadIdx.x - 64;                 // 0..127 among the epilogue threads
+        const int r = qd * 32 + lane;                        // row of the tile = TMEM lane
+        const int et = (threadIdx.x - 64) & 127;             // 0..127 inside the warpgroup
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const uint32_t t_acc1 = tmem_base + g * buf_cols + lane_off, t_acc2 = t_acc1 + p.hid;
         const int D_a = p.H * DO;
-        constexpr int MS = DO + 1;
-        for (int i = et; i < DO; i += 128) s_c2b[i] = __ldg(p.c2_bias + i);
-        int it = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            const int64_t row_g = (int64_t)t * GT_ROWS + r;
-            const bool valid = row_g < total_rows;
-            const int64_t e = valid ? row_g / p.H : 0;
-            const int h = (int)(row_g % p.H);
-            const int64_t e0 = (int64_t)t * ept;
-            if (et < ept) s_src[et] = (e0 + et < p.n_edges) ? (int)p.src[e0 + et] : -1;
-            const int64_t src = valid ? p.src[e] : 0, dst = valid ? p.dst[e] : 0;
-            // operands gathered per row: issue the loads now, they land while the tensor core runs MMA1
+        float* tps = tp_all + (warp - 2) * 32 * (DO + 1);
+        if (g == 0) for (int i = et; i < DO; i += 128) s_c2b[i] = __ldg(p.c2_bias + i);
+        asm volatile("bar.sync 15, %0;" ::"n"(128 * GT_WG) : "memory");     // c2 bias visible to every epilogue warpgroup
+        const int hshift = 31 - __clz(p.H);                  // H divides 128: a power of two
+        int j = 0;                                           // this warpgroup's tile counter
+        // row metadata of a tile: (valid, edge, head) of this thread's row and its two gathered rows
+        auto locate = [&](int it_, bool& valid_, int& e_, int& h_, int64_t& src_, int64_t& dst_) {
+            const int row_g = (blockIdx.x + it_ * (int)gridDim.x) * GT_ROWS + r;      // < 2^31 (checked by the launcher)
+            valid_ = it_ < n_local && row_g < total_rows;
+            e_ = valid_ ? row_g >> hshift : 0;
+            h_ = row_g & (p.H - 1);
+            src_ = valid_ ? p.src[e_] : 0; dst_ = valid_ ? p.dst[e_] : 0;
+        };
+        bool valid, valid_n; int e, e_n, h, h_n; int64_t src, src_n, dst, dst_n;
+        locate(g, valid, e, h, src, dst);
+        // QC staging. The edges of a tile come from a run of consecutive source nodes (CSR order; 1-3 nodes at the graph
+        // densities of the path), so instead of every (edge, head) row gathering its own 4*hid bytes - 16 rows per source
+        // asking for the same lines, measured as > 1 us of exposed load latency per tile - the warpgroup copies the QC rows
+        // of nodes [first, first + cnt) once, coalesced, one tile ahead (registers -> padded smem rows at the top of the
+        // tile), and epilogue 1 reads them with conflict-free LDS.128. Tiles spanning more than GT_QN nodes gather directly.
+        const int ppn = p.H * p.hid / 4;                     // 16-byte pieces per node row
+        const bool stage_ok = (ppn & (ppn - 1)) == 0 && !(p.dbg & 4);
+        const int lg_ppn = 31 - __clz(ppn), lg_hp = 31 - __clz(p.hid / 4);
+        float* qs_g = qs_all + g * qs_words;
+        auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+        // source ids of the first / last edge of a tile: loaded two tiles ahead, so that sizing the next block never waits
+        auto ends_of = [&](int it_, int64_t& sa_, int64_t& sb_) {
+            sa_ = 0; sb_ = GT_QN;                            // a span the staging rejects
+            if (it_ < n_local && stage_ok) {
+                const int64_t ea = (int64_t)(blockIdx.x + it_ * (int)gridDim.x) * ept, eb = min(ea + ept, p.n_edges) - 1;
+                sa_ = p.src[ea]; sb_ = p.src[eb];
+            }
+        };
+        auto block_of = [&](int64_t sa_, int64_t sb_, int64_t& first_, int& cnt_) {   // staged node range (cnt 0: gather directly)
+            first_ = sa_;
+            cnt_ = (sb_ - sa_) < GT_QN ? (int)(sb_ - sa_) + 1 : 0;
+        };
+        float4 qreg[8];                                      // this thread's pieces of the NEXT tile's block, in flight
+        auto fetch_block = [&](int64_t first_, int cnt_) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = et + 128 * k;
+                if (i < cnt_ * ppn)
+                    qreg[k] = __ldg(reinterpret_cast<const float4*>(p.qc + (first_ + (i >> lg_ppn)) * p.ld_qc) + (i & (ppn - 1)));
+            }
+        };
+        int64_t blk_first, blk_first_n, sa_n, sb_n; int blk_cnt, blk_cnt_n;
+        ends_of(g, sa_n, sb_n);
+        block_of(sa_n, sb_n, blk_first, blk_cnt);
+        fetch_block(blk_first, blk_cnt);
+        ends_of(g + GT_WG, sa_n, sb_n);
+        for (int it = g; it < n_local; it += GT_WG, ++j) {
+            GT_STAMP(0);
+            wg_sync();                                       // every reader of the previous tile's staged rows is done
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = et + 128 * k;
+                if (i < blk_cnt * ppn) {
+                    const int off = i & (ppn - 1);
+                    *reinterpret_cast<float4*>(qs_g + (((i >> lg_ppn) * p.H + (off >> lg_hp)) * (p.hid + 4)) + (off & (p.hid / 4 - 1)) * 4) = qreg[k];
+                }
+            }
+            wg_sync();
+            block_of(sa_n, sb_n, blk_first_n, blk_cnt_n);
+            fetch_block(blk_first_n, blk_cnt_n);             // lands during this tile
+            ends_of(it + 2 * GT_WG, sa_n, sb_n);
+            locate(it + GT_WG, valid_n, e_n, h_n, src_n, dst_n);     // next tile's endpoints: consumed after epilogue 1
             const float4* qrow = reinterpret_cast<const float4*>(p.qc + src * p.ld_qc + (int64_t)h * p.hid);
             const float4* vrow = reinterpret_cast<const float4*>(p.v + dst * p.ld_v + (int64_t)h * DO);
-            float4 vv[DO / 4], qv[8];
-#pragma unroll
-            for (int j = 0; j < DO / 4; ++j) vv[j] = valid ? __ldg(vrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) qv[j] = valid ? __ldg(qrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            // ---- epilogue 1: hidden = relu(acc1 + QC[src, h]) -> tf32 hi / lo -> TMEM
-            mbar_wait(acc1_full, it & 1);
+            const float4* qs_row = reinterpret_cast<const float4*>(qs_g + ((valid ? (int)(src - blk_first) : 0) * p.H + h) * (p.hid + 4));
+            const bool staged = blk_cnt > 0;
+            // ---- epilogue 1: hidden = relu(acc1 + QC[src, h]) -> bf16 pair, in place over the accumulator columns
+            mbar_wait(&acc1_full[g], j & 1);
             tc_fence_after();
+            GT_STAMP(1);
             for (int c0 = 0; c0 < p.hid; c0 += 32) {
-                uint32_t a[32], lo[32];
-                tmem_ld_32x32(t_acc1 + lane_off + c0, a);
-                float4 qn[8];                            // next chunk's QC values, in flight while this chunk is processed
-                const bool more = c0 + 32 < p.hid;
+                uint32_t a[32];
+                tmem_ld_32x32(t_acc1 + c0, a);
+                float4 qv[8];
+                if (staged) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) qn[j] = (valid && more) ? __ldg(qrow + (c0 + 32) / 4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                tmem_ld_wait();
+                    for (int u = 0; u < 8; ++u) qv[u] = qs_row[c0 / 4 + u];
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float hv[4] = {fmaxf(__uint_as_float(a[4 * j]) + qv[j].x, 0.f), fmaxf(__uint_as_float(a[4 * j + 1]) + qv[j].y, 0.f),
-                                         fmaxf(__uint_as_float(a[4 * j + 2]) + qv[j].z, 0.f), fmaxf(__uint_as_float(a[4 * j + 3]) + qv[j].w, 0.f)};
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint32_t hi;
-                        hi = tc::tf32_rna_bits(hv[u]);
-                        a[4 * j + u] = hi; lo[4 * j + u] = __float_as_uint(hv[u] - __uint_as_float(hi));
-                    }
+                    for (int u = 0; u < 8; ++u) qv[u] = (valid && !(p.dbg & 2)) ? __ldg(qrow + c0 / 4 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                tmem_st_32(t_a2hi + lane_off + c0, a);
-                tmem_st_32(t_a2lo + lane_off + c0, lo);
+                tmem_ld_wait();
+                if (c0 == 0) GT_STAMP(6);
+                uint32_t w[32];                              // 16 packed hi words, then 16 packed lo words
 #pragma unroll
-                for (int j = 0; j < 8; ++j) qv[j] = qn[j];
+                for (int u = 0; u < 8; ++u) {
+                    const float h0 = fmaxf(__uint_as_float(a[4 * u]) + qv[u].x, 0.f), h1 = fmaxf(__uint_as_float(a[4 * u + 1]) + qv[u].y, 0.f);
+                    const float h2 = fmaxf(__uint_as_float(a[4 * u + 2]) + qv[u].z, 0.f), h3 = fmaxf(__uint_as_float(a[4 * u + 3]) + qv[u].w, 0.f);
+                    split_bf16x2(h0, h1, w[2 * u], w[16 + 2 * u]);
+                    split_bf16x2(h2, h3, w[2 * u + 1], w[16 + 2 * u + 1]);
+                }
+                if (c0 == 0) GT_STAMP(7);
+                tmem_st_32(t_acc1 + c0, w);
             }
+            float4 vv[DO / 4];                               // value row: lands while the tensor core runs MMA2
+#pragma unroll
+            for (int u = 0; u < DO / 4; ++u) vv[u] = valid ? __ldg(vrow + u) : make_float4(0.f, 0.f, 0.f, 0.f);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(a2_ready);
+            mbar_arrive(&hid_ready[g]);
+            GT_STAMP(2);
             // ---- epilogue 2: softmax over d_o in registers, times value, segmented max
-            mbar_wait(acc2_full, it & 1);
+            mbar_wait(&acc2_full[g], j & 1);
             tc_fence_after();
+            GT_STAMP(3);
             float tl[DO];
 #pragma unroll
             for (int c0 = 0; c0 < DO; c0 += 32) {
                 uint32_t a[32];
-                tmem_ld_32x32(t_acc2 + lane_off + c0, a);
+                tmem_ld_32x32(t_acc2 + c0, a);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tl[c0 + j] = __uint_as_float(a[j]) + s_c2b[c0 + j];
+                for (int u = 0; u < 8; ++u) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_c2b + c0 + 4 * u);
+                    tl[c0 + 4 * u] = __uint_as_float(a[4 * u]) + b4.x; tl[c0 + 4 * u + 1] = __uint_as_float(a[4 * u + 1]) + b4.y;
+                    tl[c0 + 4 * u + 2] = __uint_as_float(a[4 * u + 2]) + b4.z; tl[c0 + 4 * u + 3] = __uint_as_float(a[4 * u + 3]) + b4.w;
+                }
             }
             tc_fence_before();
-            float mx = -FLT_MAX;
+            // softmax over the d_o channels of this (edge, head) row; four partial maxima / sums keep the chains short
+            // (one row per thread, two warps per scheduler: dependent-issue latency is what this epilogue pays for)
+            float mxp[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
 #pragma unroll
-            for (int c = 0; c < DO; ++c) mx = fmaxf(mx, tl[c]);
-            float sum = 0.f;
+            for (int c = 0; c < DO; ++c) mxp[c & 3] = fmaxf(mxp[c & 3], tl[c]);
+            const float neg_m = -fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])) * 1.4426950408889634f;
+            float smp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < DO; ++c) { tl[c] = __expf(tl[c] - mx); sum += tl[c]; }
-            const float inv = 1.f / sum;
+            for (int c = 0; c < DO; ++c) {
+                float ex;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(tl[c], 1.4426950408889634f, neg_m)));
+                tl[c] = ex; smp[c & 3] += ex;
+            }
+            const float inv = 1.f / ((smp[0] + smp[1]) + (smp[2] + smp[3]));
 #pragma unroll
             for (int c = 0; c < DO; ++c) tl[c] *= inv;
             if (p.prob && valid) {
 #pragma unroll
-                for (int c = 0; c < DO; ++c) p.prob[(e * DO + c) * p.H + h] = tl[c];
+                for (int c = 0; c < DO; ++c) p.prob[((int64_t)e * DO + c) * p.H + h] = tl[c];
             }
 #pragma unroll
-            for (int j = 0; j < DO / 4; ++j) {
-                msg[r * MS + 4 * j] = tl[4 * j] * vv[j].x; msg[r * MS + 4 * j + 1] = tl[4 * j + 1] * vv[j].y;
-                msg[r * MS + 4 * j + 2] = tl[4 * j + 2] * vv[j].z; msg[r * MS + 4 * j + 3] = tl[4 * j + 3] * vv[j].w;
-            }
-            epi_barrier();
-            for (int f = et; f < D_a; f += 128) {
-                const int fh = f / DO, fc = f % DO;      // DO is a power of two: shifts
-                float best = -FLT_MAX;
-                int cur = s_src[0];
-                for (int i = 0; i < ept; ++i) {
-                    const int sn = s_src[i];
-                    if (sn != cur) {
-                        if (cur >= 0) atomicMax(p.xx_enc + (int64_t)cur * D_a + f, enc_ordered(best));
-                        cur = sn; best = -FLT_MAX;
+            for (int u = 0; u < DO / 4; ++u) { tl[4 * u] *= vv[u].x; tl[4 * u + 1] *= vv[u].y; tl[4 * u + 2] *= vv[u].z; tl[4 * u + 3] *= vv[u].w; }
+            GT_STAMP(4);
+            // Max over the edges of a source, in registers: the lanes of a warp are (edge, head) pairs, edges in CSR order,
+            // so a segmented max-scan along the edge axis (lane distance H, 2H, ...) leaves the run maximum in the last
+            // edge of every run inside the warp; that lane sends one atomicMax per channel (order-preserving int encoding).
+            const int my_src = valid ? (int)src : -1;
+            if (p.H < 32) {
+                for (int d = p.H; d < 32; d <<= 1) {
+                    const int o_src = __shfl_up_sync(0xffffffffu, my_src, d);
+                    const bool take = lane >= d && o_src == my_src;
+#pragma unroll
+                    for (int c = 0; c < DO; ++c) {
+                        const float o = __shfl_up_sync(0xffffffffu, tl[c], d);
+                        tl[c] = take ? fmaxf(tl[c], o) : tl[c];
                     }
-                    if (sn >= 0) best = fmaxf(best, msg[(i * p.H + fh) * MS + fc]);
                 }
-                if (cur >= 0) atomicMax(p.xx_enc + (int64_t)cur * D_a + f, enc_ordered(best));
             }
-            epi_barrier();                               // msg / s_src are reused by the next tile
+            const int nx_src = __shfl_down_sync(0xffffffffu, my_src, p.H & 31);
+            const bool last = my_src >= 0 && (p.H >= 32 || lane + p.H >= 32 || nx_src != my_src);
+            // The run maxima leave through a per-warp smem transpose so that one atomic instruction covers 32 consecutive
+            // words of xx_enc (a lane owns the d_o channels of ONE head; sent directly, every lane would hit its own line).
+            const int hs = min(p.H, 32), hh = h & 31;                         // heads per warp row group, head inside it
+            // index of my run in the warp = closed runs among the edges before mine (head-0 lanes mark them)
+            const int run = __popc(__ballot_sync(0xffffffffu, last && hh == 0) & ((1u << (lane & ~(hs - 1))) - 1u));
+            float* tp = tps + (run * hs + hh) * (DO + 1);
+            if (last) {
+#pragma unroll
+                for (int c = 0; c < DO; ++c) tp[c] = tl[c];
+            }
+            const unsigned run_heads = __ballot_sync(0xffffffffu, last);      // one bit per (run, head) row written
+            __syncwarp();
+            for (unsigned m = run_heads; m && !(p.dbg & 1); m &= m - 1) {
+                const int owner = __ffs(m) - 1;                               // lane that owns this (run, head) row
+                const int o_src = __shfl_sync(0xffffffffu, my_src, owner);
+                const int o_h = __shfl_sync(0xffffffffu, h, owner);
+                const int o_run = __shfl_sync(0xffffffffu, run, owner);
+                const float* row = tps + (o_run * hs + (o_h & 31)) * (DO + 1);
+                int* const dst_row = p.xx_enc + (int64_t)o_src * D_a + o_h * DO;
+#pragma unroll
+                for (int c = lane; c < DO; c += 32) atomicMax(dst_row + c, enc_ordered(row[c]));
+            }
+            __syncwarp();                                                     // the transpose buffer is reused by the next tile
+            GT_STAMP(5);
+            valid = valid_n; e = e_n; h = h_n; src = src_n; dst = dst_n; blk_first = blk_first_n; blk_cnt = blk_cnt_n;
         }
     }
     tc_fence_before();
@@ -284,13 +406,15 @@ __global__ void fill_int_kernel(int* p, int64_t n, int v) {
 }
 
 // xx[n, c*H + h] = decode(xx_enc[n, h*d_o + c]); untouched (INT_MIN) -> 0
-__global__ void gat_finalize_kernel(const int* __restrict__ enc, float* __restrict__ xx, int64_t ld_xx, int64_t n_nodes, int H, int d_o) {
+// and restore the INT_MIN fill, so the same workspace can be handed to the next call with workspace_ready = 1
+__global__ void gat_finalize_kernel(int* __restrict__ enc, float* __restrict__ xx, int64_t ld_xx, int64_t n_nodes, int H, int d_o) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int D_a = H * d_o;
     if (idx >= n_nodes * D_a) return;
     const int64_t n = idx / D_a; const int f = (int)(idx % D_a);      // f = c*H + h (output order, coalesced writes)
     const int c = f / H, h = f % H;
     const int v = enc[n * D_a + h * d_o + c];
+    enc[n * D_a + h * d_o + c] = INT_MIN;
     xx[n * ld_xx + f] = (v == INT_MIN) ? 0.f : __int_as_float(v >= 0 ? v : v ^ 0x7fffffff);
 }
 
@@ -335,44 +459,49 @@ extern "C" int vlsat_permute_edges(const int64_t* edge_index, const int32_t* per
     return finish_launch();
 }
 
-extern "C" int vlsat_gat_edge_tc_fwd(const float* k_hi, const float* k_lo, const float* qc, int64_t ld_qc,
+extern "C" int vlsat_gat_edge_tc_fwd(const void* k_hi, const void* k_lo, const float* qc, int64_t ld_qc,
                                      const float* v, int64_t ld_v, const int64_t* src_sorted, const int64_t* dst_sorted,
-                                     const float* c1k_hi, const float* c1k_lo, const float* c2_hi, const float* c2_lo,
+                                     const void* c1k_hi, const void* c1k_lo, const void* c2_hi, const void* c2_lo,
                                      const float* c2_bias, int64_t n_nodes, int64_t n_edges, int n_heads, int d_e, int hid,
                                      int d_o, float* xx, int64_t ld_xx, float* prob, void* workspace, size_t workspace_bytes,
-                                     void* stream) {
+                                     int workspace_ready, void* stream) {
     VLSAT_REQUIRE(n_nodes >= 0 && n_edges >= 0 && n_heads >= 1);
     if (n_nodes == 0) return VLSAT_OK;
     VLSAT_REQUIRE(xx && ld_xx >= (int64_t)n_heads * d_o);
-    VLSAT_SUPPORT(GT_ROWS % n_heads == 0 && d_e % 32 == 0 && d_e >= 32 && d_e <= 256 && hid % 32 == 0 && hid >= 32 &&
-                  (d_o == 32 || d_o == 64) && 3 * hid + d_o <= 512 && hid <= 256);
+    VLSAT_SUPPORT(GT_ROWS % n_heads == 0 && d_e == GT_DE && hid % 32 == 0 && hid >= 32 && hid <= 128 &&
+                  (d_o == 32 || d_o == 64) && GT_WG * (hid + d_o) <= 512);
     VLSAT_SUPPORT(n_edges * n_heads < (1ll << 31) && n_nodes * n_heads * d_o < (1ll << 31));
     const int D_a = n_heads * d_o;
     const size_t need = (size_t)n_nodes * D_a * sizeof(int);
     if (!workspace || workspace_bytes < need) return VLSAT_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     int* enc = (int*)workspace;
-    int launches = 2;
-    fill_int_kernel<<<(unsigned)ceil_div(n_nodes * D_a, 256), 256, 0, st>>>(enc, n_nodes * D_a, INT_MIN);
+    int launches = 1;
+    if (!workspace_ready) {
+        fill_int_kernel<<<(unsigned)ceil_div(n_nodes * D_a, 256), 256, 0, st>>>(enc, n_nodes * D_a, INT_MIN);
+        ++launches;
+    }
     if (n_edges > 0) {
         VLSAT_REQUIRE(k_hi && k_lo && qc && v && src_sorted && dst_sorted && c1k_hi && c1k_lo && c2_hi && c2_lo && c2_bias);
         VLSAT_SUPPORT(ld_qc % 4 == 0 && ld_v % 4 == 0 && ((uintptr_t)qc % 16 == 0) && ((uintptr_t)v % 16 == 0));
+        VLSAT_SUPPORT((((uintptr_t)k_hi | (uintptr_t)k_lo | (uintptr_t)c1k_hi | (uintptr_t)c1k_lo | (uintptr_t)c2_hi | (uintptr_t)c2_lo) & 15) == 0);
         CUtensorMap tk, tkl, t1, t1l, t2, t2l;
-        const auto F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+        const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
         const uint64_t rows = (uint64_t)n_edges * n_heads;
-        bool ok = make_tmap_2d(&tk, k_hi, F32, 4, rows, d_e, d_e, 32, GT_ROWS) && make_tmap_2d(&tkl, k_lo, F32, 4, rows, d_e, d_e, 32, GT_ROWS) &&
-                  make_tmap_2d(&t1, c1k_hi, F32, 4, hid, d_e, d_e, 32, hid) && make_tmap_2d(&t1l, c1k_lo, F32, 4, hid, d_e, d_e, 32, hid) &&
-                  make_tmap_2d(&t2, c2_hi, F32, 4, d_o, hid, hid, 32, d_o) && make_tmap_2d(&t2l, c2_lo, F32, 4, d_o, hid, hid, 32, d_o);
+        bool ok = make_tmap_2d(&tk, k_hi, BF, 2, rows, d_e, d_e, 64, GT_ROWS) && make_tmap_2d(&tkl, k_lo, BF, 2, rows, d_e, d_e, 64, GT_ROWS) &&
+                  make_tmap_2d(&t1, c1k_hi, BF, 2, hid, d_e, d_e, 64, hid) && make_tmap_2d(&t1l, c1k_lo, BF, 2, hid, d_e, d_e, 64, hid) &&
+                  make_tmap_2d(&t2, c2_hi, BF, 2, d_o, hid, hid, 64, d_o) && make_tmap_2d(&t2l, c2_lo, BF, 2, d_o, hid, hid, 64, d_o);
         if (!ok) return VLSAT_ERR_UNSUPPORTED;
-        const int kh = d_e / 32, hc = hid / 32;
-        const size_t smem = (size_t)2 * kh * hid * 128 + (size_t)2 * hc * d_o * 128 + (size_t)2 * kh * GT_ROWS * 128 +
-                            (size_t)GT_ROWS * (d_o + 1) * 4 + 16 + GT_ROWS * 8 + (size_t)d_o * 4 + 128 + 1024;
+        const int hc = (hid + 63) / 64;
+        const size_t smem = (size_t)2 * hid * 128 + (size_t)2 * hc * d_o * 128 + (size_t)GT_STAGES * GT_K_TILE +
+                            (size_t)d_o * 4 + (size_t)4 * GT_WG * 32 * (d_o + 1) * 4 +
+                            (size_t)GT_WG * GT_QN * n_heads * (hid + 4) * 4 + 256 + 1024;
         VLSAT_SUPPORT(smem <= 227 * 1024);
         auto kern = d_o == 32 ? gat_edge_tc_kernel<32> : gat_edge_tc_kernel<64>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         GatTcParams p;
         p.qc = qc; p.ld_qc = ld_qc; p.v = v; p.ld_v = ld_v; p.src = src_sorted; p.dst = dst_sorted; p.c2_bias = c2_bias;
-        p.xx_enc = enc; p.prob = prob; p.n_edges = n_edges; p.H = n_heads; p.d_e = d_e; p.hid = hid; p.d_o = d_o;
+        p.xx_enc = enc; p.prob = prob; p.trace = g_trace; { const char* d = getenv("VLSAT_GAT_DBG"); p.dbg = d ? atoi(d) : 0; } p.n_edges = n_edges; p.H = n_heads; p.hid = hid; p.d_o = d_o;
         const int64_t n_tiles = ceil_div(n_edges * n_heads, GT_ROWS);
         const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, kNumSMs);
         kern<<<grid, GT_THREADS, smem, st>>>(tk, tkl, t1, t1l, t2, t2l, p);

@@ -71,7 +71,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
     constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TC_A_TILE + B_TILE);
     constexpr int STG_BYTES = TC_BM * 128;                  // one staged [128 rows x 32 cols] output block
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps LDS/STS
     uint8_t* staging = smem + STAGES * STAGE_BYTES;         // one block per epilogue warpgroup, swizzled, read by TMA stores
     float* bias_s = reinterpret_cast<float*>(staging + 2 * STG_BYTES);      // [2 warpgroups][BN / 2] bias of the current tile
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + BN);

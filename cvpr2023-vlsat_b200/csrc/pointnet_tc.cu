@@ -73,7 +73,7 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
                    const float* __restrict__ w3, const float* __restrict__ b3, int c_out,
                    float* __restrict__ out, int32_t* __restrict__ argmax) {
     extern __shared__ uint8_t smem_raw[];
-    PointNetTcSmem& s = *reinterpret_cast<PointNetTcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    PointNetTcSmem& s = *reinterpret_cast<PointNetTcSmem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));   // keeps the shared address space (LDS/STS)
     uint64_t* b1_ready = &s.bars[0]; uint64_t* d2_full = &s.bars[1]; uint64_t* b2_ready = &s.bars[2]; uint64_t* d3_full = &s.bars[3];
     const int c_in = CIN > 0 ? CIN : c_in_rt;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -187,7 +187,7 @@ class MultiHeadedEdgeAttention(nn.Module):
         node projection  [W_qc ; W_v' ; W1[:, :D_n] ; W1[:, D_n+D_e:]]  with
           W_qc[h*hid + j, :] = sum_c C1[j, c] W_q[c*H + h, :]   (proj_query folded into the first MLP layer),
           W_v'[h*d_o + c, :] = W_v[c*H + h, :];
-        edge projection  W_pe'[h*d_e + c, :] = W_pe[c*H + h, :];  C1k = C1[:, d_n:] and C2 as tf32 splits."""
+        edge projection  W_pe'[h*d_e + c, :] = W_pe[c*H + h, :];  C1k = C1[:, d_n:] and C2 as bf16 (hi, lo) pairs."""
         wq, wv, w1, pe = self.proj_query[0], self.proj_value[0], self.nn_edge[0], self.proj_edge[0]
         c1, c2 = self._convs()
         H, dn, de, do = self.num_heads, self.d_n, self.d_e, self.d_o
@@ -207,7 +207,7 @@ class MultiHeadedEdgeAttention(nn.Module):
             b_pe = pe.bias.view(de, H).t().reshape(H * de).contiguous()
             c1k = C1[:, dn:].contiguous()
             c2w = c2.weight.squeeze(-1).contiguous()
-            return dict(w_node=w_node, b_node=b_node, w_pe=w_pe, b_pe=b_pe, c1k=ops.tf32_split(c1k), c2=ops.tf32_split(c2w),
+            return dict(w_node=w_node, b_node=b_node, w_pe=w_pe, b_pe=b_pe, c1k=ops.bf16_split(c1k), c2=ops.bf16_split(c2w),
                         c2b=c2.bias.detach().clone().contiguous(), hid=hid)
         srcs = (wq.weight, wq.bias, wv.weight, wv.bias, w1.weight, pe.weight, pe.bias, c1.weight, c1.bias, c2.weight, c2.bias)
         return self._cache.get("tc", srcs, build)
@@ -242,7 +242,7 @@ class MultiHeadedEdgeAttention(nn.Module):
         _, h = ops.linear(edge, w1.weight.detach()[:, dn:dn + de], w1.bias.detach(), act=ops.ACT_RELU,
                           gather=(a_src, g.src, b_dst, g.dst), x_split=edge_split, emit_split=True, want_y=False)
         new_edge, self.last_edge_split = ops.linear(h, w2.weight.detach(), w2.bias.detach(), emit_split=True)
-        _, k_hm = ops.linear(edge, w["w_pe"], w["b_pe"], x_split=edge_split, emit_split="tf32", want_y=False)   # rows (e, h)
+        _, k_hm = ops.linear(edge, w["w_pe"], w["b_pe"], x_split=edge_split, emit_split="bf16", want_y=False)   # rows (e, h)
         _, prob = ops.gat_edge_tc(k_hm, qc, v_hm, g.src, g.dst, w["c1k"], w["c2"], w["c2b"], g.num_nodes, H, xx_out,
                                   want_prob=want_prob, d_n=self.d_n)
         return new_edge, prob

@@ -550,14 +550,29 @@ def permute_edges(edge_index: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
 
 
 def gat_tc_supported(n_heads: int, d_e: int, hid: int, d_o: int) -> bool:
-    return (tensor_cores_enabled() and 128 % n_heads == 0 and d_e % 32 == 0 and 32 <= d_e <= 256 and hid % 32 == 0
-            and d_o in (32, 64) and 3 * hid + d_o <= 512 and hid <= 256)
+    return (tensor_cores_enabled() and 128 % n_heads == 0 and d_e == 64 and hid % 32 == 0 and 32 <= hid <= 128
+            and d_o in (32, 64))
+
+
+_gat_workspaces = {}
+
+
+def _gat_workspace(device, stream: int, words: int) -> torch.Tensor:
+    """INT_MIN-filled scratch of the tensor-core edge kernel, kept per (device, stream, size): the kernel's finalize
+    pass restores the fill, so only the first call pays for it (the C ABI itself owns nothing: it is told
+    ``workspace_ready``)."""
+    key = (str(device), stream, words)
+    ws = _gat_workspaces.get(key)
+    if ws is None:
+        ws = _gat_workspaces[key] = torch.full((words,), -2 ** 31, device=device, dtype=torch.int32)
+    return ws
 
 
 def gat_edge_tc(k_hm, qc, v_hm, src, dst, c1k_split, c2_split, c2b, n_nodes: int, n_heads: int, out: torch.Tensor,
                 want_prob: bool = False, d_n: int = 0):
-    """Tensor-core A8 core (max aggregation). k_hm [E, H*d_e] head-major proj_edge output (CSR edge order),
-    qc [N, H*hid] / v_hm [N, H*d_o] head-major node operands (column-slice views allowed)."""
+    """Tensor-core A8 core (max aggregation). k_hm [E, H*d_e] head-major proj_edge output (CSR edge order) as fp32 or
+    as the bf16 (hi, lo) pair its projection emitted, qc [N, H*hid] / v_hm [N, H*d_o] head-major node operands
+    (column-slice views allowed), c1k / c2 bf16 pairs."""
     k_split = k_hm if isinstance(k_hm, tuple) else None
     if k_split is not None:
         k_hm = k_split[0]
@@ -569,14 +584,18 @@ def gat_edge_tc(k_hm, qc, v_hm, src, dst, c1k_split, c2_split, c2b, n_nodes: int
     xp, ldxx = _rows(out, "out")
     kh = kl = None
     if e > 0:
-        kh, kl = k_split if k_split is not None else tf32_split(k_hm)
+        kh, kl = k_split if k_split is not None else bf16_split(k_hm)
+        if kh.dtype != torch.bfloat16 or kh.stride(0) != n_heads * d_e:
+            raise TypeError("gat_edge_tc: k must be a compact bf16 (hi, lo) pair")
+    if c1k_split[0].dtype != torch.bfloat16 or c2_split[0].dtype != torch.bfloat16:
+        raise TypeError("gat_edge_tc: c1k / c2 must be bf16 (hi, lo) pairs")
     prob = torch.empty((e, d_o, n_heads), device=out.device, dtype=torch.float32) if want_prob else None
-    ws = torch.empty((n_nodes * n_heads * d_o,), device=out.device, dtype=torch.int32)
+    ws = _gat_workspace(out.device, _stream(), n_nodes * n_heads * d_o)
     st = _call("vlsat_gat_edge_tc_fwd", kh.data_ptr() if e else None, kl.data_ptr() if e else None, qp, ldq, vp_, ldv,
                src.data_ptr() if e else None, dst.data_ptr() if e else None,
                c1k_split[0].data_ptr(), c1k_split[1].data_ptr(), c2_split[0].data_ptr(), c2_split[1].data_ptr(),
                c2b.data_ptr(), n_nodes, e, n_heads, d_e, hid, d_o, xp, ldxx, prob.data_ptr() if want_prob else None,
-               ws.data_ptr(), ws.numel() * 4, _stream(),
+               ws.data_ptr(), ws.numel() * 4, 1, _stream(),
                # same algorithmic work as vlsat_gat_edge_fwd, independent of the node-side folding
                work=(2.0 * e * n_heads * (hid * ((d_n or d_e) + d_e) + d_o * hid),
                      e * (n_heads * d_e * 4.0 + 16.0) + n_nodes * (n_heads * (d_n or d_e) + 2.0 * n_heads * d_o) * 4.0))

@@ -215,22 +215,25 @@ int vlsat_gat_edge_fwd(const float* q, int64_t ldq, const float* v, int64_t ldv,
                        int64_t n_nodes, int64_t n_edges, int n_heads, int d_n, int d_e, int d_o, int hid,
                        int aggr, int use_edge, float* xx, int64_t ld_xx, float* prob, int32_t* argmax, void* stream);
 
-/* Tensor-core engine of vlsat_gat_edge_fwd for aggr = max with edge features (the mmgnet.json layer), 3xTF32.
- * Edges must be in source-sorted (CSR) order: src_sorted[i] non-decreasing; every per-edge operand uses that
- * order. Operands are "head-major" (row (e,h) or (n,h) contiguous), prepared by projections with permuted
- * weight rows (see cvpr2023-vlsat_b200/gat.py):
- *   k_hi/k_lo [E*H, d_e] tf32 split of proj_edge(e);  qc: row (n,h) = qc + n*ld_qc + h*hid holds
- *   C1[:, :d_n] . q3[n,:,h] + c1_bias;  v: row (n,h) = v + n*ld_v + h*d_o;  c1k = C1[:, d_n:] [hid, d_e] and
- *   c2 [d_o, hid] as tf32 splits.  xx [n_nodes, H*d_o] (row stride ld_xx) is written in the reference's
- *   interleaved order c*H + h; nodes without outgoing edges get 0.  prob (nullable) [E, d_o, H] in sorted order.
- * workspace >= n_nodes * H * d_o * 4 bytes.  Constraints: 128 % H == 0, d_e % 32 == 0, hid % 32 == 0,
- * d_o in {32, 64}, 3*hid + d_o <= 512 (TMEM columns); other shapes -> VLSAT_ERR_UNSUPPORTED (use vlsat_gat_edge_fwd). */
-int vlsat_gat_edge_tc_fwd(const float* k_hi, const float* k_lo, const float* qc, int64_t ld_qc,
+/* Tensor-core engine of vlsat_gat_edge_fwd for aggr = max with edge features (the mmgnet.json layer), BF16x3
+ * (csrc/gat_tc.cu). Edges must be in source-sorted (CSR) order: src_sorted[i] non-decreasing; every per-edge
+ * operand uses that order. Operands are "head-major" (row (e,h) or (n,h) contiguous), prepared by projections
+ * with permuted weight rows (see cvpr2023-vlsat_b200/gat.py):
+ *   k_hi/k_lo [E*H, d_e] bf16 pair of proj_edge(e) (as emitted by vlsat_linear_fwd with VLSAT_SPLIT_BF16);
+ *   qc: row (n,h) = qc + n*ld_qc + h*hid holds C1[:, :d_n] . q3[n,:,h] + c1_bias;  v: row (n,h) = v + n*ld_v + h*d_o;
+ *   c1k = C1[:, d_n:] [hid, d_e] and c2 [d_o, hid] as bf16 pairs (vlsat_bf16_split).
+ *   xx [n_nodes, H*d_o] (row stride ld_xx) is written in the reference's interleaved order c*H + h; nodes without
+ *   outgoing edges get 0.  prob (nullable) [E, d_o, H] in sorted order.
+ * workspace >= n_nodes * H * d_o * 4 bytes; workspace_ready = 1 promises that every word of it holds INT_MIN (the
+ *   state this call leaves it in), 0 makes the call fill it first.
+ * Constraints: 128 % H == 0, d_e == 64, hid % 32 == 0, hid <= 128, d_o in {32, 64};
+ * other shapes -> VLSAT_ERR_UNSUPPORTED (use vlsat_gat_edge_fwd). */
+int vlsat_gat_edge_tc_fwd(const void* k_hi, const void* k_lo, const float* qc, int64_t ld_qc,
                           const float* v, int64_t ld_v, const int64_t* src_sorted, const int64_t* dst_sorted,
-                          const float* c1k_hi, const float* c1k_lo, const float* c2_hi, const float* c2_lo,
+                          const void* c1k_hi, const void* c1k_lo, const void* c2_hi, const void* c2_lo,
                           const float* c2_bias, int64_t n_nodes, int64_t n_edges, int n_heads, int d_e, int hid,
                           int d_o, float* xx, int64_t ld_xx, float* prob, void* workspace, size_t workspace_bytes,
-                          void* stream);
+                          int workspace_ready, void* stream);
 
 /* Edge-order bookkeeping (bit-exact): out[i,:] = in[idx[i],:] (gather=1) or out[idx[i],:] = in[i,:] (gather=0)
  * for fp32 rows (cols % 4 == 0), and out[:, i] = edge_index[:, perm[i]] for the int64 [2, E] edge list. */
