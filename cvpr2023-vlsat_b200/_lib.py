@@ -40,12 +40,16 @@ SIGNATURES = {
     "vlsat_linear_fwd": [vp, i64, vp, i64, vp, i64, i64, i64, i64, C.POINTER(Epilogue), C.POINTER(LinearOpts), vp],
     "vlsat_linear_workspace_bytes": [i64, i64, i64, i32, i32],
     "vlsat_tf32_split": [vp, i64, i64, i64, vp, vp, vp],
-    "vlsat_add_layernorm_fwd": [vp, i64, vp, i64, vp, vp, vp, i64, i64, i32, f32, i32, vp],
+    "vlsat_add_layernorm_fwd": [vp, i64, vp, i64, vp, vp, vp, i64, i64, i32, f32, i32, vp, vp, i64, vp],
     "vlsat_relu_fwd": [vp, vp, i64, vp],
+    "vlsat_relu_pair_fwd": [vp, vp, vp, vp, i64, vp],
     "vlsat_row_l2norm_fwd": [vp, vp, i64, i32, vp],
     "vlsat_spatial_tail_fwd": [vp, vp, i64, i32, i64, vp],
     "vlsat_scene_ranges": [vp, i64, vp, vp, vp, vp],
-    "vlsat_node_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, vp, i64, i64, vp],
+    "vlsat_node_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, vp, i64, i64, i32, vp],
+    "vlsat_node_bias_table_max_scene": [],
+    "vlsat_node_bias_table": [vp, i64, vp, vp, vp, i32, vp, i64, vp],
+    "vlsat_node_attn_scene_fwd": [vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, vp, i64, i64, vp],
     "vlsat_flash_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp],
     "vlsat_flash_attn_tc_fwd": [vp, vp, i64, vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp],
     "vlsat_gat_edge_tc_fwd": [vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, i32,

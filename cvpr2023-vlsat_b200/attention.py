@@ -27,6 +27,8 @@ class SceneContext:
         self.centres = centres.detach().contiguous()
         self.fc_pack = fc_pack
         self.num_heads = num_heads
+        # the bias depends on the centres only: one table serves every attention call of this forward
+        self.bias_table = ops.node_bias_table(self.centres, self.seg_start, self.seg_end, fc_pack, num_heads)
 
 
 class ScaledDotProductAttention(nn.Module):
@@ -75,37 +77,40 @@ class MultiHeadAttention(nn.Module):
                                                          torch.cat([a.fc_k.bias, a.fc_v.bias], 0).contiguous()))
         raise KeyError(which)
 
-    def _project(self, q_in: torch.Tensor, kv_in: torch.Tensor, same: bool):
+    def _project(self, q_in: torch.Tensor, kv_in: torch.Tensor, same: bool, q_split=None, kv_split=None):
         a = self.attention
         d = a.h * a.d_k
         if same:
             w, b = self._w("qkv")
-            qkv = ops.linear(q_in, w, b)
+            qkv = ops.linear(q_in, w, b, x_split=q_split)
             return qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
-        q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach())
+        q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach(), x_split=q_split)
         w, b = self._w("kv")
-        kv = ops.linear(kv_in, w, b)
+        kv = ops.linear(kv_in, w, b, x_split=kv_split)
         return q, kv[:, :d], kv[:, d:]
 
-    def _finish(self, q_in: torch.Tensor, att: torch.Tensor, relu: bool, out: Optional[torch.Tensor]):
+    def _finish(self, q_in: torch.Tensor, att: torch.Tensor, relu: bool, out: Optional[torch.Tensor], emit_split: bool = False):
         a = self.attention
-        # fc_o with the residual folded into the GEMM epilogue, then LayerNorm (attention.py:76,122)
+        # fc_o with the residual folded into the GEMM epilogue, then LayerNorm (attention.py:76,122); with emit_split the
+        # LayerNorm also writes the (hi, lo) pair the next projection reads: returns (y, pair or None)
         pre = ops.linear(att, a.fc_o.weight.detach(), a.fc_o.bias.detach(), residual=q_in, alpha=1.0, beta=1.0)
         return ops.add_layernorm(pre, None, self.layer_norm.weight.detach(), self.layer_norm.bias.detach(),
-                                 eps=self.layer_norm.eps, relu=relu, out=out)
+                                 eps=self.layer_norm.eps, relu=relu, out=out, emit_split=emit_split)
 
     # ---- hot-path entry points -------------------------------------------------------------------
-    def attend_scenes(self, q_in, kv_in, ctx: SceneContext, relu: bool = False, out=None) -> torch.Tensor:
-        """LN(q_in + fc_o(softmax_scene(QK^T/sqrt(dk) + bias) V)); q_in, kv_in are [N, d_model]."""
+    def attend_scenes(self, q_in, kv_in, ctx: SceneContext, relu: bool = False, out=None, q_split=None, kv_split=None,
+                      emit_split: bool = False):
+        """LN(q_in + fc_o(softmax_scene(QK^T/sqrt(dk) + bias) V)); q_in, kv_in are [N, d_model]. ``q_split`` / ``kv_split``:
+        (hi, lo) pairs of the inputs when a producer emitted them; ``emit_split``: return (y, pair of y)."""
         require_inference(self, "MultiHeadAttention")
         if ctx.num_heads != self.attention.h:
             raise ValueError(f"distance bias has {ctx.num_heads} heads but attention has {self.attention.h} "
                              "(network_GNN.py:211 hard-codes 8 heads for this reason)")
-        q, k, v = self._project(q_in, kv_in, q_in is kv_in)
-        att = ops.node_attn(q, k, v, ctx.centres, ctx.seg_start, ctx.seg_end, ctx.fc_pack, self.attention.h)
-        return self._finish(q_in, att, relu, out)
+        q, k, v = self._project(q_in, kv_in, q_in is kv_in, q_split, kv_split)
+        att = ops.node_attn(q, k, v, ctx.centres, ctx.seg_start, ctx.seg_end, ctx.fc_pack, self.attention.h, ctx.bias_table)
+        return self._finish(q_in, att, relu, out, emit_split)
 
-    def attend_all(self, q_in, kv_in, relu: bool = False, out=None, q_split=None, kv_split=None) -> torch.Tensor:
+    def attend_all(self, q_in, kv_in, relu: bool = False, out=None, q_split=None, kv_split=None, emit_split: bool = False):
         """LN(q_in + fc_o(softmax(QK^T/sqrt(dk)) V)) over all keys, no mask/bias; 2-D inputs.
         ``q_split`` / ``kv_split``: (hi, lo) pairs of the inputs if the producer already emitted them."""
         from . import train_path as T
@@ -113,7 +118,7 @@ class MultiHeadAttention(nn.Module):
             y = T.mha_all(self, q_in, kv_in, relu_out=relu)
             if out is not None:
                 raise ValueError("attend_all: `out=` is an inference-path option")
-            return y
+            return (y, None) if emit_split else y
         a = self.attention
         if a.d_k == 64 and ops.tensor_cores_enabled() and kv_in.shape[1] % 4 == 0 and kv_in.shape[1] >= 32:
             # tensor-core path: Q, K row-major; the value projection is emitted transposed (V^T = W_v x^T).
@@ -134,7 +139,7 @@ class MultiHeadAttention(nn.Module):
                     ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), out=vt[:, :nk], bias_per_row=True,
                                x_is_weight=True, w_split=kv_split)
                 att = ops.flash_attn_bf16(q, k, vt, nk, a.h)
-                return self._finish(q_in, att, relu, out)
+                return self._finish(q_in, att, relu, out, emit_split)
             if kv_split is None or ops.pair_fmt(kv_split) != ops.FMT_TF32:
                 kv_split = ops.tf32_split(kv_in)
             if q_split is not None and ops.pair_fmt(q_split) != ops.FMT_TF32:
@@ -152,7 +157,7 @@ class MultiHeadAttention(nn.Module):
         else:
             q, k, v = self._project(q_in, kv_in, q_in is kv_in)
             att = ops.flash_attn(q, k, v, a.h)
-        return self._finish(q_in, att, relu, out)
+        return self._finish(q_in, att, relu, out, emit_split)
 
     # ---- reference signature -----------------------------------------------------------------------
     def forward(self, queries, keys, values, attention_mask=None, attention_weights=None, way='mul', use_knn=False,

@@ -1,6 +1,7 @@
 // Small memory-bound kernels of the path: edge descriptor (A2), residual LayerNorm (A7 tail),
 // inter-layer ReLU (A10), row L2 normalisation (A13) and the spatial tail of the 3-D node feature (A4).
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace vlsat {
 
@@ -51,6 +52,65 @@ __global__ void add_layernorm_kernel(const float* __restrict__ x, int64_t ldx, c
     }
 }
 
+// D = 128 * NV: each lane owns NV float4 groups (columns 4*lane + 128*i ..), every access is a full 512-byte warp row.
+// Optionally also writes the bf16 (hi, lo) pair of the result (the operand format of a following projection).
+template <int NV>
+__global__ void add_layernorm_vec_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ res, int64_t ldr,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float* __restrict__ y, int64_t ldy, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                         int64_t ld_split, int64_t M, float eps, int relu) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    constexpr int D = 128 * NV;
+    float4 v[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = __ldg(reinterpret_cast<const float4*>(x + row * ldx + 128 * i) + lane);
+        if (res) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(res + row * ldr + 128 * i) + lane);
+            v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+        }
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + 128 * i) + lane), b = __ldg(reinterpret_cast<const float4*>(beta + 128 * i) + lane);
+        float4 t = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                               (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+        if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+        if (y) *(reinterpret_cast<float4*>(y + row * ldy + 128 * i) + lane) = t;
+        if (hi) {
+            uint32_t h0, l0, h1, l1;
+            split_bf16x2(t.x, t.y, h0, l0); split_bf16x2(t.z, t.w, h1, l1);
+            *(reinterpret_cast<uint2*>(hi + row * ld_split + 128 * i) + lane) = make_uint2(h0, h1);
+            *(reinterpret_cast<uint2*>(lo + row * ld_split + 128 * i) + lane) = make_uint2(l0, l1);
+        }
+    }
+}
+
+// y = relu(x) with the bf16 (hi, lo) pair of y as an optional second output (flat, numel % 4 == 0)
+__global__ void relu_pair_kernel(const float* __restrict__ x, float* __restrict__ y, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t n4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    if (y) reinterpret_cast<float4*>(y)[i] = v;
+    uint32_t h0, l0, h1, l1;
+    split_bf16x2(v.x, v.y, h0, l0); split_bf16x2(v.z, v.w, h1, l1);
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2(h0, h1);
+    reinterpret_cast<uint2*>(lo)[i] = make_uint2(l0, l1);
+}
+
 __global__ void relu_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n4, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n4) {
@@ -99,12 +159,32 @@ extern "C" int vlsat_edge_descriptor_fwd(const float* desc, int64_t n_nodes, con
 
 extern "C" int vlsat_add_layernorm_fwd(const float* x, int64_t ldx, const float* res, int64_t ld_res,
                                        const float* gamma, const float* beta, float* y, int64_t ldy,
-                                       int64_t M, int D, float eps, int relu, void* stream) {
+                                       int64_t M, int D, float eps, int relu, void* split_hi, void* split_lo,
+                                       int64_t ld_split, void* stream) {
     VLSAT_REQUIRE(M >= 0 && D >= 1);
     if (M == 0) return VLSAT_OK;
-    VLSAT_REQUIRE(x && gamma && beta && y && ldx >= D && ldy >= D && (!res || ld_res >= D));
+    VLSAT_REQUIRE(x && gamma && beta && ldx >= D && (!y || ldy >= D) && (!res || ld_res >= D));
     VLSAT_SUPPORT(D <= 32 * LN_MAX_PER_LANE);
-    add_layernorm_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, res, ld_res, gamma, beta, y, ldy, M, D, eps, relu);
+    VLSAT_REQUIRE((split_hi == nullptr) == (split_lo == nullptr) && (!split_hi || ld_split >= D));
+    VLSAT_REQUIRE(y || split_hi);
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)ceil_div(M * 32, 256);
+    auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    const bool vec = D % 128 == 0 && D <= 1024 && ldx % 4 == 0 && ldy % 4 == 0 && (!res || (ld_res % 4 == 0 && al16(res))) && al16(x) &&
+                     (!y || al16(y)) && al16(gamma) && al16(beta) &&
+                     (!split_hi || (ld_split % 4 == 0 && ((uintptr_t)split_hi & 7) == 0 && ((uintptr_t)split_lo & 7) == 0));
+    uint16_t* hi = (uint16_t*)split_hi; uint16_t* lo = (uint16_t*)split_lo;
+#define VLSAT_LN(NV_) add_layernorm_vec_kernel<NV_><<<grid, 256, 0, st>>>(x, ldx, res, ld_res, gamma, beta, y, ldy, hi, lo, ld_split, M, eps, relu)
+    if (vec) {
+        switch (D / 128) {
+            case 1: VLSAT_LN(1); break; case 2: VLSAT_LN(2); break; case 3: VLSAT_LN(3); break; case 4: VLSAT_LN(4); break;
+            case 5: VLSAT_LN(5); break; case 6: VLSAT_LN(6); break; case 7: VLSAT_LN(7); break; default: VLSAT_LN(8); break;
+        }
+        return finish_launch();
+    }
+#undef VLSAT_LN
+    VLSAT_SUPPORT(!split_hi && y);            // the pair output needs the vectorised layout
+    add_layernorm_kernel<<<grid, 256, 0, st>>>(x, ldx, res, ld_res, gamma, beta, y, ldy, M, D, eps, relu);
     return finish_launch();
 }
 
@@ -118,6 +198,16 @@ extern "C" int vlsat_relu_fwd(const float* x, float* y, int64_t numel, void* str
     } else {
         relu_scalar_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, (cudaStream_t)stream>>>(x, y, numel);
     }
+    return finish_launch();
+}
+
+extern "C" int vlsat_relu_pair_fwd(const float* x, float* y, void* split_hi, void* split_lo, int64_t numel, void* stream) {
+    VLSAT_REQUIRE(numel >= 0);
+    if (numel == 0) return VLSAT_OK;
+    VLSAT_REQUIRE(x && split_hi && split_lo);
+    VLSAT_SUPPORT(numel % 4 == 0 && ((uintptr_t)x % 16 == 0) && (!y || (uintptr_t)y % 16 == 0) && ((uintptr_t)split_hi % 8 == 0) &&
+                  ((uintptr_t)split_lo % 8 == 0));
+    relu_pair_kernel<<<(unsigned)ceil_div(numel / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, y, (uint16_t*)split_hi, (uint16_t*)split_lo, numel / 4);
     return finish_launch();
 }
 

@@ -40,8 +40,9 @@ __global__ void __launch_bounds__(NA_THREADS)
 node_attn_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
                  const float* __restrict__ v, int64_t ldv, const float* __restrict__ centres, int64_t ldc,
                  const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_end,
-                 const float* __restrict__ fc, int H, float* __restrict__ out, int64_t ldo) {
+                 const float* __restrict__ fc, int H, float* __restrict__ out, int64_t ldo, int skip_upto) {
     extern __shared__ __align__(16) float sm[];
+    if (seg_end[blockIdx.x] - seg_start[blockIdx.x] <= skip_upto) return;    // served by node_attn_scene_kernel
     float* fcs = sm;                                  // FcOffsets::total(H)
     float* qs = fcs + ((FcOffsets::total(H) + 3) & ~3); // H*DK
     float* hbuf = qs + H * DK;                        // NA_TK * 33
@@ -205,6 +206,171 @@ node_attn_kernel(const float* __restrict__ q, int64_t ldq, const float* __restri
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Scene-resident form for scenes of up to NS_MAX nodes (every scene of the 3RScan / BASELINE shapes). The bias
+// depends only on the object centres, and MMG.forward runs 2 * depth attentions over the same scenes, so it is
+// evaluated ONCE per forward into a table  tab[(a * NS_MAX + j) * H + h]  (query node a, j-th key of its scene);
+// each attention call is then one CTA per (scene, head) with that head's Q, K, V slices of the scene in shared
+// memory: every K / V row is read once per scene instead of once per query.
+constexpr int NS_MAX = 64;
+constexpr int NS_THREADS = 128;
+
+__global__ void __launch_bounds__(NA_THREADS)
+node_bias_table_kernel(const float* __restrict__ centres, int64_t ldc, const int32_t* __restrict__ seg_start,
+                       const int32_t* __restrict__ seg_end, const float* __restrict__ fc, int H, float* __restrict__ tab) {
+    extern __shared__ __align__(16) float sm[];
+    float* fcs = sm;                                  // FcOffsets::total(H)
+    float* hbuf = fcs + ((FcOffsets::total(H) + 3) & ~3);   // NS_MAX * 33
+    const int tid = threadIdx.x;
+    const int64_t a = blockIdx.x;
+    const int s0 = seg_start[a], ns = seg_end[a] - s0;
+    if (ns > NS_MAX) return;                          // large scenes keep the streaming kernel (bias evaluated in place)
+    for (int i = tid; i < FcOffsets::total(H); i += NA_THREADS) fcs[i] = __ldg(fc + i);
+    const float cax = centres[a * ldc + 0], cay = centres[a * ldc + 1], caz = centres[a * ldc + 2];
+    __syncthreads();
+    // 4 threads per pair, 8 hidden units each (same arithmetic, in the same order, as node_attn_kernel)
+    const int pr = tid >> 2, part = tid & 3;
+    const bool live = pr < ns;
+    const int64_t b = s0 + (live ? pr : 0);
+    const float dx = centres[b * ldc + 0] - cax, dy = centres[b * ldc + 1] - cay, dz = centres[b * ldc + 2] - caz;
+    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+    float h[8];
+    float s1_ = 0.f, s2_ = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int j = part * 8 + u;
+        const float* w = fcs + FcOffsets::W0 + j * 4;
+        float t = fcs[FcOffsets::B0 + j] + w[0] * dx + w[1] * dy + w[2] * dz + w[3] * dist;
+        t = fmaxf(t, 0.f);
+        h[u] = t; s1_ += t;
+    }
+    s1_ += __shfl_xor_sync(0xffffffffu, s1_, 1); s1_ += __shfl_xor_sync(0xffffffffu, s1_, 2);
+    float mean = s1_ * (1.f / 32.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { float d = h[u] - mean; s2_ += d * d; }
+    s2_ += __shfl_xor_sync(0xffffffffu, s2_, 1); s2_ += __shfl_xor_sync(0xffffffffu, s2_, 2);
+    float rstd = rsqrtf(s2_ * (1.f / 32.f) + 1e-5f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int j = part * 8 + u;
+        hbuf[pr * 33 + j] = (h[u] - mean) * rstd * fcs[FcOffsets::G0 + j] + fcs[FcOffsets::BE0 + j];
+    }
+    __syncwarp();
+    s1_ = 0.f; s2_ = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int j = part * 8 + u;
+        const float* w = fcs + FcOffsets::W1 + j * 32;
+        float t = fcs[FcOffsets::B1 + j];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t = fmaf(w[i], hbuf[pr * 33 + i], t);
+        t = fmaxf(t, 0.f);
+        h[u] = t; s1_ += t;
+    }
+    s1_ += __shfl_xor_sync(0xffffffffu, s1_, 1); s1_ += __shfl_xor_sync(0xffffffffu, s1_, 2);
+    mean = s1_ * (1.f / 32.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { float d = h[u] - mean; s2_ += d * d; }
+    s2_ += __shfl_xor_sync(0xffffffffu, s2_, 1); s2_ += __shfl_xor_sync(0xffffffffu, s2_, 2);
+    rstd = rsqrtf(s2_ * (1.f / 32.f) + 1e-5f);
+    __syncwarp();                       // everyone has finished reading layer-1 values
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int j = part * 8 + u;
+        hbuf[pr * 33 + j] = (h[u] - mean) * rstd * fcs[FcOffsets::G1 + j] + fcs[FcOffsets::BE1 + j];
+    }
+    __syncwarp();
+    if (live) {
+        for (int hh = part; hh < H; hh += 4) {
+            const float* w = fcs + FcOffsets::W2 + hh * 32;
+            float t = fcs[FcOffsets::b2(H) + hh];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t = fmaf(w[i], hbuf[pr * 33 + i], t);
+            tab[((int64_t)a * NS_MAX + pr) * H + hh] = t;
+        }
+    }
+}
+
+// grid (ceil(n_nodes / NS_CAND), H): a CTA looks at NS_CAND consecutive nodes and serves, for its head, the scene of
+// every one of them that is the first node of its scene (no host-side scene list: the scene count never leaves the GPU).
+constexpr int NS_CAND = 16;
+template <int DK>
+__global__ void __launch_bounds__(NS_THREADS)
+node_attn_scene_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
+                       const float* __restrict__ v, int64_t ldv, const float* __restrict__ tab,
+                       const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_end, int H,
+                       float* __restrict__ out, int64_t ldo, int64_t n_nodes) {
+    const int hh = blockIdx.y;
+    constexpr int LD = DK + 1;                        // padded rows: lanes reading one column of 32 rows hit 32 banks
+    extern __shared__ __align__(16) float sm[];
+    float* qs = sm; float* ks = qs + NS_MAX * LD; float* vs = ks + NS_MAX * LD;
+    float (*ps)[NS_MAX] = reinterpret_cast<float (*)[NS_MAX]>(vs + NS_MAX * LD);      // [warps][NS_MAX]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int a0 = blockIdx.x * NS_CAND; a0 < min((int)n_nodes, (blockIdx.x + 1) * NS_CAND); ++a0) {
+    const int s0 = seg_start[a0], ns = seg_end[a0] - s0;
+    if (a0 != s0 || ns > NS_MAX) continue;            // block-uniform
+    __syncthreads();                                  // the previous scene's rows are no longer read
+    for (int i = tid; i < ns * (DK / 4); i += NS_THREADS) {
+        const int row = i / (DK / 4), c4 = i % (DK / 4);
+        const float4 q4 = __ldg(reinterpret_cast<const float4*>(q + (int64_t)(s0 + row) * ldq + hh * DK) + c4);
+        const float4 k4 = __ldg(reinterpret_cast<const float4*>(k + (int64_t)(s0 + row) * ldk + hh * DK) + c4);
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(v + (int64_t)(s0 + row) * ldv + hh * DK) + c4);
+        float* qd = qs + row * LD + c4 * 4; float* kd = ks + row * LD + c4 * 4; float* vd = vs + row * LD + c4 * 4;
+        qd[0] = q4.x; qd[1] = q4.y; qd[2] = q4.z; qd[3] = q4.w;
+        kd[0] = k4.x; kd[1] = k4.y; kd[2] = k4.z; kd[3] = k4.w;
+        vd[0] = v4.x; vd[1] = v4.y; vd[2] = v4.z; vd[3] = v4.w;
+    }
+    __syncthreads();
+    const float scale = rsqrtf((float)DK);
+    for (int i = warp; i < ns; i += NS_THREADS / 32) {               // one query per warp at a time
+        const float* qi = qs + i * LD;
+        const float* bias = tab + ((int64_t)(s0 + i) * NS_MAX) * H + hh;
+        float sc[NS_MAX / 32];
+        float mx = -FLT_MAX;
+#pragma unroll
+        for (int r = 0; r < NS_MAX / 32; ++r) {
+            const int j = lane + 32 * r;
+            float s = -FLT_MAX;
+            if (j < ns) {
+                const float* kj = ks + j * LD;
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                for (int d = 0; d < DK; d += 4) {
+                    d0 = fmaf(qi[d], kj[d], d0); d1 = fmaf(qi[d + 1], kj[d + 1], d1);
+                    d2 = fmaf(qi[d + 2], kj[d + 2], d2); d3 = fmaf(qi[d + 3], kj[d + 3], d3);
+                }
+                s = ((d0 + d1) + (d2 + d3)) * scale + __ldg(bias + (int64_t)j * H);
+            }
+            sc[r] = s; mx = fmaxf(mx, s);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < NS_MAX / 32; ++r) {
+            const int j = lane + 32 * r;
+            sc[r] = (j < ns) ? __expf(sc[r] - mx) : 0.f;
+            sum += sc[r];
+        }
+        const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+        for (int r = 0; r < NS_MAX / 32; ++r) ps[warp][lane + 32 * r] = sc[r] * inv;
+        __syncwarp();
+        float acc[DK / 32];
+#pragma unroll
+        for (int d = 0; d < DK / 32; ++d) acc[d] = 0.f;
+        for (int j = 0; j < ns; ++j) {
+            const float pj = ps[warp][j];
+#pragma unroll
+            for (int d = 0; d < DK / 32; ++d) acc[d] = fmaf(pj, vs[j * LD + lane + 32 * d], acc[d]);
+        }
+#pragma unroll
+        for (int d = 0; d < DK / 32; ++d) out[(int64_t)(s0 + i) * ldo + hh * DK + lane + 32 * d] = acc[d];
+        __syncwarp();                                    // ps[warp] is rewritten for this warp's next query
+    }
+    }
+}
+
 }  // namespace vlsat
 
 using namespace vlsat;
@@ -222,7 +388,8 @@ extern "C" int vlsat_scene_ranges(const int64_t* batch_ids, int64_t n_nodes, int
 extern "C" int vlsat_node_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v,
                                    int64_t ldv, const float* centres, int64_t ld_centres,
                                    const int32_t* seg_start, const int32_t* seg_end, const float* fc_w,
-                                   int n_heads, int dk, float* out, int64_t ldo, int64_t n_nodes, void* stream) {
+                                   int n_heads, int dk, float* out, int64_t ldo, int64_t n_nodes, int skip_scenes_upto,
+                                   void* stream) {
     VLSAT_REQUIRE(q && k && v && centres && seg_start && seg_end && fc_w && out && n_nodes >= 0);
     VLSAT_SUPPORT(n_heads >= 1 && n_heads <= NA_MAXH && (dk == 64 || dk == 128 || dk == 32));
     VLSAT_SUPPORT(ldq % 4 == 0 && ldk % 4 == 0 && ((uintptr_t)k % 16 == 0) && n_nodes < 0x7fffffff);
@@ -231,8 +398,43 @@ extern "C" int vlsat_node_attn_fwd(const float* q, int64_t ldq, const float* k, 
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)n_nodes;
 #define LAUNCH(DK_) node_attn_kernel<DK_><<<grid, NA_THREADS, smem, st>>>(q, ldq, k, ldk, v, ldv, centres, ld_centres, \
-        seg_start, seg_end, fc_w, n_heads, out, ldo)
+        seg_start, seg_end, fc_w, n_heads, out, ldo, skip_scenes_upto)
     if (dk == 64) LAUNCH(64); else if (dk == 128) LAUNCH(128); else LAUNCH(32);
 #undef LAUNCH
+    return finish_launch();
+}
+
+extern "C" int vlsat_node_bias_table_max_scene(void) { return NS_MAX; }
+
+extern "C" int vlsat_node_bias_table(const float* centres, int64_t ld_centres, const int32_t* seg_start,
+                                     const int32_t* seg_end, const float* fc_w, int n_heads, float* table,
+                                     int64_t n_nodes, void* stream) {
+    VLSAT_REQUIRE(centres && seg_start && seg_end && fc_w && table && n_nodes >= 0);
+    VLSAT_SUPPORT(n_heads >= 1 && n_heads <= NA_MAXH && n_nodes < 0x7fffffff);
+    if (n_nodes == 0) return VLSAT_OK;
+    const size_t smem = sizeof(float) * (((FcOffsets::total(n_heads) + 3) & ~3) + NS_MAX * 33);
+    node_bias_table_kernel<<<(unsigned)n_nodes, NA_THREADS, smem, (cudaStream_t)stream>>>(centres, ld_centres, seg_start, seg_end,
+                                                                                         fc_w, n_heads, table);
+    return finish_launch();
+}
+
+extern "C" int vlsat_node_attn_scene_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v,
+                                         int64_t ldv, const float* table, const int32_t* seg_start,
+                                         const int32_t* seg_end, int n_heads, int dk, float* out, int64_t ldo,
+                                         int64_t n_nodes, void* stream) {
+    VLSAT_REQUIRE(q && k && v && table && seg_start && seg_end && out && n_nodes >= 0);
+    VLSAT_SUPPORT(n_heads >= 1 && n_heads <= NA_MAXH && (dk == 64 || dk == 32));
+    VLSAT_SUPPORT(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) % 16 == 0) &&
+                  n_nodes < 0x7fffffff && n_heads <= 65535);
+    if (n_nodes == 0) return VLSAT_OK;
+    const dim3 grid((unsigned)ceil_div(n_nodes, NS_CAND), (unsigned)n_heads);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sizeof(float) * (3 * NS_MAX * (dk + 1) + (NS_THREADS / 32) * NS_MAX);
+    if (dk == 64) {
+        cudaFuncSetAttribute(node_attn_scene_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        node_attn_scene_kernel<64><<<grid, NS_THREADS, smem, st>>>(q, ldq, k, ldk, v, ldv, table, seg_start, seg_end, n_heads, out, ldo, n_nodes);
+    } else {
+        node_attn_scene_kernel<32><<<grid, NS_THREADS, smem, st>>>(q, ldq, k, ldk, v, ldv, table, seg_start, seg_end, n_heads, out, ldo, n_nodes);
+    }
     return finish_launch();
 }

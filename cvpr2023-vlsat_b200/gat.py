@@ -218,7 +218,7 @@ class MultiHeadedEdgeAttention(nn.Module):
                 and self.dim_node % 4 == 0 and self.dim_edge % 4 == 0)
 
     def fused_tc(self, x: torch.Tensor, edge: torch.Tensor, g: GraphContext, xx_out: torch.Tensor, want_prob: bool = False,
-                 edge_split=None):
+                 edge_split=None, x_split=None):
         """Tensor-core version of ``fused`` (same contract; ``edge`` and ``g`` in CSR edge order). Intermediate
         activations that only feed another projection are never stored unsplit: the producing epilogue emits
         the tf32 (hi, lo) pair the consumer reads. Also returns the split of the new edge feature."""
@@ -227,7 +227,7 @@ class MultiHeadedEdgeAttention(nn.Module):
         H, hid, da, de = self.num_heads, w["hid"], self.dim_atten, self.dim_edge
         dn = self.dim_node
         hid1 = self.nn_edge[0].weight.shape[0]
-        node = ops.linear(x, w["w_node"], w["b_node"])             # [N, H*hid + D_a + 2*hid1]
+        node = ops.linear(x, w["w_node"], w["b_node"], x_split=x_split)   # [N, H*hid + D_a + 2*hid1]
         qc, v_hm = node[:, :H * hid], node[:, H * hid:H * hid + da]
         a_src, b_dst = node[:, H * hid + da:H * hid + da + hid1], node[:, H * hid + da + hid1:]
         w1, w2 = self.nn_edge[0], self.nn_edge[2]
@@ -249,13 +249,13 @@ class MultiHeadedEdgeAttention(nn.Module):
 
     # ---- fused path ------------------------------------------------------------------------------
     def fused(self, x: torch.Tensor, edge: torch.Tensor, g: GraphContext, xx_out: torch.Tensor,
-              want_prob: bool = False):
+              want_prob: bool = False, edge_split=None, x_split=None):
         """x [N, D_n] (may be a column slice), edge [E, D_e] in CSR edge order -> writes the aggregate into
         ``xx_out`` [N, D_a]; returns (new edge feature [E, D_e], prob or None), both in CSR edge order."""
         require_inference(self, "MultiHeadedEdgeAttention")
         self.last_edge_split = None
         if self.tc_eligible():
-            return self.fused_tc(x, edge, g, xx_out, want_prob)
+            return self.fused_tc(x, edge, g, xx_out, want_prob, edge_split=edge_split, x_split=x_split)
         dn, de, da = self.dim_node, self.dim_edge, self.dim_atten
         hid1 = self.nn_edge[0].weight.shape[0]
         w_node, b_node = self.node_projection_weights()
@@ -327,15 +327,21 @@ class GraphEdgeAttenNetwork(nn.Module):
         self.prop = build_mlp([dim_node + dim_atten, dim_node + dim_atten, dim_node], do_bn=use_bn, on_last=False)
 
     def forward_fused(self, cat_buf: torch.Tensor, edge_feature: torch.Tensor, g: GraphContext,
-                      relu_nodes: bool = False, want_prob: bool = False):
+                      relu_nodes: bool = False, want_prob: bool = False, x_split=None, edge_split=None, emit_split: bool = False):
         """``cat_buf`` [N, D_n + D_a] already holds x in its first D_n columns; the aggregate is written
-        into the remaining columns, so ``prop(cat[x, xx])`` reads one buffer (network_MMG.py:40)."""
+        into the remaining columns, so ``prop(cat[x, xx])`` reads one buffer (network_MMG.py:40). ``x_split`` /
+        ``edge_split``: (hi, lo) pairs of x / the edge feature when their producers emitted them; ``emit_split``: also
+        return the pair of the new node feature (4-tuple)."""
         dn = self.dim_node
-        new_edge, prob = self.edgeatten.fused(cat_buf[:, :dn], edge_feature, g, cat_buf[:, dn:], want_prob)
+        new_edge, prob = self.edgeatten.fused(cat_buf[:, :dn], edge_feature, g, cat_buf[:, dn:], want_prob,
+                                              edge_split=edge_split, x_split=x_split)
         p0, p2 = self.prop[0], self.prop[2]
-        hid = ops.linear(cat_buf, p0.weight.detach(), p0.bias.detach(), act=ops.ACT_RELU)
-        out = ops.linear(hid, p2.weight.detach(), p2.bias.detach(), act=ops.ACT_RELU if relu_nodes else ops.ACT_NONE)
-        return out, new_edge, prob
+        res = ops.linear_chain(cat_buf, [(p0.weight.detach(), p0.bias.detach(), ops.ACT_RELU),
+                                         (p2.weight.detach(), p2.bias.detach(), ops.ACT_RELU if relu_nodes else ops.ACT_NONE)],
+                               emit_last=emit_split)
+        if emit_split:
+            return res[0], new_edge, prob, res[1]
+        return res, new_edge, prob
 
     def forward(self, x, edge_feature, edge_index, weight=None, istrain=False):
         assert x.ndim == 2

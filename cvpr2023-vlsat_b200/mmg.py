@@ -66,18 +66,24 @@ class MMG(nn.Module):
         g = GraphContext(edge_index, n, self.flow)
         o3, o2 = obj_feature_3d.contiguous(), obj_feature_2d.contiguous()
         e3, e2 = g.to_sorted(edge_feature_3d.contiguous()), g.to_sorted(edge_feature_2d.contiguous())   # CSR edge order
+        # (hi, lo) pairs of the four streams travel with them: every producer that feeds a projection emits the pair from
+        # its epilogue, so no activation is read back just to be split
+        o3p = o2p = e3p = e2p = None
         for i in range(self.depth):
             act = (i < self.depth - 1) or self.depth == 1          # ReLU(+Dropout) after this layer
             cat3 = torch.empty((n, dn + da), device=o3.device, dtype=torch.float32)
             cat2 = torch.empty((n, dn + da), device=o3.device, dtype=torch.float32)
-            o3 = self.self_attn[i].attend_scenes(o3, o3, ctx, out=cat3[:, :dn])
-            o2 = self.cross_attn[i].attend_scenes(o2, o3, ctx, out=cat2[:, :dn])
-            o3, e3_raw, _ = self.gcn_3ds[i].forward_fused(cat3, e3, g, relu_nodes=act)
-            o2, e2_raw, _ = self.gcn_2ds[i].forward_fused(cat2, e2, g, relu_nodes=act)
-            e2 = self.cross_attn_rel[i].attend_all(e2_raw, e3_raw, relu=act,
-                                                   q_split=self.gcn_2ds[i].edgeatten.last_edge_split,
-                                                   kv_split=self.gcn_3ds[i].edgeatten.last_edge_split)
-            e3 = ops.relu(e3_raw) if act else e3_raw
+            o3, o3p = self.self_attn[i].attend_scenes(o3, o3, ctx, out=cat3[:, :dn], q_split=o3p, kv_split=o3p, emit_split=True)
+            o2, o2p = self.cross_attn[i].attend_scenes(o2, o3, ctx, out=cat2[:, :dn], q_split=o2p, kv_split=o3p, emit_split=True)
+            o3, e3_raw, _, o3p = self.gcn_3ds[i].forward_fused(cat3, e3, g, relu_nodes=act, x_split=o3p, edge_split=e3p, emit_split=True)
+            o2, e2_raw, _, o2p = self.gcn_2ds[i].forward_fused(cat2, e2, g, relu_nodes=act, x_split=o2p, edge_split=e2p, emit_split=True)
+            e2, e2p = self.cross_attn_rel[i].attend_all(e2_raw, e3_raw, relu=act,
+                                                        q_split=self.gcn_2ds[i].edgeatten.last_edge_split,
+                                                        kv_split=self.gcn_3ds[i].edgeatten.last_edge_split, emit_split=True)
+            if act:
+                e3, e3p = ops.relu(e3_raw, emit_split=True)
+            else:
+                e3, e3p = e3_raw, self.gcn_3ds[i].edgeatten.last_edge_split
         return o3, o2, g.to_original(e3), g.to_original(e2)
 
 

@@ -72,9 +72,9 @@ class AdapterModel(nn.Module):
 
     def forward(self, x):
         """alpha * fc2(relu(fc1(x))) + (1 - alpha) * x, the residual folded into the GEMM epilogue."""
-        h = ops.linear(x, self.fc1.weight.detach(), self.fc1.bias.detach(), act=ops.ACT_RELU)
-        return ops.linear(h, self.fc2.weight.detach(), self.fc2.bias.detach(), residual=x,
-                          alpha=self.alpha, beta=1.0 - self.alpha)
+        return ops.linear_chain(x, [(self.fc1.weight.detach(), self.fc1.bias.detach(), ops.ACT_RELU),
+                                    (self.fc2.weight.detach(), self.fc2.bias.detach(), ops.ACT_NONE)],
+                                residual=x, alpha=self.alpha, beta=1.0 - self.alpha)
 
 
 class Mmgnet(nn.Module):

@@ -309,8 +309,28 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
+def linear_chain(x: torch.Tensor, layers, x_split=None, emit_last: bool = False, **last_kw):
+    """Row MLP ``x -> act(x w0^T + b0) -> ...``: ``layers`` = [(w, b, act), ...]. On the tensor-core engines an intermediate
+    activation exists only as the (hi, lo) pair the next projection reads (written by the producing epilogue); the last
+    layer takes ``last_kw`` (residual=..., out=..., ...) and, with ``emit_last``, also returns the pair of its output."""
+    h, hp = x, x_split
+    for li, (w, b, act) in enumerate(layers):
+        last = li == len(layers) - 1
+        n = w.shape[0]
+        if last:
+            return linear(h if h is not None else hp, w, b, act=act, x_split=hp if h is not None else None, emit_split=emit_last, **last_kw)
+        pair_only = tensor_cores_enabled() and n % 8 == 0 and n >= 32 and layers[li + 1][0].shape[0] >= 8
+        if pair_only:
+            _, hp2 = linear(h if h is not None else hp, w, b, act=act, x_split=hp if h is not None else None, emit_split=True, want_y=False)
+            h, hp = None, hp2
+        else:
+            h, hp = linear(h if h is not None else hp, w, b, act=act, x_split=hp if h is not None else None), None
+
+
 def add_layernorm(x: torch.Tensor, res: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
-                  eps: float = 1e-5, relu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  eps: float = 1e-5, relu: bool = False, out: Optional[torch.Tensor] = None, emit_split: bool = False):
+    """LayerNorm(x + res) (+ ReLU). ``emit_split=True`` also returns the bf16 (hi, lo) pair of the result (the x operand of
+    a following projection): ``(y, (hi, lo))``."""
     xp, ldx = _rows(x, "x")
     m, d = x.shape
     rp, ldr = (None, 0)
@@ -322,20 +342,32 @@ def add_layernorm(x: torch.Tensor, res: Optional[torch.Tensor], gamma: torch.Ten
         out = torch.empty((m, d), device=x.device, dtype=torch.float32)
     yp, ldy = _rows(out, "out")
     _f32(gamma, "gamma"); _f32(beta, "beta")
+    pair = None
+    if emit_split and d % 128 == 0 and tensor_cores_enabled() and default_fmt(d) == FMT_BF16:
+        pair = torch.empty((2, m, d), device=x.device, dtype=torch.bfloat16)
     st = _call("vlsat_add_layernorm_fwd", xp, ldx, rp, ldr, gamma.data_ptr(), beta.data_ptr(), yp, ldy, m, d,
-                                             eps, int(relu), _stream())
+                                             eps, int(relu), pair[0].data_ptr() if pair is not None else None,
+                                             pair[1].data_ptr() if pair is not None else None, d, _stream())
     _lib.check(st, "vlsat_add_layernorm_fwd")
+    if emit_split:
+        return out, ((pair[0], pair[1]) if pair is not None else None)
     return out
 
 
-def relu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def relu(x: torch.Tensor, out: Optional[torch.Tensor] = None, emit_split: bool = False):
+    """y = relu(x); ``emit_split=True`` also returns the bf16 (hi, lo) pair of y (2-D x with cols % 8 == 0): ``(y, pair)``."""
     _f32(x, "x")
     if not x.is_contiguous():
         raise ValueError("relu: x must be contiguous")
     if out is None:
         out = torch.empty_like(x)
+    if emit_split and x.dim() == 2 and x.shape[1] % 8 == 0 and tensor_cores_enabled() and default_fmt(x.shape[1]) == FMT_BF16:
+        pair = torch.empty((2,) + tuple(x.shape), device=x.device, dtype=torch.bfloat16)
+        _lib.check(_call("vlsat_relu_pair_fwd", x.data_ptr(), out.data_ptr(), pair[0].data_ptr(), pair[1].data_ptr(), x.numel(), _stream()),
+                   "vlsat_relu_pair_fwd")
+        return out, (pair[0], pair[1])
     _lib.check(_call("vlsat_relu_fwd", x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "vlsat_relu_fwd")
-    return out
+    return (out, None) if emit_split else out
 
 
 def row_l2norm(x: torch.Tensor) -> torch.Tensor:
@@ -380,7 +412,23 @@ def scene_ranges(batch_ids: torch.Tensor):
     return seg[0], seg[1], err
 
 
-def node_attn(q, k, v, centres, seg_start, seg_end, fc_pack, n_heads: int) -> torch.Tensor:
+def node_bias_table(centres, seg_start, seg_end, fc_pack, n_heads: int) -> torch.Tensor:
+    """Distance-bias table of the scene-resident node attention: [N, 64, H], row (a, j) = bias of query a towards the j-th
+    node of its scene (scenes of more than 64 nodes are left to the streaming kernel, which evaluates the MLP in place)."""
+    cp, ldc = _rows(centres, "centres")
+    n = centres.shape[0]
+    cap = int(_lib.load().vlsat_node_bias_table_max_scene())
+    if fc_pack.numel() != FC_PACK_HEAD + 33 * n_heads:
+        raise ValueError("node_bias_table: packed self_attn_fc has the wrong size for this head count")
+    tab = torch.empty((n, cap, n_heads), device=centres.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_node_bias_table", cp, ldc, seg_start.data_ptr(), seg_end.data_ptr(), _f32(fc_pack, "fc_pack").data_ptr(),
+                     n_heads, tab.data_ptr(), n, _stream()), "vlsat_node_bias_table")
+    return tab
+
+
+def node_attn(q, k, v, centres, seg_start, seg_end, fc_pack, n_heads: int, bias_table: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A6 + A7. With ``bias_table`` (``node_bias_table``, computed once per forward) scenes of up to 64 nodes run on the
+    scene-resident kernel and only larger ones on the streaming kernel; without it everything streams."""
     qp, ldq = _rows(q, "q"); kp, ldk = _rows(k, "k"); vp_, ldv = _rows(v, "v")
     cp, ldc = _rows(centres, "centres")
     n, d = q.shape
@@ -388,8 +436,14 @@ def node_attn(q, k, v, centres, seg_start, seg_end, fc_pack, n_heads: int) -> to
     if fc_pack.numel() != FC_PACK_HEAD + 33 * n_heads:
         raise ValueError("node_attn: packed self_attn_fc has the wrong size for this head count")
     out = torch.empty((n, d), device=q.device, dtype=torch.float32)
+    skip = 0
+    if bias_table is not None and dk in (32, 64) and ldv % 4 == 0 and (qp | kp | vp_) % 16 == 0:
+        skip = bias_table.shape[1]
+        st = _call("vlsat_node_attn_scene_fwd", qp, ldq, kp, ldk, vp_, ldv, bias_table.data_ptr(), seg_start.data_ptr(),
+                   seg_end.data_ptr(), n_heads, dk, out.data_ptr(), d, n, _stream())
+        _lib.check(st, "vlsat_node_attn_scene_fwd")
     st = _call("vlsat_node_attn_fwd", qp, ldq, kp, ldk, vp_, ldv, cp, ldc, seg_start.data_ptr(), seg_end.data_ptr(),
-                                         _f32(fc_pack, "fc_pack").data_ptr(), n_heads, dk, out.data_ptr(), d, n, _stream())
+                                         _f32(fc_pack, "fc_pack").data_ptr(), n_heads, dk, out.data_ptr(), d, n, skip, _stream())
     _lib.check(st, "vlsat_node_attn_fwd")
     return out
 

@@ -65,9 +65,8 @@ class PointNetfeat(nn.Module):
         if x.shape[2] == 1:
             # one "point" per row (the relationship encoders, SGFN_MMG/model.py:305-306): the max is the
             # identity, so the encoder is a 3-layer row MLP on the dense-projection kernels.
-            h = ops.linear(x.reshape(x.shape[0], x.shape[1]).contiguous(), w1, b1, act=ops.ACT_RELU)
-            h = ops.linear(h, w2, b2, act=ops.ACT_RELU)
-            out = ops.linear(h, w3, b3, act=ops.ACT_RELU)
+            out = ops.linear_chain(x.reshape(x.shape[0], x.shape[1]).contiguous(),
+                                   [(w1, b1, ops.ACT_RELU), (w2, b2, ops.ACT_RELU), (w3, b3, ops.ACT_RELU)])
         else:
             out = ops.pointnet(x.contiguous(), w1, b1, w2, b2, w3, b3)
         if return_meta:
@@ -95,6 +94,6 @@ class PointNetRelClsMulti(nn.Module):
         from . import train_path as T
         if T.differentiable(self):
             return T.rel_classifier(self, x)
-        h = ops.linear(x, self.fc1.weight.detach(), self.fc1.bias.detach(), act=ops.ACT_RELU)
-        h = ops.linear(h, self.fc2.weight.detach(), self.fc2.bias.detach(), act=ops.ACT_RELU)
-        return ops.linear(h, self.fc3.weight.detach(), self.fc3.bias.detach(), act=ops.ACT_SIGMOID)
+        return ops.linear_chain(x, [(self.fc1.weight.detach(), self.fc1.bias.detach(), ops.ACT_RELU),
+                                    (self.fc2.weight.detach(), self.fc2.bias.detach(), ops.ACT_RELU),
+                                    (self.fc3.weight.detach(), self.fc3.bias.detach(), ops.ACT_SIGMOID)])

@@ -133,15 +133,19 @@ size_t vlsat_linear_workspace_bytes(int64_t M, int64_t N, int64_t K, int need_x_
 int vlsat_tf32_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, void* stream);
 
 /* LayerNorm(x + res) (attention.py:122-123; eps 1e-5), optional ReLU on the way out
- * (network_MMG.py:236-248 fused for the streams whose raw value is not needed). */
+ * (network_MMG.py:236-248 fused for the streams whose raw value is not needed). split_hi / split_lo (nullable):
+ * also write the bf16 (hi, lo) pair of the result, compact [M, ld_split] (D % 128 == 0 only); y may then be NULL. */
 int vlsat_add_layernorm_fwd(const float* x, int64_t ldx, const float* res, int64_t ld_res,
                             const float* gamma, const float* beta, float* y, int64_t ldy,
-                            int64_t M, int D, float eps, int relu, void* stream);
+                            int64_t M, int D, float eps, int relu, void* split_hi, void* split_lo, int64_t ld_split,
+                            void* stream);
 
 /* Elementwise helpers: y = relu(x) (network_MMG.py:236-248); row L2 normalisation
  * (SGFN_MMG/model.py:329-330); spatial tail of the 3-D node feature (SGFN_MMG/model.py:296-299):
  * out[n, col0 + 0:6] = desc[n,3:9], out[n, col0+6:8] = log(desc[n,9:11]). */
 int vlsat_relu_fwd(const float* x, float* y, int64_t numel, void* stream);
+/* y = relu(x) (y nullable) together with the bf16 (hi, lo) pair of the result; numel % 4 == 0. */
+int vlsat_relu_pair_fwd(const float* x, float* y, void* split_hi, void* split_lo, int64_t numel, void* stream);
 int vlsat_row_l2norm_fwd(const float* x, float* y, int64_t M, int D, void* stream);
 int vlsat_spatial_tail_fwd(const float* desc, float* out, int64_t ld_out, int col0, int64_t n_nodes, void* stream);
 
@@ -159,7 +163,20 @@ int vlsat_node_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk
                         const float* centres, int64_t ld_centres,
                         const int32_t* seg_start, const int32_t* seg_end,
                         const float* fc_w, int n_heads, int dk,
-                        float* out, int64_t ldo, int64_t n_nodes, void* stream);
+                        float* out, int64_t ldo, int64_t n_nodes, int skip_scenes_upto, void* stream);
+/* Scene-resident form of the same attention for scenes of up to vlsat_node_bias_table_max_scene() (= 64) nodes.
+ * The bias depends only on the centres and MMG.forward evaluates 2*depth attentions over the same scenes, so it is
+ * computed once: vlsat_node_bias_table fills table[(a*64 + j)*H + h] = MLP(...)[h] for query a and the j-th node of its
+ * scene (rows of larger scenes are left untouched); vlsat_node_attn_scene_fwd then serves every scene of <= 64 nodes
+ * with one CTA per (scene, head) holding that head's Q, K, V rows in shared memory, and leaves the rows of larger
+ * scenes untouched: call vlsat_node_attn_fwd(..., skip_scenes_upto = 64) for those (it skips the scenes already
+ * served; with skip_scenes_upto = 0 it serves everything). table: n_nodes * 64 * H floats. */
+int vlsat_node_bias_table_max_scene(void);
+int vlsat_node_bias_table(const float* centres, int64_t ld_centres, const int32_t* seg_start, const int32_t* seg_end,
+                          const float* fc_w, int n_heads, float* table, int64_t n_nodes, void* stream);
+int vlsat_node_attn_scene_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                              const float* table, const int32_t* seg_start, const int32_t* seg_end, int n_heads, int dk,
+                              float* out, int64_t ldo, int64_t n_nodes, void* stream);
 
 /* A9  cross_attn_rel core (network_MMG.py:231; attention.py:54-77 without mask/bias): streaming
  * softmax(QK^T/sqrt(dk)) V over ALL keys, never materialising the [H, nq, nk] score tensor.

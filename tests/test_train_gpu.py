@@ -298,8 +298,14 @@ def _no_dropout(m):
 # error of an engine (exact FFMA: ~1e-7 relative; tcgen05 3xTF32: ~1e-5), the winner - hence the route of that single
 # gradient entry - may differ from the reference's although every forward value is within tolerance. Therefore:
 #   * "strict": exact-fp32 engine, element-wise rtol 1e-3 (+ floors) against the reference fixtures;
-#   * "norm":   tensor-core engine, and larger cases against the float32 oracle: ||g - g_ref|| <= 2e-2 ||g_ref|| per tensor.
-@pytest.fixture(params=["simt", "auto"])
+#   * "norm":   tensor-core engines, and larger cases against the float32 oracle: ||g - g_ref|| <= bound * ||g_ref|| per
+#               tensor, bound = 2e-2 for 3xTF32 ("tc", forward error ~1e-6) and 6e-2 for the default BF16x3 ("auto",
+#               forward error ~1e-5: ten times as many ReLU gates / arg-max routes sit inside the noise, and every flipped
+#               one moves a whole row of some gradient; the same ambiguity the fp32 reference has against exact arithmetic).
+NORM_BOUND = {"tc": 2e-2, "auto": 6e-2}
+
+
+@pytest.fixture(params=["simt", "tc", "auto"])
 def engine(request):
     old = ops._engine
     ops.set_gemm_engine(request.param)
@@ -307,7 +313,7 @@ def engine(request):
     ops._engine = old
 
 
-def _check_param_grads(module, want, what, extra=None, mode="strict"):
+def _check_param_grads(module, want, what, extra=None, mode="strict", rel=2e-2):
     # gradients that vanish in exact arithmetic (softmax key bias) carry the engine's noise: 1e-5 of the largest gradient
     floor = 10 * grad_floor(want)
     params = dict(module.named_parameters())
@@ -325,10 +331,10 @@ def _check_param_grads(module, want, what, extra=None, mode="strict"):
             assert torch.isfinite(g).all(), f"{what} d{k}: non-finite"
             ref = (w["full"] if "full" in w else w["head"]).double()
             err = (g[:ref.numel()] - ref).norm().item()
-            bound = 2e-2 * ref.norm().item() + floor * ref.numel() ** 0.5
+            bound = rel * ref.norm().item() + floor * ref.numel() ** 0.5
             if err > bound:
                 failures.append(f"{what} d{k}: ||g - ref|| = {err:.3g} > {bound:.3g} (||ref|| = {ref.norm().item():.3g})")
-            if "norm" in w and abs(float(g.norm()) - w["norm"]) > 2e-2 * w["norm"] + floor * g.numel() ** 0.5:
+            if "norm" in w and abs(float(g.norm()) - w["norm"]) > rel * w["norm"] + floor * g.numel() ** 0.5:
                 failures.append(f"{what} d{k}: norm {float(g.norm()):.6g} vs {w['norm']:.6g}")
         n += 1
     assert not failures, f"{len(failures)}/{n} gradients differ:\n" + "\n".join(failures)
@@ -350,7 +356,8 @@ def test_mmgnet_gradients_match_reference(name, mode, grads, engine):
     for i in (2, 3):
         assert_close(outs[i], want["outs"][i], f"{name}.{mode} output {i}")
     cases.scalar_loss(outs[:7], seed=7).backward()
-    assert _check_param_grads(model, want["grads"], f"{name}.{mode}", mode="strict" if engine == "simt" else "norm") >= 100
+    assert _check_param_grads(model, want["grads"], f"{name}.{mode}", mode="strict" if engine == "simt" else "norm",
+                              rel=NORM_BOUND.get(engine, 2e-2)) >= 100
     for p in model.clip_adapter.parameters():
         assert p.grad is None                                                   # frozen (SGFN_MMG/model.py:179-182)
     if mode == "train":
@@ -559,7 +566,9 @@ def test_graphed_train_step_matches_eager_and_redraws_dropout():
                     wmax = dict(model.named_parameters())[k[:-4] + "weight"].grad.abs().max().item()
                     assert got[k].abs().max().item() <= 1e-4 * wmax + 1e-5 and p.grad.abs().max().item() <= 1e-4 * wmax + 1e-5, k
                     continue
-                assert torch.allclose(got[k], p.grad, rtol=1e-3, atol=1e-4 * p.grad.abs().max().item() + 1e-6), k
+                # atomic accumulation order differs between the two runs: compare per tensor, not per element
+                err, ref = (got[k] - p.grad).norm().item(), p.grad.norm().item()
+                assert err <= 1e-3 * ref + 1e-6 * p.grad.numel() ** 0.5, f"{k}: ||graphed - eager|| = {err:.3g}, ||eager|| = {ref:.3g}"
     assert len(step._graphs) == 1 and step.kernels_per_replay > 500
     # dropout on: every replay draws new masks
     for m, p in saved.items():
