@@ -38,6 +38,18 @@ __device__ __forceinline__ uint32_t fb_pack_bf16(float a, float b) {
     return r;
 }
 
+__device__ __forceinline__ void tmem_st_32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
 __global__ void bf16_split_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int64_t cols,
                                   uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t ld_out) {
     const int64_t c4 = (cols + 3) >> 2;
@@ -180,7 +192,7 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
             const int s = i & 1;
             mbar_wait(&v_full[s], (i >> 1) & 1);
             for (int g = 0; g < 2; ++g) {
-                mbar_wait(&p_ready[g], i & 1);                   // P_g(i) is in smem; S_g[s] and PV_g are drained
+                mbar_wait(&p_ready[g], i & 1);                   // P_g(i) is in smem; S_g[s] is drained; O_g is rescaled if needed
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t dv = dv0 + (uint64_t)(s * (FB_V_STAGE >> 4));
@@ -188,7 +200,7 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
                     const uint32_t tpv = tmem_base + 256 + 64 * g;
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {             // 16 keys per MMA
-                        mma_ss<Kind::BF16>(tpv, dp + ((FB_BQ * 128) >> 4) + 2 * kk, dv + 2 * kk, idesc, kk > 0);       // P_lo V_hi
+                        mma_ss<Kind::BF16>(tpv, dp + ((FB_BQ * 128) >> 4) + 2 * kk, dv + 2 * kk, idesc, (kk > 0) || (i > 0));   // P_lo V_hi
                         mma_ss<Kind::BF16>(tpv, dp + 2 * kk, dv + ((FB_DK * 128) >> 4) + 2 * kk, idesc, 1);            // P_hi V_lo
                         mma_ss<Kind::BF16>(tpv, dp + 2 * kk, dv + 2 * kk, idesc, 1);                                   // P_hi V_hi
                     }
@@ -209,24 +221,13 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
         uint8_t* p_hi = p_smem + g * FB_P_BUF + row_l * 128;
         uint8_t* p_lo = p_hi + FB_BQ * 128;
         const int sw = row_l & 7;
-        float o[FB_DK];
-#pragma unroll
-        for (int d = 0; d < FB_DK; ++d) o[d] = 0.f;
-        float m_run = -FLT_MAX, l_run = 0.f, corr_prev = 1.f;
-        auto fold = [&](int i, float corr) {                     // o <- o * corr + P_g(i) V(i)
-            mbar_wait(&pv_full[g], i & 1);
-            tc_fence_after();
-            uint32_t a[32];
-            tmem_ld_32x32(t_pv + lane_off, a);
-            tmem_ld_wait();
-#pragma unroll
-            for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], corr, __uint_as_float(a[d]));
-            tmem_ld_32x32(t_pv + lane_off + 32, a);
-            tmem_ld_wait();
-#pragma unroll
-            for (int d = 0; d < 32; ++d) o[32 + d] = fmaf(o[32 + d], corr, __uint_as_float(a[d]));
-            tc_fence_before();
-        };
+        // The output accumulator O_g stays in TMEM: the P.V products of all tiles accumulate there (tensor-core fp32
+        // accumulation), so a tile costs this thread no TMEM read-back and no 64 FMAs, and 64 registers are free for the
+        // exp / split pipeline. The running maximum is LAZY: it only moves (and O, l are rescaled through a TMEM
+        // load / multiply / store) when some row of the warp exceeds it by more than 2^8; until then p = 2^(s - m_stale)
+        // <= 256, exactly representable in the bf16 pair, and l accumulates with the same stale reference.
+        float m_run = -FLT_MAX, l_run = 0.f;
+        constexpr float kRescaleAbove = 8.f;                     // log2 units
         for (int i = 0; i < n_tiles; ++i) {
             const int k0 = (tile_begin + i) * FB_BKV;
             uint32_t r[32], r2[32];
@@ -249,10 +250,29 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
 #pragma unroll
             for (int j = 0; j < 32; ++j) mxp[j & 3] = fmaxf(mxp[j & 3], fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
             const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
-            const float m_new = fmaxf(m_run, mx * scale_log2e);
-            const float corr = fb_ex2(m_run - m_new);
+            const float m_cand = fmaxf(m_run, mx * scale_log2e);
+            const bool rescale = __any_sync(0xffffffffu, m_cand > m_run + kRescaleAbove);     // warp-uniform (TMEM ops are collective)
+            const float m_new = rescale ? m_cand : m_run;
+            if (i > 0) {                                         // P.V(i-1) retired: O_g is stable and the P_g buffer is free
+                mbar_wait(&pv_full[g], (i - 1) & 1);
+                tc_fence_after();
+                if (rescale) {
+                    const float corr = fb_ex2(m_run - m_new);
+#pragma unroll
+                    for (int c0 = 0; c0 < FB_DK; c0 += 32) {
+                        uint32_t a[32];
+                        tmem_ld_32x32(t_pv + lane_off + c0, a);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int d = 0; d < 32; ++d) a[d] = __float_as_uint(__uint_as_float(a[d]) * corr);
+                        tmem_st_32(t_pv + lane_off + c0, a);
+                    }
+                    tmem_st_wait();
+                    l_run *= corr;
+                }
+                tc_fence_before();
+            }
             const float neg_m = -m_new;
-            if (i > 0) fold(i - 1, corr_prev);                   // PV_g drained => the P_g buffer is no longer read
             float rsp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -284,12 +304,26 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
             }
             fence_proxy_async();                                 // generic smem writes -> visible to the tensor core
             mbar_arrive(&p_ready[g]);
-            const float rs = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
-            l_run = l_run * corr + rs;
+            l_run += (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
             m_run = m_new;
-            corr_prev = corr;
         }
-        if (n_tiles > 0) fold(n_tiles - 1, corr_prev);
+        float o[FB_DK];
+        if (n_tiles > 0) {
+            mbar_wait(&pv_full[g], (n_tiles - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < FB_DK; c0 += 32) {
+                uint32_t a[32];
+                tmem_ld_32x32(t_pv + lane_off + c0, a);
+                tmem_ld_wait();
+#pragma unroll
+                for (int d = 0; d < 32; ++d) o[c0 + d] = __uint_as_float(a[d]);
+            }
+            tc_fence_before();
+        } else {
+#pragma unroll
+            for (int d = 0; d < FB_DK; ++d) o[d] = 0.f;
+        }
         if (row < nq) {
             if (gridDim.z == 1) {
                 const float inv = 1.f / l_run;

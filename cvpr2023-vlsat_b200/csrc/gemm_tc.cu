@@ -384,7 +384,11 @@ int linear_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
     if (epi) a.epi = *epi;
     else { a.epi = vlsat_epilogue{}; a.epi.alpha = 1.f; }
     a.trace = g_trace;
-    const int bn = (N <= 64) ? 64 : 128;
+    // 128 x 64 tiles for narrow outputs and for small problems: when 128 x 128 tiles would leave more than half of the SMs
+    // idle the GEMM is one tile-latency long, and that latency is the per-SM operand ingest (~64 B/clk): a 64-column B
+    // tile is 25 % less to pull per K block, on twice as many SMs
+    const int64_t tiles128 = ceil_div(M, TC_BM) * ceil_div(N, 128);
+    const int bn = (N <= 64 || 2 * tiles128 <= kNumSMs) ? 64 : 128;
     const auto DT = kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const int eb = kind == 1 ? 2 : 4;
     const uint32_t bk = 128 / eb;                     // elements per 128-byte K block
