@@ -8,12 +8,16 @@
 // is <= ~1e-5 of the output scale, the same noise floor the fp32-accumulating tensor core already has.
 //
 // One CTA = 256 queries (two Q tiles) of one head (dk = 64), KV tiles of 64 keys on 2-stage TMA rings, optional KV split.
-//   warp 0          TMA producer: Q (hi, lo) once; per tile K (hi, lo) [64 keys x 64] and V^T (hi, lo) [64 dims x 64 keys],
+//   warp 0          TMA producer: per tile K (hi, lo) [64 keys x 64] and (warp 10) V^T (hi, lo) [64 dims x 64 keys],
 //                   all K-major rows of exactly 128 bytes (64 bf16) with the 128B swizzle
-//   warp 1          tcgen05.mma issue: S(t) = Q K(t)^T (SS) into TMEM S[t&1]; PV(t) = P(t) V(t) (SS) into TMEM PV[t&1]
-//   warps 2-5, 6-9  two softmax warpgroups (tile parity), one query row per thread: tcgen05.ld S, online softmax in
-//                   the exp2 domain, P split to bf16 hi/lo and written as a swizzled K-major smem operand; the tile's
-//                   P.V is folded into a per-warpgroup fp32 row accumulator; states merged at the end.
+//   warp 1          tcgen05.mma issue, both products with the A operand in TMEM (TS): S(t) = Q K(t)^T into S[t&1] with
+//                   Q copied into TMEM once by the softmax threads, O += P(t) V(t) with P written over S(t)
+//   warps 2-5, 6-9  two softmax warpgroups (one Q tile each), one query row per thread: tcgen05.ld S, online softmax in
+//                   the exp2 domain, P split to bf16 hi/lo and written back IN PLACE over the S columns of TMEM (64 fp32
+//                   columns -> 32 packed hi + 32 packed lo words): P.V is a TS MMA (A from TMEM) that accumulates into
+//                   the warpgroup's O columns for the whole KV range. With S double-buffered the softmax of tile i+1
+//                   never waits for P.V of tile i (the profile of the smem-P version showed the softmax warps stalled on
+//                   exactly that barrier for 28 % of their samples).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <float.h>
@@ -24,11 +28,9 @@ namespace vlsat {
 using namespace tc;
 
 constexpr int FB_BQ = 128, FB_BKV = 64, FB_DK = 64, FB_THREADS = 352;   // + warp 10: V producer
-constexpr int FB_Q_BYTES = 2 * FB_BQ * 128;              // Q_hi | Q_lo, 128 rows x 128 B
 constexpr int FB_K_STAGE = 2 * FB_BKV * 128;             // K_hi | K_lo, 64 rows x 128 B
 constexpr int FB_V_STAGE = 2 * FB_DK * 128;              // Vt_hi | Vt_lo
-constexpr int FB_P_BUF = 2 * FB_BQ * 128;                // P_hi | P_lo, 128 rows x 128 B
-constexpr uint32_t FB_TMEM_COLS = 512;                   // S[g][b] x 64 at 64*(2g+b) | PV[g] x 64 at 256 + 64 g
+constexpr uint32_t FB_TMEM_COLS = 512;                   // S[g][b] x 64 at 64*(2g+b) | O[g] x 64 at 256 + 64 g | Q[g] (hi, lo) x 64 at 384 + 64 g
 
 __device__ __forceinline__ float fb_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // two floats -> packed bf16x2 (round to nearest even); low half = first argument
@@ -48,6 +50,14 @@ __device__ __forceinline__ void tmem_st_32(uint32_t taddr, const uint32_t (&r)[3
           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
+}
+
+// D[tmem] (+)= A[tmem] . B[smem]^T, bf16 inputs: A is read from tensor memory (lane = row, two consecutive K elements per word)
+__device__ __forceinline__ void mma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 __global__ void bf16_split_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int64_t cols,
@@ -80,18 +90,16 @@ struct FlashPartial {
 // [tile_begin, tile_end) of split blockIdx.z: every K / V tile fetched from L2 serves both Q tiles, which halves
 // the L2 -> SM traffic that bounds this kernel.
 __global__ void __launch_bounds__(FB_THREADS, 1)
-flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
+flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __restrict__ q_lo, int64_t ldq,
                        const __grid_constant__ CUtensorMap tm_khi, const __grid_constant__ CUtensorMap tm_klo,
                        const __grid_constant__ CUtensorMap tm_vhi, const __grid_constant__ CUtensorMap tm_vlo,
                        float* __restrict__ out, int64_t ldo, float* __restrict__ lse, FlashPartial part,
                        int nq, int nk, int n_heads, int tiles_per_split, float scale_log2e) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps LDS/STS
-    uint8_t* q_smem = smem;                                  // [g][Q_hi | Q_lo], g = 0, 1
-    uint8_t* k_smem = q_smem + 2 * FB_Q_BYTES;               // 2 stages x (K_hi | K_lo)
+    uint8_t* k_smem = smem;                                  // 2 stages x (K_hi | K_lo)
     uint8_t* v_smem = k_smem + 2 * FB_K_STAGE;               // 2 stages x (Vt_hi | Vt_lo)
-    uint8_t* p_smem = v_smem + 2 * FB_V_STAGE;               // [g][P_hi | P_lo]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + 2 * FB_P_BUF);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + 2 * FB_V_STAGE);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1; uint64_t* k_empty = bars + 3;
     uint64_t* v_full = bars + 5; uint64_t* v_empty = bars + 7;
@@ -108,9 +116,9 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
     const int n_tiles = max(0, min(n_tiles_all, tile_begin + tiles_per_split) - tile_begin);
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tm_qhi); prefetch_tmap(&tm_qlo); prefetch_tmap(&tm_khi);
+        prefetch_tmap(&tm_khi);
         prefetch_tmap(&tm_klo); prefetch_tmap(&tm_vhi); prefetch_tmap(&tm_vlo);
-        mbar_init(q_full, 1);
+        mbar_init(q_full, 256);                                  // every softmax thread has put its Q row into TMEM
         for (int s = 0; s < 2; ++s) {
             mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
             mbar_init(&s_full[s], 1); mbar_init(&s_full[2 + s], 1); mbar_init(&p_ready[s], 128); mbar_init(&pv_full[s], 1);
@@ -124,14 +132,6 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
     const uint32_t tmem_base = *tmem_holder;
 
     if (warp == 0) {
-        if (elect_one()) {
-            mbar_arrive_expect_tx(q_full, 2 * FB_Q_BYTES);
-            for (int g = 0; g < 2; ++g) {
-                tma_load_2d(q_smem + g * FB_Q_BYTES, &tm_qhi, q_full, head * FB_DK, q0 + g * FB_BQ);
-                tma_load_2d(q_smem + g * FB_Q_BYTES + FB_BQ * 128, &tm_qlo, q_full, head * FB_DK, q0 + g * FB_BQ);
-            }
-        }
-        __syncwarp();
         for (int i = 0; i < n_tiles; ++i) {
             const int s = i & 1;
             mbar_wait(&k_empty[s], ((i >> 1) & 1) ^ 1);
@@ -159,10 +159,8 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc<Kind::BF16>(FB_BQ, 64);
-        const uint64_t dq0 = make_sdesc_k128(smem_u32(q_smem));
         const uint64_t dk0 = make_sdesc_k128(smem_u32(k_smem));
         const uint64_t dv0 = make_sdesc_k128(smem_u32(v_smem));
-        const uint64_t dp0 = make_sdesc_k128(smem_u32(p_smem));
         // S(g, i) = Q_g K(i)^T for both Q tiles; releases the K stage afterwards
         auto issue_s = [&](int i) {
             const int s = i & 1;
@@ -172,13 +170,13 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
                 const uint64_t dk = dk0 + (uint64_t)(s * (FB_K_STAGE >> 4));
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    const uint64_t dq = dq0 + (uint64_t)(g * (FB_Q_BYTES >> 4));
+                    const uint32_t tq = tmem_base + 384 + 64 * g;           // Q_g: hi words in columns [0, 32), lo in [32, 64)
                     const uint32_t ts = tmem_base + 64 * (2 * g + s);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {             // 16 dims (32 bytes) per MMA
-                        mma_ss<Kind::BF16>(ts, dq + ((FB_BQ * 128) >> 4) + 2 * kk, dk + 2 * kk, idesc, kk > 0);        // Q_lo K_hi
-                        mma_ss<Kind::BF16>(ts, dq + 2 * kk, dk + ((FB_BKV * 128) >> 4) + 2 * kk, idesc, 1);            // Q_hi K_lo
-                        mma_ss<Kind::BF16>(ts, dq + 2 * kk, dk + 2 * kk, idesc, 1);                                    // Q_hi K_hi
+                    for (int kk = 0; kk < 4; ++kk) {             // 16 dims per MMA = 8 packed columns
+                        mma_ts_bf16(ts, tq + 32 + 8 * kk, dk + 2 * kk, idesc, kk > 0);                                 // Q_lo K_hi
+                        mma_ts_bf16(ts, tq + 8 * kk, dk + ((FB_BKV * 128) >> 4) + 2 * kk, idesc, 1);                   // Q_hi K_lo
+                        mma_ts_bf16(ts, tq + 8 * kk, dk + 2 * kk, idesc, 1);                                           // Q_hi K_hi
                     }
                     tc_commit(&s_full[2 * g + s]);
                 }
@@ -187,22 +185,23 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
             __syncwarp();
         };
         mbar_wait(q_full, 0);
+        tc_fence_after();
         for (int i = 0; i < 2 && i < n_tiles; ++i) issue_s(i);
         for (int i = 0; i < n_tiles; ++i) {
             const int s = i & 1;
             mbar_wait(&v_full[s], (i >> 1) & 1);
             for (int g = 0; g < 2; ++g) {
-                mbar_wait(&p_ready[g], i & 1);                   // P_g(i) is in smem; S_g[s] is drained; O_g is rescaled if needed
+                mbar_wait(&p_ready[g], i & 1);                   // P_g(i) is in TMEM (over S_g[s]); O_g is rescaled if needed
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t dv = dv0 + (uint64_t)(s * (FB_V_STAGE >> 4));
-                    const uint64_t dp = dp0 + (uint64_t)(g * (FB_P_BUF >> 4));
+                    const uint32_t tp = tmem_base + 64 * (2 * g + s);       // P_g(i): hi words in columns [0, 32), lo in [32, 64)
                     const uint32_t tpv = tmem_base + 256 + 64 * g;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {             // 16 keys per MMA
-                        mma_ss<Kind::BF16>(tpv, dp + ((FB_BQ * 128) >> 4) + 2 * kk, dv + 2 * kk, idesc, (kk > 0) || (i > 0));   // P_lo V_hi
-                        mma_ss<Kind::BF16>(tpv, dp + 2 * kk, dv + ((FB_DK * 128) >> 4) + 2 * kk, idesc, 1);            // P_hi V_lo
-                        mma_ss<Kind::BF16>(tpv, dp + 2 * kk, dv + 2 * kk, idesc, 1);                                   // P_hi V_hi
+                    for (int kk = 0; kk < 4; ++kk) {             // 16 keys per MMA = 8 packed columns
+                        mma_ts_bf16(tpv, tp + 32 + 8 * kk, dv + 2 * kk, idesc, (kk > 0) || (i > 0));                  // P_lo V_hi
+                        mma_ts_bf16(tpv, tp + 8 * kk, dv + ((FB_DK * 128) >> 4) + 2 * kk, idesc, 1);                   // P_hi V_lo
+                        mma_ts_bf16(tpv, tp + 8 * kk, dv + 2 * kk, idesc, 1);                                          // P_hi V_hi
                     }
                     tc_commit(&pv_full[g]);
                     if (g == 1) tc_commit(&v_empty[s]);
@@ -218,9 +217,6 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
         const int row = q0 + g * FB_BQ + row_l;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         const uint32_t t_pv = tmem_base + 256 + 64 * g;
-        uint8_t* p_hi = p_smem + g * FB_P_BUF + row_l * 128;
-        uint8_t* p_lo = p_hi + FB_BQ * 128;
-        const int sw = row_l & 7;
         // The output accumulator O_g stays in TMEM: the P.V products of all tiles accumulate there (tensor-core fp32
         // accumulation), so a tile costs this thread no TMEM read-back and no 64 FMAs, and 64 registers are free for the
         // exp / split pipeline. The running maximum is LAZY: it only moves (and O, l are rescaled through a TMEM
@@ -228,6 +224,23 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
         // <= 256, exactly representable in the bf16 pair, and l accumulates with the same stale reference.
         float m_run = -FLT_MAX, l_run = 0.f;
         constexpr float kRescaleAbove = 8.f;                     // log2 units
+        // Q_g lives in TMEM as the A operand of S = Q K^T (TS MMA): an SS MMA of this shape reads 4 KB of Q and 2 KB of K
+        // from shared memory for 32 clocks of math - 48 clocks at 128 B/clk, which is what the S products were paced by.
+        // Each thread copies its own query row (64 dims = 32 packed words, hi and lo) from global memory, once.
+        {
+            uint32_t qw[32];
+            const uint4* src_hi = reinterpret_cast<const uint4*>(q_hi + (int64_t)min(row, nq - 1) * ldq + head * FB_DK);
+            const uint4* src_lo = reinterpret_cast<const uint4*>(q_lo + (int64_t)min(row, nq - 1) * ldq + head * FB_DK);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const uint4 t = __ldg(src_hi + u); qw[4 * u] = t.x; qw[4 * u + 1] = t.y; qw[4 * u + 2] = t.z; qw[4 * u + 3] = t.w; }
+            tmem_st_32(tmem_base + 384 + 64 * g + lane_off, qw);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const uint4 t = __ldg(src_lo + u); qw[4 * u] = t.x; qw[4 * u + 1] = t.y; qw[4 * u + 2] = t.z; qw[4 * u + 3] = t.w; }
+            tmem_st_32(tmem_base + 384 + 64 * g + lane_off + 32, qw);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(q_full);
+        }
         for (int i = 0; i < n_tiles; ++i) {
             const int k0 = (tile_begin + i) * FB_BKV;
             uint32_t r[32], r2[32];
@@ -253,7 +266,36 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
             const float m_cand = fmaxf(m_run, mx * scale_log2e);
             const bool rescale = __any_sync(0xffffffffu, m_cand > m_run + kRescaleAbove);     // warp-uniform (TMEM ops are collective)
             const float m_new = rescale ? m_cand : m_run;
-            if (i > 0) {                                         // P.V(i-1) retired: O_g is stable and the P_g buffer is free
+            const float neg_m = -m_new;
+            float rsp[4] = {0.f, 0.f, 0.f, 0.f};
+            // p = 2^(s * scale - m) -> bf16 (hi, lo) pair, packed two keys per word, written over this row's S columns:
+            // r <- hi words of keys 0..63 (32 words), r2 <- lo words
+            uint32_t ph[32], pl[32];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {                   // two keys per packed word
+                    const uint32_t sa = half ? r2[2 * c] : r[2 * c], sb = half ? r2[2 * c + 1] : r[2 * c + 1];
+                    const float pa = fb_ex2(fmaf(__uint_as_float(sa), scale_log2e, neg_m));
+                    const float pb = fb_ex2(fmaf(__uint_as_float(sb), scale_log2e, neg_m));
+                    rsp[c & 3] += pa + pb;
+                    // bf16 pair by TRUNCATION, three ops per value: hi = upper 16 bits of p (the byte permute takes them
+                    // straight from the fp32 bit patterns), lo = upper 16 bits of p - hi (exact in fp32). hi + lo misses p by
+                    // less than 2^-16 p, always from below: a -8e-6 relative bias of the weights against the exactly
+                    // summed l, two orders inside the parity budget - and 40 % fewer instructions than rounding both
+                    // halves in the loop that paces this kernel.
+                    const uint32_t ua = __float_as_uint(pa), ub = __float_as_uint(pb);
+                    const float la = pa - __uint_as_float(ua & 0xffff0000u), lb = pb - __uint_as_float(ub & 0xffff0000u);
+                    ph[half * 16 + c] = __byte_perm(ua, ub, 0x7632);     // {pb.hi16, pa.hi16}: low half = even key
+                    pl[half * 16 + c] = __byte_perm(__float_as_uint(la), __float_as_uint(lb), 0x7632);
+                }
+            }
+            tmem_st_32(t_s + lane_off, ph);
+            tmem_st_32(t_s + lane_off + 32, pl);
+            tmem_st_wait();
+            if (i > 0) {
+                // P.V(i-1) was issued a whole tile ago: this wait is normally free. It orders the (rare) rescale of O_g
+                // between P.V(i-1) and P.V(i), and keeps this thread in step with the barrier's phases.
                 mbar_wait(&pv_full[g], (i - 1) & 1);
                 tc_fence_after();
                 if (rescale) {
@@ -270,39 +312,8 @@ flash_attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_
                     tmem_st_wait();
                     l_run *= corr;
                 }
-                tc_fence_before();
             }
-            const float neg_m = -m_new;
-            float rsp[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {                    // 8 keys = one 16-byte chunk of the P row
-                    float p[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const uint32_t sv = half ? r2[c * 8 + u] : r[c * 8 + u];
-                        p[u] = fb_ex2(fmaf(__uint_as_float(sv), scale_log2e, neg_m));
-                        rsp[u & 3] += p[u];
-                    }
-                    uint32_t h[4], l[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        // bf16 split with full-rate integer ops (the conversion pipe is shared with ex2): round half up
-                        // on the magnitude, keep the upper 16 bits; lo = p - hi is exact in fp32 and rounded the same way
-                        const uint32_t ha = (__float_as_uint(p[2 * u]) + 0x8000u) & 0xffff0000u;
-                        const uint32_t hb = (__float_as_uint(p[2 * u + 1]) + 0x8000u) & 0xffff0000u;
-                        const uint32_t la = __float_as_uint(p[2 * u] - __uint_as_float(ha)) + 0x8000u;
-                        const uint32_t lb = __float_as_uint(p[2 * u + 1] - __uint_as_float(hb)) + 0x8000u;
-                        h[u] = __byte_perm(ha, hb, 0x7632);      // {hb.hi16, ha.hi16}: lower address = even key
-                        l[u] = __byte_perm(la, lb, 0x7632);
-                    }
-                    const int pos = (((half * 4 + c) ^ sw) << 4);
-                    *reinterpret_cast<uint4*>(p_hi + pos) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4*>(p_lo + pos) = make_uint4(l[0], l[1], l[2], l[3]);
-                }
-            }
-            fence_proxy_async();                                 // generic smem writes -> visible to the tensor core
+            tc_fence_before();
             mbar_arrive(&p_ready[g]);
             l_run += (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
             m_run = m_new;
@@ -408,10 +419,10 @@ int flash_attn_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq, con
     int splits = 1;
     const size_t need = flash_attn_bf16_workspace_bytes(nq, nk, n_heads, &splits);
     if (need > 0 && (!workspace || workspace_bytes < need)) return VLSAT_ERR_WORKSPACE;
-    CUtensorMap tq, tql, tk, tkl, tv, tvl;
+    CUtensorMap tk, tkl, tv, tvl;
     const uint64_t d = (uint64_t)n_heads * dk;
     const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    bool ok = make_tmap_2d(&tq, q_hi, BF, 2, nq, d, ldq, 64, FB_BQ) && make_tmap_2d(&tql, q_lo, BF, 2, nq, d, ldq, 64, FB_BQ) &&
+    bool ok =
               make_tmap_2d(&tk, k_hi, BF, 2, nk, d, ldk, 64, FB_BKV) && make_tmap_2d(&tkl, k_lo, BF, 2, nk, d, ldk, 64, FB_BKV) &&
               make_tmap_2d(&tv, vt_hi, BF, 2, d, nk, ldvt, 64, FB_DK) && make_tmap_2d(&tvl, vt_lo, BF, 2, d, nk, ldvt, 64, FB_DK);
     if (!ok) return VLSAT_ERR_UNSUPPORTED;
@@ -423,11 +434,11 @@ int flash_attn_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq, con
     }
     const int n_tiles = (int)ceil_div(nk, FB_BKV);
     const int tiles_per_split = (int)ceil_div(n_tiles, splits);
-    const size_t smem = 2 * FB_Q_BYTES + 2 * FB_K_STAGE + 2 * FB_V_STAGE + 2 * FB_P_BUF + 1024 + 256;
+    const size_t smem = 2 * FB_K_STAGE + 2 * FB_V_STAGE + 1024 + 256;
     cudaFuncSetAttribute(flash_attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((unsigned)ceil_div(nq, 2 * FB_BQ), (unsigned)n_heads, (unsigned)splits);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)dk);
-    flash_attn_bf16_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tql, tk, tkl, tv, tvl, out, ldo, lse, part, (int)nq, (int)nk,
+    flash_attn_bf16_kernel<<<grid, FB_THREADS, smem, st>>>(q_hi, q_lo, ldq, tk, tkl, tv, tvl, out, ldo, lse, part, (int)nq, (int)nk,
                                                            n_heads, tiles_per_split, scale_log2e);
     int launches = 1;
     if (splits > 1) {
