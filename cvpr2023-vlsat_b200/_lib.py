@@ -54,7 +54,7 @@ SIGNATURES = {
     "vlsat_flash_attn_tc_fwd": [vp, vp, i64, vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp],
     "vlsat_gat_edge_tc_fwd": [vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, i32,
                               vp, i64, vp, vp, sz, i32, vp],
-    "vlsat_permute_rows": [vp, i64, vp, i64, i32, vp, i64, i32, vp],
+    "vlsat_permute_rows": [vp, i64, vp, i64, i32, vp, i64, i32, vp, vp, vp],
     "vlsat_permute_edges": [vp, vp, i64, vp, vp],
     "vlsat_bf16_split": [vp, i64, i64, i64, vp, vp, i64, vp],
     "vlsat_flash_attn_bf16x3_fwd": [vp, vp, i64, vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, sz, vp],

@@ -418,15 +418,24 @@ __global__ void gat_finalize_kernel(int* __restrict__ enc, float* __restrict__ x
     xx[n * ld_xx + f] = (v == INT_MIN) ? 0.f : __int_as_float(v >= 0 ? v : v ^ 0x7fffffff);
 }
 
-// out[i, :] = in[idx[i], :]  (gather == 1)   or   out[idx[i], :] = in[i, :]  (gather == 0)
+// out[i, :] = in[idx[i], :]  (gather == 1)   or   out[idx[i], :] = in[i, :]  (gather == 0); optionally also the bf16
+// (hi, lo) pair of the permuted rows (compact [rows, cols]), the operand format of the projections that read them next
 __global__ void permute_rows_kernel(const float* __restrict__ in, int64_t ld_in, const int32_t* __restrict__ idx,
-                                    int64_t rows, int cols4, float* __restrict__ out, int64_t ld_out, int gather) {
+                                    int64_t rows, int cols4, float* __restrict__ out, int64_t ld_out, int gather,
+                                    uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * cols4) return;
     const int64_t i = t / cols4; const int c = (int)(t % cols4) * 4;
     const int64_t j = idx[i];
     const int64_t ri = gather ? j : i, ro = gather ? i : j;
-    *reinterpret_cast<float4*>(out + ro * ld_out + c) = __ldg(reinterpret_cast<const float4*>(in + ri * ld_in + c));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in + ri * ld_in + c));
+    *reinterpret_cast<float4*>(out + ro * ld_out + c) = v;
+    if (hi) {
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2(v.x, v.y, h0, l0); split_bf16x2(v.z, v.w, h1, l1);
+        *reinterpret_cast<uint2*>(hi + ro * (int64_t)cols4 * 4 + c) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(lo + ro * (int64_t)cols4 * 4 + c) = make_uint2(l0, l1);
+    }
 }
 __global__ void permute_edges_kernel(const int64_t* __restrict__ ei, const int32_t* __restrict__ perm, int64_t n_edges, int64_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -441,13 +450,16 @@ __global__ void permute_edges_kernel(const int64_t* __restrict__ ei, const int32
 using namespace vlsat;
 
 extern "C" int vlsat_permute_rows(const float* in, int64_t ld_in, const int32_t* idx, int64_t rows, int cols,
-                                  float* out, int64_t ld_out, int gather, void* stream) {
+                                  float* out, int64_t ld_out, int gather, void* split_hi, void* split_lo, void* stream) {
     VLSAT_REQUIRE(rows >= 0 && cols >= 0);
     if (rows == 0 || cols == 0) return VLSAT_OK;
     VLSAT_REQUIRE(in && idx && out && ld_in >= cols && ld_out >= cols);
     VLSAT_SUPPORT(cols % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0));
     const int64_t n = rows * (cols / 4);
-    permute_rows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, idx, rows, cols / 4, out, ld_out, gather);
+    VLSAT_REQUIRE((split_hi == nullptr) == (split_lo == nullptr));
+    VLSAT_SUPPORT(!split_hi || (((uintptr_t)split_hi | (uintptr_t)split_lo) % 8 == 0));
+    permute_rows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, idx, rows, cols / 4, out, ld_out, gather,
+                                                                                      (uint16_t*)split_hi, (uint16_t*)split_lo);
     return finish_launch();
 }
 

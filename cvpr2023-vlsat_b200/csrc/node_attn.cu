@@ -302,7 +302,8 @@ node_attn_scene_kernel(const float* __restrict__ q, int64_t ldq, const float* __
                        const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_end, int H,
                        float* __restrict__ out, int64_t ldo, int64_t n_nodes) {
     const int hh = blockIdx.y;
-    constexpr int LD = DK + 1;                        // padded rows: lanes reading one column of 32 rows hit 32 banks
+    constexpr int LD = DK + 4;                        // 16-byte aligned rows whose stride is 4 banks off a multiple of 32:
+                                                      // eight lanes reading float4s of eight consecutive rows cover all 32 banks
     extern __shared__ __align__(16) float sm[];
     float* qs = sm; float* ks = qs + NS_MAX * LD; float* vs = ks + NS_MAX * LD;
     float (*ps)[NS_MAX] = reinterpret_cast<float (*)[NS_MAX]>(vs + NS_MAX * LD);      // [warps][NS_MAX]
@@ -313,13 +314,9 @@ node_attn_scene_kernel(const float* __restrict__ q, int64_t ldq, const float* __
     __syncthreads();                                  // the previous scene's rows are no longer read
     for (int i = tid; i < ns * (DK / 4); i += NS_THREADS) {
         const int row = i / (DK / 4), c4 = i % (DK / 4);
-        const float4 q4 = __ldg(reinterpret_cast<const float4*>(q + (int64_t)(s0 + row) * ldq + hh * DK) + c4);
-        const float4 k4 = __ldg(reinterpret_cast<const float4*>(k + (int64_t)(s0 + row) * ldk + hh * DK) + c4);
-        const float4 v4 = __ldg(reinterpret_cast<const float4*>(v + (int64_t)(s0 + row) * ldv + hh * DK) + c4);
-        float* qd = qs + row * LD + c4 * 4; float* kd = ks + row * LD + c4 * 4; float* vd = vs + row * LD + c4 * 4;
-        qd[0] = q4.x; qd[1] = q4.y; qd[2] = q4.z; qd[3] = q4.w;
-        kd[0] = k4.x; kd[1] = k4.y; kd[2] = k4.z; kd[3] = k4.w;
-        vd[0] = v4.x; vd[1] = v4.y; vd[2] = v4.z; vd[3] = v4.w;
+        *reinterpret_cast<float4*>(qs + row * LD + c4 * 4) = __ldg(reinterpret_cast<const float4*>(q + (int64_t)(s0 + row) * ldq + hh * DK) + c4);
+        *reinterpret_cast<float4*>(ks + row * LD + c4 * 4) = __ldg(reinterpret_cast<const float4*>(k + (int64_t)(s0 + row) * ldk + hh * DK) + c4);
+        *reinterpret_cast<float4*>(vs + row * LD + c4 * 4) = __ldg(reinterpret_cast<const float4*>(v + (int64_t)(s0 + row) * ldv + hh * DK) + c4);
     }
     __syncthreads();
     const float scale = rsqrtf((float)DK);
@@ -333,12 +330,13 @@ node_attn_scene_kernel(const float* __restrict__ q, int64_t ldq, const float* __
             const int j = lane + 32 * r;
             float s = -FLT_MAX;
             if (j < ns) {
-                const float* kj = ks + j * LD;
+                const float4* kj = reinterpret_cast<const float4*>(ks + j * LD);
+                const float4* q4 = reinterpret_cast<const float4*>(qi);
                 float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
-                for (int d = 0; d < DK; d += 4) {
-                    d0 = fmaf(qi[d], kj[d], d0); d1 = fmaf(qi[d + 1], kj[d + 1], d1);
-                    d2 = fmaf(qi[d + 2], kj[d + 2], d2); d3 = fmaf(qi[d + 3], kj[d + 3], d3);
+                for (int d = 0; d < DK / 4; ++d) {
+                    const float4 kv = kj[d], qv = q4[d];
+                    d0 = fmaf(qv.x, kv.x, d0); d1 = fmaf(qv.y, kv.y, d1); d2 = fmaf(qv.z, kv.z, d2); d3 = fmaf(qv.w, kv.w, d3);
                 }
                 s = ((d0 + d1) + (d2 + d3)) * scale + __ldg(bias + (int64_t)j * H);
             }
@@ -429,7 +427,7 @@ extern "C" int vlsat_node_attn_scene_fwd(const float* q, int64_t ldq, const floa
     if (n_nodes == 0) return VLSAT_OK;
     const dim3 grid((unsigned)ceil_div(n_nodes, NS_CAND), (unsigned)n_heads);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = sizeof(float) * (3 * NS_MAX * (dk + 1) + (NS_THREADS / 32) * NS_MAX);
+    const size_t smem = sizeof(float) * (3 * NS_MAX * (dk + 4) + (NS_THREADS / 32) * NS_MAX);
     if (dk == 64) {
         cudaFuncSetAttribute(node_attn_scene_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         node_attn_scene_kernel<64><<<grid, NS_THREADS, smem, st>>>(q, ldq, k, ldk, v, ldv, table, seg_start, seg_end, n_heads, out, ldo, n_nodes);

@@ -95,11 +95,15 @@ class GraphContext:
             self._head_rows[num_heads] = r
         return r
 
-    def to_sorted(self, edge_rows: torch.Tensor) -> torch.Tensor:
-        return ops.permute_rows(edge_rows, self.perm, gather=True) if self.num_edges else edge_rows
+    def to_sorted(self, edge_rows: torch.Tensor, emit_split: bool = False):
+        if not self.num_edges:
+            return (edge_rows, None) if emit_split else edge_rows
+        return ops.permute_rows(edge_rows, self.perm, gather=True, emit_split=emit_split)
 
-    def to_original(self, edge_rows: torch.Tensor) -> torch.Tensor:
-        return ops.permute_rows(edge_rows, self.perm, gather=False) if self.num_edges else edge_rows
+    def to_original(self, edge_rows: torch.Tensor, emit_split: bool = False):
+        if not self.num_edges:
+            return (edge_rows, None) if emit_split else edge_rows
+        return ops.permute_rows(edge_rows, self.perm, gather=False, emit_split=emit_split)
 
 
 class Gen_Index(nn.Module):

@@ -65,10 +65,10 @@ class MMG(nn.Module):
         ctx = self.scene_context(batch_ids, obj_center)
         g = GraphContext(edge_index, n, self.flow)
         o3, o2 = obj_feature_3d.contiguous(), obj_feature_2d.contiguous()
-        e3, e2 = g.to_sorted(edge_feature_3d.contiguous()), g.to_sorted(edge_feature_2d.contiguous())   # CSR edge order
+        (e3, e3p), (e2, e2p) = g.to_sorted(edge_feature_3d.contiguous(), True), g.to_sorted(edge_feature_2d.contiguous(), True)   # CSR edge order
         # (hi, lo) pairs of the four streams travel with them: every producer that feeds a projection emits the pair from
         # its epilogue, so no activation is read back just to be split
-        o3p = o2p = e3p = e2p = None
+        o3p = o2p = None
         for i in range(self.depth):
             act = (i < self.depth - 1) or self.depth == 1          # ReLU(+Dropout) after this layer
             cat3 = torch.empty((n, dn + da), device=o3.device, dtype=torch.float32)
@@ -84,7 +84,9 @@ class MMG(nn.Module):
                 e3, e3p = ops.relu(e3_raw, emit_split=True)
             else:
                 e3, e3p = e3_raw, self.gcn_3ds[i].edgeatten.last_edge_split
-        return o3, o2, g.to_original(e3), g.to_original(e2)
+        (e3o, e3op), (e2o, e2op) = g.to_original(e3, True), g.to_original(e2, True)
+        self.last_edge_pairs = (e3op, e2op)          # (hi, lo) pairs of the two returned edge features, for the caller's projections
+        return o3, o2, e3o, e2o
 
 
 class GraphEdgeAttenNetworkLayers(nn.Module):

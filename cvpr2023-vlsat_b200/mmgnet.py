@@ -197,8 +197,10 @@ class Mmgnet(nn.Module):
                            gather=(ab[:, :hid], edge_indices[0].contiguous(), ab[:, hid:], edge_indices[1].contiguous()))
             gcn_edge_feature_2d_dis = ops.linear(h, p3.weight.detach(), p3.bias.detach())
 
-        rel_cls_3d = self.rel_predictor_3d(ge3)
-        rel_cls_2d = self.rel_predictor_2d(ge2)
+        ge3p, ge2p = getattr(self.mmg, "last_edge_pairs", (None, None))
+        rel_cls_3d = self.rel_predictor_3d(ge3, x_split=ge3p)
+        rel_cls_2d = self.rel_predictor_2d(ge2, x_split=ge2p)
+        self.mmg.last_edge_pairs = (None, None)
 
         scale = self.obj_logit_scale.detach().reshape(1)
         obj_logits_3d = ops.linear(ops.row_l2norm(g3), self.obj_predictor_3d.weight.detach(),

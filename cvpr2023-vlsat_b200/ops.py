@@ -582,15 +582,22 @@ def gat_edge(q, v, k, edge_index, row_ptr, perm, c1, c1b, c2, c2b, n_heads: int,
     return out, prob, arg
 
 
-def permute_rows(x: torch.Tensor, idx: torch.Tensor, gather: bool = True) -> torch.Tensor:
-    """gather: out[i] = x[idx[i]];  scatter (gather=False): out[idx[i]] = x[i].  idx int32 permutation."""
+def permute_rows(x: torch.Tensor, idx: torch.Tensor, gather: bool = True, emit_split: bool = False):
+    """gather: out[i] = x[idx[i]];  scatter (gather=False): out[idx[i]] = x[i].  idx int32 permutation.
+    ``emit_split=True``: also return the bf16 (hi, lo) pair of the result (or None when not applicable): ``(out, pair)``."""
     xp, ldx = _rows(x, "x")
     m, d = x.shape
     out = torch.empty((m, d), device=x.device, dtype=torch.float32)
     if idx.dtype != torch.int32 or not idx.is_cuda:
         raise TypeError("permute_rows: idx must be a CUDA int32 tensor")
-    _lib.check(_call("vlsat_permute_rows", xp, ldx, idx.data_ptr(), m, d, out.data_ptr(), d, int(gather), _stream()),
+    pair = None
+    if emit_split and d % 8 == 0 and tensor_cores_enabled() and default_fmt(d) == FMT_BF16:
+        pair = torch.empty((2, m, d), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_call("vlsat_permute_rows", xp, ldx, idx.data_ptr(), m, d, out.data_ptr(), d, int(gather),
+                     pair[0].data_ptr() if pair is not None else None, pair[1].data_ptr() if pair is not None else None, _stream()),
                "vlsat_permute_rows")
+    if emit_split:
+        return out, ((pair[0], pair[1]) if pair is not None else None)
     return out
 
 

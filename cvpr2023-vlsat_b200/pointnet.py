@@ -90,10 +90,11 @@ class PointNetRelClsMulti(nn.Module):
         if init_weights:
             _init_xavier_normal(self)
 
-    def forward(self, x):
+    def forward(self, x, x_split=None):
+        """``x_split``: (hi, lo) pair of x when its producer emitted one (inference path)."""
         from . import train_path as T
         if T.differentiable(self):
             return T.rel_classifier(self, x)
-        return ops.linear_chain(x, [(self.fc1.weight.detach(), self.fc1.bias.detach(), ops.ACT_RELU),
+        return ops.linear_chain(x, x_split=x_split, layers=[(self.fc1.weight.detach(), self.fc1.bias.detach(), ops.ACT_RELU),
                                     (self.fc2.weight.detach(), self.fc2.bias.detach(), ops.ACT_RELU),
                                     (self.fc3.weight.detach(), self.fc3.bias.detach(), ops.ACT_SIGMOID)])

@@ -253,9 +253,10 @@ int vlsat_gat_edge_tc_fwd(const void* k_hi, const void* k_lo, const float* qc, i
                           int workspace_ready, void* stream);
 
 /* Edge-order bookkeeping (bit-exact): out[i,:] = in[idx[i],:] (gather=1) or out[idx[i],:] = in[i,:] (gather=0)
- * for fp32 rows (cols % 4 == 0), and out[:, i] = edge_index[:, perm[i]] for the int64 [2, E] edge list. */
+ * for fp32 rows (cols % 4 == 0), and out[:, i] = edge_index[:, perm[i]] for the int64 [2, E] edge list.
+ * split_hi / split_lo (nullable): also write the bf16 (hi, lo) pair of the permuted rows, compact [rows, cols]. */
 int vlsat_permute_rows(const float* in, int64_t ld_in, const int32_t* idx, int64_t rows, int cols,
-                       float* out, int64_t ld_out, int gather, void* stream);
+                       float* out, int64_t ld_out, int gather, void* split_hi, void* split_lo, void* stream);
 int vlsat_permute_edges(const int64_t* edge_index, const int32_t* perm, int64_t n_edges, int64_t* out, void* stream);
 
 /* ================================================================================================
