@@ -1,12 +1,13 @@
 // A1 on the tensor cores: fused PointNet encoder (c_in -> 64 -> 128 -> c_out, ReLU after every layer, max
-// over the points of an object), fp32-accurate via 3xTF32, no TMA: every operand is produced on chip.
+// over the points of an object), BF16x3 (bf16 (hi, lo) pairs, three kind::f16 MMAs per K step: ~1e-5 relative, see
+// csrc/gemm_tc.cu), no TMA: every operand is produced on chip.
 //
 // Orientation: channels on the TMEM lanes, points on the columns, so the max over points is a per-thread
 // running maximum (no cross-lane reduction):
 //   D2[c2 = 128 lanes][64 pts] = W2 (A operand, TMEM resident, hi/lo)  x  h1^T (B operand, smem, K-major)
 //   D3[ch = 128 lanes][64 pts] = W3 chunk (A operand, TMEM resident)   x  h2^T (B operand, smem, K-major)
 // A CTA is stationary on one 128-channel chunk of W3 and walks over objects; per 64-point tile:
-//   workers (4 warps)  layer 1 in FFMA -> h1 tile as tf32 hi/lo in the 128B-swizzled UMMA layout
+//   workers (4 warps)  layer 1 in FFMA -> h1 tile as bf16 hi/lo in the 128B-swizzled UMMA layout
 //   MMA warp           MMA2 -> D2
 //   workers            h2 = relu(D2 + b2) -> hi/lo -> swizzled smem (transposing store, conflict free)
 //   MMA warp           MMA3 -> D3
@@ -14,6 +15,7 @@
 // Layers 1-2 are recomputed by the c_out/128 chunk CTAs of an object (8% of the FLOPs, on the tensor pipe).
 // HBM traffic: the points once per chunk CTA (L2 hits after the first) and c_out floats per object.
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "tc_common.cuh"
 #include <float.h>
 #include <algorithm>
@@ -26,8 +28,9 @@ using namespace tc;
 constexpr int PT_THREADS = 160;          // warp 0: MMA issue + TMEM; warps 1..4: workers (TMEM lane quarter = warp & 3)
 constexpr int PT_TP = 64;                // points per tile
 constexpr int PT_C1 = 64, PT_C2 = 128, PT_CIN_MAX = 16;
-// TMEM columns: W3 hi [0,128) lo [128,256) | W2 hi [256,320) lo [320,384) | D2 [384,448) | D3 [448,512)
-constexpr uint32_t PT_W3HI = 0, PT_W3LO = 128, PT_W2HI = 256, PT_W2LO = 320, PT_D2 = 384, PT_D3 = 448;
+// TMEM columns (bf16 A operands: two K elements per 32-bit column):
+//   W3 hi [0,64) lo [64,128) | W2 hi [128,160) lo [160,192) | D2 [192,256) | D3 [256,320)
+constexpr uint32_t PT_W3HI = 0, PT_W3LO = 64, PT_W2HI = 128, PT_W2LO = 160, PT_D2 = 192, PT_D3 = 256;
 
 __device__ __forceinline__ void pt_tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -43,20 +46,22 @@ __device__ __forceinline__ void pt_tmem_st32(uint32_t taddr, const uint32_t (&r)
 __device__ __forceinline__ void pt_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void pt_split(float v, uint32_t& hi, uint32_t& lo) {
-    hi = tc::tf32_rna_bits(v);
-    lo = __float_as_uint(v - __uint_as_float(hi));
+// one value -> bf16 hi / lo halves (round half up on the magnitude, see split_bf16x2)
+__device__ __forceinline__ void pt_split16(float v, uint16_t& hi, uint16_t& lo) {
+    const uint32_t h = (__float_as_uint(v) + 0x8000u) & 0xffff0000u;
+    hi = (uint16_t)(h >> 16);
+    lo = (uint16_t)((__float_as_uint(v - __uint_as_float(h)) + 0x8000u) >> 16);
 }
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 struct PointNetTcSmem {
-    uint8_t b1_hi[2 * PT_TP * 128];      // h1 tile  [64 pts][64 k]  as 2 k-blocks of 64 rows x 128 B (swizzled)
-    uint8_t b1_lo[2 * PT_TP * 128];
-    uint8_t b2_hi[4 * PT_TP * 128];      // h2 tile  [64 pts][128 k] as 4 k-blocks
-    uint8_t b2_lo[4 * PT_TP * 128];
+    uint8_t b1_hi[PT_TP * 128];          // h1 tile  [64 pts][64 k] bf16: one k-block of 64 rows x 128 B (swizzled)
+    uint8_t b1_lo[PT_TP * 128];
+    uint8_t b2_hi[2 * PT_TP * 128];      // h2 tile  [64 pts][128 k] bf16: 2 k-blocks
+    uint8_t b2_lo[2 * PT_TP * 128];
     float xs[PT_CIN_MAX][PT_TP];
     float w1[PT_C1][PT_CIN_MAX];
     float b1[PT_C1];
@@ -97,7 +102,7 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
 
     if (warp == 0) {
         // ------------------------------------------------------------------ MMA issue (one elected lane)
-        constexpr uint32_t idesc = make_idesc<Kind::TF32>(128, PT_TP);
+        constexpr uint32_t idesc = make_idesc<Kind::BF16>(128, PT_TP);
         const uint64_t d_b1hi = make_sdesc_k128(smem_u32(s.b1_hi)), d_b1lo = make_sdesc_k128(smem_u32(s.b1_lo));
         const uint64_t d_b2hi = make_sdesc_k128(smem_u32(s.b2_hi)), d_b2lo = make_sdesc_k128(smem_u32(s.b2_lo));
         for (int it = 0; it < total_it; ++it) {
@@ -106,7 +111,7 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < PT_C1 / 8; ++kk) {
+                for (int kk = 0; kk < PT_C1 / 16; ++kk) {           // 16 channels per MMA = 8 packed TMEM columns = 32 smem bytes
                     const uint32_t ob = (kk >> 2) * ((PT_TP * 128) >> 4) + (kk & 3) * 2;
                     pt_mma_ts(tm + PT_D2, tm + PT_W2LO + kk * 8, d_b1hi + ob, idesc, kk > 0);
                     pt_mma_ts(tm + PT_D2, tm + PT_W2HI + kk * 8, d_b1lo + ob, idesc, 1);
@@ -119,7 +124,7 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < PT_C2 / 8; ++kk) {
+                for (int kk = 0; kk < PT_C2 / 16; ++kk) {
                     const uint32_t ob = (kk >> 2) * ((PT_TP * 128) >> 4) + (kk & 3) * 2;
                     pt_mma_ts(tm + PT_D3, tm + PT_W3LO + kk * 8, d_b2hi + ob, idesc, kk > 0);
                     pt_mma_ts(tm + PT_D3, tm + PT_W3HI + kk * 8, d_b2lo + ob, idesc, 1);
@@ -141,16 +146,14 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
         {
             uint32_t hi[32], lo[32];
             const float* w2row = w2 + (int64_t)l * PT_C1;
-            for (int c0 = 0; c0 < PT_C1; c0 += 32) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) pt_split(__ldg(w2row + c0 + j), hi[j], lo[j]);
-                pt_tmem_st32(tm + PT_W2HI + lane_off + c0, hi);
-                pt_tmem_st32(tm + PT_W2LO + lane_off + c0, lo);
-            }
+            for (int j = 0; j < 32; ++j) split_bf16x2(__ldg(w2row + 2 * j), __ldg(w2row + 2 * j + 1), hi[j], lo[j]);
+            pt_tmem_st32(tm + PT_W2HI + lane_off, hi);
+            pt_tmem_st32(tm + PT_W2LO + lane_off, lo);
             const float* w3row = w3 + ((int64_t)chunk * 128 + l) * PT_C2;
-            for (int c0 = 0; c0 < PT_C2; c0 += 32) {
+            for (int c0 = 0; c0 < PT_C2 / 2; c0 += 32) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) pt_split(__ldg(w3row + c0 + j), hi[j], lo[j]);
+                for (int j = 0; j < 32; ++j) split_bf16x2(__ldg(w3row + 2 * (c0 + j)), __ldg(w3row + 2 * (c0 + j) + 1), hi[j], lo[j]);
                 pt_tmem_st32(tm + PT_W3HI + lane_off + c0, hi);
                 pt_tmem_st32(tm + PT_W3LO + lane_off + c0, lo);
             }
@@ -185,21 +188,26 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
             float xv[CIN > 0 ? CIN : PT_CIN_MAX];
 #pragma unroll
             for (int d = 0; d < (CIN > 0 ? CIN : PT_CIN_MAX); ++d) xv[d] = (d < c_in) ? s.xs[d][p_own] : 0.f;
-            uint8_t* rowh = s.b1_hi + khalf * (PT_TP * 128) + p_own * 128;
-            uint8_t* rowl = s.b1_lo + khalf * (PT_TP * 128) + p_own * 128;
+            uint8_t* rowh = s.b1_hi + p_own * 128;               // row = point, 64 channels x bf16 = 128 bytes
+            uint8_t* rowl = s.b1_lo + p_own * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {                        // 8 chunks of 4 channels = one 16-byte unit each
+            for (int c = 0; c < 4; ++c) {                        // 4 chunks of 8 channels = one 16-byte unit each
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int k = khalf * 32 + c * 4 + u;
-                    float acc = s.b1[k];
+                    float a2[2];
 #pragma unroll
-                    for (int d = 0; d < (CIN > 0 ? CIN : PT_CIN_MAX); ++d)
-                        if (CIN > 0 || d < c_in) acc = fmaf(s.w1[k][d], xv[d], acc);
-                    pt_split(fmaxf(acc, 0.f), hi[u], lo[u]);
+                    for (int v = 0; v < 2; ++v) {
+                        const int k = khalf * 32 + c * 8 + u * 2 + v;
+                        float acc = s.b1[k];
+#pragma unroll
+                        for (int d = 0; d < (CIN > 0 ? CIN : PT_CIN_MAX); ++d)
+                            if (CIN > 0 || d < c_in) acc = fmaf(s.w1[k][d], xv[d], acc);
+                        a2[v] = fmaxf(acc, 0.f);
+                    }
+                    split_bf16x2(a2[0], a2[1], hi[u], lo[u]);
                 }
-                const int pos = (c ^ (p_own & 7)) * 16;           // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+                const int pos = ((khalf * 4 + c) ^ (p_own & 7)) * 16;   // 128B swizzle: 16-byte chunk index XOR (row mod 8)
                 *reinterpret_cast<uint4*>(rowh + pos) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4*>(rowl + pos) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
@@ -222,28 +230,28 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
             mbar_wait(d2_full, ph);
             tc_fence_after();
             {
-                uint8_t* bh = s.b2_hi + (l >> 5) * (PT_TP * 128);
-                uint8_t* bl = s.b2_lo + (l >> 5) * (PT_TP * 128);
-                const int cb = (l & 31) * 4;                     // byte offset of channel l inside its 128-byte row
+                uint8_t* bh = s.b2_hi + (l >> 6) * (PT_TP * 128);         // k-block of channel l (64 bf16 channels per 128-byte row)
+                uint8_t* bl = s.b2_lo + (l >> 6) * (PT_TP * 128);
+                const int chunk16 = (l & 63) >> 3, cb = (l & 7) * 2;      // 16-byte chunk of channel l inside the row, byte inside it
                 uint32_t a0[32], a1[32];
                 tmem_ld_32x32(tm + PT_D2 + lane_off, a0);
                 tmem_ld_32x32(tm + PT_D2 + lane_off + 32, a1);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    uint32_t hi, lo;
-                    pt_split(fmaxf(__uint_as_float(a0[j]) + b2l, 0.f), hi, lo);
-                    const int off = j * 128 + (cb ^ ((j & 7) << 4));
-                    *reinterpret_cast<uint32_t*>(bh + off) = hi;
-                    *reinterpret_cast<uint32_t*>(bl + off) = lo;
+                    uint16_t hi, lo;
+                    pt_split16(fmaxf(__uint_as_float(a0[j]) + b2l, 0.f), hi, lo);
+                    const int off = j * 128 + ((chunk16 ^ (j & 7)) << 4) + cb;
+                    *reinterpret_cast<uint16_t*>(bh + off) = hi;
+                    *reinterpret_cast<uint16_t*>(bl + off) = lo;
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    uint32_t hi, lo;
-                    pt_split(fmaxf(__uint_as_float(a1[j]) + b2l, 0.f), hi, lo);
-                    const int off = (32 + j) * 128 + (cb ^ ((j & 7) << 4));
-                    *reinterpret_cast<uint32_t*>(bh + off) = hi;
-                    *reinterpret_cast<uint32_t*>(bl + off) = lo;
+                    uint16_t hi, lo;
+                    pt_split16(fmaxf(__uint_as_float(a1[j]) + b2l, 0.f), hi, lo);
+                    const int off = (32 + j) * 128 + ((chunk16 ^ (j & 7)) << 4) + cb;
+                    *reinterpret_cast<uint16_t*>(bh + off) = hi;
+                    *reinterpret_cast<uint16_t*>(bl + off) = lo;
                 }
             }
             fence_proxy_async();
