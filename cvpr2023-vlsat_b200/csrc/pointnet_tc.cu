@@ -25,7 +25,8 @@ namespace vlsat {
 using namespace tc;
 
 
-constexpr int PT_THREADS = 160;          // warp 0: MMA issue + TMEM; warps 1..4: workers (TMEM lane quarter = warp & 3)
+constexpr int PT_WORKERS = 256;          // two worker groups: group h owns the points [32h, 32h + 32) of every 64-point tile
+constexpr int PT_THREADS = 32 + PT_WORKERS;   // warp 0: MMA issue + TMEM; warps 1..8: workers (TMEM lane quarter = warp & 3)
 constexpr int PT_TP = 64;                // points per tile
 constexpr int PT_C1 = 64, PT_C2 = 128, PT_CIN_MAX = 16;
 // TMEM columns (bf16 A operands: two K elements per 32-bit column):
@@ -55,7 +56,7 @@ __device__ __forceinline__ void pt_split16(float v, uint16_t& hi, uint16_t& lo) 
     hi = (uint16_t)(h >> 16);
     lo = (uint16_t)((__float_as_uint(v - __uint_as_float(h)) + 0x8000u) >> 16);
 }
-__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(PT_WORKERS) : "memory"); }
 
 struct PointNetTcSmem {
     uint8_t b1_hi[PT_TP * 128];          // h1 tile  [64 pts][64 k] bf16: one k-block of 64 rows x 128 B (swizzled)
@@ -65,7 +66,8 @@ struct PointNetTcSmem {
     float xs[PT_CIN_MAX][PT_TP];
     float w1[PT_C1][PT_CIN_MAX];
     float b1[PT_C1];
-    uint64_t bars[4];                    // b1_ready (128), d2_full (1), b2_ready (128), d3_full (1)
+    float mx[128]; int mi[128];          // running max / arg max of the upper point half, handed to the lower half per object
+    uint64_t bars[4];                    // b1_ready (workers), d2_full (1), b2_ready (workers), d3_full (1)
     uint32_t tmem_holder;
 };
 
@@ -91,7 +93,7 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
     const int total_it = n_local_obj * tiles_per_obj;            // tiles this CTA walks, flattened (object-major)
 
     if (threadIdx.x == 0) {
-        mbar_init(b1_ready, 128); mbar_init(d2_full, 1); mbar_init(b2_ready, 128); mbar_init(d3_full, 1);
+        mbar_init(b1_ready, PT_WORKERS); mbar_init(d2_full, 1); mbar_init(b2_ready, PT_WORKERS); mbar_init(d3_full, 1);
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc(&s.tmem_holder, 512); tmem_relinquish(); }
@@ -136,14 +138,15 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
         }
     } else {
         // ------------------------------------------------------------------------------ workers
-        const int wt = threadIdx.x - 32;                         // 0..127
+        const int wt = threadIdx.x - 32;                         // 0..255
+        const int half = wt >> 7;                                // point half of the tile this thread reads back from TMEM
         const int qd = warp & 3;
         const int l = qd * 32 + lane;                            // TMEM lane = channel index inside W2 / the W3 chunk
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         // stage layer-1 weights; put W2 row l and W3 row (chunk*128 + l) into TMEM as tf32 hi / lo
-        for (int i = wt; i < PT_C1 * c_in; i += 128) s.w1[i / c_in][i % c_in] = __ldg(w1 + i);
-        for (int i = wt; i < PT_C1; i += 128) s.b1[i] = __ldg(b1 + i);
-        {
+        for (int i = wt; i < PT_C1 * c_in; i += PT_WORKERS) s.w1[i / c_in][i % c_in] = __ldg(w1 + i);
+        for (int i = wt; i < PT_C1; i += PT_WORKERS) s.b1[i] = __ldg(b1 + i);
+        if (half == 0) {                                         // one writer per TMEM lane
             uint32_t hi[32], lo[32];
             const float* w2row = w2 + (int64_t)l * PT_C1;
 #pragma unroll
@@ -161,8 +164,8 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
         }
         const float b2l = __ldg(b2 + l);
         const float b3l = __ldg(b3 + chunk * 128 + l);
-        const int p_own = wt & 63, khalf = wt >> 6;              // layer 1: point p_own, channels khalf*32 .. +31
-        constexpr int XPT = (PT_CIN_MAX * PT_TP + 127) / 128;    // x values each worker stages per tile (<= 8)
+        const int p_own = wt & 63, kq = wt >> 6;                 // layer 1: point p_own, channels kq*16 .. +15
+        constexpr int XPT = (PT_CIN_MAX * PT_TP + PT_WORKERS - 1) / PT_WORKERS;    // x values each worker stages per tile (<= 4)
         float xr[XPT];
         // register prefetch of the x tile of flattened iteration `it` (global latency hidden behind the previous tile)
         auto prefetch_x = [&](int it) {
@@ -171,7 +174,7 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
             const float* xo = x + obj * (int64_t)c_in * n_pts;
 #pragma unroll
             for (int u = 0; u < XPT; ++u) {
-                const int i = wt + u * 128;
+                const int i = wt + u * PT_WORKERS;
                 const int d = i / PT_TP, p = i % PT_TP;
                 xr[u] = (it < total_it && d < c_in && p0 + p < n_pts) ? __ldg(xo + d * n_pts + p0 + p) : 0.f;
             }
@@ -180,7 +183,7 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
         auto layer1 = [&](int it) {
 #pragma unroll
             for (int u = 0; u < XPT; ++u) {
-                const int i = wt + u * 128;
+                const int i = wt + u * PT_WORKERS;
                 if (i < c_in * PT_TP) s.xs[i / PT_TP][i % PT_TP] = xr[u];
             }
             worker_barrier();
@@ -191,14 +194,14 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
             uint8_t* rowh = s.b1_hi + p_own * 128;               // row = point, 64 channels x bf16 = 128 bytes
             uint8_t* rowl = s.b1_lo + p_own * 128;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {                        // 4 chunks of 8 channels = one 16-byte unit each
+            for (int c = 0; c < 2; ++c) {                        // 2 chunks of 8 channels = one 16-byte unit each
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     float a2[2];
 #pragma unroll
                     for (int v = 0; v < 2; ++v) {
-                        const int k = khalf * 32 + c * 8 + u * 2 + v;
+                        const int k = kq * 16 + c * 8 + u * 2 + v;
                         float acc = s.b1[k];
 #pragma unroll
                         for (int d = 0; d < (CIN > 0 ? CIN : PT_CIN_MAX); ++d)
@@ -207,7 +210,7 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
                     }
                     split_bf16x2(a2[0], a2[1], hi[u], lo[u]);
                 }
-                const int pos = ((khalf * 4 + c) ^ (p_own & 7)) * 16;   // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+                const int pos = ((kq * 2 + c) ^ (p_own & 7)) * 16;      // 128B swizzle: 16-byte chunk index XOR (row mod 8)
                 *reinterpret_cast<uint4*>(rowh + pos) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4*>(rowl + pos) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
@@ -233,23 +236,14 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
                 uint8_t* bh = s.b2_hi + (l >> 6) * (PT_TP * 128);         // k-block of channel l (64 bf16 channels per 128-byte row)
                 uint8_t* bl = s.b2_lo + (l >> 6) * (PT_TP * 128);
                 const int chunk16 = (l & 63) >> 3, cb = (l & 7) * 2;      // 16-byte chunk of channel l inside the row, byte inside it
-                uint32_t a0[32], a1[32];
-                tmem_ld_32x32(tm + PT_D2 + lane_off, a0);
-                tmem_ld_32x32(tm + PT_D2 + lane_off + 32, a1);
+                uint32_t a0[32];
+                tmem_ld_32x32(tm + PT_D2 + lane_off + 32 * half, a0);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     uint16_t hi, lo;
                     pt_split16(fmaxf(__uint_as_float(a0[j]) + b2l, 0.f), hi, lo);
-                    const int off = j * 128 + ((chunk16 ^ (j & 7)) << 4) + cb;
-                    *reinterpret_cast<uint16_t*>(bh + off) = hi;
-                    *reinterpret_cast<uint16_t*>(bl + off) = lo;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    uint16_t hi, lo;
-                    pt_split16(fmaxf(__uint_as_float(a1[j]) + b2l, 0.f), hi, lo);
-                    const int off = (32 + j) * 128 + ((chunk16 ^ (j & 7)) << 4) + cb;
+                    const int off = (32 * half + j) * 128 + ((chunk16 ^ (j & 7)) << 4) + cb;
                     *reinterpret_cast<uint16_t*>(bh + off) = hi;
                     *reinterpret_cast<uint16_t*>(bl + off) = lo;
                 }
@@ -263,26 +257,29 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
             mbar_wait(d3_full, ph);
             tc_fence_after();
             {
-                uint32_t a0[32], a1[32];
-                tmem_ld_32x32(tm + PT_D3 + lane_off, a0);
-                tmem_ld_32x32(tm + PT_D3 + lane_off + 32, a1);
+                uint32_t a0[32];
+                tmem_ld_32x32(tm + PT_D3 + lane_off + 32 * half, a0);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float v = __uint_as_float(a0[j]);
-                    if (j < valid && v > run_max) { run_max = v; run_idx = (int)p0 + j; }
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float v = __uint_as_float(a1[j]);
-                    if (32 + j < valid && v > run_max) { run_max = v; run_idx = (int)p0 + 32 + j; }
+                    if (32 * half + j < valid && v > run_max) { run_max = v; run_idx = (int)p0 + 32 * half + j; }
                 }
             }
             tc_fence_before();
             if (t == tiles_per_obj - 1) {
-                const int64_t o = obj * c_out + chunk * 128 + l;
-                out[o] = fmaxf(run_max + b3l, 0.f);              // bias and ReLU commute with the max
-                if (argmax) argmax[o] = run_idx;
+                // the two point halves of a channel meet in smem; ties keep the lower point index (the order a single
+                // scan over the points would have produced)
+                if (half == 1) { s.mx[l] = run_max; s.mi[l] = run_idx; }
+                worker_barrier();
+                if (half == 0) {
+                    const float om = s.mx[l]; const int oi = s.mi[l];
+                    if (om > run_max || (om == run_max && oi < run_idx)) { run_max = om; run_idx = oi; }
+                    const int64_t o = obj * c_out + chunk * 128 + l;
+                    out[o] = fmaxf(run_max + b3l, 0.f);          // bias and ReLU commute with the max
+                    if (argmax) argmax[o] = run_idx;
+                }
+                worker_barrier();                                // s.mx / s.mi are rewritten at the next object
                 run_max = -FLT_MAX; run_idx = 0;
             }
         }

@@ -106,7 +106,8 @@ def pointnet(x, w1, b1, w2, b2, w3, b3, want_argmax: bool = False):
         raise ValueError("pointnet: weight shapes do not chain")
     out = torch.empty((n_obj, c_out), device=x.device, dtype=torch.float32)
     arg = torch.empty((n_obj, c_out), device=x.device, dtype=torch.int32) if want_argmax else None
-    use_tc = tensor_cores_enabled() and c1 == 64 and c2 == 128 and c_in <= 16 and c_out % 128 == 0
+    # the tensor-core encoder is BF16x3 only: with the 3xTF32 engine forced ('tc') the exact FFMA kernel runs instead
+    use_tc = _engine in (ENGINES["auto"], ENGINES["bf16x3"]) and c1 == 64 and c2 == 128 and c_in <= 16 and c_out % 128 == 0
     st = _call("vlsat_pointnet_tc_fwd" if use_tc else "vlsat_pointnet_fwd", x.data_ptr(), n_obj, c_in, n_pts, w1.data_ptr(), b1.data_ptr(), c1,
                                         w2.data_ptr(), b2.data_ptr(), c2, w3.data_ptr(), b3.data_ptr(), c_out,
                                         out.data_ptr(), arg.data_ptr() if want_argmax else None, _stream(),
