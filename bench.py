@@ -36,6 +36,16 @@ import torch  # noqa: E402
 METRIC = "scenes_per_sec_fwd"
 UNIT = "scenes/s"
 
+# stdout carries exactly ONE line (the JSON): everything else a library may print there (NCCL's version banner, ...) is
+# sent to stderr by pointing fd 1 at fd 2 for the duration of the run
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -351,7 +361,7 @@ def run_b200(args):
         "fwd_bwd": fwd_bwd,
         "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "roofline_gat_scatter": roofline_gat, "kernels": kernels, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -380,7 +390,7 @@ def run_reference(args):
         "cpu_baseline": {"value": round(r["value"], 4), "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": round(r["value"], 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():

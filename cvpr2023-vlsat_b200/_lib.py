@@ -71,6 +71,7 @@ SIGNATURES = {
     "vlsat_gat_softmax_aggr_fwd": [vp, vp, i64, vp, vp, i64, i64, i32, i32, i32, vp, i64, vp, vp, vp],
     "vlsat_gat_softmax_aggr_bwd": [vp, i64, vp, vp, i64, vp, vp, vp, i64, i64, i32, i32, i32, vp, vp, i64, vp],
     "vlsat_attn_prob_bwd": [vp, vp, i64, vp, vp, f32, vp, vp, vp, i64, i64, i64, vp],
+    "vlsat_attn_prob_bwd_pairs": [vp, vp, i64, vp, vp, f32, vp, vp, i64, vp, vp, vp, vp, i64, i64, i64, vp],
     "vlsat_rowdot_heads": [vp, i64, vp, i64, vp, i64, i32, i32, vp],
     "vlsat_pair_features": [vp, i64, vp, vp, vp, i64, vp, vp],
     "vlsat_node_attn_bias_fwd": [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, i32, vp, i64, i64, vp],

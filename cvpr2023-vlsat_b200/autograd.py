@@ -372,6 +372,7 @@ class _FlashAttn(Function):
         dq = torch.empty_like(q)
         dk = torch.empty((nk, d), device=q.device, dtype=torch.float32)
         dv = torch.empty((nk, d), device=q.device, dtype=torch.float32)
+        pairs = ops.tensor_cores_enabled() and ops.default_fmt(8) == ops.FMT_BF16 and nk % 8 == 0 and nk >= 32
         for h in range(H):
             cs = slice(h * dk_, (h + 1) * dk_)
             kh, vh = k[:, cs], v[:, cs]
@@ -381,8 +382,16 @@ class _FlashAttn(Function):
                 qb, dob = q[i0:i1, cs], dout[i0:i1, cs]
                 s = ops.linear(qb, kh, cache_w=False)               # [nb, nk] raw scores
                 dp = ops.linear(dob, vh, cache_w=False)             # [nb, nk]
-                ds, ds_t, p_t = ops.attn_prob_bwd(s, dp, lse[h, i0:i1], delta[h, i0:i1], scale)
                 first = i0 == 0
+                if pairs and i1 - i0 >= 32:
+                    # the score stage writes dS, dS^T, P^T as the bf16 pairs the next three products read: the fp32
+                    # [block, nk] matrices are neither stored nor re-read for a split pass
+                    ds, ds_t, p_t = ops.attn_prob_bwd_pairs(s, dp, lse[h, i0:i1], delta[h, i0:i1], scale)
+                    ops.linear(p_t, ops.transpose(dob, 8), out=dv[:, cs], residual=None if first else dv[:, cs], cache_w=False)
+                    ops.linear(ds_t, ops.transpose(qb, 8), out=dk[:, cs], residual=None if first else dk[:, cs], cache_w=False)
+                    ops.linear(ds, kh_t[:, :nk], out=dq[i0:i1, cs], cache_w=False)
+                    continue
+                ds, ds_t, p_t = ops.attn_prob_bwd(s, dp, lse[h, i0:i1], delta[h, i0:i1], scale)
                 ops.linear(p_t, ops.transpose(dob), out=dv[:, cs], residual=None if first else dv[:, cs], cache_w=False)
                 ops.linear(ds_t, ops.transpose(qb), out=dk[:, cs], residual=None if first else dk[:, cs], cache_w=False)
                 ops.linear(ds, kh_t[:, :nk], out=dq[i0:i1, cs], cache_w=False)

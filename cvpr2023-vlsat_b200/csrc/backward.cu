@@ -285,6 +285,42 @@ __global__ void attn_prob_bwd_kernel(const float* __restrict__ s, const float* _
     }
 }
 
+// Same stage with every output as the bf16 (hi, lo) pair the three following products read (dV += P^T dO, dK += dS^T Q,
+// dQ = dS K): the fp32 [nq, nk] matrices are never written and never read back to be split. ds_* [nq, ld_ds],
+// dst_* / pt_* [nk, ld_t] (columns >= nq zero-filled).
+__device__ __forceinline__ void bwd_split16(float v, uint16_t& hi, uint16_t& lo) {
+    const uint32_t h = (__float_as_uint(v) + 0x8000u) & 0xffff0000u;
+    hi = (uint16_t)(h >> 16);
+    lo = (uint16_t)((__float_as_uint(v - __uint_as_float(h)) + 0x8000u) >> 16);
+}
+__global__ void attn_prob_bwd_pairs_kernel(const float* __restrict__ s, const float* __restrict__ dp, int64_t ld,
+                                           const float* __restrict__ lse, const float* __restrict__ delta, float scale,
+                                           uint16_t* __restrict__ ds_hi, uint16_t* __restrict__ ds_lo, int64_t ld_ds,
+                                           uint16_t* __restrict__ dst_hi, uint16_t* __restrict__ dst_lo,
+                                           uint16_t* __restrict__ pt_hi, uint16_t* __restrict__ pt_lo, int64_t ld_t,
+                                           int64_t nq, int64_t nk) {
+    __shared__ float tp[32][33], td[32][33];
+    const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int64_t i = i0 + r, j = j0 + threadIdx.x;
+        float pv = 0.f, dv = 0.f;
+        if (i < nq && j < nk) {
+            pv = expf(scale * s[i * ld + j] - __ldg(lse + i));
+            dv = pv * (dp[i * ld + j] - __ldg(delta + i)) * scale;
+            bwd_split16(dv, ds_hi[i * ld_ds + j], ds_lo[i * ld_ds + j]);
+        }
+        tp[r][threadIdx.x] = pv; td[r][threadIdx.x] = dv;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int64_t j = j0 + r, i = i0 + threadIdx.x;
+        if (j < nk && i < ld_t) {
+            bwd_split16(tp[threadIdx.x][r], pt_hi[j * ld_t + i], pt_lo[j * ld_t + i]);
+            bwd_split16(td[threadIdx.x][r], dst_hi[j * ld_t + i], dst_lo[j * ld_t + i]);
+        }
+    }
+}
+
 // delta[h, i] = sum_d a[i, h*dk + d] * b[i, h*dk + d]; one warp per (i, h)
 __global__ void rowdot_heads_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
                                     float* __restrict__ out, int64_t M, int H, int dk) {
@@ -621,6 +657,20 @@ extern "C" int vlsat_attn_prob_bwd(const float* s, const float* dp, int64_t ld, 
     VLSAT_SUPPORT(ceil_div(ld_t, 32) <= 65535);
     dim3 grid((unsigned)ceil_div(nk, 32), (unsigned)ceil_div(ld_t, 32));
     attn_prob_bwd_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(s, dp, ld, lse, delta, scale, ds, ds_t, p_t, ld_t, nq, nk);
+    return finish_launch();
+}
+
+extern "C" int vlsat_attn_prob_bwd_pairs(const float* s, const float* dp, int64_t ld, const float* lse, const float* delta,
+                                         float scale, void* ds_hi, void* ds_lo, int64_t ld_ds, void* dst_hi, void* dst_lo,
+                                         void* pt_hi, void* pt_lo, int64_t ld_t, int64_t nq, int64_t nk, void* stream) {
+    VLSAT_REQUIRE(nq >= 0 && nk >= 0);
+    if (nq == 0 || nk == 0) return VLSAT_OK;
+    VLSAT_REQUIRE(s && dp && lse && delta && ds_hi && ds_lo && dst_hi && dst_lo && pt_hi && pt_lo && ld >= nk && ld_ds >= nk && ld_t >= nq);
+    VLSAT_SUPPORT(ceil_div(ld_t, 32) <= 65535);
+    dim3 grid((unsigned)ceil_div(nk, 32), (unsigned)ceil_div(ld_t, 32));
+    attn_prob_bwd_pairs_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(s, dp, ld, lse, delta, scale, (uint16_t*)ds_hi, (uint16_t*)ds_lo,
+                                                                               ld_ds, (uint16_t*)dst_hi, (uint16_t*)dst_lo, (uint16_t*)pt_hi,
+                                                                               (uint16_t*)pt_lo, ld_t, nq, nk);
     return finish_launch();
 }
 

@@ -28,6 +28,7 @@ namespace vlsat {
 using namespace tc;
 
 constexpr int FB_BQ = 128, FB_BKV = 64, FB_DK = 64, FB_THREADS = 352;   // + warp 10: V producer
+constexpr int FB_STAGES = 4;                             // K and V^T tile rings (Q and P live in TMEM: shared memory is all theirs)
 constexpr int FB_K_STAGE = 2 * FB_BKV * 128;             // K_hi | K_lo, 64 rows x 128 B
 constexpr int FB_V_STAGE = 2 * FB_DK * 128;              // Vt_hi | Vt_lo
 constexpr uint32_t FB_TMEM_COLS = 512;                   // S[g][b] x 64 at 64*(2g+b) | O[g] x 64 at 256 + 64 g | Q[g] (hi, lo) x 64 at 384 + 64 g
@@ -98,15 +99,15 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps LDS/STS
     uint8_t* k_smem = smem;                                  // 2 stages x (K_hi | K_lo)
-    uint8_t* v_smem = k_smem + 2 * FB_K_STAGE;               // 2 stages x (Vt_hi | Vt_lo)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + 2 * FB_V_STAGE);
+    uint8_t* v_smem = k_smem + FB_STAGES * FB_K_STAGE;       // FB_STAGES x (Vt_hi | Vt_lo)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + FB_STAGES * FB_V_STAGE);
     uint64_t* q_full = bars;
-    uint64_t* k_full = bars + 1; uint64_t* k_empty = bars + 3;
-    uint64_t* v_full = bars + 5; uint64_t* v_empty = bars + 7;
-    uint64_t* s_full = bars + 9;      // [g * 2 + b]
-    uint64_t* p_ready = bars + 13;    // [g]
-    uint64_t* pv_full = bars + 15;    // [g]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* k_full = bars + 1; uint64_t* k_empty = k_full + FB_STAGES;
+    uint64_t* v_full = k_empty + FB_STAGES; uint64_t* v_empty = v_full + FB_STAGES;
+    uint64_t* s_full = v_empty + FB_STAGES;   // [g * 2 + b]
+    uint64_t* p_ready = s_full + 4;           // [g]
+    uint64_t* pv_full = p_ready + 2;          // [g]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_full + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
@@ -119,8 +120,10 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
         prefetch_tmap(&tm_khi);
         prefetch_tmap(&tm_klo); prefetch_tmap(&tm_vhi); prefetch_tmap(&tm_vlo);
         mbar_init(q_full, 256);                                  // every softmax thread has put its Q row into TMEM
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < FB_STAGES; ++s) {
             mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(&s_full[s], 1); mbar_init(&s_full[2 + s], 1); mbar_init(&p_ready[s], 128); mbar_init(&pv_full[s], 1);
         }
         fence_barrier_init();
@@ -133,8 +136,8 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
 
     if (warp == 0) {
         for (int i = 0; i < n_tiles; ++i) {
-            const int s = i & 1;
-            mbar_wait(&k_empty[s], ((i >> 1) & 1) ^ 1);
+            const int s = i % FB_STAGES;
+            mbar_wait(&k_empty[s], ((i / FB_STAGES) & 1) ^ 1);
             if (elect_one()) {
                 uint8_t* st = k_smem + s * FB_K_STAGE;
                 mbar_arrive_expect_tx(&k_full[s], FB_K_STAGE);
@@ -147,8 +150,8 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
         // V producer on its own warp: S tiles are issued ahead of the P.V products, so one in-order producer would
         // stall the K ring behind the V ring while the MMA warp waits for K
         for (int i = 0; i < n_tiles; ++i) {
-            const int s = i & 1;
-            mbar_wait(&v_empty[s], ((i >> 1) & 1) ^ 1);
+            const int s = i % FB_STAGES;
+            mbar_wait(&v_empty[s], ((i / FB_STAGES) & 1) ^ 1);
             if (elect_one()) {
                 uint8_t* st = v_smem + s * FB_V_STAGE;
                 mbar_arrive_expect_tx(&v_full[s], FB_V_STAGE);
@@ -163,11 +166,11 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
         const uint64_t dv0 = make_sdesc_k128(smem_u32(v_smem));
         // S(g, i) = Q_g K(i)^T for both Q tiles; releases the K stage afterwards
         auto issue_s = [&](int i) {
-            const int s = i & 1;
-            mbar_wait(&k_full[s], (i >> 1) & 1);
+            const int s = i & 1, ks = i % FB_STAGES;             // S buffer parity, K ring stage
+            mbar_wait(&k_full[ks], (i / FB_STAGES) & 1);
             tc_fence_after();
             if (elect_one()) {
-                const uint64_t dk = dk0 + (uint64_t)(s * (FB_K_STAGE >> 4));
+                const uint64_t dk = dk0 + (uint64_t)(ks * (FB_K_STAGE >> 4));
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     const uint32_t tq = tmem_base + 384 + 64 * g;           // Q_g: hi words in columns [0, 32), lo in [32, 64)
@@ -180,7 +183,7 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
                     }
                     tc_commit(&s_full[2 * g + s]);
                 }
-                tc_commit(&k_empty[s]);
+                tc_commit(&k_empty[ks]);
             }
             __syncwarp();
         };
@@ -188,13 +191,13 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
         tc_fence_after();
         for (int i = 0; i < 2 && i < n_tiles; ++i) issue_s(i);
         for (int i = 0; i < n_tiles; ++i) {
-            const int s = i & 1;
-            mbar_wait(&v_full[s], (i >> 1) & 1);
+            const int s = i & 1, vs = i % FB_STAGES;             // S / P buffer parity, V ring stage
+            mbar_wait(&v_full[vs], (i / FB_STAGES) & 1);
             for (int g = 0; g < 2; ++g) {
                 mbar_wait(&p_ready[g], i & 1);                   // P_g(i) is in TMEM (over S_g[s]); O_g is rescaled if needed
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint64_t dv = dv0 + (uint64_t)(s * (FB_V_STAGE >> 4));
+                    const uint64_t dv = dv0 + (uint64_t)(vs * (FB_V_STAGE >> 4));
                     const uint32_t tp = tmem_base + 64 * (2 * g + s);       // P_g(i): hi words in columns [0, 32), lo in [32, 64)
                     const uint32_t tpv = tmem_base + 256 + 64 * g;
 #pragma unroll
@@ -204,7 +207,7 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
                         mma_ts_bf16(tpv, tp + 8 * kk, dv + 2 * kk, idesc, 1);                                          // P_hi V_hi
                     }
                     tc_commit(&pv_full[g]);
-                    if (g == 1) tc_commit(&v_empty[s]);
+                    if (g == 1) tc_commit(&v_empty[vs]);
                 }
                 __syncwarp();
             }
@@ -434,7 +437,7 @@ int flash_attn_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq, con
     }
     const int n_tiles = (int)ceil_div(nk, FB_BKV);
     const int tiles_per_split = (int)ceil_div(n_tiles, splits);
-    const size_t smem = 2 * FB_K_STAGE + 2 * FB_V_STAGE + 1024 + 256;
+    const size_t smem = FB_STAGES * FB_K_STAGE + FB_STAGES * FB_V_STAGE + 1024 + 256;
     cudaFuncSetAttribute(flash_attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((unsigned)ceil_div(nq, 2 * FB_BQ), (unsigned)n_heads, (unsigned)splits);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)dk);

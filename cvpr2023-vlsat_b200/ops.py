@@ -670,14 +670,14 @@ def _round4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
-def transpose(x: torch.Tensor) -> torch.Tensor:
-    """x [R, C] (row stride allowed) -> [C, round4(R)] with the tail columns zero (GEMM operand for a reduction
+def transpose(x: torch.Tensor, mult: int = 4) -> torch.Tensor:
+    """x [R, C] (row stride allowed) -> [C, round_mult(R)] with the tail columns zero (GEMM operand for a reduction
     over R). For a 3-D contiguous x [B, R, C] returns [B, C, round4(R)]."""
     _f32(x, "x")
     if x.dim() == 2:
         xp, ldx = _rows(x, "x")
         r, c = x.shape
-        out = torch.empty((c, _round4(r)), device=x.device, dtype=torch.float32)
+        out = torch.empty((c, (r + mult - 1) // mult * mult), device=x.device, dtype=torch.float32)
         _lib.check(_call("vlsat_transpose", xp, ldx, 0, out.data_ptr(), out.shape[1], 0, 1, r, c, _stream()), "vlsat_transpose")
         return out
     if x.dim() != 3 or not x.is_contiguous():
@@ -776,6 +776,21 @@ def attn_prob_bwd(s, dp, lse, delta, scale: float):
     _lib.check(_call("vlsat_attn_prob_bwd", s.data_ptr(), dp.data_ptr(), nk, lse.data_ptr(), delta.data_ptr(), scale, dp.data_ptr(),
                      ds_t.data_ptr(), p_t.data_ptr(), ldt, nq, nk, _stream()), "vlsat_attn_prob_bwd")
     return dp, ds_t, p_t
+
+
+def attn_prob_bwd_pairs(s, dp, lse, delta, scale: float):
+    """bf16 (hi, lo) pairs of dS [nq, nk], dS^T [nk, round8(nq)] and P^T [nk, round8(nq)] (no fp32 outputs); nk % 8 == 0."""
+    nq, nk = s.shape
+    if not (s.is_contiguous() and dp.is_contiguous()) or nk % 8:
+        raise ValueError("attn_prob_bwd_pairs: s and dp must be contiguous with nk % 8 == 0")
+    ldt = (nq + 7) // 8 * 8
+    ds = torch.empty((2, nq, nk), device=s.device, dtype=torch.bfloat16)
+    ds_t = torch.empty((2, nk, ldt), device=s.device, dtype=torch.bfloat16)
+    p_t = torch.empty((2, nk, ldt), device=s.device, dtype=torch.bfloat16)
+    _lib.check(_call("vlsat_attn_prob_bwd_pairs", s.data_ptr(), dp.data_ptr(), nk, lse.data_ptr(), delta.data_ptr(), scale,
+                     ds[0].data_ptr(), ds[1].data_ptr(), nk, ds_t[0].data_ptr(), ds_t[1].data_ptr(), p_t[0].data_ptr(), p_t[1].data_ptr(),
+                     ldt, nq, nk, _stream()), "vlsat_attn_prob_bwd_pairs")
+    return (ds[0], ds[1]), (ds_t[0], ds_t[1]), (p_t[0], p_t[1])
 
 
 def rowdot_heads(a, b, n_heads: int) -> torch.Tensor:

@@ -316,6 +316,11 @@ int vlsat_gat_softmax_aggr_bwd(const float* dxx, int64_t ld_dxx, const float* pr
  * out [H, M]). */
 int vlsat_attn_prob_bwd(const float* s, const float* dp, int64_t ld, const float* lse, const float* delta, float scale,
                         float* ds, float* ds_t, float* p_t, int64_t ld_t, int64_t nq, int64_t nk, void* stream);
+/* Same stage with dS, dS^T and P^T written as the bf16 (hi, lo) pairs the three following products consume
+ * (ds_* [nq, ld_ds], dst_* / pt_* [nk, ld_t], columns >= nq zero-filled); no fp32 [nq, nk] output. */
+int vlsat_attn_prob_bwd_pairs(const float* s, const float* dp, int64_t ld, const float* lse, const float* delta, float scale,
+                              void* ds_hi, void* ds_lo, int64_t ld_ds, void* dst_hi, void* dst_lo, void* pt_hi, void* pt_lo,
+                              int64_t ld_t, int64_t nq, int64_t nk, void* stream);
 int vlsat_rowdot_heads(const float* a, int64_t lda, const float* b, int64_t ldb, float* out, int64_t M, int n_heads,
                        int dk, void* stream);
 
