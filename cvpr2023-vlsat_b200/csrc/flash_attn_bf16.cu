@@ -12,7 +12,11 @@
 //                   all K-major rows of exactly 128 bytes (64 bf16) with the 128B swizzle
 //   warp 1          tcgen05.mma issue, both products with the A operand in TMEM (TS): S(t) = Q K(t)^T into S[t&1] with
 //                   Q copied into TMEM once by the softmax threads, O += P(t) V(t) with P written over S(t)
-//   warps 2-5, 6-9  two softmax warpgroups (one Q tile each), one query row per thread: tcgen05.ld S, online softmax in
+//   warps 2-17      softmax: per Q tile two warpgroups, each owning one 32-key HALF of every S tile, so a query row is
+//                   shared by two threads (they exchange the half-row maximum through smem once per tile, the row sums
+//                   once at the end) and every scheduler holds four softmax warps instead of two - the loop is
+//                   latency-bound (ncu: 38 % issue, long-scoreboard / fixed-latency stalls), not pipe-bound.
+//                   tcgen05.ld S, online softmax in
 //                   the exp2 domain, P split to bf16 hi/lo and written back IN PLACE over the S columns of TMEM (64 fp32
 //                   columns -> 32 packed hi + 32 packed lo words): P.V is a TS MMA (A from TMEM) that accumulates into
 //                   the warpgroup's O columns for the whole KV range. With S double-buffered the softmax of tile i+1
@@ -27,7 +31,8 @@ namespace vlsat {
 
 using namespace tc;
 
-constexpr int FB_BQ = 128, FB_BKV = 64, FB_DK = 64, FB_THREADS = 352;   // + warp 10: V producer
+constexpr int FB_BQ = 128, FB_BKV = 64, FB_DK = 64;
+constexpr int FB_THREADS = 64 + 512 + 32;                // K producer, MMA, 16 softmax warps, V producer (warp 18)
 constexpr int FB_STAGES = 4;                             // K and V^T tile rings (Q and P live in TMEM: shared memory is all theirs)
 constexpr int FB_K_STAGE = 2 * FB_BKV * 128;             // K_hi | K_lo, 64 rows x 128 B
 constexpr int FB_V_STAGE = 2 * FB_DK * 128;              // Vt_hi | Vt_lo
@@ -50,6 +55,15 @@ __device__ __forceinline__ void tmem_st_32(uint32_t taddr, const uint32_t (&r)[3
           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
 
@@ -108,6 +122,7 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
     uint64_t* p_ready = s_full + 4;           // [g]
     uint64_t* pv_full = p_ready + 2;          // [g]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_full + 2);
+    float* xch = reinterpret_cast<float*>(tmem_holder + 4);  // [parity 2][Q tile 2][key half 2][128 rows] half-row maxima / sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
@@ -119,12 +134,12 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_khi);
         prefetch_tmap(&tm_klo); prefetch_tmap(&tm_vhi); prefetch_tmap(&tm_vlo);
-        mbar_init(q_full, 256);                                  // every softmax thread has put its Q row into TMEM
+        mbar_init(q_full, 512);                                  // every softmax thread has put its half of a Q row into TMEM
         for (int s = 0; s < FB_STAGES; ++s) {
             mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&s_full[s], 1); mbar_init(&s_full[2 + s], 1); mbar_init(&p_ready[s], 128); mbar_init(&pv_full[s], 1);
+            mbar_init(&s_full[s], 1); mbar_init(&s_full[2 + s], 1); mbar_init(&p_ready[s], 256); mbar_init(&pv_full[s], 1);
         }
         fence_barrier_init();
     }
@@ -146,7 +161,7 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
             }
             __syncwarp();
         }
-    } else if (warp == 10) {
+    } else if (warp == 18) {
         // V producer on its own warp: S tiles are issued ahead of the P.V products, so one in-order producer would
         // stall the K ring behind the V ring while the MMA warp waits for K
         for (int i = 0; i < n_tiles; ++i) {
@@ -214,104 +229,96 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
             if (i + 2 < n_tiles) issue_s(i + 2);                 // S buffers of parity s were consumed by the softmax of tile i
         }
     } else {
-        const int g = (warp - 2) >> 2;                           // softmax warpgroup = Q tile
+        const int g = (warp - 2) >> 3;                           // Q tile
+        const int kh = ((warp - 2) >> 2) & 1;                    // key half of every S tile owned by this thread
         const int qd = warp & 3;
         const int row_l = qd * 32 + lane;
         const int row = q0 + g * FB_BQ + row_l;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         const uint32_t t_pv = tmem_base + 256 + 64 * g;
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); };    // the two halves of Q tile g
         // The output accumulator O_g stays in TMEM: the P.V products of all tiles accumulate there (tensor-core fp32
-        // accumulation), so a tile costs this thread no TMEM read-back and no 64 FMAs, and 64 registers are free for the
-        // exp / split pipeline. The running maximum is LAZY: it only moves (and O, l are rescaled through a TMEM
+        // accumulation). The running maximum is LAZY: it only moves (and O, l are rescaled through a TMEM
         // load / multiply / store) when some row of the warp exceeds it by more than 2^8; until then p = 2^(s - m_stale)
         // <= 256, exactly representable in the bf16 pair, and l accumulates with the same stale reference.
-        float m_run = -FLT_MAX, l_run = 0.f;
+        float m_run = -FLT_MAX, l_run = 0.f;                     // l_run: this thread's half of the row sum
         constexpr float kRescaleAbove = 8.f;                     // log2 units
         // Q_g lives in TMEM as the A operand of S = Q K^T (TS MMA): an SS MMA of this shape reads 4 KB of Q and 2 KB of K
         // from shared memory for 32 clocks of math - 48 clocks at 128 B/clk, which is what the S products were paced by.
-        // Each thread copies its own query row (64 dims = 32 packed words, hi and lo) from global memory, once.
+        // The two threads of a row copy its hi (key half 0) and lo (key half 1) words from global memory, once.
         {
             uint32_t qw[32];
-            const uint4* src_hi = reinterpret_cast<const uint4*>(q_hi + (int64_t)min(row, nq - 1) * ldq + head * FB_DK);
-            const uint4* src_lo = reinterpret_cast<const uint4*>(q_lo + (int64_t)min(row, nq - 1) * ldq + head * FB_DK);
+            const uint4* src = reinterpret_cast<const uint4*>((kh ? q_lo : q_hi) + (int64_t)min(row, nq - 1) * ldq + head * FB_DK);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const uint4 t = __ldg(src_hi + u); qw[4 * u] = t.x; qw[4 * u + 1] = t.y; qw[4 * u + 2] = t.z; qw[4 * u + 3] = t.w; }
-            tmem_st_32(tmem_base + 384 + 64 * g + lane_off, qw);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { const uint4 t = __ldg(src_lo + u); qw[4 * u] = t.x; qw[4 * u + 1] = t.y; qw[4 * u + 2] = t.z; qw[4 * u + 3] = t.w; }
-            tmem_st_32(tmem_base + 384 + 64 * g + lane_off + 32, qw);
+            for (int u = 0; u < 8; ++u) { const uint4 t = __ldg(src + u); qw[4 * u] = t.x; qw[4 * u + 1] = t.y; qw[4 * u + 2] = t.z; qw[4 * u + 3] = t.w; }
+            tmem_st_32(tmem_base + 384 + 64 * g + lane_off + 32 * kh, qw);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(q_full);
         }
         for (int i = 0; i < n_tiles; ++i) {
-            const int k0 = (tile_begin + i) * FB_BKV;
-            uint32_t r[32], r2[32];
+            const int k0 = (tile_begin + i) * FB_BKV + 32 * kh;  // first key of this thread's half tile
+            uint32_t r[32];
             const uint32_t t_s = tmem_base + 64 * (2 * g + (i & 1));
             mbar_wait(&s_full[2 * g + (i & 1)], (i >> 1) & 1);
             tc_fence_after();
-            tmem_ld_32x32(t_s + lane_off, r);
-            tmem_ld_32x32(t_s + lane_off + 32, r2);
+            tmem_ld_32x32(t_s + lane_off + 32 * kh, r);
             tmem_ld_wait();
             tc_fence_before();
-            if (k0 + FB_BKV > nk) {                              // ragged last tile
+            if (k0 + 32 > nk) {                                  // ragged last tile
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 32; ++j)
                     if (k0 + j >= nk) r[j] = __float_as_uint(-FLT_MAX);
-                    if (k0 + 32 + j >= nk) r2[j] = __float_as_uint(-FLT_MAX);
-                }
             }
-            // four independent partial maxima / sums: the softmax warps have little TLP, so keep the chains short
+            // four independent partial maxima / sums keep the dependent chains short
             float mxp[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mxp[j & 3] = fmaxf(mxp[j & 3], fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
-            const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
+            for (int j = 0; j < 32; ++j) mxp[j & 3] = fmaxf(mxp[j & 3], __uint_as_float(r[j]));
+            const float mx_half = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
+            // the row maximum is the larger of the two halves: exchanged through smem (double-buffered by tile parity)
+            float* xm = xch + (((i & 1) * 2 + g) * 2) * 128;
+            xm[kh * 128 + row_l] = mx_half;
+            pair_sync();
+            const float mx = fmaxf(mx_half, xm[(kh ^ 1) * 128 + row_l]);
             const float m_cand = fmaxf(m_run, mx * scale_log2e);
-            const bool rescale = __any_sync(0xffffffffu, m_cand > m_run + kRescaleAbove);     // warp-uniform (TMEM ops are collective)
+            // warp-uniform (TMEM ops are collective) and identical in the partner warp, which sees the same 32 rows
+            const bool rescale = __any_sync(0xffffffffu, m_cand > m_run + kRescaleAbove);
             const float m_new = rescale ? m_cand : m_run;
             const float neg_m = -m_new;
             float rsp[4] = {0.f, 0.f, 0.f, 0.f};
-            // p = 2^(s * scale - m) -> bf16 (hi, lo) pair, packed two keys per word, written over this row's S columns:
-            // r <- hi words of keys 0..63 (32 words), r2 <- lo words
-            uint32_t ph[32], pl[32];
+            // p = 2^(s * scale - m) -> bf16 (hi, lo) pair, packed two keys per word, written over this row's S columns
+            // (hi words of the tile's 64 keys in columns [0, 32), lo words in [32, 64); this thread owns 16 of each)
+            uint32_t ph[16], pl[16];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {                   // two keys per packed word
-                    const uint32_t sa = half ? r2[2 * c] : r[2 * c], sb = half ? r2[2 * c + 1] : r[2 * c + 1];
-                    const float pa = fb_ex2(fmaf(__uint_as_float(sa), scale_log2e, neg_m));
-                    const float pb = fb_ex2(fmaf(__uint_as_float(sb), scale_log2e, neg_m));
-                    rsp[c & 3] += pa + pb;
-                    // bf16 pair by TRUNCATION, three ops per value: hi = upper 16 bits of p (the byte permute takes them
-                    // straight from the fp32 bit patterns), lo = upper 16 bits of p - hi (exact in fp32). hi + lo misses p by
-                    // less than 2^-16 p, always from below: a -8e-6 relative bias of the weights against the exactly
-                    // summed l, two orders inside the parity budget - and 40 % fewer instructions than rounding both
-                    // halves in the loop that paces this kernel.
-                    const uint32_t ua = __float_as_uint(pa), ub = __float_as_uint(pb);
-                    const float la = pa - __uint_as_float(ua & 0xffff0000u), lb = pb - __uint_as_float(ub & 0xffff0000u);
-                    ph[half * 16 + c] = __byte_perm(ua, ub, 0x7632);     // {pb.hi16, pa.hi16}: low half = even key
-                    pl[half * 16 + c] = __byte_perm(__float_as_uint(la), __float_as_uint(lb), 0x7632);
-                }
+            for (int c = 0; c < 16; ++c) {                       // two keys per packed word
+                const float pa = fb_ex2(fmaf(__uint_as_float(r[2 * c]), scale_log2e, neg_m));
+                const float pb = fb_ex2(fmaf(__uint_as_float(r[2 * c + 1]), scale_log2e, neg_m));
+                rsp[c & 3] += pa + pb;
+                // bf16 pair by TRUNCATION, three ops per value: hi = upper 16 bits of p (the byte permute takes them
+                // straight from the fp32 bit patterns), lo = upper 16 bits of p - hi (exact in fp32). hi + lo misses p by
+                // less than 2^-16 p, always from below: a -8e-6 relative bias of the weights against the exactly
+                // summed l, two orders inside the parity budget.
+                const uint32_t ua = __float_as_uint(pa), ub = __float_as_uint(pb);
+                const float la = pa - __uint_as_float(ua & 0xffff0000u), lb = pb - __uint_as_float(ub & 0xffff0000u);
+                ph[c] = __byte_perm(ua, ub, 0x7632);             // {pb.hi16, pa.hi16}: low half = even key
+                pl[c] = __byte_perm(__float_as_uint(la), __float_as_uint(lb), 0x7632);
             }
-            tmem_st_32(t_s + lane_off, ph);
-            tmem_st_32(t_s + lane_off + 32, pl);
+            tmem_st_16(t_s + lane_off + 16 * kh, ph);
+            tmem_st_16(t_s + lane_off + 32 + 16 * kh, pl);
             tmem_st_wait();
             if (i > 0) {
                 // P.V(i-1) was issued a whole tile ago: this wait is normally free. It orders the (rare) rescale of O_g
                 // between P.V(i-1) and P.V(i), and keeps this thread in step with the barrier's phases.
                 mbar_wait(&pv_full[g], (i - 1) & 1);
                 tc_fence_after();
-                if (rescale) {
+                if (rescale) {                                   // each half rescales its 32 output columns
                     const float corr = fb_ex2(m_run - m_new);
+                    uint32_t a[32];
+                    tmem_ld_32x32(t_pv + lane_off + 32 * kh, a);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int c0 = 0; c0 < FB_DK; c0 += 32) {
-                        uint32_t a[32];
-                        tmem_ld_32x32(t_pv + lane_off + c0, a);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int d = 0; d < 32; ++d) a[d] = __float_as_uint(__uint_as_float(a[d]) * corr);
-                        tmem_st_32(t_pv + lane_off + c0, a);
-                    }
+                    for (int d = 0; d < 32; ++d) a[d] = __float_as_uint(__uint_as_float(a[d]) * corr);
+                    tmem_st_32(t_pv + lane_off + 32 * kh, a);
                     tmem_st_wait();
                     l_run *= corr;
                 }
@@ -321,39 +328,43 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
             l_run += (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
             m_run = m_new;
         }
-        float o[FB_DK];
+        // row sum = the two half sums (same reference maximum); each thread then finishes its 32 output dims
+        float* xl = xch + ((n_tiles & 1) * 2 + g) * 2 * 128;
+        xl[kh * 128 + row_l] = l_run;
+        pair_sync();
+        l_run += xl[(kh ^ 1) * 128 + row_l];
+        float o[32];
         if (n_tiles > 0) {
             mbar_wait(&pv_full[g], (n_tiles - 1) & 1);
             tc_fence_after();
+            uint32_t a[32];
+            tmem_ld_32x32(t_pv + lane_off + 32 * kh, a);
+            tmem_ld_wait();
 #pragma unroll
-            for (int c0 = 0; c0 < FB_DK; c0 += 32) {
-                uint32_t a[32];
-                tmem_ld_32x32(t_pv + lane_off + c0, a);
-                tmem_ld_wait();
-#pragma unroll
-                for (int d = 0; d < 32; ++d) o[c0 + d] = __uint_as_float(a[d]);
-            }
+            for (int d = 0; d < 32; ++d) o[d] = __uint_as_float(a[d]);
             tc_fence_before();
         } else {
 #pragma unroll
-            for (int d = 0; d < FB_DK; ++d) o[d] = 0.f;
+            for (int d = 0; d < 32; ++d) o[d] = 0.f;
         }
         if (row < nq) {
             if (gridDim.z == 1) {
                 const float inv = 1.f / l_run;
-                float* orow = out + (int64_t)row * ldo + head * FB_DK;
+                float* orow = out + (int64_t)row * ldo + head * FB_DK + 32 * kh;
 #pragma unroll
-                for (int d = 0; d < FB_DK; d += 4)
+                for (int d = 0; d < 32; d += 4)
                     *reinterpret_cast<float4*>(orow + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
-                if (lse) lse[(int64_t)head * nq + row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+                if (lse && kh == 0) lse[(int64_t)head * nq + row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
             } else {
                 const int64_t D = (int64_t)n_heads * FB_DK;
-                float* orow = part.o + ((int64_t)blockIdx.z * nq + row) * D + head * FB_DK;
+                float* orow = part.o + ((int64_t)blockIdx.z * nq + row) * D + head * FB_DK + 32 * kh;
 #pragma unroll
-                for (int d = 0; d < FB_DK; d += 4)
+                for (int d = 0; d < 32; d += 4)
                     *reinterpret_cast<float4*>(orow + d) = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
-                part.m[((int64_t)blockIdx.z * n_heads + head) * nq + row] = m_run;
-                part.l[((int64_t)blockIdx.z * n_heads + head) * nq + row] = l_run;
+                if (kh == 0) {
+                    part.m[((int64_t)blockIdx.z * n_heads + head) * nq + row] = m_run;
+                    part.l[((int64_t)blockIdx.z * n_heads + head) * nq + row] = l_run;
+                }
             }
         }
     }
@@ -437,7 +448,7 @@ int flash_attn_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq, con
     }
     const int n_tiles = (int)ceil_div(nk, FB_BKV);
     const int tiles_per_split = (int)ceil_div(n_tiles, splits);
-    const size_t smem = FB_STAGES * FB_K_STAGE + FB_STAGES * FB_V_STAGE + 1024 + 256;
+    const size_t smem = FB_STAGES * FB_K_STAGE + FB_STAGES * FB_V_STAGE + 1024 + 256 + 2 * 2 * 2 * 128 * 4;
     cudaFuncSetAttribute(flash_attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((unsigned)ceil_div(nq, 2 * FB_BQ), (unsigned)n_heads, (unsigned)splits);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)dk);
