@@ -179,32 +179,28 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
         constexpr uint32_t idesc = make_idesc<Kind::BF16>(FB_BQ, 64);
         const uint64_t dk0 = make_sdesc_k128(smem_u32(k_smem));
         const uint64_t dv0 = make_sdesc_k128(smem_u32(v_smem));
-        // S(g, i) = Q_g K(i)^T for both Q tiles; releases the K stage afterwards
-        auto issue_s = [&](int i) {
+        // S(g, i) = Q_g K(i)^T for one Q tile; the K stage is released after the second one
+        auto issue_s = [&](int i, int g) {
             const int s = i & 1, ks = i % FB_STAGES;             // S buffer parity, K ring stage
-            mbar_wait(&k_full[ks], (i / FB_STAGES) & 1);
-            tc_fence_after();
+            if (g == 0) { mbar_wait(&k_full[ks], (i / FB_STAGES) & 1); tc_fence_after(); }
             if (elect_one()) {
                 const uint64_t dk = dk0 + (uint64_t)(ks * (FB_K_STAGE >> 4));
+                const uint32_t tq = tmem_base + 384 + 64 * g;               // Q_g: hi words in columns [0, 32), lo in [32, 64)
+                const uint32_t ts = tmem_base + 64 * (2 * g + s);
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const uint32_t tq = tmem_base + 384 + 64 * g;           // Q_g: hi words in columns [0, 32), lo in [32, 64)
-                    const uint32_t ts = tmem_base + 64 * (2 * g + s);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {             // 16 dims per MMA = 8 packed columns
-                        mma_ts_bf16(ts, tq + 32 + 8 * kk, dk + 2 * kk, idesc, kk > 0);                                 // Q_lo K_hi
-                        mma_ts_bf16(ts, tq + 8 * kk, dk + ((FB_BKV * 128) >> 4) + 2 * kk, idesc, 1);                   // Q_hi K_lo
-                        mma_ts_bf16(ts, tq + 8 * kk, dk + 2 * kk, idesc, 1);                                           // Q_hi K_hi
-                    }
-                    tc_commit(&s_full[2 * g + s]);
+                for (int kk = 0; kk < 4; ++kk) {                 // 16 dims per MMA = 8 packed columns
+                    mma_ts_bf16(ts, tq + 32 + 8 * kk, dk + 2 * kk, idesc, kk > 0);                                 // Q_lo K_hi
+                    mma_ts_bf16(ts, tq + 8 * kk, dk + ((FB_BKV * 128) >> 4) + 2 * kk, idesc, 1);                   // Q_hi K_lo
+                    mma_ts_bf16(ts, tq + 8 * kk, dk + 2 * kk, idesc, 1);                                           // Q_hi K_hi
                 }
-                tc_commit(&k_empty[ks]);
+                tc_commit(&s_full[2 * g + s]);
+                if (g == 1) tc_commit(&k_empty[ks]);
             }
             __syncwarp();
         };
         mbar_wait(q_full, 0);
         tc_fence_after();
-        for (int i = 0; i < 2 && i < n_tiles; ++i) issue_s(i);
+        for (int i = 0; i < 2 && i < n_tiles; ++i) { issue_s(i, 0); issue_s(i, 1); }
         for (int i = 0; i < n_tiles; ++i) {
             const int s = i & 1, vs = i % FB_STAGES;             // S / P buffer parity, V ring stage
             mbar_wait(&v_full[vs], (i / FB_STAGES) & 1);
@@ -225,8 +221,10 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
                     if (g == 1) tc_commit(&v_empty[vs]);
                 }
                 __syncwarp();
+                // S_g(i + 2) right behind P_g(i).V(i): its buffer (the one P_g(i) sits in) is free in pipe order, and the
+                // Q tile that finished first gets its next scores without waiting for the other one
+                if (i + 2 < n_tiles) issue_s(i + 2, g);
             }
-            if (i + 2 < n_tiles) issue_s(i + 2);                 // S buffers of parity s were consumed by the softmax of tile i
         }
     } else {
         const int g = (warp - 2) >> 3;                           // Q tile
