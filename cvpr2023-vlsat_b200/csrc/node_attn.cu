@@ -210,7 +210,8 @@ node_attn_kernel(const float* __restrict__ q, int64_t ldq, const float* __restri
 // ---------------------------------------------------------------------------------------------------------------
 // Scene-resident form for scenes of up to NS_MAX nodes (every scene of the 3RScan / BASELINE shapes). The bias
 // depends only on the object centres, and MMG.forward runs 2 * depth attentions over the same scenes, so it is
-// evaluated ONCE per forward into a table  tab[(a * NS_MAX + j) * H + h]  (query node a, j-th key of its scene);
+// evaluated ONCE per forward into a head-major table  tab[(h * N + a) * NS_MAX + j]  (query node a, j-th key of its
+// scene: the row a (scene, head) CTA reads for one query is 64 contiguous floats);
 // each attention call is then one CTA per (scene, head) with that head's Q, K, V slices of the scene in shared
 // memory: every K / V row is read once per scene instead of once per query.
 constexpr int NS_MAX = 64;
@@ -218,7 +219,8 @@ constexpr int NS_THREADS = 128;
 
 __global__ void __launch_bounds__(NA_THREADS)
 node_bias_table_kernel(const float* __restrict__ centres, int64_t ldc, const int32_t* __restrict__ seg_start,
-                       const int32_t* __restrict__ seg_end, const float* __restrict__ fc, int H, float* __restrict__ tab) {
+                       const int32_t* __restrict__ seg_end, const float* __restrict__ fc, int H, float* __restrict__ tab,
+                       int64_t n_nodes) {
     extern __shared__ __align__(16) float sm[];
     float* fcs = sm;                                  // FcOffsets::total(H)
     float* hbuf = fcs + ((FcOffsets::total(H) + 3) & ~3);   // NS_MAX * 33
@@ -287,7 +289,7 @@ node_bias_table_kernel(const float* __restrict__ centres, int64_t ldc, const int
             float t = fcs[FcOffsets::b2(H) + hh];
 #pragma unroll
             for (int i = 0; i < 32; ++i) t = fmaf(w[i], hbuf[pr * 33 + i], t);
-            tab[((int64_t)a * NS_MAX + pr) * H + hh] = t;
+            tab[((int64_t)hh * n_nodes + a) * NS_MAX + pr] = t;
         }
     }
 }
@@ -304,68 +306,110 @@ node_attn_scene_kernel(const float* __restrict__ q, int64_t ldq, const float* __
     const int hh = blockIdx.y;
     constexpr int LD = DK + 4;                        // 16-byte aligned rows whose stride is 4 banks off a multiple of 32:
                                                       // eight lanes reading float4s of eight consecutive rows cover all 32 banks
+    constexpr int QB = 4;                             // queries a warp carries at once: four independent accumulator chains
+                                                      // per lane (the loops are latency-bound, not throughput-bound)
     extern __shared__ __align__(16) float sm[];
     float* qs = sm; float* ks = qs + NS_MAX * LD; float* vs = ks + NS_MAX * LD;
-    float (*ps)[NS_MAX] = reinterpret_cast<float (*)[NS_MAX]>(vs + NS_MAX * LD);      // [warps][NS_MAX]
+    float* ps = vs + NS_MAX * LD;                     // [warps][QB][NS_MAX] probabilities
+    __shared__ int lead[NS_CAND];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int a0 = blockIdx.x * NS_CAND; a0 < min((int)n_nodes, (blockIdx.x + 1) * NS_CAND); ++a0) {
-    const int s0 = seg_start[a0], ns = seg_end[a0] - s0;
-    if (a0 != s0 || ns > NS_MAX) continue;            // block-uniform
-    __syncthreads();                                  // the previous scene's rows are no longer read
-    for (int i = tid; i < ns * (DK / 4); i += NS_THREADS) {
-        const int row = i / (DK / 4), c4 = i % (DK / 4);
-        *reinterpret_cast<float4*>(qs + row * LD + c4 * 4) = __ldg(reinterpret_cast<const float4*>(q + (int64_t)(s0 + row) * ldq + hh * DK) + c4);
-        *reinterpret_cast<float4*>(ks + row * LD + c4 * 4) = __ldg(reinterpret_cast<const float4*>(k + (int64_t)(s0 + row) * ldk + hh * DK) + c4);
-        *reinterpret_cast<float4*>(vs + row * LD + c4 * 4) = __ldg(reinterpret_cast<const float4*>(v + (int64_t)(s0 + row) * ldv + hh * DK) + c4);
+    // candidate nodes of this CTA that start a scene of at most NS_MAX nodes (all lookups in flight at once)
+    if (tid < NS_CAND) {
+        const int a = blockIdx.x * NS_CAND + tid;
+        int ok = 0;
+        if (a < n_nodes) { const int s0 = seg_start[a]; ok = (a == s0 && seg_end[a] - s0 <= NS_MAX) ? 1 : 0; }
+        lead[tid] = ok;
     }
     __syncthreads();
     const float scale = rsqrtf((float)DK);
-    for (int i = warp; i < ns; i += NS_THREADS / 32) {               // one query per warp at a time
-        const float* qi = qs + i * LD;
-        const float* bias = tab + ((int64_t)(s0 + i) * NS_MAX) * H + hh;
-        float sc[NS_MAX / 32];
-        float mx = -FLT_MAX;
+    for (int c = 0; c < NS_CAND; ++c) {
+        if (!lead[c]) continue;                       // block-uniform
+        const int s0 = blockIdx.x * NS_CAND + c, ns = seg_end[s0] - s0;
+        __syncthreads();                              // the previous scene's rows are no longer read
+        for (int i = tid; i < ns * (DK / 4); i += NS_THREADS) {
+            const int row = i / (DK / 4), c4 = i % (DK / 4);
+            *reinterpret_cast<float4*>(qs + row * LD + c4 * 4) = __ldg(reinterpret_cast<const float4*>(q + (int64_t)(s0 + row) * ldq + hh * DK) + c4);
+            *reinterpret_cast<float4*>(ks + row * LD + c4 * 4) = __ldg(reinterpret_cast<const float4*>(k + (int64_t)(s0 + row) * ldk + hh * DK) + c4);
+            *reinterpret_cast<float4*>(vs + row * LD + c4 * 4) = __ldg(reinterpret_cast<const float4*>(v + (int64_t)(s0 + row) * ldv + hh * DK) + c4);
+        }
+        __syncthreads();
+        float* pw = ps + warp * QB * NS_MAX;
+        for (int i0 = warp * QB; i0 < ns; i0 += (NS_THREADS / 32) * QB) {        // QB queries per warp at a time
+            float sc[QB][NS_MAX / 32];
+            // bias rows (64 contiguous floats per query): in flight during the dot products
 #pragma unroll
-        for (int r = 0; r < NS_MAX / 32; ++r) {
-            const int j = lane + 32 * r;
-            float s = -FLT_MAX;
-            if (j < ns) {
-                const float4* kj = reinterpret_cast<const float4*>(ks + j * LD);
-                const float4* q4 = reinterpret_cast<const float4*>(qi);
-                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+            for (int u = 0; u < QB; ++u) {
+                const float* bias = tab + ((int64_t)hh * n_nodes + (s0 + min(i0 + u, ns - 1))) * NS_MAX;
+#pragma unroll
+                for (int r = 0; r < NS_MAX / 32; ++r) sc[u][r] = (lane + 32 * r < ns) ? __ldg(bias + lane + 32 * r) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < NS_MAX / 32; ++r) {
+                const int j = lane + 32 * r;
+                if (r * 32 >= ns) {                              // warp-uniform: no key in this pass
+#pragma unroll
+                    for (int u = 0; u < QB; ++u) sc[u][r] = -FLT_MAX;
+                    continue;
+                }
+                const float4* kj = reinterpret_cast<const float4*>(ks + min(j, ns - 1) * LD);
+                float dot[QB];
+#pragma unroll
+                for (int u = 0; u < QB; ++u) dot[u] = 0.f;
 #pragma unroll
                 for (int d = 0; d < DK / 4; ++d) {
-                    const float4 kv = kj[d], qv = q4[d];
-                    d0 = fmaf(qv.x, kv.x, d0); d1 = fmaf(qv.y, kv.y, d1); d2 = fmaf(qv.z, kv.z, d2); d3 = fmaf(qv.w, kv.w, d3);
+                    const float4 kv = kj[d];
+#pragma unroll
+                    for (int u = 0; u < QB; ++u) {
+                        const float4 qv = *reinterpret_cast<const float4*>(qs + min(i0 + u, ns - 1) * LD + 4 * d);    // broadcast
+                        dot[u] = fmaf(qv.x, kv.x, dot[u]); dot[u] = fmaf(qv.y, kv.y, dot[u]);
+                        dot[u] = fmaf(qv.z, kv.z, dot[u]); dot[u] = fmaf(qv.w, kv.w, dot[u]);
+                    }
                 }
-                s = ((d0 + d1) + (d2 + d3)) * scale + __ldg(bias + (int64_t)j * H);
+#pragma unroll
+                for (int u = 0; u < QB; ++u) sc[u][r] = (j < ns) ? dot[u] * scale + sc[u][r] : -FLT_MAX;
             }
-            sc[r] = s; mx = fmaxf(mx, s);
+#pragma unroll
+            for (int u = 0; u < QB; ++u) {
+                float mx = -FLT_MAX;
+#pragma unroll
+                for (int r = 0; r < NS_MAX / 32; ++r) mx = fmaxf(mx, sc[u][r]);
+                mx = warp_max(mx);
+                float sum = 0.f;
+#pragma unroll
+                for (int r = 0; r < NS_MAX / 32; ++r) {
+                    sc[u][r] = (lane + 32 * r < ns) ? __expf(sc[u][r] - mx) : 0.f;
+                    sum += sc[u][r];
+                }
+                const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+                for (int r = 0; r < NS_MAX / 32; ++r) pw[u * NS_MAX + lane + 32 * r] = sc[u][r] * inv;
+            }
+            __syncwarp();
+            float acc[QB][DK / 32];
+#pragma unroll
+            for (int u = 0; u < QB; ++u)
+#pragma unroll
+                for (int d = 0; d < DK / 32; ++d) acc[u][d] = 0.f;
+            for (int j = 0; j < ns; ++j) {
+                float vv[DK / 32];
+#pragma unroll
+                for (int d = 0; d < DK / 32; ++d) vv[d] = vs[j * LD + lane + 32 * d];
+#pragma unroll
+                for (int u = 0; u < QB; ++u) {
+                    const float pj = pw[u * NS_MAX + j];         // broadcast
+#pragma unroll
+                    for (int d = 0; d < DK / 32; ++d) acc[u][d] = fmaf(pj, vv[d], acc[u][d]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < QB; ++u) {
+                if (i0 + u < ns) {
+#pragma unroll
+                    for (int d = 0; d < DK / 32; ++d) out[(int64_t)(s0 + i0 + u) * ldo + hh * DK + lane + 32 * d] = acc[u][d];
+                }
+            }
+            __syncwarp();                                    // pw is rewritten for this warp's next queries
         }
-        mx = warp_max(mx);
-        float sum = 0.f;
-#pragma unroll
-        for (int r = 0; r < NS_MAX / 32; ++r) {
-            const int j = lane + 32 * r;
-            sc[r] = (j < ns) ? __expf(sc[r] - mx) : 0.f;
-            sum += sc[r];
-        }
-        const float inv = 1.f / warp_sum(sum);
-#pragma unroll
-        for (int r = 0; r < NS_MAX / 32; ++r) ps[warp][lane + 32 * r] = sc[r] * inv;
-        __syncwarp();
-        float acc[DK / 32];
-#pragma unroll
-        for (int d = 0; d < DK / 32; ++d) acc[d] = 0.f;
-        for (int j = 0; j < ns; ++j) {
-            const float pj = ps[warp][j];
-#pragma unroll
-            for (int d = 0; d < DK / 32; ++d) acc[d] = fmaf(pj, vs[j * LD + lane + 32 * d], acc[d]);
-        }
-#pragma unroll
-        for (int d = 0; d < DK / 32; ++d) out[(int64_t)(s0 + i) * ldo + hh * DK + lane + 32 * d] = acc[d];
-        __syncwarp();                                    // ps[warp] is rewritten for this warp's next query
-    }
     }
 }
 
@@ -412,7 +456,7 @@ extern "C" int vlsat_node_bias_table(const float* centres, int64_t ld_centres, c
     if (n_nodes == 0) return VLSAT_OK;
     const size_t smem = sizeof(float) * (((FcOffsets::total(n_heads) + 3) & ~3) + NS_MAX * 33);
     node_bias_table_kernel<<<(unsigned)n_nodes, NA_THREADS, smem, (cudaStream_t)stream>>>(centres, ld_centres, seg_start, seg_end,
-                                                                                         fc_w, n_heads, table);
+                                                                                         fc_w, n_heads, table, n_nodes);
     return finish_launch();
 }
 
@@ -427,7 +471,7 @@ extern "C" int vlsat_node_attn_scene_fwd(const float* q, int64_t ldq, const floa
     if (n_nodes == 0) return VLSAT_OK;
     const dim3 grid((unsigned)ceil_div(n_nodes, NS_CAND), (unsigned)n_heads);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = sizeof(float) * (3 * NS_MAX * (dk + 4) + (NS_THREADS / 32) * NS_MAX);
+    const size_t smem = sizeof(float) * (3 * NS_MAX * (dk + 4) + (NS_THREADS / 32) * 4 * NS_MAX);
     if (dk == 64) {
         cudaFuncSetAttribute(node_attn_scene_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         node_attn_scene_kernel<64><<<grid, NS_THREADS, smem, st>>>(q, ldq, k, ldk, v, ldv, table, seg_start, seg_end, n_heads, out, ldo, n_nodes);

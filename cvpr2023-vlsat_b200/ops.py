@@ -414,14 +414,14 @@ def scene_ranges(batch_ids: torch.Tensor):
 
 
 def node_bias_table(centres, seg_start, seg_end, fc_pack, n_heads: int) -> torch.Tensor:
-    """Distance-bias table of the scene-resident node attention: [N, 64, H], row (a, j) = bias of query a towards the j-th
-    node of its scene (scenes of more than 64 nodes are left to the streaming kernel, which evaluates the MLP in place)."""
+    """Distance-bias table of the scene-resident node attention: [H, N, 64], entry (h, a, j) = bias of query a towards the
+    j-th node of its scene (scenes of more than 64 nodes are left to the streaming kernel, which evaluates the MLP in place)."""
     cp, ldc = _rows(centres, "centres")
     n = centres.shape[0]
     cap = int(_lib.load().vlsat_node_bias_table_max_scene())
     if fc_pack.numel() != FC_PACK_HEAD + 33 * n_heads:
         raise ValueError("node_bias_table: packed self_attn_fc has the wrong size for this head count")
-    tab = torch.empty((n, cap, n_heads), device=centres.device, dtype=torch.float32)
+    tab = torch.empty((n_heads, n, cap), device=centres.device, dtype=torch.float32)
     _lib.check(_call("vlsat_node_bias_table", cp, ldc, seg_start.data_ptr(), seg_end.data_ptr(), _f32(fc_pack, "fc_pack").data_ptr(),
                      n_heads, tab.data_ptr(), n, _stream()), "vlsat_node_bias_table")
     return tab
@@ -439,7 +439,7 @@ def node_attn(q, k, v, centres, seg_start, seg_end, fc_pack, n_heads: int, bias_
     out = torch.empty((n, d), device=q.device, dtype=torch.float32)
     skip = 0
     if bias_table is not None and dk in (32, 64) and ldv % 4 == 0 and (qp | kp | vp_) % 16 == 0:
-        skip = bias_table.shape[1]
+        skip = bias_table.shape[2]
         st = _call("vlsat_node_attn_scene_fwd", qp, ldq, kp, ldk, vp_, ldv, bias_table.data_ptr(), seg_start.data_ptr(),
                    seg_end.data_ptr(), n_heads, dk, out.data_ptr(), d, n, _stream())
         _lib.check(st, "vlsat_node_attn_scene_fwd")

@@ -166,7 +166,7 @@ int vlsat_node_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk
                         float* out, int64_t ldo, int64_t n_nodes, int skip_scenes_upto, void* stream);
 /* Scene-resident form of the same attention for scenes of up to vlsat_node_bias_table_max_scene() (= 64) nodes.
  * The bias depends only on the centres and MMG.forward evaluates 2*depth attentions over the same scenes, so it is
- * computed once: vlsat_node_bias_table fills table[(a*64 + j)*H + h] = MLP(...)[h] for query a and the j-th node of its
+ * computed once: vlsat_node_bias_table fills table[(h*n_nodes + a)*64 + j] = MLP(...)[h] for query a and the j-th node of its
  * scene (rows of larger scenes are left untouched); vlsat_node_attn_scene_fwd then serves every scene of <= 64 nodes
  * with one CTA per (scene, head) holding that head's Q, K, V rows in shared memory, and leaves the rows of larger
  * scenes untouched: call vlsat_node_attn_fwd(..., skip_scenes_upto = 64) for those (it skips the scenes already
