@@ -6,6 +6,11 @@
 
 namespace vlsat {
 long long g_launch_count = 0;
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("VLSAT_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on != 0;
+}
 int linear_simt(const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int64_t, int64_t,
                 const vlsat_epilogue*, cudaStream_t);
 bool linear_tc_eligible(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, int);

@@ -16,6 +16,29 @@ inline int finish_launch(int n_kernels = 1) {
 
 constexpr int kNumSMs = 148;   // B200
 
+// Programmatic dependent launch. Every kernel of the forward path is launched with the programmatic-stream-serialisation
+// attribute and starts with pdl_launch_dependents() (the next kernel may be scheduled as soon as all CTAs of this one have
+// started) and, after its purely local prologue (barrier init, TMEM allocation, descriptor prefetch), pdl_wait(), which
+// blocks until the preceding grid has completed and its memory is visible. Launch latency and prologues of the ~120
+// kernels of a forward overlap the tail of their predecessors. The wait precedes every global access and every early
+// exit, so completion stays transitive along the chain. VLSAT_PDL=0 switches the attribute off (the instructions are then
+// no-ops).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_launch_dependents(); pdl_wait(); }      // kernels without a local prologue
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);       // errors surface in finish_launch()
+}
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -77,6 +77,7 @@ __device__ __forceinline__ void mma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, ui
 
 __global__ void bf16_split_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int64_t cols,
                                   uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t ld_out) {
+    pdl_entry();
     const int64_t c4 = (cols + 3) >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * c4) return;
@@ -110,6 +111,7 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
                        const __grid_constant__ CUtensorMap tm_vhi, const __grid_constant__ CUtensorMap tm_vlo,
                        float* __restrict__ out, int64_t ldo, float* __restrict__ lse, FlashPartial part,
                        int nq, int nk, int n_heads, int tiles_per_split, float scale_log2e) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps LDS/STS
     uint8_t* k_smem = smem;                                  // 2 stages x (K_hi | K_lo)
@@ -148,6 +150,7 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();
 
     if (warp == 0) {
         for (int i = 0; i < n_tiles; ++i) {
@@ -374,6 +377,7 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
 // Combine the KV splits: out = sum_s o_s 2^(m_s - m) / sum_s l_s 2^(m_s - m)
 __global__ void flash_merge_kernel(FlashPartial part, int splits, int nq, int n_heads, float* __restrict__ out, int64_t ldo,
                                    float* __restrict__ lse) {
+    pdl_entry();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (q, head, 4-dim group)
     const int groups = FB_DK / 4;
     if (idx >= (int64_t)nq * n_heads * groups) return;
@@ -399,7 +403,7 @@ __global__ void flash_merge_kernel(FlashPartial part, int splits, int nq, int n_
 int bf16_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ld_out, cudaStream_t st) {
     const int64_t n = rows * ((cols + 3) / 4);
     if (n == 0) return VLSAT_OK;
-    bf16_split_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(x, ldx, rows, cols, hi, lo, ld_out);
+    launch_k(bf16_split_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, st, x, ldx, rows, cols, hi, lo, ld_out);
     return finish_launch();
 }
 
@@ -450,12 +454,12 @@ int flash_attn_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq, con
     cudaFuncSetAttribute(flash_attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((unsigned)ceil_div(nq, 2 * FB_BQ), (unsigned)n_heads, (unsigned)splits);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)dk);
-    flash_attn_bf16_kernel<<<grid, FB_THREADS, smem, st>>>(q_hi, q_lo, ldq, tk, tkl, tv, tvl, out, ldo, lse, part, (int)nq, (int)nk,
+    launch_k(flash_attn_bf16_kernel, grid, dim3(FB_THREADS), smem, st, q_hi, q_lo, ldq, tk, tkl, tv, tvl, out, ldo, lse, part, (int)nq, (int)nk,
                                                            n_heads, tiles_per_split, scale_log2e);
     int launches = 1;
     if (splits > 1) {
         const int64_t n = nq * n_heads * (FB_DK / 4);
-        flash_merge_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(part, splits, (int)nq, n_heads, out, ldo, lse);
+        launch_k(flash_merge_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, st, part, splits, (int)nq, n_heads, out, ldo, lse);
         ++launches;
     }
     return finish_launch(launches);

@@ -15,10 +15,12 @@ namespace vlsat {
 
 // ---------------------------------------------------------------------------------------- CSR build
 __global__ void csr_zero_kernel(int32_t* counts, int64_t n) {
+    pdl_entry();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) counts[i] = 0;
 }
 __global__ void csr_count_kernel(const int64_t* __restrict__ row, int64_t n_edges, int64_t n_nodes, int32_t* counts) {
+    pdl_entry();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     const int64_t r = row[e];
@@ -26,6 +28,7 @@ __global__ void csr_count_kernel(const int64_t* __restrict__ row, int64_t n_edge
 }
 // single-CTA exclusive scan: row_ptr[0..n] from counts[0..n-1]; cursor <- row_ptr (for the fill pass)
 __global__ void csr_scan_kernel(int32_t* counts_cursor, int64_t n, int32_t* row_ptr) {
+    pdl_entry();
     __shared__ int32_t warp_tot[32];
     __shared__ int32_t carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -57,6 +60,7 @@ __global__ void csr_scan_kernel(int32_t* counts_cursor, int64_t n, int32_t* row_
 }
 __global__ void csr_fill_kernel(const int64_t* __restrict__ row, int64_t n_edges, int64_t n_nodes,
                                 int32_t* cursor, int32_t* tmp) {
+    pdl_entry();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     const int64_t r = row[e];
@@ -65,6 +69,7 @@ __global__ void csr_fill_kernel(const int64_t* __restrict__ row, int64_t n_edges
 // one warp per node: rank-sort its segment ascending so the permutation is the STABLE sort by row
 __global__ void csr_sort_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ tmp,
                                 int32_t* __restrict__ perm, int64_t n_nodes) {
+    pdl_entry();
     const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (node >= n_nodes) return;
@@ -100,6 +105,7 @@ gat_edge_kernel(const float* __restrict__ q, int64_t ldq, const float* __restric
                 const float* __restrict__ c2, const float* __restrict__ c2b,
                 int64_t n_nodes, int64_t n_edges, GatDims g, int aggr, int use_edge,
                 float* __restrict__ xx, int64_t ld_xx, float* __restrict__ prob, int32_t* __restrict__ argmax) {
+    pdl_entry();
     extern __shared__ __align__(16) float sm[];
     const float* c1s;                                  // [hid][s_c1]   C1 rows (K-major)
     const float* c2s;                                  // [d_o][s_c2]
@@ -268,12 +274,12 @@ extern "C" int vlsat_build_csr(const int64_t* index_row, int64_t n_edges, int64_
     int32_t* cursor = (int32_t*)workspace;
     int32_t* tmp = cursor + n_nodes + 1;
     int launches = 2;
-    csr_zero_kernel<<<(unsigned)ceil_div(n_nodes + 1, 256), 256, 0, st>>>(cursor, n_nodes + 1);
-    if (n_edges) { csr_count_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, st>>>(index_row, n_edges, n_nodes, cursor); ++launches; }
-    csr_scan_kernel<<<1, 1024, 0, st>>>(cursor, n_nodes, row_ptr);
+    launch_k(csr_zero_kernel, dim3((unsigned)ceil_div(n_nodes + 1, 256)), dim3(256), 0, st, cursor, n_nodes + 1);
+    if (n_edges) { launch_k(csr_count_kernel, dim3((unsigned)ceil_div(n_edges, 256)), dim3(256), 0, st, index_row, n_edges, n_nodes, cursor); ++launches; }
+    launch_k(csr_scan_kernel, dim3(1), dim3(1024), 0, st, cursor, n_nodes, row_ptr);
     if (n_edges) {
-        csr_fill_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, st>>>(index_row, n_edges, n_nodes, cursor, tmp);
-        csr_sort_kernel<<<(unsigned)ceil_div(n_nodes * 32, 256), 256, 0, st>>>(row_ptr, tmp, perm, n_nodes);
+        launch_k(csr_fill_kernel, dim3((unsigned)ceil_div(n_edges, 256)), dim3(256), 0, st, index_row, n_edges, n_nodes, cursor, tmp);
+        launch_k(csr_sort_kernel, dim3((unsigned)ceil_div(n_nodes * 32, 256)), dim3(256), 0, st, row_ptr, tmp, perm, n_nodes);
         launches += 2;
     }
     return finish_launch(launches);
@@ -307,7 +313,7 @@ extern "C" int vlsat_gat_edge_fwd(const float* q, int64_t ldq, const float* v, i
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t ctas_per_sm = std::max<int64_t>(1, (int64_t)(227 * 1024) / (int64_t)(smem + 1024));
     const unsigned grid = (unsigned)std::min<int64_t>(n_nodes, ctas_per_sm * kNumSMs);
-    kern<<<grid, GAT_THREADS, smem, (cudaStream_t)stream>>>(
+    launch_k(kern, grid, dim3(GAT_THREADS), smem, (cudaStream_t)stream, 
         q, ldq, v, ldv, k, ldk, edge_index, row_ptr, perm, c1, c1_bias, c2, c2_bias, n_nodes, n_edges, g, aggr, use_edge, xx, ld_xx, prob, argmax);
     return finish_launch();
 }

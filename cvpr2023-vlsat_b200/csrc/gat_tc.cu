@@ -86,6 +86,7 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
                    const __grid_constant__ CUtensorMap tm_c1hi, const __grid_constant__ CUtensorMap tm_c1lo,
                    const __grid_constant__ CUtensorMap tm_c2hi, const __grid_constant__ CUtensorMap tm_c2lo,
                    const GatTcParams p) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps LDS/STS
     const int hc = (p.hid + 63) / 64;                        // 128-byte (64 bf16) column blocks of C2
@@ -129,6 +130,7 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                                            // everything above is local to the CTA
 
     if (warp == 0) {
         if (elect_one()) {
@@ -401,6 +403,7 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
 }
 
 __global__ void fill_int_kernel(int* p, int64_t n, int v) {
+    pdl_entry();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
@@ -408,6 +411,7 @@ __global__ void fill_int_kernel(int* p, int64_t n, int v) {
 // xx[n, c*H + h] = decode(xx_enc[n, h*d_o + c]); untouched (INT_MIN) -> 0
 // and restore the INT_MIN fill, so the same workspace can be handed to the next call with workspace_ready = 1
 __global__ void gat_finalize_kernel(int* __restrict__ enc, float* __restrict__ xx, int64_t ld_xx, int64_t n_nodes, int H, int d_o) {
+    pdl_entry();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int D_a = H * d_o;
     if (idx >= n_nodes * D_a) return;
@@ -423,6 +427,7 @@ __global__ void gat_finalize_kernel(int* __restrict__ enc, float* __restrict__ x
 __global__ void permute_rows_kernel(const float* __restrict__ in, int64_t ld_in, const int32_t* __restrict__ idx,
                                     int64_t rows, int cols4, float* __restrict__ out, int64_t ld_out, int gather,
                                     uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    pdl_entry();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * cols4) return;
     const int64_t i = t / cols4; const int c = (int)(t % cols4) * 4;
@@ -438,6 +443,7 @@ __global__ void permute_rows_kernel(const float* __restrict__ in, int64_t ld_in,
     }
 }
 __global__ void permute_edges_kernel(const int64_t* __restrict__ ei, const int32_t* __restrict__ perm, int64_t n_edges, int64_t* __restrict__ out) {
+    pdl_entry();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_edges) return;
     const int64_t j = perm[i];
@@ -458,7 +464,7 @@ extern "C" int vlsat_permute_rows(const float* in, int64_t ld_in, const int32_t*
     const int64_t n = rows * (cols / 4);
     VLSAT_REQUIRE((split_hi == nullptr) == (split_lo == nullptr));
     VLSAT_SUPPORT(!split_hi || (((uintptr_t)split_hi | (uintptr_t)split_lo) % 8 == 0));
-    permute_rows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, idx, rows, cols / 4, out, ld_out, gather,
+    launch_k(permute_rows_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, in, ld_in, idx, rows, cols / 4, out, ld_out, gather,
                                                                                       (uint16_t*)split_hi, (uint16_t*)split_lo);
     return finish_launch();
 }
@@ -467,7 +473,7 @@ extern "C" int vlsat_permute_edges(const int64_t* edge_index, const int32_t* per
     VLSAT_REQUIRE(n_edges >= 0);
     if (n_edges == 0) return VLSAT_OK;
     VLSAT_REQUIRE(edge_index && perm && out);
-    permute_edges_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(edge_index, perm, n_edges, out);
+    launch_k(permute_edges_kernel, dim3((unsigned)ceil_div(n_edges, 256)), dim3(256), 0, (cudaStream_t)stream, edge_index, perm, n_edges, out);
     return finish_launch();
 }
 
@@ -490,7 +496,7 @@ extern "C" int vlsat_gat_edge_tc_fwd(const void* k_hi, const void* k_lo, const f
     int* enc = (int*)workspace;
     int launches = 1;
     if (!workspace_ready) {
-        fill_int_kernel<<<(unsigned)ceil_div(n_nodes * D_a, 256), 256, 0, st>>>(enc, n_nodes * D_a, INT_MIN);
+        launch_k(fill_int_kernel, dim3((unsigned)ceil_div(n_nodes * D_a, 256)), dim3(256), 0, st, enc, n_nodes * D_a, INT_MIN);
         ++launches;
     }
     if (n_edges > 0) {
@@ -516,9 +522,9 @@ extern "C" int vlsat_gat_edge_tc_fwd(const void* k_hi, const void* k_lo, const f
         p.xx_enc = enc; p.prob = prob; p.trace = g_trace; { const char* d = getenv("VLSAT_GAT_DBG"); p.dbg = d ? atoi(d) : 0; } p.n_edges = n_edges; p.H = n_heads; p.hid = hid; p.d_o = d_o;
         const int64_t n_tiles = ceil_div(n_edges * n_heads, GT_ROWS);
         const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, kNumSMs);
-        kern<<<grid, GT_THREADS, smem, st>>>(tk, tkl, t1, t1l, t2, t2l, p);
+        launch_k(kern, dim3(grid), dim3(GT_THREADS), smem, st, tk, tkl, t1, t1l, t2, t2l, p);
         ++launches;
     }
-    gat_finalize_kernel<<<(unsigned)ceil_div(n_nodes * D_a, 256), 256, 0, st>>>(enc, xx, ld_xx, n_nodes, n_heads, d_o);
+    launch_k(gat_finalize_kernel, dim3((unsigned)ceil_div(n_nodes * D_a, 256)), dim3(256), 0, st, enc, xx, ld_xx, n_nodes, n_heads, d_o);
     return finish_launch(launches);
 }

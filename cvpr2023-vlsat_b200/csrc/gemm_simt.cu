@@ -12,6 +12,7 @@ namespace vlsat {
 template <int BM, int BN, int T, bool VEC>
 __global__ void __launch_bounds__((BM / T) * (BN / T))
 linear_simt_kernel(const LinearArgs a) {
+    pdl_entry();
     constexpr int BK = 16;
     constexpr int NT = (BM / T) * (BN / T);
     constexpr int H = T / 4;                       // number of 4-wide halves per dimension
@@ -133,8 +134,8 @@ template <int BM, int BN, int T>
 static void launch_simt(const LinearArgs& a, bool vec, cudaStream_t st) {
     dim3 grid((unsigned)ceil_div(a.N, BN), (unsigned)ceil_div(a.M, BM));
     constexpr int NT = (BM / T) * (BN / T);
-    if (vec) linear_simt_kernel<BM, BN, T, true><<<grid, NT, 0, st>>>(a);
-    else     linear_simt_kernel<BM, BN, T, false><<<grid, NT, 0, st>>>(a);
+    if (vec) launch_k(linear_simt_kernel<BM, BN, T, true>, grid, dim3(NT), 0, st, a);
+    else     launch_k(linear_simt_kernel<BM, BN, T, false>, grid, dim3(NT), 0, st, a);
 }
 
 int linear_simt(const float* x, int64_t ldx, const float* w, int64_t ldw, float* y, int64_t ldy,

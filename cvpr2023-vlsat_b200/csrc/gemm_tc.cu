@@ -41,6 +41,7 @@ constexpr int TC_A_TILE = TC_BM * 128;    // bytes
 // hi = round-to-nearest tf32 (low 13 mantissa bits zero), lo = x - hi
 __global__ void tf32_split_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int64_t cols,
                                   float* __restrict__ hi, float* __restrict__ lo) {
+    pdl_entry();
     const int64_t c4 = cols >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * c4) return;
@@ -80,6 +81,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
     uint64_t* acc_empty = acc_full + 2;                     // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int BK = (KD == Kind::TF32) ? TC_BK : 2 * TC_BK;      // K elements per 128-byte block
     const int num_kb = (int)((a.K + BK - 1) / BK);
@@ -98,6 +100,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                                             // everything above is local; operands of the previous kernel below
 
     if (warp == 0) {
         // warp-uniform loops; one elected lane issues (keeps TMA / MMA issue on the uniform datapath)
@@ -357,7 +360,7 @@ size_t linear_tc_workspace_bytes(int64_t M, int64_t N, int64_t K, bool need_x, b
 int tf32_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, cudaStream_t st) {
     const int64_t n = rows * (cols / 4);
     if (n == 0) return VLSAT_OK;
-    tf32_split_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(x, ldx, rows, cols, hi, lo);
+    launch_k(tf32_split_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, st, x, ldx, rows, cols, hi, lo);
     return finish_launch();
 }
 
@@ -371,7 +374,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tal, const CUtens
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t n_tiles = ceil_div(a.N, BN) * ceil_div(a.M, TC_BM);
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, kNumSMs);
-    kern<<<grid, TC_THREADS, smem, st>>>(ta, tal, tb, tbl, ty, tsh, tsl, a);
+    launch_k(kern, dim3(grid), dim3(TC_THREADS), smem, st, ta, tal, tb, tbl, ty, tsh, tsl, a);
     return finish_launch();
 }
 

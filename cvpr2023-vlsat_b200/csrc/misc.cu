@@ -7,6 +7,7 @@ namespace vlsat {
 
 __global__ void edge_descriptor_kernel(const float* __restrict__ desc, const int64_t* __restrict__ ei,
                                        int64_t n_edges, float* __restrict__ out) {
+    pdl_entry();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_edges * 11) return;
     const int64_t e = idx / 11; const int c = (int)(idx % 11);
@@ -19,6 +20,7 @@ constexpr int LN_MAX_PER_LANE = 32;
 __global__ void add_layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ res, int64_t ldr,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float* __restrict__ y, int64_t ldy, int64_t M, int D, float eps, int relu) {
+    pdl_entry();
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -59,6 +61,7 @@ __global__ void add_layernorm_vec_kernel(const float* __restrict__ x, int64_t ld
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float* __restrict__ y, int64_t ldy, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
                                          int64_t ld_split, int64_t M, float eps, int relu) {
+    pdl_entry();
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -100,6 +103,7 @@ __global__ void add_layernorm_vec_kernel(const float* __restrict__ x, int64_t ld
 
 // y = relu(x) with the bf16 (hi, lo) pair of y as an optional second output (flat, numel % 4 == 0)
 __global__ void relu_pair_kernel(const float* __restrict__ x, float* __restrict__ y, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t n4) {
+    pdl_entry();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
@@ -112,6 +116,7 @@ __global__ void relu_pair_kernel(const float* __restrict__ x, float* __restrict_
 }
 
 __global__ void relu_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n4, int64_t n) {
+    pdl_entry();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n4) {
         float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -121,11 +126,13 @@ __global__ void relu_kernel(const float* __restrict__ x, float* __restrict__ y, 
     if (i == 0) for (int64_t j = n4 * 4; j < n; ++j) y[j] = fmaxf(x[j], 0.f);
 }
 __global__ void relu_scalar_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+    pdl_entry();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = fmaxf(x[i], 0.f);
 }
 
 __global__ void row_l2norm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t M, int D) {
+    pdl_entry();
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -137,6 +144,7 @@ __global__ void row_l2norm_kernel(const float* __restrict__ x, float* __restrict
 }
 
 __global__ void spatial_tail_kernel(const float* __restrict__ desc, float* __restrict__ out, int64_t ld, int col0, int64_t n) {
+    pdl_entry();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * 8) return;
     const int64_t r = idx / 8; const int c = (int)(idx % 8);
@@ -153,7 +161,7 @@ extern "C" int vlsat_edge_descriptor_fwd(const float* desc, int64_t n_nodes, con
     VLSAT_REQUIRE(n_edges >= 0 && n_nodes >= 0);
     if (n_edges == 0) return VLSAT_OK;
     VLSAT_REQUIRE(desc && edge_index && out);
-    edge_descriptor_kernel<<<(unsigned)ceil_div(n_edges * 11, 256), 256, 0, (cudaStream_t)stream>>>(desc, edge_index, n_edges, out);
+    launch_k(edge_descriptor_kernel, dim3((unsigned)ceil_div(n_edges * 11, 256)), dim3(256), 0, (cudaStream_t)stream, desc, edge_index, n_edges, out);
     return finish_launch();
 }
 
@@ -174,7 +182,7 @@ extern "C" int vlsat_add_layernorm_fwd(const float* x, int64_t ldx, const float*
                      (!y || al16(y)) && al16(gamma) && al16(beta) &&
                      (!split_hi || (ld_split % 4 == 0 && ((uintptr_t)split_hi & 7) == 0 && ((uintptr_t)split_lo & 7) == 0));
     uint16_t* hi = (uint16_t*)split_hi; uint16_t* lo = (uint16_t*)split_lo;
-#define VLSAT_LN(NV_) add_layernorm_vec_kernel<NV_><<<grid, 256, 0, st>>>(x, ldx, res, ld_res, gamma, beta, y, ldy, hi, lo, ld_split, M, eps, relu)
+#define VLSAT_LN(NV_) launch_k(add_layernorm_vec_kernel<NV_>, grid, dim3(256), 0, st, x, ldx, res, ld_res, gamma, beta, y, ldy, hi, lo, ld_split, M, eps, relu)
     if (vec) {
         switch (D / 128) {
             case 1: VLSAT_LN(1); break; case 2: VLSAT_LN(2); break; case 3: VLSAT_LN(3); break; case 4: VLSAT_LN(4); break;
@@ -184,7 +192,7 @@ extern "C" int vlsat_add_layernorm_fwd(const float* x, int64_t ldx, const float*
     }
 #undef VLSAT_LN
     VLSAT_SUPPORT(!split_hi && y);            // the pair output needs the vectorised layout
-    add_layernorm_kernel<<<grid, 256, 0, st>>>(x, ldx, res, ld_res, gamma, beta, y, ldy, M, D, eps, relu);
+    launch_k(add_layernorm_kernel, grid, dim3(256), 0, st, x, ldx, res, ld_res, gamma, beta, y, ldy, M, D, eps, relu);
     return finish_launch();
 }
 
@@ -194,9 +202,9 @@ extern "C" int vlsat_relu_fwd(const float* x, float* y, int64_t numel, void* str
     VLSAT_REQUIRE(x && y);
     if (((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0)) {
         const int64_t n4 = numel / 4;
-        relu_kernel<<<(unsigned)ceil_div(n4 > 0 ? n4 : 1, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n4, numel);
+        launch_k(relu_kernel, dim3((unsigned)ceil_div(n4 > 0 ? n4 : 1, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, n4, numel);
     } else {
-        relu_scalar_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, (cudaStream_t)stream>>>(x, y, numel);
+        launch_k(relu_scalar_kernel, dim3((unsigned)ceil_div(numel, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, numel);
     }
     return finish_launch();
 }
@@ -207,7 +215,7 @@ extern "C" int vlsat_relu_pair_fwd(const float* x, float* y, void* split_hi, voi
     VLSAT_REQUIRE(x && split_hi && split_lo);
     VLSAT_SUPPORT(numel % 4 == 0 && ((uintptr_t)x % 16 == 0) && (!y || (uintptr_t)y % 16 == 0) && ((uintptr_t)split_hi % 8 == 0) &&
                   ((uintptr_t)split_lo % 8 == 0));
-    relu_pair_kernel<<<(unsigned)ceil_div(numel / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, y, (uint16_t*)split_hi, (uint16_t*)split_lo, numel / 4);
+    launch_k(relu_pair_kernel, dim3((unsigned)ceil_div(numel / 4, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, (uint16_t*)split_hi, (uint16_t*)split_lo, numel / 4);
     return finish_launch();
 }
 
@@ -215,7 +223,7 @@ extern "C" int vlsat_row_l2norm_fwd(const float* x, float* y, int64_t M, int D, 
     VLSAT_REQUIRE(M >= 0 && D >= 1);
     if (M == 0) return VLSAT_OK;
     VLSAT_REQUIRE(x && y);
-    row_l2norm_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, y, M, D);
+    launch_k(row_l2norm_kernel, dim3((unsigned)ceil_div(M * 32, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, M, D);
     return finish_launch();
 }
 
@@ -223,6 +231,6 @@ extern "C" int vlsat_spatial_tail_fwd(const float* desc, float* out, int64_t ld_
     VLSAT_REQUIRE(n_nodes >= 0);
     if (n_nodes == 0) return VLSAT_OK;
     VLSAT_REQUIRE(desc && out && col0 >= 0 && col0 + 8 <= ld_out);
-    spatial_tail_kernel<<<(unsigned)ceil_div(n_nodes * 8, 256), 256, 0, (cudaStream_t)stream>>>(desc, out, ld_out, col0, n_nodes);
+    launch_k(spatial_tail_kernel, dim3((unsigned)ceil_div(n_nodes * 8, 256)), dim3(256), 0, (cudaStream_t)stream, desc, out, ld_out, col0, n_nodes);
     return finish_launch();
 }

@@ -19,6 +19,7 @@ struct FcOffsets {
 
 __global__ void scene_ranges_kernel(const int64_t* __restrict__ bid, int64_t n, int32_t* seg_start,
                                     int32_t* seg_end, int32_t* err) {
+    pdl_entry();
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     const int64_t me = bid[a];
@@ -41,6 +42,7 @@ node_attn_kernel(const float* __restrict__ q, int64_t ldq, const float* __restri
                  const float* __restrict__ v, int64_t ldv, const float* __restrict__ centres, int64_t ldc,
                  const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_end,
                  const float* __restrict__ fc, int H, float* __restrict__ out, int64_t ldo, int skip_upto) {
+    pdl_entry();
     extern __shared__ __align__(16) float sm[];
     if (seg_end[blockIdx.x] - seg_start[blockIdx.x] <= skip_upto) return;    // served by node_attn_scene_kernel
     float* fcs = sm;                                  // FcOffsets::total(H)
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(NA_THREADS)
 node_bias_table_kernel(const float* __restrict__ centres, int64_t ldc, const int32_t* __restrict__ seg_start,
                        const int32_t* __restrict__ seg_end, const float* __restrict__ fc, int H, float* __restrict__ tab,
                        int64_t n_nodes) {
+    pdl_entry();
     extern __shared__ __align__(16) float sm[];
     float* fcs = sm;                                  // FcOffsets::total(H)
     float* hbuf = fcs + ((FcOffsets::total(H) + 3) & ~3);   // NS_MAX * 33
@@ -303,6 +306,7 @@ node_attn_scene_kernel(const float* __restrict__ q, int64_t ldq, const float* __
                        const float* __restrict__ v, int64_t ldv, const float* __restrict__ tab,
                        const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_end, int H,
                        float* __restrict__ out, int64_t ldo, int64_t n_nodes) {
+    pdl_entry();
     const int hh = blockIdx.y;
     constexpr int LD = DK + 4;                        // 16-byte aligned rows whose stride is 4 banks off a multiple of 32:
                                                       // eight lanes reading float4s of eight consecutive rows cover all 32 banks
@@ -422,7 +426,7 @@ extern "C" int vlsat_scene_ranges(const int64_t* batch_ids, int64_t n_nodes, int
     VLSAT_REQUIRE(batch_ids && seg_start && seg_end && n_nodes >= 0);
     VLSAT_SUPPORT(n_nodes < 0x7fffffff);
     if (n_nodes == 0) return VLSAT_OK;
-    scene_ranges_kernel<<<(unsigned)ceil_div(n_nodes, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(scene_ranges_kernel, dim3((unsigned)ceil_div(n_nodes, 256)), dim3(256), 0, (cudaStream_t)stream, 
         batch_ids, n_nodes, seg_start, seg_end, err_flag);
     return finish_launch();
 }
@@ -439,7 +443,7 @@ extern "C" int vlsat_node_attn_fwd(const float* q, int64_t ldq, const float* k, 
     const size_t smem = sizeof(float) * (((FcOffsets::total(n_heads) + 3) & ~3) + n_heads * dk + NA_TK * 33 + NA_TK * n_heads);
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)n_nodes;
-#define LAUNCH(DK_) node_attn_kernel<DK_><<<grid, NA_THREADS, smem, st>>>(q, ldq, k, ldk, v, ldv, centres, ld_centres, \
+#define LAUNCH(DK_) launch_k(node_attn_kernel<DK_>, grid, dim3(NA_THREADS), smem, st, q, ldq, k, ldk, v, ldv, centres, ld_centres, \
         seg_start, seg_end, fc_w, n_heads, out, ldo, skip_scenes_upto)
     if (dk == 64) LAUNCH(64); else if (dk == 128) LAUNCH(128); else LAUNCH(32);
 #undef LAUNCH
@@ -455,7 +459,7 @@ extern "C" int vlsat_node_bias_table(const float* centres, int64_t ld_centres, c
     VLSAT_SUPPORT(n_heads >= 1 && n_heads <= NA_MAXH && n_nodes < 0x7fffffff);
     if (n_nodes == 0) return VLSAT_OK;
     const size_t smem = sizeof(float) * (((FcOffsets::total(n_heads) + 3) & ~3) + NS_MAX * 33);
-    node_bias_table_kernel<<<(unsigned)n_nodes, NA_THREADS, smem, (cudaStream_t)stream>>>(centres, ld_centres, seg_start, seg_end,
+    launch_k(node_bias_table_kernel, dim3((unsigned)n_nodes), dim3(NA_THREADS), smem, (cudaStream_t)stream, centres, ld_centres, seg_start, seg_end,
                                                                                          fc_w, n_heads, table, n_nodes);
     return finish_launch();
 }
@@ -474,9 +478,9 @@ extern "C" int vlsat_node_attn_scene_fwd(const float* q, int64_t ldq, const floa
     const size_t smem = sizeof(float) * (3 * NS_MAX * (dk + 4) + (NS_THREADS / 32) * 4 * NS_MAX);
     if (dk == 64) {
         cudaFuncSetAttribute(node_attn_scene_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        node_attn_scene_kernel<64><<<grid, NS_THREADS, smem, st>>>(q, ldq, k, ldk, v, ldv, table, seg_start, seg_end, n_heads, out, ldo, n_nodes);
+        launch_k(node_attn_scene_kernel<64>, grid, dim3(NS_THREADS), smem, st, q, ldq, k, ldk, v, ldv, table, seg_start, seg_end, n_heads, out, ldo, n_nodes);
     } else {
-        node_attn_scene_kernel<32><<<grid, NS_THREADS, smem, st>>>(q, ldq, k, ldk, v, ldv, table, seg_start, seg_end, n_heads, out, ldo, n_nodes);
+        launch_k(node_attn_scene_kernel<32>, grid, dim3(NS_THREADS), smem, st, q, ldq, k, ldk, v, ldv, table, seg_start, seg_end, n_heads, out, ldo, n_nodes);
     }
     return finish_launch();
 }

@@ -79,6 +79,7 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
                    const float* __restrict__ w2, const float* __restrict__ b2,
                    const float* __restrict__ w3, const float* __restrict__ b3, int c_out,
                    float* __restrict__ out, int32_t* __restrict__ argmax) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     PointNetTcSmem& s = *reinterpret_cast<PointNetTcSmem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));   // keeps the shared address space (LDS/STS)
     uint64_t* b1_ready = &s.bars[0]; uint64_t* d2_full = &s.bars[1]; uint64_t* b2_ready = &s.bars[2]; uint64_t* d3_full = &s.bars[3];
@@ -101,6 +102,7 @@ pointnet_tc_kernel(const float* __restrict__ x, int64_t n_obj, int c_in_rt, int6
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = s.tmem_holder;
+    pdl_wait();                                                  // everything above is local to the CTA
 
     if (warp == 0) {
         // ------------------------------------------------------------------ MMA issue (one elected lane)
@@ -303,8 +305,8 @@ int pointnet_tc(const float* x, int64_t n_obj, int c_in, int64_t n_pts, const fl
 #define PT_LAUNCH(CIN_)                                                                                          \
     do {                                                                                                          \
         cudaFuncSetAttribute(pointnet_tc_kernel<CIN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        pointnet_tc_kernel<CIN_><<<grid, PT_THREADS, smem, st>>>(x, n_obj, c_in, n_pts, w1, b1, w2, b2, w3, b3,   \
-                                                                 c_out, out, argmax);                             \
+        launch_k(pointnet_tc_kernel<CIN_>, dim3(grid), dim3(PT_THREADS), smem, st, x, n_obj, c_in, n_pts, w1, b1, w2, b2, w3, b3, \
+                 c_out, out, argmax);                                                                             \
     } while (0)
     switch (c_in) {
         case 3: PT_LAUNCH(3); break;
