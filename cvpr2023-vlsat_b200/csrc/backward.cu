@@ -17,6 +17,7 @@ namespace vlsat {
 // feed a GEMM whose reduction length is rounded up to a multiple of 4.
 __global__ void transpose_kernel(const float* __restrict__ in, int64_t ld_in, int64_t bs_in, float* __restrict__ out,
                                  int64_t ld_out, int64_t bs_out, int64_t rows, int64_t cols) {
+    pdl_entry();
     __shared__ float tile[32][33];
     const int64_t b = blockIdx.z;
     const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
@@ -40,6 +41,7 @@ constexpr int AB_ROWS = 64;       // rows per block
 __global__ void act_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ y, int64_t ldy,
                                int act, float scale, const float* __restrict__ scale_ptr, float* __restrict__ dz,
                                int64_t lddz, float* __restrict__ dbias, int64_t M, int64_t N) {
+    pdl_entry();
     __shared__ float part[8][33];
     const int64_t n = (int64_t)blockIdx.x * 32 + threadIdx.x;
     const int64_t m0 = (int64_t)blockIdx.y * AB_ROWS;
@@ -73,6 +75,7 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const
 // (rows (e, h) of a head-major edge tensor scattering onto rows (node, h)).
 __global__ void scatter_add_rows_kernel(const float* __restrict__ in, int64_t ld_in, const int64_t* __restrict__ idx,
                                         int rows_per_idx, int64_t rows, int cols, float* __restrict__ out, int64_t ld_out) {
+    pdl_entry();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r = t / cols; const int c = (int)(t % cols);
     if (r >= rows) return;
@@ -84,6 +87,7 @@ __global__ void scatter_add_rows_kernel(const float* __restrict__ in, int64_t ld
 // out[i, :] = in[idx[i / R] * R + i % R, :]   (forward of the above; also the row gather of head-major operands)
 __global__ void gather_rows_kernel(const float* __restrict__ in, int64_t ld_in, const int64_t* __restrict__ idx,
                                    int rows_per_idx, int64_t rows, int cols, float* __restrict__ out, int64_t ld_out) {
+    pdl_entry();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r = t / cols; const int c = (int)(t % cols);
     if (r >= rows) return;
@@ -100,6 +104,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __
                      const float* __restrict__ res, int64_t ldr, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ dx, int64_t lddx, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, int64_t M, int D, float eps, int relu) {
+    pdl_entry();
     extern __shared__ float sacc[];               // [2 * D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sacc[i] = 0.f;
@@ -168,6 +173,7 @@ __global__ void gat_softmax_aggr_fwd_kernel(const float* __restrict__ t, const f
                                             const int64_t* __restrict__ dst, const int32_t* __restrict__ row_ptr,
                                             int64_t n_nodes, int H, int d_o, int aggr, float* __restrict__ xx,
                                             int64_t ldxx, float* __restrict__ p_out, int32_t* __restrict__ arg) {
+    pdl_entry();
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= n_nodes * H) return;
@@ -219,6 +225,7 @@ __global__ void gat_softmax_aggr_bwd_kernel(const float* __restrict__ dxx, int64
                                             const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ arg,
                                             int64_t n_nodes, int H, int d_o, int aggr, float* __restrict__ dt,
                                             float* __restrict__ dv, int64_t lddv) {
+    pdl_entry();
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= n_nodes * H) return;
@@ -266,6 +273,7 @@ __global__ void attn_prob_bwd_kernel(const float* __restrict__ s, const float* _
                                      const float* __restrict__ lse, const float* __restrict__ delta, float scale,
                                      float* __restrict__ ds, float* __restrict__ ds_t, float* __restrict__ p_t, int64_t ld_t,
                                      int64_t nq, int64_t nk) {
+    pdl_entry();
     __shared__ float tp[32][33], td[32][33];
     const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
@@ -299,6 +307,7 @@ __global__ void attn_prob_bwd_pairs_kernel(const float* __restrict__ s, const fl
                                            uint16_t* __restrict__ dst_hi, uint16_t* __restrict__ dst_lo,
                                            uint16_t* __restrict__ pt_hi, uint16_t* __restrict__ pt_lo, int64_t ld_t,
                                            int64_t nq, int64_t nk) {
+    pdl_entry();
     __shared__ float tp[32][33], td[32][33];
     const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
@@ -324,6 +333,7 @@ __global__ void attn_prob_bwd_pairs_kernel(const float* __restrict__ s, const fl
 // delta[h, i] = sum_d a[i, h*dk + d] * b[i, h*dk + d]; one warp per (i, h)
 __global__ void rowdot_heads_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
                                     float* __restrict__ out, int64_t M, int H, int dk) {
+    pdl_entry();
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= M * H) return;
@@ -343,6 +353,7 @@ constexpr int PB_CH = 8;
 __global__ void pointnet_pool_bwd_kernel(const float* __restrict__ dz3, const int32_t* __restrict__ arg,
                                          const float* __restrict__ h2, const float* __restrict__ w3, int64_t n_obj,
                                          int64_t n_pts, int C3, int C2, float* __restrict__ dw3, float* __restrict__ dh2) {
+    pdl_entry();
     const int k = threadIdx.x;
     const int c0 = blockIdx.x * PB_CH;
     float acc[PB_CH], wv[PB_CH];
@@ -378,6 +389,7 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {
 __global__ void dropout_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int64_t rows,
                                int64_t cols, uint32_t thresh, float inv_keep, uint64_t seed, uint64_t offset,
                                const uint64_t* __restrict__ device_step) {
+    pdl_entry();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const int64_t r = i / cols, c = i % cols;
@@ -393,6 +405,7 @@ __global__ void dropout_kernel(const float* __restrict__ x, int64_t ldx, float* 
 __global__ void bn_stats_kernel(const float* __restrict__ x, int64_t ldx, int64_t M, int64_t N, float eps, float* __restrict__ mean,
                                 float* __restrict__ rstd, float* __restrict__ running_mean, float* __restrict__ running_var,
                                 float momentum) {
+    pdl_entry();
     __shared__ float part[8][33];
     const int64_t n = (int64_t)blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
@@ -424,6 +437,7 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int64_t ldx, int64_
 __global__ void bn_apply_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int relu, float* __restrict__ y,
                                 int64_t ldy, int64_t M, int64_t N) {
+    pdl_entry();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * N) return;
     const int64_t m = i / N, n = i % N;
@@ -437,6 +451,7 @@ __global__ void bn_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const 
                               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                               const float* __restrict__ beta, int relu, int batch_stats, float* __restrict__ dx, int64_t lddx,
                               float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int64_t N) {
+    pdl_entry();
     __shared__ float p1[8][33], p2[8][33];
     const int64_t n = (int64_t)blockIdx.x * 32 + threadIdx.x;
     const bool ok = n < N;
@@ -465,6 +480,7 @@ __global__ void bn_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const 
 // ------------------------------------------------------------------------------ row L2 normalisation backward
 // y = x / |x|:  dx = (dy - y (y . dy)) / |x|
 __global__ void row_l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int64_t M, int D) {
+    pdl_entry();
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -478,6 +494,7 @@ __global__ void row_l2norm_bwd_kernel(const float* __restrict__ dy, const float*
 
 // out[0] += sum_i a[i] * b[i]   (gradient of the logit scale: d/ds (e^s z) . dy = y . dy)
 __global__ void dot_accum_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* __restrict__ out) {
+    pdl_entry();
     __shared__ float part[8];
     float acc = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += a[i] * b[i];
@@ -492,6 +509,7 @@ __global__ void dot_accum_kernel(const float* __restrict__ a, const float* __res
 __global__ void pair_features_kernel(const float* __restrict__ centres, int64_t ldc, const int32_t* __restrict__ seg_start,
                                      const int32_t* __restrict__ seg_end, const int64_t* __restrict__ pair_off, int64_t n_nodes,
                                      float* __restrict__ out) {
+    pdl_entry();
     const int64_t a = blockIdx.x;
     if (a >= n_nodes) return;
     const int s0 = seg_start[a], s1 = seg_end[a];
@@ -511,6 +529,7 @@ constexpr int WG_ROWS = 32;
 __global__ void __launch_bounds__(256)
 wgrad_small_kernel(const float* __restrict__ dz, int64_t lddz, const float* __restrict__ x, int64_t ldx, int64_t M, int N, int K,
                    int64_t rows_per_cta, float* __restrict__ dw, int64_t lddw) {
+    pdl_entry();
     __shared__ float sz[WG_ROWS][128], sx[WG_ROWS][128];
     const int tn = threadIdx.x >> 4, tk = threadIdx.x & 15;
     float acc[8][8];
@@ -561,7 +580,7 @@ extern "C" int vlsat_wgrad_small(const float* dz, int64_t lddz, const float* x, 
     VLSAT_SUPPORT(N <= 128 && K <= 128);
     int64_t rows_per_cta = ceil_div(ceil_div(M, 2 * kNumSMs), WG_ROWS) * WG_ROWS;
     if (rows_per_cta < WG_ROWS) rows_per_cta = WG_ROWS;
-    wgrad_small_kernel<<<(unsigned)ceil_div(M, rows_per_cta), 256, 0, (cudaStream_t)stream>>>(dz, lddz, x, ldx, M, N, K, rows_per_cta, dw, lddw);
+    launch_k(wgrad_small_kernel, dim3((unsigned)ceil_div(M, rows_per_cta)), dim3(256), 0, (cudaStream_t)stream, dz, lddz, x, ldx, M, N, K, rows_per_cta, dw, lddw);
     return finish_launch();
 }
 
@@ -572,7 +591,7 @@ extern "C" int vlsat_transpose(const float* in, int64_t ld_in, int64_t batch_str
     VLSAT_REQUIRE(in && out);
     VLSAT_SUPPORT(batch <= 65535 && ceil_div(cols, 32) <= 65535);
     dim3 grid((unsigned)ceil_div(ld_out, 32), (unsigned)ceil_div(cols, 32), (unsigned)batch);
-    transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, ld_in, batch_stride_in, out, ld_out, batch_stride_out, rows, cols);
+    launch_k(transpose_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, in, ld_in, batch_stride_in, out, ld_out, batch_stride_out, rows, cols);
     return finish_launch();
 }
 
@@ -583,7 +602,7 @@ extern "C" int vlsat_act_bwd(const float* dy, int64_t lddy, const float* y, int6
     VLSAT_REQUIRE(dy && lddy >= N && (dz || dbias) && (!dz || lddz >= N) && (act == VLSAT_ACT_NONE || (y && ldy >= N)));
     VLSAT_SUPPORT(ceil_div(M, AB_ROWS) <= 65535);
     dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, AB_ROWS));
-    act_bwd_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dy, lddy, y, ldy, act, scale, scale_ptr, dz, lddz, dbias, M, N);
+    launch_k(act_bwd_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, dy, lddy, y, ldy, act, scale, scale_ptr, dz, lddz, dbias, M, N);
     return finish_launch();
 }
 
@@ -592,7 +611,7 @@ extern "C" int vlsat_scatter_add_rows(const float* in, int64_t ld_in, const int6
     VLSAT_REQUIRE(rows >= 0 && cols >= 0 && rows_per_idx >= 1);
     if (rows == 0 || cols == 0) return VLSAT_OK;
     VLSAT_REQUIRE(in && idx && out && ld_in >= cols && ld_out >= cols);
-    scatter_add_rows_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, idx, rows_per_idx, rows, cols, out, ld_out);
+    launch_k(scatter_add_rows_kernel, dim3((unsigned)ceil_div(rows * cols, 256)), dim3(256), 0, (cudaStream_t)stream, in, ld_in, idx, rows_per_idx, rows, cols, out, ld_out);
     return finish_launch();
 }
 
@@ -601,7 +620,7 @@ extern "C" int vlsat_gather_rows(const float* in, int64_t ld_in, const int64_t* 
     VLSAT_REQUIRE(rows >= 0 && cols >= 0 && rows_per_idx >= 1);
     if (rows == 0 || cols == 0) return VLSAT_OK;
     VLSAT_REQUIRE(in && idx && out && ld_in >= cols && ld_out >= cols);
-    gather_rows_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, idx, rows_per_idx, rows, cols, out, ld_out);
+    launch_k(gather_rows_kernel, dim3((unsigned)ceil_div(rows * cols, 256)), dim3(256), 0, (cudaStream_t)stream, in, ld_in, idx, rows_per_idx, rows, cols, out, ld_out);
     return finish_launch();
 }
 
@@ -613,7 +632,7 @@ extern "C" int vlsat_add_layernorm_bwd(const float* dy, int64_t lddy, const floa
     VLSAT_REQUIRE(dy && x && gamma && beta && dx && lddy >= D && ldx >= D && lddx >= D && (!res || ld_res >= D));
     VLSAT_SUPPORT(D <= 32 * LNB_MAX);
     const unsigned grid = (unsigned)(ceil_div(M, 8) < 2 * kNumSMs ? ceil_div(M, 8) : 2 * kNumSMs);
-    layernorm_bwd_kernel<<<grid, 256, 2 * D * sizeof(float), (cudaStream_t)stream>>>(dy, lddy, x, ldx, res, ld_res, gamma, beta, dx, lddx,
+    launch_k(layernorm_bwd_kernel, grid, dim3(256), 2 * D * sizeof(float), (cudaStream_t)stream, dy, lddy, x, ldx, res, ld_res, gamma, beta, dx, lddx,
                                                                                      dgamma, dbeta, M, D, eps, relu);
     return finish_launch();
 }
@@ -627,7 +646,7 @@ extern "C" int vlsat_gat_softmax_aggr_fwd(const float* t, const float* v, int64_
     VLSAT_SUPPORT(d_o <= 128);
     const unsigned grid = (unsigned)ceil_div(n_nodes * n_heads * 32, 256);
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(C_) gat_softmax_aggr_fwd_kernel<C_><<<grid, 256, 0, st>>>(t, v, ldv, dst_sorted, row_ptr, n_nodes, n_heads, d_o, aggr, xx, ld_xx, prob, argmax)
+#define LAUNCH(C_) launch_k(gat_softmax_aggr_fwd_kernel<C_>, grid, dim3(256), 0, st, t, v, ldv, dst_sorted, row_ptr, n_nodes, n_heads, d_o, aggr, xx, ld_xx, prob, argmax)
     if (d_o <= 32) LAUNCH(1); else if (d_o <= 64) LAUNCH(2); else LAUNCH(4);
 #undef LAUNCH
     return finish_launch();
@@ -643,7 +662,7 @@ extern "C" int vlsat_gat_softmax_aggr_bwd(const float* dxx, int64_t ld_dxx, cons
     VLSAT_SUPPORT(d_o <= 128);
     const unsigned grid = (unsigned)ceil_div(n_nodes * n_heads * 32, 256);
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(C_) gat_softmax_aggr_bwd_kernel<C_><<<grid, 256, 0, st>>>(dxx, ld_dxx, prob, v, ldv, dst_sorted, row_ptr, argmax, n_nodes, n_heads, d_o, aggr, dt, dv, ld_dv)
+#define LAUNCH(C_) launch_k(gat_softmax_aggr_bwd_kernel<C_>, grid, dim3(256), 0, st, dxx, ld_dxx, prob, v, ldv, dst_sorted, row_ptr, argmax, n_nodes, n_heads, d_o, aggr, dt, dv, ld_dv)
     if (d_o <= 32) LAUNCH(1); else if (d_o <= 64) LAUNCH(2); else LAUNCH(4);
 #undef LAUNCH
     return finish_launch();
@@ -656,7 +675,7 @@ extern "C" int vlsat_attn_prob_bwd(const float* s, const float* dp, int64_t ld, 
     VLSAT_REQUIRE(s && dp && lse && delta && ds && ds_t && p_t && ld >= nk && ld_t >= nq);
     VLSAT_SUPPORT(ceil_div(ld_t, 32) <= 65535);
     dim3 grid((unsigned)ceil_div(nk, 32), (unsigned)ceil_div(ld_t, 32));
-    attn_prob_bwd_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(s, dp, ld, lse, delta, scale, ds, ds_t, p_t, ld_t, nq, nk);
+    launch_k(attn_prob_bwd_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, s, dp, ld, lse, delta, scale, ds, ds_t, p_t, ld_t, nq, nk);
     return finish_launch();
 }
 
@@ -668,7 +687,7 @@ extern "C" int vlsat_attn_prob_bwd_pairs(const float* s, const float* dp, int64_
     VLSAT_REQUIRE(s && dp && lse && delta && ds_hi && ds_lo && dst_hi && dst_lo && pt_hi && pt_lo && ld >= nk && ld_ds >= nk && ld_t >= nq);
     VLSAT_SUPPORT(ceil_div(ld_t, 32) <= 65535);
     dim3 grid((unsigned)ceil_div(nk, 32), (unsigned)ceil_div(ld_t, 32));
-    attn_prob_bwd_pairs_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(s, dp, ld, lse, delta, scale, (uint16_t*)ds_hi, (uint16_t*)ds_lo,
+    launch_k(attn_prob_bwd_pairs_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, s, dp, ld, lse, delta, scale, (uint16_t*)ds_hi, (uint16_t*)ds_lo,
                                                                                ld_ds, (uint16_t*)dst_hi, (uint16_t*)dst_lo, (uint16_t*)pt_hi,
                                                                                (uint16_t*)pt_lo, ld_t, nq, nk);
     return finish_launch();
@@ -679,7 +698,7 @@ extern "C" int vlsat_rowdot_heads(const float* a, int64_t lda, const float* b, i
     VLSAT_REQUIRE(M >= 0 && n_heads >= 1 && dk >= 1);
     if (M == 0) return VLSAT_OK;
     VLSAT_REQUIRE(a && b && out && lda >= (int64_t)n_heads * dk && ldb >= (int64_t)n_heads * dk);
-    rowdot_heads_kernel<<<(unsigned)ceil_div(M * n_heads * 32, 256), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, out, M, n_heads, dk);
+    launch_k(rowdot_heads_kernel, dim3((unsigned)ceil_div(M * n_heads * 32, 256)), dim3(256), 0, (cudaStream_t)stream, a, lda, b, ldb, out, M, n_heads, dk);
     return finish_launch();
 }
 
@@ -691,7 +710,7 @@ extern "C" int vlsat_pointnet_pool_bwd(const float* dz3, const int32_t* argmax, 
     VLSAT_SUPPORT(c2 <= 1024);
     const unsigned gy = (unsigned)(n_obj < 32 ? n_obj : 32);
     dim3 grid((unsigned)ceil_div(c_out, PB_CH), gy);
-    pointnet_pool_bwd_kernel<<<grid, c2, 0, (cudaStream_t)stream>>>(dz3, argmax, h2, w3, n_obj, n_pts, c_out, c2, dw3, dh2);
+    launch_k(pointnet_pool_bwd_kernel, grid, dim3(c2), 0, (cudaStream_t)stream, dz3, argmax, h2, w3, n_obj, n_pts, c_out, c2, dw3, dh2);
     return finish_launch();
 }
 
@@ -702,7 +721,7 @@ extern "C" int vlsat_dropout(const float* x, int64_t ldx, float* y, int64_t ldy,
     VLSAT_REQUIRE(x && y && ldx >= cols && ldy >= cols);
     const double th = (double)p * 4294967296.0;
     const uint32_t thresh = th >= 4294967295.0 ? 4294967295u : (uint32_t)th;
-    dropout_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, rows, cols, thresh, 1.f / (1.f - p), seed, offset, device_step);
+    launch_k(dropout_kernel, dim3((unsigned)ceil_div(rows * cols, 256)), dim3(256), 0, (cudaStream_t)stream, x, ldx, y, ldy, rows, cols, thresh, 1.f / (1.f - p), seed, offset, device_step);
     return finish_launch();
 }
 
@@ -715,10 +734,10 @@ extern "C" int vlsat_batchnorm_fwd(const float* x, int64_t ldx, const float* gam
     cudaStream_t st = (cudaStream_t)stream;
     int launches = 1;
     if (batch_stats) {
-        bn_stats_kernel<<<(unsigned)ceil_div(N, 32), dim3(32, 8), 0, st>>>(x, ldx, M, N, eps, mean, rstd, running_mean, running_var, momentum);
+        launch_k(bn_stats_kernel, dim3((unsigned)ceil_div(N, 32)), dim3(32, 8), 0, st, x, ldx, M, N, eps, mean, rstd, running_mean, running_var, momentum);
         ++launches;
     }
-    bn_apply_kernel<<<(unsigned)ceil_div(M * N, 256), 256, 0, st>>>(x, ldx, mean, rstd, gamma, beta, relu, y, ldy, M, N);
+    launch_k(bn_apply_kernel, dim3((unsigned)ceil_div(M * N, 256)), dim3(256), 0, st, x, ldx, mean, rstd, gamma, beta, relu, y, ldy, M, N);
     return finish_launch(launches);
 }
 
@@ -728,7 +747,7 @@ extern "C" int vlsat_batchnorm_bwd(const float* dy, int64_t lddy, const float* x
     VLSAT_REQUIRE(M >= 0 && N >= 1);
     if (M == 0) return VLSAT_OK;
     VLSAT_REQUIRE(dy && x && mean && rstd && gamma && beta && dgamma && dbeta && lddy >= N && ldx >= N && (!dx || lddx >= N));
-    bn_bwd_kernel<<<(unsigned)ceil_div(N, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, mean, rstd, gamma, beta, relu, batch_stats,
+    launch_k(bn_bwd_kernel, dim3((unsigned)ceil_div(N, 32)), dim3(32, 8), 0, (cudaStream_t)stream, dy, lddy, x, ldx, mean, rstd, gamma, beta, relu, batch_stats,
                                                                                        dx, lddx, dgamma, dbeta, M, N);
     return finish_launch();
 }
@@ -737,7 +756,7 @@ extern "C" int vlsat_row_l2norm_bwd(const float* dy, const float* x, float* dx, 
     VLSAT_REQUIRE(M >= 0 && D >= 1);
     if (M == 0) return VLSAT_OK;
     VLSAT_REQUIRE(dy && x && dx);
-    row_l2norm_bwd_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, (cudaStream_t)stream>>>(dy, x, dx, M, D);
+    launch_k(row_l2norm_bwd_kernel, dim3((unsigned)ceil_div(M * 32, 256)), dim3(256), 0, (cudaStream_t)stream, dy, x, dx, M, D);
     return finish_launch();
 }
 
@@ -746,7 +765,7 @@ extern "C" int vlsat_dot_accum(const float* a, const float* b, int64_t n, float*
     if (n == 0) return VLSAT_OK;
     VLSAT_REQUIRE(a && b);
     const unsigned grid = (unsigned)(ceil_div(n, 256) < 4 * kNumSMs ? ceil_div(n, 256) : 4 * kNumSMs);
-    dot_accum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, n, out);
+    launch_k(dot_accum_kernel, grid, dim3(256), 0, (cudaStream_t)stream, a, b, n, out);
     return finish_launch();
 }
 
@@ -756,6 +775,6 @@ extern "C" int vlsat_pair_features(const float* centres, int64_t ld_centres, con
     if (n_nodes == 0) return VLSAT_OK;
     VLSAT_REQUIRE(centres && seg_start && seg_end && pair_off && out && ld_centres >= 3);
     VLSAT_SUPPORT((uintptr_t)out % 16 == 0);
-    pair_features_kernel<<<(unsigned)n_nodes, 64, 0, (cudaStream_t)stream>>>(centres, ld_centres, seg_start, seg_end, pair_off, n_nodes, out);
+    launch_k(pair_features_kernel, dim3((unsigned)n_nodes), dim3(64), 0, (cudaStream_t)stream, centres, ld_centres, seg_start, seg_end, pair_off, n_nodes, out);
     return finish_launch();
 }

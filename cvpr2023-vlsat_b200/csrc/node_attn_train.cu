@@ -48,6 +48,7 @@ node_attn_bias_fwd_kernel(const float* __restrict__ q, int64_t ldq, const float*
                           const float* __restrict__ v, int64_t ldv, const float* __restrict__ bias,
                           const int64_t* __restrict__ pair_off, const int32_t* __restrict__ seg_start,
                           const int32_t* __restrict__ seg_end, int H, int dk, float* __restrict__ out, int64_t ldo) {
+    pdl_entry();
     extern __shared__ __align__(16) float sm[];
     const int64_t a = blockIdx.x;
     const int s0 = seg_start[a], ns = seg_end[a] - s0;
@@ -71,6 +72,7 @@ node_attn_bias_bwd_kernel(const float* __restrict__ q, int64_t ldq, const float*
                           const int32_t* __restrict__ seg_end, const float* __restrict__ dout, int64_t lddo, int H, int dk,
                           float* __restrict__ dq, int64_t lddq, float* __restrict__ dkk, int64_t lddk, float* __restrict__ dv,
                           int64_t lddv, float* __restrict__ dbias) {
+    pdl_entry();
     extern __shared__ __align__(16) float sm[];
     const int64_t a = blockIdx.x;
     const int s0 = seg_start[a], ns = seg_end[a] - s0;
@@ -144,7 +146,7 @@ extern "C" int vlsat_node_attn_bias_fwd(const float* q, int64_t ldq, const float
     if (rc) return rc;
     VLSAT_SUPPORT(ldk % 4 == 0 && ((uintptr_t)k % 16 == 0));
     cudaFuncSetAttribute(node_attn_bias_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    node_attn_bias_fwd_kernel<<<(unsigned)n_nodes, NAT_THREADS, smem, (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, bias, pair_off, seg_start,
+    launch_k(node_attn_bias_fwd_kernel, dim3((unsigned)n_nodes), dim3(NAT_THREADS), smem, (cudaStream_t)stream, q, ldq, k, ldk, v, ldv, bias, pair_off, seg_start,
                                                                                               seg_end, n_heads, dk, out, ldo);
     return finish_launch();
 }
@@ -163,7 +165,7 @@ extern "C" int vlsat_node_attn_bias_bwd(const float* q, int64_t ldq, const float
     if (rc) return rc;
     VLSAT_SUPPORT(ldk % 4 == 0 && ldv % 4 == 0 && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0));
     cudaFuncSetAttribute(node_attn_bias_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    node_attn_bias_bwd_kernel<<<(unsigned)n_nodes, NAT_THREADS, smem, (cudaStream_t)stream>>>(
+    launch_k(node_attn_bias_bwd_kernel, dim3((unsigned)n_nodes), dim3(NAT_THREADS), smem, (cudaStream_t)stream, 
         q, ldq, k, ldk, v, ldv, bias, pair_off, seg_start, seg_end, dout, lddo, n_heads, dk, dq, lddq, dk_out, lddk, dv_out, lddv, dbias);
     return finish_launch();
 }
