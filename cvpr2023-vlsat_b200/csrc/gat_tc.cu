@@ -33,8 +33,13 @@ namespace vlsat {
 
 using namespace tc;
 
-constexpr int GT_WG = 2;                      // epilogue warpgroups = tiles in flight per CTA
-constexpr int GT_THREADS = 64 + 128 * GT_WG;
+// epilogue warpgroups = tiles in flight per CTA: three where the TMEM columns (GT_WG * (hid + d_o) <= 512) and the
+// register file (448 threads -> 128 registers each; the d_o = 32 kernel fits with 48 bytes of spill) allow it
+// (VLSAT_GAT_WG=2 forces two, for A/B timing)
+static int gt_wg(int d_o) {
+    static const int forced = [] { const char* e = getenv("VLSAT_GAT_WG"); return e ? atoi(e) : 0; }();
+    return (d_o <= 32 && forced != 2) ? 3 : 2;
+}
 constexpr int GT_ROWS = 128;
 constexpr int GT_DE = 64;                     // proj_edge channels per head: one 128-byte bf16 row
 constexpr int GT_STAGES = 3;                  // K' tile ring
@@ -80,8 +85,8 @@ __device__ __forceinline__ void mma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, ui
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <int DO>      // d_o (channels per head of the attention output): 32 or 64
-__global__ void __launch_bounds__(GT_THREADS, 1)
+template <int DO, int GT_WG>      // d_o (channels per head of the attention output): 32 or 64; epilogue warpgroups
+__global__ void __launch_bounds__(64 + 128 * GT_WG, 1)
 gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_constant__ CUtensorMap tm_klo,
                    const __grid_constant__ CUtensorMap tm_c1hi, const __grid_constant__ CUtensorMap tm_c1lo,
                    const __grid_constant__ CUtensorMap tm_c2hi, const __grid_constant__ CUtensorMap tm_c2lo,
@@ -97,9 +102,11 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
     uint8_t* c2lo_s = c2hi_s + hc * c2_box;
     uint8_t* k_s = c2lo_s + hc * c2_box;                     // GT_STAGES x (K'_hi | K'_lo)
     float* s_c2b = reinterpret_cast<float*>(k_s + GT_STAGES * GT_K_TILE);   // [DO] second-layer bias
-    float* tp_all = s_c2b + DO;                              // [epilogue warps][32 rows][DO + 1] run-maxima transpose
-    float* qs_all = tp_all + 4 * GT_WG * 32 * (DO + 1);      // [GT_WG][GT_QN nodes][H heads][hid + 4] staged QC rows
-    const int qs_words = GT_QN * p.H * (p.hid + 4);
+    // per-warpgroup scratch, two uses that never overlap in time: the staged QC rows [GT_QN nodes][H heads][hid + 4]
+    // (written at the top of a tile, last read in epilogue 1) and the run-maxima transpose [4 warps][32 rows][DO + 1]
+    // of epilogue 2 - a warp enters epilogue 2 only after acc2_full, i.e. after all 128 threads arrived on hid_ready
+    float* qs_all = s_c2b + DO;
+    const int qs_words = max(GT_QN * p.H * (p.hid + 4), 4 * 32 * (DO + 1));
     uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(qs_all + GT_WG * qs_words) + 7) & ~(uintptr_t)7);
     uint64_t* w_full = bars;
     uint64_t* k_full = bars + 1;                             // [GT_STAGES]
@@ -206,7 +213,7 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         const uint32_t t_acc1 = tmem_base + g * buf_cols + lane_off, t_acc2 = t_acc1 + p.hid;
         const int D_a = p.H * DO;
-        float* tps = tp_all + (warp - 2) * 32 * (DO + 1);
+        float* tps = qs_all + g * qs_words + ((warp - 2) & 3) * 32 * (DO + 1);
         if (g == 0) for (int i = et; i < DO; i += 128) s_c2b[i] = __ldg(p.c2_bias + i);
         asm volatile("bar.sync 15, %0;" ::"n"(128 * GT_WG) : "memory");     // c2 bias visible to every epilogue warpgroup
         const int hshift = 31 - __clz(p.H);                  // H divides 128: a power of two
@@ -487,7 +494,7 @@ extern "C" int vlsat_gat_edge_tc_fwd(const void* k_hi, const void* k_lo, const f
     if (n_nodes == 0) return VLSAT_OK;
     VLSAT_REQUIRE(xx && ld_xx >= (int64_t)n_heads * d_o);
     VLSAT_SUPPORT(GT_ROWS % n_heads == 0 && d_e == GT_DE && hid % 32 == 0 && hid >= 32 && hid <= 128 &&
-                  (d_o == 32 || d_o == 64) && GT_WG * (hid + d_o) <= 512);
+                  (d_o == 32 || d_o == 64) && gt_wg(d_o) * (hid + d_o) <= 512);
     VLSAT_SUPPORT(n_edges * n_heads < (1ll << 31) && n_nodes * n_heads * d_o < (1ll << 31));
     const int D_a = n_heads * d_o;
     const size_t need = (size_t)n_nodes * D_a * sizeof(int);
@@ -512,17 +519,18 @@ extern "C" int vlsat_gat_edge_tc_fwd(const void* k_hi, const void* k_lo, const f
         if (!ok) return VLSAT_ERR_UNSUPPORTED;
         const int hc = (hid + 63) / 64;
         const size_t smem = (size_t)2 * hid * 128 + (size_t)2 * hc * d_o * 128 + (size_t)GT_STAGES * GT_K_TILE +
-                            (size_t)d_o * 4 + (size_t)4 * GT_WG * 32 * (d_o + 1) * 4 +
-                            (size_t)GT_WG * GT_QN * n_heads * (hid + 4) * 4 + 256 + 1024;
+                            (size_t)d_o * 4 +
+                            (size_t)gt_wg(d_o) * std::max(GT_QN * n_heads * (hid + 4), 4 * 32 * (d_o + 1)) * 4 + 256 + 1024;
         VLSAT_SUPPORT(smem <= 227 * 1024);
-        auto kern = d_o == 32 ? gat_edge_tc_kernel<32> : gat_edge_tc_kernel<64>;
+        const int wg = gt_wg(d_o);
+        auto kern = d_o == 64 ? gat_edge_tc_kernel<64, 2> : wg == 3 ? gat_edge_tc_kernel<32, 3> : gat_edge_tc_kernel<32, 2>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         GatTcParams p;
         p.qc = qc; p.ld_qc = ld_qc; p.v = v; p.ld_v = ld_v; p.src = src_sorted; p.dst = dst_sorted; p.c2_bias = c2_bias;
         p.xx_enc = enc; p.prob = prob; p.trace = g_trace; { const char* d = getenv("VLSAT_GAT_DBG"); p.dbg = d ? atoi(d) : 0; } p.n_edges = n_edges; p.H = n_heads; p.hid = hid; p.d_o = d_o;
         const int64_t n_tiles = ceil_div(n_edges * n_heads, GT_ROWS);
         const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, kNumSMs);
-        launch_k(kern, dim3(grid), dim3(GT_THREADS), smem, st, tk, tkl, t1, t1l, t2, t2l, p);
+        launch_k(kern, dim3(grid), dim3(64 + 128 * wg), smem, st, tk, tkl, t1, t1l, t2, t2l, p);
         ++launches;
     }
     launch_k(gat_finalize_kernel, dim3((unsigned)ceil_div(n_nodes * D_a, 256)), dim3(256), 0, st, enc, xx, ld_xx, n_nodes, n_heads, d_o);
