@@ -22,6 +22,11 @@ class Epilogue(C.Structure):
                 ("split_hi", vp), ("split_lo", vp), ("ld_split", i64), ("split_fmt", i32)]
 
 
+class AdamWTensor(C.Structure):
+    """Mirror of ``vlsat_adamw_tensor``."""
+    _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("vmax", vp), ("n", i64), ("lr", f32), ("weight_decay", f32)]
+
+
 class LinearOpts(C.Structure):
     """Mirror of ``vlsat_linear_opts``."""
     _fields_ = [("engine", i32), ("x_hi", vp), ("x_lo", vp), ("w_hi", vp), ("w_lo", vp), ("workspace", vp),
@@ -83,6 +88,17 @@ SIGNATURES = {
     "vlsat_batchnorm_bwd": [vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, vp, i64, vp, vp, i64, i64, vp],
     "vlsat_row_l2norm_bwd": [vp, vp, vp, i64, i32, vp],
     "vlsat_dot_accum": [vp, vp, i64, vp, vp],
+    "vlsat_cross_entropy_fwd": [vp, i64, vp, i64, i32, vp, vp, vp],
+    "vlsat_cross_entropy_bwd": [vp, i64, vp, vp, vp, f32, vp, i64, i64, i32, vp],
+    "vlsat_rel_class_weights": [vp, i64, i32, f32, vp, vp],
+    "vlsat_bce_fwd": [vp, vp, vp, i64, i32, vp, vp],
+    "vlsat_bce_bwd": [vp, vp, vp, vp, f32, vp, i64, i32, vp],
+    "vlsat_cosine_margin_fwd": [vp, i64, vp, i64, i64, i32, f32, vp, vp],
+    "vlsat_cosine_margin_bwd": [vp, i64, vp, i64, vp, f32, f32, vp, i64, vp, i64, i64, i32, vp],
+    "vlsat_l1_unit_fwd": [vp, i64, vp, i64, i64, i32, vp, vp],
+    "vlsat_l1_unit_bwd": [vp, i64, vp, i64, vp, f32, vp, i64, i64, i32, vp],
+    "vlsat_sum_rows": [vp, i64, f32, vp, vp, f32, i32, vp],
+    "vlsat_adamw_step": [vp, vp, vp, i64, i32, C.c_double, C.c_double, f32, vp, i64, vp],
 }
 _RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
 

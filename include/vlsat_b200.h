@@ -367,6 +367,59 @@ int vlsat_batchnorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t l
 int vlsat_row_l2norm_bwd(const float* dy, const float* x, float* dx, int64_t M, int D, void* stream);
 int vlsat_dot_accum(const float* a, const float* b, int64_t n, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * N1  training-step glue: the losses of Mmgnet.process_train (src/model/SGFN_MMG/model.py:343-418)
+ * and the optimiser step of Mmgnet.backward (:483-488; groups and schedule :143-158).
+ * Every *_fwd writes ONE loss value per row into row_loss; vlsat_sum_rows adds a buffer up in a fixed order
+ * (reproducible bit for bit) and applies the mean / term coefficient. Every *_bwd multiplies by gout[0] (the
+ * upstream gradient of the scalar loss, read from DEVICE memory: no host sync) and by `coef` (term weight /
+ * element count of the mean), and WRITES (does not accumulate) the gradient.
+ * ---------------------------------------------------------------------------------------------- */
+/* F.cross_entropy(logits [R, C], target int64 [R]) (:343-344): row_loss = logsumexp(x) - x[target], row_lse kept for
+ * the backward: dlogits = gout * coef * (softmax(x) - onehot). Rows whose target is outside [0, C) give 0 / 0. */
+int vlsat_cross_entropy_fwd(const float* logits, int64_t ld, const int64_t* target, int64_t R, int C,
+                            float* row_loss, float* row_lse, void* stream);
+int vlsat_cross_entropy_bwd(const float* logits, int64_t ld, const int64_t* target, const float* row_lse,
+                            const float* gout, float coef, float* dlogits, int64_t ldd, int64_t R, int C, void* stream);
+/* WEIGHT_EDGE == 'DYNAMIC' (:353-366): weight[c] = |scale / (log(sum_e gt[e, c] + 1) + 1)|, gt [E, C] of 0/1 floats,
+ * C <= 64; scale = 1 (1e-2 with ignore_none_rel). */
+int vlsat_rel_class_weights(const float* gt, int64_t E, int C, float scale, float* weight, void* stream);
+/* F.binary_cross_entropy(p [E, C], y [E, C], weight [C] or NULL) (:375-376), logs clamped at -100 like ATen;
+ * backward dp = gout * coef * w (p - y) / max((1 - p) p, 1e-12). */
+int vlsat_bce_fwd(const float* p, const float* y, const float* weight, int64_t E, int C, float* row_loss, void* stream);
+int vlsat_bce_bwd(const float* p, const float* y, const float* weight, const float* gout, float coef, float* dp,
+                  int64_t E, int C, void* stream);
+/* cosine_loss (:257-258) after the row normalisations of :402-403: row_loss = max(margin - cos(a_r, b_r), 0).
+ * da / db nullable. */
+int vlsat_cosine_margin_fwd(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t R, int D, float margin,
+                            float* row_loss, void* stream);
+int vlsat_cosine_margin_bwd(const float* a, int64_t lda, const float* b, int64_t ldb, const float* gout, float coef,
+                            float margin, float* da, int64_t ldda, float* db, int64_t lddb, int64_t R, int D, void* stream);
+/* F.l1_loss(x / |x|, target) (:409-410): row_loss = sum_c |x_c / |x| - t_c|. */
+int vlsat_l1_unit_fwd(const float* x, int64_t ldx, const float* target, int64_t ldt, int64_t R, int D, float* row_loss, void* stream);
+int vlsat_l1_unit_bwd(const float* x, int64_t ldx, const float* target, int64_t ldt, const float* gout, float coef,
+                      float* dx, int64_t lddx, int64_t R, int D, void* stream);
+/* term = scale * sum_i v[i] (single CTA, fixed order); out_term[0] = term (nullable);
+ * out_total[0] = (accumulate ? out_total[0] : 0) + total_coef * term (nullable) - the weighted sum of :412. */
+int vlsat_sum_rows(const float* v, int64_t n, float scale, float* out_term, float* out_total, float total_coef,
+                   int accumulate, void* stream);
+
+/* One tensor of the multi-tensor AdamW step; the table lives in device memory. vmax: amsgrad state or NULL. */
+typedef struct {
+    float* p; const float* g; float* m; float* v; float* vmax;
+    int64_t n;
+    float lr;               /* base learning rate of the tensor's parameter group (:143-156) */
+    float weight_decay;
+} vlsat_adamw_tensor;
+/* torch.optim.AdamW.step() for every tensor of the table + CosineAnnealingLR(T_max = t_max, eta_min = 0) (:157, :483-488):
+ * with k = step[0] + 1, lr_k = lr * (1 + cos(pi (k - 1) / t_max)) / 2 (t_max <= 0: constant), p *= 1 - lr_k wd,
+ * m += (1 - beta1)(g - m), v = beta2 v + (1 - beta2) g^2, p -= lr_k / (1 - beta1^k) * m / (sqrt(v) / sqrt(1 - beta2^k) + eps);
+ * then step[0] = k. Chunk c covers elements [chunk_index[c] * chunk_elems, +chunk_elems) of tensor chunk_tensor[c]
+ * (one CTA each). The step counter lives in device memory, so the call can be replayed inside a CUDA graph. */
+int vlsat_adamw_step(const vlsat_adamw_tensor* tensors, const int32_t* chunk_tensor, const int32_t* chunk_index,
+                     int64_t n_chunks, int chunk_elems, double beta1, double beta2, float eps, int64_t* step,
+                     int64_t t_max, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

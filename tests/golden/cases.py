@@ -130,3 +130,20 @@ def grad_summary(g: torch.Tensor) -> dict:
     if g.numel() <= GRAD_FULL_LIMIT:
         return dict(full=g.float())
     return dict(head=g[:GRAD_HEAD].float(), sum=float(g.sum()), norm=float(g.norm()), absmax=float(g.abs().max()))
+
+
+# ---- training-step cases (oracle/make_golden_train.py): N1, SURVEY 8f -------------------------------------------
+TRAIN_CASES = ["mmgnet_cfg1", "mmgnet_ragged"]
+TRAIN_STEPS = 2
+
+
+def train_targets(batch, seed: int = 11, num_obj: int = 160, num_rel: int = 26):
+    """Seeded supervision of a batch: object classes [N] int64, multi-label relationship targets [E, num_rel] of 0/1
+    floats (about one label per edge, some edges with none), and a unit-norm [E, 512] stand-in for the CLIP text
+    embedding that ``get_rel_emb`` (SGFN_MMG/model.py:221-255) would return."""
+    n, e = batch.obj_points.shape[0], batch.edge_indices.shape[1]
+    g = torch.Generator().manual_seed(seed)
+    gt_cls = torch.randint(0, num_obj, (n,), generator=g)
+    gt_rel = (torch.rand(e, num_rel, generator=g) < 1.0 / num_rel).float()
+    text = torch.randn(e, 512, generator=g)
+    return gt_cls, gt_rel, text / text.norm(dim=-1, keepdim=True)
