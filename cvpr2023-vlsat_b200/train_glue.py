@@ -242,6 +242,59 @@ class FusedAdamW:
         self.steps_done += 1
         self.mark_updated()
 
+    # ---- checkpointing: the reference saves optimizer.state_dict() and lr_scheduler.state_dict() (model_base.py:72-73)
+    # and restores them on resume (:115-122); both use torch.optim.AdamW's / CosineAnnealingLR's layout here, so
+    # checkpoints move between the two implementations in either direction.
+    def state_dict(self) -> dict:
+        state, groups, idx = {}, [], 0
+        for g, lr_now in zip(self.param_groups, self.last_lr):
+            ids = []
+            for p in g["params"]:
+                s = self.state.get(id(p))
+                if s is not None:
+                    state[idx] = {"step": torch.tensor(float(self.steps_done)), "exp_avg": s["m"], "exp_avg_sq": s["v"]}
+                    if s["vmax"] is not None:
+                        state[idx]["max_exp_avg_sq"] = s["vmax"]
+                ids.append(idx)
+                idx += 1
+            groups.append(dict(lr=lr_now, initial_lr=g["lr"], betas=self.betas, eps=self.eps, weight_decay=g["weight_decay"],
+                               amsgrad=g["amsgrad"], maximize=False, foreach=None, capturable=False, differentiable=False,
+                               fused=None, decoupled_weight_decay=True, params=ids))
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd: dict) -> None:
+        groups = sd["param_groups"]
+        if len(groups) != len(self.param_groups) or any(len(a["params"]) != len(b["params"]) for a, b in zip(groups, self.param_groups)):
+            raise ValueError("loaded state dict has a different number of parameter groups / parameters per group")
+        steps = 0
+        for sg, g in zip(groups, self.param_groups):
+            g["lr"] = float(sg.get("initial_lr", sg["lr"]))
+            g["weight_decay"], g["amsgrad"] = float(sg.get("weight_decay", 0.0) or 0.0), bool(sg.get("amsgrad", False))
+            for idx, p in zip(sg["params"], g["params"]):
+                st = sd["state"].get(idx)
+                if st is None:
+                    self.state.pop(id(p), None)
+                    continue
+                conv = lambda t: t.detach().to(device=p.device, dtype=torch.float32).reshape(p.shape).contiguous().clone()
+                vmax = conv(st["max_exp_avg_sq"]) if "max_exp_avg_sq" in st else (torch.zeros_like(p, memory_format=torch.contiguous_format) if g["amsgrad"] else None)
+                self.state[id(p)] = dict(m=conv(st["exp_avg"]), v=conv(st["exp_avg_sq"]), vmax=vmax)
+                steps = max(steps, int(float(st["step"])))
+        if groups:
+            self.betas = (float(groups[0]["betas"][0]), float(groups[0]["betas"][1]))
+            self.eps = float(groups[0]["eps"])
+        self.steps_done, self._step_dev, self._table = steps, None, None
+
+    def scheduler_state_dict(self) -> dict:
+        """What ``CosineAnnealingLR.state_dict()`` holds for the same point of the schedule."""
+        return {"T_max": self.t_max, "eta_min": 0.0, "base_lrs": [g["lr"] for g in self.param_groups], "last_epoch": self.steps_done,
+                "_step_count": self.steps_done + 1, "_last_lr": self.last_lr}
+
+    def load_scheduler_state_dict(self, sd: dict) -> None:
+        self.t_max = int(sd["T_max"])
+        if float(sd.get("eta_min", 0.0)) != 0.0:
+            raise NotImplementedError("CosineAnnealingLR with eta_min != 0 is not built (the reference uses the default 0)")
+        self.steps_done, self._step_dev = int(sd["last_epoch"]), None
+
     def mark_updated(self) -> None:
         """The kernel writes the parameters behind autograd's back: bump their version counters so that every derived
         weight cache (packed / folded / split copies keyed on ``Tensor._version``) refreshes."""

@@ -118,3 +118,35 @@ def test_optimizer_and_losses_have_no_cpu_fallback():
     assert (cfg.coef_obj, cfg.coef_rel, cfg.coef_mimic) == (0.1, 3.0, 0.1)
     cfg = G.LossConfig(lambda_o=2.0)                                            # normalised by max(lambda_r, lambda_o)
     assert (cfg.coef_obj, cfg.coef_rel) == (1.0, 1.5)
+
+
+def test_optimizer_checkpoints_move_between_torch_adamw_and_fused_adamw():
+    """model_base.py:72-73,115-122 save / restore optimizer.state_dict() and lr_scheduler.state_dict()."""
+    g = torch.Generator().manual_seed(0)
+    mk = lambda: [torch.nn.Parameter(torch.randn(s, generator=torch.Generator().manual_seed(i))) for i, s in enumerate([(4, 3), (7,), ()])]
+    ref_p, my_p = mk(), mk()
+    layout = lambda ps: [dict(params=ps[:2], lr=1e-3, weight_decay=0.0, amsgrad=False), dict(params=ps[2:], lr=1e-4, weight_decay=0.0, amsgrad=False)]
+    ref = torch.optim.AdamW(layout(ref_p))
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(ref, T_max=10, last_epoch=-1)
+    for _ in range(3):
+        for p in ref_p[:2]:                       # the third parameter never gets a gradient: no state, like triplet_projector_3d
+            p.grad = torch.randn(p.shape, generator=g)
+        ref.step(); sched.step()
+    mine = G.FusedAdamW(layout(my_p), t_max=0)
+    mine.load_state_dict(ref.state_dict())
+    mine.load_scheduler_state_dict(sched.state_dict())
+    assert mine.steps_done == 3 and mine.t_max == 10
+    assert [g_["lr"] for g_ in mine.param_groups] == [1e-3, 1e-4]              # base rates, not the scheduled ones
+    assert all(math.isclose(a, b, rel_tol=1e-9) for a, b in zip(mine.last_lr, sched.get_last_lr()))
+    for p, q in zip(my_p[:2], ref_p[:2]):
+        assert torch.equal(mine.state[id(p)]["m"], ref.state[q]["exp_avg"]) and torch.equal(mine.state[id(p)]["v"], ref.state[q]["exp_avg_sq"])
+    assert id(my_p[2]) not in mine.state
+    # and back: torch's optimiser accepts the state dict FusedAdamW writes
+    back = torch.optim.AdamW(layout(mk()))
+    back.load_state_dict(mine.state_dict())
+    sd = back.state_dict()
+    assert sorted(sd["state"]) == [0, 1] and float(sd["state"][0]["step"]) == 3.0
+    assert torch.equal(sd["state"][1]["exp_avg_sq"], ref.state[ref_p[1]]["exp_avg_sq"])
+    assert math.isclose(sd["param_groups"][0]["lr"], sched.get_last_lr()[0], rel_tol=1e-9) and sd["param_groups"][0]["initial_lr"] == 1e-3
+    s2 = mine.scheduler_state_dict()
+    assert s2["last_epoch"] == sched.state_dict()["last_epoch"] and s2["T_max"] == 10
