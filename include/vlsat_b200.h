@@ -420,6 +420,18 @@ int vlsat_adamw_step(const vlsat_adamw_tensor* tensors, const int32_t* chunk_ten
                      int64_t n_chunks, int chunk_elems, double beta1, double beta2, float eps, int64_t* step,
                      int64_t t_max, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * N2  device-side object preparation of the input pipeline: for object o and sampled point p,
+ *   row = cloud[choice[o, p], :]   (src/dataset/dataset_3dssg.py:288-289; `choice` = the np.random.choice result offset
+ *                                   into the scan cloud, int64 [n_obj, n_pts]; out-of-range indices are clamped)
+ *   descriptor[o] = [mean xyz, unbiased std xyz, max - min xyz, product of the extents, largest extent]
+ *                                   (src/utils/op_utils.py:47-64 gen_descriptor, computed BEFORE centring as :291 does)
+ *   obj_points[o, c, p] = row[c] - (c < 3 ? mean[c] : 0)      (zero_mean :293 + permute(0, 2, 1) of src/model/model.py:71)
+ * cloud [n_cloud, n_channels] fp32 (xyz first; rgb / normals after), obj_points [n_obj, n_channels, n_pts], descriptor [n_obj, 11].
+ * ---------------------------------------------------------------------------------------------- */
+int vlsat_object_prep_fwd(const float* cloud, int64_t ld_cloud, int64_t n_cloud, int n_channels, const int64_t* choice,
+                          int64_t n_obj, int64_t n_pts, float* obj_points, float* descriptor, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

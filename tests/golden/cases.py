@@ -147,3 +147,32 @@ def train_targets(batch, seed: int = 11, num_obj: int = 160, num_rel: int = 26):
     gt_rel = (torch.rand(e, num_rel, generator=g) < 1.0 / num_rel).float()
     text = torch.randn(e, 512, generator=g)
     return gt_cls, gt_rel, text / text.norm(dim=-1, keepdim=True)
+
+
+# ---- object preparation (N2): seeded scan clouds + sampled indices ------------------------------------
+PREP_CASES = {           # name -> (cloud rows, channels, objects, points per object, seed)
+    "prep_xyz": (5000, 3, 12, 128, 21),
+    "prep_rgbn": (3000, 9, 5, 256, 22),
+    "prep_ragged_p": (700, 6, 3, 77, 23),
+    "prep_one_point_pool": (40, 3, 2, 64, 24),
+}
+
+
+def prep_inputs(name: str):
+    """A scan-like cloud (objects are blobs metres away from the origin) and, per object, indices drawn with
+    replacement from that object's own points (np.random.choice(len(obj_pointset), num_points, replace=True))."""
+    m, c, n, p, seed = PREP_CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    owner = torch.randint(0, n, (m,), generator=g)
+    owner[:n] = torch.arange(n)                                   # every object owns at least one point
+    centre = (torch.rand(n, 3, generator=g) - 0.5) * 12.0
+    scale = torch.rand(n, 3, generator=g) * 0.9 + 0.1
+    cloud = torch.randn(m, c, generator=g)
+    cloud[:, :3] = cloud[:, :3] * scale[owner] + centre[owner]
+    choice = torch.empty(n, p, dtype=torch.int64)
+    for o in range(n):
+        pool = torch.nonzero(owner == o).view(-1)
+        if name == "prep_one_point_pool" and o == 0:
+            pool = pool[:1]                                       # an instance with a single point: std 0, extent 0
+        choice[o] = pool[torch.randint(0, pool.numel(), (p,), generator=g)]
+    return cloud, choice
