@@ -116,6 +116,11 @@ CONFIGS = {
     "cfg2": dict(num_scenes=16, objects_per_scene=40, points_per_object=256, edges_per_scene=600),
     "cfg3": dict(num_scenes=64, objects_per_scene=40, points_per_object=512, edges_per_scene=None),
     "cfg4_per_gpu": dict(num_scenes=32, objects_per_scene=40, points_per_object=256, edges_per_scene=600),
+    # BASELINE config #5: 3RScan-shaped sub-scenes (2..9 objects, 3DSSG statistics), fully connected, 128 points per object,
+    # eval mode; the reference evaluates them one scene per forward (src/model/model.py:185), here 256 scenes share a batch.
+    # The object counts are a fixed seeded draw so that every batch of a run has the same shape signature (one CUDA graph).
+    "cfg5": dict(num_scenes=256, objects_per_scene=torch.randint(2, 10, (256,), generator=torch.Generator().manual_seed(7919)).tolist(),
+                 points_per_object=128, edges_per_scene=None),
 }
 
 
