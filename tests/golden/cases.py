@@ -176,3 +176,29 @@ def prep_inputs(name: str):
             pool = pool[:1]                                       # an instance with a single point: std 0, extent 0
         choice[o] = pool[torch.randint(0, pool.numel(), (p,), generator=g)]
     return cloud, choice
+
+
+# ---- evaluation ranks (N3): seeded predictions and targets -------------------------------------------
+EVAL_CASES = {           # name -> (objects, edges, seed)
+    "eval_small": (12, 40, 31),
+    "eval_scene": (40, 300, 32),
+}
+
+
+def eval_inputs(name: str, num_obj: int = 160, num_rel: int = 26):
+    """Object logits [N, 160], relationship probabilities [E, 26] (with tied rows, a confident and an unconfident
+    label-free edge), targets and [E, 2] (subject, object) edges as ``process_val`` holds them."""
+    n, e, seed = EVAL_CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(n, num_obj, generator=g) * 3
+    rel = torch.sigmoid(torch.randn(e, num_rel, generator=g) * 2)
+    gt_cls = torch.randint(0, num_obj, (n,), generator=g)
+    gt_rel = (torch.rand(e, num_rel, generator=g) < 0.06).float()
+    edges = torch.randint(0, n, (e, 2), generator=g)
+    rel[3], rel[4] = 0.7, 0.2                                     # ties everywhere
+    gt_rel[3], gt_rel[4] = 0, 0                                   # ... on label-free edges: all above / all below the threshold
+    gt_rel[5] = 0
+    gt_rel[5, [2, 9, 17]] = 1                                     # three labels on one edge: the sorted-minus-counter rule
+    logits[0, gt_cls[0]] = logits[0].max() + 1                   # rank 1
+    logits[1, gt_cls[1]] = logits[1].min() - 1                   # beyond top-k
+    return logits, rel, gt_cls, gt_rel, edges
