@@ -12,6 +12,6 @@ from .mmgnet import (AdapterModel, DEFAULT_MODEL_CONFIG, Mmgnet, accelerate_refe
                      adopt_parameters, load_model_config)
 from .pointnet import PointNetfeat, PointNetRelClsMulti                                      # noqa: F401
 from .graph import GraphedForward, GraphedTrainStep                                                           # noqa: F401
-from . import autograd, data_prep, ops, synth, train_glue, train_path                                   # noqa: F401
+from . import autograd, data_prep, eval_ranks, ops, synth, train_glue, train_path                                   # noqa: F401
 
 __version__ = "0.1.0"

@@ -99,6 +99,10 @@ SIGNATURES = {
     "vlsat_l1_unit_bwd": [vp, i64, vp, i64, vp, f32, vp, i64, i64, i32, vp],
     "vlsat_sum_rows": [vp, i64, f32, vp, vp, f32, i32, vp],
     "vlsat_object_prep_fwd": [vp, i64, i64, i32, vp, i64, i64, vp, vp, vp],
+    "vlsat_softmax_rows": [vp, i64, i64, i32, vp, vp],
+    "vlsat_topk_object_ranks": [vp, i64, vp, i64, i32, i32, vp, vp],
+    "vlsat_topk_predicate_ranks": [vp, vp, i64, i32, i32, f32, vp, vp],
+    "vlsat_topk_triplet_ranks": [vp, i64, i32, vp, i32, vp, vp, vp, i64, i32, f32, vp, vp],
     "vlsat_adamw_step": [vp, vp, vp, i64, i32, C.c_double, C.c_double, f32, vp, i64, vp],
 }
 _RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}

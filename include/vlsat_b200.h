@@ -432,6 +432,28 @@ int vlsat_adamw_step(const vlsat_adamw_tensor* tensors, const int32_t* chunk_ten
 int vlsat_object_prep_fwd(const float* cloud, int64_t ld_cloud, int64_t n_cloud, int n_channels, const int64_t* choice,
                           int64_t n_obj, int64_t n_pts, float* obj_points, float* descriptor, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * N3  evaluation ranks of --mode eval (src/utils/eva_utils_acc.py; Mmgnet.process_val, SGFN_MMG/model.py:463-472).
+ * rank = 1 + #{scores strictly greater than the ground truth's}, capped at topk + 1 - counted, never sorted.
+ * NOT YET RUN ON HARDWARE: written at the end of round 1 after the GPU budget was spent (tests: marker gpu_next).
+ * ---------------------------------------------------------------------------------------------- */
+/* y = softmax(x) over each row (F.softmax(objs_pred, dim=-1), eva_utils_acc.py:143-145); y compact [R, C]. */
+int vlsat_softmax_rows(const float* x, int64_t ld, int64_t R, int C, float* y, void* stream);
+/* evaluate_topk_object (:27-39): ranks[n] int32. */
+int vlsat_topk_object_ranks(const float* pred, int64_t ld, const int64_t* target, int64_t N, int C, int topk,
+                            int32_t* ranks, void* stream);
+/* evaluate_topk_predicate (:42-79) on get_gt's multi-label targets (:6-24): rel_prob, gt_rel [E, C] (C <= 64); ranks [E, C]
+ * int32: row e holds the edge's entries (one per ground-truth label, or one if it has none: first position below
+ * `threshold`) sorted ascending with the reference's "i-th smallest minus i" adjustment (:73-78), -1 beyond. */
+int vlsat_topk_predicate_ranks(const float* rel_prob, const float* gt_rel, int64_t E, int C, int topk, float threshold,
+                               int32_t* ranks, void* stream);
+/* evaluate_triplet_topk (:137-211), ranks only: score(i, j, k) = (obj_prob[sub, i] * obj_prob[obj, j]) * rel_prob[e, k] in
+ * fp32 round-to-nearest (the reference's association order); edges [E, 2] int64 (subject, object) as process_val passes
+ * them; obj_prob [n_nodes, n_obj_cls] already softmaxed; ranks [E, n_rel_cls] in the layout of vlsat_topk_predicate_ranks. */
+int vlsat_topk_triplet_ranks(const float* obj_prob, int64_t n_nodes, int n_obj_cls, const float* rel_prob, int n_rel_cls,
+                             const int64_t* gt_cls, const float* gt_rel, const int64_t* edges, int64_t E, int topk,
+                             float threshold, int32_t* ranks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

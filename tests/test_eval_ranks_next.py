@@ -1,0 +1,43 @@
+"""N3: the evaluation-rank kernels against the oracle (pinned bit-exactly on the reference's own functions,
+tests/test_oracle_eval.py) and the reference's fixtures. Marker ``gpu_next``: these kernels were written after the
+round's GPU budget was spent and have NOT run on hardware yet - ``python -m pytest tests -m gpu_next`` on a B200, then
+change the marker to ``gpu``. Ranks are integers: the bar is bit-exact (probabilities fed from the same CPU softmax)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases
+from oracle import vlsat_oracle as O
+
+pytestmark = pytest.mark.gpu_next
+
+
+@pytest.mark.parametrize("name", list(cases.EVAL_CASES))
+def test_rank_kernels_match_reference_fixture(name, golden):
+    from vlsat_b200 import eval_ranks as R
+    gold = golden("eval_ranks")[name]
+    logits, rel, gt_cls, gt_rel, edges = (t.cuda() for t in cases.eval_inputs(name))
+    assert torch.equal(R.evaluate_topk_object(logits, gt_cls, 11).cpu(), gold["obj"])
+    assert torch.equal(R.evaluate_topk_predicate(rel, gt_rel, 6).cpu(), gold["rel"])
+    probs = F.softmax(logits.cpu(), dim=-1).cuda()                    # the reference's CPU softmax, bit for bit
+    assert torch.equal(R.evaluate_triplet_topk(logits, rel, gt_cls, gt_rel, edges, 101, obj_probs=probs).cpu(), gold["triplet"])
+    # device softmax: last-bit differences can only move a rank where two scores are within an ulp
+    dev = R.evaluate_triplet_topk(logits, rel, gt_cls, gt_rel, edges, 101).cpu()
+    assert dev.shape == gold["triplet"].shape and (dev != gold["triplet"]).float().mean().item() < 0.02
+    assert torch.allclose(R.softmax_rows(logits).cpu(), F.softmax(logits.cpu(), -1), rtol=1e-5, atol=1e-9)
+
+
+def test_rank_kernels_config2_scene_against_oracle():
+    from vlsat_b200 import eval_ranks as R
+    g = torch.Generator().manual_seed(3)
+    n, e = 40, 600
+    logits, rel = torch.randn(n, 160, generator=g) * 4, torch.sigmoid(torch.randn(e, 26, generator=g) * 3)
+    gt_cls, gt_rel = torch.randint(0, 160, (n,), generator=g), (torch.rand(e, 26, generator=g) < 0.05).float()
+    edges = torch.randint(0, n, (e, 2), generator=g)
+    probs = F.softmax(logits, dim=-1)
+    got = R.evaluate_triplet_topk(logits.cuda(), rel.cuda(), gt_cls.cuda(), gt_rel.cuda(), edges.cuda(), 101, obj_probs=probs.cuda()).cpu()
+    assert torch.equal(got, O.topk_triplet_ranks(logits, rel, gt_cls, gt_rel, edges, 101))
+    assert torch.equal(R.evaluate_topk_predicate(rel.cuda(), gt_rel.cuda(), 6).cpu(), O.topk_predicate_ranks(rel, gt_rel, 6))
+    assert torch.equal(R.evaluate_topk_object(logits.cuda(), gt_cls.cuda(), 11).cpu(), O.topk_object_ranks(logits, gt_cls, 11))
+    empty = R.evaluate_triplet_topk(logits.cuda(), rel[:0].cuda(), gt_cls.cuda(), gt_rel[:0].cuda(), edges[:0].cuda(), 101, obj_probs=probs.cuda())
+    assert empty.numel() == 0

@@ -38,3 +38,12 @@ def test_oracle_ranks_against_the_live_reference_on_fresh_inputs():
     assert np.array_equal(evaluate_topk_predicate(rel, gt_edges, True, topk=6), O.topk_predicate_ranks(rel, gt_rel, 6).numpy())
     t = evaluate_triplet_topk(logits, rel, gt_edges, edges, True, topk=101, use_clip=True, obj_topk=a)[0]
     assert np.array_equal(t, O.topk_triplet_ranks(logits, rel, gt_cls, gt_rel, edges, 101).numpy())
+
+
+def test_eval_rank_mirror_has_no_cpu_fallback():
+    from vlsat_b200 import eval_ranks as R
+    logits, rel, gt_cls, gt_rel, edges = cases.eval_inputs("eval_small")
+    for call in (lambda: R.evaluate_topk_object(logits, gt_cls, 11), lambda: R.evaluate_topk_predicate(rel, gt_rel, 6),
+                 lambda: R.evaluate_triplet_topk(logits, rel, gt_cls, gt_rel, edges, 101), lambda: R.softmax_rows(logits)):
+        with pytest.raises(TypeError):
+            call()
