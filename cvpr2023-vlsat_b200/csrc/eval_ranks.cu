@@ -5,7 +5,7 @@
 // materialising: one CTA per edge streams the products (s_i * o_j) * r_k - the reference's association order, correctly
 // rounded multiplies, so its exact float equality test (:184) is reproduced bit for bit - and counts.
 // Per-edge lists are emitted sorted with the reference's "i-th smallest minus i" adjustment (:73-78, :205-210):
-// ranks_out[e, pos] for pos < number of entries of edge e, -1 beyond.
+// ranks_out[e, pos] for pos < number of entries of edge e, INT32_MIN beyond.
 // NOT YET RUN ON HARDWARE (round 1 ended without GPU budget): tests carry the gpu_next marker.
 #include "common.cuh"
 #include <limits.h>
@@ -52,7 +52,7 @@ __device__ void emit_adjusted(const int* ranks, int m, int32_t* out, int C) {
         for (int b = 0; b < m; ++b) pos += (ranks[b] < ranks[a]) || (ranks[b] == ranks[a] && b < a);
         out[pos] = ranks[a] - pos;
     }
-    for (int a = m; a < C; ++a) out[a] = -1;
+    for (int a = m; a < C; ++a) out[a] = INT_MIN;             // adjusted ranks of tied labels can reach 0 and below: no small sentinel
 }
 
 // ---- evaluate_topk_predicate (:42-79) with get_gt's multi-label targets (:6-24); one warp per edge, C <= 64 ------------

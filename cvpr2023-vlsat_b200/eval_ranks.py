@@ -28,7 +28,7 @@ def _i64(t: torch.Tensor, what: str) -> torch.Tensor:
 
 
 def _flatten(ranks: torch.Tensor) -> torch.Tensor:
-    return ranks[ranks >= 0].to(torch.int64)          # row-major: edges in order, each edge's entries ascending
+    return ranks[ranks > -2 ** 31].to(torch.int64)      # row-major: edges in order, each edge's entries ascending; INT32_MIN = empty slot
 
 
 def softmax_rows(x: torch.Tensor) -> torch.Tensor:

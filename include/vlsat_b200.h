@@ -444,7 +444,8 @@ int vlsat_topk_object_ranks(const float* pred, int64_t ld, const int64_t* target
                             int32_t* ranks, void* stream);
 /* evaluate_topk_predicate (:42-79) on get_gt's multi-label targets (:6-24): rel_prob, gt_rel [E, C] (C <= 64); ranks [E, C]
  * int32: row e holds the edge's entries (one per ground-truth label, or one if it has none: first position below
- * `threshold`) sorted ascending with the reference's "i-th smallest minus i" adjustment (:73-78), -1 beyond. */
+ * `threshold`) sorted ascending with the reference's "i-th smallest minus i" adjustment (:73-78; tied labels can take it
+ * to 0 and below), INT32_MIN beyond. */
 int vlsat_topk_predicate_ranks(const float* rel_prob, const float* gt_rel, int64_t E, int C, int topk, float threshold,
                                int32_t* ranks, void* stream);
 /* evaluate_triplet_topk (:137-211), ranks only: score(i, j, k) = (obj_prob[sub, i] * obj_prob[obj, j]) * rel_prob[e, k] in

@@ -41,3 +41,16 @@ def test_rank_kernels_config2_scene_against_oracle():
     assert torch.equal(R.evaluate_topk_object(logits.cuda(), gt_cls.cuda(), 11).cpu(), O.topk_object_ranks(logits, gt_cls, 11))
     empty = R.evaluate_triplet_topk(logits.cuda(), rel[:0].cuda(), gt_cls.cuda(), gt_rel[:0].cuda(), edges[:0].cuda(), 101, obj_probs=probs.cuda())
     assert empty.numel() == 0
+
+
+def test_tied_labels_reach_zero_and_negative_adjusted_ranks():
+    from vlsat_b200 import eval_ranks as R
+    rel = torch.full((2, 26), 0.3)
+    rel[0, [1, 2, 3]] = 1.0
+    gt_rel = torch.zeros(2, 26)
+    gt_rel[0, [1, 2, 3]] = 1
+    assert R.evaluate_topk_predicate(rel.cuda(), gt_rel.cuda(), 6).cpu().tolist() == [1, 0, -1, 1]
+    logits, gt_cls, edges = torch.randn(2, 160, generator=torch.Generator().manual_seed(1)), torch.tensor([5, 7]), torch.tensor([[0, 1], [1, 0]])
+    probs = F.softmax(logits, -1)
+    got = R.evaluate_triplet_topk(logits.cuda(), rel.cuda(), gt_cls.cuda(), gt_rel.cuda(), edges.cuda(), 101, obj_probs=probs.cuda()).cpu()
+    assert torch.equal(got, O.topk_triplet_ranks(logits, rel, gt_cls, gt_rel, edges, 101))

@@ -47,3 +47,12 @@ def test_eval_rank_mirror_has_no_cpu_fallback():
                  lambda: R.evaluate_triplet_topk(logits, rel, gt_cls, gt_rel, edges, 101), lambda: R.softmax_rows(logits)):
         with pytest.raises(TypeError):
             call()
+
+
+def test_tied_labels_take_the_adjusted_rank_to_zero_and_below():
+    """Three ground-truth labels with exactly equal (saturated) scores: the reference emits 1, 0, -1 (eva_utils_acc.py:73-78)."""
+    rel = torch.full((2, 26), 0.3)
+    rel[0, [1, 2, 3]] = 1.0
+    gt_rel = torch.zeros(2, 26)
+    gt_rel[0, [1, 2, 3]] = 1
+    assert O.topk_predicate_ranks(rel, gt_rel, 6).tolist() == [1, 0, -1, 1]
