@@ -1,5 +1,5 @@
 """Per-parameter gradient error of the CUDA path against the oracle's autograd (debug aid).
-usage: python tools/grad_check.py [case] [eval|train]"""
+usage: python tests/dev_grad_check.py [case] [eval|train]"""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))

@@ -1,5 +1,5 @@
 """Stage-by-stage gradient comparison of MMG.forward (CUDA differentiable path vs the oracle in float64). Debug aid.
-usage: python tools/grad_check_mmg.py [out_index 0..3] [scale_2d]"""
+usage: python tests/dev_grad_check_mmg.py [out_index 0..3] [scale_2d]"""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
