@@ -8,7 +8,6 @@ passes the ``[E, 512]`` text embedding - and the top-k metric code that follows 
 """
 from __future__ import annotations
 
-import ctypes as C
 import math
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 

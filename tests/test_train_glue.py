@@ -9,7 +9,6 @@ import torch
 
 import cases
 import vlsat_b200 as V
-from conftest import ROOT
 from oracle import vlsat_oracle as O
 from vlsat_b200 import train_glue as G
 
