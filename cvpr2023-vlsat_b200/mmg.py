@@ -20,6 +20,23 @@ from .attention import MultiHeadAttention, SceneContext
 from .gat import GraphContext, GraphEdgeAttenNetwork
 
 
+_side_streams = {}
+
+
+def _two_streams() -> bool:
+    """VLSAT_STREAMS=2 runs the two modality branches of a layer on two streams (experimental; off by default and while
+    the per-kernel timer is active, whose events must bracket serial execution)."""
+    import os
+    return os.environ.get("VLSAT_STREAMS", "1") == "2" and ops._timer is None
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = str(device)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 def _bias_mlp(num_heads: int) -> nn.Sequential:
     return nn.Sequential(nn.Linear(4, 32), nn.ReLU(), nn.LayerNorm(32), nn.Linear(32, 32), nn.ReLU(),
                          nn.LayerNorm(32), nn.Linear(32, num_heads))
@@ -69,14 +86,33 @@ class MMG(nn.Module):
         # (hi, lo) pairs of the four streams travel with them: every producer that feeds a projection emits the pair from
         # its epilogue, so no activation is read back just to be split
         o3p = o2p = None
+        two_streams = _two_streams()
         for i in range(self.depth):
             act = (i < self.depth - 1) or self.depth == 1          # ReLU(+Dropout) after this layer
             cat3 = torch.empty((n, dn + da), device=o3.device, dtype=torch.float32)
             cat2 = torch.empty((n, dn + da), device=o3.device, dtype=torch.float32)
             o3, o3p = self.self_attn[i].attend_scenes(o3, o3, ctx, out=cat3[:, :dn], q_split=o3p, kv_split=o3p, emit_split=True)
             o2, o2p = self.cross_attn[i].attend_scenes(o2, o3, ctx, out=cat2[:, :dn], q_split=o2p, kv_split=o3p, emit_split=True)
-            o3, e3_raw, _, o3p = self.gcn_3ds[i].forward_fused(cat3, e3, g, relu_nodes=act, x_split=o3p, edge_split=e3p, emit_split=True)
-            o2, e2_raw, _, o2p = self.gcn_2ds[i].forward_fused(cat2, e2, g, relu_nodes=act, x_split=o2p, edge_split=e2p, emit_split=True)
+            if two_streams:
+                # EXPERIMENTAL (VLSAT_STREAMS=2, never run on hardware yet - DESIGN.md section 8, item 1b): the 2D graph-attention
+                # layer on a side stream next to the 3D one; they are independent until cross_attn_rel. One CTA per SM, so the
+                # side kernel's CTAs start as the other's exit and fill the last partial round of its tiles. Allocator rules:
+                # the side branch is issued FIRST and every tensor it reads (cat2, e2, e2p, o2p, g) stays referenced by this
+                # frame until after the join, so no block it still reads can be handed to the main branch.
+                main, side = torch.cuda.current_stream(), _side_stream(o3.device)
+                fork = torch.cuda.Event()
+                fork.record(main)
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    r2 = self.gcn_2ds[i].forward_fused(cat2, e2, g, relu_nodes=act, x_split=o2p, edge_split=e2p, emit_split=True)
+                    join = torch.cuda.Event()
+                    join.record(side)
+                r3 = self.gcn_3ds[i].forward_fused(cat3, e3, g, relu_nodes=act, x_split=o3p, edge_split=e3p, emit_split=True)
+                main.wait_event(join)
+                (o3, e3_raw, _, o3p), (o2, e2_raw, _, o2p) = r3, r2
+            else:
+                o3, e3_raw, _, o3p = self.gcn_3ds[i].forward_fused(cat3, e3, g, relu_nodes=act, x_split=o3p, edge_split=e3p, emit_split=True)
+                o2, e2_raw, _, o2p = self.gcn_2ds[i].forward_fused(cat2, e2, g, relu_nodes=act, x_split=o2p, edge_split=e2p, emit_split=True)
             e2, e2p = self.cross_attn_rel[i].attend_all(e2_raw, e3_raw, relu=act,
                                                         q_split=self.gcn_2ds[i].edgeatten.last_edge_split,
                                                         kv_split=self.gcn_3ds[i].edgeatten.last_edge_split, emit_split=True)
