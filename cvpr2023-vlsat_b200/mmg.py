@@ -24,10 +24,11 @@ _side_streams = {}
 
 
 def _two_streams() -> bool:
-    """VLSAT_STREAMS=2 runs the two modality branches of a layer on two streams (experimental; off by default and while
-    the per-kernel timer is active, whose events must bracket serial execution)."""
+    """The two modality branches of a layer run on two streams (default; VLSAT_STREAMS=1 serialises them). Off while the
+    per-kernel timer is active, whose events must bracket serial execution. Round 2 on a B200: the GPU suite is green
+    with it and the config #2 forward drops from 2.78 to 2.63 ms (gpurun_out/r2_bench0*.json)."""
     import os
-    return os.environ.get("VLSAT_STREAMS", "1") == "2" and ops._timer is None
+    return os.environ.get("VLSAT_STREAMS", "2") == "2" and ops._timer is None
 
 
 def _side_stream(device) -> torch.cuda.Stream:
@@ -94,8 +95,7 @@ class MMG(nn.Module):
             o3, o3p = self.self_attn[i].attend_scenes(o3, o3, ctx, out=cat3[:, :dn], q_split=o3p, kv_split=o3p, emit_split=True)
             o2, o2p = self.cross_attn[i].attend_scenes(o2, o3, ctx, out=cat2[:, :dn], q_split=o2p, kv_split=o3p, emit_split=True)
             if two_streams:
-                # EXPERIMENTAL (VLSAT_STREAMS=2, never run on hardware yet - DESIGN.md section 8, item 1b): the 2D graph-attention
-                # layer on a side stream next to the 3D one; they are independent until cross_attn_rel. One CTA per SM, so the
+                # the 2D graph-attention layer on a side stream next to the 3D one (VLSAT_STREAMS=1 turns this off); they are independent until cross_attn_rel. One CTA per SM, so the
                 # side kernel's CTAs start as the other's exit and fill the last partial round of its tiles. Allocator rules:
                 # the side branch is issued FIRST and every tensor it reads (cat2, e2, e2p, o2p, g) stays referenced by this
                 # frame until after the join, so no block it still reads can be handed to the main branch.

@@ -1,7 +1,6 @@
 """N3: the evaluation-rank kernels against the oracle (pinned bit-exactly on the reference's own functions,
-tests/test_oracle_eval.py) and the reference's fixtures. Marker ``gpu_next``: these kernels were written after the
-round's GPU budget was spent and have NOT run on hardware yet - ``python -m pytest tests -m gpu_next`` on a B200, then
-change the marker to ``gpu``. Ranks are integers: the bar is bit-exact (probabilities fed from the same CPU softmax)."""
+tests/test_oracle_eval.py) and the reference's fixtures. First run on a B200 in round 2 (4 passed, gpurun_out/r2_gpunext.log), hence promoted from
+``gpu_next`` to ``gpu``. Ranks are integers: the bar is bit-exact (probabilities fed from the same CPU softmax)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -9,7 +8,7 @@ import torch.nn.functional as F
 import cases
 from oracle import vlsat_oracle as O
 
-pytestmark = pytest.mark.gpu_next
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", list(cases.EVAL_CASES))
