@@ -33,6 +33,18 @@ class LinearOpts(C.Structure):
                 ("workspace_bytes", sz)]
 
 
+class Bf16Pair(C.Structure):
+    """Mirror of ``vlsat_bf16_pair``."""
+    _fields_ = [("hi", vp), ("lo", vp), ("ld", i64)]
+
+
+class FlashBwdOperands(C.Structure):
+    """Mirror of ``vlsat_flash_bwd_operands``."""
+    _fields_ = [("q", Bf16Pair), ("k", Bf16Pair), ("v", Bf16Pair), ("dout", Bf16Pair),
+                ("q_t", Bf16Pair), ("k_t", Bf16Pair), ("dout_t", Bf16Pair),
+                ("lse2", vp), ("delta", vp), ("ld_stat", i64)]
+
+
 # name -> argtypes ; every function returns int status unless listed in _RESTYPES
 SIGNATURES = {
     "vlsat_version": [],
@@ -64,6 +76,10 @@ SIGNATURES = {
     "vlsat_bf16_split": [vp, i64, i64, i64, vp, vp, i64, vp],
     "vlsat_flash_attn_bf16x3_fwd": [vp, vp, i64, vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, sz, vp],
     "vlsat_flash_attn_bf16x3_workspace_bytes": [i64, i64, i32],
+    "vlsat_bf16_split_t": [vp, i64, i64, i64, vp, vp, i64, vp, vp, i64, vp],
+    "vlsat_flash_attn_bwd_stats": [vp, i64, vp, i64, vp, i64, vp, vp, i64, i64, i32, i32, vp],
+    "vlsat_flash_attn_bf16x3_bwd": [C.POINTER(FlashBwdOperands), vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, vp, sz, vp],
+    "vlsat_flash_attn_bf16x3_bwd_workspace_bytes": [i64, i64, i32],
     "vlsat_build_csr": [vp, i64, i64, vp, vp, vp, sz, vp],
     "vlsat_gat_edge_fwd": [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64,
                            i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, vp, vp],
@@ -105,7 +121,7 @@ SIGNATURES = {
     "vlsat_topk_triplet_ranks": [vp, i64, i32, vp, i32, vp, vp, vp, i64, i32, f32, vp, vp],
     "vlsat_adamw_step": [vp, vp, vp, i64, i32, C.c_double, C.c_double, f32, vp, i64, vp],
 }
-_RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
+_RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_bwd_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
 
 _lib = None
 

@@ -14,6 +14,7 @@ has no hand-written backward).
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -338,7 +339,8 @@ def node_attn(q, k, v, bias, sctx, n_heads: int):
 
 
 # ------------------------------------------------------------------------ edge cross-attention (A9)
-FLASH_BWD_QUERY_BLOCK = 8192     # queries per score block in the backward ([block, nk] fp32 buffers)
+FLASH_BWD_QUERY_BLOCK = 8192     # queries per score block in the materialising backward ([block, nk] fp32 buffers)
+FLASH_BWD_STREAMING = os.environ.get("VLSAT_FLASH_BWD", "stream") != "blocks"    # round-1 block path kept for the other engines
 
 
 class _FlashAttn(Function):
@@ -368,6 +370,10 @@ class _FlashAttn(Function):
         dk_ = d // H
         scale = 1.0 / math.sqrt(dk_)
         dout = _c(dout)
+        if d == H * 64 and ops.tensor_cores_enabled() and FLASH_BWD_STREAMING:
+            # streaming tcgen05 backward: S, P, dP, dS live in tensor memory only (csrc/flash_attn_bwd.cu)
+            dq, dk, dv = ops.flash_attn_bf16_bwd(q, k, v, dout, out, lse, H)
+            return dq, dk, dv, None
         delta = ops.rowdot_heads(dout, out, H)                      # [H, nq]
         dq = torch.empty_like(q)
         dk = torch.empty((nk, d), device=q.device, dtype=torch.float32)

@@ -528,6 +528,60 @@ def flash_attn_bf16(q, k, vt, nk: int, n_heads: int, want_lse: bool = False):
     return (out, lse) if want_lse else out
 
 
+def bf16_split_t(x: torch.Tensor, want_t: bool = True):
+    """bf16 (hi, lo) pair of an fp32 matrix [n, c] and, with ``want_t``, of its transpose [c, round8(n)] (tail columns zero):
+    ((hi, lo), (hi_t, lo_t) or None). One pass over x (csrc/flash_attn_bwd.cu)."""
+    xp, ldx = _rows(x, "x")
+    n, c = x.shape
+    ld = (c + 7) // 8 * 8
+    hl = torch.empty((2, n, ld), device=x.device, dtype=torch.bfloat16)
+    ldt = (n + 7) // 8 * 8
+    hlt = torch.empty((2, c, ldt), device=x.device, dtype=torch.bfloat16) if want_t else None
+    _lib.check(_call("vlsat_bf16_split_t", xp, ldx, n, c, hl[0].data_ptr(), hl[1].data_ptr(), ld,
+                     hlt[0].data_ptr() if want_t else None, hlt[1].data_ptr() if want_t else None, ldt, _stream()), "vlsat_bf16_split_t")
+    return (hl[0], hl[1]), ((hlt[0], hlt[1]) if want_t else None)
+
+
+def flash_attn_bwd_stats(dout, out, lse, n_heads: int):
+    """(lse2, delta), both [H, round64(nq)]: lse * log2(e) and rowsum_head(dout * out), padded with (1e30, 0)."""
+    dp, lddo = _rows(dout, "dout"); op, ldo = _rows(out, "out")
+    nq, d = dout.shape
+    ld = (nq + 63) // 64 * 64
+    st = torch.empty((2, n_heads, ld), device=dout.device, dtype=torch.float32)
+    _lib.check(_call("vlsat_flash_attn_bwd_stats", dp, lddo, op, ldo, _f32(lse, "lse").data_ptr(), lse.stride(0), st[0].data_ptr(),
+                     st[1].data_ptr(), ld, nq, n_heads, d // n_heads, _stream()), "vlsat_flash_attn_bwd_stats")
+    return st[0], st[1]
+
+
+def flash_attn_bf16_bwd(q, k, v, dout, out, lse, n_heads: int):
+    """Streaming tensor-core backward of A9 (csrc/flash_attn_bwd.cu): (dq, dk, dv) fp32 for q [nq, H*64], k / v [nk, H*64],
+    the upstream gradient dout, the forward's output and log-sum-exp [H, nq]. Scores never reach HBM."""
+    nq, d = q.shape
+    nk = k.shape[0]
+    if d != n_heads * 64:
+        raise ValueError("flash_attn_bf16_bwd needs head size 64")
+    dq = torch.empty((nq, d), device=q.device, dtype=torch.float32)
+    dk = torch.empty((nk, d), device=q.device, dtype=torch.float32)
+    dv = torch.empty((nk, d), device=q.device, dtype=torch.float32)
+    if nq == 0 or nk == 0:
+        return dq.zero_(), dk.zero_(), dv.zero_()
+    qp, qt = bf16_split_t(q)
+    kp, kt = bf16_split_t(k)
+    vp_, _ = bf16_split_t(v, want_t=False)
+    dop, dot = bf16_split_t(dout)
+    lse2, delta = flash_attn_bwd_stats(dout, out, lse, n_heads)
+    pair = lambda p: _lib.Bf16Pair(p[0].data_ptr(), p[1].data_ptr(), p[0].stride(0))
+    o = _lib.FlashBwdOperands(pair(qp), pair(kp), pair(vp_), pair(dop), pair(qt), pair(kt), pair(dot),
+                              lse2.data_ptr(), delta.data_ptr(), lse2.stride(0))
+    ws_bytes = int(_lib.load().vlsat_flash_attn_bf16x3_bwd_workspace_bytes(nq, nk, n_heads))
+    ws = torch.empty((ws_bytes // 4,), device=q.device, dtype=torch.float32) if ws_bytes else None
+    # 7 products of 2 nq nk 64 flops per head (S and dP are computed in both launches)
+    st = _call("vlsat_flash_attn_bf16x3_bwd", C.byref(o), dq.data_ptr(), d, dk.data_ptr(), d, dv.data_ptr(), d, nq, nk, n_heads, 64,
+               ws.data_ptr() if ws is not None else None, ws_bytes, _stream(), work=(14.0 * nq * nk * d, 4.0 * (4 * nq * d + 4 * nk * d)))
+    _lib.check(st, "vlsat_flash_attn_bf16x3_bwd")
+    return dq, dk, dv
+
+
 # -------------------------------------------------------------------------------------- graph attention
 def build_csr(index_row: torch.Tensor, n_nodes: int):
     """Stable grouping of edges by ``index_row``: (row_ptr [N+1] int32, perm [E] int32)."""

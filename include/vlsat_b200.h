@@ -210,6 +210,33 @@ int vlsat_flash_attn_bf16x3_fwd(const void* q_hi, const void* q_lo, int64_t ldq,
  * states then go through `workspace` (16-byte aligned, size below; 0 = no split needed). */
 size_t vlsat_flash_attn_bf16x3_workspace_bytes(int64_t nq, int64_t nk, int n_heads);
 
+/* A9 backward, streaming (round 2): gradients of softmax(QK^T/sqrt(dk)) V w.r.t. Q, K, V - autograd through
+ * attention.py:41-78 as called at network_MMG.py:231 (no mask, no bias). Scores and probabilities never leave the
+ * SM. Two launches of one tcgen05 kernel (csrc/flash_attn_bwd.cu): key tiles stationary -> dK, dV; query tiles
+ * stationary -> dQ. BF16x3 arithmetic like the forward.
+ *   vlsat_bf16_split_t       fp32 [rows, cols] -> bf16 (hi, lo) pairs [rows, cols] (row stride ld_out) and, when hi_t / lo_t
+ *                            are given, the transposed pairs [cols, ld_t] (ld_t >= rows, multiple of 8, tail zero)
+ *   vlsat_flash_attn_bwd_stats  lse2 = lse*log2(e), delta = rowsum_head(dout o out); both [H, ld_stat], ld_stat a
+ *                            multiple of 64 >= nq, padding written as (1e30, 0)
+ *   vlsat_flash_attn_bf16x3_bwd  dq [nq, H*64], dk / dv [nk, H*64] fp32 (overwritten); head_dim must be 64;
+ *                            workspace (16-byte aligned) of vlsat_flash_attn_bf16x3_bwd_workspace_bytes bytes when the
+ *                            streamed range is split over CTAs to fill the 148 SMs (deterministic slab sums). */
+typedef struct vlsat_bf16_pair { const void* hi; const void* lo; int64_t ld; } vlsat_bf16_pair;
+typedef struct vlsat_flash_bwd_operands {
+    vlsat_bf16_pair q, k, v, dout;          /* [n, H*64] */
+    vlsat_bf16_pair q_t, k_t, dout_t;       /* [H*64, n] transposed copies */
+    const float* lse2; const float* delta; int64_t ld_stat;
+} vlsat_flash_bwd_operands;
+int vlsat_bf16_split_t(const float* x, int64_t ldx, int64_t rows, int64_t cols, void* hi, void* lo, int64_t ld_out,
+                       void* hi_t, void* lo_t, int64_t ld_t, void* stream);
+int vlsat_flash_attn_bwd_stats(const float* dout, int64_t ld_dout, const float* out, int64_t ld_out, const float* lse,
+                               int64_t ld_lse, float* lse2, float* delta, int64_t ld_stat, int64_t nq, int n_heads, int dk,
+                               void* stream);
+int vlsat_flash_attn_bf16x3_bwd(const vlsat_flash_bwd_operands* operands, float* dq, int64_t ld_dq, float* dk, int64_t ld_dk,
+                                float* dv, int64_t ld_dv, int64_t nq, int64_t nk, int n_heads, int head_dim,
+                                void* workspace, size_t workspace_bytes, void* stream);
+size_t vlsat_flash_attn_bf16x3_bwd_workspace_bytes(int64_t nq, int64_t nk, int n_heads);
+
 /* ------------------------------------------------------------------------------------------------
  * A8  graph attention layer core (network_MMG.py:34-41,96-104; network_util.py:50-73).
  *   vlsat_build_csr: stable counting sort of edges by index_row (= edge_index[0] for

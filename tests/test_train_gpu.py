@@ -215,9 +215,13 @@ def test_node_attn_bias_fwd_bwd(sizes, H):
     assert_close(sctx.pair_feats, torch.cat([diff, diff.norm(dim=-1, keepdim=True)], 1), "pair features", atol=1e-6)
 
 
-@pytest.mark.parametrize("nq,nk,H", [(100, 257, 8), (1, 1, 8), (300, 129, 8), (50, 70, 4)])
-def test_flash_attention_backward(nq, nk, H, monkeypatch):
+@pytest.mark.parametrize("streaming", [True, False])
+@pytest.mark.parametrize("nq,nk,H", [(100, 257, 8), (1, 1, 8), (300, 129, 8), (50, 70, 4), (64, 128, 8), (1000, 2100, 8)])
+def test_flash_attention_backward(nq, nk, H, streaming, monkeypatch):
+    """A9 gradients against float64 autograd of attention.py:41-78, through the streaming tcgen05 backward
+    (csrc/flash_attn_bwd.cu; H * 64 = 512 only) and through the round-1 block path that the other engines keep."""
     monkeypatch.setattr(A, "FLASH_BWD_QUERY_BLOCK", 128)                   # exercise the accumulation over query blocks
+    monkeypatch.setattr(A, "FLASH_BWD_STREAMING", streaming)
     d = 512
     q, k, v = (rnd(n_, d, seed=40 + i).requires_grad_(True) for i, n_ in enumerate((nq, nk, nk)))
     out = A.flash_attn(q, k, v, H)
@@ -233,6 +237,29 @@ def test_flash_attention_backward(nq, nk, H, monkeypatch):
     assert_close(q.grad, q64.grad.float(), "dq", rtol=1e-3, atol=1e-4, atol_scale=2e-4)
     assert_close(k.grad, k64.grad.float(), "dk", rtol=1e-3, atol=1e-4, atol_scale=2e-4)
     close64(v.grad, v64.grad, "dv", rtol=1e-3, atol_scale=2e-4)
+
+
+def test_streaming_flash_backward_at_config2_size_and_forced_splits(monkeypatch):
+    """nq = 4800, nk = 9600 (config #2's key count), 8 heads, against float64; then the same call with the streamed
+    range split over 3 CTAs per tile (slab sums) must reproduce itself to rounding."""
+    nq, nk, H, d = 4800, 9600, 8, 512
+    q, k, v = (rnd(n_, d, seed=140 + i).requires_grad_(True) for i, n_ in enumerate((nq, nk, nk)))
+    dout = rnd(nq, d, seed=144)
+    A.flash_attn(q, k, v, H).backward(dout)
+    q64, k64, v64 = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("ahd,bhd->hab", q64.view(nq, H, 64), k64.view(nk, H, 64)) / 8.0
+    torch.einsum("hab,bhd->ahd", torch.softmax(s, -1), v64.view(nk, H, 64)).reshape(nq, d).backward(dout.double())
+    del s
+    for name, a, b in (("dq", q, q64), ("dk", k, k64), ("dv", v, v64)):
+        close64(a.grad, b.grad, name, rtol=1e-3, atol_scale=2e-4)
+    base = [t.grad.clone() for t in (q, k, v)]
+    for splits in ("1", "3"):
+        monkeypatch.setenv("VLSAT_FLASH_BWD_SPLITS", splits)
+        for t in (q, k, v):
+            t.grad = None
+        A.flash_attn(q, k, v, H).backward(dout)
+        for name, t, b in zip(("dq", "dk", "dv"), (q, k, v), base):
+            assert_close(t.grad, b, f"{name} splits={splits}", rtol=1e-4, atol_scale=1e-5)
 
 
 @pytest.mark.parametrize("m,n,k,act", [(300, 504, 768, ops.ACT_NONE), (9600, 64, 11, ops.ACT_RELU), (30, 26, 256, ops.ACT_SIGMOID),
