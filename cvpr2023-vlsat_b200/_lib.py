@@ -56,6 +56,8 @@ SIGNATURES = {
     "vlsat_edge_descriptor_fwd": [vp, i64, vp, i64, vp, vp],
     "vlsat_linear_fwd": [vp, i64, vp, i64, vp, i64, i64, i64, i64, C.POINTER(Epilogue), C.POINTER(LinearOpts), vp],
     "vlsat_linear_workspace_bytes": [i64, i64, i64, i32, i32],
+    "vlsat_gemm_pairs": [i32, vp, vp, i64, vp, vp, i64, vp, i64, i64, i64, i64, vp, sz, vp],
+    "vlsat_gemm_pairs_workspace_bytes": [i32, i64, i64, i64],
     "vlsat_tf32_split": [vp, i64, i64, i64, vp, vp, vp],
     "vlsat_add_layernorm_fwd": [vp, i64, vp, i64, vp, vp, vp, i64, i64, i32, f32, i32, vp, vp, i64, vp],
     "vlsat_relu_fwd": [vp, vp, i64, vp],
@@ -121,7 +123,7 @@ SIGNATURES = {
     "vlsat_topk_triplet_ranks": [vp, i64, i32, vp, i32, vp, vp, vp, i64, i32, f32, vp, vp],
     "vlsat_adamw_step": [vp, vp, vp, i64, i32, C.c_double, C.c_double, f32, vp, i64, vp],
 }
-_RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_bwd_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
+_RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_gemm_pairs_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_bwd_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
 
 _lib = None
 

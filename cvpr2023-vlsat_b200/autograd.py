@@ -34,12 +34,23 @@ def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return t.contiguous()
 
 
-def weight_grad(dz: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """dW [N, K] = dz^T x. Small [N, K] with a tall reduction: slab-parallel FP32 kernel; otherwise the GEMM engine on
-    transposed operands (reduction length zero-padded to a multiple of 4)."""
+def _pairs_engine(*dims) -> bool:
+    """The stored-operand backward GEMMs (vlsat_gemm_pairs, BF16x3) serve this projection: tensor-core engine with bf16
+    pairs and every stored row length a multiple of 8."""
+    # widths below 32 stay on the exact FFMA path: they are tiny, and some of their gradients vanish in exact arithmetic
+    # (everything upstream of the distance bias sums to zero over a softmax row), where BF16x3 noise is all there is
+    return ops.tensor_cores_enabled() and all(d % 8 == 0 and d >= 32 for d in dims) and ops.default_fmt(8) == ops.FMT_BF16
+
+
+def weight_grad(dz: torch.Tensor, x: torch.Tensor, dz_pair=None, x_pair=None) -> torch.Tensor:
+    """dW [N, K] = dz^T x. Tensor-core engine: both operands are read as stored (MN-major descriptors, the reduction over
+    the rows split across CTAs - csrc/gemm_tc.cu); otherwise a slab-parallel FP32 kernel for small [N, K], or the GEMM
+    engine on transposed copies."""
     n, k = dz.shape[1], x.shape[1]
     if dz.shape[0] == 0:
         return torch.zeros((n, k), device=dz.device, dtype=torch.float32)
+    if _pairs_engine(n, k):
+        return ops.gemm_tn(dz_pair if dz_pair is not None else ops.act_pair(dz), x_pair if x_pair is not None else ops.act_pair(x), n, k)
     if n <= 128 and k <= 128:
         return ops.wgrad_small(dz, x)
     return ops.linear(ops.transpose(dz), ops.transpose(x), cache_w=False)
@@ -52,10 +63,17 @@ class _Linear(Function):
         if (residual is not None or scale is not None) and act != ACT_NONE:
             raise ValueError("linear: residual / logit scale cannot be combined with an activation")
         gather = (ga, ia, gb, ib) if ga is not None else None
-        y = ops.linear(x, w, bias, act=act, gather=gather, residual=residual, scale_ptr=scale)
+        n, k = w.shape
+        # tensor-core engine: the bf16 pairs of x and w feed the forward GEMM and, kept for the backward, dW = dZ^T X and
+        # dX = dZ W without a transposed copy or a second split pass
+        pairs = _pairs_engine(n, k) and x.shape[0] > 0 and k >= 32
+        xp = ops.act_pair(x) if pairs else None
+        wp = ops.weight_pair(w) if pairs else None
+        y = ops.linear(x, w, bias, act=act, gather=gather, residual=residual, scale_ptr=scale, x_split=xp, w_split=wp)
         ctx.act = act
         ctx.has = (bias is not None, ga is not None, gb is not None, residual is not None, scale is not None)
         ctx.shapes = (ga.shape if ga is not None else None, gb.shape if gb is not None else None)
+        ctx.pairs = (xp, wp)
         keep_y = act != ACT_NONE or scale is not None
         ctx.save_for_backward(x, w, y if keep_y else None, ia, ib, scale)
         return y
@@ -80,11 +98,19 @@ class _Linear(Function):
         else:
             dz, db = ops.act_bwd(dy, y, ctx.act, want_dz=True, want_dbias=want_db, scale_ptr=scale if has_scale else None)
         dx = dw = d_ga = d_gb = None
-        if need[0]:
-            wt = ops.transpose(w)                               # [K, round4(N)]
-            dx = ops.linear(dz, wt[:, :n], cache_w=False)       # (an empty batch yields an empty dx)
-        if need[1]:
-            dw = weight_grad(dz, x)                             # [N, K], reduction over the rows
+        xp, wp = ctx.pairs
+        if xp is not None and dz.shape[0] > 0:
+            dzp = ops.act_pair(dz)
+            if need[0]:
+                dx = ops.gemm_nn(dzp, wp, w.shape[1])           # dZ [M, N] . W [N, K], W as the forward stores it
+            if need[1]:
+                dw = ops.gemm_tn(dzp, xp, n, w.shape[1])        # dZ^T X, both as stored
+        else:
+            if need[0]:
+                wt = ops.transpose(w)                           # [K, round4(N)]
+                dx = ops.linear(dz, wt[:, :n], cache_w=False)   # (an empty batch yields an empty dx)
+            if need[1]:
+                dw = weight_grad(dz, x)                         # [N, K], reduction over the rows
         if has_ga and need[4]:
             d_ga = ops.scatter_add_rows(dz, ia, torch.zeros(ctx.shapes[0], device=dz.device, dtype=torch.float32))
         if has_gb and need[6]:
@@ -283,7 +309,10 @@ class _PointNet(Function):
         dw3, dh2 = ops.pointnet_pool_bwd(dz3, arg, h2, w3, n_pts)
         dz2, db2 = ops.act_bwd(dh2, h2, ACT_RELU)
         dw2 = weight_grad(dz2, h1)
-        dh1 = ops.linear(dz2, ops.transpose(w2)[:, :w2.shape[0]], cache_w=False)
+        if _pairs_engine(w2.shape[0], w2.shape[1]):
+            dh1 = ops.gemm_nn(ops.act_pair(dz2), ops.weight_pair(w2), w2.shape[1])
+        else:
+            dh1 = ops.linear(dz2, ops.transpose(w2)[:, :w2.shape[0]], cache_w=False)
         dz1, db1 = ops.act_bwd(dh1, h1, ACT_RELU)
         dw1 = weight_grad(dz1, xr)
         return None, dw1, db1, dw2, db2, dw3, db3
@@ -352,9 +381,19 @@ class _FlashAttn(Function):
     def forward(ctx, q, k, v, n_heads):
         nk = k.shape[0]
         d = q.shape[1]
+        ctx.prep = None
         if d == n_heads * 64 and ops.tensor_cores_enabled():
-            vt = ops.transpose(v)                                   # [D, round4(nk)]
-            out, lse = ops.flash_attn_bf16(q, k, vt, nk, n_heads, want_lse=True)
+            if FLASH_BWD_STREAMING and q.shape[0] > 0 and nk > 0:
+                # one pass per operand gives the pair the forward reads and the transposed pair the backward reads
+                # (v: the forward takes V^T, the backward V)
+                qp, qt = ops.bf16_split_t(q)
+                kp, kt = ops.bf16_split_t(k)
+                vp, vt = ops.bf16_split_t(v)
+                out, lse = ops.flash_attn_bf16(qp, kp, vt, nk, n_heads, want_lse=True)
+                ctx.prep = (qp, qt, kp, kt, vp)
+            else:
+                vt = ops.transpose(v)                               # [D, round4(nk)]
+                out, lse = ops.flash_attn_bf16(q, k, vt, nk, n_heads, want_lse=True)
         else:
             out, lse = ops.flash_attn(q, k, v, n_heads, want_lse=True)
         ctx.save_for_backward(q, k, v, out, lse)
@@ -370,9 +409,9 @@ class _FlashAttn(Function):
         dk_ = d // H
         scale = 1.0 / math.sqrt(dk_)
         dout = _c(dout)
-        if d == H * 64 and ops.tensor_cores_enabled() and FLASH_BWD_STREAMING:
+        if ctx.prep is not None:
             # streaming tcgen05 backward: S, P, dP, dS live in tensor memory only (csrc/flash_attn_bwd.cu)
-            dq, dk, dv = ops.flash_attn_bf16_bwd(q, k, v, dout, out, lse, H)
+            dq, dk, dv = ops.flash_attn_bf16_bwd(q, k, v, dout, out, lse, H, prep=ctx.prep)
             return dq, dk, dv, None
         delta = ops.rowdot_heads(dout, out, H)                      # [H, nq]
         dq = torch.empty_like(q)

@@ -13,6 +13,11 @@ struct LinearArgs {
     vlsat_epilogue epi;
     long long* trace;      // debug: per-phase clock64 stamps of CTA (0,0); nullptr in normal use
     int tma_store;         // tensor-core engine: outputs leave through TMA stores (all rows 16-byte addressable)
+    // split reduction (backward GEMMs with a tall reduction, csrc/gemm_tc.cu): work item t covers K blocks
+    // [sp * kb_per_split, ...) of tile t / splits, sp = t % splits, and stores at row offset sp * slab_rows of the y map
+    int splits = 1;
+    int kb_per_split = 0;
+    int64_t slab_rows = 0;
 };
 
 __device__ __forceinline__ float apply_act(float t, int act) {

@@ -445,6 +445,15 @@ __global__ void sum_slabs_kernel(const float* __restrict__ slabs, int64_t slab_s
 }
 
 // ------------------------------------------------------------------------------------------------------ host
+// out [rows, cols] (row stride ldo) = sum of `splits` slabs of [slab rows >= rows, cols] fp32, slab_stride elements apart
+int sum_slabs(const float* slabs, int64_t slab_stride, int splits, float* out, int64_t ldo, int64_t rows, int64_t cols, cudaStream_t st) {
+    if (rows == 0 || cols == 0) return VLSAT_OK;
+    if (cols % 4 || ldo % 4) return VLSAT_ERR_UNSUPPORTED;
+    const int64_t n4 = rows * (cols / 4);
+    launch_k(sum_slabs_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, slabs, slab_stride, splits, out, ldo, rows, cols / 4);
+    return finish_launch();
+}
+
 static int fw_pick_splits(int64_t n_stat, int64_t n_stream, int n_heads) {
     const int64_t items = ceil_div(n_stat, FW_ROWS) * n_heads;
     const int64_t n_tiles = ceil_div(n_stream, FW_T);

@@ -62,7 +62,13 @@ __global__ void tf32_split_kernel(const float* __restrict__ x, int64_t ldx, int6
 // Persistent kernel: gridDim.x CTAs walk the output tiles round-robin (n fastest, so the CTAs that run
 // together share A row-tiles in L2). Two TMEM accumulators: the epilogue of tile i overlaps the main loop
 // of tile i+1.
-template <int BN, int STAGES, int PASSES, Kind KD, bool GATHER, bool RESID>
+// MAJ: operand storage. Bit 0: A is MN-major (stored [K, M]: the reduction index runs over the ROWS of the stored matrix),
+// bit 1: B is MN-major (stored [K, N]). Backward GEMMs read their operands as the forward left them, without transposes:
+//   dX = dZ W      A = dZ [M, N] K-major, B = W [N, K] stored with the reduction (N) on rows -> MAJ = 2
+//   dW = dZ^T X    A = dZ stored [M, N], B = X stored [M, K], reduction (M) on rows of both    -> MAJ = 3 (+ split reduction)
+// An MN-major tile of one K block is [64 reduction rows x 64 elements (128 B)] TMA boxes with the 128B swizzle, one box per 64
+// M/N elements, 8 KB apart (LBO); 8-row swizzle atoms are 1024 B apart along the reduction (SBO); one UMMA_K = 16 rows = 2 KB.
+template <int BN, int STAGES, int PASSES, Kind KD, bool GATHER, bool RESID, int MAJ = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                  const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
@@ -86,7 +92,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
     constexpr int BK = (KD == Kind::TF32) ? TC_BK : 2 * TC_BK;      // K elements per 128-byte block
     const int num_kb = (int)((a.K + BK - 1) / BK);
     const int tiles_n = (int)((a.N + BN - 1) / BN), tiles_m = (int)((a.M + TC_BM - 1) / TC_BM);
-    const int n_tiles = tiles_m * tiles_n;
+    const int n_tiles = tiles_m * tiles_n * a.splits;        // work items: (tile, reduction split)
+    const int splits = a.splits;
+    const int kb_per = splits > 1 ? a.kb_per_split : num_kb;
+    constexpr bool A_MN = (MAJ & 1) != 0, B_MN = (MAJ & 2) != 0;
+    static_assert(MAJ == 0 || KD == Kind::BF16, "MN-major operands: bf16 pairs only");
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_ahi); prefetch_tmap(&tm_bhi);
@@ -106,57 +116,81 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
         // warp-uniform loops; one elected lane issues (keeps TMA / MMA issue on the uniform datapath)
         int g = 0;                                          // k-block counter across tiles -> ring position
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * BN;
-            for (int kb = 0; kb < num_kb; ++kb, ++g) {
+            const int tl = t / splits, sp = t - tl * splits;
+            const int m0 = (tl / tiles_n) * TC_BM, n0 = (tl % tiles_n) * BN;
+            const int kb_end = min(num_kb, (sp + 1) * kb_per);
+            for (int kb = sp * kb_per; kb < kb_end; ++kb, ++g) {
                 const int s = g % STAGES;
                 mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
                 if (elect_one()) {
                     uint8_t* st = smem + s * STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                    tma_load_2d(st, &tm_ahi, &full_bar[s], kb * BK, m0);
-                    tma_load_2d(st + TC_A_TILE, &tm_bhi, &full_bar[s], kb * BK, n0);
+                    auto load_a = [&](uint8_t* dst, const CUtensorMap* tm) {
+                        if constexpr (A_MN) {
+#pragma unroll
+                            for (int j = 0; j < TC_BM / 64; ++j) tma_load_2d(dst + j * 8192, tm, &full_bar[s], m0 + 64 * j, kb * BK);
+                        } else {
+                            tma_load_2d(dst, tm, &full_bar[s], kb * BK, m0);
+                        }
+                    };
+                    auto load_b = [&](uint8_t* dst, const CUtensorMap* tm) {
+                        if constexpr (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j) tma_load_2d(dst + j * 8192, tm, &full_bar[s], n0 + 64 * j, kb * BK);
+                        } else {
+                            tma_load_2d(dst, tm, &full_bar[s], kb * BK, n0);
+                        }
+                    };
+                    load_a(st, &tm_ahi);
+                    load_b(st + TC_A_TILE, &tm_bhi);
                     if (PASSES == 3) {
-                        tma_load_2d(st + TC_A_TILE + B_TILE, &tm_alo, &full_bar[s], kb * BK, m0);
-                        tma_load_2d(st + 2 * TC_A_TILE + B_TILE, &tm_blo, &full_bar[s], kb * BK, n0);
+                        load_a(st + TC_A_TILE + B_TILE, &tm_alo);
+                        load_b(st + 2 * TC_A_TILE + B_TILE, &tm_blo);
                     }
                 }
                 __syncwarp();
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc<KD>(TC_BM, BN);
-        // descriptors differ only in the 14-bit start-address field: build one, then add offsets (>>4)
+        constexpr uint32_t idesc = make_idesc<KD>(TC_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+        // descriptors differ only in the 14-bit start-address field: build one per operand form, then add offsets (>>4)
         const uint64_t desc0 = make_sdesc_k128(smem_u32(smem));
+        const uint64_t desc0_mn = make_sdesc_mn128(smem_u32(smem), 8192, 1024);
+        const uint64_t da0 = A_MN ? desc0_mn : desc0, db0 = B_MN ? desc0_mn : desc0;
+        constexpr uint64_t a_step = A_MN ? (2048 >> 4) : 2, b_step = B_MN ? (2048 >> 4) : 2;    // one UMMA_K along the reduction
         int g = 0, i = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int buf = i & 1;
+            const int sp = t % splits;
+            const int kb_begin = sp * kb_per, kb_end = min(num_kb, (sp + 1) * kb_per);
             mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
             tc_fence_after();
             if (a.trace && blockIdx.x == 0 && lane == 0 && i < 8) a.trace[i * 4 + 0] = gtime();
             const uint32_t tacc = tmem_base + buf * BN;
-            for (int kb = 0; kb < num_kb; ++kb, ++g) {
+            for (int kb = kb_begin; kb < kb_end; ++kb, ++g) {
                 const int s = g % STAGES;
                 mbar_wait(&full_bar[s], (g / STAGES) & 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint64_t dah = desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
-                    const uint64_t dbh = dah + (TC_A_TILE >> 4);
-                    const uint64_t dal = dah + ((TC_A_TILE + B_TILE) >> 4);
-                    const uint64_t dbl = dah + ((2 * TC_A_TILE + B_TILE) >> 4);
+                    const uint64_t so = (uint64_t)(s * (STAGE_BYTES >> 4));
+                    const uint64_t dah = da0 + so;
+                    const uint64_t dbh = db0 + so + (TC_A_TILE >> 4);
+                    const uint64_t dal = da0 + so + ((TC_A_TILE + B_TILE) >> 4);
+                    const uint64_t dbl = db0 + so + ((2 * TC_A_TILE + B_TILE) >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {               // UMMA_K = 8 tf32 / 16 bf16 = 32 bytes = 2 x 16 B
-                        const uint32_t acc = (k > 0) ? 1u : (kb > 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {               // UMMA_K = 8 tf32 / 16 bf16 = 32 bytes = 2 x 16 B (K-major)
+                        const uint32_t acc = (k > 0) ? 1u : (kb > kb_begin ? 1u : 0u);
                         if (PASSES == 3) {
                             // small terms first, then the leading product
-                            mma_ss<KD>(tacc, dal + 2 * k, dbh + 2 * k, idesc, acc);
-                            mma_ss<KD>(tacc, dah + 2 * k, dbl + 2 * k, idesc, 1);
-                            mma_ss<KD>(tacc, dah + 2 * k, dbh + 2 * k, idesc, 1);
+                            mma_ss<KD>(tacc, dal + a_step * k, dbh + b_step * k, idesc, acc);
+                            mma_ss<KD>(tacc, dah + a_step * k, dbl + b_step * k, idesc, 1);
+                            mma_ss<KD>(tacc, dah + a_step * k, dbh + b_step * k, idesc, 1);
                         } else {
-                            mma_ss<KD>(tacc, dah + 2 * k, dbh + 2 * k, idesc, acc);
+                            mma_ss<KD>(tacc, dah + a_step * k, dbh + b_step * k, idesc, acc);
                         }
                     }
                     tc_commit(&empty_bar[s]);                    // stage reusable once these MMAs retire
-                    if (kb == num_kb - 1) tc_commit(&acc_full[buf]);
+                    if (kb == kb_end - 1) tc_commit(&acc_full[buf]);
                 }
                 __syncwarp();
             }
@@ -211,7 +245,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
         int i = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int buf = i & 1;
-            const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * BN;
+            const int tl = t / splits, sp = t - tl * splits;
+            const int m0 = (tl / tiles_n) * TC_BM, n0 = (tl % tiles_n) * BN;
+            const int row_out0 = m0 + sp * (int)a.slab_rows;     // split reductions store into their own slab of the y map
             const int64_t m_own = (int64_t)m0 + q * 32 + lane;
             const bool own_ok = m_own < a.M;
             const int64_t ia_own = (own_ok && e.gather_a) ? e.idx_a[m_own] : 0;
@@ -301,7 +337,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
                     // the prefetched row operands are consumed: refill them for this warpgroup's next chunk, in flight
                     // during the store hand-off below and the next TMEM load
                     if ((GATHER || RESID) && c0 + 64 < BN) issue_row_loads(nb + 64);
-                    if (a.y) stage_store(&tm_y, v, (int)nb, m0);
+                    if (a.y) stage_store(&tm_y, v, (int)nb, row_out0);
                     if (e.split_hi && split_bf16) {
                         uint32_t hp[16], lp[16];
 #pragma unroll
@@ -364,15 +400,15 @@ int tf32_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* h
     return finish_launch();
 }
 
-template <int BN, int STAGES, int PASSES, Kind KD, bool GATHER, bool RESID>
+template <int BN, int STAGES, int PASSES, Kind KD, bool GATHER, bool RESID, int MAJ = 0>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tal, const CUtensorMap& tb, const CUtensorMap& tbl,
                      const CUtensorMap& ty, const CUtensorMap& tsh, const CUtensorMap& tsl,
                      const LinearArgs& a, cudaStream_t st) {
     constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TC_A_TILE + BN * 128);
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 2 * TC_BM * 128 /*store staging*/ + BN * 4 /*bias*/ + 1024 /*align*/ + 256 /*barriers*/;
-    auto kern = linear_tc_kernel<BN, STAGES, PASSES, KD, GATHER, RESID>;
+    auto kern = linear_tc_kernel<BN, STAGES, PASSES, KD, GATHER, RESID, MAJ>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int64_t n_tiles = ceil_div(a.N, BN) * ceil_div(a.M, TC_BM);
+    const int64_t n_tiles = ceil_div(a.N, BN) * ceil_div(a.M, TC_BM) * a.splits;
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, kNumSMs);
     launch_k(kern, dim3(grid), dim3(TC_THREADS), smem, st, ta, tal, tb, tbl, ty, tsh, tsl, a);
     return finish_launch();
@@ -436,4 +472,96 @@ int linear_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
 #undef VLSAT_TC_LAUNCH
 }
 
+// ------------------------------------------------------------------------------ backward GEMMs on stored operands
+int sum_slabs(const float* slabs, int64_t slab_stride, int splits, float* out, int64_t ldo, int64_t rows, int64_t cols, cudaStream_t st);
+
+// Reduction split of a [M, N] output with num_kb K blocks: fill the 148 SMs when there are few output tiles (weight
+// gradients: small [N_w, K_w] outputs, reductions over thousands of rows). Every split gets at least one K block.
+static void pick_reduction_split(int64_t M, int64_t N, int bn, int64_t num_kb, int* splits, int* kb_per) {
+    const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, bn);
+    int best = 1; double best_cost = 1e30;
+    for (int s = 1; s <= kNumSMs && s <= num_kb; ++s) {
+        const int64_t per = ceil_div(num_kb, s);
+        if (ceil_div(num_kb, per) != s) continue;                // same blocks per split as a smaller s: skip
+        const double waves = (double)ceil_div(tiles * s, kNumSMs);
+        // K blocks per wave + tile prologue / epilogue (~8 blocks' worth) + writing and summing the slabs
+        const double cost = waves * ((double)per + 8.0) + (s > 1 ? 6.0 + 0.1 * s : 0.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+    }
+    *splits = best;
+    *kb_per = (int)ceil_div(num_kb, best);
+}
+
+size_t gemm_pairs_workspace_bytes(int mode, int64_t M, int64_t N, int64_t K) {
+    if (mode != 3) return 0;
+    const int bn = (N <= 64) ? 64 : 128;
+    int splits, kb_per;
+    pick_reduction_split(M, N, bn, ceil_div(K, 64), &splits, &kb_per);
+    return splits > 1 ? (size_t)splits * (size_t)(ceil_div(M, TC_BM) * TC_BM) * (size_t)N * sizeof(float) : 0;
+}
+
+// y [M, N] (fp32, row stride ldy) from bf16 (hi, lo) pair operands read AS STORED:
+//   mode 2: y = a b      a stored [M, K] (row stride lda), b stored [K, N] (row stride ldb)
+//   mode 3: y = a^T b    a stored [K, M], b stored [K, N]; the reduction runs over the stored rows and is split over CTAs
+// Row strides in elements, multiples of 8; M, N multiples of 8 where they are a stored row length.
+int gemm_pairs_tc(int mode, const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi, const uint16_t* b_lo,
+                  int64_t ldb, float* y, int64_t ldy, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes,
+                  cudaStream_t st) {
+    if (mode != 2 && mode != 3) return VLSAT_ERR_INVALID_ARG;
+    if ((lda | ldb) % 8 || ldy % 4 || ((uintptr_t)y & 15) || M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return VLSAT_ERR_UNSUPPORTED;
+    LinearArgs a;
+    a.x = nullptr; a.ldx = lda; a.w = nullptr; a.ldw = ldb; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.K = K;
+    a.epi = vlsat_epilogue{}; a.epi.alpha = 1.f;
+    a.trace = nullptr;
+    const int64_t tiles128 = ceil_div(M, TC_BM) * ceil_div(N, 128);
+    const int bn = (N <= 64 || (mode == 2 && 2 * tiles128 <= kNumSMs)) ? 64 : 128;
+    const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUtensorMap ta, tal, tb, tbl, ty;
+    bool ok;
+    if (mode == 2) ok = make_tmap_2d(&ta, a_hi, BF, 2, M, K, lda, 64, TC_BM) && make_tmap_2d(&tal, a_lo, BF, 2, M, K, lda, 64, TC_BM);
+    else ok = make_tmap_2d(&ta, a_hi, BF, 2, K, M, lda, 64, 64) && make_tmap_2d(&tal, a_lo, BF, 2, K, M, lda, 64, 64);
+    ok = ok && make_tmap_2d(&tb, b_hi, BF, 2, K, N, ldb, 64, 64) && make_tmap_2d(&tbl, b_lo, BF, 2, K, N, ldb, 64, 64);
+    if (!ok) return VLSAT_ERR_UNSUPPORTED;
+    int splits = 1, kb_per = 0;
+    float* dst = y; int64_t ld_dst = ldy; int64_t rows_dst = M;
+    if (mode == 3) {
+        pick_reduction_split(M, N, bn, ceil_div(K, 64), &splits, &kb_per);
+        if (splits > 1) {
+            const size_t need = gemm_pairs_workspace_bytes(mode, M, N, K);
+            if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15) || N % 4) return VLSAT_ERR_WORKSPACE;
+            a.splits = splits; a.kb_per_split = kb_per; a.slab_rows = ceil_div(M, TC_BM) * TC_BM;
+            dst = (float*)workspace; ld_dst = N; rows_dst = a.slab_rows * splits;
+            a.y = dst; a.ldy = ld_dst;
+        }
+    }
+    if (!make_tmap_2d(&ty, dst, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows_dst, N, ld_dst, 32, TC_BM)) return VLSAT_ERR_UNSUPPORTED;
+    a.tma_store = 1;
+    int rc;
+    if (mode == 2) rc = bn == 64 ? launch_tc<64, 4, 3, Kind::BF16, false, false, 2>(ta, tal, tb, tbl, ty, ty, ty, a, st)
+                                 : launch_tc<128, 3, 3, Kind::BF16, false, false, 2>(ta, tal, tb, tbl, ty, ty, ty, a, st);
+    else rc = bn == 64 ? launch_tc<64, 4, 3, Kind::BF16, false, false, 3>(ta, tal, tb, tbl, ty, ty, ty, a, st)
+                       : launch_tc<128, 3, 3, Kind::BF16, false, false, 3>(ta, tal, tb, tbl, ty, ty, ty, a, st);
+    if (rc != VLSAT_OK || splits == 1) return rc;
+    return sum_slabs(dst, a.slab_rows * N, splits, y, ldy, M, N, st);
+}
+
 }  // namespace vlsat
+
+using namespace vlsat;
+
+extern "C" size_t vlsat_gemm_pairs_workspace_bytes(int mode, int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return gemm_pairs_workspace_bytes(mode, M, N, K);
+}
+
+extern "C" int vlsat_gemm_pairs(int mode, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo,
+                                int64_t ldb, float* y, int64_t ldy, int64_t M, int64_t N, int64_t K, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+    VLSAT_REQUIRE(M >= 0 && N >= 0 && K >= 1 && (mode == VLSAT_GEMM_NN || mode == VLSAT_GEMM_TN));
+    if (M == 0 || N == 0) return VLSAT_OK;
+    VLSAT_REQUIRE(a_hi && a_lo && b_hi && b_lo && y && ldy >= N && ldb >= N && lda >= (mode == VLSAT_GEMM_NN ? K : M));
+    VLSAT_SUPPORT(encode_fn() != nullptr && N >= 8);
+    VLSAT_SUPPORT((((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)b_hi | (uintptr_t)b_lo) & 15) == 0);
+    return gemm_pairs_tc(mode, (const uint16_t*)a_hi, (const uint16_t*)a_lo, lda, (const uint16_t*)b_hi, (const uint16_t*)b_lo, ldb,
+                         y, ldy, M, N, K, workspace, workspace_bytes, (cudaStream_t)stream);
+}

@@ -171,6 +171,35 @@ def _tc_eligible(x, ldx, w, ldw, n, k, fmt) -> bool:
             and w.data_ptr() % 16 == 0 and n >= 8)
 
 
+def _cacheable_weight(w: torch.Tensor) -> bool:
+    """A weight whose split may be cached by storage address: a parameter, a view of one, or a persistent derived tensor
+    (no autograd history). Temporaries built inside a differentiable forward (e.g. the head-major permutations of
+    train_path, a fresh copy per call) are NOT: caching them would pin one buffer per call for ever."""
+    base = w if w._base is None else w._base
+    return isinstance(base, torch.nn.Parameter) or (w.grad_fn is None and not w.requires_grad)
+
+
+def weight_pair(w: torch.Tensor, fmt: int = FMT_BF16):
+    """(hi, lo) pair of a weight matrix [N, K] (row stride allowed): cached per parameter version when ``w`` is
+    parameter-backed, split per call otherwise."""
+    _, ldw = _rows(w, "w")
+    return _weight_split(w, ldw, fmt) if _cacheable_weight(w) else split_pair(w, fmt)
+
+
+def act_pair(x: torch.Tensor):
+    """bf16 (hi, lo) pair of an activation, remembered on the tensor object while its version stands: the projections that
+    read the same tensor (q / k / v of one input, forward and backward of one layer) share one split pass."""
+    ent = getattr(x, "_vlsat_pair", None)
+    if ent is not None and ent[0] == x._version and ent[1][0].shape == x.shape:
+        return ent[1]
+    pair = bf16_split(x)
+    try:
+        x._vlsat_pair = (x._version, pair)
+    except AttributeError:
+        pass
+    return pair
+
+
 def _weight_split(w: torch.Tensor, ldw: int, fmt: int):
     """(hi, lo) copies of a weight (view) in pair format ``fmt``, cached until the parameter is written again."""
     key = (w.data_ptr(), tuple(w.shape), ldw, fmt)
@@ -292,7 +321,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
                 ws = torch.empty((2 * n * k,), device=x.device, dtype=torch.float32)
         else:
             # cache_w=False: w is an activation / a per-call temporary (backward GEMMs), never cache its split
-            hl = w_split if w_split is not None else (_weight_split(w, ldw, fmt) if cache_w else split_pair(w, fmt))
+            hl = w_split if w_split is not None else (_weight_split(w, ldw, fmt) if (cache_w and _cacheable_weight(w)) else split_pair(w, fmt))
             opts.w_hi, opts.w_lo = hl[0].data_ptr(), hl[1].data_ptr()
             if x_split is not None:
                 opts.x_hi, opts.x_lo = x_split[0].data_ptr(), x_split[1].data_ptr()
@@ -307,6 +336,43 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     _lib.check(st, "vlsat_linear_fwd")
     if emit_split:
         return out, (y_split[0], y_split[1])
+    return out
+
+
+GEMM_NN, GEMM_TN = 2, 3
+
+
+def gemm_pairs_ok(*pairs) -> bool:
+    """Operands the stored-operand backward GEMMs can address: bf16 pairs with 16-byte aligned rows."""
+    return tensor_cores_enabled() and all(p is not None and p[0].dtype == torch.bfloat16 and p[0].stride(0) % 8 == 0
+                                          and p[0].data_ptr() % 16 == 0 and p[1].data_ptr() % 16 == 0 for p in pairs)
+
+
+def gemm_nn(a_pair, b_pair, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y [M, n] = a [M, K] . b [K, n] on bf16 (hi, lo) pairs read as stored (dX = dZ W with W the forward's weight pair)."""
+    m, k = a_pair[0].shape[0], b_pair[0].shape[0]
+    if out is None:
+        out = torch.empty((m, n), device=a_pair[0].device, dtype=torch.float32)
+    yp, ldy = _rows(out, "out")
+    st = _call("vlsat_gemm_pairs", GEMM_NN, a_pair[0].data_ptr(), a_pair[1].data_ptr(), a_pair[0].stride(0), b_pair[0].data_ptr(),
+               b_pair[1].data_ptr(), b_pair[0].stride(0), yp, ldy, m, n, k, None, 0, _stream(), work=(2.0 * m * n * k, 4.0 * (m * k + n * k + m * n)))
+    _lib.check(st, "vlsat_gemm_pairs(NN)")
+    return out
+
+
+def gemm_tn(a_pair, b_pair, m: int, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y [m, n] = a^T b with a stored [K, m], b stored [K, n] (dW = dZ^T X): the reduction runs over the stored rows and is
+    split over CTAs for small outputs (deterministic slab sums)."""
+    k = a_pair[0].shape[0]
+    if out is None:
+        out = torch.empty((m, n), device=a_pair[0].device, dtype=torch.float32)
+    yp, ldy = _rows(out, "out")
+    ws_bytes = int(_lib.load().vlsat_gemm_pairs_workspace_bytes(GEMM_TN, m, n, k))
+    ws = torch.empty((ws_bytes // 4,), device=out.device, dtype=torch.float32) if ws_bytes else None
+    st = _call("vlsat_gemm_pairs", GEMM_TN, a_pair[0].data_ptr(), a_pair[1].data_ptr(), a_pair[0].stride(0), b_pair[0].data_ptr(),
+               b_pair[1].data_ptr(), b_pair[0].stride(0), yp, ldy, m, n, k, ws.data_ptr() if ws is not None else None, ws_bytes, _stream(),
+               work=(2.0 * m * n * k, 4.0 * (m * k + n * k + m * n)))
+    _lib.check(st, "vlsat_gemm_pairs(TN)")
     return out
 
 
@@ -553,7 +619,7 @@ def flash_attn_bwd_stats(dout, out, lse, n_heads: int):
     return st[0], st[1]
 
 
-def flash_attn_bf16_bwd(q, k, v, dout, out, lse, n_heads: int):
+def flash_attn_bf16_bwd(q, k, v, dout, out, lse, n_heads: int, prep=None):
     """Streaming tensor-core backward of A9 (csrc/flash_attn_bwd.cu): (dq, dk, dv) fp32 for q [nq, H*64], k / v [nk, H*64],
     the upstream gradient dout, the forward's output and log-sum-exp [H, nq]. Scores never reach HBM."""
     nq, d = q.shape
@@ -565,9 +631,12 @@ def flash_attn_bf16_bwd(q, k, v, dout, out, lse, n_heads: int):
     dv = torch.empty((nk, d), device=q.device, dtype=torch.float32)
     if nq == 0 or nk == 0:
         return dq.zero_(), dk.zero_(), dv.zero_()
-    qp, qt = bf16_split_t(q)
-    kp, kt = bf16_split_t(k)
-    vp_, _ = bf16_split_t(v, want_t=False)
+    if prep is not None:                     # (q, q^T, k, k^T, v) pairs the forward already made
+        qp, qt, kp, kt, vp_ = prep
+    else:
+        qp, qt = bf16_split_t(q)
+        kp, kt = bf16_split_t(k)
+        vp_, _ = bf16_split_t(v, want_t=False)
     dop, dot = bf16_split_t(dout)
     lse2, delta = flash_attn_bwd_stats(dout, out, lse, n_heads)
     pair = lambda p: _lib.Bf16Pair(p[0].data_ptr(), p[1].data_ptr(), p[0].stride(0))

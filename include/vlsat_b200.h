@@ -128,6 +128,21 @@ int vlsat_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw,
                      float* y, int64_t ldy, int64_t M, int64_t N, int64_t K,
                      const vlsat_epilogue* epi, const vlsat_linear_opts* opts, void* stream);
 size_t vlsat_linear_workspace_bytes(int64_t M, int64_t N, int64_t K, int need_x_split, int need_w_split);
+
+/* Backward GEMMs of the dense projections on bf16 (hi, lo) pair operands read AS STORED - no transposed copies
+ * (autograd of every nn.Linear / Conv1d(k=1) of the path, e.g. network_MMG.py:87-100; the reference has no
+ * hand-written backward). BF16x3 arithmetic, MN-major tcgen05 shared-memory descriptors (csrc/gemm_tc.cu).
+ *   VLSAT_GEMM_NN: y [M, N] = a [M, K] . b [K, N]         (dX = dZ W: b is the weight as the forward stores it)
+ *   VLSAT_GEMM_TN: y [M, N] = a^T . b, a stored [K, M], b stored [K, N]   (dW = dZ^T X; the reduction over the stored
+ *                  rows is split over CTAs when the output has few tiles: deterministic slab sums through `workspace`,
+ *                  16-byte aligned, vlsat_gemm_pairs_workspace_bytes bytes)
+ * Row strides in elements, multiples of 8; y fp32, 16-byte aligned, ldy % 4 == 0 (overwritten). */
+#define VLSAT_GEMM_NN 2
+#define VLSAT_GEMM_TN 3
+int vlsat_gemm_pairs(int mode, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo,
+                     int64_t ldb, float* y, int64_t ldy, int64_t M, int64_t N, int64_t K, void* workspace,
+                     size_t workspace_bytes, void* stream);
+size_t vlsat_gemm_pairs_workspace_bytes(int mode, int64_t M, int64_t N, int64_t K);
 /* hi = tf32-rounded x (round to nearest), lo = x - hi; x [rows, cols] with row stride ldx, cols % 4 == 0,
  * outputs compact [rows, cols]. */
 int vlsat_tf32_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, void* stream);

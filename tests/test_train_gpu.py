@@ -262,6 +262,24 @@ def test_streaming_flash_backward_at_config2_size_and_forced_splits(monkeypatch)
             assert_close(t.grad, b, f"{name} splits={splits}", rtol=1e-4, atol_scale=1e-5)
 
 
+@pytest.mark.parametrize("m,n,k", [(9600, 512, 1024), (640, 768, 512), (300, 64, 200), (9600, 1536, 1024), (77, 8, 40), (1000, 160, 512)])
+def test_gemm_nn_on_stored_pairs(m, n, k):
+    """dX = dZ W with W read as the forward stores it (MN-major B operand, no transposed copy) against float64."""
+    a, b = rnd(m, k, seed=150), rnd(k, n, seed=151) / math.sqrt(k)
+    got = ops.gemm_nn(ops.bf16_split(a), ops.bf16_split(b), n)
+    close64(got, a.double() @ b.double(), "gemm_nn", rtol=1e-3, atol_scale=1e-4)
+
+
+@pytest.mark.parametrize("k,m,n", [(9600, 1024, 1536), (76800, 128, 128), (76800, 32, 128), (640, 768, 768), (9600, 512, 512), (100, 504, 768),
+                                   (1000, 160, 512), (70, 8, 64)])
+def test_gemm_tn_on_stored_pairs(k, m, n):
+    """dW = dZ^T X with both operands read as stored (MN-major A and B, reduction split over CTAs) against float64."""
+    a, b = rnd(k, m, seed=152), rnd(k, n, seed=153)
+    got = ops.gemm_tn(ops.bf16_split(a), ops.bf16_split(b), m, n)
+    close64(got, a.double().t() @ b.double(), "gemm_tn", rtol=1e-3, atol_scale=1e-4)
+    assert torch.equal(got, ops.gemm_tn(ops.bf16_split(a), ops.bf16_split(b), m, n)), "split reduction must be deterministic"
+
+
 @pytest.mark.parametrize("m,n,k,act", [(300, 504, 768, ops.ACT_NONE), (9600, 64, 11, ops.ACT_RELU), (30, 26, 256, ops.ACT_SIGMOID),
                                        (1000, 160, 512, ops.ACT_NONE), (0, 64, 64, ops.ACT_RELU)])
 def test_linear_backward(m, n, k, act):
@@ -512,6 +530,27 @@ def test_training_mode_with_dropout_runs_and_is_seeded():
     assert torch.allclose(g1, g2, rtol=1e-3, atol=1e-4 * g1.abs().max().item())   # atomics reorder sums, masks are identical
     assert not torch.equal(o1[2], o3[2])
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+def test_eager_training_does_not_grow_the_weight_split_cache():
+    """Round-1 advisor finding: the split cache keyed the head-major weight copies of the differentiable path by their
+    storage address, a fresh buffer per call, and pinned them for ever (about 20 MB per eager step). Forty eager steps
+    with parameter updates must leave the cache size and the allocated memory flat."""
+    model = V.Mmgnet(cases.model_config({}), 160, 26)
+    model.load_state_dict(cases.seeded_state(model, cases.MMGNET_WEIGHT_SEED))
+    model = model.to(DEV).train()
+    b = cases.MMGNET_CASES["mmgnet_ragged"][1]().to(DEV)
+    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=1e-6)
+    sizes, mem = [], []
+    for it in range(40):
+        opt.zero_grad(set_to_none=True)
+        cases.scalar_loss(model(*b.forward_args(), istrain=True)[:7], seed=7).backward()
+        opt.step()
+        if it in (4, 39):
+            torch.cuda.synchronize()
+            sizes.append(len(ops._weight_splits)); mem.append(torch.cuda.memory_allocated())
+    assert sizes[1] == sizes[0], f"weight-split cache grew from {sizes[0]} to {sizes[1]} entries"
+    assert mem[1] <= mem[0] + (4 << 20), f"allocated memory grew from {mem[0]} to {mem[1]} bytes over 35 eager steps"
 
 
 @pytest.mark.parametrize("gemm,bound", [("tc", 1e-3), ("auto", 2e-2)])
