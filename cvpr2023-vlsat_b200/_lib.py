@@ -27,6 +27,11 @@ class AdamWTensor(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("vmax", vp), ("n", i64), ("lr", f32), ("weight_decay", f32)]
 
 
+class CopyTensor(C.Structure):
+    """Mirror of ``vlsat_copy_tensor``."""
+    _fields_ = [("dst", vp), ("src", vp), ("n", i64)]
+
+
 class LinearOpts(C.Structure):
     """Mirror of ``vlsat_linear_opts``."""
     _fields_ = [("engine", i32), ("x_hi", vp), ("x_lo", vp), ("w_hi", vp), ("w_lo", vp), ("workspace", vp),
@@ -122,6 +127,7 @@ SIGNATURES = {
     "vlsat_topk_predicate_ranks": [vp, vp, i64, i32, i32, f32, vp, vp],
     "vlsat_topk_triplet_ranks": [vp, i64, i32, vp, i32, vp, vp, vp, i64, i32, f32, vp, vp],
     "vlsat_adamw_step": [vp, vp, vp, i64, i32, C.c_double, C.c_double, f32, vp, i64, vp],
+    "vlsat_pack_scale": [vp, vp, vp, i64, i32, f32, vp],
 }
 _RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_gemm_pairs_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_bwd_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
 

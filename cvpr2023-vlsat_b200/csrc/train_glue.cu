@@ -243,6 +243,26 @@ __global__ void adamw_kernel(const vlsat_adamw_tensor* __restrict__ tab, const i
         if (T.vmax) T.vmax[i] = vm;
     }
 }
+// dst_t[i] = scale * src_t[i] for every chunk of every tensor of the table, one launch: packs the gradients of a step
+// into the flat buffer the NCCL all-reduce runs on, with the 1 / world_size of the mean folded in (train_glue / dist.py).
+__global__ void pack_scale_kernel(const vlsat_copy_tensor* __restrict__ tab, const int32_t* __restrict__ chunk_tensor,
+                                  const int32_t* __restrict__ chunk_index, int chunk_elems, float scale) {
+    pdl_entry();
+    const vlsat_copy_tensor T = tab[chunk_tensor[blockIdx.x]];
+    const int64_t base = (int64_t)chunk_index[blockIdx.x] * chunk_elems;
+    const int64_t end = base + chunk_elems < T.n ? base + chunk_elems : T.n;
+    int64_t i0 = base;
+    if (((((uintptr_t)T.dst | (uintptr_t)T.src) & 15) == 0) && (chunk_elems % 4 == 0)) {
+        const int64_t n4 = (end - base) >> 2;
+        for (int64_t j = threadIdx.x; j < n4; j += blockDim.x) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(T.src + base + 4 * j));
+            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+            *reinterpret_cast<float4*>(T.dst + base + 4 * j) = v;
+        }
+        i0 = base + 4 * n4;
+    }
+    for (int64_t i = i0 + threadIdx.x; i < end; i += blockDim.x) T.dst[i] = T.src[i] * scale;
+}
 __global__ void bump_step_kernel(int64_t* step) {
     pdl_entry();
     if (threadIdx.x == 0 && blockIdx.x == 0) step[0] += 1;
@@ -352,4 +372,14 @@ extern "C" int vlsat_adamw_step(const vlsat_adamw_tensor* tensors, const int32_t
     }
     launch_k(bump_step_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, step);
     return finish_launch(launches);
+}
+
+extern "C" int vlsat_pack_scale(const vlsat_copy_tensor* tensors, const int32_t* chunk_tensor, const int32_t* chunk_index,
+                                int64_t n_chunks, int chunk_elems, float scale, void* stream) {
+    VLSAT_REQUIRE(n_chunks >= 0 && chunk_elems >= 1);
+    VLSAT_SUPPORT(n_chunks < (1ll << 31));
+    if (n_chunks == 0) return VLSAT_OK;
+    VLSAT_REQUIRE(tensors && chunk_tensor && chunk_index);
+    launch_k(pack_scale_kernel, dim3((unsigned)n_chunks), dim3(256), 0, (cudaStream_t)stream, tensors, chunk_tensor, chunk_index, chunk_elems, scale);
+    return finish_launch();
 }

@@ -43,48 +43,72 @@ def sum_over_ranks(value: float, device="cpu") -> float:
 
 class GradientAllReducer:
     """Data-parallel training: scenes shard by batch, the only collective is one all-reduce (mean) of the
-    gradients per step - NCCL over NVLink on the GPU box, gloo in the CPU tests.
+    gradients per step - NCCL over NVLink on the GPU box, gloo in the CPU tests. The reference is single-process; the
+    ordering follows its ``backward()`` (SGFN_MMG/model.py:483-488): between ``loss.backward()`` and ``optimizer.step()``.
 
-    Gradients are packed into a few flat buckets (one collective launch each, sized for launch latency rather than link
-    count), reduced asynchronously and unpacked; ``attach(optimizer)`` runs this from an optimizer pre-step hook, so the
-    reference's own ``loss.backward(); optimizer.step()`` (SGFN_MMG/model.py:483-488) needs no change.
-    Parameters without a gradient in this step (``triplet_projector_3d`` is never used by the forward) are skipped; the
-    set is the same on every rank because it depends on the model graph only."""
+    One persistent flat fp32 buffer holds every gradient of a step (16-byte aligned slots, allocated once per set of
+    gradient addresses). Per step: ONE multi-tensor launch packs the gradients into it with the 1 / world_size of the mean
+    folded in (``vlsat_pack_scale``), ONE all-reduce (sum) runs on the whole buffer, and every ``p.grad`` is re-pointed at
+    its slot - no ``torch.cat``, no divide pass, no copy back; the optimiser reads the averaged gradients where NCCL left
+    them. Parameters without a gradient in this step (``triplet_projector_3d`` is never used by the forward) are skipped;
+    the set is the same on every rank because it depends on the model graph only. ``attach(optimizer)`` runs this from an
+    optimizer pre-step hook, so the reference's own ``loss.backward(); optimizer.step()`` needs no change."""
 
-    def __init__(self, params, bucket_bytes: int = 64 << 20):
+    def __init__(self, params, chunk_elems: int = 16384):
         self.params = [p for p in params if p.requires_grad]
-        self.bucket_bytes = bucket_bytes
+        self.chunk_elems = chunk_elems
         self.last_bytes = 0
+        self._plan = None            # (signature, flat, views, table, chunk_tensor, chunk_index, n_chunks)
 
-    def _buckets(self, grads):
-        cur, size = [], 0
+    def _build(self, ps, grads):
+        sig = tuple((g.data_ptr(), g.numel()) for g in grads)
+        if self._plan is not None and self._plan[0] == sig:
+            return self._plan
+        dev = grads[0].device
+        offs, total = [], 0
         for g in grads:
-            nbytes = g.numel() * g.element_size()
-            if cur and size + nbytes > self.bucket_bytes:
-                yield cur
-                cur, size = [], 0
-            cur.append(g)
-            size += nbytes
-        if cur:
-            yield cur
+            offs.append(total)
+            total += (g.numel() + 3) // 4 * 4                      # 16-byte aligned slots
+        flat = torch.zeros((total,), device=dev, dtype=torch.float32)
+        views = [flat[o:o + g.numel()].view(g.shape) for o, g in zip(offs, grads)]
+        table = ct = ci = None
+        n_chunks = 0
+        if dev.type == "cuda":
+            from ._lib import CopyTensor
+            arr = (CopyTensor * len(grads))()
+            cts, cis = [], []
+            for i, (g, v) in enumerate(zip(grads, views)):
+                arr[i].dst, arr[i].src, arr[i].n = v.data_ptr(), g.data_ptr(), g.numel()
+                nch = (g.numel() + self.chunk_elems - 1) // self.chunk_elems
+                cts += [i] * nch
+                cis += list(range(nch))
+            table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+            ct, ci = torch.tensor(cts, dtype=torch.int32).to(dev), torch.tensor(cis, dtype=torch.int32).to(dev)
+            n_chunks = len(cts)
+        self._plan = (sig, flat, views, table, ct, ci, n_chunks)
+        return self._plan
 
     def allreduce(self) -> None:
         _, size = world()
-        grads = [p.grad for p in self.params if p.grad is not None]
+        ps = [p for p in self.params if p.grad is not None]
+        grads = [p.grad for p in ps]
         self.last_bytes = sum(g.numel() * g.element_size() for g in grads)
         if size == 1 or not grads:
             return
-        pending = []
-        for bucket in self._buckets(grads):
-            flat = torch.cat([g.reshape(-1) for g in bucket])
-            pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, bucket))
-        for work, flat, bucket in pending:
-            work.wait()
-            flat.div_(size)
-            off = 0
-            for g in bucket:
-                g.copy_(flat[off:off + g.numel()].view_as(g))
-                off += g.numel()
+        for i, g in enumerate(grads):
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                grads[i] = ps[i].grad = g.float().contiguous()
+        _, flat, views, table, ct, ci, n_chunks = self._build(ps, grads)
+        if flat.is_cuda:
+            from . import _lib, ops
+            _lib.check(ops._call("vlsat_pack_scale", table.data_ptr(), ct.data_ptr(), ci.data_ptr(), n_chunks, self.chunk_elems,
+                                 1.0 / size, ops._stream()), "vlsat_pack_scale")
+        else:                                                      # CPU tensors: the gloo tests of the host-side logic
+            for v, g in zip(views, grads):
+                v.copy_(g).div_(size)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        for p, v in zip(ps, views):
+            p.grad = v
 
     def attach(self, optimizer: torch.optim.Optimizer):
         """Average gradients across ranks right before every ``optimizer.step()``."""

@@ -462,6 +462,13 @@ int vlsat_adamw_step(const vlsat_adamw_tensor* tensors, const int32_t* chunk_ten
                      int64_t n_chunks, int chunk_elems, double beta1, double beta2, float eps, int64_t* step,
                      int64_t t_max, void* stream);
 
+/* Data-parallel training (the reference is single-process, SGFN_MMG/model.py:483-488 runs backward() and
+ * optimizer.step() back to back): dst_t = scale * src_t for every tensor of a table in ONE launch - packs a step's
+ * gradients into the flat buffer the NCCL all-reduce runs on, with 1 / world_size folded in. */
+typedef struct { float* dst; const float* src; int64_t n; } vlsat_copy_tensor;
+int vlsat_pack_scale(const vlsat_copy_tensor* tensors, const int32_t* chunk_tensor, const int32_t* chunk_index,
+                     int64_t n_chunks, int chunk_elems, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * N2  device-side object preparation of the input pipeline: for object o and sampled point p,
  *   row = cloud[choice[o, p], :]   (src/dataset/dataset_3dssg.py:288-289; `choice` = the np.random.choice result offset

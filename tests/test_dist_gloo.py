@@ -82,7 +82,7 @@ def _grad_worker(rank, world, port, q):
         unused = torch.nn.Linear(4, 4)                     # trainable but never used (triplet_projector_3d): grad stays None
         params = list(net.parameters()) + list(unused.parameters())
         opt = torch.optim.SGD([p for p in params if p.requires_grad], lr=0.5)
-        red = vd.GradientAllReducer(params, bucket_bytes=256)          # several buckets
+        red = vd.GradientAllReducer(params, chunk_elems=64)            # flat buffer, several chunks per tensor
         red.attach(opt)
         g = torch.Generator().manual_seed(100 + rank)      # different data per rank
         x = torch.randn(6, 8, generator=g)
