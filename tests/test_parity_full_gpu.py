@@ -1,0 +1,138 @@
+"""Parity at BASELINE.json's FULL sizes (round-1 verdict: the benchmarked shapes were only covered through self-consistency
+properties). Every output of the CUDA path is compared with the oracle restatement of the reference run on the SAME inputs
+and weights; the oracle (test infrastructure, pinned on the unmodified reference by tests/test_oracle.py) runs in fp32 eager
+PyTorch on the same GPU because its dense [8, sum_E, sum_E] score tensors (attention.py:55-66) take minutes on host cores.
+torch's fp32 matmuls are exact fp32 here (TF32 off, asserted below).
+
+Tolerance (north_star: 1e-3 relative, fp32): relationship probabilities rtol 1e-3 + atol 1e-5 (the reference's own
+op_utils.py:281); object logits - they cross zero - rtol 1e-3 + 1e-4 x max|reference| on the BF16x3 tensor-core engine.
+
+Shapes: config #2 at 16 scenes (the benchmark line) and at north_star's 64 scenes; config #4's per-GPU shard (32 scenes);
+config #5 (256 3RScan-shaped scenes of 2..9 objects, fully connected, mmgnet.json verbatim); config #3's shape (64 scenes x 40
+objects x 512 points, dense graphs, sum_E 99,840) through the PointNet encoder and the SGFN stack GraphEdgeAttenNetworkLayers,
+which is where the reference fits (its Mmgnet needs a 319 GB score tensor there); and the reference's own Mmgnet
+class wrapped by accelerate_reference_model (the "drops into main.py" path) when baseline/_ref travelled with the repo.
+"""
+import os
+
+import pytest
+import torch
+
+import cases
+import vlsat_b200 as V
+from conftest import FEATURE_ATOL_SCALE, ROOT, assert_close
+from oracle import vlsat_oracle as O
+from vlsat_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _model():
+    m = V.Mmgnet({"MODEL": V.DEFAULT_MODEL_CONFIG}, 160, 26)
+    synth.load_seeded(m, 0)
+    return m.to(DEV).eval()
+
+
+def _check_outputs(got, want, what):
+    for i in (0, 1):
+        assert_close(got[i], want[i], f"{what}: object logits {i}", atol_scale=FEATURE_ATOL_SCALE)
+    for i in (2, 3):
+        assert_close(got[i], want[i], f"{what}: relationship probabilities {i}")
+
+
+@pytest.mark.parametrize("cfg,scenes", [("cfg2", 16), ("cfg2", 64), ("cfg4_per_gpu", 32), ("cfg5", 256)])
+def test_all_outputs_match_the_oracle_at_full_size(cfg, scenes):
+    assert not torch.backends.cuda.matmul.allow_tf32, "the fp32 yardstick must not run its matmuls in TF32"
+    model = _model()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = synth.make_config_batch(cfg, seed=11) if cfg == "cfg5" else synth.make_config_batch(cfg, seed=11, num_scenes=scenes)
+    assert batch.num_scenes == scenes
+    batch = batch.to(DEV)
+    with torch.no_grad():
+        got = [t.clone() for t in model(*batch.forward_args(), istrain=False)]
+        try:
+            want = O.mmgnet_forward(sd, *batch.forward_args(), istrain=False)
+        except torch.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            pytest.skip("the reference restatement does not fit this GPU at this batch")
+    _check_outputs(got, want, f"{cfg} x {scenes} scenes")
+    # the CUDA-graph replay the benchmark times returns the same tensors
+    graphed = V.GraphedForward(model)
+    with torch.no_grad():
+        rep = graphed(*batch.forward_args())
+    for i, (a, b) in enumerate(zip(rep, got)):
+        assert_close(a, b, f"{cfg}: graph replay output {i}", rtol=1e-4, atol=1e-5)
+
+
+def test_config3_shape_through_pointnet_and_the_sgfn_stack():
+    """64 scenes x 40 objects x 512 points, fully connected (sum_N 2,560, sum_E 99,840): PointNetfeat and
+    GraphEdgeAttenNetworkLayers (network_GNN.py:197-284) against the oracle; CSR / arg bookkeeping is covered bit-exactly
+    by tests/test_parity_gpu.py, here the numbers at the size BASELINE names."""
+    batch = synth.make_config_batch("cfg3", seed=12)
+    n, e = batch.obj_points.shape[0], batch.edge_indices.shape[1]
+    assert (n, e) == (2560, 99840)
+    enc = V.PointNetfeat(global_feat=True, batch_norm=False, point_size=3, input_transform=False, feature_transform=False, out_size=768)
+    esd = cases.seeded_state(enc, 21)
+    enc.load_state_dict(esd)
+    enc = enc.to(DEV).eval()
+    with torch.no_grad():
+        got = enc(batch.obj_points.to(DEV))
+        want = O.pointnet_feat({k: v.to(DEV) for k, v in esd.items()}, "", batch.obj_points.to(DEV))
+    assert_close(got, want, "PointNetfeat at config #3", atol_scale=FEATURE_ATOL_SCALE)
+
+    net = V.GraphEdgeAttenNetworkLayers(**{k: v for k, v in cases.GNN_CASE.items()})
+    sd = cases.seeded_state(net, 22)
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    g = torch.Generator().manual_seed(13)
+    node, edge = torch.randn(n, 512, generator=g).to(DEV), torch.randn(e, 256, generator=g).to(DEV)
+    centres = batch.descriptor[:, :3].to(DEV)
+    ei, bids = batch.edge_indices.to(DEV), batch.batch_ids.to(DEV)
+    with torch.no_grad():
+        gn, ge, gp = net(node, edge, ei, centres, bids)
+        wn, we, wp = O.gnn_layers_forward({k: v.to(DEV) for k, v in sd.items()}, "", node, edge, ei, centres, bids,
+                                          cases.GNN_CASE["num_layers"], cases.GNN_CASE["num_heads"])
+    assert_close(gn, wn, "SGFN stack node features at config #3", atol_scale=FEATURE_ATOL_SCALE)
+    assert_close(ge, we, "SGFN stack edge features at config #3", atol_scale=FEATURE_ATOL_SCALE)
+    for i, (a, b) in enumerate(zip(gp, wp)):
+        assert_close(a.to(DEV), b, f"SGFN stack attention probabilities, layer {i}")
+
+
+def test_wrapped_reference_instance_runs_process_val_style_forward():
+    """accelerate_reference_model on an instance of the reference's OWN Mmgnet class (imported from the staged, unmodified
+    files under baseline/_ref): the reference forward first, then the same object with its forward on the vlsat kernels -
+    same parameters (shared), same outputs, in eval and in training-mode signature (istrain=True returns 8 tensors)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref_dir, "src", "model", "SGFN_MMG", "model.py")):
+        pytest.skip("baseline/_ref was not staged (oracle/stage_reference.py runs in the build container)")
+    os.environ["VLSAT_REFERENCE_ROOT"] = ref_dir
+    from oracle import ref_shims
+    net, _ = ref_shims.build_reference_mmgnet(0)
+    ours = V.Mmgnet({"MODEL": V.DEFAULT_MODEL_CONFIG}, 160, 26)
+    synth.load_seeded(ours, 0)
+    net.load_state_dict(ours.state_dict(), strict=True)
+    net = net.to(DEV).eval()
+    batch = synth.make_config_batch("cfg2", seed=14, num_scenes=4).to(DEV)
+    with torch.no_grad():
+        want_eval = [t.clone() for t in net(*batch.forward_args(), istrain=False)]
+        want_train = [t.clone() for t in net(*batch.forward_args(), istrain=True)]
+    n_params = sum(1 for _ in net.parameters())
+    keys = list(net.state_dict().keys())
+    V.accelerate_reference_model(net)
+    assert sum(1 for _ in net.parameters()) == n_params and list(net.state_dict().keys()) == keys
+    with torch.no_grad():
+        got_eval = net(*batch.forward_args(), istrain=False)
+        got_train = net(*batch.forward_args(), istrain=True)
+    _check_outputs(got_eval, want_eval, "wrapped reference, eval")
+    assert len(got_train) == len(want_train) == 8
+    _check_outputs(got_train, want_train, "wrapped reference, istrain=True")
+    for i in (4, 5, 6):
+        assert_close(got_train[i], want_train[i], f"wrapped reference train output {i}", atol_scale=FEATURE_ATOL_SCALE)
+    # the reference's backward() (SGFN_MMG/model.py:483-488) drives the kernels' gradients through its own optimiser
+    net.train()
+    before = net.mmg.gcn_3ds[0].prop[0].weight.detach().clone()
+    outs = net(*batch.forward_args(), istrain=True)
+    loss = sum(o.float().square().mean() for o in outs[:7])
+    net.backward(loss)
+    assert torch.isfinite(loss) and not torch.equal(before, net.mmg.gcn_3ds[0].prop[0].weight.detach())
