@@ -114,9 +114,16 @@ def test_wrapped_reference_instance_runs_process_val_style_forward():
     net.load_state_dict(ours.state_dict(), strict=True)
     net = net.to(DEV).eval()
     batch = synth.make_config_batch("cfg2", seed=14, num_scenes=4).to(DEV)
-    with torch.no_grad():
-        want_eval = [t.clone() for t in net(*batch.forward_args(), istrain=False)]
-        want_train = [t.clone() for t in net(*batch.forward_args(), istrain=True)]
+    # the reference's Conv1d layers go to cuDNN, which defaults to TF32 on this GPU (10-bit mantissa): the fp32 reference
+    # north_star names is the one with that switched off (its CPU path, which the golden fixtures pin, is fp32 throughout)
+    tf32_was = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want_eval = [t.clone() for t in net(*batch.forward_args(), istrain=False)]
+            want_train = [t.clone() for t in net(*batch.forward_args(), istrain=True)]
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32_was
     n_params = sum(1 for _ in net.parameters())
     keys = list(net.state_dict().keys())
     V.accelerate_reference_model(net)
