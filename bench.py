@@ -149,8 +149,9 @@ def describe_edges(kw) -> str:
     return f"{kw['edges_per_scene']} edges/scene" if kw["edges_per_scene"] is not None else "fully connected"
 
 
-def workload_text(name: str, kw, scenes: int, metric: str) -> str:
-    what = "fp32 forward (eval)" if metric == "fwd" else "fp32 training step (forward, losses, backward, AdamW)"
+def workload_text(name: str, kw, scenes: int, metric: str, dtype: str = "f32") -> str:
+    what = "forward (eval)" if metric == "fwd" else "training step (forward, losses, backward, AdamW)"
+    what = ("fp32 " if dtype == "f32" else "single-pass bf16 ") + what
     return (f"{name}: {scenes} scenes/GPU x {describe_objects(kw)} x {kw['points_per_object']} pts, {describe_edges(kw)}, "
             f"mmgnet.json model (L=2, H=8), {what}")
 
@@ -247,6 +248,19 @@ def time_reference(workload: str, metric: str, steps: int, warmup: int, budget_s
         b = synth.make_batch(seed=100, **kw_)
         t = make_targets(b, gen, ref.device) if train else None
         return b.to(ref.device), t
+    # the reference materialises [8, sum_E, sum_E] fp32 score tensors (attention.py:55-66), about three alive at once (more
+    # with autograd): bound the sample BEFORE the first run so that it fits the host (8 GB) / the GPU (100 GB)
+    per_scene_edges = kw["edges_per_scene"]
+    if per_scene_edges is None:
+        o = kw["objects_per_scene"]
+        per_scene_edges = max(o) * (max(o) - 1) if not isinstance(o, int) else o * (o - 1)
+    limit = (8e9 if ref.device.type == "cpu" else 100e9) / (96.0 * (3.0 if train else 1.0))
+    while scenes > 1 and (scenes * per_scene_edges) ** 2 > limit:
+        scenes = max(1, scenes // 2)
+    if scenes != kw["num_scenes"]:
+        kw["num_scenes"] = scenes
+        if not isinstance(kw["objects_per_scene"], int):
+            kw["objects_per_scene"] = list(kw["objects_per_scene"])[:scenes]
     batch, tg = make(kw)
     run = (lambda: ref.train_step(batch, tg)) if train else (lambda: ref.forward(batch))
     sync = torch.cuda.synchronize if ref.device.type == "cuda" else (lambda: None)
@@ -338,6 +352,8 @@ def run_b200(args):
     peaks = load_peaks()
     kw = workload_kwargs(args.workload)
     scenes = kw["num_scenes"]
+    if args.dtype == "bf16":
+        ops.set_precision("bf16")
     model = build_model(dev)
     n_batches = 4
     host = [synth.make_batch(seed=1 + rank * 100 + i, **kw).pin() for i in range(n_batches)]
@@ -408,7 +424,8 @@ def run_b200(args):
     fwd_e2e_line = {"value": round(fwd_e2e, 2), "unit": UNIT, "h2d_bytes_per_step": host[0].nbytes(), "d2h_bytes_per_step": d2h_bytes}
 
     # ---- the reference's PyTorch forward on this GPU (north_star's ">= 10x" denominator); rank 0, N = 1 only
-    yard = reference_gpu_yardstick(model, graphed, dev) if (rank == 0 and world == 1 and not args.no_ref_gpu) else {}
+    yard = reference_gpu_yardstick(model, graphed, dev) if (rank == 0 and world == 1 and not args.no_ref_gpu and args.workload == "cfg2"
+                                                            and args.dtype == "f32") else {}
 
     # ================= training: forward + backward, then the full step =================
     fwd_bwd = train_line = None
@@ -579,7 +596,8 @@ def run_b200(args):
         dom = next(iter(kernels))
         roofline = dict(kernel=dom, **{k: kernels[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")},
                         traffic=load_traffic(dom), peak_source=peaks["source"],
-                        note="tensor-bound kernels compute in BF16x3 (three bf16 MMAs per product for fp32 parity): 0.33 is the ceiling of frac")
+                        note=("tensor-bound kernels compute in BF16x3 (three bf16 MMAs per product for fp32 parity): 0.33 is the ceiling of frac"
+                              if args.dtype == "f32" else "single-pass bf16 MMAs: frac is against the full bf16 peak"))
         # the other kernels the spec names, as scalars next to the dominant one (the driver's records keep `roofline` whole)
         short = {"vlsat_gat_edge_tc_fwd": "gat", "vlsat_gat_edge_fwd": "gat", "vlsat_linear_fwd": "linear", "vlsat_flash_attn_bf16x3_fwd": "flash",
                  "vlsat_pointnet_tc_fwd": "pointnet", "vlsat_flash_attn_bf16x3_bwd": "flash_bwd", "vlsat_gemm_pairs": "gemm_bwd"}
@@ -611,12 +629,14 @@ def run_b200(args):
     headline_train = args.metric == "train_step" and train_line is not None and "error" not in train_line
     if args.metric == "train_step" and not headline_train:
         raise SystemExit(f"train_step leg failed: {train_line}")
-    config = {"workload": workload_text(args.workload, kw, scenes, args.metric),
+    config = {"workload": workload_text(args.workload, kw, scenes, args.metric, args.dtype),
               "global_scenes": world * scenes,
               "parallelism": f"scene-sharded x{world}, " + ("NCCL all-reduce (mean) of the gradients, none in the forward" if headline_train else "no data-path collective"),
               "l2": "flushed between timed steps (256 MB write)", "gemm_engine": ops.gemm_engine(),
               "launch": "eager C-ABI launches" if args.eager else "CUDA graph replay of the C-ABI launches",
-              "tolerance": "parity tests: rtol 1e-3 + atol 1e-5 on probabilities; object logits (cross zero) rtol 1e-3 + 1e-4 x max|ref| on the BF16x3 engine",
+              "tolerance": ("parity tests: rtol 1e-3 + atol 1e-5 on probabilities; object logits (cross zero) rtol 1e-3 + 1e-4 x max|ref| on the BF16x3 engine"
+                            if args.dtype == "f32" else
+                            "single-pass bf16 vs the fp32 reference (tests/test_bf16_mode_gpu.py): probabilities |err| <= 2.5e-2, object logits |err| <= 3e-2 x max|ref|"),
               "fwd_ms": round(fwd_ms, 4), "fwd_scenes_per_s": round(fwd_value, 2), "fwd_e2e_scenes_per_s": fwd_e2e_line["value"]}
     config.update(train_scalars)
     config.update(yard)
@@ -626,12 +646,12 @@ def run_b200(args):
     if headline_train:
         line = {"metric": METRICS["train_step"], "value": train_line["value"], "unit": UNIT, "n_gpus": world, "steps": n_train,
                 "warmup": args.warmup, "ms_per_step": train_line["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "e2e": train_e2e_line,
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": config, "e2e": train_e2e_line,
                 "gpu_launches": train_launches}
     else:
         line = {"metric": METRICS["fwd"], "value": round(fwd_value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(fwd_ms, 4), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "e2e": fwd_e2e_line,
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": config, "e2e": fwd_e2e_line,
                 "gpu_launches": fwd_launches}
     line.update({"clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "fwd_bwd": fwd_bwd, "train_step": train_line})
     emit(line)
@@ -674,6 +694,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--metric", default="fwd", choices=list(METRICS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"], help="f32 = BF16x3 (fp32 parity); bf16 = single-pass bf16 MMAs (BASELINE configs #3 / #4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training legs")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-this-GPU yardstick")

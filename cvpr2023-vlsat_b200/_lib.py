@@ -56,6 +56,8 @@ SIGNATURES = {
     "vlsat_error_string": [i32],
     "vlsat_gemm_engine": [],
     "vlsat_launch_count": [],
+    "vlsat_set_precision": [i32],
+    "vlsat_get_precision": [],
     "vlsat_pointnet_fwd": [vp, i64, i32, i64, vp, vp, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp],
     "vlsat_pointnet_tc_fwd": [vp, i64, i32, i64, vp, vp, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp],
     "vlsat_edge_descriptor_fwd": [vp, i64, vp, i64, vp, vp],

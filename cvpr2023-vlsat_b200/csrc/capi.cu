@@ -6,6 +6,10 @@
 
 namespace vlsat {
 long long g_launch_count = 0;
+// Arithmetic of the tensor-core kernels: 0 = BF16x3 (three bf16 MMAs per product: fp32 parity, the default),
+// 1 = single-pass bf16 (one MMA per product on the hi halves: BASELINE configs #3 / #4, looser stated tolerance).
+int g_precision = [] { const char* e = getenv("VLSAT_PRECISION"); return (e && (e[0] == 'b' || e[0] == '1')) ? 1 : 0; }();
+int tc_passes() { return g_precision == 1 ? 1 : 3; }
 bool pdl_enabled() {
     static int on = -1;
     if (on < 0) { const char* e = getenv("VLSAT_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
@@ -51,9 +55,19 @@ extern "C" const char* vlsat_error_string(int status) {
     }
 }
 
-extern "C" const char* vlsat_gemm_engine(void) { return "tcgen05-bf16x3 (tcgen05-3xtf32 / ffma-fp32 for shapes bf16 pairs cannot address)"; }
+extern "C" const char* vlsat_gemm_engine(void) {
+    return g_precision == 1 ? "tcgen05-bf16 single pass (one kind::f16 MMA per product on the hi halves of the operand pairs)"
+                            : "tcgen05-bf16x3 (tcgen05-3xtf32 / ffma-fp32 for shapes bf16 pairs cannot address)";
+}
 
 extern "C" int64_t vlsat_launch_count(void) { return g_launch_count; }
+
+extern "C" int vlsat_set_precision(int mode) {
+    if (mode != VLSAT_PRECISION_FP32 && mode != VLSAT_PRECISION_BF16) return VLSAT_ERR_INVALID_ARG;
+    g_precision = mode;
+    return VLSAT_OK;
+}
+extern "C" int vlsat_get_precision(void) { return g_precision; }
 
 extern "C" size_t vlsat_linear_workspace_bytes(int64_t M, int64_t N, int64_t K, int need_x_split, int need_w_split) {
     return linear_tc_workspace_bytes(M, N, K, need_x_split != 0, need_w_split != 0);

@@ -15,6 +15,7 @@ inline int finish_launch(int n_kernels = 1) {
 }
 
 constexpr int kNumSMs = 148;   // B200
+int tc_passes();               // 3 = BF16x3 (fp32 parity), 1 = single-pass bf16 (vlsat_set_precision, csrc/capi.cu)
 
 // Programmatic dependent launch. Every kernel of the forward path is launched with the programmatic-stream-serialisation
 // attribute and starts with pdl_launch_dependents() (the next kernel may be scheduled as soon as all CTAs of this one have

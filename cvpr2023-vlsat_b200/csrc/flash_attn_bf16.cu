@@ -105,6 +105,7 @@ struct FlashPartial {
 // One CTA = 256 queries (two 128-row Q tiles, one per softmax warpgroup) of one head over the KV tiles
 // [tile_begin, tile_end) of split blockIdx.z: every K / V tile fetched from L2 serves both Q tiles, which halves
 // the L2 -> SM traffic that bounds this kernel.
+template <int PASSES>       // 3 = BF16x3 (lo*hi + hi*lo + hi*hi), 1 = the hi halves alone (single-pass bf16 mode)
 __global__ void __launch_bounds__(FB_THREADS, 1)
 flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __restrict__ q_lo, int64_t ldq,
                        const __grid_constant__ CUtensorMap tm_khi, const __grid_constant__ CUtensorMap tm_klo,
@@ -158,9 +159,9 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
             mbar_wait(&k_empty[s], ((i / FB_STAGES) & 1) ^ 1);
             if (elect_one()) {
                 uint8_t* st = k_smem + s * FB_K_STAGE;
-                mbar_arrive_expect_tx(&k_full[s], FB_K_STAGE);
+                mbar_arrive_expect_tx(&k_full[s], PASSES == 3 ? FB_K_STAGE : FB_K_STAGE / 2);
                 tma_load_2d(st, &tm_khi, &k_full[s], head * FB_DK, (tile_begin + i) * FB_BKV);          // rows = keys
-                tma_load_2d(st + FB_BKV * 128, &tm_klo, &k_full[s], head * FB_DK, (tile_begin + i) * FB_BKV);
+                if (PASSES == 3) tma_load_2d(st + FB_BKV * 128, &tm_klo, &k_full[s], head * FB_DK, (tile_begin + i) * FB_BKV);
             }
             __syncwarp();
         }
@@ -172,9 +173,9 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
             mbar_wait(&v_empty[s], ((i / FB_STAGES) & 1) ^ 1);
             if (elect_one()) {
                 uint8_t* st = v_smem + s * FB_V_STAGE;
-                mbar_arrive_expect_tx(&v_full[s], FB_V_STAGE);
+                mbar_arrive_expect_tx(&v_full[s], PASSES == 3 ? FB_V_STAGE : FB_V_STAGE / 2);
                 tma_load_2d(st, &tm_vhi, &v_full[s], (tile_begin + i) * FB_BKV, head * FB_DK);          // rows = dims, cols = keys
-                tma_load_2d(st + FB_DK * 128, &tm_vlo, &v_full[s], (tile_begin + i) * FB_BKV, head * FB_DK);
+                if (PASSES == 3) tma_load_2d(st + FB_DK * 128, &tm_vlo, &v_full[s], (tile_begin + i) * FB_BKV, head * FB_DK);
             }
             __syncwarp();
         }
@@ -192,9 +193,11 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
                 const uint32_t ts = tmem_base + 64 * (2 * g + s);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {                 // 16 dims per MMA = 8 packed columns
-                    mma_ts_bf16(ts, tq + 32 + 8 * kk, dk + 2 * kk, idesc, kk > 0);                                 // Q_lo K_hi
-                    mma_ts_bf16(ts, tq + 8 * kk, dk + ((FB_BKV * 128) >> 4) + 2 * kk, idesc, 1);                   // Q_hi K_lo
-                    mma_ts_bf16(ts, tq + 8 * kk, dk + 2 * kk, idesc, 1);                                           // Q_hi K_hi
+                    if (PASSES == 3) {
+                        mma_ts_bf16(ts, tq + 32 + 8 * kk, dk + 2 * kk, idesc, kk > 0);                             // Q_lo K_hi
+                        mma_ts_bf16(ts, tq + 8 * kk, dk + ((FB_BKV * 128) >> 4) + 2 * kk, idesc, 1);               // Q_hi K_lo
+                    }
+                    mma_ts_bf16(ts, tq + 8 * kk, dk + 2 * kk, idesc, PASSES == 3 ? 1u : (kk > 0 ? 1u : 0u));       // Q_hi K_hi
                 }
                 tc_commit(&s_full[2 * g + s]);
                 if (g == 1) tc_commit(&k_empty[ks]);
@@ -216,9 +219,11 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
                     const uint32_t tpv = tmem_base + 256 + 64 * g;
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {             // 16 keys per MMA = 8 packed columns
-                        mma_ts_bf16(tpv, tp + 32 + 8 * kk, dv + 2 * kk, idesc, (kk > 0) || (i > 0));                  // P_lo V_hi
-                        mma_ts_bf16(tpv, tp + 8 * kk, dv + ((FB_DK * 128) >> 4) + 2 * kk, idesc, 1);                   // P_hi V_lo
-                        mma_ts_bf16(tpv, tp + 8 * kk, dv + 2 * kk, idesc, 1);                                          // P_hi V_hi
+                        if (PASSES == 3) {
+                            mma_ts_bf16(tpv, tp + 32 + 8 * kk, dv + 2 * kk, idesc, (kk > 0) || (i > 0));              // P_lo V_hi
+                            mma_ts_bf16(tpv, tp + 8 * kk, dv + ((FB_DK * 128) >> 4) + 2 * kk, idesc, 1);               // P_hi V_lo
+                        }
+                        mma_ts_bf16(tpv, tp + 8 * kk, dv + 2 * kk, idesc, PASSES == 3 ? 1u : ((kk > 0 || i > 0) ? 1u : 0u));   // P_hi V_hi
                     }
                     tc_commit(&pv_full[g]);
                     if (g == 1) tc_commit(&v_empty[vs]);
@@ -301,11 +306,15 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
                 // summed l, two orders inside the parity budget.
                 const uint32_t ua = __float_as_uint(pa), ub = __float_as_uint(pb);
                 const float la = pa - __uint_as_float(ua & 0xffff0000u), lb = pb - __uint_as_float(ub & 0xffff0000u);
-                ph[c] = __byte_perm(ua, ub, 0x7632);             // {pb.hi16, pa.hi16}: low half = even key
-                pl[c] = __byte_perm(__float_as_uint(la), __float_as_uint(lb), 0x7632);
+                if (PASSES == 3) {
+                    ph[c] = __byte_perm(ua, ub, 0x7632);         // {pb.hi16, pa.hi16}: low half = even key
+                    pl[c] = __byte_perm(__float_as_uint(la), __float_as_uint(lb), 0x7632);
+                } else {
+                    ph[c] = fb_pack_bf16(pa, pb);                // single pass: round to nearest (a truncated hi alone is biased by 2^-9)
+                }
             }
             tmem_st_16(t_s + lane_off + 16 * kh, ph);
-            tmem_st_16(t_s + lane_off + 32 + 16 * kh, pl);
+            if (PASSES == 3) tmem_st_16(t_s + lane_off + 32 + 16 * kh, pl);
             tmem_st_wait();
             if (i > 0) {
                 // P.V(i-1) was issued a whole tile ago: this wait is normally free. It orders the (rare) rescale of O_g
@@ -451,11 +460,17 @@ int flash_attn_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq, con
     const int n_tiles = (int)ceil_div(nk, FB_BKV);
     const int tiles_per_split = (int)ceil_div(n_tiles, splits);
     const size_t smem = FB_STAGES * FB_K_STAGE + FB_STAGES * FB_V_STAGE + 1024 + 256 + 2 * 2 * 2 * 128 * 4;
-    cudaFuncSetAttribute(flash_attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_bf16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((unsigned)ceil_div(nq, 2 * FB_BQ), (unsigned)n_heads, (unsigned)splits);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)dk);
-    launch_k(flash_attn_bf16_kernel, grid, dim3(FB_THREADS), smem, st, q_hi, q_lo, ldq, tk, tkl, tv, tvl, out, ldo, lse, part, (int)nq, (int)nk,
-                                                           n_heads, tiles_per_split, scale_log2e);
+    if (tc_passes() == 1) {
+        cudaFuncSetAttribute(flash_attn_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        launch_k(flash_attn_bf16_kernel<1>, grid, dim3(FB_THREADS), smem, st, q_hi, q_lo, ldq, tk, tkl, tv, tvl, out, ldo, lse, part, (int)nq, (int)nk,
+                 n_heads, tiles_per_split, scale_log2e);
+    } else {
+        launch_k(flash_attn_bf16_kernel<3>, grid, dim3(FB_THREADS), smem, st, q_hi, q_lo, ldq, tk, tkl, tv, tvl, out, ldo, lse, part, (int)nq, (int)nk,
+                 n_heads, tiles_per_split, scale_log2e);
+    }
     int launches = 1;
     if (splits > 1) {
         const int64_t n = nq * n_heads * (FB_DK / 4);

@@ -93,7 +93,13 @@ __device__ __forceinline__ void fw_split2(float a, float b, uint32_t& hi, uint32
     lo = __byte_perm(__float_as_uint(la), __float_as_uint(lb), 0x7632);
 }
 
-template <bool KV>
+__device__ __forceinline__ uint32_t fw_pack_rn(float a, float b) {          // packed bf16x2, round to nearest even, low half = a
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+
+template <bool KV, int PASSES>      // PASSES: 3 = BF16x3, 1 = the hi halves alone (single-pass bf16 mode)
 __global__ void __launch_bounds__(FW_THREADS, 1)
 flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_constant__ CUtensorMap tm_y1l,
                       const __grid_constant__ CUtensorMap tm_y2h, const __grid_constant__ CUtensorMap tm_y2l,
@@ -162,11 +168,11 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
             }
             if (elect_one()) {
                 uint8_t* st = y_smem + s * Y_STAGE;
-                mbar_arrive_expect_tx(&y_full[s], Y_STAGE);
+                mbar_arrive_expect_tx(&y_full[s], PASSES == 3 ? Y_STAGE : Y_STAGE / 2);
                 tma_load_2d(st, &tm_y1h, &y_full[s], head * FW_DK, c0);
-                tma_load_2d(st + FW_TILE, &tm_y1l, &y_full[s], head * FW_DK, c0);
+                if (PASSES == 3) tma_load_2d(st + FW_TILE, &tm_y1l, &y_full[s], head * FW_DK, c0);
                 tma_load_2d(st + 2 * FW_TILE, &tm_y2h, &y_full[s], head * FW_DK, c0);
-                tma_load_2d(st + 3 * FW_TILE, &tm_y2l, &y_full[s], head * FW_DK, c0);
+                if (PASSES == 3) tma_load_2d(st + 3 * FW_TILE, &tm_y2l, &y_full[s], head * FW_DK, c0);
             }
             __syncwarp();
         }
@@ -178,14 +184,14 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
             mbar_wait(&z_empty[s], ((i / FW_ZST) & 1) ^ 1);
             if (elect_one()) {
                 uint8_t* st = z_smem + s * Z_STAGE;
-                mbar_arrive_expect_tx(&z_full[s], Z_STAGE);
+                mbar_arrive_expect_tx(&z_full[s], PASSES == 3 ? Z_STAGE : Z_STAGE / 2);
                 if (KV) {
                     tma_load_2d(st, &tm_z1h, &z_full[s], c0, head * FW_DK);
-                    tma_load_2d(st + FW_TILE, &tm_z1l, &z_full[s], c0, head * FW_DK);
+                    if (PASSES == 3) tma_load_2d(st + FW_TILE, &tm_z1l, &z_full[s], c0, head * FW_DK);
                     st += FW_PAIR;
                 }
                 tma_load_2d(st, &tm_z2h, &z_full[s], c0, head * FW_DK);
-                tma_load_2d(st + FW_TILE, &tm_z2l, &z_full[s], c0, head * FW_DK);
+                if (PASSES == 3) tma_load_2d(st + FW_TILE, &tm_z2l, &z_full[s], c0, head * FW_DK);
             }
             __syncwarp();
         }
@@ -197,9 +203,13 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
         const uint32_t tx1 = tmem_base + 384, tx2 = tmem_base + 448;
         // three MMAs per 16-wide reduction step: A_lo B_hi + A_hi B_lo + A_hi B_hi
         auto mma3 = [&](uint32_t td, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint32_t acc) {
-            fw_mma_ts(td, a_lo, b_hi, idesc, acc);
-            fw_mma_ts(td, a_hi, b_hi + LO, idesc, 1);
-            fw_mma_ts(td, a_hi, b_hi, idesc, 1);
+            if (PASSES == 3) {
+                fw_mma_ts(td, a_lo, b_hi, idesc, acc);
+                fw_mma_ts(td, a_hi, b_hi + LO, idesc, 1);
+                fw_mma_ts(td, a_hi, b_hi, idesc, 1);
+            } else {
+                fw_mma_ts(td, a_hi, b_hi, idesc, acc);
+            }
         };
         auto issue_scores = [&](int i) {
             const int b = i & 1, ys = i % FW_YST;
@@ -314,14 +324,19 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
                     if (ragged && c0 + j >= a.n_stream) p[u] = 0.f;
                     g[u] = p[u] * (__uint_as_float(d[j]) - e4[u]);
                 }
-                if (KV) { fw_split2(p[0], p[1], ph[2 * c4], pl[2 * c4]); fw_split2(p[2], p[3], ph[2 * c4 + 1], pl[2 * c4 + 1]); }
-                fw_split2(g[0], g[1], dh[2 * c4], dl[2 * c4]);
-                fw_split2(g[2], g[3], dh[2 * c4 + 1], dl[2 * c4 + 1]);
+                if (PASSES == 3) {
+                    if (KV) { fw_split2(p[0], p[1], ph[2 * c4], pl[2 * c4]); fw_split2(p[2], p[3], ph[2 * c4 + 1], pl[2 * c4 + 1]); }
+                    fw_split2(g[0], g[1], dh[2 * c4], dl[2 * c4]);
+                    fw_split2(g[2], g[3], dh[2 * c4 + 1], dl[2 * c4 + 1]);
+                } else {                                         // single pass: round to nearest (a truncated hi alone is biased)
+                    if (KV) { ph[2 * c4] = fw_pack_rn(p[0], p[1]); ph[2 * c4 + 1] = fw_pack_rn(p[2], p[3]); }
+                    dh[2 * c4] = fw_pack_rn(g[0], g[1]); dh[2 * c4 + 1] = fw_pack_rn(g[2], g[3]);
+                }
             }
             // in place: this thread's 32 fp32 columns become 16 hi words + 16 lo words of the same 32 streamed elements
-            if (KV) { fw_tmem_st_16(t1, ph); fw_tmem_st_16(t1 + 16, pl); }
+            if (KV) { fw_tmem_st_16(t1, ph); if (PASSES == 3) fw_tmem_st_16(t1 + 16, pl); }
             fw_tmem_st_16(t2, dh);
-            fw_tmem_st_16(t2 + 16, dl);
+            if (PASSES == 3) fw_tmem_st_16(t2 + 16, dl);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&p_ready[b]);
@@ -542,9 +557,14 @@ int flash_attn_bwd_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq,
             a.out1 = dv; a.out2 = dk; a.ldo = lddk; a.split_stride = 0;
         }
         const size_t smem = smem_bytes(true);
-        cudaFuncSetAttribute(flash_attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid((unsigned)ceil_div(nk, FW_ROWS), (unsigned)n_heads, (unsigned)splits);
-        launch_k(flash_attn_bwd_kernel<true>, grid, dim3(FW_THREADS), smem, st, tq[0], tq[1], tdo[0], tdo[1], tdot[0], tdot[1], tqt[0], tqt[1], a);
+        if (tc_passes() == 1) {
+            cudaFuncSetAttribute(flash_attn_bwd_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            launch_k(flash_attn_bwd_kernel<true, 1>, grid, dim3(FW_THREADS), smem, st, tq[0], tq[1], tdo[0], tdo[1], tdot[0], tdot[1], tqt[0], tqt[1], a);
+        } else {
+            cudaFuncSetAttribute(flash_attn_bwd_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            launch_k(flash_attn_bwd_kernel<true, 3>, grid, dim3(FW_THREADS), smem, st, tq[0], tq[1], tdo[0], tdo[1], tdot[0], tdot[1], tqt[0], tqt[1], a);
+        }
         ++launches;
         if (splits > 1) {
             const int64_t n4 = nk * (int64_t)(D / 4);
@@ -566,9 +586,14 @@ int flash_attn_bwd_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq,
         if (splits > 1) { a.out2 = (float*)workspace; a.ldo = (int64_t)D; a.split_stride = (int64_t)nq * (int64_t)D; }
         else { a.out2 = dq; a.ldo = lddq; a.split_stride = 0; }
         const size_t smem = smem_bytes(false);
-        cudaFuncSetAttribute(flash_attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid((unsigned)ceil_div(nq, FW_ROWS), (unsigned)n_heads, (unsigned)splits);
-        launch_k(flash_attn_bwd_kernel<false>, grid, dim3(FW_THREADS), smem, st, tk[0], tk[1], tv[0], tv[1], tkt[0], tkt[1], tkt[0], tkt[1], a);
+        if (tc_passes() == 1) {
+            cudaFuncSetAttribute(flash_attn_bwd_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            launch_k(flash_attn_bwd_kernel<false, 1>, grid, dim3(FW_THREADS), smem, st, tk[0], tk[1], tv[0], tv[1], tkt[0], tkt[1], tkt[0], tkt[1], a);
+        } else {
+            cudaFuncSetAttribute(flash_attn_bwd_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            launch_k(flash_attn_bwd_kernel<false, 3>, grid, dim3(FW_THREADS), smem, st, tk[0], tk[1], tv[0], tv[1], tkt[0], tkt[1], tkt[0], tkt[1], a);
+        }
         ++launches;
         if (splits > 1) {
             const int64_t n4 = nq * (int64_t)(D / 4);

@@ -85,7 +85,18 @@ __device__ __forceinline__ void mma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, ui
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <int DO, int GT_WG>      // d_o (channels per head of the attention output): 32 or 64; epilogue warpgroups
+__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+// d_o (channels per head of the attention output): 32 or 64; epilogue warpgroups; PASSES: 3 = BF16x3, 1 = the hi halves
+// alone (single-pass bf16 mode: K'_lo, C1_lo, C2_lo are neither loaded nor multiplied, the hidden layer keeps its hi words)
+template <int DO, int GT_WG, int PASSES>
 __global__ void __launch_bounds__(64 + 128 * GT_WG, 1)
 gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_constant__ CUtensorMap tm_klo,
                    const __grid_constant__ CUtensorMap tm_c1hi, const __grid_constant__ CUtensorMap tm_c1lo,
@@ -141,12 +152,12 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
 
     if (warp == 0) {
         if (elect_one()) {
-            mbar_arrive_expect_tx(w_full, 2 * c1_box + 2 * hc * c2_box);
+            mbar_arrive_expect_tx(w_full, (PASSES == 3 ? 2 : 1) * (c1_box + hc * c2_box));
             tma_load_2d(c1hi_s, &tm_c1hi, w_full, 0, 0);
-            tma_load_2d(c1lo_s, &tm_c1lo, w_full, 0, 0);
+            if (PASSES == 3) tma_load_2d(c1lo_s, &tm_c1lo, w_full, 0, 0);
             for (int b = 0; b < hc; ++b) {
                 tma_load_2d(c2hi_s + b * c2_box, &tm_c2hi, w_full, b * 64, 0);
-                tma_load_2d(c2lo_s + b * c2_box, &tm_c2lo, w_full, b * 64, 0);
+                if (PASSES == 3) tma_load_2d(c2lo_s + b * c2_box, &tm_c2lo, w_full, b * 64, 0);
             }
         }
         __syncwarp();
@@ -155,9 +166,9 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
             const int s = it % GT_STAGES;
             mbar_wait(&k_empty[s], ((it / GT_STAGES) & 1) ^ 1);
             if (elect_one()) {
-                mbar_arrive_expect_tx(&k_full[s], GT_K_TILE);
+                mbar_arrive_expect_tx(&k_full[s], PASSES == 3 ? GT_K_TILE : GT_K_TILE / 2);
                 tma_load_2d(k_s + s * GT_K_TILE, &tm_khi, &k_full[s], 0, t * GT_ROWS);
-                tma_load_2d(k_s + s * GT_K_TILE + GT_ROWS * 128, &tm_klo, &k_full[s], 0, t * GT_ROWS);
+                if (PASSES == 3) tma_load_2d(k_s + s * GT_K_TILE + GT_ROWS * 128, &tm_klo, &k_full[s], 0, t * GT_ROWS);
             }
             __syncwarp();
         }
@@ -176,9 +187,11 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
                 const uint32_t t_acc1 = tmem_base + b * buf_cols;
 #pragma unroll
                 for (int kk = 0; kk < GT_DE / 16; ++kk) {       // 16 channels (32 bytes) per MMA
-                    mma_ss<Kind::BF16>(t_acc1, d_klo + 2 * kk, d_c1hi + 2 * kk, idesc1, kk > 0);
-                    mma_ss<Kind::BF16>(t_acc1, d_khi + 2 * kk, d_c1lo + 2 * kk, idesc1, 1);
-                    mma_ss<Kind::BF16>(t_acc1, d_khi + 2 * kk, d_c1hi + 2 * kk, idesc1, 1);
+                    if (PASSES == 3) {
+                        mma_ss<Kind::BF16>(t_acc1, d_klo + 2 * kk, d_c1hi + 2 * kk, idesc1, kk > 0);
+                        mma_ss<Kind::BF16>(t_acc1, d_khi + 2 * kk, d_c1lo + 2 * kk, idesc1, 1);
+                    }
+                    mma_ss<Kind::BF16>(t_acc1, d_khi + 2 * kk, d_c1hi + 2 * kk, idesc1, PASSES == 3 ? 1u : (kk > 0 ? 1u : 0u));
                 }
                 tc_commit(&k_empty[s]);
                 tc_commit(&acc1_full[b]);
@@ -196,9 +209,11 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
                 for (int kk = 0; kk < ks2; ++kk) {              // 16 hidden units per MMA = 8 packed columns
                     const uint32_t a_hi = t_hid + 32 * (kk >> 1) + 8 * (kk & 1), a_lo = a_hi + 16;
                     const uint32_t ob = (kk >> 2) * (c2_box >> 4) + (kk & 3) * 2;
-                    mma_ts_bf16(t_acc2, a_lo, d_c2hi + ob, idesc2, kk > 0);
-                    mma_ts_bf16(t_acc2, a_hi, d_c2lo + ob, idesc2, 1);
-                    mma_ts_bf16(t_acc2, a_hi, d_c2hi + ob, idesc2, 1);
+                    if (PASSES == 3) {
+                        mma_ts_bf16(t_acc2, a_lo, d_c2hi + ob, idesc2, kk > 0);
+                        mma_ts_bf16(t_acc2, a_hi, d_c2lo + ob, idesc2, 1);
+                    }
+                    mma_ts_bf16(t_acc2, a_hi, d_c2hi + ob, idesc2, PASSES == 3 ? 1u : (kk > 0 ? 1u : 0u));
                 }
                 tc_commit(&acc2_full[b]);
             }
@@ -310,7 +325,8 @@ gat_edge_tc_kernel(const __grid_constant__ CUtensorMap tm_khi, const __grid_cons
                     split_bf16x2(h2, h3, w[2 * u + 1], w[16 + 2 * u + 1]);
                 }
                 if (c0 == 0) GT_STAMP(7);
-                tmem_st_32(t_acc1 + c0, w);
+                if (PASSES == 3) tmem_st_32(t_acc1 + c0, w);
+                else tmem_st_16(t_acc1 + c0, w);                 // hi words only (split_bf16x2 rounds hi to nearest)
             }
             float4 vv[DO / 4];                               // value row: lands while the tensor core runs MMA2
 #pragma unroll
@@ -523,7 +539,8 @@ extern "C" int vlsat_gat_edge_tc_fwd(const void* k_hi, const void* k_lo, const f
                             (size_t)gt_wg(d_o) * std::max(GT_QN * n_heads * (hid + 4), 4 * 32 * (d_o + 1)) * 4 + 256 + 1024;
         VLSAT_SUPPORT(smem <= 227 * 1024);
         const int wg = gt_wg(d_o);
-        auto kern = d_o == 64 ? gat_edge_tc_kernel<64, 2> : wg == 3 ? gat_edge_tc_kernel<32, 3> : gat_edge_tc_kernel<32, 2>;
+        auto kern = tc_passes() == 1 ? (d_o == 64 ? gat_edge_tc_kernel<64, 2, 1> : wg == 3 ? gat_edge_tc_kernel<32, 3, 1> : gat_edge_tc_kernel<32, 2, 1>)
+                                     : (d_o == 64 ? gat_edge_tc_kernel<64, 2, 3> : wg == 3 ? gat_edge_tc_kernel<32, 3, 3> : gat_edge_tc_kernel<32, 2, 3>);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         GatTcParams p;
         p.qc = qc; p.ld_qc = ld_qc; p.v = v; p.ld_v = ld_v; p.src = src_sorted; p.dst = dst_sorted; p.c2_bias = c2_bias;

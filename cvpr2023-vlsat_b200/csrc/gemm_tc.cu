@@ -431,7 +431,7 @@ int linear_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
     const auto DT = kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const int eb = kind == 1 ? 2 : 4;
     const uint32_t bk = 128 / eb;                     // elements per 128-byte K block
-    if (kind == 1 && passes != 3) return VLSAT_ERR_UNSUPPORTED;
+    if (kind == 1) passes = tc_passes();              // bf16 pairs: BF16x3, or the hi halves alone in the single-pass mode
     CUtensorMap ta, tal, tb, tbl;
     bool ok = make_tmap_2d(&ta, x_hi, DT, eb, M, K, K, bk, TC_BM) && make_tmap_2d(&tb, w_hi, DT, eb, N, K, K, bk, bn);
     if (passes == 3)
@@ -459,6 +459,7 @@ int linear_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
     a.tma_store = tma_out ? 1 : 0;
     const bool g = e.gather_a || e.gather_b, r = e.residual != nullptr;
 #define VLSAT_TC_LAUNCH(BN_, ST_, PS_, KD_, G_, R_) launch_tc<BN_, ST_, PS_, KD_, G_, R_>(ta, tal, tb, tbl, ty, tsh, tsl, a, st)
+    if (kind == 1 && passes == 1) return bn == 64 ? VLSAT_TC_LAUNCH(64, 6, 1, Kind::BF16, true, true) : VLSAT_TC_LAUNCH(128, 6, 1, Kind::BF16, true, true);
     if (kind == 1) {
         // BF16x3: the engine of the hot path gets epilogue instantiations without the unused prefetch registers
         if (bn == 64) return VLSAT_TC_LAUNCH(64, 4, 3, Kind::BF16, true, true);
@@ -537,7 +538,12 @@ int gemm_pairs_tc(int mode, const uint16_t* a_hi, const uint16_t* a_lo, int64_t 
     if (!make_tmap_2d(&ty, dst, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows_dst, N, ld_dst, 32, TC_BM)) return VLSAT_ERR_UNSUPPORTED;
     a.tma_store = 1;
     int rc;
-    if (mode == 2) rc = bn == 64 ? launch_tc<64, 4, 3, Kind::BF16, false, false, 2>(ta, tal, tb, tbl, ty, ty, ty, a, st)
+    if (tc_passes() == 1) {
+        if (mode == 2) rc = bn == 64 ? launch_tc<64, 6, 1, Kind::BF16, false, false, 2>(ta, tal, tb, tbl, ty, ty, ty, a, st)
+                                     : launch_tc<128, 6, 1, Kind::BF16, false, false, 2>(ta, tal, tb, tbl, ty, ty, ty, a, st);
+        else rc = bn == 64 ? launch_tc<64, 6, 1, Kind::BF16, false, false, 3>(ta, tal, tb, tbl, ty, ty, ty, a, st)
+                           : launch_tc<128, 6, 1, Kind::BF16, false, false, 3>(ta, tal, tb, tbl, ty, ty, ty, a, st);
+    } else if (mode == 2) rc = bn == 64 ? launch_tc<64, 4, 3, Kind::BF16, false, false, 2>(ta, tal, tb, tbl, ty, ty, ty, a, st)
                                  : launch_tc<128, 3, 3, Kind::BF16, false, false, 2>(ta, tal, tb, tbl, ty, ty, ty, a, st);
     else rc = bn == 64 ? launch_tc<64, 4, 3, Kind::BF16, false, false, 3>(ta, tal, tb, tbl, ty, ty, ty, a, st)
                        : launch_tc<128, 3, 3, Kind::BF16, false, false, 3>(ta, tal, tb, tbl, ty, ty, ty, a, st);

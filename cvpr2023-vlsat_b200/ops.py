@@ -145,6 +145,19 @@ def set_gemm_engine(name: str) -> None:
     _engine = ENGINES[name]
 
 
+PRECISIONS = {"fp32": 0, "bf16": 1}
+
+
+def set_precision(name: str) -> None:
+    """Arithmetic of the tensor-core kernels: 'fp32' (default; BF16x3, fp32 parity with the reference) or 'bf16' (one MMA
+    per product on the hi halves of the operand pairs - BASELINE configs #3 / #4; tolerance in tests/test_bf16_mode_gpu.py)."""
+    _lib.check(_lib.load().vlsat_set_precision(PRECISIONS[name]), "vlsat_set_precision")
+
+
+def precision() -> str:
+    return "bf16" if int(_lib.load().vlsat_get_precision()) == 1 else "fp32"
+
+
 def tensor_cores_enabled() -> bool:
     return _engine != ENGINES["simt"]
 

@@ -124,6 +124,17 @@ typedef struct {
     size_t workspace_bytes;   /* >= vlsat_linear_workspace_bytes(M, N, K, x_hi == NULL, w_hi == NULL)   */
 } vlsat_linear_opts;
 
+/* Process-wide arithmetic of the tensor-core kernels (projections, A9 forward / backward, A8 edge kernel):
+ *   VLSAT_PRECISION_FP32 (default): BF16x3 - every product is three bf16 MMAs on (hi, lo) operand pairs, fp32 parity
+ *                                   with the reference (north_star: 1e-3 relative);
+ *   VLSAT_PRECISION_BF16: one MMA per product on the hi halves - the "bf16" BASELINE configs #3 / #4, which have no
+ *                         reference-side counterpart (the reference has no AMP); tolerance against
+ *                         the fp32 reference stated in tests/test_bf16_mode_gpu.py. Also set by VLSAT_PRECISION=bf16. */
+#define VLSAT_PRECISION_FP32 0
+#define VLSAT_PRECISION_BF16 1
+int vlsat_set_precision(int mode);
+int vlsat_get_precision(void);
+
 int vlsat_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw,
                      float* y, int64_t ldy, int64_t M, int64_t N, int64_t K,
                      const vlsat_epilogue* epi, const vlsat_linear_opts* opts, void* stream);

@@ -1,0 +1,102 @@
+"""Single-pass bf16 mode (vlsat_set_precision(VLSAT_PRECISION_BF16); BASELINE configs #3 / #4 are "bf16"): one tcgen05 MMA
+per product on the hi halves of the operand pairs instead of BF16x3's three. The reference has no reduced-precision path
+(no AMP), so the oracle is the reference in fp32 and the tolerance is LOOSER and STATED here:
+
+    relationship probabilities (sigmoid outputs)   |err| <= 2.5e-2
+    object logits (scale ~ exp(logit_scale) = 14)   |err| <= 3e-2 * max|reference|
+    gradients (per tensor)                          ||g - g_fp32|| <= 8e-2 * ||g_fp32||  for tensors that carry gradient signal
+
+(bf16 has an 8-bit mantissa: 2^-9 relative per operand, accumulated through two message-passing layers, LayerNorms and the
+O(sum_E) softmax of cross_attn_rel.) The fp32 mode must be restored after every test: it is process-wide state.
+"""
+import pytest
+import torch
+
+import cases
+import vlsat_b200 as V
+from oracle import vlsat_oracle as O
+from vlsat_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+PROB_ATOL, LOGIT_REL_TO_MAX, GRAD_REL = 2.5e-2, 3e-2, 8e-2
+
+
+@pytest.fixture
+def bf16_mode():
+    ops.set_precision("bf16")
+    try:
+        yield
+    finally:
+        ops.set_precision("fp32")
+
+
+def _model(train=False):
+    m = V.Mmgnet({"MODEL": V.DEFAULT_MODEL_CONFIG}, 160, 26)
+    synth.load_seeded(m, 0)
+    m = m.to(DEV)
+    return m.train() if train else m.eval()
+
+
+@pytest.mark.parametrize("name", ["mmgnet_cfg1", "mmgnet_cfg2x2", "mmgnet_ragged"])
+def test_bf16_forward_against_the_fp32_reference_fixtures(name, golden, bf16_mode):
+    assert ops.precision() == "bf16" and "single pass" in ops.gemm_engine()
+    over, make = cases.MMGNET_CASES[name]
+    model = V.Mmgnet(cases.model_config(over), 160, 26)
+    model.load_state_dict(cases.seeded_state(model, cases.MMGNET_WEIGHT_SEED))
+    model = model.to(DEV).eval()
+    b = make().to(DEV)
+    with torch.no_grad():
+        ev = model(*b.forward_args(), istrain=False)
+    g = golden(name)["eval"]
+    worst = {}
+    for i in (0, 1):
+        ref = g[i]
+        worst[i] = ((ev[i].cpu() - ref).abs().max() / ref.abs().max()).item()
+        assert worst[i] <= LOGIT_REL_TO_MAX, f"{name}: object logits {i}: max|err| / max|ref| = {worst[i]:.3g}"
+    for i in (2, 3):
+        worst[i] = (ev[i].cpu() - g[i]).abs().max().item()
+        assert worst[i] <= PROB_ATOL, f"{name}: relationship probabilities {i}: max|err| = {worst[i]:.3g}"
+    print(f"[bf16 mode] {name}: logits err/max {worst[0]:.3g} {worst[1]:.3g}; probabilities abs err {worst[2]:.3g} {worst[3]:.3g}")
+
+
+def test_bf16_forward_full_config2_against_the_oracle(bf16_mode):
+    model = _model()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = synth.make_config_batch("cfg2", seed=21).to(DEV)
+    with torch.no_grad():
+        got = model(*batch.forward_args(), istrain=False)
+        want = O.mmgnet_forward(sd, *batch.forward_args(), istrain=False)
+    for i in (0, 1):
+        r = ((got[i] - want[i]).abs().max() / want[i].abs().max()).item()
+        assert r <= LOGIT_REL_TO_MAX, f"object logits {i}: {r:.3g}"
+    for i in (2, 3):
+        a = (got[i] - want[i]).abs().max().item()
+        assert a <= PROB_ATOL, f"relationship probabilities {i}: {a:.3g}"
+
+
+def test_bf16_gradients_track_the_fp32_mode():
+    """Same model, same batch, same fixed cotangents: gradients of the single-pass mode against the BF16x3 mode (which
+    tests/test_train_gpu.py pins on the reference's gradients)."""
+    b = synth.make_config_batch("cfg2", seed=22, num_scenes=2).to(DEV)
+    grads = {}
+    for mode in ("fp32", "bf16"):
+        ops.set_precision(mode)
+        try:
+            model = _model().eval()                      # eval: no dropout, running BatchNorm statistics; autograd on
+            outs = model(*b.forward_args(), istrain=True)
+            cases.scalar_loss(outs[:7], seed=7).backward()
+            grads[mode] = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+        finally:
+            ops.set_precision("fp32")
+    ref, got = grads["fp32"], grads["bf16"]
+    scale = max(float(g.abs().max()) for g in ref.values())
+    bad, n = [], 0
+    for k, r in ref.items():
+        if float(r.abs().max()) < 1e-4 * scale:      # rounding-noise tensors (e.g. key biases under a softmax)
+            continue
+        err = (got[k] - r).norm().item() / (r.norm().item() + 1e-30)
+        n += 1
+        if err > GRAD_REL:
+            bad.append(f"{k}: {err:.3g}")
+    assert n >= 100 and not bad, "\n".join(bad)
