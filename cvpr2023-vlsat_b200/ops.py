@@ -158,6 +158,10 @@ def precision() -> str:
     return "bf16" if int(_lib.load().vlsat_get_precision()) == 1 else "fp32"
 
 
+def _elem_bytes() -> float:
+    return 2.0 if precision() == "bf16" else 4.0
+
+
 def tensor_cores_enabled() -> bool:
     return _engine != ENGINES["simt"]
 
@@ -795,8 +799,9 @@ def gat_edge_tc(k_hm, qc, v_hm, src, dst, c1k_split, c2_split, c2b, n_nodes: int
                c2b.data_ptr(), n_nodes, e, n_heads, d_e, hid, d_o, xp, ldxx, prob.data_ptr() if want_prob else None,
                ws.data_ptr(), ws.numel() * 4, 1, _stream(),
                # same algorithmic work as vlsat_gat_edge_fwd, independent of the node-side folding
+               # s = 4 bytes per element in the fp32-parity mode, 2 in the single-pass bf16 mode
                work=(2.0 * e * n_heads * (hid * ((d_n or d_e) + d_e) + d_o * hid),
-                     e * (n_heads * d_e * 4.0 + 16.0) + n_nodes * (n_heads * (d_n or d_e) + 2.0 * n_heads * d_o) * 4.0))
+                     e * (n_heads * d_e * _elem_bytes() + 16.0) + n_nodes * (n_heads * (d_n or d_e) + 2.0 * n_heads * d_o) * _elem_bytes()))
     _lib.check(st, "vlsat_gat_edge_tc_fwd")
     return out, prob
 
