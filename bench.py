@@ -510,17 +510,16 @@ def run_b200(args):
             # ---- the collective alone: pack + NCCL all-reduce of this step's gradients, CUDA events, max over ranks
             if world > 1:
                 for _ in range(3):
-                    treducer.allreduce()
+                    treducer.replay()
                 barrier()
                 a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 for _ in range(10):
-                    treducer.allreduce()
+                    treducer.replay()                  # pack (one launch, 1 / N folded in) + NCCL all-reduce of the flat buffer
                 b_.record()
                 barrier()
                 train_scalars["grad_allreduce_ms"] = round(max_ranks(a.elapsed_time(b_) / 10), 4)
                 train_scalars["grad_allreduce_bytes"] = treducer.last_bytes
-                ts.step(*resident[0].forward_args(), *targets_of(resident[0]), scene_stats=stats_of(resident[0]))     # re-point the gradients at this step's
             # ---- training step end to end: batch AND targets from pinned host memory every step, loss read back
             if args.metric == "train_step":
                 for b in host:

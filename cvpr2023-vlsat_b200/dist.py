@@ -58,35 +58,50 @@ class GradientAllReducer:
         self.params = [p for p in params if p.requires_grad]
         self.chunk_elems = chunk_elems
         self.last_bytes = 0
-        self._plan = None            # (signature, flat, views, table, chunk_tensor, chunk_index, n_chunks)
+        self._plan = None
 
     def _build(self, ps, grads):
-        sig = tuple((g.data_ptr(), g.numel()) for g in grads)
-        if self._plan is not None and self._plan[0] == sig:
-            return self._plan
-        dev = grads[0].device
-        offs, total = [], 0
-        for g in grads:
-            offs.append(total)
-            total += (g.numel() + 3) // 4 * 4                      # 16-byte aligned slots
-        flat = torch.zeros((total,), device=dev, dtype=torch.float32)
-        views = [flat[o:o + g.numel()].view(g.shape) for o, g in zip(offs, grads)]
-        table = ct = ci = None
-        n_chunks = 0
-        if dev.type == "cuda":
-            from ._lib import CopyTensor
-            arr = (CopyTensor * len(grads))()
+        """(flat, views, table, chunk lists): the flat buffer and its views depend on the gradient SHAPES only (allocated once);
+        the pointer table is rebuilt when the gradients live somewhere else (eager steps allocate new gradients; a replayed
+        CUDA graph keeps them in place, so the steady state rebuilds nothing)."""
+        shapes = tuple(tuple(g.shape) for g in grads)
+        if self._plan is None or self._plan["shapes"] != shapes or self._plan["flat"].device != grads[0].device:
+            offs, total = [], 0
+            for g in grads:
+                offs.append(total)
+                total += (g.numel() + 3) // 4 * 4                  # 16-byte aligned slots
+            flat = torch.zeros((total,), device=grads[0].device, dtype=torch.float32)
+            views = [flat[o:o + g.numel()].view(g.shape) for o, g in zip(offs, grads)]
             cts, cis = [], []
-            for i, (g, v) in enumerate(zip(grads, views)):
-                arr[i].dst, arr[i].src, arr[i].n = v.data_ptr(), g.data_ptr(), g.numel()
+            for i, g in enumerate(grads):
                 nch = (g.numel() + self.chunk_elems - 1) // self.chunk_elems
                 cts += [i] * nch
                 cis += list(range(nch))
-            table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
-            ct, ci = torch.tensor(cts, dtype=torch.int32).to(dev), torch.tensor(cis, dtype=torch.int32).to(dev)
-            n_chunks = len(cts)
-        self._plan = (sig, flat, views, table, ct, ci, n_chunks)
-        return self._plan
+            dev = grads[0].device
+            self._plan = dict(shapes=shapes, flat=flat, views=views, ptrs=None, table=None, n_chunks=len(cts),
+                              ct=torch.tensor(cts, dtype=torch.int32).to(dev) if dev.type == "cuda" else None,
+                              ci=torch.tensor(cis, dtype=torch.int32).to(dev) if dev.type == "cuda" else None)
+        plan = self._plan
+        ptrs = tuple(g.data_ptr() for g in grads)
+        if plan["flat"].is_cuda and plan["ptrs"] != ptrs:
+            from ._lib import CopyTensor
+            arr = (CopyTensor * len(grads))()
+            for i, (g, v) in enumerate(zip(grads, plan["views"])):
+                arr[i].dst, arr[i].src, arr[i].n = v.data_ptr(), g.data_ptr(), g.numel()
+            plan["table"] = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(plan["flat"].device)
+            plan["ptrs"] = ptrs
+        return plan
+
+    def _pack_and_reduce(self, plan, grads, size: int) -> None:
+        flat = plan["flat"]
+        if flat.is_cuda:
+            from . import _lib, ops
+            _lib.check(ops._call("vlsat_pack_scale", plan["table"].data_ptr(), plan["ct"].data_ptr(), plan["ci"].data_ptr(), plan["n_chunks"],
+                                 self.chunk_elems, 1.0 / size, ops._stream()), "vlsat_pack_scale")
+        else:                                                      # CPU tensors: the gloo tests of the host-side logic
+            for v, g in zip(plan["views"], grads):
+                v.copy_(g).div_(size)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
 
     def allreduce(self) -> None:
         _, size = world()
@@ -95,20 +110,22 @@ class GradientAllReducer:
         self.last_bytes = sum(g.numel() * g.element_size() for g in grads)
         if size == 1 or not grads:
             return
+        if self._plan is not None and len(grads) == len(self._plan["views"]) and all(g.data_ptr() == v.data_ptr() for g, v in zip(grads, self._plan["views"])):
+            return                                                 # already this step's averaged gradients (called twice)
         for i, g in enumerate(grads):
             if g.dtype != torch.float32 or not g.is_contiguous():
                 grads[i] = ps[i].grad = g.float().contiguous()
-        _, flat, views, table, ct, ci, n_chunks = self._build(ps, grads)
-        if flat.is_cuda:
-            from . import _lib, ops
-            _lib.check(ops._call("vlsat_pack_scale", table.data_ptr(), ct.data_ptr(), ci.data_ptr(), n_chunks, self.chunk_elems,
-                                 1.0 / size, ops._stream()), "vlsat_pack_scale")
-        else:                                                      # CPU tensors: the gloo tests of the host-side logic
-            for v, g in zip(views, grads):
-                v.copy_(g).div_(size)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        for p, v in zip(ps, views):
+        plan = self._build(ps, grads)
+        self._pack_and_reduce(plan, grads, size)
+        for p, v in zip(ps, plan["views"]):
             p.grad = v
+
+    def replay(self) -> None:
+        """Pack + all-reduce once more from the gradient buffers of the last ``allreduce()`` call, without touching ``.grad``:
+        the collective alone, for timing (bench.py's grad_allreduce_ms)."""
+        _, size = world()
+        if size > 1 and self._plan is not None and self._plan["flat"].is_cuda and self._plan["table"] is not None:
+            self._pack_and_reduce(self._plan, None, size)
 
     def attach(self, optimizer: torch.optim.Optimizer):
         """Average gradients across ranks right before every ``optimizer.step()``."""
