@@ -19,11 +19,30 @@ from . import ops
 from ._cache import DerivedCache, require_inference
 
 
+_last_err_flag = {}          # device -> the scene-range error flag of the most recent context (read by validate_inputs)
+
+
+def validate_inputs(device=None) -> None:
+    """Raise if the ``batch_ids`` of the most recent forward on ``device`` were not non-decreasing (DataLoader.py:172 always
+    writes them sorted; the segment kernels binary-search them, so unsorted ids would give silently wrong attention masks).
+    One small D2H read, i.e. a host sync: the eager inference path calls it after the last launch of a forward, the
+    training path piggy-backs on the sync it already has, CUDA-graph replays check the previous replay's flag
+    (``GraphedForward``)."""
+    for dev, flag in list(_last_err_flag.items()):
+        if device is not None and torch.device(device) != dev:
+            continue
+        if flag is not None and int(flag.item()) != 0:
+            _last_err_flag[dev] = None
+            raise RuntimeError("vlsat_b200: batch_ids must be non-decreasing scene ids (one contiguous block of nodes per scene, as "
+                               "collate_fn_mmg builds them, src/dataset/DataLoader.py:153-176)")
+
+
 class SceneContext:
     """Per-batch bookkeeping for node attention: scene range of every node + packed bias MLP."""
 
     def __init__(self, batch_ids: torch.Tensor, centres: torch.Tensor, fc_pack: torch.Tensor, num_heads: int):
         self.seg_start, self.seg_end, self.err_flag = ops.scene_ranges(batch_ids)
+        _last_err_flag[batch_ids.device] = self.err_flag
         self.centres = centres.detach().contiguous()
         self.fc_pack = fc_pack
         self.num_heads = num_heads

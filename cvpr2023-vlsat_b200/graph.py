@@ -21,6 +21,27 @@ class GraphedForward:
         self.model, self.istrain, self.max_graphs = model, istrain, max_graphs
         self._graphs: Dict[Tuple, tuple] = {}
         self.kernels_per_replay = 0
+        self._flag_host = None          # pinned copy of the last replay's sorted-batch_ids flag, checked one call later
+        self._flag_event = None
+
+    def _weights_version(self) -> int:
+        """Sum of the version counters of every parameter and buffer: the derived weights a captured graph reads (packed /
+        folded / split copies) were built from these versions; a different sum means an optimiser step or a
+        ``load_state_dict`` happened since the capture and the graphs must be re-captured."""
+        v = 0
+        for p in self.model.parameters():
+            v += p._version
+        for b in self.model.buffers():
+            v += b._version
+        return v
+
+    def _check_previous_flag(self) -> None:
+        if self._flag_event is not None:
+            self._flag_event.synchronize()
+            self._flag_event = None
+            if int(self._flag_host.item()) != 0:
+                raise RuntimeError("vlsat_b200: the batch_ids of the previous replay were not non-decreasing scene ids "
+                                   "(src/dataset/DataLoader.py:153-176); its outputs are invalid")
 
     @staticmethod
     def _sig(args) -> Tuple:
@@ -43,20 +64,32 @@ class GraphedForward:
             with torch.cuda.graph(graph):
                 static_out = self.model(*static_in, istrain=self.istrain)
             self.kernels_per_replay = ops.launch_count() - n0      # vlsat kernel nodes in the graph
+        from .attention import _last_err_flag
+        flag = _last_err_flag.get(static_in[0].device)          # written by the scene-range kernel inside the graph
         if len(self._graphs) >= self.max_graphs:
             self._graphs.pop(next(iter(self._graphs)))
-        self._graphs[sig] = (graph, static_in, static_out)
+        self._graphs[sig] = (graph, static_in, static_out, self._weights_version(), flag)
         return self._graphs[sig]
 
     def __call__(self, *args):
+        self._check_previous_flag()
         entry = self._graphs.get(self._sig(args))
+        if entry is not None and entry[3] != self._weights_version():
+            self._graphs.clear()                                 # weights changed since the capture: the derived copies are stale
+            entry = None
         if entry is None:
             entry = self.capture(*args)
-        graph, static_in, static_out = entry
+        graph, static_in, static_out, _, flag = entry
         for dst, src in zip(static_in, args):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         graph.replay()
+        if flag is not None:                                     # checked at the next call: no host sync on this one
+            if self._flag_host is None:
+                self._flag_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+            self._flag_host.copy_(flag, non_blocking=True)
+            self._flag_event = torch.cuda.Event()
+            self._flag_event.record()
         return static_out
 
 
@@ -94,6 +127,12 @@ class GraphedTrainStep:
         old_hint, old_step = T._scene_hint, A.DropoutState.device_step
         T._scene_hint, A.DropoutState.device_step = stats, self._step
         try:
+            # The two warm-up passes are real training-mode forwards: without care the first step of every new input
+            # signature would update the BatchNorm running statistics three times (and count three batches) and consume
+            # two steps of dropout stream - the reference does each once per step (advisor finding, round 1). Snapshot the
+            # buffers and the dropout offset, restore them after the warm-up.
+            buffers = [(b, b.detach().clone()) for b in self.model.buffers()]
+            drop_state = (A.DropoutState.seed, A.DropoutState.offset)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                 # warm-up: lazy init, allocator pool
@@ -102,6 +141,10 @@ class GraphedTrainStep:
                     self._run(static_in)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            with torch.no_grad():
+                for b, saved in buffers:
+                    b.copy_(saved)
+            A.DropoutState.seed, A.DropoutState.offset = drop_state
             self.model.zero_grad(set_to_none=True)
             ops._weight_splits.clear()                    # every weight split must be a kernel node of the graph
             graph = torch.cuda.CUDAGraph()

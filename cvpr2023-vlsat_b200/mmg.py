@@ -122,6 +122,7 @@ class MMG(nn.Module):
                 e3, e3p = e3_raw, self.gcn_3ds[i].edgeatten.last_edge_split
         (e3o, e3op), (e2o, e2op) = g.to_original(e3, True), g.to_original(e2, True)
         self.last_edge_pairs = (e3op, e2op)          # (hi, lo) pairs of the two returned edge features, for the caller's projections
+        self.last_context = ctx                      # its err_flag: batch_ids not sorted (attention.validate_inputs)
         return o3, o2, e3o, e2o
 
 

@@ -207,6 +207,9 @@ class Mmgnet(nn.Module):
                                    self.obj_predictor_3d.bias.detach(), scale_ptr=scale)
         obj_logits_2d = ops.linear(ops.row_l2norm(g2), self.obj_predictor_2d.weight.detach(),
                                    self.obj_predictor_2d.bias.detach(), scale_ptr=scale)
+        if not torch.cuda.is_current_stream_capturing():
+            from .attention import validate_inputs
+            validate_inputs(obj_points.device)           # unsorted batch_ids raise here, after the last launch (one host sync)
         if istrain:
             return (obj_logits_3d, obj_logits_2d, rel_cls_3d, rel_cls_2d, obj_feature_3d_mimic, obj_features_2d_mimic,
                     gcn_edge_feature_2d_dis, self.obj_logit_scale.detach().exp())

@@ -80,7 +80,9 @@ class SceneContextTrain:
         if _scene_hint is not None:
             tot, mx = _scene_hint
         elif n:
-            tot, mx = torch.stack([ends[-1], sizes.max()]).tolist()      # the one host sync
+            tot, mx, bad = torch.stack([ends[-1], sizes.max(), self.err_flag[0].to(torch.int64)]).tolist()      # the one host sync
+            if bad:
+                raise RuntimeError("vlsat_b200: batch_ids must be non-decreasing scene ids (src/dataset/DataLoader.py:153-176)")
         else:
             tot, mx = 0, 1
         self.n_pairs, self.max_scene = int(tot), max(int(mx), 1)

@@ -485,3 +485,48 @@ def test_pair_emitting_producers_reconstruct_their_output():
         assert p is not None and p[0].dtype == torch.bfloat16
         rec = p[0].double() + p[1].double()
         assert ((rec - out.double()).abs() <= 2.0 ** -16 * out.double().abs() + 1e-30).all()
+
+
+def test_unsorted_batch_ids_raise_instead_of_silently_wrong_masks():
+    """Round-1 advisor finding: the scene-range kernel flags non-monotonic batch_ids but nobody read the flag. Eager
+    inference raises after the last launch of the forward, the differentiable path with the host sync it already has, a
+    CUDA-graph replay at the next call (no sync on the replay itself)."""
+    model = _cuda_model({})
+    b = synth.make_config_batch("cfg2", seed=5, num_scenes=3).to(DEV)
+    bad_ids = b.batch_ids.clone()
+    bad_ids[0], bad_ids[-1] = bad_ids[-1].clone(), bad_ids[0].clone()           # scene 2 ... scene 0: not non-decreasing
+    args_bad = (b.obj_points, b.obj_2d_feats, b.edge_indices, b.descriptor, bad_ids)
+    with torch.no_grad():
+        model(*b.forward_args())                                               # sorted ids pass
+        with pytest.raises(RuntimeError, match="non-decreasing"):
+            model(*args_bad)
+        model(*b.forward_args())                                               # and the flag does not stick
+    model.train()
+    with pytest.raises(RuntimeError, match="non-decreasing"):
+        model(*args_bad, istrain=True)
+    model.eval()
+    graphed = V.GraphedForward(model)
+    with torch.no_grad():
+        graphed(*b.forward_args())
+        graphed(*args_bad)                                                     # same shapes: replayed, flag copied asynchronously
+        with pytest.raises(RuntimeError, match="previous replay"):
+            graphed(*b.forward_args())
+        graphed(*b.forward_args())
+
+
+def test_graphed_forward_recaptures_after_a_weight_change():
+    """Round-1 advisor finding: a captured graph bakes the addresses of derived weights (packed / folded / split copies) that
+    are refreshed only by eager calls; after an optimiser step or load_state_dict a replay must not run on stale copies."""
+    model = _cuda_model({})
+    b = synth.make_config_batch("cfg2", seed=6, num_scenes=2).to(DEV)
+    graphed = V.GraphedForward(model)
+    with torch.no_grad():
+        before = [t.clone() for t in graphed(*b.forward_args())]
+        for p in model.mmg.gcn_3ds[1].prop[2].parameters():
+            p.mul_(1.5)                                                        # what an optimiser step does: in-place update
+        model.rel_predictor_3d.fc3.bias.add_(0.25)
+        after = [t.clone() for t in graphed(*b.forward_args())]
+        want = model(*b.forward_args())
+    for i, (a, w) in enumerate(zip(after, want)):
+        assert_close(a, w, f"replay after a weight change, output {i}", rtol=1e-4, atol=1e-5)
+    assert not torch.allclose(after[0], before[0]) and not torch.allclose(after[2], before[2])

@@ -643,3 +643,28 @@ def test_graphed_train_step_matches_eager_and_redraws_dropout():
     l1 = step2(*b.forward_args())[0].detach().clone()
     l2 = step2(*b.forward_args())[0].detach().clone()
     assert torch.isfinite(l1) and torch.isfinite(l2) and not torch.equal(l1, l2)
+
+
+def test_graph_capture_leaves_batchnorm_statistics_as_one_step_would():
+    """Round-1 advisor finding: the warm-up passes of GraphedTrainStep.capture updated the BatchNorm running statistics
+    (three updates and num_batches_tracked += 3 on the first step of every new signature). After the first call the buffers
+    must equal those of ONE eager training step from the same state."""
+    def fresh():
+        m = V.Mmgnet(cases.model_config({}), 160, 26)
+        m.load_state_dict(cases.seeded_state(m, cases.MMGNET_WEIGHT_SEED))
+        return m.to(DEV).train()
+    b = cases.MMGNET_CASES["mmgnet_ragged"][1]().to(DEV)
+    loss_fn = lambda outs: cases.scalar_loss(outs[:7], seed=7)
+    eager, graphed_model = fresh(), fresh()
+    _no_dropout(eager); _no_dropout(graphed_model)
+    loss_fn(eager(*b.forward_args(), istrain=True)).backward()
+    step = V.GraphedTrainStep(graphed_model, loss_fn)
+    step(*b.forward_args())
+    be, bg = eager.mlp_3d[1], graphed_model.mlp_3d[1]
+    assert int(bg.num_batches_tracked) == int(be.num_batches_tracked) == 1
+    assert_close(bg.running_mean, be.running_mean, "running_mean after the first graphed step", rtol=1e-5, atol=1e-6)
+    assert_close(bg.running_var, be.running_var, "running_var after the first graphed step", rtol=1e-5, atol=1e-6)
+    step(*b.forward_args())
+    loss_fn(eager(*b.forward_args(), istrain=True)).backward()
+    assert int(bg.num_batches_tracked) == int(be.num_batches_tracked) == 2
+    assert_close(bg.running_mean, be.running_mean, "running_mean after the second step", rtol=1e-5, atol=1e-6)
