@@ -29,10 +29,27 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("VLSAT_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _resolve_root() -> str:
+    """VLSAT_REFERENCE_ROOT if set, else /root/reference (build container), else the staged byte-for-byte copy of the path's
+    files under baseline/_ref (GPU box; oracle/stage_reference.py). Resolved at call time: test modules import this file
+    in any order."""
+    env = os.environ.get("VLSAT_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/src/model"):
+        return "/root/reference"
+    return _STAGED
+
+
+REF_ROOT = _resolve_root()
 
 
 def reference_available() -> bool:
+    global REF_ROOT
+    REF_ROOT = _resolve_root()
     return os.path.isdir(os.path.join(REF_ROOT, "src", "model"))
 
 
