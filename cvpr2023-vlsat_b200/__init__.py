@@ -11,7 +11,7 @@ from .mmg import MMG, GraphEdgeAttenNetworkLayers                               
 from .mmgnet import (AdapterModel, DEFAULT_MODEL_CONFIG, Mmgnet, accelerate_reference_model,  # noqa: F401
                      adopt_parameters, load_model_config)
 from .pointnet import PointNetfeat, PointNetRelClsMulti                                      # noqa: F401
-from .graph import GraphedForward, GraphedTrainStep                                                           # noqa: F401
+from .graph import GraphedForward, GraphedTrainStep, StreamedInference                                                           # noqa: F401
 from . import autograd, data_prep, eval_ranks, ops, synth, train_glue, train_path                                   # noqa: F401
 
 __version__ = "0.1.0"

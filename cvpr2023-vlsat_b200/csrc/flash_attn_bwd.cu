@@ -21,8 +21,10 @@
 // TMEM (512 columns): T1[b] (S / P) at 64 b | T2[b] (dP / dS) at 128 + 64 b | acc1 (dV) at 256 | acc2 (dK or dQ) at 320 |
 //                     X1 (hi 32 words, lo 32 words) at 384 | X2 at 448.  b = tile parity: the scores of tile i + 1 are
 //                     issued before the accumulation of tile i, so the tensor pipe never waits for the conversion warps.
-// Warps: 0 = producer of the score operands (Y ring), 1 = MMA issue, 2..9 = conversion (two threads per row, one 32-column
-//        half each), 10 = producer of the accumulation operands (Z ring).
+// Warps: 0 = producer of the score operands (Y ring), 1 = MMA issue, 2..17 = conversion (FOUR threads per row, one 16-column
+//        quarter of every score tile each: the conversion is a chain of dependent TMEM loads, ex2 and splits, and with
+//        two warps per scheduler ncu showed it pacing the kernel - tensor pipe 55 % active, issue 33 %, long-scoreboard
+//        stalls; four warps per scheduler hide that latency), 18 = producer of the accumulation operands (Z ring).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
@@ -34,7 +36,8 @@ namespace vlsat {
 using namespace tc;
 
 constexpr int FW_ROWS = 128, FW_T = 64, FW_DK = 64;
-constexpr int FW_THREADS = 11 * 32;
+constexpr int FW_CONV_WARPS = 16;                         // conversion warps: 4 per TMEM lane quarter
+constexpr int FW_THREADS = (3 + FW_CONV_WARPS) * 32;
 constexpr int FW_TILE = FW_T * 128;                       // one [64 x 64] bf16 tile: 64 rows of 128 bytes
 constexpr int FW_PAIR = 2 * FW_TILE;                      // hi | lo
 constexpr int FW_YST = 3, FW_ZST = 3;                     // ring depths
@@ -62,6 +65,18 @@ __device__ __forceinline__ void fw_tmem_st_16(uint32_t taddr, const uint32_t (&r
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
+}
+__device__ __forceinline__ void fw_tmem_st_8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void fw_tmem_ld_16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
 }
 // D[tmem] (+)= A[tmem] . B[smem]^T, bf16 inputs, A read from tensor memory (lane = row, two consecutive K elements per word)
 __device__ __forceinline__ void fw_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -135,10 +150,10 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
         prefetch_tmap(&tm_y1h); prefetch_tmap(&tm_y1l); prefetch_tmap(&tm_y2h); prefetch_tmap(&tm_y2l);
         prefetch_tmap(&tm_z2h); prefetch_tmap(&tm_z2l);
         if (KV) { prefetch_tmap(&tm_z1h); prefetch_tmap(&tm_z1l); }
-        mbar_init(x_full, 256);
+        mbar_init(x_full, 32 * FW_CONV_WARPS);
         for (int s = 0; s < FW_YST; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
         for (int s = 0; s < FW_ZST; ++s) { mbar_init(&z_full[s], 1); mbar_init(&z_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&p_ready[s], 256); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&p_ready[s], 32 * FW_CONV_WARPS); }
         for (int s = 0; s < FW_NSTAT; ++s) mbar_init(&stat_full[s], 1);
         mbar_init(acc_done, 1);
         fence_barrier_init();
@@ -176,7 +191,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
             }
             __syncwarp();
         }
-    } else if (warp == 10) {
+    } else if (warp == 2 + FW_CONV_WARPS) {
         // ---- accumulation operands (transposed copies): rows = 64 dims, 64 streamed elements = 128 bytes
         for (int i = 0; i < n_tiles; ++i) {
             const int s = i % FW_ZST;
@@ -240,13 +255,13 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
                 const uint32_t tp = tmem_base + 64 * b, tds = tmem_base + 128 + 64 * b;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {                // 16 streamed elements per MMA = 8 packed columns
-                    const uint32_t off = 32 * (kk >> 1) + 8 * (kk & 1);       // this half's hi words; its lo words sit 16 columns on
+                    const uint32_t off = 16 * kk;                  // quarter kk of the tile: 8 hi words, then its 8 lo words
                     const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
                     if (KV) {
-                        mma3(tmem_base + 256, tp + off, tp + off + 16, dz + 2 * kk, acc);                 // dV += P^T dO
-                        mma3(tmem_base + 320, tds + off, tds + off + 16, dz + 2 * LO + 2 * kk, acc);      // dK += dS^T Q
+                        mma3(tmem_base + 256, tp + off, tp + off + 8, dz + 2 * kk, acc);                  // dV += P^T dO
+                        mma3(tmem_base + 320, tds + off, tds + off + 8, dz + 2 * LO + 2 * kk, acc);       // dK += dS^T Q
                     } else {
-                        mma3(tmem_base + 320, tds + off, tds + off + 16, dz + 2 * kk, acc);               // dQ += dS K
+                        mma3(tmem_base + 320, tds + off, tds + off + 8, dz + 2 * kk, acc);                // dQ += dS K
                     }
                 }
                 tc_commit(&z_empty[zs]);
@@ -256,30 +271,24 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
             if (i + 2 < n_tiles) issue_scores(i + 2);            // T1[b] / T2[b] are free in pipe order behind the accumulation
         }
     } else {
-        const int kh = ((warp - 2) >> 2) & 1;                    // 32-column half of every score tile owned by this thread
+        const int kq = ((warp - 2) >> 2) & 3;                    // 16-column quarter of every score tile owned by this thread
         const int qd = warp & 3;                                 // TMEM lane quarter this warp may access
         const int row_l = qd * 32 + lane;
         const int row = r0 + row_l;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        // stationary operands into TMEM, once: the two threads of a row copy its hi (kh = 0) and lo (kh = 1) words
+        // stationary operands into TMEM, once: the four threads of a row copy X1 hi, X1 lo, X2 hi, X2 lo (32 words each)
         {
             uint32_t w[32];
-            const bool live = row < a.n_stat;
-            const int64_t rr = live ? row : 0;
-            const uint4* s1 = reinterpret_cast<const uint4*>((kh ? a.x1_lo : a.x1_hi) + rr * a.ldx1 + head * FW_DK);
+            const bool live = row < a.n_stat && (PASSES == 3 || (kq & 1) == 0);
+            const int64_t rr = row < a.n_stat ? row : 0;
+            const uint16_t* base = kq == 0 ? a.x1_hi : kq == 1 ? a.x1_lo : kq == 2 ? a.x2_hi : a.x2_lo;
+            const uint4* s1 = reinterpret_cast<const uint4*>(base + rr * (kq < 2 ? a.ldx1 : a.ldx2) + head * FW_DK);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const uint4 t = live ? __ldg(s1 + u) : make_uint4(0u, 0u, 0u, 0u);
                 w[4 * u] = t.x; w[4 * u + 1] = t.y; w[4 * u + 2] = t.z; w[4 * u + 3] = t.w;
             }
-            fw_tmem_st_32(tmem_base + 384 + lane_off + 32 * kh, w);
-            const uint4* s2 = reinterpret_cast<const uint4*>((kh ? a.x2_lo : a.x2_hi) + rr * a.ldx2 + head * FW_DK);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint4 t = live ? __ldg(s2 + u) : make_uint4(0u, 0u, 0u, 0u);
-                w[4 * u] = t.x; w[4 * u + 1] = t.y; w[4 * u + 2] = t.z; w[4 * u + 3] = t.w;
-            }
-            fw_tmem_st_32(tmem_base + 448 + lane_off + 32 * kh, w);
+            fw_tmem_st_32(tmem_base + 384 + lane_off + 32 * kq, w);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(x_full);
@@ -291,21 +300,21 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
         }
         for (int i = 0; i < n_tiles; ++i) {
             const int b = i & 1;
-            const int c0 = (tile_begin + i) * FW_T + 32 * kh;     // first streamed element of this thread's half tile
-            const uint32_t t1 = tmem_base + 64 * b + lane_off + 32 * kh;
-            const uint32_t t2 = tmem_base + 128 + 64 * b + lane_off + 32 * kh;
-            uint32_t s[32], d[32];
+            const int c0 = (tile_begin + i) * FW_T + 16 * kq;     // first streamed element of this thread's quarter tile
+            const uint32_t t1 = tmem_base + 64 * b + lane_off + 16 * kq;
+            const uint32_t t2 = tmem_base + 128 + 64 * b + lane_off + 16 * kq;
+            uint32_t s[16], d[16];
             mbar_wait(&t_full[b], (i >> 1) & 1);
             tc_fence_after();
-            tmem_ld_32x32(t1, s);
-            tmem_ld_32x32(t2, d);
+            fw_tmem_ld_16(t1, s);
+            fw_tmem_ld_16(t2, d);
             tmem_ld_wait();
-            const float* st = stat_smem + (i % FW_NSTAT) * 128 + 32 * kh;
+            const float* st = stat_smem + (i % FW_NSTAT) * 128 + 16 * kq;
             if (KV) mbar_wait(&stat_full[i % FW_NSTAT], (i / FW_NSTAT) & 1);
-            const bool ragged = !KV && (c0 + 32 > a.n_stream);
-            uint32_t ph[16], pl[16], dh[16], dl[16];
+            const bool ragged = !KV && (c0 + 16 > a.n_stream);
+            uint32_t ph[8], pl[8], dh[8], dl[8];
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {                     // four streamed elements per step
+            for (int c4 = 0; c4 < 4; ++c4) {                     // four streamed elements per step
                 float l4[4], e4[4];
                 if (KV) {
                     const float4 lv = *reinterpret_cast<const float4*>(st + 4 * c4);          // broadcast reads
@@ -333,43 +342,43 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
                     dh[2 * c4] = fw_pack_rn(g[0], g[1]); dh[2 * c4 + 1] = fw_pack_rn(g[2], g[3]);
                 }
             }
-            // in place: this thread's 32 fp32 columns become 16 hi words + 16 lo words of the same 32 streamed elements
-            if (KV) { fw_tmem_st_16(t1, ph); if (PASSES == 3) fw_tmem_st_16(t1 + 16, pl); }
-            fw_tmem_st_16(t2, dh);
-            if (PASSES == 3) fw_tmem_st_16(t2 + 16, dl);
+            // in place: this thread's 16 fp32 columns become 8 hi words + 8 lo words of the same 16 streamed elements
+            if (KV) { fw_tmem_st_8(t1, ph); if (PASSES == 3) fw_tmem_st_8(t1 + 8, pl); }
+            fw_tmem_st_8(t2, dh);
+            if (PASSES == 3) fw_tmem_st_8(t2 + 8, dl);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&p_ready[b]);
         }
-        // ---- epilogue: each thread stores its row's 32-column half of the accumulators
+        // ---- epilogue: each thread stores its row's 16-column quarter of the accumulators
         float* o1 = a.out1 ? a.out1 + (int64_t)blockIdx.z * a.split_stride : nullptr;
         float* o2 = a.out2 + (int64_t)blockIdx.z * a.split_stride;
-        uint32_t acc[32];
+        uint32_t acc[16];
         if (n_tiles > 0) { mbar_wait(acc_done, 0); tc_fence_after(); }
         if (KV) {
-            if (n_tiles > 0) { tmem_ld_32x32(tmem_base + 256 + lane_off + 32 * kh, acc); tmem_ld_wait(); }
+            if (n_tiles > 0) { fw_tmem_ld_16(tmem_base + 256 + lane_off + 16 * kq, acc); tmem_ld_wait(); }
             else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = 0u;
+                for (int j = 0; j < 16; ++j) acc[j] = 0u;
             }
             if (row < a.n_stat) {
-                float* orow = o1 + (int64_t)row * a.ldo + head * FW_DK + 32 * kh;
+                float* orow = o1 + (int64_t)row * a.ldo + head * FW_DK + 16 * kq;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
+                for (int j = 0; j < 16; j += 4)
                     *reinterpret_cast<float4*>(orow + j) = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
                                                                        __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
             }
         }
-        if (n_tiles > 0) { tmem_ld_32x32(tmem_base + 320 + lane_off + 32 * kh, acc); tmem_ld_wait(); }
+        if (n_tiles > 0) { fw_tmem_ld_16(tmem_base + 320 + lane_off + 16 * kq, acc); tmem_ld_wait(); }
         else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0u;
+            for (int j = 0; j < 16; ++j) acc[j] = 0u;
         }
         if (row < a.n_stat) {
-            float* orow = o2 + (int64_t)row * a.ldo + head * FW_DK + 32 * kh;
+            float* orow = o2 + (int64_t)row * a.ldo + head * FW_DK + 16 * kq;
             const float sc = a.scale;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
+            for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(orow + j) = make_float4(__uint_as_float(acc[j]) * sc, __uint_as_float(acc[j + 1]) * sc,
                                                                    __uint_as_float(acc[j + 2]) * sc, __uint_as_float(acc[j + 3]) * sc);
         }

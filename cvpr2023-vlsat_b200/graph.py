@@ -178,3 +178,75 @@ class GraphedTrainStep:
         for p, g in grads:
             p.grad = g
         return loss, outs
+
+
+class StreamedInference:
+    """Host-to-host inference loop around ``GraphedForward``: every batch comes from (pinned) host memory and every result
+    goes back to pinned host memory, with the copies of neighbouring batches overlapped with the compute of the current one.
+
+        pipe = StreamedInference(model)
+        for batch in loader:                       # tuples of the five forward arguments, host tensors
+            done = pipe.submit(batch)              # returns the PREVIOUS batch's outputs (host tensors) or None
+        last = pipe.drain()
+
+    This is the serving-side counterpart of ``MMGNet.validation`` (src/model/model.py:201-215: ``.cuda()`` of the collated
+    batch, forward, ``.detach().cpu()`` of the logits). Three streams: H2D into one of two staging sets on the copy-in
+    stream, a device-to-device hop into the graph's static inputs + the replay + a hop of the outputs into one of two
+    staging sets on the compute stream, D2H on the copy-out stream. The result buffers returned for batch i are reused for
+    batch i + 2: consume (or copy) them before submitting two more."""
+
+    def __init__(self, model: torch.nn.Module):
+        self.graphed = GraphedForward(model)
+        self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        self._in = [None, None]        # device staging sets of the inputs
+        self._out_dev = [None, None]   # device staging sets of the outputs
+        self._out_host = [None, None]
+        self._in_free = [None, None]   # events: the compute stream has consumed staging set k
+        self._out_done = [None, None]  # events: D2H of staging set k has finished
+        self._i = 0
+        self._pending = None
+
+    def submit(self, host_args):
+        k = self._i & 1
+        comp = torch.cuda.current_stream()
+        with torch.cuda.stream(self.h2d):
+            if self._in_free[k] is not None:
+                self.h2d.wait_event(self._in_free[k])
+            if self._in[k] is None or any(a.shape != b.shape for a, b in zip(self._in[k], host_args)):
+                self._in[k] = [torch.empty(a.shape, dtype=a.dtype, device="cuda") for a in host_args]
+            for dst, src in zip(self._in[k], host_args):
+                dst.copy_(src, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.h2d)
+        comp.wait_event(ready)
+        outs = self.graphed(*self._in[k])                       # device-to-device hop into the static inputs + replay
+        self._in_free[k] = torch.cuda.Event()
+        self._in_free[k].record(comp)
+        if self._out_dev[k] is None or any(a.shape != b.shape for a, b in zip(self._out_dev[k], outs)):
+            self._out_dev[k] = [torch.empty_like(o) for o in outs]
+            self._out_host[k] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+        if self._out_done[k] is not None:
+            comp.wait_event(self._out_done[k])                  # the D2H that last read this staging set is done
+        for dst, src in zip(self._out_dev[k], outs):
+            dst.copy_(src, non_blocking=True)
+        computed = torch.cuda.Event()
+        computed.record(comp)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(computed)
+            for dst, src in zip(self._out_host[k], self._out_dev[k]):
+                dst.copy_(src, non_blocking=True)
+            self._out_done[k] = torch.cuda.Event()
+            self._out_done[k].record(self.d2h)
+        prev, self._pending = self._pending, k
+        self._i += 1
+        if prev is None:
+            return None
+        self._out_done[prev].synchronize()                      # the caller consumes batch i - 1 while batch i computes
+        return self._out_host[prev]
+
+    def drain(self):
+        if self._pending is None:
+            return None
+        k, self._pending = self._pending, None
+        self._out_done[k].synchronize()
+        return self._out_host[k]

@@ -530,3 +530,23 @@ def test_graphed_forward_recaptures_after_a_weight_change():
     for i, (a, w) in enumerate(zip(after, want)):
         assert_close(a, w, f"replay after a weight change, output {i}", rtol=1e-4, atol=1e-5)
     assert not torch.allclose(after[0], before[0]) and not torch.allclose(after[2], before[2])
+
+
+def test_streamed_inference_returns_each_batch_results_in_order():
+    """StreamedInference (overlapped H2D / replay / D2H): the host tensors handed back for batch i equal the plain forward of
+    batch i, for a run longer than its two staging sets, including the drain."""
+    model = _cuda_model({})
+    batches = [synth.make_config_batch("cfg2", seed=30 + i, num_scenes=2).pin() for i in range(5)]
+    with torch.no_grad():
+        want = [[t.cpu() for t in model(*b.to(DEV).forward_args())] for b in batches]
+        pipe = V.StreamedInference(model)
+        got = []
+        for b in batches:
+            done = pipe.submit(b.forward_args())
+            if done is not None:
+                got.append([t.clone() for t in done])
+        got.append([t.clone() for t in pipe.drain()])
+    assert len(got) == len(want)
+    for i, (g, w) in enumerate(zip(got, want)):
+        for j, (a, e) in enumerate(zip(g, w)):
+            assert_close(a, e, f"batch {i} output {j}", rtol=1e-4, atol=1e-5)

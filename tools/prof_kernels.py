@@ -31,5 +31,21 @@ if "gat" in which or "pointnet" in which:
                 layer = model.mmg.gcn_3ds[0]
                 x = torch.randn(640, 512, device=dev); e = torch.randn(9600, 512, device=dev)
                 layer(x, e, b.edge_indices)
+if "flash_bwd" in which:
+    q, k, v, dout = (torch.randn(9600, 512, generator=g).to(dev) for _ in range(4))
+    (qp, qt), (kp, kt), (vp, vt) = ops.bf16_split_t(q), ops.bf16_split_t(k), ops.bf16_split_t(v)
+    out, lse = ops.flash_attn_bf16(qp, kp, vt, 9600, 8, want_lse=True)
+    for _ in range(2):
+        ops.flash_attn_bf16_bwd(q, k, v, dout, out, lse, 8, prep=(qp, qt, kp, kt, vp))
+if "gemm_pairs" in which:
+    dz, x, w = torch.randn(9600, 1024, generator=g).to(dev), torch.randn(9600, 512, generator=g).to(dev), torch.randn(1024, 512, generator=g).to(dev)
+    dzp, xp, wp = ops.bf16_split(dz), ops.bf16_split(x), ops.bf16_split(w)
+    for _ in range(2):
+        ops.gemm_nn(dzp, wp, 512)            # dX = dZ W      [9600, 512]
+        ops.gemm_tn(dzp, xp, 1024, 512)      # dW = dZ^T X    [1024, 512], reduction 9600 split over CTAs
+    t, h = torch.randn(76800, 128, generator=g).to(dev), torch.randn(76800, 128, generator=g).to(dev)
+    tp, hp = ops.bf16_split(t), ops.bf16_split(h)
+    for _ in range(2):
+        ops.gemm_tn(tp, hp, 128, 128)        # attention-MLP weight gradient: one output tile, reduction 76,800
 torch.cuda.synchronize()
 print("done")
