@@ -509,9 +509,12 @@ def test_unsorted_batch_ids_raise_instead_of_silently_wrong_masks():
     with torch.no_grad():
         graphed(*b.forward_args())
         graphed(*args_bad)                                                     # same shapes: replayed, flag copied asynchronously
+        torch.cuda.synchronize()                                               # (the check never waits for the copy itself)
         with pytest.raises(RuntimeError, match="previous replay"):
             graphed(*b.forward_args())
         graphed(*b.forward_args())
+        torch.cuda.synchronize()
+        graphed(*b.forward_args())                                             # the flag was cleared
 
 
 def test_graphed_forward_recaptures_after_a_weight_change():
