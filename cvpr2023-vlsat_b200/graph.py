@@ -63,11 +63,19 @@ class GraphedForward:
             from . import ops
             graph = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
+            from .attention import _last_err_flag
+            if self._flag_host is None:
+                self._flag_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+                self._sticky = torch.zeros((1,), dtype=torch.int32, device=static_in[0].device)
             with torch.cuda.graph(graph):
                 static_out = self.model(*static_in, istrain=self.istrain)
+                flag = _last_err_flag.get(static_in[0].device)      # written by the scene-range kernel inside the graph
+                if flag is not None:
+                    # input validation without a host sync: a sticky device counter and its 4-byte copy to pinned memory
+                    # are nodes of the graph; __call__ polls the pinned value
+                    self._sticky.add_(flag)
+                    self._flag_host.copy_(self._sticky, non_blocking=True)
             self.kernels_per_replay = ops.launch_count() - n0      # vlsat kernel nodes in the graph
-        from .attention import _last_err_flag
-        flag = _last_err_flag.get(static_in[0].device)          # written by the scene-range kernel inside the graph
         if len(self._graphs) >= self.max_graphs:
             self._graphs.pop(next(iter(self._graphs)))
         self._graphs[sig] = (graph, static_in, static_out, self._weights_version(), flag)
@@ -86,12 +94,6 @@ class GraphedForward:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         graph.replay()
-        if flag is not None:                                     # checked at a later call: no host sync on this one
-            if self._flag_host is None:
-                self._flag_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
-                self._sticky = torch.zeros((1,), dtype=torch.int32, device=flag.device)
-            self._sticky.add_(flag)                              # plumbing: a 4-byte counter and its copy to pinned memory
-            self._flag_host.copy_(self._sticky, non_blocking=True)
         return static_out
 
 
