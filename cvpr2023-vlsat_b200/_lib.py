@@ -128,6 +128,7 @@ SIGNATURES = {
     "vlsat_topk_object_ranks": [vp, i64, vp, i64, i32, i32, vp, vp],
     "vlsat_topk_predicate_ranks": [vp, vp, i64, i32, i32, f32, vp, vp],
     "vlsat_topk_triplet_ranks": [vp, i64, i32, vp, i32, vp, vp, vp, i64, i32, f32, vp, vp],
+    "vlsat_recall_at": [vp, i64, i32, i32, i32, vp, vp],
     "vlsat_adamw_step": [vp, vp, vp, i64, i32, C.c_double, C.c_double, f32, vp, i64, vp],
     "vlsat_pack_scale": [vp, vp, vp, i64, i32, f32, vp],
 }

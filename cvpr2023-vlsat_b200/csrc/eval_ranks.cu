@@ -146,6 +146,36 @@ topk_triplet_ranks_kernel(const float* __restrict__ obj_prob, int No, const floa
     }
 }
 
+// 100 * #{valid ranks <= t_j} / #{valid ranks} for three thresholds, one CTA, fixed summation order (deterministic):
+// the "R@k" figures process_train logs after every step (SGFN_MMG/model.py:422-432). INT32_MIN marks an empty slot.
+__global__ void recall_at_kernel(const int32_t* __restrict__ ranks, int64_t n, int t0, int t1, int t2, float* __restrict__ out) {
+    pdl_entry();
+    __shared__ int sm[4][32];
+    int c[4] = {0, 0, 0, 0};
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int r = ranks[i];
+        if (r != INT_MIN) { ++c[3]; c[0] += r <= t0; c[1] += r <= t1; c[2] += r <= t2; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int v = c[j];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[j][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int tot[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int v = lane < (int)(blockDim.x >> 5) ? sm[j][lane] : 0;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            tot[j] = v;
+        }
+        if (lane < 3) out[lane] = tot[3] > 0 ? 100.f * (float)tot[lane] / (float)tot[3] : 0.f;
+    }
+}
+
 }  // namespace vlsat
 
 using namespace vlsat;
@@ -188,5 +218,11 @@ extern "C" int vlsat_topk_triplet_ranks(const float* obj_prob, int64_t n_nodes, 
     const size_t smem = (size_t)(2 * n_obj_cls + 2 * n_rel_cls) * sizeof(float);
     launch_k(topk_triplet_ranks_kernel, dim3((unsigned)E), dim3(TR_THREADS), smem, (cudaStream_t)stream, obj_prob, n_obj_cls, rel_prob, n_rel_cls,
              gt_cls, gt_rel, edges, n_nodes, topk, threshold, ranks);
+    return finish_launch();
+}
+
+extern "C" int vlsat_recall_at(const int32_t* ranks, int64_t n, int t0, int t1, int t2, float* out3, void* stream) {
+    VLSAT_REQUIRE(n >= 0 && out3 && (n == 0 || ranks));
+    launch_k(recall_at_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, ranks, n, t0, t1, t2, out3);
     return finish_launch();
 }

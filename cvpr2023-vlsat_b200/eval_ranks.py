@@ -4,9 +4,9 @@ SGFN_MMG/model.py:463-472). Same function names and result order as the referenc
 tensors ``process_val`` holds (``gt_cls`` [N], ``gt_rel_cls`` [E, 26], ``edge_indices`` [E, 2]) instead of ``get_gt``'s
 python list. Results stay on the device (flat int64, the reference returns numpy arrays). No CPU fallback.
 
-STATUS: written at the end of round 1 after the GPU budget was spent - compiles for sm_100a, NOT YET RUN ON HARDWARE.
-The parity tests (tests/test_eval_ranks_next.py, against the oracle pinned on the reference's functions) carry the
-``gpu_next`` marker and are not part of ``-m gpu`` until they have passed once on a B200.
+First run on a B200 in round 2: tests/test_eval_ranks_gpu.py (bit-exact against the oracle, which is pinned on the
+reference's own functions and fixtures) is part of ``-m gpu``. ``train_metrics`` is the device-side form of the metric
+code that follows ``self.backward(loss)`` in ``process_train`` (SGFN_MMG/model.py:422-432).
 """
 from __future__ import annotations
 
@@ -77,3 +77,39 @@ def evaluate_triplet_topk(objs_pred: torch.Tensor, rels_pred: torch.Tensor, gt_c
                          y.data_ptr(), ed.data_ptr(), r.shape[0], int(topk), float(confidence_threshold), out.data_ptr(),
                          ops._stream()), "vlsat_topk_triplet_ranks")
     return _flatten(out)
+
+
+def _ranks_raw(kind: str, pred, target, topk: int, threshold: float = 0.5) -> torch.Tensor:
+    """int32 rank array in the kernels' own layout (INT32_MIN = empty slot): no boolean indexing, hence no host sync."""
+    if kind == "obj":
+        p, t = _f32(pred, "objs_pred"), _i64(target, "objs_target").view(-1)
+        out = torch.empty((p.shape[0],), device=p.device, dtype=torch.int32)
+        _lib.check(ops._call("vlsat_topk_object_ranks", p.data_ptr(), p.stride(0), t.data_ptr(), p.shape[0], p.shape[1], int(topk),
+                             out.data_ptr(), ops._stream()), "vlsat_topk_object_ranks")
+        return out
+    p, y = _f32(pred, "rels_pred"), _f32(target, "gt_rel_cls")
+    out = torch.empty(p.shape, device=p.device, dtype=torch.int32)
+    _lib.check(ops._call("vlsat_topk_predicate_ranks", p.data_ptr(), y.data_ptr(), p.shape[0], p.shape[1], int(topk), float(threshold),
+                         out.data_ptr(), ops._stream()), "vlsat_topk_predicate_ranks")
+    return out
+
+
+def recall_at(ranks: torch.Tensor, thresholds) -> torch.Tensor:
+    """[3] float32 on the device: 100 * (ranks <= t).sum() / len(ranks) for three thresholds (SGFN_MMG/model.py:425-426)."""
+    t = [int(x) for x in thresholds]
+    out = torch.empty((3,), device=ranks.device, dtype=torch.float32)
+    _lib.check(ops._call("vlsat_recall_at", ranks.data_ptr(), ranks.numel(), t[0], t[1], t[2], out.data_ptr(), ops._stream()), "vlsat_recall_at")
+    return out
+
+
+def train_metrics(obj_logits_3d, obj_logits_2d, rel_cls_3d, rel_cls_2d, gt_cls, gt_rel_cls) -> dict:
+    """The twelve recall figures ``process_train`` computes after ``self.backward(loss)`` (SGFN_MMG/model.py:422-432), as
+    device scalars under the reference's log names - no ``.item()``, no python loop over edges, CUDA-graph capturable."""
+    o3 = recall_at(_ranks_raw("obj", obj_logits_3d.detach(), gt_cls, 11), (1, 5, 10))
+    o2 = recall_at(_ranks_raw("obj", obj_logits_2d.detach(), gt_cls, 11), (1, 5, 10))
+    r3 = recall_at(_ranks_raw("rel", rel_cls_3d.detach(), gt_rel_cls, 6), (1, 3, 5))
+    r2 = recall_at(_ranks_raw("rel", rel_cls_2d.detach(), gt_rel_cls, 6), (1, 3, 5))
+    return {"train/Obj_R1": o3[0], "train/Obj_R5": o3[1], "train/Obj_R10": o3[2],
+            "train/Pred_R1": r3[0], "train/Pred_R3": r3[1], "train/Pred_R5": r3[2],
+            "train/Obj_R1_2d": o2[0], "train/Obj_R5_2d": o2[1], "train/Obj_R10_2d": o2[2],
+            "train/Pred_R1_2d": r2[0], "train/Pred_R3_2d": r2[1], "train/Pred_R5_2d": r2[2]}

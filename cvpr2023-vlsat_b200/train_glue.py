@@ -333,9 +333,12 @@ class TrainStep:
     returns ``(loss, terms)`` as device tensors (no host sync; they are overwritten by the next step)."""
 
     def __init__(self, model: torch.nn.Module, optimizer: FusedAdamW, loss_cfg: Optional[LossConfig] = None, reducer=None,
-                 graphed: bool = True):
+                 graphed: bool = True, metrics: bool = False):
         from .graph import GraphedTrainStep
         self.model, self.optimizer, self.cfg, self.reducer = model, optimizer, loss_cfg or LossConfig(), reducer
+        # metrics=True: the twelve recall figures process_train logs after backward() (SGFN_MMG/model.py:422-432), computed
+        # by the rank kernels inside the same captured step and left in ``self.metrics`` as device scalars
+        self.with_metrics, self.metrics = metrics, None
         self._targets: Dict[Tuple, Tuple[torch.Tensor, ...]] = {}
         self._current: Optional[Tuple[torch.Tensor, ...]] = None
         self.terms: Optional[Dict[str, torch.Tensor]] = None
@@ -343,6 +346,9 @@ class TrainStep:
 
     def _loss(self, outs):
         loss, self.terms = reference_loss(outs, *self._current, cfg=self.cfg)
+        if self.with_metrics:
+            from .eval_ranks import train_metrics
+            self.metrics = train_metrics(outs[0], outs[1], outs[2], outs[3], self._current[0], self._current[1])
         return loss
 
     def step(self, obj_points, obj_2d_feats, edge_index, descriptor, batch_ids, gt_cls, gt_rel_cls, rel_text_feat, scene_stats=None):

@@ -495,7 +495,7 @@ int vlsat_object_prep_fwd(const float* cloud, int64_t ld_cloud, int64_t n_cloud,
 /* ------------------------------------------------------------------------------------------------
  * N3  evaluation ranks of --mode eval (src/utils/eva_utils_acc.py; Mmgnet.process_val, SGFN_MMG/model.py:463-472).
  * rank = 1 + #{scores strictly greater than the ground truth's}, capped at topk + 1 - counted, never sorted.
- * NOT YET RUN ON HARDWARE: written at the end of round 1 after the GPU budget was spent (tests: marker gpu_next).
+ * First run on a B200 in round 2 (tests/test_eval_ranks_gpu.py, bit-exact against the oracle and the reference's fixtures).
  * ---------------------------------------------------------------------------------------------- */
 /* y = softmax(x) over each row (F.softmax(objs_pred, dim=-1), eva_utils_acc.py:143-145); y compact [R, C]. */
 int vlsat_softmax_rows(const float* x, int64_t ld, int64_t R, int C, float* y, void* stream);
@@ -514,6 +514,11 @@ int vlsat_topk_predicate_ranks(const float* rel_prob, const float* gt_rel, int64
 int vlsat_topk_triplet_ranks(const float* obj_prob, int64_t n_nodes, int n_obj_cls, const float* rel_prob, int n_rel_cls,
                              const int64_t* gt_cls, const float* gt_rel, const int64_t* edges, int64_t E, int topk,
                              float threshold, int32_t* ranks, void* stream);
+
+/* 100 * #{ranks <= t_j} / #{ranks} for three thresholds over a rank array in either layout above (INT32_MIN = empty slot):
+ * the Obj_R1/5/10 and Pred_R1/3/5 figures process_train logs every step (SGFN_MMG/model.py:422-432), without a host
+ * sync. out3 [3] float; one CTA, deterministic. */
+int vlsat_recall_at(const int32_t* ranks, int64_t n, int t0, int t1, int t2, float* out3, void* stream);
 
 #ifdef __cplusplus
 }

@@ -53,3 +53,25 @@ def test_tied_labels_reach_zero_and_negative_adjusted_ranks():
     probs = F.softmax(logits, -1)
     got = R.evaluate_triplet_topk(logits.cuda(), rel.cuda(), gt_cls.cuda(), gt_rel.cuda(), edges.cuda(), 101, obj_probs=probs.cuda()).cpu()
     assert torch.equal(got, O.topk_triplet_ranks(logits, rel, gt_cls, gt_rel, edges, 101))
+
+
+def test_train_metrics_match_the_reference_metric_code():
+    """SURVEY 8f N1 remainder: the recall figures process_train logs after backward() (SGFN_MMG/model.py:422-432) from the
+    rank kernels, as device scalars, against the oracle's rank functions (pinned on evaluate_topk_object / _predicate)."""
+    from vlsat_b200 import eval_ranks as R
+    g = torch.Generator().manual_seed(9)
+    n, e = 640, 9600
+    o3, o2 = torch.randn(n, 160, generator=g) * 3, torch.randn(n, 160, generator=g) * 3
+    r3, r2 = torch.sigmoid(torch.randn(e, 26, generator=g) * 2), torch.sigmoid(torch.randn(e, 26, generator=g) * 2)
+    gt_cls, gt_rel = torch.randint(0, 160, (n,), generator=g), (torch.rand(e, 26, generator=g) < 0.04).float()
+    got = R.train_metrics(o3.cuda(), o2.cuda(), r3.cuda(), r2.cuda(), gt_cls.cuda(), gt_rel.cuda())
+    assert len(got) == 12 and all(v.is_cuda and v.dim() == 0 for v in got.values())
+
+    def want(ranks, ks):
+        return [100.0 * float((ranks <= k).sum()) / len(ranks) for k in ks]
+    exp = dict(zip(("train/Obj_R1", "train/Obj_R5", "train/Obj_R10"), want(O.topk_object_ranks(o3, gt_cls, 11), (1, 5, 10))))
+    exp.update(zip(("train/Obj_R1_2d", "train/Obj_R5_2d", "train/Obj_R10_2d"), want(O.topk_object_ranks(o2, gt_cls, 11), (1, 5, 10))))
+    exp.update(zip(("train/Pred_R1", "train/Pred_R3", "train/Pred_R5"), want(O.topk_predicate_ranks(r3, gt_rel, 6), (1, 3, 5))))
+    exp.update(zip(("train/Pred_R1_2d", "train/Pred_R3_2d", "train/Pred_R5_2d"), want(O.topk_predicate_ranks(r2, gt_rel, 6), (1, 3, 5))))
+    for k, v in exp.items():
+        assert abs(float(got[k]) - v) <= 1e-4 * max(1.0, abs(v)), f"{k}: {float(got[k])} vs {v}"
