@@ -447,6 +447,31 @@ def run_b200(args):
     yard = reference_gpu_yardstick(model, graphed, dev) if (rank == 0 and world == 1 and not args.no_ref_gpu and args.workload == "cfg2"
                                                             and args.dtype == "f32") else {}
 
+    # ---- N2: device side of the loader's per-object loop at this workload's object / point counts
+    prep = {}
+    if rank == 0 and world == 1:
+        try:
+            from vlsat_b200 import data_prep
+            n_obj, n_pts = resident[0].obj_points.shape[0], resident[0].obj_points.shape[2]
+            gen = torch.Generator(device=dev).manual_seed(9)
+            per = 2048                                              # points of an instance in the scan cloud
+            cloud = torch.randn(n_obj * per, 3, device=dev, generator=gen)
+            choice = (torch.randint(0, per, (n_obj, n_pts), device=dev, generator=gen) + torch.arange(n_obj, device=dev).view(-1, 1) * per)
+            for _ in range(3):
+                data_prep.prepare_objects(cloud, choice)
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(20):
+                data_prep.prepare_objects(cloud, choice)
+            b_.record()
+            torch.cuda.synchronize()
+            us = a.elapsed_time(b_) / 20 * 1e3
+            prep = {"object_prep_us": round(us, 2), "object_prep_gbs": round(n_obj * n_pts * 32.0 / (us * 1e-6) / 1e9, 1)}
+            del cloud, choice
+        except Exception as exc:
+            prep = {"object_prep_error": f"{type(exc).__name__}: {exc}"[:160]}
+
     # ================= training: forward + backward, then the full step =================
     fwd_bwd = train_line = None
     train_scalars = {}
@@ -660,6 +685,7 @@ def run_b200(args):
                             "single-pass bf16 vs the fp32 reference (tests/test_bf16_mode_gpu.py): probabilities |err| <= 2.5e-2, object logits |err| <= 3e-2 x max|ref|"),
               "fwd_ms": round(fwd_ms, 4), "fwd_scenes_per_s": round(fwd_value, 2), "fwd_e2e_scenes_per_s": fwd_e2e_line["value"]}
     config.update(train_scalars)
+    config.update(prep)
     config.update(yard)
     if yard.get("ref_gpu_kind"):
         config["ref_gpu_note"] = ("reference PyTorch forward on the same B200 (python edge / scene loops of SGFN_MMG/model.py:260-265 and network_MMG.py:183-205 "

@@ -9,7 +9,9 @@ No CPU fallback: CPU tensors raise.
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Sequence, Tuple
+
+import numpy as np
 
 import torch
 
@@ -35,3 +37,28 @@ def prepare_objects(cloud: torch.Tensor, choice: torch.Tensor) -> Tuple[torch.Te
                          obj_points.data_ptr(), descriptor.data_ptr(), ops._stream(),
                          work=(0.0, n * p * (8.0 + 8.0 * c))), "vlsat_object_prep_fwd")
     return obj_points, descriptor
+
+
+def sample_object_indices(instances: np.ndarray, nodes: Sequence[int], num_points: int, rng=np.random) -> np.ndarray:
+    """Host side of the loader's per-object loop (src/dataset/dataset_3dssg.py:279-290): for every node, in order,
+    ``rows = np.where(instances == id)[0]`` and ``choice = np.random.choice(len(rows), num_points, replace=True)`` - one RNG
+    call per node exactly like the reference, so its random stream is preserved - returned as GLOBAL row indices
+    ``rows[choice]`` into the scan cloud, [N, num_points] int64."""
+    out = np.empty((len(nodes), num_points), dtype=np.int64)
+    for i, instance_id in enumerate(nodes):
+        rows = np.where(instances == instance_id)[0]
+        if len(rows) == 0:
+            raise ValueError(f"instance {instance_id} has no points in this scan")
+        out[i] = rows[rng.choice(len(rows), num_points, replace=True)]
+    return out
+
+
+def prepare_scene(points, instances: np.ndarray, nodes: Sequence[int], num_points: int, rng=np.random, device="cuda"):
+    """Loader hook for ``SSGDatasetGraph.data_preparation`` (dataset_3dssg.py:279-293): the scan cloud ``points`` [M, C]
+    (numpy or a CUDA tensor already resident, e.g. cached per scan) and its per-point instance ids -> ``(obj_points
+    [N, C, P], descriptor [N, 11])`` on the device, in the layout ``Mmgnet.forward`` takes (src/model/model.py:71).
+    Sampling stays on the host with the reference's RNG stream; gather, descriptor, centring and the channels-first
+    permute are one kernel (csrc/object_prep.cu)."""
+    choice = torch.from_numpy(sample_object_indices(instances, nodes, num_points, rng)).to(device, non_blocking=True)
+    cloud = points if isinstance(points, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(points, dtype=np.float32))
+    return prepare_objects(cloud.to(device, non_blocking=True), choice)

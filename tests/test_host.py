@@ -127,3 +127,28 @@ def test_adopt_parameters_shares_storage():
     V.adopt_parameters(b, a)
     for (n1, p1), (n2, p2) in zip(a.named_parameters(), b.named_parameters()):
         assert n1 == n2 and p1 is p2
+
+
+def test_loader_hook_reproduces_the_reference_sampling_stream():
+    """N2 loader hook (host side): the indices drawn by data_prep.sample_object_indices select exactly the rows the
+    reference's loop selects (dataset_3dssg.py:285-290: points[np.where(instances == id)[0]][choice]) under the same seed."""
+    import numpy as np
+    from vlsat_b200 import data_prep
+    rs = np.random.RandomState(3)
+    m = 5000
+    points = rs.randn(m, 6).astype(np.float32)
+    instances = rs.randint(1, 9, size=m)
+    nodes = [3, 1, 7, 5]
+    np.random.seed(11)
+    want = []
+    for instance_id in nodes:                                   # the reference's loop, verbatim semantics
+        obj_pointset = points[np.where(instances == instance_id)[0]]
+        choice = np.random.choice(len(obj_pointset), 64, replace=True)
+        want.append(obj_pointset[choice, :])
+    np.random.seed(11)
+    idx = data_prep.sample_object_indices(instances, nodes, 64)
+    assert idx.shape == (4, 64) and idx.dtype == np.int64
+    for i in range(4):
+        assert np.array_equal(points[idx[i]], want[i])
+    with pytest.raises(ValueError):
+        data_prep.sample_object_indices(instances, [99], 64)

@@ -67,3 +67,24 @@ def test_kernel_object_prep_config2_shape_and_strided_cloud():
     assert torch.isnan(d1[:, 3:6]).all() and torch.equal(d1[:, 6:].cpu(), torch.zeros(3, 5)) and p1[:, :3].abs().max().item() == 0.0
     e0, e1 = data_prep.prepare_objects(cloud.cuda(), choice[:0].cuda())
     assert e0.shape == (0, 9, 256) and e1.shape == (0, 11)
+
+
+@pytest.mark.gpu
+def test_prepare_scene_hook_matches_the_reference_loop():
+    """The loader hook end to end: host sampling with the reference's RNG stream + the device kernel against the reference's
+    per-object numpy / torch loop (dataset_3dssg.py:279-293, op_utils.py:47-64) restated by the oracle."""
+    import numpy as np
+    from oracle import vlsat_oracle as O
+    from vlsat_b200 import data_prep
+    rs = np.random.RandomState(5)
+    m = 20000
+    points = (rs.randn(m, 3) * 0.4 + rs.randn(1, 3) * 3).astype(np.float32)
+    instances = rs.randint(1, 12, size=m)
+    nodes = [2, 9, 4, 11, 6]
+    np.random.seed(21)
+    idx = data_prep.sample_object_indices(instances, nodes, 128)
+    np.random.seed(21)
+    obj_points, desc = data_prep.prepare_scene(points, instances, nodes, 128)
+    want_pts, want_desc = O.prepare_objects(torch.from_numpy(points), torch.from_numpy(idx))
+    assert torch.allclose(obj_points.cpu(), want_pts, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(desc.cpu(), want_desc, rtol=1e-4, atol=1e-5)
