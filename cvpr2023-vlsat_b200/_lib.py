@@ -76,6 +76,7 @@ SIGNATURES = {
     "vlsat_node_bias_table_max_scene": [],
     "vlsat_node_bias_table": [vp, i64, vp, vp, vp, i32, vp, i64, vp],
     "vlsat_node_attn_scene_fwd": [vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, vp, i64, i64, vp],
+    "vlsat_dense_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, i32, vp, i64, vp, i64, i64, i64, i32, i32, vp],
     "vlsat_flash_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp],
     "vlsat_flash_attn_tc_fwd": [vp, vp, i64, vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp],
     "vlsat_gat_edge_tc_fwd": [vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, i32,

@@ -181,14 +181,31 @@ class MultiHeadAttention(nn.Module):
     # ---- reference signature -----------------------------------------------------------------------
     def forward(self, queries, keys, values, attention_mask=None, attention_weights=None, way='mul', use_knn=False,
                 output_attn=False):
-        """Same signature as attention.py:105. Unmasked calls ([b_s, n, d] inputs) run the streaming
-        kernel. Dense ``attention_mask`` / ``attention_weights`` tensors are never built in this
-        implementation (``MMG.forward`` calls ``attend_scenes``), so passing them is an error."""
-        if attention_mask is not None or attention_weights is not None or use_knn or output_attn:
-            raise NotImplementedError(
-                "dense attention_mask/attention_weights/att maps are not materialised by vlsat_b200; "
-                "scene-restricted attention goes through MMG.forward / MultiHeadAttention.attend_scenes")
+        """Same signature as attention.py:105, [b_s, n, d] inputs. Without mask / weights the streaming kernel runs
+        (``attend_all``). With the dense ``attention_mask`` [b_s, 1 | h, nq, nk] (0 = masked) and ``attention_weights``
+        [b_s, h, nq, nk] that the reference's own ``MMG.forward`` builds (network_MMG.py:183-205) and passes with
+        ``way='add'`` (:217-218), the exact-fp32 dense kernel runs (csrc/dense_attn.cu; inference only) - so this module can
+        replace the reference's MultiHeadAttention under the reference's MMG. The fast path of this package never builds
+        those tensors (``MMG.forward`` here calls ``attend_scenes``)."""
+        if use_knn or output_attn:
+            raise NotImplementedError("use_knn / output_attn (attention.py:62-63,124-125) are not used on the VL-SAT path and not built")
         if queries.dim() != 3 or keys is not values and keys.data_ptr() != values.data_ptr():
             raise NotImplementedError("expected [b_s, n, d] inputs with keys is values (the only use on the path)")
-        outs = [self.attend_all(queries[b], keys[b]) for b in range(queries.shape[0])]
+        if attention_mask is None and attention_weights is None:
+            outs = [self.attend_all(queries[b], keys[b]) for b in range(queries.shape[0])]
+            return torch.stack(outs, 0)
+        require_inference(self, "MultiHeadAttention with dense attention_mask / attention_weights")
+        if way not in ("mul", "add"):
+            raise NotImplementedError(way)                       # attention.py:72
+        a = self.attention
+        outs = []
+        for b in range(queries.shape[0]):
+            q_in, kv_in = queries[b].contiguous(), keys[b].contiguous()
+            q, k, v = self._project(q_in, kv_in, queries is keys or queries.data_ptr() == keys.data_ptr())
+            w = attention_weights[b] if attention_weights is not None else None
+            m = attention_mask[b] if attention_mask is not None else None
+            if m is not None and m.dim() == 3 and m.shape[0] == 1:
+                m = m[0]
+            att = ops.dense_attn(q, k, v, a.h, weights=w, way=way, mask=m)
+            outs.append(self._finish(q_in, att, False, None))
         return torch.stack(outs, 0)

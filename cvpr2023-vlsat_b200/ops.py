@@ -532,6 +532,33 @@ def node_attn(q, k, v, centres, seg_start, seg_end, fc_pack, n_heads: int, bias_
     return out
 
 
+def dense_attn(q, k, v, n_heads: int, weights=None, way: str = "mul", mask=None) -> torch.Tensor:
+    """softmax(mask(q k^T / sqrt(dk) (*|+) weights)) v with the reference's dense arguments (attention.py:41-78):
+    weights [H, nq, nk], mask [nq, nk] or [H, nq, nk] with 0 = masked (float, bool or integer)."""
+    qp, ldq = _rows(q, "q"); kp, ldk = _rows(k, "k"); vp_, ldv = _rows(v, "v")
+    nq, d = q.shape
+    nk = k.shape[0]
+    out = torch.empty((nq, d), device=q.device, dtype=torch.float32)
+    wp, wstride, wcode = None, 0, 0
+    if weights is not None:
+        weights = _f32(weights, "attention_weights").contiguous()
+        if tuple(weights.shape) != (n_heads, nq, nk):
+            raise ValueError(f"attention_weights must be [H, nq, nk] = {(n_heads, nq, nk)}, got {tuple(weights.shape)}")
+        wp, wstride, wcode = weights.data_ptr(), nq * nk, {"mul": 1, "add": 2}[way]
+    mp, mstride = None, 0
+    if mask is not None:
+        mask = mask.to(torch.float32).contiguous()
+        if tuple(mask.shape) == (n_heads, nq, nk) and n_heads > 1:
+            mstride = nq * nk
+        elif mask.numel() != nq * nk:
+            raise ValueError(f"attention_mask must be [nq, nk] or [H, nq, nk], got {tuple(mask.shape)}")
+        mp = mask.data_ptr()
+    st = _call("vlsat_dense_attn_fwd", qp, ldq, kp, ldk, vp_, ldv, wp, wstride, wcode, mp, mstride, out.data_ptr(), d, nq, nk, n_heads,
+               d // n_heads, _stream(), work=(4.0 * nq * nk * d, 4.0 * (2 * nq * d + 2 * nk * d + (n_heads + 1) * nq * nk)))
+    _lib.check(st, "vlsat_dense_attn_fwd")
+    return out
+
+
 def flash_attn(q, k, v, n_heads: int, want_lse: bool = False):
     qp, ldq = _rows(q, "q"); kp, ldk = _rows(k, "k"); vp_, ldv = _rows(v, "v")
     nq, d = q.shape

@@ -204,6 +204,17 @@ int vlsat_node_attn_scene_fwd(const float* q, int64_t ldq, const float* k, int64
                               const float* table, const int32_t* seg_start, const int32_t* seg_end, int n_heads, int dk,
                               float* out, int64_t ldo, int64_t n_nodes, void* stream);
 
+/* A7 with the reference's DENSE arguments (ScaledDotProductAttention.forward, attention.py:41-78, as MMG.forward calls it,
+ * network_MMG.py:217-218): out = softmax(mask(q k^T / sqrt(dk) (*|+) weights)) v.
+ *   weights [H, nq, nk] fp32 (head stride given; way: 0 none, 1 'mul', 2 'add'), mask fp32, 0 = masked, [nq, nk] shared
+ *   by all heads (mask_head_stride 0) or per head; a fully masked row yields NaN like torch.softmax does.
+ * Exact fp32; exists for module-level drop-in of MultiHeadAttention under the reference's own MMG - the fast path
+ * (vlsat_node_attn_scene_fwd) never builds these tensors. */
+int vlsat_dense_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                         const float* weights, int64_t weights_head_stride, int way, const float* mask,
+                         int64_t mask_head_stride, float* out, int64_t ldo, int64_t nq, int64_t nk, int n_heads,
+                         int dk, void* stream);
+
 /* A9  cross_attn_rel core (network_MMG.py:231; attention.py:54-77 without mask/bias): streaming
  * softmax(QK^T/sqrt(dk)) V over ALL keys, never materialising the [H, nq, nk] score tensor.
  * lse (nullable) [H, nq] = log-sum-exp per row (saved for backward). */

@@ -553,3 +553,74 @@ def test_streamed_inference_returns_each_batch_results_in_order():
     for i, (g, w) in enumerate(zip(got, want)):
         for j, (a, e) in enumerate(zip(g, w)):
             assert_close(a, e, f"batch {i} output {j}", rtol=1e-4, atol=1e-5)
+
+
+def test_reference_signature_attention_with_dense_mask_and_weights():
+    """MultiHeadAttention.forward(queries, keys, values, attention_mask, attention_weights, way='add') exactly as the
+    reference's MMG.forward calls it (network_MMG.py:217-218) against the oracle's dense restatement of attention.py:41-126,
+    self- and cross-attention, ragged scenes; plus way='mul' and a per-head mask against a float64 restatement."""
+    att = V.MMG(512, 512, 256, num_heads=8, depth=1, DROP_OUT_ATTEN=0.5)
+    sd = cases.seeded_state(att, 5)
+    att.load_state_dict(sd)
+    att = att.to(DEV).eval()
+    g = torch.Generator().manual_seed(6)
+    counts = [3, 40, 1, 17]
+    n = sum(counts)
+    bids = torch.cat([torch.full((c,), i) for i, c in enumerate(counts)]).view(-1, 1)
+    centres = torch.randn(n, 3, generator=g) * 2
+    x, y = torch.randn(n, 512, generator=g), torch.randn(n, 512, generator=g)
+    mask, bias = O.distance_bias(sd, "self_attn_fc.", centres, bids, 8)          # [1,1,n,n], [1,8,n,n] as the reference builds them
+    want_self = O.mha(sd, "self_attn.0.", x, x, x, 8, mask, bias)
+    want_cross = O.mha(sd, "cross_attn.0.", y, x, x, 8, mask, bias)
+    xd, yd, md, bd = x.to(DEV).unsqueeze(0), y.to(DEV).unsqueeze(0), mask.to(DEV), bias.to(DEV)
+    with torch.no_grad():
+        got_self = att.self_attn[0](xd, xd, xd, attention_weights=bd, way='add', attention_mask=md, use_knn=False)
+        got_cross = att.cross_attn[0](yd, xd, xd, attention_weights=bd, way='add', attention_mask=md, use_knn=False)
+    assert got_self.shape == (1, n, 512)
+    feat(got_self[0], want_self, "dense-argument self attention")
+    feat(got_cross[0], want_cross, "dense-argument cross attention")
+    # the kernel alone: multiplicative weights and a per-head mask, float64 restatement
+    H, nq, nk = 4, 37, 53
+    q, k, v = (torch.randn(m, 256, generator=g) for m in (nq, nk, nk))
+    w = torch.rand(H, nq, nk, generator=g) + 0.5
+    mk = (torch.rand(H, nq, nk, generator=g) > 0.3).float()
+    mk[:, :, 0] = 1                                                              # no fully masked row
+    s = torch.einsum("ahd,bhd->hab", q.double().view(nq, H, 64), k.double().view(nk, H, 64)) / 8.0 * w.double()
+    s = s.masked_fill(mk == 0, float("-inf"))
+    want = torch.einsum("hab,bhd->ahd", torch.softmax(s, -1), v.double().view(nk, H, 64)).reshape(nq, 256).float()
+    got = ops.dense_attn(q.to(DEV), k.to(DEV), v.to(DEV), H, weights=w.to(DEV), way="mul", mask=mk.to(DEV))
+    assert_close(got, want, "dense attention kernel (mul weights, per-head mask)", rtol=1e-4, atol=1e-5)
+
+
+def test_module_level_swap_under_the_reference_mmg():
+    """replace ONLY the MultiHeadAttention modules of the reference's own MMG (imported from the
+    staged unmodified files) by this package's; the reference's MMG.forward then drives them with its dense mask / bias."""
+    import os
+    from conftest import ROOT
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref_dir, "src", "model", "model_utils", "network_MMG.py")):
+        pytest.skip("baseline/_ref was not staged")
+    from oracle import ref_shims
+    ref_shims.install()
+    from src.model.model_utils.network_MMG import MMG as RefMMG
+    torch.manual_seed(3)
+    ref = RefMMG(dim_node=512, dim_edge=512, dim_atten=256, depth=2, num_heads=8, aggr='max', flow='target_to_source',
+                 attention='fat', use_edge=True, DROP_OUT_ATTEN=0.5).to(DEV).eval()
+    b = synth.make_config_batch("cfg2", seed=8, num_scenes=3).to(DEV)
+    g = torch.Generator().manual_seed(4)
+    n, e = b.obj_points.shape[0], b.edge_indices.shape[1]
+    o3, o2 = torch.randn(n, 512, generator=g).to(DEV), torch.randn(n, 512, generator=g).to(DEV)
+    e3, e2 = torch.randn(e, 512, generator=g).to(DEV), torch.randn(e, 512, generator=g).to(DEV)
+    centres = b.descriptor[:, :3].contiguous()
+    args = (o3, o2, e3, e2, b.edge_indices, b.batch_ids, centres)
+    with torch.no_grad():
+        want = [t.clone() for t in ref(*args)]
+        for name in ("self_attn", "cross_attn", "cross_attn_rel"):
+            lst = getattr(ref, name)
+            for i in range(len(lst)):
+                mine = V.MultiHeadAttention(d_model=512, d_k=64, d_v=64, h=8)
+                mine.load_state_dict(lst[i].state_dict())
+                lst[i] = mine.to(DEV).eval()
+        got = ref(*args)
+    for i, (a, w) in enumerate(zip(got, want)):
+        feat(a, w, f"reference MMG with swapped attention modules, output {i}")
