@@ -95,6 +95,7 @@ SIGNATURES = {
                            i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, vp, vp],
     "vlsat_transpose": [vp, i64, i64, vp, i64, i64, i64, i64, i64, vp],
     "vlsat_act_bwd": [vp, i64, vp, i64, i32, f32, vp, vp, i64, vp, i64, i64, vp],
+    "vlsat_act_bwd_pair": [vp, i64, vp, i64, i32, f32, vp, vp, i64, vp, vp, vp, i64, i64, i64, vp],
     "vlsat_wgrad_small": [vp, i64, vp, i64, i64, i32, i32, vp, i64, vp],
     "vlsat_gather_rows": [vp, i64, vp, i32, i64, i32, vp, i64, vp],
     "vlsat_scatter_add_rows": [vp, i64, vp, i32, i64, i32, vp, i64, vp],

@@ -59,7 +59,7 @@ def weight_grad(dz: torch.Tensor, x: torch.Tensor, dz_pair=None, x_pair=None) ->
 # ------------------------------------------------------------------------------------------- projections
 class _Linear(Function):
     @staticmethod
-    def forward(ctx, x, w, bias, act, ga, ia, gb, ib, residual, scale):
+    def forward(ctx, x, w, bias, act, ga, ia, gb, ib, residual, scale, emit_pair=False):
         if (residual is not None or scale is not None) and act != ACT_NONE:
             raise ValueError("linear: residual / logit scale cannot be combined with an activation")
         gather = (ga, ia, gb, ib) if ga is not None else None
@@ -69,7 +69,13 @@ class _Linear(Function):
         pairs = _pairs_engine(n, k) and x.shape[0] > 0 and k >= 32
         xp = ops.act_pair(x) if pairs else None
         wp = ops.weight_pair(w) if pairs else None
-        y = ops.linear(x, w, bias, act=act, gather=gather, residual=residual, scale_ptr=scale, x_split=xp, w_split=wp)
+        # emit_pair: the consumer of y is another projection - its bf16 pair leaves through this GEMM's epilogue
+        emit = bool(emit_pair) and pairs and n >= 32
+        y = ops.linear(x, w, bias, act=act, gather=gather, residual=residual, scale_ptr=scale, x_split=xp, w_split=wp,
+                       emit_split="bf16" if emit else False)
+        if emit:
+            y, ypair = y
+            y._vlsat_pair = (y._version, ypair)
         ctx.act = act
         ctx.has = (bias is not None, ga is not None, gb is not None, residual is not None, scale is not None)
         ctx.shapes = (ga.shape if ga is not None else None, gb.shape if gb is not None else None)
@@ -92,13 +98,14 @@ class _Linear(Function):
         d_res = dy if (has_res and need[8]) else None
         plain = ctx.act == ACT_NONE and not has_scale
         want_db = has_b and need[2]
+        xp, wp = ctx.pairs
+        pairs = xp is not None and dy.shape[0] > 0              # dz feeds the stored-operand GEMMs: its pair comes out of this pass
         if plain:
             dz = dy
-            db = ops.act_bwd(dy, None, ACT_NONE, want_dz=False)[1] if want_db else None
+            db = ops.act_bwd(dy, None, ACT_NONE, want_dz=False, want_dbias=want_db, emit_pair=pairs)[1] if (want_db or pairs) else None
         else:
-            dz, db = ops.act_bwd(dy, y, ctx.act, want_dz=True, want_dbias=want_db, scale_ptr=scale if has_scale else None)
+            dz, db = ops.act_bwd(dy, y, ctx.act, want_dz=True, want_dbias=want_db, scale_ptr=scale if has_scale else None, emit_pair=pairs)
         dx = dw = d_ga = d_gb = None
-        xp, wp = ctx.pairs
         if xp is not None and dz.shape[0] > 0:
             dzp = ops.act_pair(dz)
             if need[0]:
@@ -115,19 +122,22 @@ class _Linear(Function):
             d_ga = ops.scatter_add_rows(dz, ia, torch.zeros(ctx.shapes[0], device=dz.device, dtype=torch.float32))
         if has_gb and need[6]:
             d_gb = ops.scatter_add_rows(dz, ib, torch.zeros(ctx.shapes[1], device=dz.device, dtype=torch.float32))
-        return dx, dw, db, None, d_ga, None, d_gb, None, d_res, d_scale
+        return dx, dw, db, None, d_ga, None, d_gb, None, d_res, d_scale, None
 
 
-def linear(x, w, bias=None, act=ACT_NONE, gather=None, residual=None, scale=None):
-    """y = act(x w^T + bias + ga[ia] + gb[ib]) (+ residual) (* exp(scale)); all tensor arguments differentiable."""
+def linear(x, w, bias=None, act=ACT_NONE, gather=None, residual=None, scale=None, emit_pair=False):
+    """y = act(x w^T + bias + ga[ia] + gb[ib]) (+ residual) (* exp(scale)); all tensor arguments differentiable.
+    ``emit_pair``: y feeds another projection directly - write its bf16 (hi, lo) pair from this GEMM's epilogue."""
     ga, ia, gb, ib = gather if gather is not None else (None, None, None, None)
-    return _Linear.apply(x, w, bias, act, ga, ia, gb, ib, residual, scale)
+    return _Linear.apply(x, w, bias, act, ga, ia, gb, ib, residual, scale, emit_pair)
 
 
 class _Relu(Function):
     @staticmethod
     def forward(ctx, x):
-        y = ops.relu(x.contiguous())
+        y, pair = ops.relu(x.contiguous(), emit_split=True)     # the next layer's projections read the pair
+        if pair is not None:
+            y._vlsat_pair = (y._version, pair)
         ctx.save_for_backward(y)
         return y
 
@@ -145,7 +155,11 @@ def relu(x):
 class _AddLayerNorm(Function):
     @staticmethod
     def forward(ctx, x, res, gamma, beta, eps, relu_out):
-        y = ops.add_layernorm(x, res, gamma, beta, eps=eps, relu=relu_out)
+        y = ops.add_layernorm(x, res, gamma, beta, eps=eps, relu=relu_out, emit_split=True)
+        if isinstance(y, tuple):                                # (y, pair or None): q / k / v and node projections read the pair
+            y, pair = y
+            if pair is not None:
+                y._vlsat_pair = (y._version, pair)
         ctx.save_for_backward(x, res, gamma, beta)
         ctx.eps, ctx.relu = eps, relu_out
         return y

@@ -8,6 +8,7 @@
 // Reference semantics: autograd of the modules cited in include/vlsat_b200.h (the reference has no hand-written
 // backward; torch.autograd over network_MMG.py / network_PointNet.py / attention.py defines it).
 #include "common.cuh"
+#include "epilogue.cuh"
 #include <float.h>
 
 namespace vlsat {
@@ -66,6 +67,55 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const
 #pragma unroll
             for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
             atomicAdd(dbias + n, s);
+        }
+    }
+}
+
+// Vectorised form (N % 4 == 0, 16-byte aligned rows): four columns per thread, and optionally the bf16 (hi, lo) pair of
+// dz written in the same pass - dz feeds the two backward GEMMs of its projection (dX = dZ W, dW = dZ^T X), which read bf16
+// pairs; emitting them here removes one split launch per projection backward.
+__global__ void act_bwd_vec_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ y, int64_t ldy,
+                                   int act, float scale, const float* __restrict__ scale_ptr, float* __restrict__ dz,
+                                   int64_t lddz, float* __restrict__ dbias, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                   int64_t ld_pair, int64_t M, int64_t N) {
+    pdl_entry();
+    __shared__ float4 part[8][33];
+    const int64_t n = ((int64_t)blockIdx.x * 32 + threadIdx.x) * 4;
+    const int64_t m0 = (int64_t)blockIdx.y * AB_ROWS;
+    const float sc = scale * (scale_ptr ? expf(__ldg(scale_ptr)) : 1.f);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N) {
+        for (int i = threadIdx.y; i < AB_ROWS; i += 8) {
+            const int64_t m = m0 + i;
+            if (m >= M) break;
+            float4 g = __ldg(reinterpret_cast<const float4*>(dy + m * lddy + n));
+            g.x *= sc; g.y *= sc; g.z *= sc; g.w *= sc;
+            if (act != VLSAT_ACT_NONE) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(y + m * ldy + n));
+                if (act == VLSAT_ACT_RELU) {
+                    if (!(t.x > 0.f)) g.x = 0.f; if (!(t.y > 0.f)) g.y = 0.f; if (!(t.z > 0.f)) g.z = 0.f; if (!(t.w > 0.f)) g.w = 0.f;
+                } else {
+                    g.x *= t.x * (1.f - t.x); g.y *= t.y * (1.f - t.y); g.z *= t.z * (1.f - t.z); g.w *= t.w * (1.f - t.w);
+                }
+            }
+            if (dz) *reinterpret_cast<float4*>(dz + m * lddz + n) = g;
+            if (hi) {
+                uint32_t h0, l0, h1, l1;
+                split_bf16x2(g.x, g.y, h0, l0); split_bf16x2(g.z, g.w, h1, l1);
+                *reinterpret_cast<uint2*>(hi + m * ld_pair + n) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(lo + m * ld_pair + n) = make_uint2(l0, l1);
+            }
+            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        }
+    }
+    if (dbias) {
+        part[threadIdx.y][threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.y == 0 && n < N) {
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float4 t = part[i][threadIdx.x]; s4.x += t.x; s4.y += t.y; s4.z += t.z; s4.w += t.w; }
+            atomicAdd(dbias + n, s4.x); atomicAdd(dbias + n + 1, s4.y); atomicAdd(dbias + n + 2, s4.z); atomicAdd(dbias + n + 3, s4.w);
         }
     }
 }
@@ -603,6 +653,23 @@ extern "C" int vlsat_act_bwd(const float* dy, int64_t lddy, const float* y, int6
     VLSAT_SUPPORT(ceil_div(M, AB_ROWS) <= 65535);
     dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, AB_ROWS));
     launch_k(act_bwd_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, dy, lddy, y, ldy, act, scale, scale_ptr, dz, lddz, dbias, M, N);
+    return finish_launch();
+}
+
+extern "C" int vlsat_act_bwd_pair(const float* dy, int64_t lddy, const float* y, int64_t ldy, int act, float scale,
+                                  const float* scale_ptr, float* dz, int64_t lddz, float* dbias, void* split_hi, void* split_lo,
+                                  int64_t ld_split, int64_t M, int64_t N, void* stream) {
+    VLSAT_REQUIRE(M >= 0 && N >= 0 && act >= VLSAT_ACT_NONE && act <= VLSAT_ACT_SIGMOID);
+    if (M == 0 || N == 0) return VLSAT_OK;
+    VLSAT_REQUIRE(dy && lddy >= N && (dz || dbias || split_hi) && (!dz || lddz >= N) && (act == VLSAT_ACT_NONE || (y && ldy >= N)));
+    VLSAT_REQUIRE((split_hi == nullptr) == (split_lo == nullptr) && (!split_hi || ld_split >= N));
+    VLSAT_SUPPORT(ceil_div(M, AB_ROWS) <= 65535);
+    const uintptr_t al = (uintptr_t)dy | (uintptr_t)y | (uintptr_t)dz;
+    VLSAT_SUPPORT(N % 4 == 0 && lddy % 4 == 0 && (act == VLSAT_ACT_NONE || ldy % 4 == 0) && (!dz || lddz % 4 == 0) && (al & 15) == 0);
+    VLSAT_SUPPORT(!split_hi || (ld_split % 4 == 0 && (((uintptr_t)split_hi | (uintptr_t)split_lo) & 7) == 0));
+    dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(M, AB_ROWS));
+    launch_k(act_bwd_vec_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, dy, lddy, y, ldy, act, scale, scale_ptr, dz, lddz, dbias,
+             (uint16_t*)split_hi, (uint16_t*)split_lo, ld_split, M, N);
     return finish_launch();
 }
 

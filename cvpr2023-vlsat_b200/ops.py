@@ -858,13 +858,36 @@ def transpose(x: torch.Tensor, mult: int = 4) -> torch.Tensor:
 
 
 def act_bwd(dy: torch.Tensor, y: Optional[torch.Tensor], act: int, want_dz: bool = True, want_dbias: bool = True,
-            scale: float = 1.0, scale_ptr: Optional[torch.Tensor] = None):
-    """(dz, dbias): dz = dy * act'(y) * scale * exp(scale_ptr), dbias = column sums of dz."""
+            scale: float = 1.0, scale_ptr: Optional[torch.Tensor] = None, emit_pair: bool = False):
+    """(dz, dbias): dz = dy * act'(y) * scale * exp(scale_ptr), dbias = column sums of dz. ``emit_pair``: the same pass also
+    writes the bf16 (hi, lo) pair of dz - the operand of the backward GEMMs that read it next - and remembers it on the
+    returned tensor (on ``dy`` itself when the activation is the identity and no dz is written): ``act_pair`` finds it."""
     dp, lddy = _rows(dy, "dy")
     m, n = dy.shape
     yp, ldy = (None, 0) if y is None else _rows(y, "y")
     dz = torch.empty((m, n), device=dy.device, dtype=torch.float32) if want_dz else None
     db = torch.zeros((n,), device=dy.device, dtype=torch.float32) if want_dbias else None
+    vec = (n % 4 == 0 and lddy % 4 == 0 and (y is None or ldy % 4 == 0) and dp % 16 == 0 and (yp is None or yp % 16 == 0) and m > 0)
+    if vec:
+        pair = None
+        if emit_pair and n % 8 == 0 and tensor_cores_enabled() and default_fmt(n) == FMT_BF16:
+            pair = torch.empty((2, m, n), device=dy.device, dtype=torch.bfloat16)
+        if dz is None and db is None and pair is None:
+            return dz, db
+        _lib.check(_call("vlsat_act_bwd_pair", dp, lddy, yp, ldy, act, scale, scale_ptr.data_ptr() if scale_ptr is not None else None,
+                         dz.data_ptr() if want_dz else None, n, db.data_ptr() if want_dbias else None,
+                         pair[0].data_ptr() if pair is not None else None, pair[1].data_ptr() if pair is not None else None, n, m, n,
+                         _stream()), "vlsat_act_bwd_pair")
+        if pair is not None:
+            owner = dz if dz is not None else (dy if (act == ACT_NONE and scale == 1.0 and scale_ptr is None) else None)
+            if owner is not None:
+                try:
+                    owner._vlsat_pair = (owner._version, (pair[0], pair[1]))
+                except AttributeError:
+                    pass
+        return dz, db
+    if dz is None and db is None:
+        return dz, db
     _lib.check(_call("vlsat_act_bwd", dp, lddy, yp, ldy, act, scale, scale_ptr.data_ptr() if scale_ptr is not None else None,
                      dz.data_ptr() if want_dz else None, n, db.data_ptr() if want_dbias else None, m, n, _stream()), "vlsat_act_bwd")
     return dz, db

@@ -40,7 +40,7 @@ def pointnet_feat(m, x: torch.Tensor) -> torch.Tensor:
     b1, b2, b3 = m.conv1.bias, m.conv2.bias, m.conv3.bias
     if x.shape[2] == 1:
         h = A.linear(x.reshape(x.shape[0], x.shape[1]).contiguous(), w1, b1, RELU)
-        h = A.linear(h, w2, b2, RELU)
+        h = A.linear(h, w2, b2, RELU, emit_pair=True)
         return A.linear(h, w3, b3, RELU)
     return A.pointnet(x.contiguous(), w1, b1, w2, b2, w3, b3)
 
@@ -48,7 +48,7 @@ def pointnet_feat(m, x: torch.Tensor) -> torch.Tensor:
 def rel_classifier(m, x: torch.Tensor) -> torch.Tensor:
     """PointNetRelClsMulti.forward (network_PointNet.py:328-341): fc1 ReLU fc2 Dropout ReLU fc3 sigmoid. Dropout and ReLU
     commute (both are non-negative scalings), so the ReLU sits in the projection epilogue."""
-    h = A.linear(x, m.fc1.weight, m.fc1.bias, RELU)
+    h = A.linear(x, m.fc1.weight, m.fc1.bias, RELU, emit_pair=True)
     h = A.linear(h, m.fc2.weight, m.fc2.bias, RELU)
     if m.use_drop_out:
         h = A.dropout(h, m.dropout.p, m.training)
@@ -145,7 +145,7 @@ def edge_attention(m, x, edge, g: GraphContext, x_value=None, aggr=None):
     w1, w2 = m.nn_edge[0], m.nn_edge[2]
     a_src = A.linear(x, w1.weight[:, :Dn])
     b_dst = A.linear(xv, w1.weight[:, Dn + De:])
-    h1 = A.linear(edge, w1.weight[:, Dn:Dn + De], w1.bias, RELU, gather=(a_src, g.src, b_dst, g.dst))
+    h1 = A.linear(edge, w1.weight[:, Dn:Dn + De], w1.bias, RELU, gather=(a_src, g.src, b_dst, g.dst), emit_pair=True)
     new_edge = A.linear(h1, w2.weight, w2.bias)
     # attention MLP over rows (e, h)
     convs = m._convs()
@@ -173,7 +173,7 @@ def gat_layer(layer, x, edge, g: GraphContext, relu_nodes: bool = False):
     """GraphEdgeAttenNetwork.forward on CSR-ordered edges (network_MMG.py:34-41)."""
     xx, new_edge, prob = edge_attention(layer.edgeatten, x, edge, g)
     p0, p2 = layer.prop[0], layer.prop[2]
-    hid = A.linear(torch.cat([x, xx], 1), p0.weight, p0.bias, RELU)
+    hid = A.linear(torch.cat([x, xx], 1), p0.weight, p0.bias, RELU, emit_pair=True)
     out = A.linear(hid, p2.weight, p2.bias, RELU if relu_nodes else NONE)
     return out, new_edge, prob
 

@@ -341,6 +341,12 @@ int vlsat_transpose(const float* in, int64_t ld_in, int64_t batch_stride_in, flo
  * (nullable, accumulated). nn.Linear + ReLU / sigmoid sites: network_PointNet.py:328-341, network_MMG.py:31-32,59-60. */
 int vlsat_act_bwd(const float* dy, int64_t lddy, const float* y, int64_t ldy, int act, float scale,
                   const float* scale_ptr, float* dz, int64_t lddz, float* dbias, int64_t M, int64_t N, void* stream);
+/* Same, four columns per thread (N % 4 == 0, 16-byte aligned rows), optionally writing the bf16 (hi, lo) pair of dz in the
+ * same pass (row stride ld_split): the operand format of the two backward GEMMs that read dz next (vlsat_gemm_pairs).
+ * dz, dbias and the pair are each nullable (at least one must be given). */
+int vlsat_act_bwd_pair(const float* dy, int64_t lddy, const float* y, int64_t ldy, int act, float scale,
+                       const float* scale_ptr, float* dz, int64_t lddz, float* dbias, void* split_hi, void* split_lo,
+                       int64_t ld_split, int64_t M, int64_t N, void* stream);
 
 /* Weight gradient of a small projection over a tall operand pair: dw[n, k] += sum_m dz[m, n] * x[m, k] (accumulated),
  * N, K <= 128 (the per-(edge, head) attention MLP network_MMG.py:73 and the PointNet convs network_PointNet.py:99-100,
