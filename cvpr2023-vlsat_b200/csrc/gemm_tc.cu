@@ -485,8 +485,10 @@ static void pick_reduction_split(int64_t M, int64_t N, int bn, int64_t num_kb, i
         const int64_t per = ceil_div(num_kb, s);
         if (ceil_div(num_kb, per) != s) continue;                // same blocks per split as a smaller s: skip
         const double waves = (double)ceil_div(tiles * s, kNumSMs);
-        // K blocks per wave + tile prologue / epilogue (~8 blocks' worth) + writing and summing the slabs
-        const double cost = waves * ((double)per + 8.0) + (s > 1 ? 6.0 + 0.1 * s : 0.0);
+        // K blocks per wave + tile prologue / epilogue (~8 blocks' worth) + writing and summing the slabs (the sum is its own
+        // launch: ~8.5 us in the ncu launch list of a training step = 14 K blocks; 95 of them per step cost 0.8 ms when the
+        // penalty was 6, so split only where it pays for that)
+        const double cost = waves * ((double)per + 8.0) + (s > 1 ? 14.0 + 0.1 * s : 0.0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
     }
     *splits = best;
