@@ -68,9 +68,10 @@ def set_timer(t: Optional[KernelTimer]) -> None:
     _timer = t
 
 
-def _call(name: str, *args, work=(0.0, 0.0)):
+def _call(name: str, *args, work=(0.0, 0.0), tag: str = ""):
     """One C-ABI call. ``work`` = (algorithmic FLOPs, algorithmic HBM bytes) of this launch, used only
-    by the optional timer (definitions: DESIGN.md section 'Kernels and their rooflines')."""
+    by the optional timer (definitions: DESIGN.md section 'Kernels and their rooflines'); ``tag`` distinguishes the kernel
+    instantiations behind one entry point in the timer's table (e.g. the 128x128 and 128x64 tile kernels of the projections)."""
     fn = getattr(_lib.load(), name)
     if _timer is None:
         return fn(*args)
@@ -78,7 +79,7 @@ def _call(name: str, *args, work=(0.0, 0.0)):
     a.record()
     st = fn(*args)
     b.record()
-    _timer.events.append((name, a, b, float(work[0]), float(work[1])))
+    _timer.events.append((name + tag, a, b, float(work[0]), float(work[1])))
     return st
 
 
@@ -348,8 +349,15 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
             opts.workspace, opts.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     elif x_pair_only:
         raise RuntimeError("linear: a pre-split activation can only feed the tensor-core engine")
+    # which kernel runs (csrc/gemm_tc.cu linear_tc): 128 x 64 tiles for narrow outputs and for problems whose 128 x 128 tiling
+    # would leave more than half of the SMs idle, 128 x 128 tiles otherwise; the FFMA engine for shapes pairs cannot address
+    if opts.engine == ENGINES["simt"]:
+        tag = "[ffma]"
+    else:
+        tiles128 = ((m + 127) // 128) * ((n + 127) // 128)
+        tag = "[128x64]" if (n <= 64 or 2 * tiles128 <= 148) else "[128x128]"
     st = _call("vlsat_linear_fwd", xp, ldx, wp, ldw, yp, ldy, m, n, k, C.byref(epi), C.byref(opts), _stream(),
-               work=(2.0 * m * n * k, 4.0 * (m * k + n * k + m * n)))
+               work=(2.0 * m * n * k, 4.0 * (m * k + n * k + m * n)), tag=tag)
     _lib.check(st, "vlsat_linear_fwd")
     if emit_split:
         return out, (y_split[0], y_split[1])
