@@ -132,6 +132,7 @@ SIGNATURES = {
     "vlsat_topk_triplet_ranks": [vp, i64, i32, vp, i32, vp, vp, vp, i64, i32, f32, vp, vp],
     "vlsat_recall_at": [vp, i64, i32, i32, i32, vp, vp],
     "vlsat_adamw_step": [vp, vp, vp, i64, i32, C.c_double, C.c_double, f32, vp, i64, vp],
+    "vlsat_rel_text_embed": [vp, i32, i32, i32, vp, vp, i64, vp, i64, vp, i64, vp],
     "vlsat_pack_scale": [vp, vp, vp, i64, i32, f32, vp],
 }
 _RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_gemm_pairs_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_bwd_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}

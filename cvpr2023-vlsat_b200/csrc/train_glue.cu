@@ -263,6 +263,46 @@ __global__ void pack_scale_kernel(const vlsat_copy_tensor* __restrict__ tab, con
     }
     for (int64_t i = i0 + threadIdx.x; i < end; i += blockDim.x) T.dst[i] = T.src[i] * scale;
 }
+// N4: the text supervision target of an edge from a cached table of prompt features (get_rel_emb, SGFN_MMG/model.py:221-255):
+// mean over the edge's ground-truth predicates of table[cls[subject], cls[object], r, :] (row R = "no relation" when it has
+// none), then L2 normalisation. One warp per edge, D / 32 features per lane, fixed summation order.
+template <int PER>
+__global__ void rel_text_embed_kernel(const float* __restrict__ table, int n_obj, int n_rel, const int64_t* __restrict__ gt_cls,
+                                      const float* __restrict__ gt_rel, int64_t ld_rel, const int64_t* __restrict__ edges,
+                                      int64_t E, float* __restrict__ out, int64_t ld_out) {
+    pdl_entry();
+    const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= E) return;
+    const int lane = threadIdx.x & 31;
+    constexpr int D = PER * 32;
+    const int64_t s = gt_cls[edges[2 * e]], o = gt_cls[edges[2 * e + 1]];
+    const float* base = table + ((s * n_obj + o) * (int64_t)(n_rel + 1)) * D;
+    float acc[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) acc[i] = 0.f;
+    int cnt = 0;
+    for (int r = 0; r < n_rel; ++r) {
+        if (gt_rel[e * ld_rel + r] == 1.f) {                     // warp-uniform
+            ++cnt;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) acc[i] += __ldg(base + (int64_t)r * D + lane + 32 * i);
+        }
+    }
+    if (cnt == 0) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) acc[i] = __ldg(base + (int64_t)n_rel * D + lane + 32 * i);
+    } else {
+        const float inv = 1.f / (float)cnt;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) acc[i] *= inv;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) ss += acc[i] * acc[i];
+    const float rn = 1.f / sqrtf(warp_sum(ss));
+#pragma unroll
+    for (int i = 0; i < PER; ++i) out[e * ld_out + lane + 32 * i] = acc[i] * rn;
+}
 __global__ void bump_step_kernel(int64_t* step) {
     pdl_entry();
     if (threadIdx.x == 0 && blockIdx.x == 0) step[0] += 1;
@@ -381,5 +421,20 @@ extern "C" int vlsat_pack_scale(const vlsat_copy_tensor* tensors, const int32_t*
     if (n_chunks == 0) return VLSAT_OK;
     VLSAT_REQUIRE(tensors && chunk_tensor && chunk_index);
     launch_k(pack_scale_kernel, dim3((unsigned)n_chunks), dim3(256), 0, (cudaStream_t)stream, tensors, chunk_tensor, chunk_index, chunk_elems, scale);
+    return finish_launch();
+}
+
+extern "C" int vlsat_rel_text_embed(const float* table, int n_obj_cls, int n_rel_cls, int dim, const int64_t* gt_cls,
+                                    const float* gt_rel, int64_t ld_rel, const int64_t* edges, int64_t E, float* out,
+                                    int64_t ld_out, void* stream) {
+    VLSAT_REQUIRE(E >= 0 && n_obj_cls >= 1 && n_rel_cls >= 1 && ld_rel >= n_rel_cls && ld_out >= dim);
+    if (E == 0) return VLSAT_OK;
+    VLSAT_REQUIRE(table && gt_cls && gt_rel && edges && out);
+    VLSAT_SUPPORT(dim == 512 || dim == 768 || dim == 256);
+    dim3 grid((unsigned)ceil_div(E, 8)), block(256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dim == 512) launch_k(rel_text_embed_kernel<16>, grid, block, 0, st, table, n_obj_cls, n_rel_cls, gt_cls, gt_rel, ld_rel, edges, E, out, ld_out);
+    else if (dim == 768) launch_k(rel_text_embed_kernel<24>, grid, block, 0, st, table, n_obj_cls, n_rel_cls, gt_cls, gt_rel, ld_rel, edges, E, out, ld_out);
+    else launch_k(rel_text_embed_kernel<8>, grid, block, 0, st, table, n_obj_cls, n_rel_cls, gt_cls, gt_rel, ld_rel, edges, E, out, ld_out);
     return finish_launch();
 }

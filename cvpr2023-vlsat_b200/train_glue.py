@@ -321,6 +321,63 @@ def build_optimizer(model: torch.nn.Module, lr: float = 1e-4, weight_decay=False
     return FusedAdamW(reference_param_groups(model, lr, weight_decay, amsgrad), t_max=max_iteration)
 
 
+# ------------------------------------------------------------------------------------- N4: cached text supervision
+class RelTextCache:
+    """``Mmgnet.get_rel_emb`` (SGFN_MMG/model.py:221-255) without the per-step python loop and text-encoder call: the
+    features of every prompt the function can build are computed ONCE into a table [S, O, R + 1, D] (160 * 160 * 27 prompts
+    for mmgnet.json = 1.4 GB fp32), and the target of a batch is one gather-mean-normalise kernel (``vlsat_rel_text_embed``).
+
+    ``fill(encode)`` takes any ``encode(list_of_prompts) -> [n, D]`` (the reference's: ``lambda p: clip_model.encode_text(
+    clip.tokenize(p).cuda())``; CLIP weights are not available offline, so this package ships none). ``from_table`` adopts
+    a table computed elsewhere. ``__call__(gt_cls, gt_rel_cls, edge_indices [E, 2])`` -> [E, D] fp32, the ``rel_text_feat``
+    argument of ``reference_loss`` / ``TrainStep.step``."""
+
+    def __init__(self, obj_names, rel_names, dim: int = 512, device="cuda"):
+        self.obj_names, self.rel_names, self.dim = list(obj_names), list(rel_names), dim
+        self.table = torch.zeros((len(self.obj_names), len(self.obj_names), len(self.rel_names) + 1, dim), device=device, dtype=torch.float32)
+        self.filled = False
+
+    @classmethod
+    def from_table(cls, table: torch.Tensor):
+        s, o, r1, d = table.shape
+        me = cls([None] * s, [None] * (r1 - 1), d, table.device)
+        me.table, me.filled = table.to(torch.float32).contiguous(), True
+        return me
+
+    def prompts(self, s: int):
+        """The (O * (R + 1)) prompts of subject class ``s`` in table order (:232-240)."""
+        a = self.obj_names[s]
+        out = []
+        for b in self.obj_names:
+            out += [f"a point cloud of a {a} {rel} a {b}" for rel in self.rel_names]
+            out.append(f"the {a} and the {b} has no relation in the point cloud")
+        return out
+
+    def fill(self, encode, batch: int = 4096) -> "RelTextCache":
+        o, r1 = len(self.obj_names), len(self.rel_names) + 1
+        with torch.no_grad():
+            for s in range(len(self.obj_names)):
+                p = self.prompts(s)
+                feats = torch.cat([encode(p[i:i + batch]).to(self.table.device, torch.float32) for i in range(0, len(p), batch)])
+                self.table[s] = feats.view(o, r1, self.dim)
+        self.filled = True
+        return self
+
+    def __call__(self, gt_cls: torch.Tensor, gt_rel_cls: torch.Tensor, edge_indices: torch.Tensor) -> torch.Tensor:
+        if not self.filled:
+            raise RuntimeError("RelTextCache: fill(encode) or from_table(...) first (no text encoder ships with vlsat_b200)")
+        if edge_indices.dim() != 2 or edge_indices.shape[1] != 2:
+            raise ValueError("edge_indices must be [E, 2] (subject, object) as process_train holds them")
+        e = edge_indices.shape[0]
+        rel = gt_rel_cls.to(torch.float32).contiguous()
+        ed, cls_ = edge_indices.to(torch.int64).contiguous(), gt_cls.to(torch.int64).contiguous()
+        out = torch.empty((e, self.dim), device=self.table.device, dtype=torch.float32)
+        s, o, r1, d = self.table.shape
+        _lib.check(ops._call("vlsat_rel_text_embed", self.table.data_ptr(), s, r1 - 1, d, cls_.data_ptr(), rel.data_ptr(), rel.stride(0) if e else r1 - 1,
+                         ed.data_ptr(), e, out.data_ptr(), d, ops._stream()), "vlsat_rel_text_embed")
+        return out
+
+
 # --------------------------------------------------------------------------------------------------------- train step
 class TrainStep:
     """One ``process_train`` iteration up to and including ``self.backward(loss)`` (SGFN_MMG/model.py:337-413, 483-488):

@@ -490,6 +490,15 @@ int vlsat_adamw_step(const vlsat_adamw_tensor* tensors, const int32_t* chunk_ten
                      int64_t n_chunks, int chunk_elems, double beta1, double beta2, float eps, int64_t* step,
                      int64_t t_max, void* stream);
 
+/* N4: text supervision target of get_rel_emb (SGFN_MMG/model.py:221-255) from a CACHED table of prompt features
+ * instead of a python loop + CLIP text encoder per step. table [S, O, R + 1, dim] fp32: features of "a point cloud of a {s}
+ * {rel} a {o}" at [s, o, r] and of "the {s} and the {o} has no relation in the point cloud" at [s, o, R] (filled once by the
+ * caller's text encoder). out[e] = normalise(mean over the ground-truth predicates of edge e), or the no-relation row;
+ * edges [E, 2] int64 (subject, object), gt_rel [E, R] 0/1. dim in {256, 512, 768}. */
+int vlsat_rel_text_embed(const float* table, int n_obj_cls, int n_rel_cls, int dim, const int64_t* gt_cls,
+                         const float* gt_rel, int64_t ld_rel, const int64_t* edges, int64_t E, float* out,
+                         int64_t ld_out, void* stream);
+
 /* Data-parallel training (the reference is single-process, SGFN_MMG/model.py:483-488 runs backward() and
  * optimizer.step() back to back): dst_t = scale * src_t for every tensor of a table in ONE launch - packs a step's
  * gradients into the flat buffer the NCCL all-reduce runs on, with 1 / world_size folded in. */

@@ -202,3 +202,26 @@ def eval_inputs(name: str, num_obj: int = 160, num_rel: int = 26):
     logits[0, gt_cls[0]] = logits[0].max() + 1                   # rank 1
     logits[1, gt_cls[1]] = logits[1].min() - 1                   # beyond top-k
     return logits, rel, gt_cls, gt_rel, edges
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N4: CLIP text supervision. name -> (object classes, predicate classes, nodes, edges, seed)
+TEXT_CASES = {"text_small": (7, 5, 12, 40, 3), "text_mmgnet_vocab": (160, 26, 40, 600, 4)}
+
+
+def text_table(n_obj_cls: int, n_rel_cls: int, seed: int, dim: int = 512) -> torch.Tensor:
+    """Seeded stand-in for the CLIP text features of every prompt get_rel_emb can build: [S, O, R + 1, dim], slot R = the
+    "no relation" prompt (SGFN_MMG/model.py:232-240)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    return torch.randn(n_obj_cls, n_obj_cls, n_rel_cls + 1, dim, generator=g)
+
+
+def text_inputs(name: str):
+    """(gt_cls [N] int64, gt_rel_cls [E, R] float 0/1 with label-free, single- and multi-label edges, edges [E, 2] int64)."""
+    n_obj_cls, n_rel_cls, n_nodes, n_edges, seed = TEXT_CASES[name]
+    g = torch.Generator().manual_seed(2000 + seed)
+    gt_cls = torch.randint(0, n_obj_cls, (n_nodes,), generator=g)
+    gt_rel = (torch.rand(n_edges, n_rel_cls, generator=g) < 1.5 / n_rel_cls).float()
+    gt_rel[::5] = 0                                              # label-free edges
+    edges = torch.randint(0, n_nodes, (n_edges, 2), generator=g)
+    return gt_cls, gt_rel, edges
