@@ -487,42 +487,7 @@ def run_b200(args):
             stats[id(b)] = T.scene_stats(b.batch_ids)
         return stats[id(b)]
     if not args.no_train:
-        model.train()
         A.DropoutState.manual_seed(1234 + rank)
-        if args.metric == "fwd":
-            cot = None
-
-            def loss_fn(outs):        # fixed cotangents stand in for the losses in this leg
-                nonlocal cot
-                if cot is None:
-                    gen = torch.Generator(device=dev).manual_seed(5)
-                    cot = [torch.randn(o.shape, device=dev, generator=gen) / o.numel() for o in outs[:7]]
-                return sum((o * c).sum() for o, c in zip(outs[:7], cot))
-            model.zero_grad(set_to_none=True)
-            loss_fn(model(*resident[0].forward_args(), istrain=True)).backward()       # creates the cotangents outside the capture
-            graphed_train = V.GraphedTrainStep(model, loss_fn)
-            reducer = vd.GradientAllReducer(model.parameters())
-
-            def fb_step(i):
-                b = resident[i % n_batches]
-                if args.eager:
-                    model.zero_grad(set_to_none=True)
-                    loss_fn(model(*b.forward_args(), istrain=True)).backward()
-                else:
-                    graphed_train(*b.forward_args(), scene_stats=stats_of(b))
-                reducer.allreduce()
-            l0 = ops.launch_count()
-            tms = timed_device(fb_step, n_train, 2)
-            fb_launches = (ops.launch_count() - l0) if args.eager else graphed_train.kernels_per_replay * n_train
-            fwd_bwd = {"value": round(world * scenes * n_train / (tms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(tms / n_train, 3),
-                       "steps": n_train, "gpu_launches": fb_launches, "grad_allreduce_bytes_per_step": reducer.last_bytes if world > 1 else 0,
-                       "mode": "train(): dropout on, BatchNorm batch statistics, forward(istrain=True) + backward of a fixed-cotangent "
-                               "scalar, " + ("eager launches" if args.eager else "one CUDA graph replay per step") + (", NCCL all-reduce (mean) of all gradients" if world > 1 else "")}
-            train_scalars["fwd_bwd_ms"] = fwd_bwd["ms_per_step"]
-            train_scalars["fwd_bwd_scenes_per_s"] = fwd_bwd["value"]
-            model.zero_grad(set_to_none=True)
-            del graphed_train, reducer
-            torch.cuda.empty_cache()
         # ---- full training step: the same forward + backward driven by the reference's losses
         # (process_train, SGFN_MMG/model.py:343-412) and followed by its optimiser step (AdamW, 13 groups, cosine schedule)
         try:
@@ -541,6 +506,19 @@ def run_b200(args):
             ts = G.TrainStep(tmodel, opt, reducer=treducer, graphed=not args.eager)
             full_step = lambda b: ts.step(*b.forward_args(), *targets_of(b), scene_stats=stats_of(b))
             first_loss = float(full_step(resident[0])[0].item())
+            if args.metric == "fwd":
+                # forward + backward alone: the same captured step (train-mode forward, the reference's six loss terms,
+                # backward) without the collective and the optimiser - ONE training graph per process serves both legs (a
+                # second training graph captured in the same process replays ~2 ms slower)
+                fb = lambda i: ts.forward_backward(*resident[i % n_batches].forward_args(), *targets_of(resident[i % n_batches]),
+                                                   scene_stats=stats_of(resident[i % n_batches]))
+                fb_ms = timed_device(fb, n_train, 2)
+                fwd_bwd = {"value": round(world * scenes * n_train / (fb_ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(fb_ms / n_train, 3),
+                           "steps": n_train, "gpu_launches": (ts.kernels_per_step - 2) * n_train,
+                           "mode": "train(): dropout on, BatchNorm batch statistics, forward(istrain=True) + the reference's six loss terms + backward, "
+                                   + ("eager launches" if args.eager else "one CUDA graph replay per step") + "; no collective, no optimiser"}
+                train_scalars["fwd_bwd_ms"] = fwd_bwd["ms_per_step"]
+                train_scalars["fwd_bwd_scenes_per_s"] = fwd_bwd["value"]
             l0 = ops.launch_count()
             tms = timed_device(lambda i: full_step(resident[i % n_batches]), n_train, 2)
             last_loss = float(full_step(resident[0])[0].item())
@@ -594,8 +572,6 @@ def run_b200(args):
         except Exception as exc:          # the forward numbers above stay valid; rank-local failures are reported, not fatal
             train_line = {"error": f"{type(exc).__name__}: {exc}"[:300]}
             train_scalars["train_step_error"] = train_line["error"]
-        model.zero_grad(set_to_none=True)
-        model.eval()
 
     # ================= per-kernel pass for the roofline (rank 0) =================
     roofline, kernels = None, {}

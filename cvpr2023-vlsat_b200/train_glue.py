@@ -409,6 +409,18 @@ class TrainStep:
         return loss
 
     def step(self, obj_points, obj_2d_feats, edge_index, descriptor, batch_ids, gt_cls, gt_rel_cls, rel_text_feat, scene_stats=None):
+        loss = self.forward_backward(obj_points, obj_2d_feats, edge_index, descriptor, batch_ids, gt_cls, gt_rel_cls, rel_text_feat,
+                                     scene_stats=scene_stats)
+        if self.reducer is not None:
+            self.reducer.allreduce()
+        self.optimizer.step()
+        if self._graphed is None:
+            self.optimizer.zero_grad(set_to_none=True)       # graph replays overwrite their static gradient buffers
+        return loss, self.terms
+
+    def forward_backward(self, obj_points, obj_2d_feats, edge_index, descriptor, batch_ids, gt_cls, gt_rel_cls, rel_text_feat, scene_stats=None):
+        """forward(istrain=True) -> the six loss terms -> loss.backward(): everything of ``step`` before the collective and the
+        optimiser (one CUDA graph replay). Every parameter's ``.grad`` holds this batch's gradient afterwards."""
         targets = (gt_cls, gt_rel_cls, rel_text_feat)
         if self._graphed is not None:
             key = tuple((tuple(t.shape), t.dtype) for t in targets) + (tuple(edge_index.shape), tuple(obj_points.shape))
@@ -425,12 +437,7 @@ class TrainStep:
             outs = self.model(obj_points, obj_2d_feats, edge_index, descriptor, batch_ids, istrain=True)
             loss = self._loss(outs)
             loss.backward()
-        if self.reducer is not None:
-            self.reducer.allreduce()
-        self.optimizer.step()
-        if self._graphed is None:
-            self.optimizer.zero_grad(set_to_none=True)       # graph replays overwrite their static gradient buffers
-        return loss, self.terms
+        return loss
 
     @property
     def kernels_per_step(self) -> int:
