@@ -148,15 +148,21 @@ class MultiHeadAttention(nn.Module):
                 # L2-bandwidth bound and bf16 pairs halve its traffic (csrc/flash_attn_bf16.cu)
                 if kv_split is None:
                     kv_split = ops.split_pair(kv_in)
-                _, q = ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach(), x_split=q_split, emit_split="bf16", want_y=False)
-                _, k = ops.linear(kv_in, a.fc_k.weight.detach(), a.fc_k.bias.detach(), x_split=kv_split, emit_split="bf16", want_y=False)
-                if nk % 8 == 0:
-                    _, vt = ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), bias_per_row=True, x_is_weight=True,
-                                       w_split=kv_split, emit_split="bf16", want_y=False)
-                else:
-                    vt = torch.empty((a.h * a.d_v, (nk + 3) // 4 * 4), device=q_in.device, dtype=torch.float32)
-                    ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), out=vt[:, :nk], bias_per_row=True,
-                               x_is_weight=True, w_split=kv_split)
+                def project_q():
+                    return ops.linear(q_in, a.fc_q.weight.detach(), a.fc_q.bias.detach(), x_split=q_split, emit_split="bf16", want_y=False)[1]
+
+                def project_kv():
+                    _, k_ = ops.linear(kv_in, a.fc_k.weight.detach(), a.fc_k.bias.detach(), x_split=kv_split, emit_split="bf16", want_y=False)
+                    if nk % 8 == 0:
+                        _, vt_ = ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), bias_per_row=True, x_is_weight=True,
+                                            w_split=kv_split, emit_split="bf16", want_y=False)
+                    else:
+                        vt_ = torch.empty((a.h * a.d_v, (nk + 3) // 4 * 4), device=q_in.device, dtype=torch.float32)
+                        ops.linear(a.fc_v.weight.detach(), kv_in, a.fc_v.bias.detach(), out=vt_[:, :nk], bias_per_row=True,
+                                   x_is_weight=True, w_split=kv_split)
+                    return k_, vt_
+                # the query projection (2D edges) next to the key / value projections (3D edges): independent, two streams
+                q, (k, vt) = ops.fork_join(project_q, project_kv, q_in.device)
                 att = ops.flash_attn_bf16(q, k, vt, nk, a.h)
                 return self._finish(q_in, att, relu, out, emit_split)
             if kv_split is None or ops.pair_fmt(kv_split) != ops.FMT_TF32:

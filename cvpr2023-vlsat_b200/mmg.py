@@ -20,22 +20,12 @@ from .attention import MultiHeadAttention, SceneContext
 from .gat import GraphContext, GraphEdgeAttenNetwork
 
 
-_side_streams = {}
-
-
 def _two_streams() -> bool:
-    """The two modality branches of a layer run on two streams (default; VLSAT_STREAMS=1 serialises them). Off while the
-    per-kernel timer is active, whose events must bracket serial execution. Round 2 on a B200: the GPU suite is green
-    with it and the config #2 forward drops from 2.78 to 2.63 ms (gpurun_out/r2_bench0*.json)."""
-    import os
-    return os.environ.get("VLSAT_STREAMS", "2") == "2" and ops._timer is None
+    return ops.two_streams()
 
 
 def _side_stream(device) -> torch.cuda.Stream:
-    key = str(device)
-    if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=device)
-    return _side_streams[key]
+    return ops.side_stream(device)
 
 
 def _bias_mlp(num_heads: int) -> nn.Sequential:

@@ -176,8 +176,8 @@ class Mmgnet(nn.Module):
 
         edge_feature = ops.edge_descriptor(descriptor.contiguous(), edge_indices.contiguous())   # [E, 11]
         ef = edge_feature.unsqueeze(-1)
-        rel_feature_2d = self.rel_encoder_2d(ef)
-        rel_feature_3d = self.rel_encoder_3d(ef)
+        # the two relationship encoders read the same input and are independent: two streams (ops.fork_join)
+        rel_feature_2d, rel_feature_3d = ops.fork_join(lambda: self.rel_encoder_2d(ef), lambda: self.rel_encoder_3d(ef), ef.device)
 
         obj_2d = self.clip_adapter(obj_2d_feats.contiguous())
         obj_features_2d_mimic = obj_2d.clone() if istrain else None
@@ -198,8 +198,8 @@ class Mmgnet(nn.Module):
             gcn_edge_feature_2d_dis = ops.linear(h, p3.weight.detach(), p3.bias.detach())
 
         ge3p, ge2p = getattr(self.mmg, "last_edge_pairs", (None, None))
-        rel_cls_3d = self.rel_predictor_3d(ge3, x_split=ge3p)
-        rel_cls_2d = self.rel_predictor_2d(ge2, x_split=ge2p)
+        rel_cls_2d, rel_cls_3d = ops.fork_join(lambda: self.rel_predictor_2d(ge2, x_split=ge2p),
+                                               lambda: self.rel_predictor_3d(ge3, x_split=ge3p), ge3.device)
         self.mmg.last_edge_pairs = (None, None)
 
         scale = self.obj_logit_scale.detach().reshape(1)

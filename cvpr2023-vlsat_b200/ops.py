@@ -83,6 +83,45 @@ def _call(name: str, *args, work=(0.0, 0.0), tag: str = ""):
     return st
 
 
+# ------------------------------------------------------------------------------------------ two-stream regions
+_side_streams = {}
+
+
+def two_streams() -> bool:
+    """Independent branches of the inference forward run on two streams (default; VLSAT_STREAMS=1 serialises them). Off while
+    the per-kernel timer is active, whose events must bracket serial execution. One CTA per SM for every tensor-core kernel,
+    so the second kernel's CTAs start as the first one's exit: the partial last round of its tiles fills for free."""
+    return os.environ.get("VLSAT_STREAMS", "2") == "2" and _timer is None
+
+
+def side_stream(device) -> torch.cuda.Stream:
+    key = str(device)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def fork_join(side_fn, main_fn, device):
+    """(side_fn(), main_fn()) with ``side_fn`` on THE side stream next to ``main_fn`` on the current one. Allocator rules that
+    make this safe with PyTorch's caching allocator (also inside a CUDA-graph capture): the side branch is issued FIRST;
+    every tensor it reads must stay referenced by the caller until this function returns (so the main branch cannot be
+    handed a block the side branch still reads); there is ONE side stream, every use of which starts by waiting for an
+    event recorded on the main stream (so a block the side pool hands out again is ordered after its last main-stream use)."""
+    if not two_streams():
+        return side_fn(), main_fn()
+    main, side = torch.cuda.current_stream(), side_stream(device)
+    fork = torch.cuda.Event()
+    fork.record(main)
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        a = side_fn()
+        join = torch.cuda.Event()
+        join.record(side)
+    b = main_fn()
+    main.wait_event(join)
+    return a, b
+
+
 def launch_count() -> int:
     return int(_lib.load().vlsat_launch_count())
 
