@@ -203,10 +203,10 @@ class Mmgnet(nn.Module):
         self.mmg.last_edge_pairs = (None, None)
 
         scale = self.obj_logit_scale.detach().reshape(1)
-        obj_logits_3d = ops.linear(ops.row_l2norm(g3), self.obj_predictor_3d.weight.detach(),
-                                   self.obj_predictor_3d.bias.detach(), scale_ptr=scale)
-        obj_logits_2d = ops.linear(ops.row_l2norm(g2), self.obj_predictor_2d.weight.detach(),
-                                   self.obj_predictor_2d.bias.detach(), scale_ptr=scale)
+        obj_logits_2d, obj_logits_3d = ops.fork_join(
+            lambda: ops.linear(ops.row_l2norm(g2), self.obj_predictor_2d.weight.detach(), self.obj_predictor_2d.bias.detach(), scale_ptr=scale),
+            lambda: ops.linear(ops.row_l2norm(g3), self.obj_predictor_3d.weight.detach(), self.obj_predictor_3d.bias.detach(), scale_ptr=scale),
+            g3.device)
         if not torch.cuda.is_current_stream_capturing():
             from .attention import validate_inputs
             validate_inputs(obj_points.device)           # unsorted batch_ids raise here, after the last launch (one host sync)
