@@ -24,6 +24,7 @@
 //                   exactly that barrier for 28 % of their samples).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <algorithm>
 #include <float.h>
 #include <stdlib.h>
 
@@ -97,9 +98,10 @@ __global__ void bf16_split_kernel(const float* __restrict__ x, int64_t ldx, int6
 
 // Partial softmax state of one KV split: o (un-normalised, relative to m), m (running max, exp2 domain), l (sum).
 struct FlashPartial {
-    float* o;          // [splits, nq, H*64]
-    float* m;          // [splits, H, nq]
-    float* l;          // [splits, H, nq]
+    float* o;          // [splits, rows, H*64]   rows = nq - row_base: the query rows this (split) launch covers
+    float* m;          // [splits, H, rows]
+    float* l;          // [splits, H, rows]
+    int rows, row_base;
 };
 
 // One CTA = 256 queries (two 128-row Q tiles, one per softmax warpgroup) of one head over the KV tiles
@@ -111,7 +113,7 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
                        const __grid_constant__ CUtensorMap tm_khi, const __grid_constant__ CUtensorMap tm_klo,
                        const __grid_constant__ CUtensorMap tm_vhi, const __grid_constant__ CUtensorMap tm_vlo,
                        float* __restrict__ out, int64_t ldo, float* __restrict__ lse, FlashPartial part,
-                       int nq, int nk, int n_heads, int tiles_per_split, float scale_log2e) {
+                       int nq, int nk, int n_heads, int tiles_per_split, float scale_log2e, int item_offset) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array keeps LDS/STS
@@ -128,8 +130,10 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
     float* xch = reinterpret_cast<float*>(tmem_holder + 4);  // [parity 2][Q tile 2][key half 2][128 rows] half-row maxima / sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int head = blockIdx.y;
-    const int q0 = blockIdx.x * 2 * FB_BQ;
+    // work item = (256-query block, head), heads fastest: launches cover a contiguous range of items starting at item_offset
+    const int item = blockIdx.x + item_offset;
+    const int head = item % n_heads;
+    const int q0 = (item / n_heads) * 2 * FB_BQ;
     const int n_tiles_all = (nk + FB_BKV - 1) / FB_BKV;
     const int tile_begin = blockIdx.z * tiles_per_split;
     const int n_tiles = max(0, min(n_tiles_all, tile_begin + tiles_per_split) - tile_begin);
@@ -367,13 +371,14 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
                 if (lse && kh == 0) lse[(int64_t)head * nq + row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
             } else {
                 const int64_t D = (int64_t)n_heads * FB_DK;
-                float* orow = part.o + ((int64_t)blockIdx.z * nq + row) * D + head * FB_DK + 32 * kh;
+                const int64_t pr = row - part.row_base;
+                float* orow = part.o + ((int64_t)blockIdx.z * part.rows + pr) * D + head * FB_DK + 32 * kh;
 #pragma unroll
                 for (int d = 0; d < 32; d += 4)
                     *reinterpret_cast<float4*>(orow + d) = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
                 if (kh == 0) {
-                    part.m[((int64_t)blockIdx.z * n_heads + head) * nq + row] = m_run;
-                    part.l[((int64_t)blockIdx.z * n_heads + head) * nq + row] = l_run;
+                    part.m[((int64_t)blockIdx.z * n_heads + head) * part.rows + pr] = m_run;
+                    part.l[((int64_t)blockIdx.z * n_heads + head) * part.rows + pr] = l_run;
                 }
             }
         }
@@ -383,25 +388,27 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
     if (warp == 1) tmem_dealloc(tmem_base, FB_TMEM_COLS);
 }
 
-// Combine the KV splits: out = sum_s o_s 2^(m_s - m) / sum_s l_s 2^(m_s - m)
+// Combine the KV splits of the rows [row_base, nq): out = sum_s o_s 2^(m_s - m) / sum_s l_s 2^(m_s - m)
 __global__ void flash_merge_kernel(FlashPartial part, int splits, int nq, int n_heads, float* __restrict__ out, int64_t ldo,
                                    float* __restrict__ lse) {
     pdl_entry();
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (q, head, 4-dim group)
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (row, head, 4-dim group)
     const int groups = FB_DK / 4;
-    if (idx >= (int64_t)nq * n_heads * groups) return;
+    if (idx >= (int64_t)part.rows * n_heads * groups) return;
     const int gidx = (int)(idx % groups);
     const int head = (int)((idx / groups) % n_heads);
-    const int64_t q = idx / (groups * n_heads);
+    const int64_t pr = idx / (groups * n_heads);
+    const int64_t q = pr + part.row_base;
+    if (q >= nq) return;
     const int64_t D = (int64_t)n_heads * FB_DK;
     float m = -FLT_MAX;
-    for (int s = 0; s < splits; ++s) m = fmaxf(m, part.m[((int64_t)s * n_heads + head) * nq + q]);
+    for (int s = 0; s < splits; ++s) m = fmaxf(m, part.m[((int64_t)s * n_heads + head) * part.rows + pr]);
     float l = 0.f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = 0; s < splits; ++s) {
-        const float w = exp2f(part.m[((int64_t)s * n_heads + head) * nq + q] - m);
-        l += part.l[((int64_t)s * n_heads + head) * nq + q] * w;
-        const float4 v = *reinterpret_cast<const float4*>(part.o + ((int64_t)s * nq + q) * D + head * FB_DK + gidx * 4);
+        const float w = exp2f(part.m[((int64_t)s * n_heads + head) * part.rows + pr] - m);
+        l += part.l[((int64_t)s * n_heads + head) * part.rows + pr] * w;
+        const float4 v = *reinterpret_cast<const float4*>(part.o + ((int64_t)s * part.rows + pr) * D + head * FB_DK + gidx * 4);
         acc.x += v.x * w; acc.y += v.y * w; acc.z += v.z * w; acc.w += v.w * w;
     }
     const float inv = 1.f / l;
@@ -416,12 +423,20 @@ int bf16_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t
     return finish_launch();
 }
 
-size_t flash_attn_bf16_workspace_bytes(int64_t nq, int64_t nk, int n_heads, int* splits_out) {
-    // KV splits so that (256-query blocks x heads x splits) fills the 148 SMs in whole rounds
+// Launch plan. Work items = (256-query block, head); every item costs n_tiles key tiles; one CTA per SM.
+//   uniform: every item split s ways over CTAs (s = 1: no merge) - round 1's scheme; at config #2 (304 items, 150 tiles) the best
+//            is s = 3: 7 rounds x 50 tiles = 350 tile-times + a merge of everything, against an ideal of 308;
+//   hybrid:  the first floor(items / 148) * 148 items run UNSPLIT in whole rounds (no partial state, written directly), the
+//            leftover items are split so that together they fill one more round (config #2: 296 + 8 items x 18 splits:
+//            300 + 9 tile-times, and only the last 128 query rows go through the merge).
+struct FlashPlan { int items_a, items_b, splits_b, splits_uniform; bool hybrid; int row_base; };
+
+static FlashPlan flash_plan(int64_t nq, int64_t nk, int n_heads) {
     const int64_t items = ceil_div(nq, 2 * FB_BQ) * n_heads;
     const int64_t n_tiles = ceil_div(nk, FB_BKV);
+    FlashPlan p{};
     int best = 1; double best_cost = 1e30;
-    const char* forced = getenv("VLSAT_FLASH_SPLITS");           // experiments only
+    const char* forced = getenv("VLSAT_FLASH_SPLITS");           // experiments only: forces the uniform scheme
     for (int s = 1; s <= 4; ++s) {
         if (s > n_tiles) break;
         const double rounds = (double)ceil_div(items * s, kNumSMs);
@@ -430,9 +445,30 @@ size_t flash_attn_bf16_workspace_bytes(int64_t nq, int64_t nk, int n_heads, int*
         if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
     }
     if (forced && atoi(forced) >= 1 && atoi(forced) <= 4 && atoi(forced) <= n_tiles) best = atoi(forced);
-    if (splits_out) *splits_out = best;
-    if (best == 1) return 0;
-    return (size_t)best * (size_t)nq * ((size_t)n_heads * FB_DK + 2 * (size_t)n_heads) * sizeof(float);
+    p.splits_uniform = best;
+    // hybrid: whole rounds of unsplit items (a multiple of the head count so that launch A ends on a query-block boundary)
+    int64_t a = (items / kNumSMs) * kNumSMs;
+    a -= a % n_heads;
+    const int64_t b = items - a;
+    if (!forced && a > 0 && b > 0 && b < kNumSMs) {
+        const int sb = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(kNumSMs / b, n_tiles), 32));
+        // launch B: its CTAs pay the prologue (Q into TMEM, pipeline fill: ~4 tiles' worth) + a second launch + a small merge
+        const double cost = (double)(a / kNumSMs) * n_tiles + (double)ceil_div(n_tiles, sb) + 4.0 + 6.0;
+        if (sb > 1 && cost < best_cost - 1e-9) {
+            p.hybrid = true; p.items_a = (int)a; p.items_b = (int)b; p.splits_b = sb;
+            p.row_base = (int)(a / n_heads) * 2 * FB_BQ;
+        }
+    }
+    return p;
+}
+
+size_t flash_attn_bf16_workspace_bytes(int64_t nq, int64_t nk, int n_heads, int* splits_out) {
+    const FlashPlan p = flash_plan(nq, nk, n_heads);
+    if (splits_out) *splits_out = p.hybrid ? p.splits_b : p.splits_uniform;
+    const size_t per_row = ((size_t)n_heads * FB_DK + 2 * (size_t)n_heads) * sizeof(float);
+    if (p.hybrid) return (size_t)p.splits_b * (size_t)(nq - p.row_base) * per_row;
+    if (p.splits_uniform == 1) return 0;
+    return (size_t)p.splits_uniform * (size_t)nq * per_row;
 }
 
 // q_* [nq, H*64] bf16 (row stride ldq elements), k_* [nk, H*64], vt_* [H*64, nk] (row stride ldvt, multiple of 8)
@@ -441,8 +477,8 @@ int flash_attn_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq, con
                     int64_t nq, int64_t nk, int n_heads, int dk, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (dk != FB_DK || nq >= (1ll << 31) || nk >= (1ll << 31)) return VLSAT_ERR_UNSUPPORTED;
     if ((ldq | ldk | ldvt) % 8 || ldo % 4) return VLSAT_ERR_UNSUPPORTED;
-    int splits = 1;
-    const size_t need = flash_attn_bf16_workspace_bytes(nq, nk, n_heads, &splits);
+    const FlashPlan plan = flash_plan(nq, nk, n_heads);
+    const size_t need = flash_attn_bf16_workspace_bytes(nq, nk, n_heads, nullptr);
     if (need > 0 && (!workspace || workspace_bytes < need)) return VLSAT_ERR_WORKSPACE;
     CUtensorMap tk, tkl, tv, tvl;
     const uint64_t d = (uint64_t)n_heads * dk;
@@ -451,31 +487,43 @@ int flash_attn_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq, con
               make_tmap_2d(&tk, k_hi, BF, 2, nk, d, ldk, 64, FB_BKV) && make_tmap_2d(&tkl, k_lo, BF, 2, nk, d, ldk, 64, FB_BKV) &&
               make_tmap_2d(&tv, vt_hi, BF, 2, d, nk, ldvt, 64, FB_DK) && make_tmap_2d(&tvl, vt_lo, BF, 2, d, nk, ldvt, 64, FB_DK);
     if (!ok) return VLSAT_ERR_UNSUPPORTED;
-    FlashPartial part{nullptr, nullptr, nullptr};
-    if (splits > 1) {
-        part.o = (float*)workspace;
-        part.m = part.o + (size_t)splits * nq * d;
-        part.l = part.m + (size_t)splits * n_heads * nq;
-    }
     const int n_tiles = (int)ceil_div(nk, FB_BKV);
-    const int tiles_per_split = (int)ceil_div(n_tiles, splits);
+    const int64_t items = ceil_div(nq, 2 * FB_BQ) * n_heads;
     const size_t smem = FB_STAGES * FB_K_STAGE + FB_STAGES * FB_V_STAGE + 1024 + 256 + 2 * 2 * 2 * 128 * 4;
-    cudaFuncSetAttribute(flash_attn_bf16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((unsigned)ceil_div(nq, 2 * FB_BQ), (unsigned)n_heads, (unsigned)splits);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)dk);
-    if (tc_passes() == 1) {
-        cudaFuncSetAttribute(flash_attn_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        launch_k(flash_attn_bf16_kernel<1>, grid, dim3(FB_THREADS), smem, st, q_hi, q_lo, ldq, tk, tkl, tv, tvl, out, ldo, lse, part, (int)nq, (int)nk,
-                 n_heads, tiles_per_split, scale_log2e);
-    } else {
-        launch_k(flash_attn_bf16_kernel<3>, grid, dim3(FB_THREADS), smem, st, q_hi, q_lo, ldq, tk, tkl, tv, tvl, out, ldo, lse, part, (int)nq, (int)nk,
-                 n_heads, tiles_per_split, scale_log2e);
-    }
-    int launches = 1;
-    if (splits > 1) {
-        const int64_t n = nq * n_heads * (FB_DK / 4);
-        launch_k(flash_merge_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, st, part, splits, (int)nq, n_heads, out, ldo, lse);
+    const bool one_pass = tc_passes() == 1;
+    cudaFuncSetAttribute(flash_attn_bf16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flash_attn_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int launches = 0;
+    // one launch over items [offset, offset + count) with `splits` key ranges each; partial state for rows >= row_base
+    auto run = [&](int offset, int count, int splits, int row_base) {
+        FlashPartial part{nullptr, nullptr, nullptr, 0, row_base};
+        if (splits > 1) {
+            part.rows = (int)(nq - row_base);
+            part.o = (float*)workspace;
+            part.m = part.o + (size_t)splits * part.rows * d;
+            part.l = part.m + (size_t)splits * n_heads * part.rows;
+        }
+        const int tiles_per_split = (int)ceil_div(n_tiles, splits);
+        dim3 grid((unsigned)count, 1u, (unsigned)splits);
+        if (one_pass)
+            launch_k(flash_attn_bf16_kernel<1>, grid, dim3(FB_THREADS), smem, st, q_hi, q_lo, ldq, tk, tkl, tv, tvl, out, ldo, lse, part, (int)nq, (int)nk,
+                     n_heads, tiles_per_split, scale_log2e, offset);
+        else
+            launch_k(flash_attn_bf16_kernel<3>, grid, dim3(FB_THREADS), smem, st, q_hi, q_lo, ldq, tk, tkl, tv, tvl, out, ldo, lse, part, (int)nq, (int)nk,
+                     n_heads, tiles_per_split, scale_log2e, offset);
         ++launches;
+        if (splits > 1) {
+            const int64_t n = (int64_t)part.rows * n_heads * (FB_DK / 4);
+            launch_k(flash_merge_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, st, part, splits, (int)nq, n_heads, out, ldo, lse);
+            ++launches;
+        }
+    };
+    if (plan.hybrid) {
+        run(0, plan.items_a, 1, 0);
+        run(plan.items_a, plan.items_b, plan.splits_b, plan.row_base);
+    } else {
+        run(0, (int)items, plan.splits_uniform, 0);
     }
     return finish_launch(launches);
 }
