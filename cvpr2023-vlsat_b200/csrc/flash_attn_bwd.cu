@@ -94,8 +94,9 @@ struct FlashBwdArgs {
     const float *lse2, *delta;
     int64_t ld_stat;
     float *out1, *out2;                  // KV mode: dV, dK. Q mode: out2 = dQ. fp32 [n_stat, H*64], row stride ldo
-    int64_t ldo, split_stride;           // split z writes at out + z * split_stride
+    int64_t ldo, split_stride;           // split z writes row r at out + z * split_stride + (r - row_base) * ldo
     int n_stat, n_stream, tiles_per_split;
+    int n_heads, item_offset, row_base;  // this launch covers work items (stationary tile, head), heads fastest, from item_offset on
     float scale_log2e, scale;
 };
 
@@ -140,8 +141,9 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int head = blockIdx.y;
-    const int r0 = blockIdx.x * FW_ROWS;
+    const int item = blockIdx.x + a.item_offset;
+    const int head = item % a.n_heads;
+    const int r0 = (item / a.n_heads) * FW_ROWS;
     const int n_tiles_all = (a.n_stream + FW_T - 1) / FW_T;
     const int tile_begin = blockIdx.z * a.tiles_per_split;
     const int n_tiles = max(0, min(n_tiles_all, tile_begin + a.tiles_per_split) - tile_begin);
@@ -362,7 +364,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
                 for (int j = 0; j < 16; ++j) acc[j] = 0u;
             }
             if (row < a.n_stat) {
-                float* orow = o1 + (int64_t)row * a.ldo + head * FW_DK + 16 * kq;
+                float* orow = o1 + (int64_t)(row - a.row_base) * a.ldo + head * FW_DK + 16 * kq;
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
                     *reinterpret_cast<float4*>(orow + j) = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
@@ -375,7 +377,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
             for (int j = 0; j < 16; ++j) acc[j] = 0u;
         }
         if (row < a.n_stat) {
-            float* orow = o2 + (int64_t)row * a.ldo + head * FW_DK + 16 * kq;
+            float* orow = o2 + (int64_t)(row - a.row_base) * a.ldo + head * FW_DK + 16 * kq;
             const float sc = a.scale;
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
@@ -478,11 +480,22 @@ int sum_slabs(const float* slabs, int64_t slab_stride, int splits, float* out, i
     return finish_launch();
 }
 
-static int fw_pick_splits(int64_t n_stat, int64_t n_stream, int n_heads) {
+// Launch plan of one mode (same scheme as the forward, csrc/flash_attn_bf16.cu): work items = (128-row stationary tile, head).
+//   uniform: every item split s ways over CTAs, each split writing its own slab of the WHOLE output, summed afterwards;
+//   hybrid:  the first floor(items / 148) * 148 items unsplit in whole rounds, written directly; the leftover items split so
+//            that together they fill one more round (config #2: 592 + 8 items x 18 splits instead of 3 x 600 and slab sums
+//            of everything) - only the rows of the leftover tiles go through slabs.
+struct FwPlan { int items_a, items_b, splits_b, splits_uniform, row_base; bool hybrid; };
+
+static FwPlan fw_plan(int64_t n_stat, int64_t n_stream, int n_heads) {
     const int64_t items = ceil_div(n_stat, FW_ROWS) * n_heads;
     const int64_t n_tiles = ceil_div(n_stream, FW_T);
-    const char* forced = getenv("VLSAT_FLASH_BWD_SPLITS");       // experiments only
-    if (forced && atoi(forced) >= 1 && atoi(forced) <= 8) return (int)min((int64_t)atoi(forced), max((int64_t)1, n_tiles));
+    FwPlan p{};
+    const char* forced = getenv("VLSAT_FLASH_BWD_SPLITS");       // experiments only: forces the uniform scheme
+    if (forced && atoi(forced) >= 1 && atoi(forced) <= 8) {
+        p.splits_uniform = (int)min((int64_t)atoi(forced), max((int64_t)1, n_tiles));
+        return p;
+    }
     int best = 1; double best_cost = 1e30;
     for (int s = 1; s <= 8; ++s) {
         if (s > n_tiles) break;
@@ -491,16 +504,30 @@ static int fw_pick_splits(int64_t n_stat, int64_t n_stream, int n_heads) {
         const double cost = rounds * ((double)ceil_div(n_tiles, s) + 3.0) + (s > 1 ? 2.0 + 0.02 * n_tiles : 0.0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
     }
-    return best;
+    p.splits_uniform = best;
+    int64_t a = (items / kNumSMs) * kNumSMs;
+    a -= a % n_heads;
+    const int64_t b = items - a;
+    if (a > 0 && b > 0 && b < kNumSMs) {
+        const int sb = (int)max((int64_t)1, min(min((int64_t)kNumSMs / b, n_tiles), (int64_t)32));
+        const double cost = (double)(a / kNumSMs) * ((double)n_tiles + 3.0) + (double)ceil_div(n_tiles, sb) + 3.0 + 5.0;
+        if (sb > 1 && cost < best_cost - 1e-9) {
+            p.hybrid = true; p.items_a = (int)a; p.items_b = (int)b; p.splits_b = sb;
+            p.row_base = (int)(a / n_heads) * FW_ROWS;
+        }
+    }
+    return p;
+}
+
+static size_t fw_plan_slab_floats(const FwPlan& p, int64_t n_stat, size_t D) {        // per output tensor
+    if (p.hybrid) return (size_t)p.splits_b * (size_t)(n_stat - p.row_base) * D;
+    return p.splits_uniform > 1 ? (size_t)p.splits_uniform * (size_t)n_stat * D : 0;
 }
 
 size_t flash_attn_bwd_workspace_bytes(int64_t nq, int64_t nk, int n_heads) {
-    const int s_kv = fw_pick_splits(nk, nq, n_heads), s_q = fw_pick_splits(nq, nk, n_heads);
     const size_t D = (size_t)n_heads * FW_DK;
-    size_t bytes = 0;
-    if (s_kv > 1) bytes = max(bytes, (size_t)2 * s_kv * (size_t)nk * D * sizeof(float));
-    if (s_q > 1) bytes = max(bytes, (size_t)s_q * (size_t)nq * D * sizeof(float));
-    return bytes;
+    const size_t kv = 2 * fw_plan_slab_floats(fw_plan(nk, nq, n_heads), nk, D), q = fw_plan_slab_floats(fw_plan(nq, nk, n_heads), nq, D);
+    return max(kv, q) * sizeof(float);
 }
 
 int bf16_split_t(const float* x, int64_t ldx, int64_t n, int64_t D, uint16_t* hi, uint16_t* lo, int64_t ld_out,
@@ -551,65 +578,66 @@ int flash_attn_bwd_bf16(const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq,
     auto smem_bytes = [](bool kv) {
         return (size_t)FW_YST * 2 * FW_PAIR + (size_t)FW_ZST * (kv ? 2 : 1) * FW_PAIR + FW_NSTAT * 128 * 4 + 256 + 1024;
     };
-    // ---- dK, dV: key tiles stationary, queries streamed
-    {
-        const int splits = fw_pick_splits(nk, nq, n_heads);
-        const int n_tiles = (int)ceil_div(nq, FW_T);
-        FlashBwdArgs a{};
-        a.x1_hi = k_hi; a.x1_lo = k_lo; a.ldx1 = ldk; a.x2_hi = v_hi; a.x2_lo = v_lo; a.ldx2 = ldv;
-        a.lse2 = lse2; a.delta = delta; a.ld_stat = ld_stat;
-        a.n_stat = (int)nk; a.n_stream = (int)nq; a.tiles_per_split = (int)ceil_div(n_tiles, splits);
-        a.scale_log2e = 1.4426950408889634f * scale; a.scale = scale;
-        if (splits > 1) {
-            a.out1 = (float*)workspace; a.out2 = a.out1 + (size_t)splits * nk * D; a.ldo = (int64_t)D; a.split_stride = (int64_t)nk * (int64_t)D;
-        } else {
-            a.out1 = dv; a.out2 = dk; a.ldo = lddk; a.split_stride = 0;
-        }
-        const size_t smem = smem_bytes(true);
-        dim3 grid((unsigned)ceil_div(nk, FW_ROWS), (unsigned)n_heads, (unsigned)splits);
-        if (tc_passes() == 1) {
-            cudaFuncSetAttribute(flash_attn_bwd_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            launch_k(flash_attn_bwd_kernel<true, 1>, grid, dim3(FW_THREADS), smem, st, tq[0], tq[1], tdo[0], tdo[1], tdot[0], tdot[1], tqt[0], tqt[1], a);
-        } else {
-            cudaFuncSetAttribute(flash_attn_bwd_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            launch_k(flash_attn_bwd_kernel<true, 3>, grid, dim3(FW_THREADS), smem, st, tq[0], tq[1], tdo[0], tdo[1], tdot[0], tdot[1], tqt[0], tqt[1], a);
-        }
-        ++launches;
-        if (splits > 1) {
-            const int64_t n4 = nk * (int64_t)(D / 4);
-            launch_k(sum_slabs_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, (const float*)a.out1, a.split_stride, splits, dv, lddv, nk, (int64_t)(D / 4));
-            launch_k(sum_slabs_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, (const float*)a.out2, a.split_stride, splits, dk, lddk, nk, (int64_t)(D / 4));
-            launches += 2;
-        }
-    }
-    // ---- dQ: query tiles stationary, keys streamed
-    {
-        const int splits = fw_pick_splits(nq, nk, n_heads);
-        const int n_tiles = (int)ceil_div(nk, FW_T);
-        FlashBwdArgs a{};
-        a.x1_hi = q_hi; a.x1_lo = q_lo; a.ldx1 = ldq; a.x2_hi = do_hi; a.x2_lo = do_lo; a.ldx2 = lddo;
-        a.lse2 = lse2; a.delta = delta; a.ld_stat = ld_stat;
-        a.n_stat = (int)nq; a.n_stream = (int)nk; a.tiles_per_split = (int)ceil_div(n_tiles, splits);
-        a.scale_log2e = 1.4426950408889634f * scale; a.scale = scale;
-        a.out1 = nullptr;
-        if (splits > 1) { a.out2 = (float*)workspace; a.ldo = (int64_t)D; a.split_stride = (int64_t)nq * (int64_t)D; }
-        else { a.out2 = dq; a.ldo = lddq; a.split_stride = 0; }
-        const size_t smem = smem_bytes(false);
-        dim3 grid((unsigned)ceil_div(nq, FW_ROWS), (unsigned)n_heads, (unsigned)splits);
-        if (tc_passes() == 1) {
-            cudaFuncSetAttribute(flash_attn_bwd_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            launch_k(flash_attn_bwd_kernel<false, 1>, grid, dim3(FW_THREADS), smem, st, tk[0], tk[1], tv[0], tv[1], tkt[0], tkt[1], tkt[0], tkt[1], a);
-        } else {
-            cudaFuncSetAttribute(flash_attn_bwd_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            launch_k(flash_attn_bwd_kernel<false, 3>, grid, dim3(FW_THREADS), smem, st, tk[0], tk[1], tv[0], tv[1], tkt[0], tkt[1], tkt[0], tkt[1], a);
-        }
-        ++launches;
-        if (splits > 1) {
-            const int64_t n4 = nq * (int64_t)(D / 4);
-            launch_k(sum_slabs_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, (const float*)a.out2, a.split_stride, splits, dq, lddq, nq, (int64_t)(D / 4));
+    // one mode = one or two kernel launches (+ slab sums) following its plan
+    auto run_mode = [&](bool kv) {
+        const int64_t n_stat = kv ? nk : nq, n_stream = kv ? nq : nk;
+        const FwPlan plan = fw_plan(n_stat, n_stream, n_heads);
+        const int n_tiles = (int)ceil_div(n_stream, FW_T);
+        const int64_t items = ceil_div(n_stat, FW_ROWS) * n_heads;
+        float* const dst1 = kv ? dv : nullptr;
+        float* const dst2 = kv ? dk : dq;
+        const int64_t ld1 = lddv, ld2 = kv ? lddk : lddq;
+        const size_t smem = smem_bytes(kv);
+        auto launch = [&](int offset, int count, int splits, int row_base) {
+            FlashBwdArgs a{};
+            if (kv) { a.x1_hi = k_hi; a.x1_lo = k_lo; a.ldx1 = ldk; a.x2_hi = v_hi; a.x2_lo = v_lo; a.ldx2 = ldv; }
+            else { a.x1_hi = q_hi; a.x1_lo = q_lo; a.ldx1 = ldq; a.x2_hi = do_hi; a.x2_lo = do_lo; a.ldx2 = lddo; }
+            a.lse2 = lse2; a.delta = delta; a.ld_stat = ld_stat;
+            a.n_stat = (int)n_stat; a.n_stream = (int)n_stream; a.tiles_per_split = (int)ceil_div(n_tiles, splits);
+            a.scale_log2e = 1.4426950408889634f * scale; a.scale = scale;
+            a.n_heads = n_heads; a.item_offset = offset; a.row_base = 0;
+            const int64_t rows = n_stat - row_base;                       // rows that go through slabs when splits > 1
+            if (splits > 1) {
+                a.row_base = row_base;
+                a.split_stride = rows * (int64_t)D; a.ldo = (int64_t)D;
+                a.out1 = kv ? (float*)workspace : nullptr;
+                a.out2 = kv ? (float*)workspace + (size_t)splits * rows * D : (float*)workspace;
+            } else {
+                a.out1 = dst1; a.out2 = dst2; a.ldo = ld2; a.split_stride = 0;   // (lddk == lddv is checked above)
+            }
+            dim3 grid((unsigned)count, 1u, (unsigned)splits);
+            const bool one = tc_passes() == 1;
+            if (kv) {
+                auto kern = one ? flash_attn_bwd_kernel<true, 1> : flash_attn_bwd_kernel<true, 3>;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                launch_k(kern, grid, dim3(FW_THREADS), smem, st, tq[0], tq[1], tdo[0], tdo[1], tdot[0], tdot[1], tqt[0], tqt[1], a);
+            } else {
+                auto kern = one ? flash_attn_bwd_kernel<false, 1> : flash_attn_bwd_kernel<false, 3>;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                launch_k(kern, grid, dim3(FW_THREADS), smem, st, tk[0], tk[1], tv[0], tv[1], tkt[0], tkt[1], tkt[0], tkt[1], a);
+            }
             ++launches;
+            if (splits > 1) {
+                const int64_t n4 = rows * (int64_t)(D / 4);
+                if (kv) {
+                    launch_k(sum_slabs_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, (const float*)a.out1, a.split_stride, splits,
+                             dst1 + (int64_t)row_base * ld1, ld1, rows, (int64_t)(D / 4));
+                    ++launches;
+                }
+                launch_k(sum_slabs_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, (const float*)a.out2, a.split_stride, splits,
+                         dst2 + (int64_t)row_base * ld2, ld2, rows, (int64_t)(D / 4));
+                ++launches;
+            }
+        };
+        if (plan.hybrid) {
+            launch(0, plan.items_a, 1, 0);
+            launch(plan.items_a, plan.items_b, plan.splits_b, plan.row_base);
+        } else {
+            launch(0, (int)items, plan.splits_uniform, 0);
         }
-    }
+    };
+    run_mode(true);      // dK, dV: key tiles stationary, queries streamed
+    run_mode(false);     // dQ: query tiles stationary, keys streamed
     return finish_launch(launches);
 }
 
