@@ -148,7 +148,10 @@ __global__ void gather_rows_kernel(const float* __restrict__ in, int64_t ld_in, 
 // ------------------------------------------------------------------------------------- LayerNorm backward
 // y = [relu](LN(x + res) * gamma + beta). One warp per row (grid-stride); D <= 1024.
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma [masked by y > 0]; dgamma += dy' * xhat; dbeta += dy'.
+// NPL = columns per lane (template: the 512-wide rows of the path need 16, the 32-wide distance-bias MLP 1; a fixed 32 cost
+// 128 accumulator registers per thread and half-empty loops - 71 us per call in the ncu launch list of a training step).
 constexpr int LNB_MAX = 32;
+template <int NPL>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx,
                      const float* __restrict__ res, int64_t ldr, const float* __restrict__ gamma,
@@ -159,14 +162,14 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sacc[i] = 0.f;
     __syncthreads();
-    float dg[LNB_MAX], db[LNB_MAX];
+    float dg[NPL], db[NPL];
 #pragma unroll
-    for (int i = 0; i < LNB_MAX; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+    for (int i = 0; i < NPL; ++i) { dg[i] = 0.f; db[i] = 0.f; }
     for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < M; row += (int64_t)gridDim.x * nwarp) {
-        float v[LNB_MAX], g[LNB_MAX];
+        float v[NPL], g[NPL];
         float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < LNB_MAX; ++i) {
+        for (int i = 0; i < NPL; ++i) {
             const int c = lane + 32 * i;
             float t = 0.f;
             if (c < D) { t = x[row * ldx + c]; if (res) t += res[row * ldr + c]; }
@@ -175,11 +178,11 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __
         const float mean = warp_sum(sum) / (float)D;
         float sq = 0.f;
 #pragma unroll
-        for (int i = 0; i < LNB_MAX; ++i) { const int c = lane + 32 * i; if (c < D) { const float d = v[i] - mean; sq += d * d; } }
+        for (int i = 0; i < NPL; ++i) { const int c = lane + 32 * i; if (c < D) { const float d = v[i] - mean; sq += d * d; } }
         const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < LNB_MAX; ++i) {
+        for (int i = 0; i < NPL; ++i) {
             const int c = lane + 32 * i;
             g[i] = 0.f;
             if (c < D) {
@@ -195,13 +198,13 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __
         }
         s1 = warp_sum(s1) / (float)D; s2 = warp_sum(s2) / (float)D;
 #pragma unroll
-        for (int i = 0; i < LNB_MAX; ++i) {
+        for (int i = 0; i < NPL; ++i) {
             const int c = lane + 32 * i;
             if (c < D) dx[row * lddx + c] = rstd * (g[i] - s1 - v[i] * s2);
         }
     }
 #pragma unroll
-    for (int i = 0; i < LNB_MAX; ++i) {
+    for (int i = 0; i < NPL; ++i) {
         const int c = lane + 32 * i;
         if (c < D) { atomicAdd(sacc + c, dg[i]); atomicAdd(sacc + D + c, db[i]); }
     }
@@ -698,9 +701,11 @@ extern "C" int vlsat_add_layernorm_bwd(const float* dy, int64_t lddy, const floa
     if (M == 0) return VLSAT_OK;
     VLSAT_REQUIRE(dy && x && gamma && beta && dx && lddy >= D && ldx >= D && lddx >= D && (!res || ld_res >= D));
     VLSAT_SUPPORT(D <= 32 * LNB_MAX);
-    const unsigned grid = (unsigned)(ceil_div(M, 8) < 2 * kNumSMs ? ceil_div(M, 8) : 2 * kNumSMs);
-    launch_k(layernorm_bwd_kernel, grid, dim3(256), 2 * D * sizeof(float), (cudaStream_t)stream, dy, lddy, x, ldx, res, ld_res, gamma, beta, dx, lddx,
-                                                                                     dgamma, dbeta, M, D, eps, relu);
+    const unsigned grid = (unsigned)(ceil_div(M, 8) < 4 * kNumSMs ? ceil_div(M, 8) : 4 * kNumSMs);
+#define LNB_LAUNCH(NPL_) launch_k(layernorm_bwd_kernel<NPL_>, grid, dim3(256), 2 * D * sizeof(float), (cudaStream_t)stream, dy, lddy, x, ldx, res, \
+                                  ld_res, gamma, beta, dx, lddx, dgamma, dbeta, M, D, eps, relu)
+    if (D <= 32) LNB_LAUNCH(1); else if (D <= 128) LNB_LAUNCH(4); else if (D <= 512) LNB_LAUNCH(16); else LNB_LAUNCH(32);
+#undef LNB_LAUNCH
     return finish_launch();
 }
 

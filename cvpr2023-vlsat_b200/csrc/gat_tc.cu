@@ -544,7 +544,10 @@ extern "C" int vlsat_gat_edge_tc_fwd(const void* k_hi, const void* k_lo, const f
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         GatTcParams p;
         p.qc = qc; p.ld_qc = ld_qc; p.v = v; p.ld_v = ld_v; p.src = src_sorted; p.dst = dst_sorted; p.c2_bias = c2_bias;
-        p.xx_enc = enc; p.prob = prob; p.trace = g_trace; { const char* d = getenv("VLSAT_GAT_DBG"); p.dbg = d ? atoi(d) : 0; } p.n_edges = n_edges; p.H = n_heads; p.hid = hid; p.d_o = d_o;
+        p.xx_enc = enc; p.prob = prob; p.trace = g_trace;
+        static const int dbg_env = [] { const char* d = getenv("VLSAT_GAT_DBG"); return d ? atoi(d) : 0; }();   // read once, not per launch
+        p.dbg = dbg_env;
+        p.n_edges = n_edges; p.H = n_heads; p.hid = hid; p.d_o = d_o;
         const int64_t n_tiles = ceil_div(n_edges * n_heads, GT_ROWS);
         const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, kNumSMs);
         launch_k(kern, dim3(grid), dim3(64 + 128 * wg), smem, st, tk, tkl, t1, t1l, t2, t2l, p);
