@@ -714,7 +714,9 @@ def run_reference(args, device: str):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_text(args.workload, kw, kw["num_scenes"], args.metric),
-                   "sample_scenes": r["scenes"], "device": "host CPU" if device == "cpu" else "cuda:0", "reference_kind": r["kind"]},
+                   "sample_scenes": r["scenes"], "device": "host CPU" if device == "cpu" else "cuda:0", "reference_kind": r["kind"],
+                   "note": "the reference evaluates generate_object_pair_features + triplet_projector_2d in eval mode and discards the result "
+                           "(SGFN_MMG/model.py:319-322); the B200 arm computes them only when istrain=True"},
         "cpu_baseline": {"value": round(r["value"], 4), "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": round(r["value"], 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
