@@ -108,9 +108,14 @@ class _Linear(Function):
         dx = dw = d_ga = d_gb = None
         if xp is not None and dz.shape[0] > 0:
             dzp = ops.act_pair(dz)
-            if need[0]:
+            if need[0] and need[1]:
+                # the two gradients are independent: dW on the side stream next to dX (ops.fork_join; dzp, xp, wp stay
+                # referenced by this frame until the join). Most of these GEMMs are one tile-latency long, so two at a
+                # time nearly halves their share of the step.
+                dw, dx = ops.fork_join(lambda: ops.gemm_tn(dzp, xp, n, w.shape[1]), lambda: ops.gemm_nn(dzp, wp, w.shape[1]), dz.device)
+            elif need[0]:
                 dx = ops.gemm_nn(dzp, wp, w.shape[1])           # dZ [M, N] . W [N, K], W as the forward stores it
-            if need[1]:
+            elif need[1]:
                 dw = ops.gemm_tn(dzp, xp, n, w.shape[1])        # dZ^T X, both as stored
         else:
             if need[0]:
