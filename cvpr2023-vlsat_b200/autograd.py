@@ -109,16 +109,10 @@ class _Linear(Function):
         if xp is not None and dz.shape[0] > 0:
             dzp = ops.act_pair(dz)
             if need[0] and need[1]:
-                # the gradients are independent: dW (and the scatter-add of the second gathered operand) on the side stream
-                # next to dX (ops.fork_join; dz, dzp, xp, wp stay referenced by this frame until the join). Most of these
-                # GEMMs are one tile-latency long, so two at a time nearly halves their share of the step.
-                def side():
-                    dw_ = ops.gemm_tn(dzp, xp, n, w.shape[1])
-                    dgb_ = None
-                    if has_gb and need[6]:
-                        dgb_ = ops.scatter_add_rows(dz, ib, torch.zeros(ctx.shapes[1], device=dz.device, dtype=torch.float32))
-                    return dw_, dgb_
-                (dw, d_gb), dx = ops.fork_join(side, lambda: ops.gemm_nn(dzp, wp, w.shape[1]), dz.device)
+                # the two gradients are independent: dW on the side stream next to dX (ops.fork_join; dzp, xp, wp stay
+                # referenced by this frame until the join). Most of these GEMMs are one tile-latency long, so two at a
+                # time nearly halves their share of the step.
+                dw, dx = ops.fork_join(lambda: ops.gemm_tn(dzp, xp, n, w.shape[1]), lambda: ops.gemm_nn(dzp, wp, w.shape[1]), dz.device)
             elif need[0]:
                 dx = ops.gemm_nn(dzp, wp, w.shape[1])           # dZ [M, N] . W [N, K], W as the forward stores it
             elif need[1]:
@@ -131,7 +125,7 @@ class _Linear(Function):
                 dw = weight_grad(dz, x)                         # [N, K], reduction over the rows
         if has_ga and need[4]:
             d_ga = ops.scatter_add_rows(dz, ia, torch.zeros(ctx.shapes[0], device=dz.device, dtype=torch.float32))
-        if has_gb and need[6] and d_gb is None:
+        if has_gb and need[6]:
             d_gb = ops.scatter_add_rows(dz, ib, torch.zeros(ctx.shapes[1], device=dz.device, dtype=torch.float32))
         return dx, dw, db, None, d_ga, None, d_gb, None, d_res, d_scale, None
 
