@@ -100,19 +100,29 @@ class _Linear(Function):
         want_db = has_b and need[2]
         xp, wp = ctx.pairs
         pairs = xp is not None and dy.shape[0] > 0              # dz feeds the stored-operand GEMMs: its pair comes out of this pass
+        dzp = None
         if plain:
             dz = dy
-            db = ops.act_bwd(dy, None, ACT_NONE, want_dz=False, want_dbias=want_db, emit_pair=pairs)[1] if (want_db or pairs) else None
+            if want_db or pairs:
+                _, db, dzp = ops.act_bwd(dy, None, ACT_NONE, want_dz=False, want_dbias=want_db, emit_pair=pairs, return_pair=True)
+            else:
+                db = None
         else:
-            dz, db = ops.act_bwd(dy, y, ctx.act, want_dz=True, want_dbias=want_db, scale_ptr=scale if has_scale else None, emit_pair=pairs)
+            # the fp32 dz is only read by the scatter-adds of gathered operands; the two GEMMs read its bf16 pair
+            need_dz = not pairs or (has_ga and need[4]) or (has_gb and need[6])
+            dz, db, dzp = ops.act_bwd(dy, y, ctx.act, want_dz=need_dz, want_dbias=want_db, scale_ptr=scale if has_scale else None,
+                                      emit_pair=pairs, return_pair=True)
+            if dzp is None and dz is None:                      # pair emission declined (shape): fall back to the fp32 dz
+                dz, db2 = ops.act_bwd(dy, y, ctx.act, want_dz=True, want_dbias=False, scale_ptr=scale if has_scale else None)
         dx = dw = d_ga = d_gb = None
-        if xp is not None and dz.shape[0] > 0:
-            dzp = ops.act_pair(dz)
+        if xp is not None and dy.shape[0] > 0:
+            if dzp is None:
+                dzp = ops.act_pair(dz)
             if need[0] and need[1]:
                 # the two gradients are independent: dW on the side stream next to dX (ops.fork_join; dzp, xp, wp stay
                 # referenced by this frame until the join). Most of these GEMMs are one tile-latency long, so two at a
                 # time nearly halves their share of the step.
-                dw, dx = ops.fork_join(lambda: ops.gemm_tn(dzp, xp, n, w.shape[1]), lambda: ops.gemm_nn(dzp, wp, w.shape[1]), dz.device)
+                dw, dx = ops.fork_join(lambda: ops.gemm_tn(dzp, xp, n, w.shape[1]), lambda: ops.gemm_nn(dzp, wp, w.shape[1]), dy.device)
             elif need[0]:
                 dx = ops.gemm_nn(dzp, wp, w.shape[1])           # dZ [M, N] . W [N, K], W as the forward stores it
             elif need[1]:

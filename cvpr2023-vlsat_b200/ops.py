@@ -905,7 +905,7 @@ def transpose(x: torch.Tensor, mult: int = 4) -> torch.Tensor:
 
 
 def act_bwd(dy: torch.Tensor, y: Optional[torch.Tensor], act: int, want_dz: bool = True, want_dbias: bool = True,
-            scale: float = 1.0, scale_ptr: Optional[torch.Tensor] = None, emit_pair: bool = False):
+            scale: float = 1.0, scale_ptr: Optional[torch.Tensor] = None, emit_pair: bool = False, return_pair: bool = False):
     """(dz, dbias): dz = dy * act'(y) * scale * exp(scale_ptr), dbias = column sums of dz. ``emit_pair``: the same pass also
     writes the bf16 (hi, lo) pair of dz - the operand of the backward GEMMs that read it next - and remembers it on the
     returned tensor (on ``dy`` itself when the activation is the identity and no dz is written): ``act_pair`` finds it."""
@@ -920,7 +920,7 @@ def act_bwd(dy: torch.Tensor, y: Optional[torch.Tensor], act: int, want_dz: bool
         if emit_pair and n % 8 == 0 and tensor_cores_enabled() and default_fmt(n) == FMT_BF16:
             pair = torch.empty((2, m, n), device=dy.device, dtype=torch.bfloat16)
         if dz is None and db is None and pair is None:
-            return dz, db
+            return (dz, db, None) if return_pair else (dz, db)
         _lib.check(_call("vlsat_act_bwd_pair", dp, lddy, yp, ldy, act, scale, scale_ptr.data_ptr() if scale_ptr is not None else None,
                          dz.data_ptr() if want_dz else None, n, db.data_ptr() if want_dbias else None,
                          pair[0].data_ptr() if pair is not None else None, pair[1].data_ptr() if pair is not None else None, n, m, n,
@@ -932,12 +932,14 @@ def act_bwd(dy: torch.Tensor, y: Optional[torch.Tensor], act: int, want_dz: bool
                     owner._vlsat_pair = (owner._version, (pair[0], pair[1]))
                 except AttributeError:
                     pass
+        if return_pair:
+            return dz, db, ((pair[0], pair[1]) if pair is not None else None)
         return dz, db
     if dz is None and db is None:
-        return dz, db
+        return (dz, db, None) if return_pair else (dz, db)
     _lib.check(_call("vlsat_act_bwd", dp, lddy, yp, ldy, act, scale, scale_ptr.data_ptr() if scale_ptr is not None else None,
                      dz.data_ptr() if want_dz else None, n, db.data_ptr() if want_dbias else None, m, n, _stream()), "vlsat_act_bwd")
-    return dz, db
+    return (dz, db, None) if return_pair else (dz, db)
 
 
 def scatter_add_rows(x: torch.Tensor, idx: torch.Tensor, out: torch.Tensor, rows_per_idx: int = 1) -> torch.Tensor:
