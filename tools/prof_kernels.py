@@ -31,6 +31,11 @@ if "gat" in which or "pointnet" in which:
                 layer = model.mmg.gcn_3ds[0]
                 x = torch.randn(640, 512, device=dev); e = torch.randn(9600, 512, device=dev)
                 layer(x, e, b.edge_indices)
+if "flash_fwd" in which:
+    q, k, v = (torch.randn(9600, 512, generator=g).to(dev) for _ in range(3))
+    (qp, _), (kp, _), (_, vt) = ops.bf16_split_t(q), ops.bf16_split_t(k), ops.bf16_split_t(v)
+    for _ in range(2):
+        ops.flash_attn_bf16(qp, kp, vt, 9600, 8)
 if "flash_bwd" in which:
     q, k, v, dout = (torch.randn(9600, 512, generator=g).to(dev) for _ in range(4))
     (qp, qt), (kp, kt), (vp, vt) = ops.bf16_split_t(q), ops.bf16_split_t(k), ops.bf16_split_t(v)
