@@ -1,4 +1,6 @@
-"""Time one projection shape with the default tiles and (VLSAT_GEMM_BN=256 in the environment) 128x256 tiles. Profiling aid."""
+"""Back-to-back time of the projection kernel at the large shapes of the path (exactly two tile rounds: M = 9472; the path's own M = 9600).
+Round 2 used it to compare the default 128x128 tiles with an experimental 128x256 / two-stage instantiation (dropped: DESIGN.md section 8 item 4).
+Profiling aid."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vlsat_b200 as V
