@@ -54,6 +54,12 @@ class MMG(nn.Module):
         self.drop_out = nn.Dropout(kwargs['DROP_OUT_ATTEN'])
         self._cache = DerivedCache()
 
+    def prebuild(self, edge_index, batch_ids, obj_center, n: int) -> None:
+        """Build the per-batch bookkeeping of the next ``forward`` now (inference path): scene ranges, distance-bias table,
+        CSR. None of these kernels uses tensor memory, so they run next to the PointNet encoder on the side stream."""
+        self._prebuilt = (self.scene_context(batch_ids, obj_center), GraphContext(edge_index, n, self.flow),
+                          (edge_index.data_ptr(), batch_ids.data_ptr(), n))
+
     def scene_context(self, batch_ids, obj_center) -> SceneContext:
         fc = self.self_attn_fc
         pack = self._cache.get("fc", tuple(fc.parameters()), lambda: ops.pack_attn_fc(fc))
@@ -70,8 +76,15 @@ class MMG(nn.Module):
                                  edge_feature_2d, edge_index, batch_ids, obj_center)
         n = obj_feature_3d.shape[0]
         dn, da = self.dim_node, self.dim_atten
-        ctx = self.scene_context(batch_ids, obj_center)
-        g = GraphContext(edge_index, n, self.flow)
+        # scene ranges + distance-bias table and the CSR of the edge list depend on the batch only: a caller that has other
+        # work to overlap them with (Mmgnet.forward: the PointNet encoder) builds them early and hands them over
+        pre = getattr(self, "_prebuilt", None)
+        self._prebuilt = None
+        if pre is not None and pre[2] == (edge_index.data_ptr(), batch_ids.data_ptr(), n):
+            ctx, g = pre[0], pre[1]
+        else:
+            ctx = self.scene_context(batch_ids, obj_center)
+            g = GraphContext(edge_index, n, self.flow)
         o3, o2 = obj_feature_3d.contiguous(), obj_feature_2d.contiguous()
         (e3, e3p), (e2, e2p) = g.to_sorted(edge_feature_3d.contiguous(), True), g.to_sorted(edge_feature_2d.contiguous(), True)   # CSR edge order
         # (hi, lo) pairs of the four streams travel with them: every producer that feeds a projection emits the pair from

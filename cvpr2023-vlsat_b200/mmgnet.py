@@ -163,7 +163,15 @@ class Mmgnet(nn.Module):
             return T.mmgnet_forward(self, obj_points, obj_2d_feats, edge_indices, descriptor, batch_ids, istrain,
                                     use_spatial=bool(_need(self.mconfig, "USE_SPATIAL")))
         n = obj_points.shape[0]
-        obj_feature = self.obj_encoder(obj_points)                                   # [N, 768]
+        edge_indices = edge_indices.contiguous()
+        obj_center = descriptor[:, :3].contiguous()
+
+        def bookkeeping():
+            # batch-only work without tensor-memory kernels (scene ranges, distance-bias table, CSR build, edge descriptor):
+            # on the side stream next to the PointNet encoder, whose CTAs hold all of TMEM but leave registers / smem over
+            self.mmg.prebuild(edge_indices, batch_ids, obj_center, n)
+            return ops.edge_descriptor(descriptor.contiguous(), edge_indices)           # [E, 11]
+        edge_feature, obj_feature = ops.fork_join(bookkeeping, lambda: self.obj_encoder(obj_points), obj_points.device)   # [N, 768]
         obj_feature_3d_mimic = obj_feature[..., :512].clone() if istrain else None
 
         w, b = self._mlp3d_folded()
@@ -174,7 +182,6 @@ class Mmgnet(nn.Module):
         else:
             node3d = ops.linear(obj_feature, w, b, act=ops.ACT_RELU)
 
-        edge_feature = ops.edge_descriptor(descriptor.contiguous(), edge_indices.contiguous())   # [E, 11]
         ef = edge_feature.unsqueeze(-1)
         # the two relationship encoders read the same input and are independent: two streams (ops.fork_join)
         rel_feature_2d, rel_feature_3d = ops.fork_join(lambda: self.rel_encoder_2d(ef), lambda: self.rel_encoder_3d(ef), ef.device)
@@ -182,7 +189,6 @@ class Mmgnet(nn.Module):
         obj_2d = self.clip_adapter(obj_2d_feats.contiguous())
         obj_features_2d_mimic = obj_2d.clone() if istrain else None
 
-        obj_center = descriptor[:, :3].contiguous()
         g3, g2, ge3, ge2 = self.mmg(node3d, obj_2d, rel_feature_3d, rel_feature_2d, edge_indices, batch_ids,
                                     obj_center, descriptor, istrain=istrain)
 
