@@ -201,7 +201,8 @@ class StreamedInference:
 
     def __init__(self, model: torch.nn.Module):
         self.graphed = GraphedForward(model)
-        self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        self.device = next(model.parameters()).device
+        self.h2d, self.d2h = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
         self._in = [None, None]        # device staging sets of the inputs
         self._out_dev = [None, None]   # device staging sets of the outputs
         self._out_host = [None, None]
@@ -217,7 +218,7 @@ class StreamedInference:
             if self._in_free[k] is not None:
                 self.h2d.wait_event(self._in_free[k])
             if self._in[k] is None or any(a.shape != b.shape for a, b in zip(self._in[k], host_args)):
-                self._in[k] = [torch.empty(a.shape, dtype=a.dtype, device="cuda") for a in host_args]
+                self._in[k] = [torch.empty(a.shape, dtype=a.dtype, device=self.device) for a in host_args]
             for dst, src in zip(self._in[k], host_args):
                 dst.copy_(src, non_blocking=True)
             ready = torch.cuda.Event()

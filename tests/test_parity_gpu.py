@@ -624,3 +624,26 @@ def test_module_level_swap_under_the_reference_mmg():
         got = ref(*args)
     for i, (a, w) in enumerate(zip(got, want)):
         feat(a, w, f"reference MMG with swapped attention modules, output {i}")
+
+
+def test_two_stream_regions_do_not_change_the_results(monkeypatch):
+    """The independent branches of the inference forward run on two streams (ops.fork_join: graph-attention layers,
+    relationship encoders, q vs k/v projections, heads, batch bookkeeping next to PointNet). Every kernel involved is
+    deterministic (the only atomics are order-independent maxima), so the serial order must give the same bits - eagerly
+    and through a CUDA-graph replay."""
+    model = _cuda_model({})
+    b = synth.make_config_batch("cfg2", seed=9, num_scenes=4).to(DEV)
+    with torch.no_grad():
+        monkeypatch.setenv("VLSAT_STREAMS", "1")
+        serial = [t.clone() for t in model(*b.forward_args())]
+        monkeypatch.setenv("VLSAT_STREAMS", "2")
+        assert ops.two_streams()
+        for _ in range(3):                                   # repeated: a stream-ordering bug would be a race
+            eager = model(*b.forward_args())
+            for i, (a, w) in enumerate(zip(eager, serial)):
+                assert torch.equal(a, w), f"two-stream eager forward differs from the serial order in output {i}"
+        graphed = V.GraphedForward(model)
+        for _ in range(3):
+            rep = graphed(*b.forward_args())
+            for i, (a, w) in enumerate(zip(rep, serial)):
+                assert torch.equal(a, w), f"two-stream graph replay differs from the serial order in output {i}"
