@@ -1,5 +1,5 @@
 """Per-kernel static evidence from the built library: registers / spill (cuobjdump --dump-resource-usage) and the count of
-tensor-core / TMA / TMEM SASS instructions (cuobjdump -sass). Writes profiles/sass_evidence_r1.txt. Runs without a GPU."""
+tensor-core / TMA / TMEM SASS instructions (cuobjdump -sass). Writes profiles/sass_evidence_r<round>.txt (argv[1], default 2). Runs without a GPU."""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "cvpr2023-vlsat_b200", "libvlsat_b200.so")
@@ -37,7 +37,7 @@ for fn, f in res.items():
     c = counts.get(fn, {})
     rows.append((demangle(fn), f.get("REG", "?"), f.get("STACK", "?"), f.get("SHARED", "?"), c))
 rows.sort(key=lambda r: r[0])
-with open(os.path.join(ROOT, "profiles", "sass_evidence_r1.txt"), "w") as fo:
+with open(os.path.join(ROOT, "profiles", f"sass_evidence_r{sys.argv[1] if len(sys.argv) > 1 else 2}.txt"), "w") as fo:
     fo.write("libvlsat_b200.so (sm_100a), static per-kernel evidence: registers / stack bytes / static smem, then SASS instruction counts\n")
     fo.write("(dynamic shared memory is set at launch; UTC*MMA = tcgen05.mma, UTMALDG/UTMASTG = TMA, LDTM/STTM = tcgen05.ld/st)\n\n")
     for name, reg, st, sh, c in rows:
