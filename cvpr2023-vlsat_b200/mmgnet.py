@@ -159,6 +159,8 @@ class Mmgnet(nn.Module):
     # ---- forward -----------------------------------------------------------------------------------
     def forward(self, obj_points, obj_2d_feats, edge_indices, descriptor=None, batch_ids=None, istrain=False):
         from . import train_path as T
+        if not obj_points.is_cuda:
+            raise RuntimeError(f"Mmgnet.forward: expected CUDA tensors (vlsat_b200 has no CPU path), got obj_points on {obj_points.device}")
         if T.differentiable(self):
             return T.mmgnet_forward(self, obj_points, obj_2d_feats, edge_indices, descriptor, batch_ids, istrain,
                                     use_spatial=bool(_need(self.mconfig, "USE_SPATIAL")))
