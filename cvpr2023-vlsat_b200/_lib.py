@@ -63,7 +63,6 @@ SIGNATURES = {
     "vlsat_edge_descriptor_fwd": [vp, i64, vp, i64, vp, vp],
     "vlsat_linear_fwd": [vp, i64, vp, i64, vp, i64, i64, i64, i64, C.POINTER(Epilogue), C.POINTER(LinearOpts), vp],
     "vlsat_linear_workspace_bytes": [i64, i64, i64, i32, i32],
-    "vlsat_linear_tail_workspace_bytes": [i64, i64, i64, i32],
     "vlsat_gemm_pairs": [i32, vp, vp, i64, vp, vp, i64, vp, i64, i64, i64, i64, vp, sz, vp],
     "vlsat_gemm_pairs_workspace_bytes": [i32, i64, i64, i64],
     "vlsat_tf32_split": [vp, i64, i64, i64, vp, vp, vp],
@@ -136,7 +135,7 @@ SIGNATURES = {
     "vlsat_rel_text_embed": [vp, i32, i32, i32, vp, vp, i64, vp, i64, vp, i64, vp],
     "vlsat_pack_scale": [vp, vp, vp, i64, i32, f32, vp],
 }
-_RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_linear_tail_workspace_bytes": sz, "vlsat_gemm_pairs_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_bwd_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
+_RESTYPES = {"vlsat_linear_workspace_bytes": sz, "vlsat_gemm_pairs_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_workspace_bytes": sz, "vlsat_flash_attn_bf16x3_bwd_workspace_bytes": sz, "vlsat_error_string": C.c_char_p, "vlsat_gemm_engine": C.c_char_p, "vlsat_launch_count": i64}
 
 _lib = None
 

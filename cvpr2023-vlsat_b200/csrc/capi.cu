@@ -21,8 +21,7 @@ bool linear_tc_eligible(const float*, int64_t, const float*, int64_t, int64_t, i
 size_t linear_tc_workspace_bytes(int64_t, int64_t, int64_t, bool, bool);
 int tf32_split(const float*, int64_t, int64_t, int64_t, float*, float*, cudaStream_t);
 int linear_tc(const void*, const void*, const void*, const void*, float*, int64_t, int64_t, int64_t, int64_t,
-              const vlsat_epilogue*, int, int, void*, size_t, cudaStream_t);
-size_t linear_tail_workspace_bytes(int64_t, int64_t, int64_t, int);
+              const vlsat_epilogue*, int, int, cudaStream_t);
 bool pointnet_tc_eligible(int, int, int, int, int64_t);
 int pointnet_tc(const float*, int64_t, int, int64_t, const float*, const float*, const float*, const float*, const float*,
                 const float*, int, float*, int32_t*, cudaStream_t);
@@ -72,12 +71,6 @@ extern "C" int vlsat_get_precision(void) { return g_precision; }
 
 extern "C" size_t vlsat_linear_workspace_bytes(int64_t M, int64_t N, int64_t K, int need_x_split, int need_w_split) {
     return linear_tc_workspace_bytes(M, N, K, need_x_split != 0, need_w_split != 0);
-}
-
-extern "C" size_t vlsat_linear_tail_workspace_bytes(int64_t M, int64_t N, int64_t K, int engine) {
-    if (M <= 0 || N <= 0 || K <= 0 || engine == VLSAT_ENGINE_SIMT) return 0;
-    const int kind = engine == VLSAT_ENGINE_TC_BF16X3 || (engine == VLSAT_ENGINE_AUTO && K % 8 == 0) ? 1 : 0;
-    return linear_tail_workspace_bytes(M, N, K, kind);
 }
 
 extern "C" int vlsat_tf32_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* hi, float* lo, void* stream) {
@@ -136,9 +129,7 @@ extern "C" int vlsat_linear_fwd(const float* x, int64_t ldx, const float* w, int
     };
     if (!xh) { int rc = split(x, ldx, M, xh, xl); if (rc) return rc; }
     if (!wh) { int rc = split(w, ldw, N, wh, wl); if (rc) return rc; }
-    // whatever the caller lent beyond the split area is the scratch of the tail split (optional: vlsat_linear_tail_workspace_bytes)
-    const size_t spare = opts->workspace && opts->workspace_bytes > need ? opts->workspace_bytes - need : 0;
-    return linear_tc(xh, xl, wh, wl, y, ldy, M, N, K, epi, passes, kind, spare ? (void*)ws : nullptr, spare, st);
+    return linear_tc(xh, xl, wh, wl, y, ldy, M, N, K, epi, passes, kind, st);
 }
 
 extern "C" int vlsat_flash_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,

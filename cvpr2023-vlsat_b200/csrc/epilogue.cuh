@@ -18,14 +18,6 @@ struct LinearArgs {
     int splits = 1;
     int kb_per_split = 0;
     int64_t slab_rows = 0;
-    // tail split (forward / dX GEMMs whose tile count is a little over a multiple of the grid): work items below tail_first
-    // are whole tiles; item tail_first + j covers K blocks [sp * tail_kb_per, ...) of tile tail_first + j / tail_splits,
-    // sp = j % tail_splits, and leaves its raw fp32 accumulator in tail_ws[j][128][BN]; linear_tail_fixup_kernel sums the
-    // partials in split order and applies the epilogue
-    int tail_first = 0x7fffffff;
-    int tail_splits = 1;
-    int tail_kb_per = 0;
-    float* tail_ws = nullptr;
 };
 
 __device__ __forceinline__ float apply_act(float t, int act) {

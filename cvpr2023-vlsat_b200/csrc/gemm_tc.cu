@@ -92,26 +92,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
     constexpr int BK = (KD == Kind::TF32) ? TC_BK : 2 * TC_BK;      // K elements per 128-byte block
     const int num_kb = (int)((a.K + BK - 1) / BK);
     const int tiles_n = (int)((a.N + BN - 1) / BN), tiles_m = (int)((a.M + TC_BM - 1) / TC_BM);
+    const int n_tiles = tiles_m * tiles_n * a.splits;        // work items: (tile, reduction split)
     const int splits = a.splits;
     const int kb_per = splits > 1 ? a.kb_per_split : num_kb;
-    const int tail_first = a.tail_first, tail_splits = a.tail_splits, tail_kb_per = a.tail_kb_per;
-    // work items: (tile, reduction split); with a tail split, the whole tiles first and then the split ones
-    const int n_tiles = tail_splits > 1 ? tail_first + (tiles_m * tiles_n - tail_first) * tail_splits : tiles_m * tiles_n * splits;
-    // item -> output tile, K-block range, slot of its partial in tail_ws (-1: the item owns the whole reduction or a slab)
-    auto decode = [&](int t, int& tl, int& sp, int& kb0, int& kb1, int& part) {
-        if (t >= tail_first) {
-            part = t - tail_first;
-            tl = tail_first + part / tail_splits;
-            sp = 0;
-            kb0 = (part % tail_splits) * tail_kb_per;
-            kb1 = min(num_kb, kb0 + tail_kb_per);
-        } else {
-            part = -1;
-            tl = t / splits; sp = t - tl * splits;
-            kb0 = sp * kb_per;
-            kb1 = min(num_kb, kb0 + kb_per);
-        }
-    };
     constexpr bool A_MN = (MAJ & 1) != 0, B_MN = (MAJ & 2) != 0;
     static_assert(MAJ == 0 || KD == Kind::BF16, "MN-major operands: bf16 pairs only");
 
@@ -133,10 +116,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
         // warp-uniform loops; one elected lane issues (keeps TMA / MMA issue on the uniform datapath)
         int g = 0;                                          // k-block counter across tiles -> ring position
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            int tl, sp, kb_begin, kb_end, part;
-            decode(t, tl, sp, kb_begin, kb_end, part);
+            const int tl = t / splits, sp = t - tl * splits;
             const int m0 = (tl / tiles_n) * TC_BM, n0 = (tl % tiles_n) * BN;
-            for (int kb = kb_begin; kb < kb_end; ++kb, ++g) {
+            const int kb_end = min(num_kb, (sp + 1) * kb_per);
+            for (int kb = sp * kb_per; kb < kb_end; ++kb, ++g) {
                 const int s = g % STAGES;
                 mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
                 if (elect_one()) {
@@ -178,8 +161,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
         int g = 0, i = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int buf = i & 1;
-            int tl, sp, kb_begin, kb_end, part;
-            decode(t, tl, sp, kb_begin, kb_end, part);
+            const int sp = t % splits;
+            const int kb_begin = sp * kb_per, kb_end = min(num_kb, (sp + 1) * kb_per);
             mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
             tc_fence_after();
             if (a.trace && blockIdx.x == 0 && lane == 0 && i < 8) a.trace[i * 4 + 0] = gtime();
@@ -262,30 +245,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
         int i = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int buf = i & 1;
-            int tl, sp, kb_begin, kb_end, part;
-            decode(t, tl, sp, kb_begin, kb_end, part);
+            const int tl = t / splits, sp = t - tl * splits;
             const int m0 = (tl / tiles_n) * TC_BM, n0 = (tl % tiles_n) * BN;
             const int row_out0 = m0 + sp * (int)a.slab_rows;     // split reductions store into their own slab of the y map
-            if (part >= 0) {
-                // tail item: the raw accumulator of this K range goes to its slot of the workspace (thread = row, 128 B per
-                // chunk); bias / activation / stores happen in linear_tail_fixup_kernel once every split has landed
-                mbar_wait(&acc_full[buf], (i >> 1) & 1);
-                tc_fence_after();
-                const uint32_t tacc_p = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-                float* wrow = a.tail_ws + ((int64_t)part * TC_BM + srow) * BN;
-#pragma unroll 1
-                for (int c0 = wg * 32; c0 < BN; c0 += 64) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tacc_p + (uint32_t)c0, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(wrow + c0 + 4 * j) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                }
-                tc_fence_before();
-                mbar_arrive(&acc_empty[buf]);
-                continue;
-            }
             const int64_t m_own = (int64_t)m0 + q * 32 + lane;
             const bool own_ok = m_own < a.M;
             const int64_t ia_own = (own_ok && e.gather_a) ? e.idx_a[m_own] : 0;
@@ -415,77 +377,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_consta
     if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
-// Second half of the tail split: for every split tile, sum its partials in split order (deterministic) and apply the fused
-// epilogue. One thread per 4 consecutive columns; a few tiles per launch, so this is a latency-sized kernel that starts
-// under the GEMM's tail through programmatic dependent launch.
-__global__ void __launch_bounds__(256)
-linear_tail_fixup_kernel(const LinearArgs a, int bn, int tiles_n) {
-    pdl_entry();
-    const vlsat_epilogue& e = a.epi;
-    const int quads = bn >> 2;
-    const int64_t per_tile = (int64_t)TC_BM * quads;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int jt = (int)(idx / per_tile);                    // tail tile
-    const int tl = a.tail_first + jt;
-    const int rem = (int)(idx - jt * per_tile);
-    const int r = rem / quads, c = (rem - r * quads) * 4;
-    const int64_t m = (int64_t)(tl / tiles_n) * TC_BM + r, n0 = (int64_t)(tl % tiles_n) * bn + c;
-    if (tl >= tiles_n * (int)ceil_div(a.M, TC_BM) || m >= a.M || n0 >= a.N) return;
-    const float* p = a.tail_ws + (((int64_t)jt * a.tail_splits) * TC_BM + r) * bn + c;
-    float4 acc = __ldcg(reinterpret_cast<const float4*>(p));
-    for (int s = 1; s < a.tail_splits; ++s) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)s * TC_BM * bn));
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    const float post_scale = e.scale_ptr ? expf(__ldg(e.scale_ptr)) : 1.f;
-    const int64_t ia = e.gather_a ? e.idx_a[m] : 0, ib = e.gather_b ? e.idx_b[m] : 0;
-    const float in[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (n0 + j >= a.N) break;
-        const float v = epilogue_one(e, in[j], m, n0 + j, ia, ib, post_scale);
-        if (a.y) a.y[m * a.ldy + n0 + j] = v;
-        if (e.split_hi) store_split(e, v, m, n0 + j);
-    }
-}
-
-// Tail split plan: the tiles beyond the last whole round of the persistent grid are split along K so that one more
-// (short) round finishes them on every SM instead of a full-length round on a few. Only when it saves enough K blocks to
-// pay for the partial round trip and the fix-up launch.
-struct TailPlan { int first = 0x7fffffff, splits = 1, kb_per = 0, tiles = 0; };
-static bool tail_split_enabled() { const char* v = getenv("VLSAT_TAIL_SPLIT"); return !(v && v[0] == '0'); }     // read per call: tests toggle it
-static TailPlan pick_tail_split(int64_t M, int64_t N, int bn, int64_t num_kb, int passes) {
-    TailPlan p;
-    const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, bn);
-    const int64_t left = tiles % kNumSMs;
-    if (!tail_split_enabled() || tiles <= kNumSMs || left == 0 || 2 * left > kNumSMs || tiles >= (1ll << 30)) return p;
-    const int64_t want = std::min<int64_t>(num_kb, kNumSMs / left);
-    const int64_t per = ceil_div(num_kb, want);
-    const int64_t s = ceil_div(num_kb, per);
-    if (s < 2 || num_kb - per < (passes == 3 ? 4 : 10)) return p;
-    p.first = (int)(tiles - left); p.splits = (int)s; p.kb_per = (int)per; p.tiles = (int)left;
-    return p;
-}
-static size_t tail_bytes(const TailPlan& p, int bn) { return p.splits > 1 ? (size_t)p.tiles * p.splits * TC_BM * bn * sizeof(float) : 0; }
-static int linear_bn(int64_t M, int64_t N) {
-    const int64_t tiles128 = ceil_div(M, TC_BM) * ceil_div(N, 128);
-    return (N <= 64 || 2 * tiles128 <= kNumSMs) ? 64 : 128;
-}
-
-// scratch of the tail split of a forward projection (kind as in linear_tc); 0 when the shape is not split
-size_t linear_tail_workspace_bytes(int64_t M, int64_t N, int64_t K, int kind) {
-    const int bn = linear_bn(M, N);
-    const int passes = kind == 1 ? tc_passes() : 3;
-    return tail_bytes(pick_tail_split(M, N, bn, ceil_div(K, kind == 1 ? 64 : 32), passes), bn);
-}
-
-static int launch_tail_fixup(const LinearArgs& a, int bn, cudaStream_t st) {
-    const int tiles_n = (int)ceil_div(a.N, bn);
-    const int64_t threads = (int64_t)(ceil_div(a.M, TC_BM) * tiles_n - a.tail_first) * TC_BM * (bn / 4);
-    launch_k(linear_tail_fixup_kernel, dim3((unsigned)ceil_div(threads, 256)), dim3(256), 0, st, a, bn, tiles_n);
-    return finish_launch();
-}
-
 long long* g_trace = nullptr;
 
 int bf16_split(const float*, int64_t, int64_t, int64_t, uint16_t*, uint16_t*, int64_t, cudaStream_t);
@@ -517,8 +408,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tal, const CUtens
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 2 * TC_BM * 128 /*store staging*/ + BN * 4 /*bias*/ + 1024 /*align*/ + 256 /*barriers*/;
     auto kern = linear_tc_kernel<BN, STAGES, PASSES, KD, GATHER, RESID, MAJ>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int64_t tiles_out = ceil_div(a.N, BN) * ceil_div(a.M, TC_BM);
-    const int64_t n_tiles = a.tail_splits > 1 ? a.tail_first + (tiles_out - a.tail_first) * a.tail_splits : tiles_out * a.splits;
+    const int64_t n_tiles = ceil_div(a.N, BN) * ceil_div(a.M, TC_BM) * a.splits;
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, kNumSMs);
     launch_k(kern, dim3(grid), dim3(TC_THREADS), smem, st, ta, tal, tb, tbl, ty, tsh, tsl, a);
     return finish_launch();
@@ -527,8 +417,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tal, const CUtens
 // x_hi/x_lo and w_hi/w_lo: compact [rows, K] split operands (ld = K) in the pair format of `kind`
 // (0 = tf32 floats, 1 = bf16). passes = 3 (x3 split product) or 1 (plain TF32, kind 0 only).
 int linear_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* y, int64_t ldy,
-              int64_t M, int64_t N, int64_t K, const vlsat_epilogue* epi, int passes, int kind, void* tail_ws, size_t tail_ws_bytes,
-              cudaStream_t st) {
+              int64_t M, int64_t N, int64_t K, const vlsat_epilogue* epi, int passes, int kind, cudaStream_t st) {
     LinearArgs a;
     a.x = (const float*)x_hi; a.ldx = K; a.w = (const float*)w_hi; a.ldw = K; a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.K = K;
     if (epi) a.epi = *epi;
@@ -537,7 +426,8 @@ int linear_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
     // 128 x 64 tiles for narrow outputs and for small problems: when 128 x 128 tiles would leave more than half of the SMs
     // idle the GEMM is one tile-latency long, and that latency is the per-SM operand ingest (~64 B/clk): a 64-column B
     // tile is 25 % less to pull per K block, on twice as many SMs
-    const int bn = linear_bn(M, N);
+    const int64_t tiles128 = ceil_div(M, TC_BM) * ceil_div(N, 128);
+    const int bn = (N <= 64 || 2 * tiles128 <= kNumSMs) ? 64 : 128;
     const auto DT = kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const int eb = kind == 1 ? 2 : 4;
     const uint32_t bk = 128 / eb;                     // elements per 128-byte K block
@@ -567,30 +457,20 @@ int linear_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
                       make_tmap_2d(&tsl, e.split_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, e.ld_split, 32, TC_BM);
     }
     a.tma_store = tma_out ? 1 : 0;
-    // tail split when the caller lent the scratch for it (ops.linear does); without it the plain persistent schedule runs
-    const TailPlan tp = pick_tail_split(M, N, bn, ceil_div(K, (int64_t)bk), passes);
-    if (tp.splits > 1 && tail_ws && tail_ws_bytes >= tail_bytes(tp, bn) && ((uintptr_t)tail_ws & 15) == 0) {
-        a.tail_first = tp.first; a.tail_splits = tp.splits; a.tail_kb_per = tp.kb_per; a.tail_ws = (float*)tail_ws;
-    }
     const bool g = e.gather_a || e.gather_b, r = e.residual != nullptr;
-    auto launch = [&]() -> int {
 #define VLSAT_TC_LAUNCH(BN_, ST_, PS_, KD_, G_, R_) launch_tc<BN_, ST_, PS_, KD_, G_, R_>(ta, tal, tb, tbl, ty, tsh, tsl, a, st)
-        if (kind == 1 && passes == 1) return bn == 64 ? VLSAT_TC_LAUNCH(64, 6, 1, Kind::BF16, true, true) : VLSAT_TC_LAUNCH(128, 6, 1, Kind::BF16, true, true);
-        if (kind == 1) {
-            // BF16x3: the engine of the hot path gets epilogue instantiations without the unused prefetch registers
-            if (bn == 64) return VLSAT_TC_LAUNCH(64, 4, 3, Kind::BF16, true, true);
-            if (!g && !r) return VLSAT_TC_LAUNCH(128, 3, 3, Kind::BF16, false, false);
-            if (g && !r) return VLSAT_TC_LAUNCH(128, 3, 3, Kind::BF16, true, false);
-            if (!g && r) return VLSAT_TC_LAUNCH(128, 3, 3, Kind::BF16, false, true);
-            return VLSAT_TC_LAUNCH(128, 3, 3, Kind::BF16, true, true);
-        }
-        if (passes == 3) return bn == 64 ? VLSAT_TC_LAUNCH(64, 4, 3, Kind::TF32, true, true) : VLSAT_TC_LAUNCH(128, 3, 3, Kind::TF32, true, true);
-        return bn == 64 ? VLSAT_TC_LAUNCH(64, 6, 1, Kind::TF32, true, true) : VLSAT_TC_LAUNCH(128, 6, 1, Kind::TF32, true, true);
+    if (kind == 1 && passes == 1) return bn == 64 ? VLSAT_TC_LAUNCH(64, 6, 1, Kind::BF16, true, true) : VLSAT_TC_LAUNCH(128, 6, 1, Kind::BF16, true, true);
+    if (kind == 1) {
+        // BF16x3: the engine of the hot path gets epilogue instantiations without the unused prefetch registers
+        if (bn == 64) return VLSAT_TC_LAUNCH(64, 4, 3, Kind::BF16, true, true);
+        if (!g && !r) return VLSAT_TC_LAUNCH(128, 3, 3, Kind::BF16, false, false);
+        if (g && !r) return VLSAT_TC_LAUNCH(128, 3, 3, Kind::BF16, true, false);
+        if (!g && r) return VLSAT_TC_LAUNCH(128, 3, 3, Kind::BF16, false, true);
+        return VLSAT_TC_LAUNCH(128, 3, 3, Kind::BF16, true, true);
+    }
+    if (passes == 3) return bn == 64 ? VLSAT_TC_LAUNCH(64, 4, 3, Kind::TF32, true, true) : VLSAT_TC_LAUNCH(128, 3, 3, Kind::TF32, true, true);
+    return bn == 64 ? VLSAT_TC_LAUNCH(64, 6, 1, Kind::TF32, true, true) : VLSAT_TC_LAUNCH(128, 6, 1, Kind::TF32, true, true);
 #undef VLSAT_TC_LAUNCH
-    };
-    const int rc = launch();
-    if (rc != VLSAT_OK || a.tail_splits == 1) return rc;
-    return launch_tail_fixup(a, bn, st);
 }
 
 // ------------------------------------------------------------------------------ backward GEMMs on stored operands
@@ -616,10 +496,6 @@ static void pick_reduction_split(int64_t M, int64_t N, int bn, int64_t num_kb, i
 }
 
 size_t gemm_pairs_workspace_bytes(int mode, int64_t M, int64_t N, int64_t K) {
-    if (mode == 2) {                                         // dX: tail split scratch, like a forward projection
-        const int bn2 = linear_bn(M, N);
-        return tail_bytes(pick_tail_split(M, N, bn2, ceil_div(K, 64), tc_passes()), bn2);
-    }
     if (mode != 3) return 0;
     const int bn = (N <= 64) ? 64 : 128;
     int splits, kb_per;
@@ -663,12 +539,6 @@ int gemm_pairs_tc(int mode, const uint16_t* a_hi, const uint16_t* a_lo, int64_t 
     }
     if (!make_tmap_2d(&ty, dst, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows_dst, N, ld_dst, 32, TC_BM)) return VLSAT_ERR_UNSUPPORTED;
     a.tma_store = 1;
-    if (mode == 2) {
-        const TailPlan tp = pick_tail_split(M, N, bn, ceil_div(K, 64), tc_passes());
-        if (tp.splits > 1 && workspace && workspace_bytes >= tail_bytes(tp, bn) && ((uintptr_t)workspace & 15) == 0) {
-            a.tail_first = tp.first; a.tail_splits = tp.splits; a.tail_kb_per = tp.kb_per; a.tail_ws = (float*)workspace;
-        }
-    }
     int rc;
     if (tc_passes() == 1) {
         if (mode == 2) rc = bn == 64 ? launch_tc<64, 6, 1, Kind::BF16, false, false, 2>(ta, tal, tb, tbl, ty, ty, ty, a, st)
@@ -679,7 +549,6 @@ int gemm_pairs_tc(int mode, const uint16_t* a_hi, const uint16_t* a_lo, int64_t 
                                  : launch_tc<128, 3, 3, Kind::BF16, false, false, 2>(ta, tal, tb, tbl, ty, ty, ty, a, st);
     else rc = bn == 64 ? launch_tc<64, 4, 3, Kind::BF16, false, false, 3>(ta, tal, tb, tbl, ty, ty, ty, a, st)
                        : launch_tc<128, 3, 3, Kind::BF16, false, false, 3>(ta, tal, tb, tbl, ty, ty, ty, a, st);
-    if (rc == VLSAT_OK && a.tail_splits > 1) return launch_tail_fixup(a, bn, st);
     if (rc != VLSAT_OK || splits == 1) return rc;
     return sum_slabs(dst, a.slab_rows * N, splits, y, ldy, M, N, st);
 }

@@ -107,7 +107,7 @@ def fork_join(side_fn, main_fn, device):
     every tensor it reads must stay referenced by the caller until this function returns (so the main branch cannot be
     handed a block the side branch still reads); there is ONE side stream, every use of which starts by waiting for an
     event recorded on the main stream (so a block the side pool hands out again is ordered after its last main-stream use)."""
-    if not two_streams() or torch.device(device).type != "cuda":    # CPU tensors: serial, the kernels' own checks raise
+    if not two_streams():
         return side_fn(), main_fn()
     main, side = torch.cuda.current_stream(), side_stream(device)
     fork = torch.cuda.Event()
@@ -384,11 +384,6 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
                 opts.x_hi, opts.x_lo = x_split[0].data_ptr(), x_split[1].data_ptr()
             else:
                 ws = torch.empty((2 * m * k,), device=x.device, dtype=torch.float32)
-        # scratch of the tail split (csrc/gemm_tc.cu): appended to the split area; shapes that are not split ask for 0 bytes
-        tail = _tail_bytes("linear", m, n, k, opts.engine)
-        if tail:
-            base = 0 if ws is None else ws.numel()
-            ws = torch.empty((base + tail // 4,), device=x.device, dtype=torch.float32)
         if ws is not None:
             opts.workspace, opts.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     elif x_pair_only:
@@ -410,19 +405,6 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 GEMM_NN, GEMM_TN = 2, 3
 
-_tail_cache = {}
-
-
-def _tail_bytes(kind: str, m: int, n: int, k: int, engine: int = 0) -> int:
-    """Bytes of tail-split scratch the library wants for this shape (0 for most); cached per shape and arithmetic mode."""
-    key = (kind, m, n, k, engine, precision())
-    v = _tail_cache.get(key)
-    if v is None:
-        lib = _lib.load()
-        v = int(lib.vlsat_linear_tail_workspace_bytes(m, n, k, engine) if kind == "linear" else lib.vlsat_gemm_pairs_workspace_bytes(GEMM_NN, m, n, k))
-        _tail_cache[key] = v
-    return v
-
 
 def gemm_pairs_ok(*pairs) -> bool:
     """Operands the stored-operand backward GEMMs can address: bf16 pairs with 16-byte aligned rows."""
@@ -436,11 +418,8 @@ def gemm_nn(a_pair, b_pair, n: int, out: Optional[torch.Tensor] = None) -> torch
     if out is None:
         out = torch.empty((m, n), device=a_pair[0].device, dtype=torch.float32)
     yp, ldy = _rows(out, "out")
-    ws_bytes = _tail_bytes("nn", m, n, k)
-    ws = torch.empty((ws_bytes // 4,), device=out.device, dtype=torch.float32) if ws_bytes else None
     st = _call("vlsat_gemm_pairs", GEMM_NN, a_pair[0].data_ptr(), a_pair[1].data_ptr(), a_pair[0].stride(0), b_pair[0].data_ptr(),
-               b_pair[1].data_ptr(), b_pair[0].stride(0), yp, ldy, m, n, k, ws.data_ptr() if ws is not None else None, ws_bytes, _stream(),
-               work=(2.0 * m * n * k, 4.0 * (m * k + n * k + m * n)))
+               b_pair[1].data_ptr(), b_pair[0].stride(0), yp, ldy, m, n, k, None, 0, _stream(), work=(2.0 * m * n * k, 4.0 * (m * k + n * k + m * n)))
     _lib.check(st, "vlsat_gemm_pairs(NN)")
     return out
 

@@ -121,8 +121,7 @@ typedef struct {
     const void* w_hi;         /*   AUTO they are taken to be BF16 pairs when K % 8 == 0, else TF32 pairs      */
     const void* w_lo;         /* optional pre-split weights, compact [N, K] (cache them per parameter)  */
     void* workspace;          /* device scratch for the splits that were not supplied                  */
-    size_t workspace_bytes;   /* >= vlsat_linear_workspace_bytes(M, N, K, x_hi == NULL, w_hi == NULL);  */
-                              /* + vlsat_linear_tail_workspace_bytes(...) to allow the tail split       */
+    size_t workspace_bytes;   /* >= vlsat_linear_workspace_bytes(M, N, K, x_hi == NULL, w_hi == NULL)   */
 } vlsat_linear_opts;
 
 /* Process-wide arithmetic of the tensor-core kernels (projections, A9 forward / backward, A8 edge kernel):
@@ -140,13 +139,6 @@ int vlsat_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw,
                      float* y, int64_t ldy, int64_t M, int64_t N, int64_t K,
                      const vlsat_epilogue* epi, const vlsat_linear_opts* opts, void* stream);
 size_t vlsat_linear_workspace_bytes(int64_t M, int64_t N, int64_t K, int need_x_split, int need_w_split);
-/* Optional extra scratch (appended to `workspace`, 16-byte aligned) for the tail split of the tensor-core engines: when
- * the 128-row output tiles number a little over a multiple of the 148-CTA persistent grid (config #2: 300 tiles), the
- * tiles of the last, nearly empty round are split along K over all SMs, their fp32 partials go through this scratch and a
- * small fix-up kernel sums them in split order (deterministic) and applies the epilogue. 0 = this shape is not split.
- * Without the extra bytes the call runs the plain schedule - same results up to fp32 summation order of those tiles.
- * VLSAT_TAIL_SPLIT=0 disables it. */
-size_t vlsat_linear_tail_workspace_bytes(int64_t M, int64_t N, int64_t K, int engine);
 
 /* Backward GEMMs of the dense projections on bf16 (hi, lo) pair operands read AS STORED - no transposed copies
  * (autograd of every nn.Linear / Conv1d(k=1) of the path, e.g. network_MMG.py:87-100; the reference has no
@@ -155,8 +147,6 @@ size_t vlsat_linear_tail_workspace_bytes(int64_t M, int64_t N, int64_t K, int en
  *   VLSAT_GEMM_TN: y [M, N] = a^T . b, a stored [K, M], b stored [K, N]   (dW = dZ^T X; the reduction over the stored
  *                  rows is split over CTAs when the output has few tiles: deterministic slab sums through `workspace`,
  *                  16-byte aligned, vlsat_gemm_pairs_workspace_bytes bytes)
- * For VLSAT_GEMM_NN the workspace is optional: with vlsat_gemm_pairs_workspace_bytes bytes it enables the tail split
- * described at vlsat_linear_tail_workspace_bytes.
  * Row strides in elements, multiples of 8; y fp32, 16-byte aligned, ldy % 4 == 0 (overwritten). */
 #define VLSAT_GEMM_NN 2
 #define VLSAT_GEMM_TN 3
