@@ -107,7 +107,7 @@ def fork_join(side_fn, main_fn, device):
     every tensor it reads must stay referenced by the caller until this function returns (so the main branch cannot be
     handed a block the side branch still reads); there is ONE side stream, every use of which starts by waiting for an
     event recorded on the main stream (so a block the side pool hands out again is ordered after its last main-stream use)."""
-    if not two_streams():
+    if not two_streams() or torch.device(device).type != "cuda":    # CPU tensors: serial, the kernels' own checks raise
         return side_fn(), main_fn()
     main, side = torch.cuda.current_stream(), side_stream(device)
     fork = torch.cuda.Event()
