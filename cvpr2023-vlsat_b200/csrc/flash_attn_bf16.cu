@@ -280,10 +280,12 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
                 for (int j = 0; j < 32; ++j)
                     if (k0 + j >= nk) r[j] = __float_as_uint(-FLT_MAX);
             }
-            // four independent partial maxima / sums keep the dependent chains short
+            // The loop is bound by the instructions its warps issue (four softmax warps per scheduler against one MMA stream), so
+            // it is written for the 3-input FMNMX3 and the packed FFMA2 / FADD2 forms: half the issue slots of the scalar code
+            // for the maximum, the scaling and the row sum. Independent partial maxima / sums keep the dependent chains short.
             float mxp[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mxp[j & 3] = fmaxf(mxp[j & 3], __uint_as_float(r[j]));
+            for (int j = 0; j < 32; j += 2) mxp[(j >> 1) & 3] = fmaxf(mxp[(j >> 1) & 3], fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
             const float mx_half = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
             // the row maximum is the larger of the two halves: exchanged through smem (double-buffered by tile parity)
             float* xm = xch + (((i & 1) * 2 + g) * 2) * 128;
@@ -294,27 +296,27 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
             // warp-uniform (TMEM ops are collective) and identical in the partner warp, which sees the same 32 rows
             const bool rescale = __any_sync(0xffffffffu, m_cand > m_run + kRescaleAbove);
             const float m_new = rescale ? m_cand : m_run;
-            const float neg_m = -m_new;
-            float rsp[4] = {0.f, 0.f, 0.f, 0.f};
+            const float2 scale2 = make_float2(scale_log2e, scale_log2e), neg_m2 = make_float2(-m_new, -m_new);
+            float2 rsp[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
             // p = 2^(s * scale - m) -> bf16 (hi, lo) pair, packed two keys per word, written over this row's S columns
             // (hi words of the tile's 64 keys in columns [0, 32), lo words in [32, 64); this thread owns 16 of each)
             uint32_t ph[16], pl[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {                       // two keys per packed word
-                const float pa = fb_ex2(fmaf(__uint_as_float(r[2 * c]), scale_log2e, neg_m));
-                const float pb = fb_ex2(fmaf(__uint_as_float(r[2 * c + 1]), scale_log2e, neg_m));
-                rsp[c & 3] += pa + pb;
-                // bf16 pair by TRUNCATION, three ops per value: hi = upper 16 bits of p (the byte permute takes them
-                // straight from the fp32 bit patterns), lo = upper 16 bits of p - hi (exact in fp32). hi + lo misses p by
-                // less than 2^-16 p, always from below: a -8e-6 relative bias of the weights against the exactly
-                // summed l, two orders inside the parity budget.
-                const uint32_t ua = __float_as_uint(pa), ub = __float_as_uint(pb);
-                const float la = pa - __uint_as_float(ua & 0xffff0000u), lb = pb - __uint_as_float(ub & 0xffff0000u);
+                const float2 x = ffma2(make_float2(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1])), scale2, neg_m2);
+                const float2 p = make_float2(fb_ex2(x.x), fb_ex2(x.y));
+                rsp[c & 3] = fadd2(rsp[c & 3], p);
                 if (PASSES == 3) {
+                    // bf16 pair by TRUNCATION: hi = upper 16 bits of p (the byte permute takes them straight from the fp32 bit
+                    // patterns), lo = upper 16 bits of p - hi (exact in fp32). hi + lo misses p by less than 2^-16 p, always
+                    // from below: a -8e-6 relative bias of the weights against the exactly summed l, two orders inside the
+                    // parity budget.
+                    const uint32_t ua = __float_as_uint(p.x), ub = __float_as_uint(p.y);
+                    const float2 l = fsub2(p, make_float2(__uint_as_float(ua & 0xffff0000u), __uint_as_float(ub & 0xffff0000u)));
                     ph[c] = __byte_perm(ua, ub, 0x7632);         // {pb.hi16, pa.hi16}: low half = even key
-                    pl[c] = __byte_perm(__float_as_uint(la), __float_as_uint(lb), 0x7632);
+                    pl[c] = __byte_perm(__float_as_uint(l.x), __float_as_uint(l.y), 0x7632);
                 } else {
-                    ph[c] = fb_pack_bf16(pa, pb);                // single pass: round to nearest (a truncated hi alone is biased by 2^-9)
+                    ph[c] = fb_pack_bf16(p.x, p.y);              // single pass: round to nearest (a truncated hi alone is biased by 2^-9)
                 }
             }
             tmem_st_16(t_s + lane_off + 16 * kh, ph);
@@ -339,7 +341,10 @@ flash_attn_bf16_kernel(const uint16_t* __restrict__ q_hi, const uint16_t* __rest
             }
             tc_fence_before();
             mbar_arrive(&p_ready[g]);
-            l_run += (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
+            {
+                const float2 t = fadd2(fadd2(rsp[0], rsp[1]), fadd2(rsp[2], rsp[3]));
+                l_run += t.x + t.y;
+            }
             m_run = m_new;
         }
         // row sum = the two half sums (same reference maximum); each thread then finishes its 32 output dims

@@ -104,12 +104,14 @@ struct FlashBwdArgs {
 // lo = upper 16 bits of x - hi (exact in fp32); hi + lo misses x by < 2^-16 |x|, towards zero.
 __device__ __forceinline__ void fw_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
-    const float la = a - __uint_as_float(ua & 0xffff0000u), lb = b - __uint_as_float(ub & 0xffff0000u);
+    const float2 l = fsub2(make_float2(a, b), make_float2(__uint_as_float(ua & 0xffff0000u), __uint_as_float(ub & 0xffff0000u)));
     hi = __byte_perm(ua, ub, 0x7632);
-    lo = __byte_perm(__float_as_uint(la), __float_as_uint(lb), 0x7632);
+    lo = __byte_perm(__float_as_uint(l.x), __float_as_uint(l.y), 0x7632);
 }
 
-__device__ __forceinline__ uint32_t fw_pack_rn(float a, float b) {          // packed bf16x2, round to nearest even, low half = a
+// packed bf16x2, round to nearest even, low half = a. One issue slot per pair: the conversion warps are bound by the
+// instructions they issue, and the integer form (two adds + a permute) measured slower than this XU-pipe conversion.
+__device__ __forceinline__ uint32_t fw_pack_rn(float a, float b) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
@@ -129,7 +131,7 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* y_smem = smem;
     uint8_t* z_smem = y_smem + FW_YST * Y_STAGE;
-    float* stat_smem = reinterpret_cast<float*>(z_smem + FW_ZST * Z_STAGE);          // [FW_NSTAT][128]: lse2 x 64 | delta x 64
+    float* stat_smem = reinterpret_cast<float*>(z_smem + FW_ZST * Z_STAGE);          // [FW_NSTAT][128]: -lse2 x 64 | delta x 64
     uint64_t* bars = reinterpret_cast<uint64_t*>(stat_smem + FW_NSTAT * 128);
     uint64_t* x_full = bars;
     uint64_t* y_full = bars + 1;            uint64_t* y_empty = y_full + FW_YST;
@@ -179,7 +181,9 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
                 // warps are done with slot (i - 5) % 5.
                 float* st = stat_smem + (i % FW_NSTAT) * 128;
                 const float* src = (lane < 16 ? a.lse2 : a.delta) + (int64_t)head * a.ld_stat + c0 + 4 * (lane & 15);
-                *reinterpret_cast<float4*>(st + 4 * lane) = __ldg(reinterpret_cast<const float4*>(src));
+                float4 sv = __ldg(reinterpret_cast<const float4*>(src));
+                if (lane < 16) sv = make_float4(-sv.x, -sv.y, -sv.z, -sv.w);      // -lse2: the addend of the packed FMA below
+                *reinterpret_cast<float4*>(st + 4 * lane) = sv;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&stat_full[i % FW_NSTAT]);
             }
@@ -295,11 +299,12 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
             tc_fence_before();
             mbar_arrive(x_full);
         }
-        float lse_r = FW_LSE_PAD, delta_r = 0.f;                 // Q mode: the statistics belong to this thread's row
+        float nlse_r = -FW_LSE_PAD, delta_r = 0.f;               // Q mode: the statistics (-lse2, delta) belong to this thread's row
         if (!KV && row < a.n_stat) {
-            lse_r = __ldg(a.lse2 + (int64_t)head * a.ld_stat + row);
+            nlse_r = -__ldg(a.lse2 + (int64_t)head * a.ld_stat + row);
             delta_r = __ldg(a.delta + (int64_t)head * a.ld_stat + row);
         }
+        const float2 scale2 = make_float2(a.scale_log2e, a.scale_log2e);
         for (int i = 0; i < n_tiles; ++i) {
             const int b = i & 1;
             const int c0 = (tile_begin + i) * FW_T + 16 * kq;     // first streamed element of this thread's quarter tile
@@ -315,33 +320,37 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_y1h, const __grid_c
             if (KV) mbar_wait(&stat_full[i % FW_NSTAT], (i / FW_NSTAT) & 1);
             const bool ragged = !KV && (c0 + 16 > a.n_stream);
             uint32_t ph[8], pl[8], dh[8], dl[8];
+            // p = 2^(s scale - lse2), dS = p (dP - delta) on packed fp32 pairs (FFMA2 / FADD2 / FMUL2: one issued instruction per
+            // two elements - the conversion warps are issue-bound, four of them per scheduler next to the MMA stream)
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {                     // four streamed elements per step
-                float l4[4], e4[4];
+                float2 nl[2], e2[2];
                 if (KV) {
                     const float4 lv = *reinterpret_cast<const float4*>(st + 4 * c4);          // broadcast reads
                     const float4 ev = *reinterpret_cast<const float4*>(st + 64 + 4 * c4);
-                    l4[0] = lv.x; l4[1] = lv.y; l4[2] = lv.z; l4[3] = lv.w;
-                    e4[0] = ev.x; e4[1] = ev.y; e4[2] = ev.z; e4[3] = ev.w;
+                    nl[0] = make_float2(lv.x, lv.y); nl[1] = make_float2(lv.z, lv.w);
+                    e2[0] = make_float2(ev.x, ev.y); e2[1] = make_float2(ev.z, ev.w);
                 } else {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { l4[u] = lse_r; e4[u] = delta_r; }
+                    nl[0] = nl[1] = make_float2(nlse_r, nlse_r);
+                    e2[0] = e2[1] = make_float2(delta_r, delta_r);
                 }
-                float p[4], g[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = 4 * c4 + u;
-                    p[u] = fw_ex2(fmaf(__uint_as_float(s[j]), a.scale_log2e, -l4[u]));
-                    if (ragged && c0 + j >= a.n_stream) p[u] = 0.f;
-                    g[u] = p[u] * (__uint_as_float(d[j]) - e4[u]);
-                }
-                if (PASSES == 3) {
-                    if (KV) { fw_split2(p[0], p[1], ph[2 * c4], pl[2 * c4]); fw_split2(p[2], p[3], ph[2 * c4 + 1], pl[2 * c4 + 1]); }
-                    fw_split2(g[0], g[1], dh[2 * c4], dl[2 * c4]);
-                    fw_split2(g[2], g[3], dh[2 * c4 + 1], dl[2 * c4 + 1]);
-                } else {                                         // single pass: round to nearest (a truncated hi alone is biased)
-                    if (KV) { ph[2 * c4] = fw_pack_rn(p[0], p[1]); ph[2 * c4 + 1] = fw_pack_rn(p[2], p[3]); }
-                    dh[2 * c4] = fw_pack_rn(g[0], g[1]); dh[2 * c4 + 1] = fw_pack_rn(g[2], g[3]);
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 4 * c4 + 2 * h, w = 2 * c4 + h;
+                    const float2 x = ffma2(make_float2(__uint_as_float(s[j]), __uint_as_float(s[j + 1])), scale2, nl[h]);
+                    float2 p = make_float2(fw_ex2(x.x), fw_ex2(x.y));
+                    if (ragged) {
+                        if (c0 + j >= a.n_stream) p.x = 0.f;
+                        if (c0 + j + 1 >= a.n_stream) p.y = 0.f;
+                    }
+                    const float2 g = fmul2(p, fsub2(make_float2(__uint_as_float(d[j]), __uint_as_float(d[j + 1])), e2[h]));
+                    if (PASSES == 3) {
+                        if (KV) fw_split2(p.x, p.y, ph[w], pl[w]);
+                        fw_split2(g.x, g.y, dh[w], dl[w]);
+                    } else {                                     // single pass: round to nearest (a truncated hi alone is biased)
+                        if (KV) ph[w] = fw_pack_rn(p.x, p.y);
+                        dh[w] = fw_pack_rn(g.x, g.y);
+                    }
                 }
             }
             // in place: this thread's 16 fp32 columns become 8 hi words + 8 lo words of the same 16 streamed elements
@@ -471,12 +480,42 @@ __global__ void sum_slabs_kernel(const float* __restrict__ slabs, int64_t slab_s
 }
 
 // ------------------------------------------------------------------------------------------------------ host
+// Many slabs of a small output (weight gradients of narrow layers: up to 148 slabs of a few thousand float4): 16 threads share
+// one output quad, thread g summing slabs g, g + 16, ... and the 16 partial sums combined in lane order through shared memory -
+// a fixed association for a given slab count, so still deterministic; 16 x the loads in flight of the kernel above.
+__global__ void __launch_bounds__(256)
+sum_slabs_wide_kernel(const float* __restrict__ slabs, int64_t slab_stride, int splits, float* __restrict__ out,
+                      int64_t ldo, int64_t rows, int64_t cols4) {
+    __shared__ float4 part[16][17];
+    pdl_entry();
+    const int o = threadIdx.x & 15, g = threadIdx.x >> 4;
+    const int64_t idx = (int64_t)blockIdx.x * 16 + o;
+    const bool ok = idx < rows * cols4;
+    const int64_t r = ok ? idx / cols4 : 0, c = ok ? (idx % cols4) * 4 : 0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok)
+        for (int s = g; s < splits; s += 16) {
+            const float4 v = *reinterpret_cast<const float4*>(slabs + (int64_t)s * slab_stride + r * (cols4 * 4) + c);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    part[g][o] = acc;
+    __syncthreads();
+    if (g == 0 && ok) {
+#pragma unroll
+        for (int j = 1; j < 16; ++j) { const float4 v = part[j][o]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        *reinterpret_cast<float4*>(out + r * ldo + c) = acc;
+    }
+}
+
 // out [rows, cols] (row stride ldo) = sum of `splits` slabs of [slab rows >= rows, cols] fp32, slab_stride elements apart
 int sum_slabs(const float* slabs, int64_t slab_stride, int splits, float* out, int64_t ldo, int64_t rows, int64_t cols, cudaStream_t st) {
     if (rows == 0 || cols == 0) return VLSAT_OK;
     if (cols % 4 || ldo % 4) return VLSAT_ERR_UNSUPPORTED;
     const int64_t n4 = rows * (cols / 4);
-    launch_k(sum_slabs_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, slabs, slab_stride, splits, out, ldo, rows, cols / 4);
+    if (splits >= 16 && n4 <= 16 * 1024)
+        launch_k(sum_slabs_wide_kernel, dim3((unsigned)ceil_div(n4, 16)), dim3(256), 0, st, slabs, slab_stride, splits, out, ldo, rows, cols / 4);
+    else
+        launch_k(sum_slabs_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, slabs, slab_stride, splits, out, ldo, rows, cols / 4);
     return finish_launch();
 }
 

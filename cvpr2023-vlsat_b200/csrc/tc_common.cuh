@@ -73,6 +73,31 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: two fp32 results per issued instruction). The element-wise passes of the
+// attention kernels (softmax, dS) are bound by instruction issue of their conversion warps, not by any one pipe.
+#define VLSAT_F32X2_OP3(name, op)                                                                                          \
+    __device__ __forceinline__ float2 name(float2 a, float2 b, float2 c) {                                                 \
+        float2 d;                                                                                                          \
+        asm("{.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};\n\t" op          \
+            " rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;}"                                                                   \
+            : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));                          \
+        return d;                                                                                                          \
+    }
+#define VLSAT_F32X2_OP2(name, op)                                                                                          \
+    __device__ __forceinline__ float2 name(float2 a, float2 b) {                                                           \
+        float2 d;                                                                                                          \
+        asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n\t" op                                  \
+            " rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;}"                                                                       \
+            : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                              \
+        return d;                                                                                                          \
+    }
+VLSAT_F32X2_OP3(ffma2, "fma.rn.f32x2")
+VLSAT_F32X2_OP2(fadd2, "add.rn.f32x2")
+VLSAT_F32X2_OP2(fsub2, "sub.rn.f32x2")
+VLSAT_F32X2_OP2(fmul2, "mul.rn.f32x2")
+#undef VLSAT_F32X2_OP3
+#undef VLSAT_F32X2_OP2
+
 // round-to-nearest (ties away from zero) to tf32 = cvt.rna.tf32.f32, done with two full-rate integer ops instead
 // of the quarter-rate conversion pipe: add half an ulp of the 10-bit mantissa to the magnitude, clear 13 bits.
 __device__ __forceinline__ uint32_t tf32_rna_bits(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
