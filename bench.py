@@ -641,6 +641,12 @@ def run_b200(args):
             roofline["linear_all_frac"] = round(fl_ / (ms_ * 1e-3) / 1e12 / peaks["tensor"], 5)
             roofline["linear_all_share_of_step"] = round(ms_ / step_ms, 4)
             roofline["linear_all_launches_per_step"] = la_ / n_pass
+        # the step as a whole: algorithmic tensor work of one step (every tensor-bound entry point) over the measured step time
+        # of the graph replay - per-kernel fractions understate the machine's use when kernels of two streams overlap
+        tens = sum(d["flops"] for n_, d in summ.items() if n_ not in hbm_names) / n_pass
+        whole_ms = train_line["ms_per_step"] if (args.metric == "train_step" and train_line) else fwd_ms
+        roofline["step_tensor_gflop"] = round(tens / 1e9, 1)
+        roofline["step_tensor_frac"] = round(tens / (whole_ms * 1e-3) / 1e12 / peaks["tensor"], 5)
         if "gat_frac" in roofline:
             gname = "vlsat_gat_edge_tc_fwd" if "vlsat_gat_edge_tc_fwd" in kernels else "vlsat_gat_edge_fwd"
             roofline["gat_traffic"] = load_traffic(gname)
