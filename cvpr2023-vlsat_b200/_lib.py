@@ -111,6 +111,7 @@ SIGNATURES = {
                                  vp, i64, vp, i64, vp],
     "vlsat_pointnet_pool_bwd": [vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp],
     "vlsat_dropout": [vp, i64, vp, i64, i64, i64, f32, C.c_uint64, C.c_uint64, vp, vp],
+    "vlsat_dropout_pair": [vp, i64, vp, i64, i64, i64, f32, C.c_uint64, C.c_uint64, vp, vp, vp, i64, vp],
     "vlsat_batchnorm_fwd": [vp, i64, vp, vp, vp, vp, vp, vp, f32, f32, i32, i32, vp, i64, i64, i64, vp],
     "vlsat_batchnorm_bwd": [vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, vp, i64, vp, vp, i64, i64, vp],
     "vlsat_row_l2norm_bwd": [vp, vp, vp, i64, i32, vp],

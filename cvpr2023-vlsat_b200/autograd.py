@@ -149,8 +149,11 @@ def linear(x, w, bias=None, act=ACT_NONE, gather=None, residual=None, scale=None
 
 class _Relu(Function):
     @staticmethod
-    def forward(ctx, x):
-        y, pair = ops.relu(x.contiguous(), emit_split=True)     # the next layer's projections read the pair
+    def forward(ctx, x, emit_pair=True):
+        if emit_pair:
+            y, pair = ops.relu(x.contiguous(), emit_split=True)           # the next layer's projections read the pair
+        else:
+            y, pair = ops.relu(x.contiguous()), None
         if pair is not None:
             y._vlsat_pair = (y._version, pair)
         ctx.save_for_backward(y)
@@ -160,11 +163,12 @@ class _Relu(Function):
     def backward(ctx, dy):
         (y,) = ctx.saved_tensors
         dy = _c(dy)
-        return ops.act_bwd(dy.view(-1, y.shape[-1]), y.view(-1, y.shape[-1]), ACT_RELU, want_dbias=False)[0].view(y.shape)
+        return ops.act_bwd(dy.view(-1, y.shape[-1]), y.view(-1, y.shape[-1]), ACT_RELU, want_dbias=False)[0].view(y.shape), None
 
 
-def relu(x):
-    return _Relu.apply(x)
+def relu(x, emit_pair: bool = True):
+    """``emit_pair=False``: something other than a projection reads the result (a dropout pass that emits the pair itself)."""
+    return _Relu.apply(x, emit_pair)
 
 
 class _AddLayerNorm(Function):
@@ -212,21 +216,22 @@ class DropoutState:
 
 class _Dropout(Function):
     @staticmethod
-    def forward(ctx, x, p):
+    def forward(ctx, x, p, emit_pair=False):
         ctx.p = p
         ctx.key = DropoutState.take(x.numel())
         ctx.step = DropoutState.device_step
-        return ops.dropout(x, p, *ctx.key, device_step=ctx.step)
+        return ops.dropout(x, p, *ctx.key, device_step=ctx.step, emit_pair=bool(emit_pair) and x.dim() == 2)
 
     @staticmethod
     def backward(ctx, dy):
-        return ops.dropout(_c(dy), ctx.p, *ctx.key, device_step=ctx.step), None
+        return ops.dropout(_c(dy), ctx.p, *ctx.key, device_step=ctx.step), None, None
 
 
-def dropout(x, p: float, training: bool):
+def dropout(x, p: float, training: bool, emit_pair: bool = False):
+    """``emit_pair``: x feeds a projection next - its bf16 pair leaves with the dropout pass."""
     if not training or p <= 0.0:
         return x
-    return _Dropout.apply(x, float(p))
+    return _Dropout.apply(x, float(p), emit_pair)
 
 
 # ------------------------------------------------------------------------------------------ batch norm
@@ -282,19 +287,25 @@ def row_l2norm(x):
 
 class _PermuteRows(Function):
     @staticmethod
-    def forward(ctx, x, perm, gather):
+    def forward(ctx, x, perm, gather, emit_pair=False):
         ctx.perm, ctx.gather = perm, gather
+        if emit_pair:
+            y, pair = ops.permute_rows(x, perm, gather=gather, emit_split=True)
+            if pair is not None:
+                y._vlsat_pair = (y._version, pair)
+            return y
         return ops.permute_rows(x, perm, gather=gather)
 
     @staticmethod
     def backward(ctx, dy):
-        return ops.permute_rows(_c(dy), ctx.perm, gather=not ctx.gather), None, None
+        return ops.permute_rows(_c(dy), ctx.perm, gather=not ctx.gather), None, None, None
 
 
-def permute_rows(x, perm, gather: bool):
+def permute_rows(x, perm, gather: bool, emit_pair: bool = False):
+    """``emit_pair``: the permuted rows feed projections - their bf16 pair leaves with the permutation pass."""
     if x.shape[0] == 0:
         return x
-    return _PermuteRows.apply(x, perm, gather)
+    return _PermuteRows.apply(x, perm, gather, emit_pair)
 
 
 class _GatherRows(Function):
@@ -332,14 +343,23 @@ class _PointNet(Function):
         xt = ops.transpose(x)                                       # [n_obj, c_in, P] -> [n_obj, P, round4(c_in)]
         ldx = xt.shape[2]
         xr = xt.view(n_obj * n_pts, ldx)[:, :c_in]                  # rows = points
-        h1 = ops.linear(xr, w1, b1, act=ACT_RELU)
-        h2 = ops.linear(h1, w2, b2, act=ACT_RELU)
+        pairs = _pairs_engine(w2.shape[0], w2.shape[1])
+        h1p = dz2p = None
+        if pairs:                                                   # h1's pair feeds the second projection and dW2 = dZ2^T H1
+            h1, h1p = ops.linear(xr, w1, b1, act=ACT_RELU, emit_split="bf16")
+            h2 = ops.linear(h1, w2, b2, act=ACT_RELU, x_split=h1p)
+        else:
+            h1 = ops.linear(xr, w1, b1, act=ACT_RELU)
+            h2 = ops.linear(h1, w2, b2, act=ACT_RELU)
         dz3, db3 = ops.act_bwd(_c(dout), out, ACT_RELU)            # max of ReLU outputs: zero where the pooled value is 0
         dw3, dh2 = ops.pointnet_pool_bwd(dz3, arg, h2, w3, n_pts)
-        dz2, db2 = ops.act_bwd(dh2, h2, ACT_RELU)
-        dw2 = weight_grad(dz2, h1)
-        if _pairs_engine(w2.shape[0], w2.shape[1]):
-            dh1 = ops.gemm_nn(ops.act_pair(dz2), ops.weight_pair(w2), w2.shape[1])
+        if pairs:
+            dz2, db2, dz2p = ops.act_bwd(dh2, h2, ACT_RELU, emit_pair=True, return_pair=True)
+        else:
+            dz2, db2 = ops.act_bwd(dh2, h2, ACT_RELU)
+        dw2 = weight_grad(dz2, h1, dz_pair=dz2p, x_pair=h1p)
+        if pairs:
+            dh1 = ops.gemm_nn(dz2p if dz2p is not None else ops.act_pair(dz2), ops.weight_pair(w2), w2.shape[1])
         else:
             dh1 = ops.linear(dz2, ops.transpose(w2)[:, :w2.shape[0]], cache_w=False)
         dz1, db1 = ops.act_bwd(dh1, h1, ACT_RELU)

@@ -469,7 +469,8 @@ __global__ void dropout_kernel(const float* __restrict__ x, int64_t ldx, float* 
 // of element (r, c) is r * cols + c), without its 64-bit division per element.
 __global__ void dropout_vec_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy, int64_t rows,
                                    int cols4, uint32_t thresh, float inv_keep, uint64_t seed, uint64_t offset,
-                                   const uint64_t* __restrict__ device_step) {
+                                   const uint64_t* __restrict__ device_step, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                   int64_t ld_pair) {
     pdl_entry();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows * cols4) return;
@@ -483,6 +484,12 @@ __global__ void dropout_vec_kernel(const float* __restrict__ x, int64_t ldx, flo
     v.z = mix32(base + 2) >= thresh ? v.z * inv_keep : 0.f;
     v.w = mix32(base + 3) >= thresh ? v.w * inv_keep : 0.f;
     *reinterpret_cast<float4*>(y + r * ldy + c) = v;
+    if (hi) {                                                // the consumer is a projection: its bf16 (hi, lo) operand pair from this pass
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2(v.x, v.y, h0, l0); split_bf16x2(v.z, v.w, h1, l1);
+        *reinterpret_cast<uint2*>(hi + r * ld_pair + c) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(lo + r * ld_pair + c) = make_uint2(l0, l1);
+    }
 }
 
 // ------------------------------------------------------------------- BatchNorm1d with batch statistics
@@ -823,19 +830,35 @@ extern "C" int vlsat_pointnet_pool_bwd(const float* dz3, const int32_t* argmax, 
     return finish_launch();
 }
 
+static int dropout_launch(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int64_t cols, float p, uint64_t seed,
+                          uint64_t offset, const uint64_t* device_step, uint16_t* hi, uint16_t* lo, int64_t ld_pair, void* stream) {
+    const double th = (double)p * 4294967296.0;
+    const uint32_t thresh = th >= 4294967295.0 ? 4294967295u : (uint32_t)th;
+    const bool vec = cols % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0) && cols / 4 < (1ll << 31);
+    if (hi && !(vec && ld_pair % 4 == 0 && ((((uintptr_t)hi | (uintptr_t)lo) & 7) == 0))) return VLSAT_ERR_UNSUPPORTED;
+    if (vec)
+        launch_k(dropout_vec_kernel, dim3((unsigned)ceil_div(rows * (cols / 4), 256)), dim3(256), 0, (cudaStream_t)stream, x, ldx, y, ldy, rows,
+                 (int)(cols / 4), thresh, 1.f / (1.f - p), seed, offset, device_step, hi, lo, ld_pair);
+    else
+        launch_k(dropout_kernel, dim3((unsigned)ceil_div(rows * cols, 256)), dim3(256), 0, (cudaStream_t)stream, x, ldx, y, ldy, rows, cols, thresh, 1.f / (1.f - p), seed, offset, device_step);
+    return finish_launch();
+}
+
 extern "C" int vlsat_dropout(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int64_t cols, float p,
                              uint64_t seed, uint64_t offset, const uint64_t* device_step, void* stream) {
     VLSAT_REQUIRE(rows >= 0 && cols >= 0 && p >= 0.f && p < 1.f);
     if (rows == 0 || cols == 0) return VLSAT_OK;
     VLSAT_REQUIRE(x && y && ldx >= cols && ldy >= cols);
-    const double th = (double)p * 4294967296.0;
-    const uint32_t thresh = th >= 4294967295.0 ? 4294967295u : (uint32_t)th;
-    if (cols % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0) && cols / 4 < (1ll << 31))
-        launch_k(dropout_vec_kernel, dim3((unsigned)ceil_div(rows * (cols / 4), 256)), dim3(256), 0, (cudaStream_t)stream, x, ldx, y, ldy, rows,
-                 (int)(cols / 4), thresh, 1.f / (1.f - p), seed, offset, device_step);
-    else
-        launch_k(dropout_kernel, dim3((unsigned)ceil_div(rows * cols, 256)), dim3(256), 0, (cudaStream_t)stream, x, ldx, y, ldy, rows, cols, thresh, 1.f / (1.f - p), seed, offset, device_step);
-    return finish_launch();
+    return dropout_launch(x, ldx, y, ldy, rows, cols, p, seed, offset, device_step, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int vlsat_dropout_pair(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int64_t cols, float p,
+                                  uint64_t seed, uint64_t offset, const uint64_t* device_step, void* pair_hi, void* pair_lo,
+                                  int64_t ld_pair, void* stream) {
+    VLSAT_REQUIRE(rows >= 0 && cols >= 0 && p >= 0.f && p < 1.f);
+    if (rows == 0 || cols == 0) return VLSAT_OK;
+    VLSAT_REQUIRE(x && y && pair_hi && pair_lo && ldx >= cols && ldy >= cols && ld_pair >= cols);
+    return dropout_launch(x, ldx, y, ldy, rows, cols, p, seed, offset, device_step, (uint16_t*)pair_hi, (uint16_t*)pair_lo, ld_pair, stream);
 }
 
 extern "C" int vlsat_batchnorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float* mean, float* rstd,

@@ -161,6 +161,12 @@ linear_smallk_kernel(const LinearArgs a) {
         o[j] = apply_act(acc, a.epi.act) * a.epi.alpha;
     }
     *reinterpret_cast<float4*>(a.y + m * a.ldy + n) = make_float4(o[0], o[1], o[2], o[3]);
+    if (a.epi.split_hi) {                               // bf16 (hi, lo) pair of the same four outputs (vectorisable layout checked by the host)
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2(o[0], o[1], h0, l0); split_bf16x2(o[2], o[3], h1, l1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.epi.split_hi) + m * a.epi.ld_split + n) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.epi.split_lo) + m * a.epi.ld_split + n) = make_uint2(l0, l1);
+    }
 }
 
 template <int BM, int BN, int T>
@@ -181,7 +187,8 @@ int linear_simt(const float* x, int64_t ldx, const float* w, int64_t ldw, float*
     // plain bias + activation epilogue on a tiny reduction: the register-row kernel
     const vlsat_epilogue& e = a.epi;
     if (K <= 16 && N % 4 == 0 && N <= 1024 && y && ldy % 4 == 0 && ((uintptr_t)y % 16 == 0) && !e.gather_a && !e.gather_b && !e.residual &&
-        !e.scale_ptr && !e.split_hi && !e.bias_per_row && M * (N / 4) < (1ll << 40) && (N * K + N) * 4 <= 48 * 1024) {
+        !e.scale_ptr && !e.bias_per_row && M * (N / 4) < (1ll << 40) && (N * K + N) * 4 <= 48 * 1024 &&
+        (!e.split_hi || (e.split_fmt == VLSAT_SPLIT_BF16 && e.ld_split % 4 == 0 && ((((uintptr_t)e.split_hi | (uintptr_t)e.split_lo) & 7) == 0)))) {
         const size_t smem = (size_t)(N * K + N) * sizeof(float);
         launch_k(linear_smallk_kernel<16>, dim3((unsigned)ceil_div(M * (N / 4), 256)), dim3(256), smem, st, a);
         return finish_launch();

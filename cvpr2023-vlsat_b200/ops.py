@@ -257,6 +257,19 @@ def act_pair(x: torch.Tensor):
     return pair
 
 
+def view_rows(x: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    """``x.view(rows, cols)`` that keeps the remembered bf16 pair: [E, H * d] seen as (edge, head) rows [E * H, d] is the same
+    memory for the compact pair tensors too, so the projection over the rows needs no split pass of its own."""
+    y = x.view(rows, cols)
+    ent = getattr(x, "_vlsat_pair", None)
+    if ent is not None and ent[0] == x._version and ent[1][0].shape == x.shape and ent[1][0].is_contiguous() and ent[1][1].is_contiguous():
+        try:
+            y._vlsat_pair = (y._version, (ent[1][0].view(rows, cols), ent[1][1].view(rows, cols)))
+        except AttributeError:
+            pass
+    return y
+
+
 def _weight_split(w: torch.Tensor, ldw: int, fmt: int):
     """(hi, lo) copies of a weight (view) in pair format ``fmt``, cached until the parameter is written again."""
     key = (w.data_ptr(), tuple(w.shape), ldw, fmt)
@@ -1085,13 +1098,23 @@ def pointnet_pool_bwd(dz3, arg, h2, w3, n_pts: int):
     return dw3, dh2
 
 
-def dropout(x: torch.Tensor, p: float, seed: int, offset: int, device_step: Optional[torch.Tensor] = None) -> torch.Tensor:
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int, device_step: Optional[torch.Tensor] = None,
+            emit_pair: bool = False) -> torch.Tensor:
+    """Counter-based dropout (csrc/backward.cu). ``emit_pair``: the result feeds a projection - the same pass also writes its
+    bf16 (hi, lo) pair and remembers it on the returned tensor (``act_pair`` finds it); ignored where pairs do not apply."""
     xp, ldx = _rows(x, "x")
     out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
     if device_step is not None and (device_step.dtype != torch.int64 or not device_step.is_cuda):
         raise TypeError("dropout: device_step must be a CUDA int64 scalar tensor")
-    _lib.check(_call("vlsat_dropout", xp, ldx, out.data_ptr(), x.shape[1], x.shape[0], x.shape[1], p, seed, offset,
-                     device_step.data_ptr() if device_step is not None else None, _stream()), "vlsat_dropout")
+    step_p = device_step.data_ptr() if device_step is not None else None
+    r, c = x.shape
+    if (emit_pair and r > 0 and c % 8 == 0 and c >= 32 and ldx % 4 == 0 and xp % 16 == 0 and tensor_cores_enabled() and default_fmt(c) == FMT_BF16):
+        pair = torch.empty((2, r, c), device=x.device, dtype=torch.bfloat16)
+        _lib.check(_call("vlsat_dropout_pair", xp, ldx, out.data_ptr(), c, r, c, p, seed, offset, step_p, pair[0].data_ptr(), pair[1].data_ptr(),
+                         c, _stream()), "vlsat_dropout_pair")
+        out._vlsat_pair = (out._version, (pair[0], pair[1]))
+        return out
+    _lib.check(_call("vlsat_dropout", xp, ldx, out.data_ptr(), c, r, c, p, seed, offset, step_p, _stream()), "vlsat_dropout")
     return out
 
 

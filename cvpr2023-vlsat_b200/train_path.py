@@ -146,24 +146,26 @@ def edge_attention(m, x, edge, g: GraphContext, x_value=None, aggr=None):
     a_src = A.linear(x, w1.weight[:, :Dn])
     b_dst = A.linear(xv, w1.weight[:, Dn + De:])
     h1 = A.linear(edge, w1.weight[:, Dn:Dn + De], w1.bias, RELU, gather=(a_src, g.src, b_dst, g.dst), emit_pair=True)
-    new_edge = A.linear(h1, w2.weight, w2.bias)
+    new_edge = A.linear(h1, w2.weight, w2.bias, emit_pair=True)           # read next by the edge cross-attention's q / k / v projections
     # attention MLP over rows (e, h)
     convs = m._convs()
     c1, c2 = convs[0].weight.squeeze(-1), convs[1].weight.squeeze(-1)
     wq, bq = _head_major(m.proj_query[0], dn, H)
     wv, bv = _head_major(m.proj_value[0], do, H)
-    q_hm = A.linear(x, wq, bq)                                            # [N, H*d_n]
+    q_hm = A.linear(x, wq, bq, emit_pair=True)                            # [N, H*d_n]
     v_hm = A.linear(xv, wv, bv)                                           # [N, H*d_o]
-    qc = A.linear(q_hm.view(N * H, dn), c1[:, :dn], convs[0].bias)        # [N*H, hid]: C1[:, :d_n] q + c1
+    # (node, head) / (edge, head) rows are views of the head-major projections; ops.view_rows carries the emitted pair along
+    qc = A.linear(ops.view_rows(q_hm, N * H, dn), c1[:, :dn], convs[0].bias)   # [N*H, hid]: C1[:, :d_n] q + c1
     rows_q = g.head_rows(H)                                               # row (e, h) -> row src(e)*H + h
+    drop = next((mod.p for mod in m.nn if isinstance(mod, torch.nn.Dropout)), 0.0)
+    dropping = tr and drop > 0.0                                          # then the pair of `hidden` leaves with the dropout pass
     if m.use_edge:
         wk, bk = _head_major(m.proj_edge[0], de, H)
-        k_hm = A.linear(edge, wk, bk)                                     # [E, H*d_e]
-        hidden = A.linear(k_hm.view(E * H, de), c1[:, dn:], None, RELU, gather=(qc, rows_q, None, None))
+        k_hm = A.linear(edge, wk, bk, emit_pair=True)                     # [E, H*d_e]
+        hidden = A.linear(ops.view_rows(k_hm, E * H, de), c1[:, dn:], None, RELU, gather=(qc, rows_q, None, None), emit_pair=not dropping)
     else:
         hidden = A.relu(A.gather_rows(qc, rows_q))                        # MLP [d_n, 2 d_n, d_o] on the query alone
-    drop = next((mod.p for mod in m.nn if isinstance(mod, torch.nn.Dropout)), 0.0)
-    hidden = A.dropout(hidden, drop, tr)
+    hidden = A.dropout(hidden, drop, tr, emit_pair=True)
     t = A.linear(hidden, c2, convs[1].bias)                               # [E*H, d_o]
     xx, prob = A.gat_softmax_aggr(t, v_hm, g, H, aggr or getattr(m, "_aggr", "max"))
     return xx, new_edge, prob
@@ -184,8 +186,8 @@ def mmg_forward(m, o3, o2, e3, e2, edge_index, batch_ids, obj_center):
     sctx = SceneContextTrain(batch_ids, obj_center)
     bias = distance_bias(m.self_attn_fc, sctx)
     g = GraphContext(edge_index, n, m.flow)
-    e3 = A.permute_rows(e3.contiguous(), g.perm, True)
-    e2 = A.permute_rows(e2.contiguous(), g.perm, True)
+    e3 = A.permute_rows(e3.contiguous(), g.perm, True, emit_pair=True)    # both feed the layer's edge projections
+    e2 = A.permute_rows(e2.contiguous(), g.perm, True, emit_pair=True)
     p = m.drop_out.p
     for i in range(m.depth):
         act = (i < m.depth - 1) or m.depth == 1
@@ -195,10 +197,12 @@ def mmg_forward(m, o3, o2, e3, e2, edge_index, batch_ids, obj_center):
         o2, e2, _ = gat_layer(m.gcn_2ds[i], o2, e2, g, relu_nodes=act)
         e2 = mha_all(m.cross_attn_rel[i], e2, e3)
         if act:
-            e3, e2 = A.relu(e3), A.relu(e2)                               # the node streams got theirs in the epilogue
-            o3, o2 = A.dropout(o3, p, m.training), A.dropout(o2, p, m.training)
-            e3, e2 = A.dropout(e3, p, m.training), A.dropout(e2, p, m.training)
-    return o3, o2, A.permute_rows(e3, g.perm, False), A.permute_rows(e2, g.perm, False)
+            dropping = m.training and p > 0.0
+            e3, e2 = A.relu(e3, not dropping), A.relu(e2, not dropping)   # the node streams got theirs in the epilogue
+            # the next layer's projections read these: their bf16 pairs leave with the dropout pass
+            o3, o2 = A.dropout(o3, p, m.training, emit_pair=True), A.dropout(o2, p, m.training, emit_pair=True)
+            e3, e2 = A.dropout(e3, p, m.training, emit_pair=True), A.dropout(e2, p, m.training, emit_pair=True)
+    return o3, o2, A.permute_rows(e3, g.perm, False, emit_pair=True), A.permute_rows(e2, g.perm, False, emit_pair=True)
 
 
 def gnn_layers_forward(m, node, edge, edge_index, obj_center, batch_ids):
@@ -207,7 +211,7 @@ def gnn_layers_forward(m, node, edge, edge_index, obj_center, batch_ids):
     sctx = SceneContextTrain(batch_ids, obj_center)
     bias = distance_bias(m.self_attn_fc, sctx)
     g = GraphContext(edge_index, n, m.flow)
-    edge = A.permute_rows(edge.contiguous(), g.perm, True)
+    edge = A.permute_rows(edge.contiguous(), g.perm, True, emit_pair=True)
     p = m.drop_out.p if m.drop_out is not None else 0.0
     probs = []
     for i in range(m.num_layers):
@@ -215,8 +219,8 @@ def gnn_layers_forward(m, node, edge, edge_index, obj_center, batch_ids):
         node = mha_scenes(m.self_attn[i], node, node, bias, sctx)
         node, edge, prob = gat_layer(m.gconvs[i], node, edge, g, relu_nodes=act)
         if act:
-            edge = A.relu(edge)
-            node, edge = A.dropout(node, p, m.training), A.dropout(edge, p, m.training)
+            edge = A.relu(edge, not (m.training and p > 0.0))
+            node, edge = A.dropout(node, p, m.training, emit_pair=True), A.dropout(edge, p, m.training, emit_pair=True)
         H, do = m.gconvs[i].edgeatten.num_heads, m.gconvs[i].edgeatten.d_o
         E = g.num_edges
         pr = prob.view(E, H, do).permute(0, 2, 1).contiguous()           # [E, d_o, H] as the reference returns it
@@ -259,7 +263,7 @@ def mmgnet_forward(m, obj_points, obj_2d_feats, edge_indices, descriptor, batch_
         a = A.linear(g2, p0.weight[:, :512])
         b = A.linear(g2, p0.weight[:, 512:1024])
         hh = A.linear(ge2, p0.weight[:, 1024:], p0.bias, RELU, gather=(a, src, b, dst))      # Linear Dropout ReLU: commute
-        hh = A.dropout(hh, m.triplet_projector_2d[1].p, tr)
+        hh = A.dropout(hh, m.triplet_projector_2d[1].p, tr, emit_pair=True)
         dis = A.linear(hh, p3.weight, p3.bias)
     rel_cls_3d = rel_classifier(m.rel_predictor_3d, ge3)
     rel_cls_2d = rel_classifier(m.rel_predictor_2d, ge2)

@@ -422,6 +422,11 @@ int vlsat_pointnet_pool_bwd(const float* dz3, const int32_t* argmax, const float
  * training step bumps it so that every replay draws fresh masks. */
 int vlsat_dropout(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int64_t cols, float p,
                   uint64_t seed, uint64_t offset, const uint64_t* device_step, void* stream);
+/* The same pass also writing the bf16 (hi, lo) pair of y, compact rows of ld_pair elements (cols % 4 == 0, 16-byte aligned x / y
+ * rows, ld_pair % 4 == 0): the operand a following projection reads, without a separate split pass. */
+int vlsat_dropout_pair(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int64_t cols, float p,
+                       uint64_t seed, uint64_t offset, const uint64_t* device_step, void* pair_hi, void* pair_lo,
+                       int64_t ld_pair, void* stream);
 
 /* nn.BatchNorm1d of mlp_3d (SGFN_MMG/model.py:108). batch_stats = 1: mean / rstd computed from x (biased variance) and
  * written, running stats (nullable) updated with `momentum` and the unbiased variance; batch_stats = 0: mean / rstd

@@ -155,6 +155,43 @@ def test_dropout_mask_statistics_and_backward():
     assert torch.equal(A.dropout(x, 0.3, True), y)              # and is reproducible
     assert A.dropout(x, 0.3, False) is x and A.dropout(x, 0.0, True) is x
 
+def _pair_sum(pair):
+    return pair[0].float() + pair[1].float()
+
+
+def test_pairs_emitted_by_dropout_permutation_views_and_small_k_projection():
+    """Producers that hand the next projection its bf16 (hi, lo) pair: the pair must be the split of exactly the fp32 result
+    (hi + lo within 2^-16 relative), remembered on the returned tensor, and survive the (rows, head) view."""
+    A.DropoutState.manual_seed(7)
+    x = rnd(1000, 128, seed=160)
+    y = A.dropout(x, 0.4, True, emit_pair=True)
+    A.DropoutState.manual_seed(7)
+    assert torch.equal(A.dropout(x, 0.4, True), y)                          # same mask and values as the plain pass
+    pair = ops.act_pair(y)
+    assert pair is y._vlsat_pair[1], "dropout must have remembered the pair"
+    assert torch.allclose(_pair_sum(pair), y, rtol=2e-5, atol=0.0)
+    # permutation (scatter and gather forms)
+    perm = torch.randperm(1000, generator=torch.Generator().manual_seed(3)).to(DEV, torch.int32)
+    for gather in (True, False):
+        z = A.permute_rows(x, perm, gather, emit_pair=True)
+        assert torch.equal(z, A.permute_rows(x, perm, gather))
+        assert torch.allclose(_pair_sum(z._vlsat_pair[1]), z, rtol=2e-5, atol=0.0)
+    # (edge, head) rows as a view of a head-major projection
+    w = rnd(512, 128, seed=161) / 11.0
+    k_hm = A.linear(x, w, None, emit_pair=True)                             # [1000, 8 * 64]
+    rows = ops.view_rows(k_hm, 8000, 64)
+    assert rows.data_ptr() == k_hm.data_ptr() and tuple(rows.shape) == (8000, 64)
+    assert torch.allclose(_pair_sum(ops.act_pair(rows)), rows, rtol=2e-5, atol=0.0)
+    assert ops.act_pair(rows)[0].data_ptr() == k_hm._vlsat_pair[1][0].data_ptr()
+    plain = ops.view_rows(rnd(1000, 128, seed=165), 2000, 64)               # no pair remembered: a plain view
+    assert getattr(plain, "_vlsat_pair", None) is None
+    # K = 3 register-row kernel (PointNet's first layer in the backward recompute)
+    pts, w1, b1 = rnd(5000, 3, seed=162), rnd(64, 3, seed=163), rnd(64, seed=164)
+    h, hp = ops.linear(pts, w1, b1, act=ops.ACT_RELU, emit_split="bf16")
+    want = torch.relu(pts.double() @ w1.double().t() + b1.double()).float()
+    close64(h, want.double(), "small-K projection", rtol=1e-5, atol_scale=1e-6)
+    assert torch.allclose(_pair_sum(hp), h, rtol=2e-5, atol=0.0)
+
 
 @pytest.mark.parametrize("aggr", ["max", "add", "mean"])
 def test_gat_softmax_aggr_fwd_bwd(aggr):
