@@ -36,6 +36,13 @@ if "flash_fwd" in which:
     (qp, _), (kp, _), (_, vt) = ops.bf16_split_t(q), ops.bf16_split_t(k), ops.bf16_split_t(v)
     for _ in range(2):
         ops.flash_attn_bf16(qp, kp, vt, 9600, 8)
+if "flash_fwd_bf16" in which:                       # single-pass bf16 mode: which pipe fills up
+    ops.set_precision("bf16")
+    q, k, v = (torch.randn(9600, 512, generator=g).to(dev) for _ in range(3))
+    (qp, _), (kp, _), (_, vt) = ops.bf16_split_t(q), ops.bf16_split_t(k), ops.bf16_split_t(v)
+    for _ in range(2):
+        ops.flash_attn_bf16(qp, kp, vt, 9600, 8)
+    ops.set_precision("fp32")
 if "flash_bwd" in which:
     q, k, v, dout = (torch.randn(9600, 512, generator=g).to(dev) for _ in range(4))
     (qp, qt), (kp, kt), (vp, vt) = ops.bf16_split_t(q), ops.bf16_split_t(k), ops.bf16_split_t(v)
