@@ -93,7 +93,7 @@ class _Linear(Function):
         n = dy.shape[1]
         d_scale = None
         if has_scale and need[9]:
-            d_scale = torch.zeros_like(scale)
+            d_scale = ops.zeros(tuple(scale.shape), scale.device)
             ops.dot_accum(dy, y, d_scale)                       # y = e^s z  =>  dy/ds = y
         d_res = dy if (has_res and need[8]) else None
         plain = ctx.act == ACT_NONE and not has_scale
@@ -134,9 +134,9 @@ class _Linear(Function):
             if need[1]:
                 dw = weight_grad(dz, x)                         # [N, K], reduction over the rows
         if has_ga and need[4]:
-            d_ga = ops.scatter_add_rows(dz, ia, torch.zeros(ctx.shapes[0], device=dz.device, dtype=torch.float32))
+            d_ga = ops.scatter_add_rows(dz, ia, ops.zeros(tuple(ctx.shapes[0]), dz.device))
         if has_gb and need[6]:
-            d_gb = ops.scatter_add_rows(dz, ib, torch.zeros(ctx.shapes[1], device=dz.device, dtype=torch.float32))
+            d_gb = ops.scatter_add_rows(dz, ib, ops.zeros(tuple(ctx.shapes[1]), dz.device))
         return dx, dw, db, None, d_ga, None, d_gb, None, d_res, d_scale, None
 
 
@@ -316,7 +316,7 @@ class _GatherRows(Function):
 
     @staticmethod
     def backward(ctx, dy):
-        out = torch.zeros(ctx.shape, device=dy.device, dtype=torch.float32)
+        out = ops.zeros(tuple(ctx.shape), dy.device)
         return ops.scatter_add_rows(_c(dy), ctx.idx, out), None
 
 

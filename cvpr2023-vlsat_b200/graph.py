@@ -115,9 +115,11 @@ class GraphedTrainStep:
         self._step = None
 
     def _run(self, static_in):
-        outs = self.model(*static_in, istrain=True)
-        loss = self.loss_fn(outs)
-        loss.backward()
+        from . import ops
+        with ops.zero_arena(self, static_in[0].device):      # the backward's small accumulation targets: one fill per step
+            outs = self.model(*static_in, istrain=True)
+            loss = self.loss_fn(outs)
+            loss.backward()
         return loss, outs
 
     def capture(self, args, stats):

@@ -6,6 +6,7 @@ No wrapper has a CPU or PyTorch compute path: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import contextlib
 import os
 from typing import Optional, Tuple
 
@@ -81,6 +82,64 @@ def _call(name: str, *args, work=(0.0, 0.0), tag: str = ""):
     b.record()
     _timer.events.append((name + tag, a, b, float(work[0]), float(work[1])))
     return st
+
+
+# ------------------------------------------------------------------------------------------ zero arena
+# The backward pass accumulates into ~150 small zero-initialised buffers per step (bias gradients, LayerNorm dgamma / dbeta,
+# scatter-add targets, slab-free weight gradients): one fill launch each. Inside ``zero_arena`` they are carved out of ONE buffer
+# that is zeroed by one fill at the start of the step. The buffer is allocated afresh every step (inside a CUDA-graph capture:
+# once, as a node of the graph), so slices never alias across steps; gradients that autograd keeps as ``.grad`` keep their arena
+# alive. Sized from the previous step's demand; anything that does not fit falls back to ``torch.zeros``.
+ZERO_ARENA_MAX_ITEM = 2 << 20          # bytes: larger buffers are bandwidth-sized fills anyway
+
+
+class _ZeroArena:
+    def __init__(self, hint_bytes: int, device):
+        self.demand = 0                 # bytes asked for during this step (256-byte granules): next step's size
+        self.off = 0
+        self.fallbacks = 0
+        # allocated up front on the step's main stream: every later use, on any stream, is ordered behind this fill
+        self.buf = torch.zeros((hint_bytes // 4,), device=device, dtype=torch.float32) if hint_bytes > 0 and device is not None else None
+
+
+_arena: Optional[_ZeroArena] = None
+
+
+@contextlib.contextmanager
+def zero_arena(owner, device):
+    """``owner`` carries the size hint from step to step (attribute ``_zero_arena_bytes``). VLSAT_ZERO_ARENA=0 disables."""
+    global _arena
+    if os.environ.get("VLSAT_ZERO_ARENA", "1") == "0" or torch.device(device).type != "cuda":
+        yield None
+        return
+    prev = _arena
+    a = _ZeroArena(int(getattr(owner, "_zero_arena_bytes", 0)), device)
+    _arena = a
+    try:
+        yield a
+    finally:
+        _arena = prev
+        owner._zero_arena_bytes = a.demand
+        owner._zero_arena_fallbacks = a.fallbacks
+
+
+def zeros(shape, device) -> torch.Tensor:
+    """fp32 zeros for an accumulation target of the backward pass: a slice of the step's arena when one is active."""
+    a = _arena
+    numel = 1
+    for d in shape:
+        numel *= int(d)
+    nbytes = numel * 4
+    if a is None or nbytes == 0 or nbytes > ZERO_ARENA_MAX_ITEM:
+        return torch.zeros(shape, device=device, dtype=torch.float32)
+    granule = (nbytes + 255) // 256 * 256
+    a.demand += granule
+    if a.buf is None or a.buf.device != torch.device(device) or a.off + granule > a.buf.numel() * 4:
+        a.fallbacks += 1
+        return torch.zeros(shape, device=device, dtype=torch.float32)
+    out = a.buf[a.off // 4: a.off // 4 + numel].view(shape)
+    a.off += granule
+    return out
 
 
 # ------------------------------------------------------------------------------------------ two-stream regions
@@ -926,7 +985,7 @@ def act_bwd(dy: torch.Tensor, y: Optional[torch.Tensor], act: int, want_dz: bool
     m, n = dy.shape
     yp, ldy = (None, 0) if y is None else _rows(y, "y")
     dz = torch.empty((m, n), device=dy.device, dtype=torch.float32) if want_dz else None
-    db = torch.zeros((n,), device=dy.device, dtype=torch.float32) if want_dbias else None
+    db = zeros((n,), dy.device) if want_dbias else None
     vec = (n % 4 == 0 and lddy % 4 == 0 and (y is None or ldy % 4 == 0) and dp % 16 == 0 and (yp is None or yp % 16 == 0) and m > 0)
     if vec:
         pair = None
@@ -981,8 +1040,8 @@ def add_layernorm_bwd(dy, x, res, gamma, beta, eps: float, relu: bool):
     rp, ldr = (None, 0) if res is None else _rows(res, "res")
     m, d = x.shape
     dx = torch.empty((m, d), device=x.device, dtype=torch.float32)
-    dg = torch.zeros((d,), device=x.device, dtype=torch.float32)
-    db = torch.zeros((d,), device=x.device, dtype=torch.float32)
+    dg = zeros((d,), x.device)
+    db = zeros((d,), x.device)
     _lib.check(_call("vlsat_add_layernorm_bwd", dp, lddy, xp, ldx, rp, ldr, gamma.data_ptr(), beta.data_ptr(), dx.data_ptr(), d,
                      dg.data_ptr(), db.data_ptr(), m, d, eps, int(relu), _stream()), "vlsat_add_layernorm_bwd")
     return dx, dg, db
@@ -1011,7 +1070,7 @@ def gat_softmax_aggr_bwd(dxx, prob, v_hm, dst, row_ptr, arg, n_nodes: int, n_hea
     d_o = v_hm.shape[1] // n_heads
     e = prob.shape[0] // n_heads
     dt = torch.empty_like(prob)
-    dv = torch.zeros((n_nodes, n_heads * d_o), device=dxx.device, dtype=torch.float32)
+    dv = zeros((n_nodes, n_heads * d_o), dxx.device)
     _lib.check(_call("vlsat_gat_softmax_aggr_bwd", dp, lddxx, prob.data_ptr() if e else None, vp_, ldv, dst.data_ptr() if e else None,
                      row_ptr.data_ptr(), arg.data_ptr() if arg is not None else None, n_nodes, e, n_heads, d_o, AGGR[aggr],
                      dt.data_ptr() if e else None, dv.data_ptr(), dv.shape[1], _stream()), "vlsat_gat_softmax_aggr_bwd")
@@ -1076,8 +1135,8 @@ def node_attn_bias_bwd(q, k, v, bias, pair_off, seg_start, seg_end, dout, n_head
     qp, ldq = _rows(q, "q"); kp, ldk = _rows(k, "k"); vp_, ldv = _rows(v, "v"); dp, lddo = _rows(dout, "dout")
     n, d = q.shape
     dq = torch.empty((n, d), device=q.device, dtype=torch.float32)
-    dk = torch.zeros((k.shape[0], d), device=q.device, dtype=torch.float32)
-    dv = torch.zeros((v.shape[0], d), device=q.device, dtype=torch.float32)
+    dk = zeros((k.shape[0], d), q.device)
+    dv = zeros((v.shape[0], d), q.device)
     dbias = torch.empty_like(bias)
     _lib.check(_call("vlsat_node_attn_bias_bwd", qp, ldq, kp, ldk, vp_, ldv, bias.data_ptr(), pair_off.data_ptr(), seg_start.data_ptr(),
                      seg_end.data_ptr(), dp, lddo, n_heads, d // n_heads, max_scene, dq.data_ptr(), d, dk.data_ptr(), d, dv.data_ptr(), d,
@@ -1089,8 +1148,8 @@ def pointnet_pool_bwd(dz3, arg, h2, w3, n_pts: int):
     """(dW3 [c_out, c2], dh2 [n_obj*n_pts, c2])."""
     n_obj, c_out = dz3.shape
     c2 = w3.shape[1]
-    dw3 = torch.zeros((c_out, c2), device=dz3.device, dtype=torch.float32)
-    dh2 = torch.zeros((n_obj * n_pts, c2), device=dz3.device, dtype=torch.float32)
+    dw3 = zeros((c_out, c2), dz3.device)
+    dh2 = zeros((n_obj * n_pts, c2), dz3.device)
     if not (dz3.is_contiguous() and h2.is_contiguous() and w3.is_contiguous() and arg.is_contiguous()):
         raise ValueError("pointnet_pool_bwd: operands must be contiguous")
     _lib.check(_call("vlsat_pointnet_pool_bwd", dz3.data_ptr(), arg.data_ptr(), h2.data_ptr(), w3.data_ptr(), n_obj, n_pts, c_out, c2,
@@ -1158,7 +1217,7 @@ def wgrad_small(dz: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     dp, lddz = _rows(dz, "dz"); xp, ldx = _rows(x, "x")
     m, n = dz.shape
     k = x.shape[1]
-    dw = torch.zeros((n, k), device=dz.device, dtype=torch.float32)
+    dw = zeros((n, k), dz.device)
     _lib.check(_call("vlsat_wgrad_small", dp, lddz, xp, ldx, m, n, k, dw.data_ptr(), k, _stream(), work=(2.0 * m * n * k, 4.0 * m * (n + k))),
                "vlsat_wgrad_small")
     return dw

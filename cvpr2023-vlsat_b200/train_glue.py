@@ -434,9 +434,10 @@ class TrainStep:
             loss, _ = self._graphed(obj_points, obj_2d_feats, edge_index, descriptor, batch_ids, scene_stats=scene_stats)
         else:
             self._current = targets
-            outs = self.model(obj_points, obj_2d_feats, edge_index, descriptor, batch_ids, istrain=True)
-            loss = self._loss(outs)
-            loss.backward()
+            with ops.zero_arena(self, obj_points.device):
+                outs = self.model(obj_points, obj_2d_feats, edge_index, descriptor, batch_ids, istrain=True)
+                loss = self._loss(outs)
+                loss.backward()
         return loss
 
     @property

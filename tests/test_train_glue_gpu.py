@@ -225,3 +225,46 @@ def test_graphed_train_step_matches_eager_train_step():
             agree.append(float(torch.dot(de, dg) / (de.norm() * dg.norm() + 1e-30)))
     agree.sort()
     assert agree[len(agree) // 10] > 0.9, agree[:20]
+
+
+def test_zero_arena_serves_the_backward_accumulators(monkeypatch):
+    """The small zero-initialised accumulation targets of the backward (bias gradients, LayerNorm dgamma / dbeta, scatter-add
+    targets) come out of one per-step arena (ops.zero_arena): same gradients as with one torch.zeros each, the second step
+    fits entirely, and nothing aliases across steps (eager and graphed)."""
+    from vlsat_b200 import autograd as A
+    from vlsat_b200 import synth
+    b = synth.make_config_batch("cfg1", seed=5).to(DEV)
+    gen = torch.Generator().manual_seed(11)
+    n, e = b.obj_points.shape[0], b.edge_indices.shape[1]
+    gt_cls = torch.randint(0, 160, (n,), generator=gen).to(DEV)
+    gt_rel = (torch.rand(e, 26, generator=gen) < 0.1).float().to(DEV)
+    text = torch.nn.functional.normalize(torch.randn(e, 512, generator=gen), dim=-1).to(DEV)
+
+    def grads(arena: str, graphed: bool):
+        monkeypatch.setenv("VLSAT_ZERO_ARENA", arena)
+        A.DropoutState.manual_seed(99)
+        model = V.Mmgnet({"MODEL": V.DEFAULT_MODEL_CONFIG}, 160, 26)
+        synth.load_seeded(model, 0)
+        model = model.to(DEV).train()
+        ts = G.TrainStep(model, G.build_optimizer(model, lr=0.0, max_iteration=10), graphed=graphed)
+        out = []
+        for _ in range(2):
+            loss = ts.forward_backward(*b.forward_args(), gt_cls, gt_rel, text)
+            out.append((float(loss.detach()), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+            if not graphed:
+                model.zero_grad(set_to_none=True)
+        owner = ts._graphed if graphed else ts
+        return out, getattr(owner, "_zero_arena_bytes", 0), getattr(owner, "_zero_arena_fallbacks", -1)
+
+    for graphed in (False, True):
+        (ref, rb, _), (got, gb, gf) = grads("0", graphed), grads("1", graphed)
+        assert rb == 0 and gb > 0 and gf == 0, (rb, gb, gf)
+        for (l0, g0), (l1, g1) in zip(ref, got):
+            assert abs(l0 - l1) <= 1e-5 * abs(l0)
+            assert g0.keys() == g1.keys()
+            # gradients that vanish in exact arithmetic (everything upstream of the distance bias) are run-to-run noise of the
+            # atomic accumulation order: a floor relative to the largest gradient of the step, as in conftest.grad_floor
+            floor = 1e-6 * max(g.abs().max().item() for g in g0.values())
+            bad = {k: ((g0[k] - g1[k]).abs().max().item(), g0[k].abs().max().item()) for k in g0
+                   if (g0[k] - g1[k]).abs().max().item() > 2e-4 * g0[k].abs().max().item() + floor}
+            assert not bad, bad
