@@ -234,6 +234,34 @@ def dropout(x, p: float, training: bool, emit_pair: bool = False):
     return _Dropout.apply(x, float(p), emit_pair)
 
 
+# ------------------------------------------------------------------------------------------ weight column blocks
+class _SplitCols(Function):
+    """Column blocks of a weight [N, K] as views (``w[:, a:b]``), with ONE backward: the blocks' gradients concatenated.
+    Plain slicing gives every block its own SliceBackward - a zero fill of the whole [N, K], a copy into the slice and an add
+    per extra block (61 launches per training step for the split nn_edge / attention-MLP / pair-projector weights, 9 now)."""
+
+    @staticmethod
+    def forward(ctx, w, *sizes):
+        ctx.sizes, ctx.rows = sizes, w.shape[0]
+        return tuple(w.split(list(sizes), dim=1))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ref = next(g for g in grads if g is not None)
+        parts = [g if g is not None else torch.zeros((ctx.rows, n), device=ref.device, dtype=ref.dtype) for g, n in zip(grads, ctx.sizes)]
+        return (torch.cat(parts, 1),) + (None,) * len(ctx.sizes)
+
+
+def split_cols(w, sizes):
+    """``w[:, :s0], w[:, s0:s0+s1], ...`` (views of ``w``; sizes must add up to its width) with a single fused backward."""
+    sizes = tuple(int(n) for n in sizes)
+    if sum(sizes) != w.shape[1] or any(n <= 0 for n in sizes):
+        raise ValueError(f"split_cols: sizes {sizes} do not tile the {w.shape[1]} columns")
+    if not (torch.is_grad_enabled() and w.requires_grad):
+        return tuple(w.split(list(sizes), dim=1))
+    return _SplitCols.apply(w, *sizes)
+
+
 # ------------------------------------------------------------------------------------------ batch norm
 class _BatchNorm(Function):
     @staticmethod

@@ -143,9 +143,10 @@ def edge_attention(m, x, edge, g: GraphContext, x_value=None, aggr=None):
     tr = m.training
     # nn_edge on cat[x_i, e, x_j]: project per node, gather per edge
     w1, w2 = m.nn_edge[0], m.nn_edge[2]
-    a_src = A.linear(x, w1.weight[:, :Dn])
-    b_dst = A.linear(xv, w1.weight[:, Dn + De:])
-    h1 = A.linear(edge, w1.weight[:, Dn:Dn + De], w1.bias, RELU, gather=(a_src, g.src, b_dst, g.dst), emit_pair=True)
+    w1_src, w1_edge, w1_dst = A.split_cols(w1.weight, (Dn, De, w1.weight.shape[1] - Dn - De))    # one backward for the three blocks
+    a_src = A.linear(x, w1_src)
+    b_dst = A.linear(xv, w1_dst)
+    h1 = A.linear(edge, w1_edge, w1.bias, RELU, gather=(a_src, g.src, b_dst, g.dst), emit_pair=True)
     new_edge = A.linear(h1, w2.weight, w2.bias, emit_pair=True)           # read next by the edge cross-attention's q / k / v projections
     # attention MLP over rows (e, h)
     convs = m._convs()
@@ -155,14 +156,15 @@ def edge_attention(m, x, edge, g: GraphContext, x_value=None, aggr=None):
     q_hm = A.linear(x, wq, bq, emit_pair=True)                            # [N, H*d_n]
     v_hm = A.linear(xv, wv, bv)                                           # [N, H*d_o]
     # (node, head) / (edge, head) rows are views of the head-major projections; ops.view_rows carries the emitted pair along
-    qc = A.linear(ops.view_rows(q_hm, N * H, dn), c1[:, :dn], convs[0].bias)   # [N*H, hid]: C1[:, :d_n] q + c1
+    c1_q, c1_k = A.split_cols(c1, (dn, c1.shape[1] - dn)) if c1.shape[1] > dn else (c1, None)
+    qc = A.linear(ops.view_rows(q_hm, N * H, dn), c1_q, convs[0].bias)         # [N*H, hid]: C1[:, :d_n] q + c1
     rows_q = g.head_rows(H)                                               # row (e, h) -> row src(e)*H + h
     drop = next((mod.p for mod in m.nn if isinstance(mod, torch.nn.Dropout)), 0.0)
     dropping = tr and drop > 0.0                                          # then the pair of `hidden` leaves with the dropout pass
     if m.use_edge:
         wk, bk = _head_major(m.proj_edge[0], de, H)
         k_hm = A.linear(edge, wk, bk, emit_pair=True)                     # [E, H*d_e]
-        hidden = A.linear(ops.view_rows(k_hm, E * H, de), c1[:, dn:], None, RELU, gather=(qc, rows_q, None, None), emit_pair=not dropping)
+        hidden = A.linear(ops.view_rows(k_hm, E * H, de), c1_k, None, RELU, gather=(qc, rows_q, None, None), emit_pair=not dropping)
     else:
         hidden = A.relu(A.gather_rows(qc, rows_q))                        # MLP [d_n, 2 d_n, d_o] on the query alone
     hidden = A.dropout(hidden, drop, tr, emit_pair=True)
@@ -260,9 +262,10 @@ def mmgnet_forward(m, obj_points, obj_2d_feats, edge_indices, descriptor, batch_
     if istrain:
         p0, p3 = m.triplet_projector_2d[0], m.triplet_projector_2d[3]
         src, dst = edge_indices[0].contiguous(), edge_indices[1].contiguous()
-        a = A.linear(g2, p0.weight[:, :512])
-        b = A.linear(g2, p0.weight[:, 512:1024])
-        hh = A.linear(ge2, p0.weight[:, 1024:], p0.bias, RELU, gather=(a, src, b, dst))      # Linear Dropout ReLU: commute
+        p0_src, p0_dst, p0_edge = A.split_cols(p0.weight, (512, 512, p0.weight.shape[1] - 1024))
+        a = A.linear(g2, p0_src)
+        b = A.linear(g2, p0_dst)
+        hh = A.linear(ge2, p0_edge, p0.bias, RELU, gather=(a, src, b, dst))                  # Linear Dropout ReLU: commute
         hh = A.dropout(hh, m.triplet_projector_2d[1].p, tr, emit_pair=True)
         dis = A.linear(hh, p3.weight, p3.bias)
     rel_cls_3d = rel_classifier(m.rel_predictor_3d, ge3)

@@ -152,3 +152,23 @@ def test_loader_hook_reproduces_the_reference_sampling_stream():
         assert np.array_equal(points[idx[i]], want[i])
     with pytest.raises(ValueError):
         data_prep.sample_object_indices(instances, [99], 64)
+
+
+def test_split_cols_is_slicing_with_one_backward():
+    """autograd.split_cols: the blocks are views of the weight (no copy), the gradient equals that of plain slicing, unused
+    blocks get zeros; without autograd it is a plain split."""
+    from vlsat_b200 import autograd as A
+    w = torch.randn(6, 10, requires_grad=True)
+    x0, x1, x2 = torch.randn(4, 3), torch.randn(4, 5), torch.randn(4, 2)
+    a, b, c = A.split_cols(w, (3, 5, 2))
+    assert a.data_ptr() == w.data_ptr() and b.data_ptr() == w[:, 3:].data_ptr() and tuple(c.shape) == (6, 2)
+    ((x0 @ a.t()).sum() * 2 + (x2 @ c.t()).pow(2).sum()).backward()          # block b unused
+    got = w.grad.clone()
+    w.grad = None
+    ((x0 @ w[:, :3].t()).sum() * 2 + (x2 @ w[:, 8:].t()).pow(2).sum()).backward()
+    assert torch.allclose(got, w.grad) and torch.count_nonzero(got[:, 3:8]) == 0
+    with torch.no_grad():
+        p, q = A.split_cols(w, (4, 6))
+        assert p.grad_fn is None and p.data_ptr() == w.data_ptr() and tuple(q.shape) == (6, 6)
+    with pytest.raises(ValueError):
+        A.split_cols(w, (4, 4))
