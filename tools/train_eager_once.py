@@ -1,9 +1,10 @@
-"""One eager training step (forward + backward of a fixed-cotangent scalar) at config #2 after two warm-up steps: the command
-to put under `ncu --metrics gpu__time_duration.sum` for a per-kernel launch list of the training path. Profiling aid."""
+"""One eager training step (TrainStep.forward_backward: train-mode forward, the reference's six loss terms, backward) at config #2
+after two warm-up steps: the command to put under `ncu --profile-from-start off --metrics gpu__time_duration.sum` for a
+per-kernel launch list of the training path as bench.py times it (zero arena, pair hand-offs). Profiling aid."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vlsat_b200 as V
-from vlsat_b200 import synth
+from vlsat_b200 import autograd as A, synth, train_glue as G
 import torch.cuda.profiler as prof
 
 dev = "cuda"
@@ -11,14 +12,20 @@ model = V.Mmgnet({"MODEL": V.DEFAULT_MODEL_CONFIG}, 160, 26)
 synth.load_seeded(model, 0)
 model = model.to(dev).train()
 b = synth.make_config_batch("cfg2", seed=1).to(dev)
-cot = None
+gen = torch.Generator().manual_seed(77)
+n, e = b.obj_points.shape[0], b.edge_indices.shape[1]
+text = torch.randn(e, 512, generator=gen)
+targets = (torch.randint(0, 160, (n,), generator=gen).to(dev), (torch.rand(e, 26, generator=gen) < 1.0 / 26).float().to(dev),
+           (text / text.norm(dim=-1, keepdim=True)).to(dev))
+A.DropoutState.manual_seed(1234)
+ts = G.TrainStep(model, G.build_optimizer(model, lr=1e-4, max_iteration=1000), graphed=False)
+
+
 def step():
-    global cot
     model.zero_grad(set_to_none=True)
-    outs = model(*b.forward_args(), istrain=True)
-    if cot is None:
-        cot = [torch.randn_like(o) / o.numel() for o in outs[:7]]
-    sum((o * c).sum() for o, c in zip(outs[:7], cot)).backward()
+    ts.forward_backward(*b.forward_args(), *targets)
+
+
 for _ in range(2):
     step()
 torch.cuda.synchronize()
