@@ -172,3 +172,25 @@ def test_split_cols_is_slicing_with_one_backward():
         assert p.grad_fn is None and p.data_ptr() == w.data_ptr() and tuple(q.shape) == (6, 6)
     with pytest.raises(ValueError):
         A.split_cols(w, (4, 4))
+
+
+def test_view_rows_and_zero_arena_host_logic():
+    """Host-side bookkeeping that needs no GPU: the (rows, head) view carries a remembered pair along as views of the same
+    memory; the zero arena is inert off the GPU (plain torch.zeros, no state left behind)."""
+    from vlsat_b200 import ops
+    x = torch.randn(6, 16)
+    hi, lo = torch.randn(6, 16).bfloat16(), torch.randn(6, 16).bfloat16()
+    x._vlsat_pair = (x._version, (hi, lo))
+    y = ops.view_rows(x, 12, 8)
+    assert y.data_ptr() == x.data_ptr() and tuple(y.shape) == (12, 8)
+    assert y._vlsat_pair[1][0].data_ptr() == hi.data_ptr() and tuple(y._vlsat_pair[1][1].shape) == (12, 8)
+    x.add_(1.0)                                                  # a stale pair (version moved on) must not travel
+    assert getattr(ops.view_rows(x, 12, 8), "_vlsat_pair", None) is None
+
+    class Owner:
+        pass
+    owner = Owner()
+    with ops.zero_arena(owner, "cpu") as arena:
+        assert arena is None and ops._arena is None
+        z = ops.zeros((3, 4), "cpu")
+    assert z.shape == (3, 4) and torch.count_nonzero(z) == 0 and not hasattr(owner, "_zero_arena_bytes")
